@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — image-pairs/sec of the newUNetTrans bitemporal forward (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload levir256|xbd1024]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+A "step" is one forward over one batch of synthetic image pairs (weights: torch.manual_seed(0) + define_G
+random init, exactly what the reference builds).  Workload = BASELINE.json configs[1]: LEVIR 256x256, 64 pairs
+per GPU per step, sharded by pair with no collective (weak scaling: every rank runs 64 pairs).
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "levir256": dict(H=256, W=256, pairs=64, nc=2, variant="levir",
+                     desc="newUNetTrans LEVIR-CD 256x256 batched inference, 64 pairs per GPU per step"),
+    "xbd1024": dict(H=1024, W=1024, pairs=8, nc=5, variant="xbd",
+                    desc="xBD 1024x1024 pre/post pair 5-class forward, 8 pairs per GPU per step"),
+}
+FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0)
+
+
+class Args:
+    net_G = "newUNetTrans"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                        bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"]))), "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc, self.path = None, f"/tmp/dahitra_clocks_{os.getpid()}.csv"
+        try:
+            uuid = str(torch.cuda.get_device_properties(device).uuid)
+            sel = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            self.cmd = ["nvidia-smi", "-i", sel, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"]
+        except Exception:
+            self.cmd = None
+
+    def start(self):
+        if self.cmd is None:
+            return
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(self.cmd, stdout=self.f, stderr=subprocess.DEVNULL)
+            time.sleep(0.25)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def cpu_port_pairs_per_sec(wl, pairs, steps, warmup):
+    """The oracle port of the reference forward on the host cores (all threads).  Checker/baseline only."""
+    from oracle import dahitra_oracle as O
+    from oracle import synth
+    from dahitra_b200.networks import define_G
+    from dahitra_b200.xbd import BASE_Transformer_UNet as XNet
+    torch.manual_seed(0)
+    if wl["variant"] == "levir":
+        sd = define_G(Args(), gpu_ids=[]).state_dict()
+    else:
+        sd = XNet(input_nc=3, output_nc=wl["nc"], token_len=4, resnet_stages_num=4, with_pos="learned",
+                  with_decoder_pos="learned", enc_depth=1, dec_depth=8).state_dict()
+    sd = {k: v.detach() for k, v in sd.items()}
+    x1, x2 = synth.synth_pair(pairs, wl["H"], wl["W"], seed=1, kind="uniform")
+    fn = (lambda: O.forward_levir(sd, x1, x2)) if wl["variant"] == "levir" else (lambda: O.forward_xbd(sd, torch.cat([x1, x2], 1)))
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(steps):
+        t = time.perf_counter(); fn(); ts.append(time.perf_counter() - t)
+    sec = sum(ts) / len(ts)
+    return pairs / sec, sec
+
+
+def run_reference(a, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    pairs = 4 if wl["variant"] == "levir" else 1
+    v, sec = cpu_port_pairs_per_sec(wl, pairs, a.steps, min(a.warmup, 3))
+    sample = f"{pairs} pairs per step of the {wl['pairs']}-pair workload, {a.steps} steps, torch CPU fp32, {torch.get_num_threads()} threads"
+    line = dict(impl="reference", metric="image-pairs/sec", value=v, unit="pairs/s", n_gpus=a.gpus, steps=a.steps,
+                warmup=a.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=wl["desc"], H=wl["H"], W=wl["W"], pairs_per_gpu=wl["pairs"], sample_pairs=pairs),
+                cpu_baseline=dict(value=v, unit="pairs/s", cores=torch.get_num_threads(), kind="port", sample=sample),
+                e2e=dict(value=v, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- native arm
+def run_native(a, wl):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the native arm has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from dahitra_b200.networks import define_G
+    from dahitra_b200.xbd import BASE_Transformer_UNet as XNet
+    from oracle import synth   # input generator only (synthetic data)
+
+    H, W, Bp = wl["H"], wl["W"], (a.pairs or wl["pairs"])
+    torch.manual_seed(0)
+    if wl["variant"] == "levir":
+        net = define_G(Args(), gpu_ids=[local]).eval()
+    else:
+        net = XNet(input_nc=3, output_nc=wl["nc"], token_len=4, resnet_stages_num=4, with_pos="learned",
+                   with_decoder_pos="learned", enc_depth=1, dec_depth=8).to(dev).eval()
+    if a.flags is not None:
+        net._engine.flags = a.flags
+    # rotating input sets so consecutive steps never re-read the same inputs from L2 (3 x 100 MB > 126 MB L2;
+    # the ~3.5 GB of per-step intermediates stream through HBM regardless)
+    nsets = 3
+    sets = []
+    for i in range(nsets):
+        x1, x2 = synth.synth_pair(Bp, H, W, seed=100 + 10 * rank + i, kind="uniform")
+        sets.append((x1.to(dev), x2.to(dev)))
+
+    def step(i):
+        x1, x2 = sets[i % nsets]
+        if wl["variant"] == "levir":
+            return net(x1, x2)
+        return net._engine.forward_pair(net, x1, x2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(a.warmup, 3)):
+            step(i)
+        barrier()
+        sampler = ClockSampler(dev) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(a.steps):
+            step(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # ---- e2e: host (pinned) inputs -> H2D -> forward -> argmax -> D2H of the class map, every step
+        hx = [(s[0].cpu().pin_memory(), s[1].cpu().pin_memory()) for s in sets]
+        pred_h = torch.empty((Bp, H, W), dtype=torch.int64).pin_memory()
+
+        def e2e_step(i):
+            h1, h2 = hx[i % nsets]
+            d1, d2 = h1.to(dev, non_blocking=True), h2.to(dev, non_blocking=True)
+            y = net(d1, d2) if wl["variant"] == "levir" else net._engine.forward_pair(net, d1, d2)
+            pred_h.copy_(torch.argmax(y, dim=1), non_blocking=True)   # what models/evaluator.py:89-103 moves to the host
+            torch.cuda.current_stream().synchronize()
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(a.steps):
+            e2e_step(i)
+        barrier()
+        e2e_sec = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        # ---- per-launch profile (after the timed regions): roofline of the dominant kernel
+        prof = None
+        if rank == 0:
+            runs = [net._engine.profile_pair(net, *sets[i % nsets]) for i in range(3)]
+            prof = [dict(name=r["name"], flops=r["flops"], bytes=r["bytes"],
+                         ms=statistics.mean(x[j]["ms"] for x in runs)) for j, r in enumerate(runs[0])]
+    tmax = torch.tensor([ms, e2e_sec * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(tmax[0]), float(tmax[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_src = load_peaks()
+    ms_step = ms / a.steps
+    value = world * Bp / (ms_step / 1e3)
+    e2e_value = world * Bp * a.steps / (e2e_ms / 1e3)
+    top = max(prof, key=lambda r: r["ms"])
+    ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    ai = top["flops"] / max(top["bytes"], 1.0)
+    if ai > ridge:
+        achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
+        roof = dict(kernel=top["name"], bound="tensor", achieved=achieved, peak=peaks["bf16_tflops_sustained"],
+                    unit="TFLOP/s", frac=achieved / peaks["bf16_tflops_sustained"])
+    else:
+        achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+        roof = dict(kernel=top["name"], bound="hbm", achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
+                    frac=achieved / peaks["hbm_gbs"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")      # per-launch DRAM bytes from the committed ncu capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top["name"])
+    roof.update(traffic=traffic, peak_source=f"MEASURED_PEAKS.json ({peak_src}; sustained bf16 for a kernel inside a step)",
+                ai_flop_per_byte=ai, launch_ms=top["ms"], share_of_step=top["ms"] / sum(r["ms"] for r in prof),
+                algorithmic_flops=top["flops"], algorithmic_bytes=top["bytes"],
+                whole_step=dict(algorithmic_gflop=sum(r["flops"] for r in prof) / 1e9,
+                                algorithmic_mb=sum(r["bytes"] for r in prof) / 1e6,
+                                profiled_ms=sum(r["ms"] for r in prof)))
+    kernels = sorted(prof, key=lambda r: -r["ms"])[:6]
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        cp = 4 if wl["variant"] == "levir" else 1
+        v, sec = cpu_port_pairs_per_sec(wl, cp, 3, 1)
+        cpu = dict(value=v, unit="pairs/s", cores=torch.get_num_threads(), kind="port",
+                   sample=f"oracle port (torch CPU fp32), {cp} pairs per call, mean of 3 calls after 1 warm-up ({sec:.2f} s/call)")
+    line = dict(metric="image-pairs/sec", value=value, unit="pairs/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
+                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=wl["desc"], H=H, W=W, pairs_per_gpu=Bp, global_pairs_per_step=world * Bp,
+                            sharding="by image pair, one process per GPU, no collective",
+                            weights="torch.manual_seed(0); define_G random init", flags=net._engine.flags,
+                            l2="3 rotating input sets (3x%.0f MB) + multi-GB per-step intermediates >> 126 MB L2" % (2 * Bp * 3 * H * W * 4 / 1e6)),
+                clocks=clocks,
+                e2e=dict(value=e2e_value, unit="pairs/s", h2d_bytes_per_step=2 * Bp * 3 * H * W * 4,
+                         d2h_bytes_per_step=Bp * H * W * 8, ms_per_step=e2e_ms / a.steps,
+                         api="net(x1.to(dev), x2.to(dev)); torch.argmax(.,1) -> pinned host int64 map; per-step sync"),
+                gpu_launches=len(prof) * a.steps, launches_per_step=len(prof),
+                roofline=roof, top_kernels=[dict(name=k["name"], ms=round(k["ms"], 4)) for k in kernels])
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="levir256", choices=list(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU per step (default: the workload's)")
+    ap.add_argument("--flags", type=int, default=None, help="DH_FLAG_* bitmask for the native engine")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    wl = WORKLOADS[a.workload]
+    if a.impl == "reference":
+        return run_reference(a, wl)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.gpus != world and world == 1 and a.gpus > 1:
+        # convenience: re-launch under torchrun when asked for N>1 without it
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_native(a, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,95 @@
+"""ctypes binding of the C-ABI kernel library (include/dahitra_b200.h) and its in-tree build.
+
+The shared object lives next to this file (``dahitra_b200/libdahitra_b200.so``) so it travels with the
+source tree; it is produced by ``build()`` (``nvcc -gencode arch=compute_100a,code=sm_100a``).
+There is no fallback: if the library is missing or fails to load, every native entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libdahitra_b200.so")
+SOURCES = ["conv_ffma.cu", "conv_tc.cu", "tokens.cu", "decoder.cu", "aux.cu", "forward.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _sources():
+    return [os.path.join(_CSRC, s) for s in SOURCES if os.path.exists(os.path.join(_CSRC, s))]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = _sources() + [os.path.join(_CSRC, "common.cuh"),
+                         os.path.join(_HERE, "..", "include", "dahitra_b200.h")]
+    deps += [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu under csrc/ into one shared object for sm_100a (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + _sources() + ["-o", LIB_PATH + ".tmp"]
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    return LIB_PATH
+
+
+# (name, restype, argtypes) — must match include/dahitra_b200.h exactly
+_P, _I, _LL, _SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t
+SIGNATURES = {
+    "dahitra_version": (_I, []),
+    "dahitra_error_string": (C.c_char_p, [_I]),
+    "dahitra_weight_slot_name": (C.c_char_p, [_I]),
+    "dahitra_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
+    "dahitra_forward": (_I, [_P, _I, _P, _P, _LL, _P, _P, _P, _SZ, _I, _I, _I, _I, _I, _I, _P]),
+    "dahitra_forward_profiled": (_I, [_P, _I, _P, _P, _LL, _P, _P, _P, _SZ, _I, _I, _I, _I, _I, _I, _P,
+                                      _I, _P, _P, _P, _P]),
+    "dahitra_conv2d": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P]),
+    "dahitra_stem": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P, _P]),
+    "dahitra_maxpool3x3s2": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "dahitra_squeeze_tokens": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "dahitra_token_encoder": (_I, [_P, _I, _I, _P, _I, _I, _P, _P]),
+    "dahitra_decoder_tables": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
+    "dahitra_pixel_decoder": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
+    "dahitra_classifier": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+}
+
+
+def load():
+    """Return the loaded library (ctypes.CDLL) or raise — never returns a stub."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"dahitra_b200: {LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(nvcc, sm_100a). There is no fallback path.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)          # AttributeError if the .so does not export it
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+        return _lib
+
+
+def check(rc: int, what: str = "dahitra"):
+    if rc != 0:
+        msg = load().dahitra_error_string(rc)
+        raise RuntimeError(f"{what} failed with code {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,63 @@
+// dahitra_b200 — shared device/host helpers (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/dahitra_b200.h"
+
+#ifndef __CUDA_ARCH_LIST__
+#endif
+
+#define DH_CHECK_LAUNCH()                                   \
+  do {                                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return (int)e__;                \
+  } while (0)
+
+#define DH_REQUIRE(cond, code) \
+  do {                         \
+    if (!(cond)) return (code);\
+  } while (0)
+
+static inline bool dh_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int dh_cdiv(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// exact-erf GELU (nn.GELU() default; reference models/help_funcs.py:57)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ---- internal launchers shared between the per-kernel C ABI and dahitra_forward ----------------
+struct ConvArgs {
+  const float* in0; const float* in1; int C0, C1;
+  int N, inH, inW, up;           // stored input size; `up`=2 => virtual nearest x2 upsample
+  int KH, KW, stride, pad, Cout;
+  const float* w; const float* bias; const float* res; int relu;
+  float* out;
+};
+int dh_launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
+int dh_launch_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* b, float* out, cudaStream_t s);
+int dh_launch_maxpool(const float* in, int N, int H, int W, int C, float* out, cudaStream_t s);
+int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* b,
+                         float* logits, unsigned char* amax, cudaStream_t s);
+int dh_launch_squeeze_tokens(const float* feat, int N, int npix, int Cin, const float* wsq, const float* wtok,
+                             float* xs, float* partials, cudaStream_t s);
+int dh_launch_token_encoder(const float* partials, int B, int nchunk, const float* enc, int heads, int add_pos,
+                            float* mem, cudaStream_t s);
+int dh_launch_decoder_tables(const float* mem, int B, int first_call, int ncalls, const float* dec, int heads, int depth,
+                             float* tables, cudaStream_t s);
+int dh_launch_pixel_decoder(const float* x, const float* pos, const float* tables, const float* dec,
+                            int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up, float* out,
+                            cudaStream_t s);

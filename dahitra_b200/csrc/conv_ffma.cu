@@ -1,0 +1,387 @@
+// dahitra_b200 — fp32 CUDA-core convolution kernels (NHWC): generic implicit-GEMM conv, 7x7 stem,
+// 3x3/s2 max-pool and the classifier head.  These are the strict-fp32 path and the fallback for the
+// shapes the tcgen05 kernel (conv_tc.cu) does not take (strided convs, Cin=3, tiny Cout).
+#include "common.cuh"
+
+// =====================================================================================================
+// Generic conv: out[n,oy,ox,co] = act( sum_{r,s,ci} in[n, oy*st+r-pad, ox*st+s-pad, ci] * w[(r*KW+s)*Cin+ci][co]
+//                                      + bias[co] + res[n,oy,ox,co] )
+// Implicit GEMM, CTA tile = 128 output pixels (8 rows x 16 cols) x TN output channels, K step = 32 input
+// channels of one filter tap.  Thread tile 8 pixels x 4 channels, smem A stored K-major (transposed) so
+// the 8 pixel operands are two LDS.128; register prefetch of the next K step overlaps the FFMA block.
+// `in` may be a virtual concat of two NHWC tensors and may be virtually nearest-upsampled x2.
+// =====================================================================================================
+namespace {
+
+constexpr int TILE_H = 8, TILE_W = 16, TILE_P = TILE_H * TILE_W;   // 128 pixels
+constexpr int KC = 32;                                              // channels per K step
+constexpr int AS_STRIDE = TILE_P + 4;
+
+template <int TN>
+__global__ void __launch_bounds__(4 * TN, (TN == 64) ? 2 : 4)
+conv_ffma_kernel(ConvArgs a, int OH, int OW, int tilesX) {
+  constexpr int NT = 4 * TN;            // threads: (TILE_P/8) * (TN/4)
+  constexpr int TXN = TN / 4;           // threads along Cout
+  constexpr int A_LD = (TILE_P * KC / 4) / NT;    // float4 A loads per thread (4 or 8)
+  constexpr int B_LD = (KC * TN / 4) / NT;        // float4 B loads per thread (2)
+  __shared__ __align__(16) float As[KC][AS_STRIDE];
+  __shared__ __align__(16) float Bs[KC][TN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const int n = blockIdx.z;
+  const int n0 = blockIdx.y * TN;
+  const int oy0 = (blockIdx.x / tilesX) * TILE_H, ox0 = (blockIdx.x % tilesX) * TILE_W;
+  const int Cin = a.C0 + a.C1;
+  const int ush = a.up == 2 ? 1 : 0;
+  const int H = a.inH << ush, W = a.inW << ush;
+
+  // loader roles: this thread always gathers the same output pixel
+  const int lpx = tid % TILE_P;
+  const int lc4_0 = tid / TILE_P;                 // 0 (NT=128) or 0..1 (NT=256)
+  constexpr int LC4_STEP = NT / TILE_P;           // 1 or 2
+  const int loy = oy0 + lpx / TILE_W, lox = ox0 + lpx % TILE_W;
+  const bool lvalid_px = (loy < OH) && (lox < OW);
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int cchunks = Cin / KC;
+  const int nsteps = a.KH * a.KW * cchunks;
+  float4 ra[A_LD], rb[B_LD];
+
+  auto gload = [&](int step) {
+    const int tap = step / cchunks, cc = (step - tap * cchunks) * KC;
+    const int r = tap / a.KW, s = tap - r * a.KW;
+    const int iy = loy * a.stride + r - a.pad, ix = lox * a.stride + s - a.pad;
+    const bool ok = lvalid_px && iy >= 0 && iy < H && ix >= 0 && ix < W;
+    const float* src;
+    int cs, cb;
+    if (cc < a.C0) { src = a.in0; cs = a.C0; cb = cc; } else { src = a.in1; cs = a.C1; cb = cc - a.C0; }
+    const float* p = src + ((size_t)(n * a.inH + (iy >> ush)) * a.inW + (ix >> ush)) * cs + cb;
+#pragma unroll
+    for (int j = 0; j < A_LD; ++j) {
+      const int c4 = lc4_0 + j * LC4_STEP;
+      ra[j] = ok ? ldg4(p + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* wp = a.w + (size_t)(tap * Cin + cc) * a.Cout + n0;
+#pragma unroll
+    for (int j = 0; j < B_LD; ++j) {
+      const int idx = j * NT + tid;
+      const int row = idx / TXN, col4 = idx % TXN;
+      rb[j] = ldg4(wp + (size_t)row * a.Cout + col4 * 4);
+    }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int j = 0; j < A_LD; ++j) {
+      const int c4 = lc4_0 + j * LC4_STEP;
+      As[c4 * 4 + 0][lpx] = ra[j].x;
+      As[c4 * 4 + 1][lpx] = ra[j].y;
+      As[c4 * 4 + 2][lpx] = ra[j].z;
+      As[c4 * 4 + 3][lpx] = ra[j].w;
+    }
+#pragma unroll
+    for (int j = 0; j < B_LD; ++j) {
+      const int idx = j * NT + tid;
+      const int row = idx / TXN, col4 = idx % TXN;
+      *reinterpret_cast<float4*>(&Bs[row][col4 * 4]) = rb[j];
+    }
+  };
+
+  gload(0);
+  sstore();
+  __syncthreads();
+  for (int step = 0; step < nsteps; ++step) {
+    if (step + 1 < nsteps) gload(step + 1);
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kc][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kc][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kc][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+    if (step + 1 < nsteps) {
+      sstore();
+      __syncthreads();
+    }
+  }
+
+  // epilogue: bias, residual, ReLU, NHWC store
+  const int co = n0 + tx * 4;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.bias) bv = ldg4(a.bias + co);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int p = ty * 8 + i;
+    const int oy = oy0 + p / TILE_W, ox = ox0 + p % TILE_W;
+    if (oy < OH && ox < OW) {
+      const size_t o = ((size_t)(n * OH + oy) * OW + ox) * a.Cout + co;
+      float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+      if (a.res) {
+        const float4 rv = ldg4(a.res + o);
+        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+      }
+      if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      st4(a.out + o, v);
+    }
+  }
+}
+
+}  // namespace
+
+int dh_launch_conv_ffma(const ConvArgs& a, cudaStream_t s) {
+  DH_REQUIRE(a.in0 && a.w && a.out, DH_E_NULL);
+  DH_REQUIRE(a.C1 == 0 || a.in1, DH_E_NULL);
+  DH_REQUIRE(a.C0 > 0 && a.C0 % 32 == 0 && a.C1 % 32 == 0 && a.Cout % 32 == 0, DH_E_SHAPE);
+  DH_REQUIRE(a.N > 0 && a.inH > 0 && a.inW > 0 && (a.up == 1 || a.up == 2) && a.stride >= 1, DH_E_SHAPE);
+  DH_REQUIRE(dh_aligned16(a.in0) && dh_aligned16(a.in1) && dh_aligned16(a.w) && dh_aligned16(a.out) &&
+             dh_aligned16(a.bias) && dh_aligned16(a.res), DH_E_ALIGN);
+  const int H = a.inH * a.up, W = a.inW * a.up;
+  const int OH = (H + 2 * a.pad - a.KH) / a.stride + 1, OW = (W + 2 * a.pad - a.KW) / a.stride + 1;
+  DH_REQUIRE(OH > 0 && OW > 0, DH_E_SHAPE);
+  const int tx = dh_cdiv(OW, TILE_W), ty = dh_cdiv(OH, TILE_H);
+  if (a.Cout % 64 == 0) {
+    dim3 grid(tx * ty, a.Cout / 64, a.N);
+    conv_ffma_kernel<64><<<grid, 256, 0, s>>>(a, OH, OW, tx);
+  } else {
+    dim3 grid(tx * ty, a.Cout / 32, a.N);
+    conv_ffma_kernel<32><<<grid, 128, 0, s>>>(a, OH, OW, tx);
+  }
+  DH_CHECK_LAUNCH();
+  return 0;
+}
+
+// =====================================================================================================
+// Stem: 7x7 stride 2 pad 3, 3 -> 64 channels, BN folded, ReLU.  NCHW planes in, NHWC out.
+// CTA = 16x16 output pixels x 64 channels; the 37x37x3 input halo and the whole 147x64 filter live in
+// shared memory.  Thread tile: 4 pixels (along x) x 16 channels.
+// =====================================================================================================
+namespace {
+constexpr int ST_T = 16, ST_IN = 2 * ST_T + 5, ST_INP = 40;   // halo 37, padded row stride 40
+constexpr int ST_SMEM_FLOATS = 147 * 64 + 3 * ST_IN * ST_INP;
+
+__global__ void __launch_bounds__(256, 2)
+stem_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH, int OW, int tilesX,
+            const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  float* w_s = sm;                   // [147][64]
+  float* in_s = sm + 147 * 64;       // [3][37][40]
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z;
+  const int oy0 = (blockIdx.x / tilesX) * ST_T, ox0 = (blockIdx.x % tilesX) * ST_T;
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+
+  for (int i = tid; i < 147 * 64 / 4; i += 256)
+    reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  const float* xn = x + (size_t)n * xbs;
+  for (int i = tid; i < 3 * ST_IN * ST_IN; i += 256) {
+    const int ci = i / (ST_IN * ST_IN), rem = i - ci * ST_IN * ST_IN;
+    const int yy = rem / ST_IN, xx = rem - yy * ST_IN;
+    const int iy = iy0 + yy, ix = ix0 + xx;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xn + ((size_t)ci * H + iy) * W + ix);
+    in_s[(ci * ST_IN + yy) * ST_INP + xx] = v;
+  }
+  __syncthreads();
+
+  const int cg = tid & 3, pg = tid >> 2;
+  const int row = pg >> 2, xg = pg & 3;
+  float acc[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+
+  for (int r = 0; r < 7; ++r) {
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* ip = in_s + (ci * ST_IN + 2 * row + r) * ST_INP + 8 * xg + s;
+        const float av[4] = {ip[0], ip[2], ip[4], ip[6]};
+        const float* wp = w_s + ((r * 7 + s) * 3 + ci) * 64 + cg * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b = *reinterpret_cast<const float4*>(wp + q * 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i][q * 4 + 0] = fmaf(av[i], b.x, acc[i][q * 4 + 0]);
+            acc[i][q * 4 + 1] = fmaf(av[i], b.y, acc[i][q * 4 + 1]);
+            acc[i][q * 4 + 2] = fmaf(av[i], b.z, acc[i][q * 4 + 2]);
+            acc[i][q * 4 + 3] = fmaf(av[i], b.w, acc[i][q * 4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  const int oy = oy0 + row;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ox = ox0 + xg * 4 + i;
+    if (oy < OH && ox < OW) {
+      float* op = out + ((size_t)(n * OH + oy) * OW + ox) * 64 + cg * 16;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 bv = ldg4(bias + cg * 16 + q * 4);
+        float4 v = make_float4(fmaxf(acc[i][q * 4 + 0] + bv.x, 0.f), fmaxf(acc[i][q * 4 + 1] + bv.y, 0.f),
+                               fmaxf(acc[i][q * 4 + 2] + bv.z, 0.f), fmaxf(acc[i][q * 4 + 3] + bv.w, 0.f));
+        st4(op + q * 4, v);
+      }
+    }
+  }
+}
+}  // namespace
+
+int dh_launch_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* b, float* out,
+                   cudaStream_t s) {
+  DH_REQUIRE(x && w && b && out, DH_E_NULL);
+  DH_REQUIRE(N > 0 && H >= 8 && W >= 8 && H % 2 == 0 && W % 2 == 0, DH_E_SHAPE);
+  DH_REQUIRE(dh_aligned16(w) && dh_aligned16(b) && dh_aligned16(out), DH_E_ALIGN);
+  const int OH = H / 2, OW = W / 2;
+  const int tx = dh_cdiv(OW, ST_T), ty = dh_cdiv(OH, ST_T);
+  const int smem = ST_SMEM_FLOATS * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(tx * ty, 1, N);
+  stem_kernel<<<grid, 256, smem, s>>>(x, xbs, H, W, OH, OW, tx, w, b, out);
+  DH_CHECK_LAUNCH();
+  return 0;
+}
+
+// =====================================================================================================
+// MaxPool2d(kernel 3, stride 2, pad 1), NHWC, one thread per (pixel, 4 channels).
+// =====================================================================================================
+namespace {
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const float* __restrict__ in, int H, int W, int C4, int OH, int OW, size_t total, float* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  size_t t = idx / C4;
+  const int ox = (int)(t % OW); t /= OW;
+  const int oy = (int)(t % OH);
+  const int n = (int)(t / OH);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = oy * 2 + r - 1;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int ix = ox * 2 + s - 1;
+      if (ix < 0 || ix >= W) continue;
+      const float4 v = ldg4(in + (((size_t)n * H + iy) * W + ix) * (C4 * 4) + c4 * 4);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  st4(out + idx * 4, m);
+}
+}  // namespace
+
+int dh_launch_maxpool(const float* in, int N, int H, int W, int C, float* out, cudaStream_t s) {
+  DH_REQUIRE(in && out, DH_E_NULL);
+  DH_REQUIRE(N > 0 && H > 0 && W > 0 && C % 4 == 0, DH_E_SHAPE);
+  DH_REQUIRE(dh_aligned16(in) && dh_aligned16(out), DH_E_ALIGN);
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)N * OH * OW * (C / 4);
+  maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, H, W, C / 4, OH, OW, total, out);
+  DH_CHECK_LAUNCH();
+  return 0;
+}
+
+// =====================================================================================================
+// Classifier: 3x3 pad 1 conv 32 -> NC (NC <= 8) + bias.  NHWC in, NCHW logits out (+ optional uint8
+// argmax map, ties -> lowest class index like torch.argmax).  CTA = 16x16 pixels, 18x18x32 halo in smem
+// with the pixel stride padded to 36 floats so 128-bit reads of neighbouring pixels do not conflict.
+// =====================================================================================================
+namespace {
+constexpr int CL_T = 16, CL_HALO = CL_T + 2, CL_PS = 36;
+
+template <int NC>
+__global__ void __launch_bounds__(256)
+classifier_kernel(const float* __restrict__ in, int H, int W, int tilesX, const float* __restrict__ w,
+                  const float* __restrict__ bias, float* __restrict__ logits, unsigned char* __restrict__ amax) {
+  extern __shared__ __align__(16) float cl_sm[];
+  float* halo = cl_sm;                                   // [18*18][36]
+  float* w_s = cl_sm + CL_HALO * CL_HALO * CL_PS;        // [9][NC][32]
+  const int tid = threadIdx.x, n = blockIdx.z;
+  const int y0 = (blockIdx.x / tilesX) * CL_T, x0 = (blockIdx.x % tilesX) * CL_T;
+  for (int i = tid; i < 9 * NC * 8; i += 256) reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  for (int i = tid; i < CL_HALO * CL_HALO * 8; i += 256) {
+    const int c4 = i & 7, p = i >> 3;
+    const int yy = p / CL_HALO, xx = p - yy * CL_HALO;
+    const int iy = y0 + yy - 1, ix = x0 + xx - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = ldg4(in + (((size_t)n * H + iy) * W + ix) * 32 + c4 * 4);
+    *reinterpret_cast<float4*>(&halo[p * CL_PS + c4 * 4]) = v;
+  }
+  __syncthreads();
+  const int ly = tid / CL_T, lx = tid % CL_T;
+  float acc[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) acc[k] = __ldg(bias + k);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int r = tap / 3, s = tap % 3;
+    const float* hp = &halo[((ly + r) * CL_HALO + lx + s) * CL_PS];
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 v = *reinterpret_cast<const float4*>(hp + c4 * 4);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const float4 ww = *reinterpret_cast<const float4*>(&w_s[(tap * NC + k) * 32 + c4 * 4]);
+        acc[k] = fmaf(v.x, ww.x, acc[k]);
+        acc[k] = fmaf(v.y, ww.y, acc[k]);
+        acc[k] = fmaf(v.z, ww.z, acc[k]);
+        acc[k] = fmaf(v.w, ww.w, acc[k]);
+      }
+    }
+  }
+  const int y = y0 + ly, x = x0 + lx;
+  if (y < H && x < W) {
+    int best = 0;
+    float bv = acc[0];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      logits[(((size_t)n * NC + k) * H + y) * W + x] = acc[k];
+      if (k > 0 && acc[k] > bv) { bv = acc[k]; best = k; }
+    }
+    if (amax) amax[((size_t)n * H + y) * W + x] = (unsigned char)best;
+  }
+}
+}  // namespace
+
+int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* b,
+                         float* logits, unsigned char* amax, cudaStream_t s) {
+  DH_REQUIRE(in && w && b && logits, DH_E_NULL);
+  DH_REQUIRE(N > 0 && H > 0 && W > 0 && nc >= 1 && nc <= 8, DH_E_SHAPE);
+  DH_REQUIRE(dh_aligned16(in) && dh_aligned16(w), DH_E_ALIGN);
+  const int tx = dh_cdiv(W, CL_T), ty = dh_cdiv(H, CL_T);
+  dim3 grid(tx * ty, 1, N);
+#define DH_CLS_CASE(NC)                                                                                   \
+  case NC: {                                                                                              \
+    const int smem = (CL_HALO * CL_HALO * CL_PS + 9 * NC * 32) * (int)sizeof(float);                      \
+    cudaError_t e = cudaFuncSetAttribute(classifier_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    if (e != cudaSuccess) return (int)e;                                                                  \
+    classifier_kernel<NC><<<grid, 256, smem, s>>>(in, H, W, tx, w, b, logits, amax);                      \
+  } break;
+  switch (nc) {
+    DH_CLS_CASE(1) DH_CLS_CASE(2) DH_CLS_CASE(3) DH_CLS_CASE(4)
+    DH_CLS_CASE(5) DH_CLS_CASE(6) DH_CLS_CASE(7) DH_CLS_CASE(8)
+  }
+#undef DH_CLS_CASE
+  DH_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,351 @@
+// dahitra_b200 — C ABI + whole-network orchestration (launch sequence of the bitemporal forward).
+#include "common.cuh"
+#include <string.h>
+
+// ----------------------------------------------------------------------------------------------------
+// workspace plan
+// ----------------------------------------------------------------------------------------------------
+namespace {
+
+struct Level {           // per transformer level (5, 4, 3)
+  int cin, heads, depth, h, w;
+  size_t xs, xd, dx, out, part, mem, tab;    // float offsets into the workspace
+  int nchunk;
+};
+
+struct Plan {
+  int B, H, W, nc, variant;
+  size_t f2, p2, t4a, t4b, f4, t8a, t8b, t8c, f8, p8, t16a, t16b, t16c, f16;
+  Level lv[3];
+  size_t c4, c3, y20, o2, c2;
+  size_t total_floats;
+};
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t nfloats) {
+    const size_t o = off;
+    off += (nfloats + 63) & ~(size_t)63;   // 256-byte granules
+    return o;
+  }
+};
+
+bool make_plan(Plan& p, int variant, int B, int H, int W, int nc) {
+  if (B < 1 || H < 32 || W < 32 || (H % 32) || (W % 32) || nc < 1 || nc > 8) return false;
+  if (variant != DH_VARIANT_LEVIR && variant != DH_VARIANT_XBD) return false;
+  p.B = B; p.H = H; p.W = W; p.nc = nc; p.variant = variant;
+  const size_t N2 = 2 * (size_t)B;
+  const size_t s2 = (size_t)(H / 2) * (W / 2), s4 = s2 / 4, s8 = s4 / 4, s16 = s8 / 4;
+  Bump b;
+  p.f2 = b.take(N2 * s2 * 64);
+  p.p2 = b.take(N2 * s4 * 64);
+  p.t4a = b.take(N2 * s4 * 64); p.t4b = b.take(N2 * s4 * 64); p.f4 = b.take(N2 * s4 * 64);
+  p.t8a = b.take(N2 * s8 * 128); p.t8b = b.take(N2 * s8 * 128); p.t8c = b.take(N2 * s8 * 128); p.f8 = b.take(N2 * s8 * 128);
+  p.p8 = b.take(N2 * s16 * 128);
+  p.t16a = b.take(N2 * s16 * 256); p.t16b = b.take(N2 * s16 * 256); p.t16c = b.take(N2 * s16 * 256); p.f16 = b.take(N2 * s16 * 256);
+  const int cins[3] = {256, 128, 64}, heads[3] = {4, 4, 8}, depths[3] = {4, 4, 8}, div[3] = {16, 8, 4};
+  for (int i = 0; i < 3; ++i) {
+    Level& L = p.lv[i];
+    L.cin = cins[i]; L.heads = heads[i]; L.depth = depths[i]; L.h = H / div[i]; L.w = W / div[i];
+    const size_t n = (size_t)L.h * L.w;
+    L.nchunk = (int)((n + 127) / 128);
+    L.xs = b.take(N2 * n * 32);
+    L.xd = b.take(N2 * n * 32);
+    L.dx = b.take((size_t)B * n * 32);
+    L.out = b.take((size_t)B * n * 32);
+    L.part = b.take(N2 * L.nchunk * 4 * 34);
+    L.mem = b.take((size_t)B * 3 * 128);
+    L.tab = b.take((size_t)3 * B * L.depth * DH_TAB_FLOATS(L.heads));
+  }
+  p.c4 = b.take((size_t)B * s4 * 32);
+  p.c3 = b.take((size_t)B * s2 * 32);
+  p.y20 = b.take((size_t)B * s2 * 128);
+  p.o2 = b.take((size_t)B * s2 * 32);
+  p.c2 = b.take((size_t)B * H * W * 32);
+  p.total_floats = b.off;
+  return true;
+}
+
+const char* kSlotNames[DH_W_COUNT] = {
+  "DH_W_STEM_W", "DH_W_STEM_B",
+  "DH_W_L1_0_C1_W", "DH_W_L1_0_C1_B", "DH_W_L1_0_C2_W", "DH_W_L1_0_C2_B",
+  "DH_W_L1_1_C1_W", "DH_W_L1_1_C1_B", "DH_W_L1_1_C2_W", "DH_W_L1_1_C2_B",
+  "DH_W_L2_0_C1_W", "DH_W_L2_0_C1_B", "DH_W_L2_0_C2_W", "DH_W_L2_0_C2_B", "DH_W_L2_0_DS_W", "DH_W_L2_0_DS_B",
+  "DH_W_L2_1_C1_W", "DH_W_L2_1_C1_B", "DH_W_L2_1_C2_W", "DH_W_L2_1_C2_B",
+  "DH_W_L3_0_C1_W", "DH_W_L3_0_C1_B", "DH_W_L3_0_C2_W", "DH_W_L3_0_C2_B", "DH_W_L3_0_DS_W", "DH_W_L3_0_DS_B",
+  "DH_W_L3_1_C1_W", "DH_W_L3_1_C1_B", "DH_W_L3_1_C2_W", "DH_W_L3_1_C2_B",
+  "DH_W_LV5_SQ", "DH_W_LV5_TOK", "DH_W_LV5_ENC", "DH_W_LV5_DEC", "DH_W_LV5_POS", "DH_W_LV5_DECODE",
+  "DH_W_LV4_SQ", "DH_W_LV4_TOK", "DH_W_LV4_ENC", "DH_W_LV4_DEC", "DH_W_LV4_POS", "DH_W_LV4_DECODE",
+  "DH_W_LV3_SQ", "DH_W_LV3_TOK", "DH_W_LV3_ENC", "DH_W_LV3_DEC", "DH_W_LV3_POS", "DH_W_LV3_DECODE",
+  "DH_W_CL4_W", "DH_W_CL4_B", "DH_W_CL3_W", "DH_W_CL3_B", "DH_W_CL2_W", "DH_W_CL2_B",
+  "DH_W_CL20A_W", "DH_W_CL20A_B", "DH_W_CL20B_W", "DH_W_CL20B_B", "DH_W_CLS_W", "DH_W_CLS_B"};
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------
+// C ABI — utilities
+// ----------------------------------------------------------------------------------------------------
+extern "C" int dahitra_version(void) { return DAHITRA_ABI_VERSION; }
+
+extern "C" const char* dahitra_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case DH_E_NULL: return "dahitra: required pointer is NULL";
+    case DH_E_SHAPE: return "dahitra: unsupported shape";
+    case DH_E_ALIGN: return "dahitra: pointer not 16-byte aligned";
+    case DH_E_WORKSPACE: return "dahitra: workspace too small";
+    case DH_E_VARIANT: return "dahitra: unknown variant or flags";
+    case DH_E_WEIGHTS: return "dahitra: malformed weight table";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "dahitra: unknown error";
+  }
+}
+
+extern "C" const char* dahitra_weight_slot_name(int slot) {
+  return (slot >= 0 && slot < DH_W_COUNT) ? kSlotNames[slot] : nullptr;
+}
+
+extern "C" size_t dahitra_workspace_bytes(int variant, int B, int H, int W, int output_nc, int flags) {
+  (void)flags;
+  Plan p;
+  if (!make_plan(p, variant, B, H, W, output_nc)) return 0;
+  return p.total_floats * sizeof(float);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// C ABI — per-kernel entry points
+// ----------------------------------------------------------------------------------------------------
+static int conv_dispatch(const ConvArgs& a, int flags, cudaStream_t s) {
+  (void)flags;   // DH_FLAG_CONV_TC routing is added with conv_tc.cu
+  return dh_launch_conv_ffma(a, s);
+}
+
+extern "C" int dahitra_conv2d(const float* in0, const float* in1, int C0, int C1, int N, int inH, int inW, int up,
+                              int KH, int KW, int stride, int pad, int Cout, const float* w, const float* bias,
+                              const float* res, int relu, float* out, int flags, void* stream) {
+  ConvArgs a{in0, in1, C0, C1, N, inH, inW, up, KH, KW, stride, pad, Cout, w, bias, res, relu, out};
+  return conv_dispatch(a, flags, (cudaStream_t)stream);
+}
+extern "C" int dahitra_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* bias,
+                            float* out, void* stream) {
+  return dh_launch_stem(x, xbs, N, H, W, w, bias, out, (cudaStream_t)stream);
+}
+extern "C" int dahitra_maxpool3x3s2(const float* in, int N, int H, int W, int C, float* out, void* stream) {
+  return dh_launch_maxpool(in, N, H, W, C, out, (cudaStream_t)stream);
+}
+extern "C" int dahitra_squeeze_tokens(const float* feat, int N, int npix, int Cin, const float* w_sq, const float* w_tok,
+                                      float* xs, float* partials, void* stream) {
+  return dh_launch_squeeze_tokens(feat, N, npix, Cin, w_sq, w_tok, xs, partials, (cudaStream_t)stream);
+}
+extern "C" int dahitra_token_encoder(const float* partials, int B, int nchunk, const float* enc_pack, int heads,
+                                     int add_pos, float* mem, void* stream) {
+  return dh_launch_token_encoder(partials, B, nchunk, enc_pack, heads, add_pos, mem, (cudaStream_t)stream);
+}
+extern "C" int dahitra_decoder_tables(const float* mem, int B, int first_call, int ncalls, const float* dec_pack,
+                                      int heads, int depth, float* tables, void* stream) {
+  return dh_launch_decoder_tables(mem, B, first_call, ncalls, dec_pack, heads, depth, tables, (cudaStream_t)stream);
+}
+extern "C" int dahitra_pixel_decoder(const float* x, const float* pos, const float* tables, const float* dec_pack,
+                                     int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up,
+                                     float* out, void* stream) {
+  return dh_launch_pixel_decoder(x, pos, tables, dec_pack, nimg, h, w, heads, depth, skip, skip_up, out,
+                                 (cudaStream_t)stream);
+}
+extern "C" int dahitra_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* bias,
+                                  float* logits, unsigned char* argmax_u8, void* stream) {
+  return dh_launch_classifier(in, N, H, W, nc, w, bias, logits, argmax_u8, (cudaStream_t)stream);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// per-launch profiler (diagnostic; used by bench.py for the roofline of the dominant kernel)
+// ----------------------------------------------------------------------------------------------------
+namespace {
+constexpr int PROF_MAX = 160;
+struct ProfRec { const char* name; double flops, bytes; };
+struct Profiler {
+  bool on = false, created = false;
+  int n = 0;
+  cudaEvent_t ev[PROF_MAX + 1];
+  ProfRec rec[PROF_MAX];
+};
+thread_local Profiler g_prof;
+
+inline void prof_mark(cudaStream_t s, const char* name, double flops, double bytes) {
+  if (!g_prof.on || g_prof.n >= PROF_MAX) return;
+  g_prof.rec[g_prof.n] = {name, flops, bytes};
+  ++g_prof.n;
+  cudaEventRecord(g_prof.ev[g_prof.n], s);
+}
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------
+// whole forward
+// ----------------------------------------------------------------------------------------------------
+#define DH_STEP(name, fl, by, expr)        \
+  do {                                     \
+    const int rc__ = (expr);               \
+    if (rc__ != 0) return rc__;            \
+    prof_mark(s, name, (fl), (by));        \
+  } while (0)
+
+extern "C" int dahitra_forward(const void* const* weights, int n_weights, const float* x1, const float* x2,
+                               long long x_batch_stride, float* logits, unsigned char* argmax_u8, void* workspace,
+                               size_t workspace_bytes, int variant, int B, int H, int W, int output_nc, int flags,
+                               void* stream) {
+  DH_REQUIRE(weights && x1 && x2 && logits && workspace, DH_E_NULL);
+  DH_REQUIRE(n_weights == DH_W_COUNT, DH_E_WEIGHTS);
+  Plan p;
+  DH_REQUIRE(variant == DH_VARIANT_LEVIR || variant == DH_VARIANT_XBD, DH_E_VARIANT);
+  DH_REQUIRE(make_plan(p, variant, B, H, W, output_nc), DH_E_SHAPE);
+  DH_REQUIRE(workspace_bytes >= p.total_floats * sizeof(float), DH_E_WORKSPACE);
+  DH_REQUIRE(dh_aligned16(workspace), DH_E_ALIGN);
+  for (int i = 0; i < DH_W_COUNT; ++i) {
+    const bool optional = (i == DH_W_LV5_POS || i == DH_W_LV4_POS || i == DH_W_LV3_POS);
+    DH_REQUIRE(weights[i] || optional, DH_E_WEIGHTS);
+    DH_REQUIRE(dh_aligned16(weights[i]), DH_E_ALIGN);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  auto Wt = [&](int slot) { return (const float*)weights[slot]; };
+  const int N2 = 2 * B;
+  const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8, h16 = H / 16, w16 = W / 16;
+
+  // conv launch + its algorithmic cost (2*MACs as written; one read of the stored inputs/weights, one write)
+  auto conv = [&](const char* name, const float* in0, const float* in1, int C0, int C1, int N, int inH, int inW, int up,
+                  int K, int stride, int Cout, int wslot, int bslot, const float* res, int relu, float* out) -> int {
+    ConvArgs a{in0, in1, C0, C1, N, inH, inW, up, K, K, stride, K / 2, Cout, Wt(wslot), bslot >= 0 ? Wt(bslot) : nullptr,
+               res, relu, out};
+    const int rc = conv_dispatch(a, flags, s);
+    if (rc != 0) return rc;
+    const double OH = (double)(inH * up) / stride, OW = (double)(inW * up) / stride, Cin = C0 + C1;
+    const double fl = 2.0 * N * OH * OW * Cout * K * K * Cin;
+    const double by = 4.0 * ((double)N * inH * inW * Cin + (double)N * OH * OW * Cout * (res ? 2 : 1) + (double)K * K * Cin * Cout);
+    prof_mark(s, name, fl, by);
+    return 0;
+  };
+#define DH_CONV(...)                     \
+  do {                                   \
+    const int rc__ = conv(__VA_ARGS__);  \
+    if (rc__ != 0) return rc__;          \
+  } while (0)
+
+  // ---- Siamese trunk on 2B images: [pre batch | post batch]  (reference networks.py:1118-1138, 1323-1324)
+  float* F2 = ws + p.f2;
+  const double stem_fl = 2.0 * B * h2 * w2 * 64 * 147, stem_by = 4.0 * B * ((double)3 * H * W + (double)h2 * w2 * 64);
+  DH_STEP("stem_pre", stem_fl, stem_by, dh_launch_stem(x1, x_batch_stride, B, H, W, Wt(DH_W_STEM_W), Wt(DH_W_STEM_B), F2, s));
+  DH_STEP("stem_post", stem_fl, stem_by,
+          dh_launch_stem(x2, x_batch_stride, B, H, W, Wt(DH_W_STEM_W), Wt(DH_W_STEM_B), F2 + (size_t)B * h2 * w2 * 64, s));
+  float* P2 = ws + p.p2;
+  DH_STEP("maxpool_2", 0.0, 4.0 * N2 * 64 * ((double)h2 * w2 + (double)h4 * w4), dh_launch_maxpool(F2, N2, h2, w2, 64, P2, s));
+  float *T4a = ws + p.t4a, *T4b = ws + p.t4b, *F4 = ws + p.f4;
+  DH_CONV("layer1.0.conv1", P2, nullptr, 64, 0, N2, h4, w4, 1, 3, 1, 64, DH_W_L1_0_C1_W, DH_W_L1_0_C1_B, nullptr, 1, T4a);
+  DH_CONV("layer1.0.conv2", T4a, nullptr, 64, 0, N2, h4, w4, 1, 3, 1, 64, DH_W_L1_0_C2_W, DH_W_L1_0_C2_B, P2, 1, T4b);
+  DH_CONV("layer1.1.conv1", T4b, nullptr, 64, 0, N2, h4, w4, 1, 3, 1, 64, DH_W_L1_1_C1_W, DH_W_L1_1_C1_B, nullptr, 1, T4a);
+  DH_CONV("layer1.1.conv2", T4a, nullptr, 64, 0, N2, h4, w4, 1, 3, 1, 64, DH_W_L1_1_C2_W, DH_W_L1_1_C2_B, T4b, 1, F4);
+  float *T8a = ws + p.t8a, *T8b = ws + p.t8b, *T8c = ws + p.t8c, *F8 = ws + p.f8;
+  DH_CONV("layer2.0.conv1", F4, nullptr, 64, 0, N2, h4, w4, 1, 3, 2, 128, DH_W_L2_0_C1_W, DH_W_L2_0_C1_B, nullptr, 1, T8a);
+  DH_CONV("layer2.0.down", F4, nullptr, 64, 0, N2, h4, w4, 1, 1, 2, 128, DH_W_L2_0_DS_W, DH_W_L2_0_DS_B, nullptr, 0, T8b);
+  DH_CONV("layer2.0.conv2", T8a, nullptr, 128, 0, N2, h8, w8, 1, 3, 1, 128, DH_W_L2_0_C2_W, DH_W_L2_0_C2_B, T8b, 1, T8c);
+  DH_CONV("layer2.1.conv1", T8c, nullptr, 128, 0, N2, h8, w8, 1, 3, 1, 128, DH_W_L2_1_C1_W, DH_W_L2_1_C1_B, nullptr, 1, T8a);
+  DH_CONV("layer2.1.conv2", T8a, nullptr, 128, 0, N2, h8, w8, 1, 3, 1, 128, DH_W_L2_1_C2_W, DH_W_L2_1_C2_B, T8c, 1, F8);
+  float* P8 = ws + p.p8;
+  DH_STEP("maxpool_8", 0.0, 4.0 * N2 * 128 * ((double)h8 * w8 + (double)h16 * w16), dh_launch_maxpool(F8, N2, h8, w8, 128, P8, s));
+  float *T16a = ws + p.t16a, *T16b = ws + p.t16b, *T16c = ws + p.t16c, *F16 = ws + p.f16;
+  DH_CONV("layer3.0.conv1", P8, nullptr, 128, 0, N2, h16, w16, 1, 3, 1, 256, DH_W_L3_0_C1_W, DH_W_L3_0_C1_B, nullptr, 1, T16a);
+  DH_CONV("layer3.0.down", P8, nullptr, 128, 0, N2, h16, w16, 1, 1, 1, 256, DH_W_L3_0_DS_W, DH_W_L3_0_DS_B, nullptr, 0, T16b);
+  DH_CONV("layer3.0.conv2", T16a, nullptr, 256, 0, N2, h16, w16, 1, 3, 1, 256, DH_W_L3_0_C2_W, DH_W_L3_0_C2_B, T16b, 1, T16c);
+  DH_CONV("layer3.1.conv1", T16c, nullptr, 256, 0, N2, h16, w16, 1, 3, 1, 256, DH_W_L3_1_C1_W, DH_W_L3_1_C1_B, nullptr, 1, T16a);
+  DH_CONV("layer3.1.conv2", T16a, nullptr, 256, 0, N2, h16, w16, 1, 3, 1, 256, DH_W_L3_1_C2_W, DH_W_L3_1_C2_B, T16c, 1, F16);
+
+  // ---- transformer levels 5, 4, 3  (reference networks.py:1297-1318; xBD: model_transformer_encoding.py:385-406)
+  const float* feats[3] = {F16, F8, F4};
+  const int base[3] = {DH_W_LV5_SQ, DH_W_LV4_SQ, DH_W_LV3_SQ};
+  static const char* const nm[3][7] = {
+      {"squeeze_tok_5", "token_enc_5", "dec_tables_5", "decoder_5_x12", "conv_decode_5", "decoder_5_diff", "conv_layer4"},
+      {"squeeze_tok_4", "token_enc_4", "dec_tables_4", "decoder_4_x12", "conv_decode_4", "decoder_4_diff", "conv_layer4"},
+      {"squeeze_tok_3", "token_enc_3", "dec_tables_3", "decoder_3_x12", "conv_decode_3", "decoder_3_diff", "conv_layer4"}};
+  float* C4 = ws + p.c4;
+  for (int i = 0; i < 3; ++i) {
+    const Level& L = p.lv[i];
+    const int npix = L.h * L.w;
+    const float *wsq = Wt(base[i] + 0), *wtok = Wt(base[i] + 1), *enc = Wt(base[i] + 2), *dec = Wt(base[i] + 3),
+                *pos = Wt(base[i] + 4);
+    float *XS = ws + L.xs, *XD = ws + L.xd, *DX = ws + L.dx, *OUT = ws + L.out, *PART = ws + L.part, *MEM = ws + L.mem,
+          *TAB = ws + L.tab;
+    // what the reference adds to this level's result: nothing (level 5), up2(out_5) (level 4, :1333),
+    // conv_layer4(up2(out_4)) at the same resolution (level 3, :1340)
+    const float* skip = (i == 0) ? nullptr : (i == 1 ? ws + p.lv[0].out : C4);
+    const int skip_up = (i == 1) ? 2 : 1;
+    // as-written FLOPs per pixel of one decoder call (help_funcs.py:66-114): q proj + dots + attn.V + out proj + MLP
+    const double inner = 64.0 * L.heads;
+    const double dec_fl_px = L.depth * 2.0 * (32 * inner + 4 * inner + 4 * inner + inner * 32 + 2 * 32 * 32);
+    const double dec_by_px = 4.0 * 32 * (pos ? 3 : 2);
+    DH_STEP(nm[i][0], 2.0 * N2 * npix * 32 * (L.cin + 4 + 4), 4.0 * N2 * npix * (L.cin + 32.0),
+            dh_launch_squeeze_tokens(feats[i], N2, npix, L.cin, wsq, wtok, XS, PART, s));
+    const int add_tok_pos = (variant == DH_VARIANT_LEVIR) ? 1 : (i == 0 ? 1 : 0);
+    DH_STEP(nm[i][1], 0.0, 4.0 * N2 * L.nchunk * 136.0, dh_launch_token_encoder(PART, B, L.nchunk, enc, L.heads, add_tok_pos, MEM, s));
+    const size_t half = (size_t)B * npix * 32;
+    if (variant == DH_VARIANT_LEVIR) {
+      DH_STEP(nm[i][2], 0.0, 4.0 * 3 * B * L.depth * DH_TAB_FLOATS(L.heads), dh_launch_decoder_tables(MEM, B, 0, 3, dec, L.heads, L.depth, TAB, s));
+      DH_STEP(nm[i][3], dec_fl_px * N2 * npix, dec_by_px * N2 * npix,
+              dh_launch_pixel_decoder(XS, pos, TAB, dec, N2, L.h, L.w, L.heads, L.depth, nullptr, 1, XD, s));
+      DH_CONV(nm[i][4], XD, XD + half, 32, 32, B, L.h, L.w, 1, 3, 1, 32, base[i] + 5, -1, nullptr, 0, DX);
+      const float* tab2 = TAB + (size_t)2 * B * L.depth * DH_TAB_FLOATS(L.heads);
+      DH_STEP(nm[i][5], dec_fl_px * B * npix, (dec_by_px + (skip ? 128.0 / (skip_up * skip_up) : 0.0)) * B * npix,
+              dh_launch_pixel_decoder(DX, pos, tab2, dec, B, L.h, L.w, L.heads, L.depth, skip, skip_up, OUT, s));
+    } else {
+      DH_STEP(nm[i][2], 0.0, 4.0 * B * L.depth * DH_TAB_FLOATS(L.heads), dh_launch_decoder_tables(MEM, B, 2, 1, dec, L.heads, L.depth, TAB, s));
+      DH_CONV(nm[i][4], XS, XS + half, 32, 32, B, L.h, L.w, 1, 3, 1, 32, base[i] + 5, -1, nullptr, 0, DX);
+      DH_STEP(nm[i][5], dec_fl_px * B * npix, (dec_by_px + (skip ? 128.0 / (skip_up * skip_up) : 0.0)) * B * npix,
+              dh_launch_pixel_decoder(DX, pos, TAB, dec, B, L.h, L.w, L.heads, L.depth, skip, skip_up, OUT, s));
+    }
+    if (i == 1)   // conv_layer4(up2(out_4)) -> C4 at H/4 (:1335-1336)
+      DH_CONV(nm[i][6], OUT, nullptr, 32, 0, B, L.h, L.w, 2, 3, 1, 32, DH_W_CL4_W, DH_W_CL4_B, nullptr, 1, C4);
+  }
+  // ---- UNet head (reference networks.py:1341-1357)
+  float *C3 = ws + p.c3, *Y20 = ws + p.y20, *O2 = ws + p.o2, *C2 = ws + p.c2;
+  const float* OUT3 = ws + p.lv[2].out;                                   // out_3 = level3 + C4
+  DH_CONV("conv_layer3", OUT3, nullptr, 32, 0, B, h4, w4, 2, 3, 1, 32, DH_W_CL3_W, DH_W_CL3_B, nullptr, 1, C3);   // on up2(out_3)
+  const float* A128 = F2;
+  const float* B128 = F2 + (size_t)B * h2 * w2 * 64;
+  DH_CONV("conv_layer2_0.0", A128, B128, 64, 64, B, h2, w2, 1, 3, 1, 128, DH_W_CL20A_W, DH_W_CL20A_B, nullptr, 1, Y20);  // conv+BN+ReLU
+  DH_CONV("conv_layer2_0.3", Y20, nullptr, 128, 0, B, h2, w2, 1, 3, 1, 32, DH_W_CL20B_W, DH_W_CL20B_B, C3, 0, O2);       // + out_3
+  DH_CONV("conv_layer2", O2, nullptr, 32, 0, B, h2, w2, 2, 3, 1, 32, DH_W_CL2_W, DH_W_CL2_B, nullptr, 1, C2);            // on up2(out_2)
+  DH_STEP("classifier", 2.0 * B * H * W * 9 * 32 * output_nc, 4.0 * B * H * W * (32.0 + output_nc) + (argmax_u8 ? (double)B * H * W : 0.0),
+          dh_launch_classifier(C2, B, H, W, output_nc, Wt(DH_W_CLS_W), Wt(DH_W_CLS_B), logits, argmax_u8, s));
+  return 0;
+}
+
+// Diagnostic twin of dahitra_forward: records a CUDA event after every launch, SYNCHRONISES the stream, and
+// returns per-launch device time plus the algorithmic FLOPs / bytes of each launch.  Not for the hot path.
+//   ms/flops/bytes: host arrays of capacity `cap`; names: host array of `cap` const char*; returns the number
+//   of launches (>0) or an error code (<=0).
+extern "C" int dahitra_forward_profiled(const void* const* weights, int n_weights, const float* x1, const float* x2,
+                                        long long x_batch_stride, float* logits, unsigned char* argmax_u8,
+                                        void* workspace, size_t workspace_bytes, int variant, int B, int H, int W,
+                                        int output_nc, int flags, void* stream, int cap, float* ms, double* flops,
+                                        double* bytes, const char** names) {
+  DH_REQUIRE(ms && flops && bytes && names && cap > 0, DH_E_NULL);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!g_prof.created) {
+    for (int i = 0; i <= PROF_MAX; ++i)
+      if (cudaEventCreate(&g_prof.ev[i]) != cudaSuccess) return -(int)cudaGetLastError() - 1000;
+    g_prof.created = true;
+  }
+  g_prof.n = 0;
+  g_prof.on = true;
+  cudaEventRecord(g_prof.ev[0], s);
+  const int rc = dahitra_forward(weights, n_weights, x1, x2, x_batch_stride, logits, argmax_u8, workspace, workspace_bytes,
+                                 variant, B, H, W, output_nc, flags, stream);
+  g_prof.on = false;
+  if (rc != 0) return rc > 0 ? -rc - 1000 : rc;
+  const cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return -(int)e - 1000;
+  const int n = g_prof.n < cap ? g_prof.n : cap;
+  for (int i = 0; i < n; ++i) {
+    cudaEventElapsedTime(&ms[i], g_prof.ev[i], g_prof.ev[i + 1]);
+    flops[i] = g_prof.rec[i].flops;
+    bytes[i] = g_prof.rec[i].bytes;
+    names[i] = g_prof.rec[i].name;
+  }
+  return n;
+}

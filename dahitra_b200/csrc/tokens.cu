@@ -1,0 +1,294 @@
+// dahitra_b200 — token path: squeeze(1x1 conv+ReLU) fused with the tokenizer's spatial softmax partials,
+// the 1-layer token encoder, and the per-(pair,call,layer) attention tables of the collapsed pixel decoder.
+#include "common.cuh"
+
+// =====================================================================================================
+// squeeze + tokenizer partials.
+//   xs[p][:]  = relu(Wsq^T feat[p][:])                      (reference models/networks.py:1177-1184)
+//   a[p][l]   = sum_c Wtok[c][l] xs[p][c]                   (conv_token, :1187-1189)
+//   per CTA (128 pixels): m_l = max_p a, s_l = sum_p exp(a-m_l), t_l[c] = sum_p exp(a-m_l) xs[p][c]
+// The spatial softmax over all N pixels (:1273-1280) is finished by the token-encoder kernel, which merges
+// the per-CTA (m, s, t) triples with the usual log-sum-exp rescaling.
+// =====================================================================================================
+namespace {
+constexpr int SQ_T = 128;   // pixels (= threads) per CTA
+
+__global__ void __launch_bounds__(SQ_T)
+squeeze_tokens_kernel(const float* __restrict__ feat, int npix, int Cin, int nchunk, const float* __restrict__ wsq,
+                      const float* __restrict__ wtok, float* __restrict__ xs, float* __restrict__ partials) {
+  extern __shared__ __align__(16) float sm[];
+  float* w_s = sm;                         // [Cin][32]
+  float* wt_s = w_s + Cin * 32;            // [32][4]
+  float* tile = wt_s + 128;                // [128][33]
+  float* e_s = tile + SQ_T * 33;           // [128][4]
+  float* red = e_s + SQ_T * 4;             // [4 warps][4]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int img = blockIdx.y, chunk = blockIdx.x;
+  for (int i = tid; i < Cin * 8; i += SQ_T) reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(wsq) + i);
+  if (tid < 32) reinterpret_cast<float4*>(wt_s)[tid] = __ldg(reinterpret_cast<const float4*>(wtok) + tid);
+  __syncthreads();
+
+  const int p = chunk * SQ_T + tid;
+  const bool valid = p < npix;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  if (valid) {
+    const float* fp = feat + ((size_t)img * npix + p) * Cin;
+    for (int c = 0; c < Cin; c += 4) {
+      const float4 f = ldg4(fp + c);
+      const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float* wr = w_s + (c + e) * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 ww = *reinterpret_cast<const float4*>(wr + q * 4);
+          acc[q * 4 + 0] = fmaf(fv[e], ww.x, acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(fv[e], ww.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(fv[e], ww.z, acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(fv[e], ww.w, acc[q * 4 + 3]);
+        }
+      }
+    }
+  }
+  float lg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    acc[j] = fmaxf(acc[j], 0.f);
+    const float4 wt = *reinterpret_cast<const float4*>(wt_s + j * 4);
+    lg[0] = fmaf(acc[j], wt.x, lg[0]);
+    lg[1] = fmaf(acc[j], wt.y, lg[1]);
+    lg[2] = fmaf(acc[j], wt.z, lg[2]);
+    lg[3] = fmaf(acc[j], wt.w, lg[3]);
+  }
+  if (valid) {
+    float* op = xs + ((size_t)img * npix + p) * 32;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) st4(op + q * 4, make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]));
+  }
+  // block max of each token's logits
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const float m = warp_max(valid ? lg[l] : -INFINITY);
+    if (lane == 0) red[wid * 4 + l] = m;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tile[tid * 33 + j] = acc[j];
+  __syncthreads();
+  float mx[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    mx[l] = fmaxf(fmaxf(red[l], red[4 + l]), fmaxf(red[8 + l], red[12 + l]));
+    e_s[tid * 4 + l] = valid ? expf(lg[l] - mx[l]) : 0.f;
+  }
+  __syncthreads();
+  // thread (l, c): weighted sum over the CTA's pixels
+  const int l = tid >> 5, c = tid & 31;
+  float t = 0.f, ssum = 0.f;
+#pragma unroll 8
+  for (int q = 0; q < SQ_T; ++q) {
+    const float e = e_s[q * 4 + l];
+    ssum += e;
+    t = fmaf(e, tile[q * 33 + c], t);
+  }
+  float* pp = partials + (((size_t)img * nchunk + chunk) * 4 + l) * 34;
+  if (c == 0) {
+    pp[0] = fmaxf(fmaxf(red[l], red[4 + l]), fmaxf(red[8 + l], red[12 + l]));
+    pp[1] = ssum;
+  }
+  pp[2 + c] = t;
+}
+}  // namespace
+
+int dh_launch_squeeze_tokens(const float* feat, int N, int npix, int Cin, const float* wsq, const float* wtok,
+                             float* xs, float* partials, cudaStream_t s) {
+  DH_REQUIRE(feat && wsq && wtok && xs && partials, DH_E_NULL);
+  DH_REQUIRE(N > 0 && npix > 0 && Cin % 4 == 0 && Cin >= 4 && Cin <= 256, DH_E_SHAPE);
+  DH_REQUIRE(dh_aligned16(feat) && dh_aligned16(wsq) && dh_aligned16(wtok) && dh_aligned16(xs), DH_E_ALIGN);
+  const int nchunk = dh_cdiv(npix, SQ_T);
+  const int smem = (Cin * 32 + 128 + SQ_T * 33 + SQ_T * 4 + 16) * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(squeeze_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(nchunk, N);
+  squeeze_tokens_kernel<<<grid, SQ_T, smem, s>>>(feat, npix, Cin, nchunk, wsq, wtok, xs, partials);
+  DH_CHECK_LAUNCH();
+  return 0;
+}
+
+// =====================================================================================================
+// Token encoder: one CTA (8 warps = 8 tokens) per image pair.
+//   tokens = softmax-merge(partials) ; tokens += pos ; 1 pre-norm self-attention layer + MLP
+//   (reference models/networks.py:1282-1286 and the Transformer at :434-512).
+// The q.k and v.out products are evaluated through the host-collapsed per-head 32x32 matrices
+//   Mqk[h] = dim^-0.5 Wq[h]^T Wk[h],  MvoT[h][c'][c] = sum_d Wo[c][hd] Wv[hd][c']      (include/dahitra_b200.h)
+// Output: mem[pair][0] = token1', mem[pair][1] = token2', mem[pair][2] = |token2' - token1'| (:1304,1315).
+// =====================================================================================================
+namespace {
+
+__device__ __forceinline__ float ln_lane(float v, float g, float b) {   // LayerNorm(32) across a warp
+  const float mu = warp_sum(v) * (1.f / 32.f);
+  const float d = v - mu;
+  const float var = warp_sum(d * d) * (1.f / 32.f);
+  return d * (1.0f / sqrtf(var + 1e-5f)) * g + b;
+}
+
+__global__ void __launch_bounds__(256)
+token_encoder_kernel(const float* __restrict__ partials, int B, int nchunk, const float* __restrict__ enc, int heads,
+                     int add_pos, float* __restrict__ mem) {
+  __shared__ float X[8][32], XN[8][32], Y[8][32], Hh[8][32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;   // warp w <-> token w; lane <-> channel
+  const int pair = blockIdx.x;
+  const float* pos = enc;
+  const float* ln1g = enc + 256; const float* ln1b = ln1g + 32;
+  const float* Mqk = ln1b + 32;
+  const float* MvoT = Mqk + (size_t)heads * 1024;
+  const float* bo = MvoT + (size_t)heads * 1024;
+  const float* ln2g = bo + 32; const float* ln2b = ln2g + 32;
+  const float* W1t = ln2b + 32; const float* b1 = W1t + 1024;
+  const float* W2t = b1 + 32; const float* b2 = W2t + 1024;
+
+  // 1. finish the spatial softmax for token (img = w/4, l = w%4), channel = lane
+  {
+    const int img = (w < 4) ? pair : (B + pair), l = w & 3;
+    const float* pp = partials + ((size_t)img * nchunk * 4 + l) * 34;
+    float M = -INFINITY;
+    for (int k = lane; k < nchunk; k += 32) M = fmaxf(M, __ldg(pp + (size_t)k * 4 * 34));
+    M = warp_max(M);
+    float S = 0.f, T = 0.f;
+    for (int k = 0; k < nchunk; ++k) {
+      const float* q = pp + (size_t)k * 4 * 34;
+      const float sc = expf(__ldg(q) - M);
+      S = fmaf(__ldg(q + 1), sc, S);
+      T = fmaf(__ldg(q + 2 + lane), sc, T);
+    }
+    float v = T / S;
+    if (add_pos) v += __ldg(pos + w * 32 + lane);
+    X[w][lane] = v;
+    XN[w][lane] = ln_lane(v, __ldg(ln1g + lane), __ldg(ln1b + lane));
+  }
+  __syncthreads();
+  // 2. attention, head by head
+  float att_out = 0.f;
+  for (int h = 0; h < heads; ++h) {
+    const float* mq = Mqk + (size_t)h * 1024;
+    const float* mv = MvoT + (size_t)h * 1024;
+    float u = 0.f, y = 0.f;     // u[c'] = sum_c xn_w[c] Mqk[c][c'] ;  y[c] = sum_c' MvoT[c'][c] xn_w[c']
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const float xv = XN[w][c];
+      u = fmaf(xv, __ldg(mq + c * 32 + lane), u);
+      y = fmaf(xv, __ldg(mv + c * 32 + lane), y);
+    }
+    __syncthreads();            // previous head's readers of Y are done
+    Y[w][lane] = y;
+    float d[8], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d[j] = warp_sum(u * XN[j][lane]);
+      mx = fmaxf(mx, d[j]);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { d[j] = expf(d[j] - mx); den += d[j]; }
+    const float inv = 1.f / den;
+    __syncthreads();            // Y complete
+#pragma unroll
+    for (int j = 0; j < 8; ++j) att_out = fmaf(d[j] * inv, Y[j][lane], att_out);
+  }
+  float x = X[w][lane] + att_out + __ldg(bo + lane);
+  // 3. MLP
+  const float xn2 = ln_lane(x, __ldg(ln2g + lane), __ldg(ln2b + lane));
+  __syncthreads();
+  XN[w][lane] = xn2;
+  __syncwarp();
+  float hsum = __ldg(b1 + lane);
+#pragma unroll 8
+  for (int c = 0; c < 32; ++c) hsum = fmaf(XN[w][c], __ldg(W1t + c * 32 + lane), hsum);
+  Hh[w][lane] = gelu_erf(hsum);
+  __syncwarp();
+  float o = __ldg(b2 + lane);
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) o = fmaf(Hh[w][k], __ldg(W2t + k * 32 + lane), o);
+  x += o;
+  __syncthreads();
+  X[w][lane] = x;
+  __syncthreads();
+  float* mp = mem + (size_t)pair * 3 * 128;
+  mp[w * 32 + lane] = x;                                    // calls 0 (tokens 0-3) and 1 (tokens 4-7)
+  if (w < 4) mp[256 + w * 32 + lane] = fabsf(X[w + 4][lane] - X[w][lane]);
+}
+}  // namespace
+
+int dh_launch_token_encoder(const float* partials, int B, int nchunk, const float* enc, int heads, int add_pos,
+                            float* mem, cudaStream_t s) {
+  DH_REQUIRE(partials && enc && mem, DH_E_NULL);
+  DH_REQUIRE(B > 0 && nchunk > 0 && heads >= 1 && heads <= 16, DH_E_SHAPE);
+  token_encoder_kernel<<<B, 256, 0, s>>>(partials, B, nchunk, enc, heads, add_pos, mem);
+  DH_CHECK_LAUNCH();
+  return 0;
+}
+
+// =====================================================================================================
+// Decoder attention tables.  For memory tokens m (4x32) of one (pair, call) and decoder layer L:
+//   mn_j = LN_L(m_j)                           (PreNorm2 shares the layer's LayerNorm, help_funcs.py:43-49)
+//   A [c][h*4+j] = g_c * sum_c' Mqk_L[h][c][c'] mn_j[c']       (LN gamma of the query side folded in)
+//   cA[h*4+j]    = sum_c b_c * (A/g)[c][h*4+j]                  (LN beta of the query side)
+//   Bv[h*4+j][c] = sum_c' Mov_L[h][c][c'] mn_j[c']
+// so that per pixel  s = xhat . A + cA ; p = softmax_j(s) ; x += sum p Bv + b_out   (xhat = (x-mu)/sigma).
+// Table layout: A[32][4H] | cA[4H] | Bv[4H][32] | b_out[32].
+// grid = (depth, ncalls*B); 128 threads (warp j <-> memory token j, lane <-> channel).
+// =====================================================================================================
+namespace {
+__global__ void __launch_bounds__(128)
+decoder_tables_kernel(const float* __restrict__ mem, int B, int first_call, const float* __restrict__ dec, int heads,
+                      float* __restrict__ tables, int depth) {
+  __shared__ float MN[4][32];
+  const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int layer = blockIdx.x;
+  const int ci = blockIdx.y / B, pair = blockIdx.y % B;       // call index relative to first_call
+  const int call = first_call + ci;
+  const size_t lstride = DH_DEC_LAYER_FLOATS(heads);
+  const float* L = dec + (size_t)layer * lstride;
+  const float* ln1g = L; const float* ln1b = L + 32;
+  const float* MqkT = L + 64;
+  const float* MovT = MqkT + (size_t)heads * 1024;
+  const float* bo = MovT + (size_t)heads * 1024;
+  const int H4 = heads * 4;
+  float* T = tables + ((size_t)blockIdx.y * depth + layer) * DH_TAB_FLOATS(heads);
+  float* A = T; float* cA = T + 32 * H4; float* Bv = cA + H4; float* bout = Bv + H4 * 32;
+
+  const float g = __ldg(ln1g + lane), b = __ldg(ln1b + lane);
+  const float m = __ldg(mem + ((size_t)pair * 3 + call) * 128 + j * 32 + lane);
+  MN[j][lane] = ln_lane(m, g, b);
+  __syncwarp();
+  for (int h = 0; h < heads; ++h) {
+    const float* mq = MqkT + (size_t)h * 1024;
+    const float* mv = MovT + (size_t)h * 1024;
+    float a = 0.f, v = 0.f;
+#pragma unroll 8
+    for (int c2 = 0; c2 < 32; ++c2) {
+      const float mn = MN[j][c2];
+      a = fmaf(__ldg(mq + c2 * 32 + lane), mn, a);     // MqkT[h][c'][c]
+      v = fmaf(__ldg(mv + c2 * 32 + lane), mn, v);     // MovT[h][c'][c]
+    }
+    const int col = h * 4 + j;
+    A[lane * H4 + col] = g * a;
+    const float ca = warp_sum(b * a);
+    if (lane == 0) cA[col] = ca;
+    Bv[col * 32 + lane] = v;
+  }
+  if (j == 0) bout[lane] = __ldg(bo + lane);
+}
+}  // namespace
+
+int dh_launch_decoder_tables(const float* mem, int B, int first_call, int ncalls, const float* dec, int heads, int depth,
+                             float* tables, cudaStream_t s) {
+  DH_REQUIRE(mem && dec && tables, DH_E_NULL);
+  DH_REQUIRE(B > 0 && first_call >= 0 && ncalls >= 1 && first_call + ncalls <= 3 && (heads == 4 || heads == 8) &&
+             depth >= 1, DH_E_SHAPE);
+  dim3 grid(depth, ncalls * B);
+  decoder_tables_kernel<<<grid, 128, 0, s>>>(mem, B, first_call, dec, heads, tables, depth);
+  DH_CHECK_LAUNCH();
+  return 0;
+}

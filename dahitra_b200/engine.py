@@ -1,0 +1,269 @@
+"""Native inference engine: host-side weight preparation + the call into ``dahitra_forward``.
+
+Weight preparation (once per set of weights, re-done after ``load_state_dict`` / ``train()`` / ``.to()``):
+  * eval-mode BatchNorm folded into the preceding convolution (W' = W*g/sigma, b' = beta - mu*g/sigma)
+  * conv weights re-laid-out OIHW -> [KH*KW*Cin][Cout] (implicit-GEMM "B" operand, Cout contiguous)
+  * token encoder / pixel decoder products collapsed to per-head 32x32 matrices in fp64
+    (Mqk = dim^-0.5 Wq^T Wk, Mov = Wo Wv), second LayerNorm of each decoder layer folded into W1/b1
+  * decoder positional embeddings NCHW -> [h*w][32]
+Layouts are documented slot by slot in include/dahitra_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+
+BN_EPS = 1e-5
+SCALE = 32 ** -0.5
+LEVELS = ((5, 256, 4, 4), (4, 128, 4, 4), (3, 64, 8, 8))   # (k, trunk channels, heads, decoder depth)
+
+DH_VARIANT_LEVIR, DH_VARIANT_XBD = 0, 1
+DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32 = 1, 2
+
+
+def slot_names():
+    lib = _lib.load()
+    out, i = [], 0
+    while True:
+        s = lib.dahitra_weight_slot_name(i)
+        if s is None:
+            return out
+        out.append(s.decode())
+        i += 1
+
+
+# ----------------------------------------------------------------------------- host-side preparation
+def _fold_conv_bn(sd, conv, bn):
+    w = sd[conv + ".weight"].double()
+    if bn is None:
+        return w, (sd[conv + ".bias"].double() if (conv + ".bias") in sd else None)
+    g, b = sd[bn + ".weight"].double(), sd[bn + ".bias"].double()
+    mu, var = sd[bn + ".running_mean"].double(), sd[bn + ".running_var"].double()
+    k = g / torch.sqrt(var + BN_EPS)
+    return w * k[:, None, None, None], b - mu * k
+
+
+def _khwc(w):
+    """OIHW -> [KH*KW*Cin][Cout]"""
+    o, i, kh, kw = w.shape
+    return w.permute(2, 3, 1, 0).reshape(kh * kw * i, o)
+
+
+def _heads(w, h):                       # (h*64, 32) -> (h, 64, 32)
+    return w.reshape(h, -1, w.shape[-1])
+
+
+def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
+    """state_dict (reference key layout, any device/dtype) -> {slot name: fp32 CPU tensor (or None)}."""
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    P = {}
+
+    def put_conv(slot, conv, bn):
+        w, b = _fold_conv_bn(sd, conv, bn)
+        P[slot + "_W"] = _khwc(w)
+        P[slot + "_B"] = b
+
+    put_conv("DH_W_STEM", "resnet.conv1", "resnet.bn1")
+    for li in (1, 2, 3):
+        for bi in (0, 1):
+            p = f"resnet.layer{li}.{bi}"
+            put_conv(f"DH_W_L{li}_{bi}_C1", p + ".conv1", p + ".bn1")
+            put_conv(f"DH_W_L{li}_{bi}_C2", p + ".conv2", p + ".bn2")
+            if (p + ".downsample.0.weight") in sd:
+                put_conv(f"DH_W_L{li}_{bi}_DS", p + ".downsample.0", p + ".downsample.1")
+    for k, cin, heads, depth in LEVELS:
+        s = f"DH_W_LV{k}_"
+        P[s + "SQ"] = sd[f"conv_squeeze_{k}.0.weight"].double()[:, :, 0, 0].T          # [Cin][32]
+        P[s + "TOK"] = sd[f"conv_token_{k}.weight"].double()[:, :, 0, 0].T             # [32][4]
+        P[s + "DECODE"] = _khwc(sd[f"conv_decode_{k}.weight"].double())
+        # ---- token encoder pack
+        t = f"transformer_{k}.layers.0"
+        if variant == DH_VARIANT_LEVIR:
+            pos = sd[f"pos_embedding_{k}"].double().reshape(-1) if f"pos_embedding_{k}" in sd \
+                else torch.zeros(256, dtype=torch.float64)
+        else:   # xBD: only the H/16 level adds one, and it is pos_embedding_3 (model_transformer_encoding.py:358-366)
+            pos = sd["pos_embedding_3"].double().reshape(-1) if k == 5 else torch.zeros(256, dtype=torch.float64)
+        wqkv = sd[t + ".0.fn.fn.to_qkv.weight"].double()
+        inner = heads * 64
+        wq, wk, wv = (_heads(wqkv[i * inner:(i + 1) * inner], heads) for i in range(3))
+        wo = sd[t + ".0.fn.fn.to_out.0.weight"].double().reshape(32, heads, 64).permute(1, 0, 2)   # (h, c, d)
+        mqk = SCALE * torch.einsum("hdc,hde->hce", wq, wk)              # [h][c][c']
+        mvoT = torch.einsum("hcd,hde->hec", wo, wv)                     # [h][c'][c]
+        P[s + "ENC"] = torch.cat([
+            pos, sd[t + ".0.fn.norm.weight"].double(), sd[t + ".0.fn.norm.bias"].double(),
+            mqk.reshape(-1), mvoT.reshape(-1), sd[t + ".0.fn.fn.to_out.0.bias"].double(),
+            sd[t + ".1.fn.norm.weight"].double(), sd[t + ".1.fn.norm.bias"].double(),
+            sd[t + ".1.fn.fn.net.0.weight"].double().T.reshape(-1), sd[t + ".1.fn.fn.net.0.bias"].double(),
+            sd[t + ".1.fn.fn.net.3.weight"].double().T.reshape(-1), sd[t + ".1.fn.fn.net.3.bias"].double()])
+        # ---- pixel decoder pack
+        layers = []
+        for l in range(depth):
+            d = f"transformer_decoder_{k}.layers.{l}"
+            wq = _heads(sd[d + ".0.fn.fn.to_q.weight"].double(), heads)
+            wk = _heads(sd[d + ".0.fn.fn.to_k.weight"].double(), heads)
+            wv = _heads(sd[d + ".0.fn.fn.to_v.weight"].double(), heads)
+            wo = sd[d + ".0.fn.fn.to_out.0.weight"].double().reshape(32, heads, 64).permute(1, 0, 2)
+            mqkT = SCALE * torch.einsum("hdc,hde->hec", wq, wk)         # [h][c'][c]
+            movT = torch.einsum("hcd,hde->hec", wo, wv)                 # [h][c'][c]
+            g2, b2n = sd[d + ".1.fn.norm.weight"].double(), sd[d + ".1.fn.norm.bias"].double()
+            w1, b1 = sd[d + ".1.fn.fn.net.0.weight"].double(), sd[d + ".1.fn.fn.net.0.bias"].double()
+            w2, b2 = sd[d + ".1.fn.fn.net.3.weight"].double(), sd[d + ".1.fn.fn.net.3.bias"].double()
+            layers += [sd[d + ".0.fn.norm.weight"].double(), sd[d + ".0.fn.norm.bias"].double(),
+                       mqkT.reshape(-1), movT.reshape(-1), sd[d + ".0.fn.fn.to_out.0.bias"].double(),
+                       (w1 * g2[None, :]).T.reshape(-1), b1 + w1 @ b2n, w2.T.reshape(-1), b2]
+        P[s + "DEC"] = torch.cat(layers)
+        # ---- decoder positional embedding
+        if variant == DH_VARIANT_LEVIR:
+            pe = sd.get(f"pos_embedding_decoder_{k}")
+        else:
+            pe = sd.get("pos_embedding_decoder_3") if k == 5 else None
+        P[s + "POS"] = None if pe is None else pe.double()[0].permute(1, 2, 0).reshape(-1, 32)
+    for name, key in (("DH_W_CL4", "conv_layer4.0"), ("DH_W_CL3", "conv_layer3.0"), ("DH_W_CL2", "conv_layer2.0")):
+        put_conv(name, key, None)
+    put_conv("DH_W_CL20A", "conv_layer2_0.0", "conv_layer2_0.1")
+    put_conv("DH_W_CL20B", "conv_layer2_0.3", None)
+    wc = sd["classifier.weight"].double()
+    assert wc.shape[0] == out_nc
+    P["DH_W_CLS_W"] = wc.permute(2, 3, 0, 1).reshape(9, out_nc, 32)
+    P["DH_W_CLS_B"] = sd["classifier.bias"].double()
+    return {k: (None if v is None else v.to(torch.float32).contiguous()) for k, v in P.items()}
+
+
+class PreparedWeights:
+    """Device copies of the prepared tensors + the C pointer table handed to dahitra_forward."""
+
+    def __init__(self, sd, variant, out_nc, device):
+        names = slot_names()
+        host = prepare_weights(sd, variant, out_nc)
+        missing = [n for n in names if n not in host]
+        if missing:
+            raise RuntimeError(f"weight preparation does not produce slots {missing}")
+        # one flat buffer, every slot 256-byte aligned
+        offs, total = {}, 0
+        for n in names:
+            if host[n] is not None:
+                offs[n] = total
+                total += (host[n].numel() + 63) // 64 * 64
+        flat = torch.zeros(total, dtype=torch.float32)
+        for n, o in offs.items():
+            flat[o:o + host[n].numel()] = host[n].reshape(-1)
+        self.flat = flat.to(device)
+        self.shapes = {n: (None if host[n] is None else tuple(host[n].shape)) for n in names}
+        base = self.flat.data_ptr()
+        self.table = (C.c_void_p * len(names))(*[(base + 4 * offs[n]) if n in offs else None for n in names])
+        self.n = len(names)
+        self.names = names
+        self.offs = offs
+
+    def view(self, name):
+        o = self.offs[name]
+        shp = self.shapes[name]
+        n = 1
+        for d in shp:
+            n *= d
+        return self.flat[o:o + n].view(shp)
+
+    def ptr(self, name):
+        return self.flat.data_ptr() + 4 * self.offs[name] if name in self.offs else None
+
+
+# ----------------------------------------------------------------------------- engine
+class NativeEngine:
+    def __init__(self):
+        self._prep = None
+        self._prep_key = None
+        self._ws = {}
+        self.flags = int(os.environ.get("DAHITRA_FLAGS", "0"))
+        self.last_argmax = None
+
+    def invalidate(self):
+        self._prep = None
+        self._prep_key = None
+
+    def _prepared(self, module, device):
+        key = (str(device), module.VARIANT, self.flags)
+        if self._prep is None or self._prep_key != key:
+            variant = DH_VARIANT_LEVIR if module.VARIANT == "levir" else DH_VARIANT_XBD
+            self._prep = PreparedWeights(module.state_dict(), variant, module.output_nc, device)
+            self._prep_key = key
+        return self._prep
+
+    def _workspace(self, lib, device, variant, B, H, W, nc):
+        key = (str(device), variant, B, H, W, nc, self.flags)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = lib.dahitra_workspace_bytes(variant, B, H, W, nc, self.flags)
+            if nbytes == 0:
+                raise RuntimeError(f"dahitra_b200: unsupported shape B={B} H={H} W={W} (H, W must be multiples of 32)")
+            if len(self._ws) > 4:
+                self._ws.clear()
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+        return ws
+
+    def run(self, module, x1, x2, batch_stride, B, H, W, want_argmax=False):
+        lib = _lib.load()
+        dev = x1.device
+        variant = DH_VARIANT_LEVIR if module.VARIANT == "levir" else DH_VARIANT_XBD
+        prep = self._prepared(module, dev)
+        for name, hw in module.pos_shapes(H, W).items():
+            shp = prep.shapes.get(name)
+            if shp is not None and shp[0] != hw:
+                raise RuntimeError(
+                    f"dahitra_b200: decoder positional embedding {name} has {shp[0]} positions but the input needs {hw} "
+                    f"(the {module.VARIANT} variant only runs at the resolution its embeddings were built for, like the reference)")
+        nc = module.output_nc
+        ws = self._workspace(lib, dev, variant, B, H, W, nc)
+        logits = torch.empty((B, nc, H, W), dtype=torch.float32, device=dev)
+        amax = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_argmax else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.dahitra_forward(prep.table, prep.n, x1.data_ptr(), x2.data_ptr(), batch_stride,
+                                 logits.data_ptr(), amax.data_ptr() if amax is not None else None,
+                                 ws.data_ptr(), ws.numel(), variant, B, H, W, nc, self.flags, stream)
+        _lib.check(rc, "dahitra_forward")
+        self.last_argmax = amax
+        return logits
+
+    def profile_pair(self, module, x1, x2):
+        """One forward with a CUDA event after every launch (synchronises).  -> list of
+        {name, ms, flops, bytes} in launch order; diagnostic only (bench.py roofline)."""
+        lib = _lib.load()
+        x1 = x1.float().contiguous()
+        x2 = x2.float().contiguous()
+        B, _, H, W = x1.shape
+        dev = x1.device
+        variant = DH_VARIANT_LEVIR if module.VARIANT == "levir" else DH_VARIANT_XBD
+        prep = self._prepared(module, dev)
+        nc = module.output_nc
+        ws = self._workspace(lib, dev, variant, B, H, W, nc)
+        logits = torch.empty((B, nc, H, W), dtype=torch.float32, device=dev)
+        cap = 160
+        ms, fl, by = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
+        names = (C.c_char_p * cap)()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        n = lib.dahitra_forward_profiled(prep.table, prep.n, x1.data_ptr(), x2.data_ptr(), 3 * H * W, logits.data_ptr(),
+                                         None, ws.data_ptr(), ws.numel(), variant, B, H, W, nc, self.flags, stream,
+                                         cap, ms, fl, by, names)
+        if n <= 0:
+            _lib.check(n if n > -1000 else -(n + 1000), "dahitra_forward_profiled")
+        return [dict(name=names[i].decode(), ms=float(ms[i]), flops=float(fl[i]), bytes=float(by[i])) for i in range(n)]
+
+    def forward_pair(self, module, x1, x2, want_argmax=False):
+        if x1.shape != x2.shape or x1.dim() != 4 or x1.shape[1] != 3:
+            raise RuntimeError(f"dahitra_b200: expected two (B,3,H,W) tensors, got {tuple(x1.shape)} and {tuple(x2.shape)}")
+        x1 = x1.float().contiguous()
+        x2 = x2.float().contiguous()
+        B, _, H, W = x1.shape
+        return self.run(module, x1, x2, 3 * H * W, B, H, W, want_argmax)
+
+    def forward_stacked(self, module, x, want_argmax=False):
+        """xBD calling convention: x = cat[pre, post] on channels, (B,6,H,W)."""
+        if x.dim() != 4 or x.shape[1] != 6:
+            raise RuntimeError(f"dahitra_b200: expected a (B,6,H,W) tensor, got {tuple(x.shape)}")
+        x = x.float().contiguous()
+        B, _, H, W = x.shape
+        return self.run(module, x, x[:, 3:], 6 * H * W, B, H, W, want_argmax)

@@ -1,0 +1,202 @@
+"""Parameter containers for the drop-in ``newUNetTrans`` network.
+
+These classes exist to hold tensors under EXACTLY the state_dict keys, shapes,
+registration order and RNG-consumption order of the reference, so that
+
+* checkpoints written by the reference trainer load with ``strict=True``
+  (reference: models/evaluator.py:71-73, models/trainer.py:106-134), and
+* ``torch.manual_seed(s); define_G(...)`` yields bit-identical weights
+  (reference: models/networks.py:77-127 ``init_weights`` matches on the class
+  names 'Conv' / 'Linear' / 'BatchNorm2d' during ``net.apply``).
+
+None of them carries the arithmetic of the inference path: the native forward in
+``dahitra_b200.networks`` reads the tensors and launches sm_100a kernels.  The
+small ``forward`` methods below exist only for the autograd (training) route,
+which is stock PyTorch by design (see DESIGN.md "training step").
+
+Key layout that is mirrored (reference file:line):
+  * ResNet-18 trunk           models/resnet.py:125-204 (conv1, bn1, layer1..4, fc)
+  * token encoder             models/networks.py:434-512 (Residual/PreNorm/Attention/FeedForward)
+  * pixel decoder             models/help_funcs.py:26-31,43-49,66-114,170-186
+  * TwoLayerConv2d            models/help_funcs.py:7-15
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------- trunk
+class TrunkBlock(nn.Module):
+    """ResNet BasicBlock container: keys conv1/bn1/conv2/bn2/downsample.{0,1}."""
+
+    def __init__(self, cin: int, cout: int, stride: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(cout, cout, 3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        # The 1x1 projection (if any) is attached by Trunk._stage, which creates it
+        # BEFORE this block's convs (RNG order of models/resnet.py:188-197) but
+        # registers it after bn2 (key order of BasicBlock, models/resnet.py:47-55).
+        self.downsample = None
+        self.stride = stride
+
+    def forward(self, x):
+        idt = x if self.downsample is None else self.downsample(x)
+        y = F.relu(self.bn1(self.conv1(x)))
+        y = self.bn2(self.conv2(y))
+        return F.relu(y + idt)
+
+
+class Trunk(nn.Module):
+    """ResNet-18 as the reference instantiates it (stride-2 layer2, stride-1
+    layer3/4 because of ``replace_stride_with_dilation=[False, True, True]`` with
+    dilation forced back to 1 in BasicBlock; models/resnet.py:45-46,182-204)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.layer1 = self._stage(64, 64, 1)
+        self.layer2 = self._stage(64, 128, 2)
+        self.layer3 = self._stage(128, 256, 1)   # "dilated" => stride 1
+        self.layer4 = self._stage(256, 512, 1)   # never evaluated; checkpoint ballast
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Linear(512, 1000)
+        # same post-construction init sweep as models/resnet.py:162-167
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    @staticmethod
+    def _stage(cin: int, cout: int, stride: int) -> nn.Sequential:
+        proj = None
+        if stride != 1 or cin != cout:
+            proj = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False),
+                                 nn.BatchNorm2d(cout))
+        first = TrunkBlock(cin, cout, stride)
+        first.downsample = proj
+        return nn.Sequential(first, TrunkBlock(cout, cout, 1))
+
+
+# --------------------------------------------------------------------------- token transformer
+class _Res(nn.Module):
+    """y = fn(x, *ctx) + x  (key: fn)."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def forward(self, x, *ctx):
+        return self.fn(x, *ctx) + x
+
+
+class _Norm(nn.Module):
+    """fn(LN(x), LN(ctx)...) with ONE LayerNorm shared by all inputs (keys: norm, fn).
+    reference: models/help_funcs.py:35-49."""
+
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+    def forward(self, x, *ctx):
+        return self.fn(self.norm(x), *[self.norm(c) for c in ctx])
+
+
+class _Mlp(nn.Module):
+    """Linear-GELU(erf)-Linear under keys net.0 / net.3."""
+
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Dropout(0.0),
+                                 nn.Linear(hidden, dim), nn.Dropout(0.0))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+def _split_heads(t, h):
+    b, n, _ = t.shape
+    return t.view(b, n, h, -1).transpose(1, 2)
+
+
+class TokenSelfAttn(nn.Module):
+    """keys: to_qkv.weight, to_out.0.{weight,bias}; scale = dim**-0.5."""
+
+    def __init__(self, dim, heads, dim_head):
+        super().__init__()
+        self.heads, self.scale = heads, dim ** -0.5
+        self.to_qkv = nn.Linear(dim, heads * dim_head * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(heads * dim_head, dim), nn.Dropout(0.0))
+
+    def forward(self, x):
+        q, k, v = (_split_heads(t, self.heads) for t in self.to_qkv(x).chunk(3, dim=-1))
+        p = (q @ k.transpose(-1, -2) * self.scale).softmax(-1)
+        o = (p @ v).transpose(1, 2).flatten(2)
+        return self.to_out(o)
+
+
+class PixelCrossAttn(nn.Module):
+    """keys: to_q/to_k/to_v.weight, to_out.0.{weight,bias}."""
+
+    def __init__(self, dim, heads, dim_head):
+        super().__init__()
+        self.heads, self.scale = heads, dim ** -0.5
+        inner = heads * dim_head
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_k = nn.Linear(dim, inner, bias=False)
+        self.to_v = nn.Linear(dim, inner, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(0.0))
+
+    def forward(self, x, m):
+        q, k, v = (_split_heads(t, self.heads) for t in (self.to_q(x), self.to_k(m), self.to_v(m)))
+        p = (q @ k.transpose(-1, -2) * self.scale).softmax(-1)
+        o = (p @ v).transpose(1, 2).flatten(2)
+        return self.to_out(o)
+
+
+class TokenEncoder(nn.Module):
+    """keys: layers.L.0.fn.{norm,fn.*}, layers.L.1.fn.{norm,fn.net.*}."""
+
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                _Res(_Norm(dim, TokenSelfAttn(dim, heads, dim_head))),
+                _Res(_Norm(dim, _Mlp(dim, mlp_dim)))]))
+
+    def forward(self, x):
+        for attn, ff in self.layers:
+            x = ff(attn(x))
+        return x
+
+
+class PixelDecoder(nn.Module):
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                _Res(_Norm(dim, PixelCrossAttn(dim, heads, dim_head))),
+                _Res(_Norm(dim, _Mlp(dim, mlp_dim)))]))
+
+    def forward(self, x, m):
+        for attn, ff in self.layers:
+            x = ff(attn(x, m))
+        return x
+
+
+def two_layer_head(cin: int, cout: int) -> nn.Sequential:
+    """keys 0.weight, 1.*, 3.{weight,bias}  (models/help_funcs.py:7-15)."""
+    return nn.Sequential(nn.Conv2d(cin, cin, 3, padding=1, bias=False), nn.BatchNorm2d(cin),
+                         nn.ReLU(), nn.Conv2d(cin, cout, 3, padding=1))

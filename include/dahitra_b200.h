@@ -1,0 +1,181 @@
+/*
+ * dahitra_b200 — C ABI of the sm_100a kernel library behind the drop-in `newUNetTrans` module.
+ *
+ * The reference (nka77/DAHiTra) is pure Python/PyTorch and has no FFI of its own; the boundary this
+ * library sits behind is the nn.Module contract
+ *     net = define_G(args, gpu_ids)            reference models/networks.py:130-168
+ *     logits = net(x1, x2)                     reference models/networks.py:1321-1357
+ * Each entry point below names the reference code whose arithmetic it replaces.  A reference
+ * maintainer binds it with ctypes; no torch types cross this interface.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; the caller owns all memory (inputs, outputs,
+ *     prepared weights, workspace).  The library never allocates, frees or synchronises.
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*), CUDA-graph capturable.
+ *   - return value: 0 ok; <0 argument/shape/alignment error detected on the host before any launch
+ *     (DH_E_*); >0 a cudaError_t reported by cudaGetLastError() after a launch.
+ *   - internal activation layout is NHWC fp32 ("pixels x channels"); public inputs/outputs of
+ *     dahitra_forward keep the reference layout (NCHW fp32).
+ */
+#ifndef DAHITRA_B200_H
+#define DAHITRA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAHITRA_ABI_VERSION 1
+
+/* error codes (negative) */
+#define DH_E_NULL      (-1)   /* a required pointer is NULL */
+#define DH_E_SHAPE     (-2)   /* unsupported shape (e.g. H or W not a multiple of 32, B < 1) */
+#define DH_E_ALIGN     (-3)   /* pointer not 16-byte aligned */
+#define DH_E_WORKSPACE (-4)   /* workspace smaller than dahitra_workspace_bytes() */
+#define DH_E_VARIANT   (-5)   /* unknown variant / flags */
+#define DH_E_WEIGHTS   (-6)   /* weight table has the wrong number of slots or a NULL slot */
+
+/* network variants */
+#define DH_VARIANT_LEVIR 0    /* models/networks.py:1142-1357: 3 decoder passes per level, pos-emb on all levels */
+#define DH_VARIANT_XBD   1    /* xBD_code/zoo/model_transformer_encoding.py:242-449 */
+
+/* flags for dahitra_forward */
+#define DH_FLAG_NONE        0
+#define DH_FLAG_CONV_TC     1   /* route eligible convolutions through the tcgen05/TMEM/TMA implicit-GEMM kernel */
+#define DH_FLAG_TC_3XTF32   2   /* with CONV_TC: error-compensated 3xTF32 (fp32-grade accuracy) instead of 1xTF32 */
+
+/* ---- prepared-weight table -------------------------------------------------------------------
+ * dahitra_forward takes `const void* const* weights` with DH_W_COUNT slots, each a device pointer to
+ * fp32 data prepared on the host side by dahitra_b200/engine.py (BN folded into conv weight/bias,
+ * conv weights re-laid-out to [KH*KW*Cin][Cout], transformer products collapsed).  Slot meaning:
+ */
+enum dh_weight_slot {
+  DH_W_STEM_W = 0, DH_W_STEM_B,                    /* resnet.conv1+bn1: [7*7*3][64] (r,s,ci major->minor), [64] */
+  /* trunk 3x3 / 1x1 convs with their BN folded: weight [K][Cout], bias [Cout] */
+  DH_W_L1_0_C1_W, DH_W_L1_0_C1_B, DH_W_L1_0_C2_W, DH_W_L1_0_C2_B,
+  DH_W_L1_1_C1_W, DH_W_L1_1_C1_B, DH_W_L1_1_C2_W, DH_W_L1_1_C2_B,
+  DH_W_L2_0_C1_W, DH_W_L2_0_C1_B, DH_W_L2_0_C2_W, DH_W_L2_0_C2_B, DH_W_L2_0_DS_W, DH_W_L2_0_DS_B,
+  DH_W_L2_1_C1_W, DH_W_L2_1_C1_B, DH_W_L2_1_C2_W, DH_W_L2_1_C2_B,
+  DH_W_L3_0_C1_W, DH_W_L3_0_C1_B, DH_W_L3_0_C2_W, DH_W_L3_0_C2_B, DH_W_L3_0_DS_W, DH_W_L3_0_DS_B,
+  DH_W_L3_1_C1_W, DH_W_L3_1_C1_B, DH_W_L3_1_C2_W, DH_W_L3_1_C2_B,
+  /* per level (5, 4, 3): squeeze [Cin][32]; token conv [32][4]; encoder pack; decoder pack;
+   * decoder positional embedding [h*w][32] (NULL when the variant adds none); conv_decode [9*64][32] */
+  DH_W_LV5_SQ, DH_W_LV5_TOK, DH_W_LV5_ENC, DH_W_LV5_DEC, DH_W_LV5_POS, DH_W_LV5_DECODE,
+  DH_W_LV4_SQ, DH_W_LV4_TOK, DH_W_LV4_ENC, DH_W_LV4_DEC, DH_W_LV4_POS, DH_W_LV4_DECODE,
+  DH_W_LV3_SQ, DH_W_LV3_TOK, DH_W_LV3_ENC, DH_W_LV3_DEC, DH_W_LV3_POS, DH_W_LV3_DECODE,
+  /* UNet head */
+  DH_W_CL4_W, DH_W_CL4_B, DH_W_CL3_W, DH_W_CL3_B, DH_W_CL2_W, DH_W_CL2_B,   /* conv_layer4/3/2: [9*32][32],[32] */
+  DH_W_CL20A_W, DH_W_CL20A_B,                      /* conv_layer2_0.0 + BN: [9*128][128],[128] */
+  DH_W_CL20B_W, DH_W_CL20B_B,                      /* conv_layer2_0.3: [9*128][32],[32] */
+  DH_W_CLS_W, DH_W_CLS_B,                          /* classifier: [9][output_nc][32], [output_nc] */
+  DH_W_COUNT
+};
+
+/* Encoder pack (floats), per level, heads = He:
+ *   pos[8*32]  ln1_g[32] ln1_b[32]  Mqk[He][32 c][32 c']  MvoT[He][32 c'][32 c]  b_out[32]
+ *   ln2_g[32] ln2_b[32]  W1t[32 c][32 o]  b1[32]  W2t[32 o][32 c]  b2[32]
+ * Decoder pack (floats), per level, heads = Hd, per layer (stride DH_DEC_LAYER_FLOATS(Hd)):
+ *   ln1_g[32] ln1_b[32]  MqkT[Hd][32 c'][32 c]  MovT[Hd][32 c'][32 c]  b_out[32]
+ *   W1f[32 c][32 o] (ln2 gamma folded; ln2 beta folded into b1f)  b1f[32]  W2t[32 o][32 c]  b2[32]
+ * with Mqk[h][c][c'] = dim^-0.5 * sum_d Wq[h*64+d][c] * Wk[h*64+d][c']   (c: query side, c': token side),
+ *      Mvo[h][c][c'] = Mov[h][c][c'] = sum_d Wo[c][h*64+d] * Wv[h*64+d][c'];  "T" = stored transposed.
+ */
+#define DH_ENC_FLOATS(H)       (8*32 + 64 + 2*(H)*1024 + 32 + 64 + 1024 + 32 + 1024 + 32)
+#define DH_DEC_LAYER_FLOATS(H) (64 + 2*(H)*1024 + 32 + 1024 + 32 + 1024 + 32)
+
+int         dahitra_version(void);
+const char* dahitra_error_string(int code);
+const char* dahitra_weight_slot_name(int slot);          /* "DH_W_STEM_W", ... ; NULL if out of range */
+
+/* Bytes of scratch dahitra_forward needs for B pairs of HxW images (H, W multiples of 32). */
+size_t dahitra_workspace_bytes(int variant, int B, int H, int W, int output_nc, int flags);
+
+/* Whole bitemporal forward: replaces BASE_Transformer_UNet.forward (reference
+ * models/networks.py:1321-1357; xBD variant model_transformer_encoding.py:409-449).
+ *   x1, x2        (B,3,H,W) fp32 NCHW planes of the pre / post image; `x_batch_stride` = elements between
+ *                 consecutive images of the same tensor (3*H*W for separate tensors, 6*H*W when x1/x2 are
+ *                 the two halves of one (B,6,H,W) xBD input)
+ *   logits        (B,output_nc,H,W) fp32 NCHW
+ *   argmax_u8     optional (B,H,W) uint8 class map (torch.argmax(logits,1) tie rule: lowest index), or NULL
+ */
+int dahitra_forward(const void* const* weights, int n_weights,
+                    const float* x1, const float* x2, long long x_batch_stride,
+                    float* logits, unsigned char* argmax_u8,
+                    void* workspace, size_t workspace_bytes,
+                    int variant, int B, int H, int W, int output_nc, int flags, void* stream);
+
+/* Diagnostic twin of dahitra_forward (same arguments, same arithmetic): records a CUDA event after every
+ * launch, SYNCHRONISES `stream`, and fills host arrays (capacity `cap`) with each launch's device time (ms),
+ * algorithmic FLOPs (2*MACs as the reference writes the op), algorithmic bytes (one read of its stored
+ * inputs and weights + one write of its output) and a static name.  Returns the number of launches (> 0),
+ * or an error (< 0; CUDA errors are reported as -(cudaError_t) - 1000).  Used by bench.py for the roofline. */
+int dahitra_forward_profiled(const void* const* weights, int n_weights,
+                             const float* x1, const float* x2, long long x_batch_stride,
+                             float* logits, unsigned char* argmax_u8,
+                             void* workspace, size_t workspace_bytes,
+                             int variant, int B, int H, int W, int output_nc, int flags, void* stream,
+                             int cap, float* ms, double* flops, double* bytes, const char** names);
+
+/* ---- per-kernel entry points (block-level parity tests; NHWC fp32 activations) ---------------- */
+
+/* Generic convolution: replaces nn.Conv2d(+folded BN)(+residual)(+ReLU) call sites, reference
+ * models/resnet.py:57-73, models/networks.py:1194-1197,1243-1249, models/help_funcs.py:7-15.
+ *   in0/in1   NHWC sources forming a virtual channel concat [in0 (C0) | in1 (C1)], C1 may be 0 (in1 NULL)
+ *   up        1, or 2 = the input is virtually nearest-upsampled x2 first (nn.Upsample, networks.py:1102)
+ *   w         [KH*KW*(C0+C1)][Cout], bias [Cout] or NULL, res NHWC [N][OH][OW][Cout] or NULL
+ *   C0, C1 multiples of 32; Cout multiple of 32.
+ */
+int dahitra_conv2d(const float* in0, const float* in1, int C0, int C1, int N, int inH, int inW, int up,
+                   int KH, int KW, int stride, int pad, int Cout,
+                   const float* w, const float* bias, const float* res, int relu,
+                   float* out, int flags, void* stream);
+
+/* Stem: 7x7 stride-2 pad-3 conv 3->64 + folded BN + ReLU, NCHW planes in, NHWC out
+ * (reference models/networks.py:1120-1122, models/resnet.py:150-153). */
+int dahitra_stem(const float* x, long long x_batch_stride, int N, int H, int W,
+                 const float* w, const float* bias, float* out, void* stream);
+
+/* MaxPool2d(3, stride 2, pad 1) on NHWC (reference models/networks.py:1123,1128). */
+int dahitra_maxpool3x3s2(const float* in, int N, int H, int W, int C, float* out, void* stream);
+
+/* Squeeze (1x1 conv + ReLU) fused with the tokenizer's spatial-softmax partial sums
+ * (reference models/networks.py:1177-1184, 1273-1280).
+ *   feat NHWC [N][npix][Cin] -> xs NHWC [N][npix][32]; partials [N][nchunk][4][34] = {max, sum, t[32]} per token,
+ *   nchunk = ceil(npix/128). */
+int dahitra_squeeze_tokens(const float* feat, int N, int npix, int Cin, const float* w_sq, const float* w_tok,
+                           float* xs, float* partials, void* stream);
+
+/* Token stage for B pairs: finishes the spatial softmax, adds pos-emb (if pos != 0), runs the 1-layer token
+ * encoder (reference models/networks.py:1282-1286, 434-512) and emits the decoder memories
+ *   mem [B][3][4][32] = {token1', token2', |token2' - token1'|}.
+ * partials are laid out for 2B images: image b = pre image of pair b, image B+b = post image. */
+int dahitra_token_encoder(const float* partials, int B, int nchunk, const float* enc_pack, int heads, int add_pos,
+                          float* mem, void* stream);
+
+/* Per (pair, call, layer) attention tables of the collapsed pixel decoder:
+ *   tables [B*ncalls][depth][DH_TAB_FLOATS(heads)] from mem [B][3][4][32] (calls first_call..first_call+ncalls-1). */
+#define DH_TAB_FLOATS(H) (32*4*(H) + 4*(H) + 4*(H)*32 + 32)
+int dahitra_decoder_tables(const float* mem, int B, int first_call, int ncalls, const float* dec_pack, int heads, int depth,
+                           float* tables, void* stream);
+
+/* Pixel decoder: replaces _forward_transformer_decoder + TransformerDecoder
+ * (reference models/networks.py:1288-1295, models/help_funcs.py:66-114,170-186).
+ *   x NHWC [nimg][npix][32]; pos [npix][32] or NULL; tables [nimg][depth][DH_TAB_FLOATS];
+ *   skip: optional NHWC tensor added to the result: skip_up=2 -> [nimg][h/2][w/2][32] nearest-upsampled x2
+ *         (networks.py:1329,1333), skip_up=1 -> [nimg][h][w][32] (networks.py:1340);
+ *   out NHWC [nimg][npix][32]. */
+int dahitra_pixel_decoder(const float* x, const float* pos, const float* tables, const float* dec_pack,
+                          int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up, float* out,
+                          void* stream);
+
+/* Classifier 3x3 conv 32->nc (+bias), NHWC in, NCHW logits out, optional uint8 argmax map
+ * (reference models/networks.py:1249,1355; harness argmax models/evaluator.py:89-92). */
+int dahitra_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* bias,
+                       float* logits, unsigned char* argmax_u8, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAHITRA_B200_H */

@@ -1,0 +1,89 @@
+"""Test helper: call the per-kernel C-ABI entry points with torch CUDA tensors (NHWC fp32)."""
+import torch
+
+from dahitra_b200 import _lib
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def conv2d(in0, in1, w, bias, res, relu, K, stride, pad, up=1, flags=0):
+    lib = _lib.load()
+    N, inH, inW, C0 = in0.shape
+    C1 = 0 if in1 is None else in1.shape[-1]
+    Cout = w.shape[1]
+    H, W = inH * up, inW * up
+    OH, OW = (H + 2 * pad - K) // stride + 1, (W + 2 * pad - K) // stride + 1
+    out = torch.empty((N, OH, OW, Cout), device=in0.device, dtype=torch.float32)
+    rc = lib.dahitra_conv2d(_p(in0), _p(in1), C0, C1, N, inH, inW, up, K, K, stride, pad, Cout, _p(w), _p(bias), _p(res),
+                            int(relu), _p(out), flags, _stream())
+    _lib.check(rc, "dahitra_conv2d")
+    return out
+
+
+def stem(x, w, b):
+    lib = _lib.load()
+    N, _, H, W = x.shape
+    out = torch.empty((N, H // 2, W // 2, 64), device=x.device, dtype=torch.float32)
+    _lib.check(lib.dahitra_stem(_p(x), 3 * H * W, N, H, W, _p(w), _p(b), _p(out), _stream()), "dahitra_stem")
+    return out
+
+
+def maxpool(x):
+    lib = _lib.load()
+    N, H, W, C = x.shape
+    out = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), device=x.device, dtype=torch.float32)
+    _lib.check(lib.dahitra_maxpool3x3s2(_p(x), N, H, W, C, _p(out), _stream()), "dahitra_maxpool3x3s2")
+    return out
+
+
+def squeeze_tokens(feat, wsq, wtok):
+    lib = _lib.load()
+    N, npix, Cin = feat.shape
+    nchunk = (npix + 127) // 128
+    xs = torch.empty((N, npix, 32), device=feat.device, dtype=torch.float32)
+    parts = torch.empty((N, nchunk, 4, 34), device=feat.device, dtype=torch.float32)
+    _lib.check(lib.dahitra_squeeze_tokens(_p(feat), N, npix, Cin, _p(wsq), _p(wtok), _p(xs), _p(parts), _stream()),
+               "dahitra_squeeze_tokens")
+    return xs, parts
+
+
+def token_encoder(parts, B, enc, heads, add_pos):
+    lib = _lib.load()
+    mem = torch.empty((B, 3, 4, 32), device=parts.device, dtype=torch.float32)
+    _lib.check(lib.dahitra_token_encoder(_p(parts), B, parts.shape[1], _p(enc), heads, int(add_pos), _p(mem), _stream()),
+               "dahitra_token_encoder")
+    return mem
+
+
+def decoder_tables(mem, first_call, ncalls, dec, heads, depth):
+    lib = _lib.load()
+    B = mem.shape[0]
+    tabf = 32 * 4 * heads + 4 * heads + 4 * heads * 32 + 32
+    tab = torch.empty((ncalls * B, depth, tabf), device=mem.device, dtype=torch.float32)
+    _lib.check(lib.dahitra_decoder_tables(_p(mem), B, first_call, ncalls, _p(dec), heads, depth, _p(tab), _stream()),
+               "dahitra_decoder_tables")
+    return tab
+
+
+def pixel_decoder(x, pos, tab, dec, h, w, heads, depth, skip=None, skip_up=1):
+    lib = _lib.load()
+    nimg = x.shape[0]
+    out = torch.empty_like(x)
+    _lib.check(lib.dahitra_pixel_decoder(_p(x), _p(pos), _p(tab), _p(dec), nimg, h, w, heads, depth, _p(skip), skip_up,
+                                         _p(out), _stream()), "dahitra_pixel_decoder")
+    return out
+
+
+def classifier(x, w, b, nc, want_argmax=True):
+    lib = _lib.load()
+    N, H, W, _ = x.shape
+    logits = torch.empty((N, nc, H, W), device=x.device, dtype=torch.float32)
+    am = torch.empty((N, H, W), device=x.device, dtype=torch.uint8) if want_argmax else None
+    _lib.check(lib.dahitra_classifier(_p(x), N, H, W, nc, _p(w), _p(b), _p(logits), _p(am), _stream()), "dahitra_classifier")
+    return logits, am

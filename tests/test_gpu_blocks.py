@@ -1,0 +1,156 @@
+"""GPU: every kernel behind the C ABI against the oracle / an fp64 torch statement of the same op."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import abi
+import emulate as E
+from oracle import dahitra_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def close(a, b, rtol=2e-5, atol=None):
+    a, b = a.double().cpu(), b.double().cpu()
+    atol = (atol if atol is not None else 2e-5 * float(b.abs().max()))
+    bad = (a - b).abs() > atol + rtol * b.abs()
+    assert not bad.any(), f"max|d|={float((a - b).abs().max()):.3e} (ref max {float(b.abs().max()):.3e}), {int(bad.sum())} bad"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale).to(DEV)
+
+
+CONVS = [  # (N, H, W, C0, C1, Cout, K, stride, up, res, relu, bias)
+    (2, 16, 16, 64, 0, 64, 3, 1, 1, True, True, True),       # layer1 block conv2
+    (1, 32, 32, 64, 0, 128, 3, 2, 1, False, True, True),     # layer2.0.conv1 (stride 2)
+    (1, 32, 32, 64, 0, 128, 1, 2, 1, False, False, True),    # layer2.0 downsample
+    (2, 16, 16, 128, 0, 256, 1, 1, 1, False, False, True),   # layer3.0 downsample
+    (1, 16, 16, 256, 0, 256, 3, 1, 1, True, True, True),     # layer3
+    (2, 16, 16, 32, 32, 32, 3, 1, 1, False, False, False),   # conv_decode on a virtual concat
+    (1, 16, 32, 32, 0, 32, 3, 1, 2, False, True, True),      # conv_layerN on a virtually upsampled input
+    (1, 32, 32, 64, 64, 128, 3, 1, 1, False, True, True),    # conv_layer2_0.0
+    (1, 32, 32, 128, 0, 32, 3, 1, 1, True, False, True),     # conv_layer2_0.3 + out_3
+    (1, 20, 28, 32, 0, 64, 3, 1, 1, False, True, True),      # ragged: not a multiple of the 8x16 tile
+    (1, 7, 9, 32, 0, 32, 3, 2, 1, False, False, False),      # ragged + stride 2
+]
+
+
+@pytest.mark.parametrize("cfg", CONVS)
+def test_conv2d(cfg):
+    N, H, W, C0, C1, Cout, K, stride, up, res, relu, bias = cfg
+    x0 = rnd(N, H, W, C0, seed=1)
+    x1 = rnd(N, H, W, C1, seed=2) if C1 else None
+    w = rnd(K * K * (C0 + C1), Cout, seed=3, scale=(K * K * (C0 + C1)) ** -0.5)
+    b = rnd(Cout, seed=4) if bias else None
+    pad = K // 2
+    OH, OW = (H * up + 2 * pad - K) // stride + 1, (W * up + 2 * pad - K) // stride + 1
+    r = rnd(N, OH, OW, Cout, seed=5) if res else None
+    y = abi.conv2d(x0, x1, w, b, r, relu, K, stride, pad, up)
+    xin = x0 if x1 is None else torch.cat([x0, x1], -1)
+    ref = E.conv_nhwc(xin.double(), w.double(), None if b is None else b.double(), K, stride, pad,
+                      None if r is None else r.double(), relu, up)
+    assert y.shape == ref.shape
+    close(y, ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 96, 160), (1, 256, 256)])
+def test_stem(shape):
+    N, H, W = shape
+    x = rnd(N, 3, H, W, seed=1)
+    w = rnd(147, 64, seed=2, scale=147 ** -0.5)
+    b = rnd(64, seed=3)
+    y = abi.stem(x, w, b)
+    close(y, E.stem(x.double(), w.double(), b.double()))
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64), (1, 18, 30, 128)])
+def test_maxpool_bit_exact(shape):
+    x = rnd(*shape, seed=1)
+    y = abi.maxpool(x)
+    assert torch.equal(y, E.maxpool(x))
+
+
+@pytest.mark.parametrize("k,npix", [(5, 256), (4, 1024), (3, 4096), (3, 1000)])
+def test_tokens_and_encoder(k, npix, levir_template):
+    """squeeze + spatial-softmax tokenizer + 1-layer encoder vs the oracle (networks.py:1273-1286)."""
+    from dahitra_b200.engine import prepare_weights
+    sd = synth.synth_state_dict(levir_template, seed=3, style="default")
+    P = {n: (None if v is None else v.to(DEV)) for n, v in prepare_weights(sd, 0, 2).items()}
+    cin, heads = O.LEVELS[k]["cin"], O.LEVELS[k]["heads"]
+    B = 3
+    h = npix // 8 if npix == 1000 else int(npix ** 0.5)
+    w = npix // h
+    feat = F.relu(rnd(2 * B, npix, cin, seed=7))
+    s = f"DH_W_LV{k}_"
+    xs, parts = abi.squeeze_tokens(feat, P[s + "SQ"], P[s + "TOK"])
+    mem = abi.token_encoder(parts, B, P[s + "ENC"], heads, True)
+    f = feat.cpu().double().transpose(1, 2).reshape(2 * B, cin, h, w)
+    xs_ref = O.squeeze(sd, f, k, torch.float64)
+    close(xs, xs_ref.flatten(2).transpose(1, 2))
+    tok = torch.cat([O.semantic_tokens(sd, xs_ref[:B], k, torch.float64), O.semantic_tokens(sd, xs_ref[B:], k, torch.float64)], 1)
+    tok = O.token_encoder(sd, tok, k, torch.float64)
+    ref = torch.stack([tok[:, :4], tok[:, 4:], (tok[:, 4:] - tok[:, :4]).abs()], 1)
+    close(mem, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("k,h,w", [(5, 16, 16), (4, 32, 32), (3, 64, 64), (3, 24, 40)])
+def test_pixel_decoder(k, h, w, levir_template):
+    """tables + streaming decoder vs TransformerDecoder as written (help_funcs.py:66-114,170-186)."""
+    from dahitra_b200.engine import prepare_weights
+    sd = dict(synth.synth_state_dict(levir_template, seed=3, style="default"))
+    heads, depth = O.LEVELS[k]["heads"], O.LEVELS[k]["depth"]
+    pos_nchw = torch.randn(1, 32, h, w, generator=torch.Generator().manual_seed(5))
+    sd[f"pos_embedding_decoder_{k}"] = pos_nchw
+    P = {n: (None if v is None else v.to(DEV)) for n, v in prepare_weights(sd, 0, 2).items()}
+    B = 2
+    x = rnd(B, h * w, 32, seed=8)
+    mem = rnd(B, 3, 4, 32, seed=9)
+    s = f"DH_W_LV{k}_"
+    tab = abi.decoder_tables(mem, 0, 3, P[s + "DEC"], heads, depth)
+    xn = x.cpu().double().transpose(1, 2).reshape(B, 32, h, w)
+    for call in range(3):
+        y = abi.pixel_decoder(x, P[s + "POS"], tab[call * B:(call + 1) * B].contiguous(), P[s + "DEC"], h, w, heads, depth)
+        ref = O.pixel_decoder(sd, xn, mem[:, call].cpu().double(), k, torch.float64)
+        close(y, ref.flatten(2).transpose(1, 2), rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
+    # skip hooks: x2-upsampled coarser map, and same-size map
+    if h % 2 == 0 and w % 2 == 0:
+        sk = rnd(B, h // 2, w // 2, 32, seed=10)
+        y2 = abi.pixel_decoder(x, P[s + "POS"], tab[:B].contiguous(), P[s + "DEC"], h, w, heads, depth, sk, 2)
+        y1 = abi.pixel_decoder(x, P[s + "POS"], tab[:B].contiguous(), P[s + "DEC"], h, w, heads, depth)
+        up = sk.repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(B, h * w, 32)
+        assert torch.equal(y2, y1 + up)
+    sk = rnd(B, h, w, 32, seed=11)
+    y3 = abi.pixel_decoder(x, None, tab[:B].contiguous(), P[s + "DEC"], h, w, heads, depth, sk, 1)
+    y0 = abi.pixel_decoder(x, None, tab[:B].contiguous(), P[s + "DEC"], h, w, heads, depth)
+    assert torch.equal(y3, y0 + sk.reshape(B, h * w, 32))
+
+
+@pytest.mark.parametrize("nc", [2, 5])
+def test_classifier_and_argmax(nc):
+    x = rnd(2, 48, 80, 32, seed=1)
+    w = rnd(9, nc, 32, seed=2, scale=0.1)
+    b = rnd(nc, seed=3, scale=0.1)
+    logits, am = abi.classifier(x, w, b, nc)
+    wt = w.reshape(3, 3, nc, 32).permute(2, 3, 0, 1).double()
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), wt, b.double(), 1, 1)
+    close(logits, ref)
+    assert torch.equal(am.long(), logits.argmax(1))        # the fused map is the argmax of the logits it wrote
+
+
+def test_argument_errors():
+    from dahitra_b200 import _lib
+    lib = _lib.load()
+    x = rnd(1, 8, 8, 48, seed=1)                           # 48 channels: not a multiple of 32
+    w = rnd(9 * 48, 32, seed=2)
+    out = torch.empty(1, 8, 8, 32, device=DEV)
+    rc = lib.dahitra_conv2d(x.data_ptr(), None, 48, 0, 1, 8, 8, 1, 3, 3, 1, 1, 32, w.data_ptr(), None, None, 0,
+                            out.data_ptr(), 0, None)
+    assert rc == -2
+    rc = lib.dahitra_conv2d(x.data_ptr() + 4, None, 32, 0, 1, 8, 8, 1, 3, 3, 1, 1, 32, w.data_ptr(), None, None, 0,
+                            out.data_ptr(), 0, None)
+    assert rc == -3
+    with pytest.raises(RuntimeError, match="code -2"):
+        _lib.check(-2, "x")

@@ -1,0 +1,105 @@
+"""CPU: host-side logic — weight preparation algebra, the C-ABI library surface, module behaviour without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import emulate as E
+from oracle import dahitra_oracle as O
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dahitra_b200 import _lib
+    if _lib.needs_build():
+        _lib.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "dahitra_b200.h")).read()
+    declared = set(re.findall(r"\b(dahitra_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 13
+    from dahitra_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dahitra_version() == 1
+    assert b"ok" == lib.dahitra_error_string(0)
+    assert b"workspace" in lib.dahitra_error_string(-4)
+
+
+def test_slot_table_matches_preparation(lib, levir_template):
+    from dahitra_b200.engine import slot_names, prepare_weights
+    names = slot_names()
+    assert names[0] == "DH_W_STEM_W" and names[-1] == "DH_W_CLS_B" and len(names) == len(set(names))
+    P = prepare_weights(levir_template, 0, 2)
+    assert set(P) == set(names)
+    assert P["DH_W_LV3_ENC"].numel() == 8 * 32 + 64 + 2 * 8 * 1024 + 32 + 64 + 1024 + 32 + 1024 + 32
+    assert P["DH_W_LV5_DEC"].numel() == 4 * (64 + 2 * 4 * 1024 + 32 + 1024 + 32 + 1024 + 32)
+
+
+def test_workspace_and_argument_checks_without_gpu(lib):
+    assert lib.dahitra_workspace_bytes(0, 1, 256, 256, 2, 0) > 0
+    assert lib.dahitra_workspace_bytes(0, 1, 250, 256, 2, 0) == 0         # not a multiple of 32
+    assert lib.dahitra_workspace_bytes(7, 1, 256, 256, 2, 0) == 0         # unknown variant
+    big = lib.dahitra_workspace_bytes(1, 8, 1024, 1024, 5, 0)
+    assert 1 << 30 < big < 40 << 30
+    # host-side validation happens before any CUDA call, so these are safe on a GPU-less box
+    rc = lib.dahitra_forward(None, 60, None, None, 0, None, None, None, 0, 0, 1, 256, 256, 2, 0, None)
+    assert rc == -1
+    rc = lib.dahitra_conv2d(None, None, 32, 0, 1, 8, 8, 1, 3, 3, 1, 1, 32, None, None, None, 0, None, 0, None)
+    assert rc == -1
+
+
+def test_module_refuses_cpu_inference(levir_template):
+    from dahitra_b200.networks import BASE_Transformer_UNet
+    net = BASE_Transformer_UNet(3, 2, 'learned', resnet_stages_num=4, with_decoder_pos='learned', enc_depth=1, dec_depth=8).eval()
+    x = torch.zeros(1, 3, 256, 256)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        net(x, x)
+
+
+def test_define_G_scope():
+    from dahitra_b200.networks import define_G
+
+    class A:
+        net_G = "base_resnet18"
+    with pytest.raises(NotImplementedError):
+        define_G(A())
+
+
+@pytest.mark.parametrize("variant", ["levir"])
+def test_prepared_weights_algebra_matches_oracle(variant, levir_template):
+    """Runs the kernels' algebra (collapsed attention, folded BN/LN, re-laid-out filters) in torch fp64 on the
+    prepared packs and compares with the fp64 oracle: validates engine.prepare_weights end to end."""
+    from dahitra_b200.engine import prepare_weights
+    sd = synth.synth_state_dict(levir_template, seed=3, style="default")
+    P = {k: (None if v is None else v.double()) for k, v in prepare_weights(sd, 0, 2).items()}
+    x1, x2 = synth.synth_pair(1, 256, 256, seed=2, kind="uniform")
+    y = O.forward_levir(sd, x1, x2, dtype=torch.float64)
+    e = E.forward(P, x1.double(), x2.double(), "levir", 2)
+    # packs are stored in fp32: expect ~1e-6 relative, nothing structural
+    assert float((y - e).abs().max()) < 5e-5 * float(y.abs().max())
+
+
+def test_prepared_weights_algebra_xbd():
+    from dahitra_b200.engine import prepare_weights
+    from dahitra_b200.xbd import BASE_Transformer_UNet as X
+    net = X(input_nc=3, output_nc=5, token_len=4, resnet_stages_num=4, with_pos="learned",
+            with_decoder_pos="learned", enc_depth=1, dec_depth=8)
+    # run at 256x256 with the H/16-level embedding cropped to 16x16: the xBD variant itself only runs at 1024^2
+    sd = synth.synth_state_dict(net.state_dict(), seed=6, style="default")
+    sd = dict(sd)
+    sd["pos_embedding_decoder_3"] = sd["pos_embedding_decoder_3"][:, :, :16, :16].contiguous()
+    P = {k: (None if v is None else v.double()) for k, v in prepare_weights(sd, 1, 5).items()}
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(1, 6, 256, 256, generator=g) * 2 - 1
+    y = O.forward_xbd(sd, x, dtype=torch.float64)
+    e = E.forward(P, x[:, :3].double(), x[:, 3:].double(), "xbd", 5)
+    assert float((y - e).abs().max()) < 5e-5 * float(y.abs().max())
