@@ -44,10 +44,14 @@ struct ConvArgs {
   const float* in0; const float* in1; int C0, C1;
   int N, inH, inW, up;           // stored input size; `up`=2 => virtual nearest x2 upsample
   int KH, KW, stride, pad, Cout;
-  const float* w; const float* bias; const float* res; int relu;
+  const float* w;                // [KH*KW*Cin][Cout]  (CUDA-core kernel)
+  const float* wt;               // [Cout][KH*KW*Cin]  (tcgen05 kernel), may be NULL
+  const float* bias; const float* res; int relu;
   float* out;
 };
 int dh_launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
+bool dh_conv_tc_eligible(const ConvArgs& a);
+int dh_launch_conv_tc(const ConvArgs& a, cudaStream_t s);
 int dh_launch_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* b, float* out, cudaStream_t s);
 int dh_launch_maxpool(const float* in, int N, int H, int W, int C, float* out, cudaStream_t s);
 int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* b,

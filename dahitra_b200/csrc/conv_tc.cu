@@ -1,0 +1,305 @@
+// dahitra_b200 — implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a):
+// TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma kind::tf32 -> TMEM accumulator
+// -> tcgen05.ld epilogue with folded-BN bias / residual / ReLU fused, NHWC fp32 in and out.
+//
+// GEMM view (stride-1 convolution, pad = K/2):  D[m][co] = sum_{tap, ci} A_tap[m][ci] * Wt[co][tap*Cin + ci]
+//   M tile  = 128 output pixels = an 8 x 16 spatial patch of one image
+//   N tile  = NT output channels (32 / 64 / 128)
+//   K step  = 32 input channels of one filter tap (32 fp32 = 128 B = one swizzle row)
+// A_tap is never materialised: for tap (r, s) the A tile is the 8x16 input patch shifted by (r-pad, s-pad),
+// fetched by ONE 4-D TMA box {32 ch, 16, 8, 1} over the NHWC tensor.  Out-of-image coordinates (the zero
+// padding, and ragged tile edges) are zero-filled by the TMA unit, so there is no im2col buffer, no halo
+// logic and no predication in the main loop.  The virtual channel concat of two tensors (conv_decode,
+// conv_layer2_0) is two tensor maps.  The filter is a 2-D K-major tensor [Cout][K] (box {32, NT}).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (each owns the 32 TMEM lanes matching warp_id % 4).
+// Pipeline: STAGES-deep smem ring with full/empty mbarriers; tcgen05.commit releases a stage when the MMAs
+// that read it have retired, and signals the epilogue after the last K step.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+constexpr int TC_TH = 8, TC_TW = 16;          // output patch
+constexpr int TC_M = TC_TH * TC_TW;            // 128 rows
+constexpr uint32_t TC_A_BYTES = TC_M * 128;    // 16 KB per stage
+
+struct TcEpilogue {
+  const float* bias; const float* res; float* out;
+  int OH, OW, Cout, relu, tilesX, nsteps, cchunks0, cchunks, KW, pad, Cin;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline that cannot make progress (bad tensor map, lost arrive) traps after a few seconds
+// instead of hanging the GPU; the launch then reports cudaErrorLaunchFailure to the caller.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, SWIZZLE_128B operand descriptor: 8-row atoms of 1024 B (SBO = 1024), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int NT> struct TcCfg {
+  static constexpr int STAGES = (NT == 128) ? 3 : (NT == 64 ? 4 : 5);      // ~96-100 KB -> 2 CTAs per SM
+  static constexpr uint32_t B_BYTES = NT * 128;
+  static constexpr uint32_t STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024;             // + slack for the 1024 B alignment
+  // instruction descriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7 and 10), K-major both, N>>3 at 17, M>>4 at 24
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+};
+
+template <int NT>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB, const TcEpilogue e) {
+  using Cfg = TcCfg<NT>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t tc_smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  const int n = blockIdx.z;
+  const int n0 = blockIdx.y * NT;
+  const int oy0 = (blockIdx.x / e.tilesX) * TC_TH, ox0 = (blockIdx.x % e.tilesX) * TC_TW;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(&accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {   // TMEM: NT fp32 accumulator columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)NT) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                                          // ---------------- TMA producer
+      for (int ks = 0; ks < e.nsteps; ++ks) {
+        const int st = ks % STAGES, round = ks / STAGES;
+        mbar_wait(smem_u32(&empty_bar[st]), (round & 1) ^ 1);
+        const int tap = ks / e.cchunks, cc = ks - tap * e.cchunks;
+        const int r = tap / e.KW, s = tap - r * e.KW;
+        const uint32_t a_dst = tiles + st * Cfg::STAGE_BYTES, b_dst = a_dst + TC_A_BYTES;
+        const uint32_t bar = smem_u32(&full_bar[st]);
+        mbar_expect_tx(bar, Cfg::STAGE_BYTES);
+        if (cc < e.cchunks0) tma_load_4d(a_dst, &tmA0, bar, cc * 32, ox0 + s - e.pad, oy0 + r - e.pad, n);
+        else                 tma_load_4d(a_dst, &tmA1, bar, (cc - e.cchunks0) * 32, ox0 + s - e.pad, oy0 + r - e.pad, n);
+        tma_load_2d(b_dst, &tmB, bar, tap * e.Cin + cc * 32, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                          // ---------------- MMA issuer
+      for (int ks = 0; ks < e.nsteps; ++ks) {
+        const int st = ks % STAGES, round = ks / STAGES;
+        mbar_wait(smem_u32(&full_bar[st]), round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = tiles + st * Cfg::STAGE_BYTES;
+        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + TC_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzle row
+          umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::IDESC, (ks | k) ? 1u : 0u);
+        umma_commit(smem_u32(&empty_bar[st]));                // frees the stage once these MMAs have read it
+      }
+      umma_commit(smem_u32(&accum_bar));                      // accumulator complete
+    }
+  } else {                                                    // ---------------- epilogue (warps 2..5)
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    const int oy = oy0 + m / TC_TW, ox = ox0 + m % TC_TW;
+    const bool valid = (oy < e.OH) && (ox < e.OW);
+    mbar_wait(smem_u32(&accum_bar), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const size_t row = ((size_t)(n * e.OH + oy) * e.OW + ox) * e.Cout + n0;
+#pragma unroll 1
+    for (int j = 0; j < NT / 32; ++j) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+      if (valid) {
+        float* op = e.out + row + j * 32;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 o = make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
+                                 __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+          if (e.bias) { const float4 b = ldg4(e.bias + n0 + j * 32 + c4 * 4); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+          if (e.res) { const float4 rr = ldg4(e.res + row + j * 32 + c4 * 4); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+          if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          st4(op + c4 * 4, o);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)NT) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int d0, d1, d2, d3, b1, b2;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && b1 == o.b1 && b2 == o.b2;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.ptr;
+    for (int v : {k.d0, k.d1, k.d2, k.d3, k.b1, k.b2}) h = h * 1000003u ^ (size_t)v;
+    return h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// NHWC activation map: dims (C, W, H, N), box (32, 16, 8, 1).  rank-2 filter map: dims (K, Cout), box (32, NT).
+int get_map(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d2, int d3, int b1, int b2) {
+  MapKey key{ptr, d0, d1, d2, d3, b1, b2};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return DH_E_VARIANT;
+  cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)d3};
+  cuuint64_t strides[3] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4, (cuuint64_t)d0 * d1 * d2 * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)b1, (cuuint32_t)b2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)ptr, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return DH_E_SHAPE;
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = m;
+  }
+  *out = m;
+  return 0;
+}
+
+template <int NT>
+int launch(const ConvArgs& a, const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const TcEpilogue& e,
+           dim3 grid, cudaStream_t s) {
+  cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<NT>::SMEM);
+  if (err != cudaSuccess) return (int)err;
+  conv_tc_kernel<NT><<<grid, 192, TcCfg<NT>::SMEM, s>>>(A0, A1, Bm, e);
+  DH_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+bool dh_conv_tc_eligible(const ConvArgs& a) {
+  return a.wt != nullptr && a.stride == 1 && a.up == 1 && a.KH == a.KW && (a.KH == 1 || a.KH == 3) && a.pad == a.KH / 2 &&
+         a.C0 > 0 && a.C0 % 32 == 0 && a.C1 % 32 == 0 && (a.Cout == 32 || a.Cout == 64 || a.Cout == 128 || a.Cout == 256) &&
+         a.inH >= 1 && a.inW >= 1;
+}
+
+int dh_launch_conv_tc(const ConvArgs& a, cudaStream_t s) {
+  DH_REQUIRE(a.in0 && a.wt && a.out, DH_E_NULL);
+  DH_REQUIRE(a.C1 == 0 || a.in1, DH_E_NULL);
+  DH_REQUIRE(dh_conv_tc_eligible(a), DH_E_SHAPE);
+  DH_REQUIRE(dh_aligned16(a.in0) && dh_aligned16(a.in1) && dh_aligned16(a.wt) && dh_aligned16(a.out) &&
+             dh_aligned16(a.bias) && dh_aligned16(a.res), DH_E_ALIGN);
+  const int Cin = a.C0 + a.C1, K = a.KH * a.KW * Cin;
+  const int NT = a.Cout >= 128 ? 128 : a.Cout;
+  CUtensorMap A0, A1, Bm;
+  int rc = get_map(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, TC_TW, TC_TH);
+  if (rc) return rc;
+  if (a.C1) { rc = get_map(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, TC_TW, TC_TH); if (rc) return rc; } else A1 = A0;
+  rc = get_map(&Bm, a.wt, 2, K, a.Cout, 1, 1, NT, 1);
+  if (rc) return rc;
+  TcEpilogue e;
+  e.bias = a.bias; e.res = a.res; e.out = a.out;
+  e.OH = a.inH; e.OW = a.inW; e.Cout = a.Cout; e.relu = a.relu;
+  e.tilesX = dh_cdiv(a.inW, TC_TW);
+  e.cchunks0 = a.C0 / 32; e.cchunks = Cin / 32; e.nsteps = a.KH * a.KW * e.cchunks;
+  e.KW = a.KW; e.pad = a.pad; e.Cin = Cin;
+  dim3 grid(e.tilesX * dh_cdiv(a.inH, TC_TH), a.Cout / NT, a.N);
+  switch (NT) {
+    case 128: return launch<128>(a, A0, A1, Bm, e, grid, s);
+    case 64: return launch<64>(a, A0, A1, Bm, e, grid, s);
+    default: return launch<32>(a, A0, A1, Bm, e, grid, s);
+  }
+}

@@ -78,7 +78,28 @@ const char* kSlotNames[DH_W_COUNT] = {
   "DH_W_LV4_SQ", "DH_W_LV4_TOK", "DH_W_LV4_ENC", "DH_W_LV4_DEC", "DH_W_LV4_POS", "DH_W_LV4_DECODE",
   "DH_W_LV3_SQ", "DH_W_LV3_TOK", "DH_W_LV3_ENC", "DH_W_LV3_DEC", "DH_W_LV3_POS", "DH_W_LV3_DECODE",
   "DH_W_CL4_W", "DH_W_CL4_B", "DH_W_CL3_W", "DH_W_CL3_B", "DH_W_CL2_W", "DH_W_CL2_B",
-  "DH_W_CL20A_W", "DH_W_CL20A_B", "DH_W_CL20B_W", "DH_W_CL20B_B", "DH_W_CLS_W", "DH_W_CLS_B"};
+  "DH_W_CL20A_W", "DH_W_CL20A_B", "DH_W_CL20B_W", "DH_W_CL20B_B", "DH_W_CLS_W", "DH_W_CLS_B",
+  "DH_W_L1_0_C1_WT", "DH_W_L1_0_C2_WT", "DH_W_L1_1_C1_WT", "DH_W_L1_1_C2_WT",
+  "DH_W_L2_0_C2_WT", "DH_W_L2_1_C1_WT", "DH_W_L2_1_C2_WT",
+  "DH_W_L3_0_C1_WT", "DH_W_L3_0_C2_WT", "DH_W_L3_0_DS_WT", "DH_W_L3_1_C1_WT", "DH_W_L3_1_C2_WT",
+  "DH_W_LV5_DECODE_WT", "DH_W_LV4_DECODE_WT", "DH_W_LV3_DECODE_WT", "DH_W_CL20A_WT", "DH_W_CL20B_WT"};
+
+// filter slot -> slot of its K-major copy (or -1)
+int wt_slot_of(int wslot) {
+  switch (wslot) {
+    case DH_W_L1_0_C1_W: return DH_W_L1_0_C1_WT; case DH_W_L1_0_C2_W: return DH_W_L1_0_C2_WT;
+    case DH_W_L1_1_C1_W: return DH_W_L1_1_C1_WT; case DH_W_L1_1_C2_W: return DH_W_L1_1_C2_WT;
+    case DH_W_L2_0_C2_W: return DH_W_L2_0_C2_WT; case DH_W_L2_1_C1_W: return DH_W_L2_1_C1_WT;
+    case DH_W_L2_1_C2_W: return DH_W_L2_1_C2_WT;
+    case DH_W_L3_0_C1_W: return DH_W_L3_0_C1_WT; case DH_W_L3_0_C2_W: return DH_W_L3_0_C2_WT;
+    case DH_W_L3_0_DS_W: return DH_W_L3_0_DS_WT; case DH_W_L3_1_C1_W: return DH_W_L3_1_C1_WT;
+    case DH_W_L3_1_C2_W: return DH_W_L3_1_C2_WT;
+    case DH_W_LV5_DECODE: return DH_W_LV5_DECODE_WT; case DH_W_LV4_DECODE: return DH_W_LV4_DECODE_WT;
+    case DH_W_LV3_DECODE: return DH_W_LV3_DECODE_WT;
+    case DH_W_CL20A_W: return DH_W_CL20A_WT; case DH_W_CL20B_W: return DH_W_CL20B_WT;
+    default: return -1;
+  }
+}
 
 }  // namespace
 
@@ -115,14 +136,14 @@ extern "C" size_t dahitra_workspace_bytes(int variant, int B, int H, int W, int 
 // C ABI — per-kernel entry points
 // ----------------------------------------------------------------------------------------------------
 static int conv_dispatch(const ConvArgs& a, int flags, cudaStream_t s) {
-  (void)flags;   // DH_FLAG_CONV_TC routing is added with conv_tc.cu
+  if ((flags & DH_FLAG_CONV_TC) && dh_conv_tc_eligible(a)) return dh_launch_conv_tc(a, s);
   return dh_launch_conv_ffma(a, s);
 }
 
 extern "C" int dahitra_conv2d(const float* in0, const float* in1, int C0, int C1, int N, int inH, int inW, int up,
-                              int KH, int KW, int stride, int pad, int Cout, const float* w, const float* bias,
-                              const float* res, int relu, float* out, int flags, void* stream) {
-  ConvArgs a{in0, in1, C0, C1, N, inH, inW, up, KH, KW, stride, pad, Cout, w, bias, res, relu, out};
+                              int KH, int KW, int stride, int pad, int Cout, const float* w, const float* wt,
+                              const float* bias, const float* res, int relu, float* out, int flags, void* stream) {
+  ConvArgs a{in0, in1, C0, C1, N, inH, inW, up, KH, KW, stride, pad, Cout, w, wt, bias, res, relu, out};
   return conv_dispatch(a, flags, (cudaStream_t)stream);
 }
 extern "C" int dahitra_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* bias,
@@ -212,8 +233,9 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
   // conv launch + its algorithmic cost (2*MACs as written; one read of the stored inputs/weights, one write)
   auto conv = [&](const char* name, const float* in0, const float* in1, int C0, int C1, int N, int inH, int inW, int up,
                   int K, int stride, int Cout, int wslot, int bslot, const float* res, int relu, float* out) -> int {
-    ConvArgs a{in0, in1, C0, C1, N, inH, inW, up, K, K, stride, K / 2, Cout, Wt(wslot), bslot >= 0 ? Wt(bslot) : nullptr,
-               res, relu, out};
+    const int wts = wt_slot_of(wslot);
+    ConvArgs a{in0, in1, C0, C1, N, inH, inW, up, K, K, stride, K / 2, Cout, Wt(wslot), wts >= 0 ? Wt(wts) : nullptr,
+               bslot >= 0 ? Wt(bslot) : nullptr, res, relu, out};
     const int rc = conv_dispatch(a, flags, s);
     if (rc != 0) return rc;
     const double OH = (double)(inH * up) / stride, OW = (double)(inW * up) / stride, Cin = C0 + C1;

@@ -62,10 +62,16 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
     sd = {k: v.detach().cpu() for k, v in sd.items()}
     P = {}
 
+    tc_slots = {"DH_W_L1_0_C1", "DH_W_L1_0_C2", "DH_W_L1_1_C1", "DH_W_L1_1_C2", "DH_W_L2_0_C2", "DH_W_L2_1_C1",
+                "DH_W_L2_1_C2", "DH_W_L3_0_C1", "DH_W_L3_0_C2", "DH_W_L3_0_DS", "DH_W_L3_1_C1", "DH_W_L3_1_C2",
+                "DH_W_CL20A", "DH_W_CL20B"}
+
     def put_conv(slot, conv, bn):
         w, b = _fold_conv_bn(sd, conv, bn)
         P[slot + "_W"] = _khwc(w)
         P[slot + "_B"] = b
+        if slot in tc_slots:
+            P[slot + "_WT"] = _khwc(w).T.contiguous()          # [Cout][KH*KW*Cin], K-major B operand of tcgen05.mma
 
     put_conv("DH_W_STEM", "resnet.conv1", "resnet.bn1")
     for li in (1, 2, 3):
@@ -80,6 +86,7 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
         P[s + "SQ"] = sd[f"conv_squeeze_{k}.0.weight"].double()[:, :, 0, 0].T          # [Cin][32]
         P[s + "TOK"] = sd[f"conv_token_{k}.weight"].double()[:, :, 0, 0].T             # [32][4]
         P[s + "DECODE"] = _khwc(sd[f"conv_decode_{k}.weight"].double())
+        P[s + "DECODE_WT"] = P[s + "DECODE"].T.contiguous()
         # ---- token encoder pack
         t = f"transformer_{k}.layers.0"
         if variant == DH_VARIANT_LEVIR:

@@ -70,6 +70,13 @@ enum dh_weight_slot {
   DH_W_CL20A_W, DH_W_CL20A_B,                      /* conv_layer2_0.0 + BN: [9*128][128],[128] */
   DH_W_CL20B_W, DH_W_CL20B_B,                      /* conv_layer2_0.3: [9*128][32],[32] */
   DH_W_CLS_W, DH_W_CLS_B,                          /* classifier: [9][output_nc][32], [output_nc] */
+  /* K-major ("[Cout][KH*KW*Cin]") copies of the filters the tcgen05 kernel takes as its B operand
+   * (stride-1 convolutions with Cin a multiple of 32); same values as the matching _W / _DECODE slot */
+  DH_W_L1_0_C1_WT, DH_W_L1_0_C2_WT, DH_W_L1_1_C1_WT, DH_W_L1_1_C2_WT,
+  DH_W_L2_0_C2_WT, DH_W_L2_1_C1_WT, DH_W_L2_1_C2_WT,
+  DH_W_L3_0_C1_WT, DH_W_L3_0_C2_WT, DH_W_L3_0_DS_WT, DH_W_L3_1_C1_WT, DH_W_L3_1_C2_WT,
+  DH_W_LV5_DECODE_WT, DH_W_LV4_DECODE_WT, DH_W_LV3_DECODE_WT,
+  DH_W_CL20A_WT, DH_W_CL20B_WT,
   DH_W_COUNT
 };
 
@@ -125,11 +132,15 @@ int dahitra_forward_profiled(const void* const* weights, int n_weights,
  *   in0/in1   NHWC sources forming a virtual channel concat [in0 (C0) | in1 (C1)], C1 may be 0 (in1 NULL)
  *   up        1, or 2 = the input is virtually nearest-upsampled x2 first (nn.Upsample, networks.py:1102)
  *   w         [KH*KW*(C0+C1)][Cout], bias [Cout] or NULL, res NHWC [N][OH][OW][Cout] or NULL
+ *   wt        K-major copy of the filter, [Cout][KH*KW*(C0+C1)], or NULL.  With flags & DH_FLAG_CONV_TC and a
+ *             non-NULL wt, stride-1 un-upsampled convolutions (KH=KW in {1,3}, pad=KH/2, Cout in
+ *             {32,64,128,256}) run on the tcgen05/TMEM/TMA implicit-GEMM kernel (TF32 operands, fp32
+ *             accumulate); everything else runs on the fp32 CUDA-core kernel.
  *   C0, C1 multiples of 32; Cout multiple of 32.
  */
 int dahitra_conv2d(const float* in0, const float* in1, int C0, int C1, int N, int inH, int inW, int up,
                    int KH, int KW, int stride, int pad, int Cout,
-                   const float* w, const float* bias, const float* res, int relu,
+                   const float* w, const float* wt, const float* bias, const float* res, int relu,
                    float* out, int flags, void* stream);
 
 /* Stem: 7x7 stride-2 pad-3 conv 3->64 + folded BN + ReLU, NCHW planes in, NHWC out

@@ -20,8 +20,9 @@ def conv2d(in0, in1, w, bias, res, relu, K, stride, pad, up=1, flags=0):
     H, W = inH * up, inW * up
     OH, OW = (H + 2 * pad - K) // stride + 1, (W + 2 * pad - K) // stride + 1
     out = torch.empty((N, OH, OW, Cout), device=in0.device, dtype=torch.float32)
-    rc = lib.dahitra_conv2d(_p(in0), _p(in1), C0, C1, N, inH, inW, up, K, K, stride, pad, Cout, _p(w), _p(bias), _p(res),
-                            int(relu), _p(out), flags, _stream())
+    wt = w.t().contiguous() if flags else None             # K-major copy for the tcgen05 path
+    rc = lib.dahitra_conv2d(_p(in0), _p(in1), C0, C1, N, inH, inW, up, K, K, stride, pad, Cout, _p(w), _p(wt), _p(bias),
+                            _p(res), int(relu), _p(out), flags, _stream())
     _lib.check(rc, "dahitra_conv2d")
     return out
 

@@ -56,6 +56,43 @@ def test_conv2d(cfg):
     close(y, ref)
 
 
+TC_CONVS = [  # stride-1, un-upsampled shapes the tcgen05 kernel takes: (N, H, W, C0, C1, Cout, K, res, relu, bias)
+    (2, 16, 16, 32, 0, 32, 1, False, False, False),          # smallest: one K step
+    (1, 16, 16, 32, 0, 32, 3, False, False, False),          # 9 taps, zero padding through TMA OOB fill
+    (2, 64, 64, 64, 0, 64, 3, True, True, True),             # layer1 conv2 (+identity, ReLU)
+    (2, 32, 32, 128, 0, 128, 3, True, True, True),           # layer2
+    (2, 16, 16, 128, 0, 256, 1, False, False, True),         # layer3.0 downsample (1x1)
+    (1, 16, 16, 256, 0, 256, 3, True, True, True),           # layer3 (two N tiles, 72 K steps)
+    (2, 32, 32, 32, 32, 32, 3, False, False, False),         # conv_decode on a virtual concat (two tensor maps)
+    (1, 64, 64, 64, 64, 128, 3, False, True, True),          # conv_layer2_0.0
+    (1, 64, 64, 128, 0, 32, 3, True, False, True),           # conv_layer2_0.3 + out_3
+    (1, 20, 28, 32, 0, 64, 3, False, True, True),            # ragged edges
+]
+
+
+@pytest.mark.parametrize("cfg", TC_CONVS)
+def test_conv2d_tcgen05(cfg):
+    """tcgen05/TMEM/TMA implicit GEMM vs fp64: TF32 operands (10-bit mantissa), fp32 accumulate."""
+    N, H, W, C0, C1, Cout, K, res, relu, bias = cfg
+    x0 = rnd(N, H, W, C0, seed=1)
+    x1 = rnd(N, H, W, C1, seed=2) if C1 else None
+    Kt = K * K * (C0 + C1)
+    w = rnd(Kt, Cout, seed=3, scale=Kt ** -0.5)
+    b = rnd(Cout, seed=4) if bias else None
+    r = rnd(N, H, W, Cout, seed=5) if res else None
+    y = abi.conv2d(x0, x1, w, b, r, relu, K, 1, K // 2, 1, flags=1)
+    torch.cuda.synchronize()
+    xin = x0 if x1 is None else torch.cat([x0, x1], -1)
+    ref = E.conv_nhwc(xin.double(), w.double(), None if b is None else b.double(), K, 1, K // 2,
+                      None if r is None else r.double(), relu, 1)
+    d = (y.double().cpu() - ref.cpu()).abs()
+    print(f"[tc] {cfg}: max|d|={float(d.max()):.3e} mean|d|={float(d.mean()):.3e} ref_absmax={float(ref.abs().max()):.3e}")
+    # TF32 rounding of both operands: ~2^-11 relative per product, accumulated over Kt terms of unit-variance data
+    close(y, ref, rtol=2e-3, atol=4e-3)
+    # and it must agree with the fp32 CUDA-core kernel to the same level
+    close(y, abi.conv2d(x0, x1, w, b, r, relu, K, 1, K // 2, 1, flags=0), rtol=2e-3, atol=4e-3)
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 64), (1, 96, 160), (1, 256, 256)])
 def test_stem(shape):
     N, H, W = shape
@@ -146,10 +183,10 @@ def test_argument_errors():
     x = rnd(1, 8, 8, 48, seed=1)                           # 48 channels: not a multiple of 32
     w = rnd(9 * 48, 32, seed=2)
     out = torch.empty(1, 8, 8, 32, device=DEV)
-    rc = lib.dahitra_conv2d(x.data_ptr(), None, 48, 0, 1, 8, 8, 1, 3, 3, 1, 1, 32, w.data_ptr(), None, None, 0,
+    rc = lib.dahitra_conv2d(x.data_ptr(), None, 48, 0, 1, 8, 8, 1, 3, 3, 1, 1, 32, w.data_ptr(), None, None, None, 0,
                             out.data_ptr(), 0, None)
     assert rc == -2
-    rc = lib.dahitra_conv2d(x.data_ptr() + 4, None, 32, 0, 1, 8, 8, 1, 3, 3, 1, 1, 32, w.data_ptr(), None, None, 0,
+    rc = lib.dahitra_conv2d(x.data_ptr() + 4, None, 32, 0, 1, 8, 8, 1, 3, 3, 1, 1, 32, w.data_ptr(), None, None, None, 0,
                             out.data_ptr(), 0, None)
     assert rc == -3
     with pytest.raises(RuntimeError, match="code -2"):

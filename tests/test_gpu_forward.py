@@ -31,10 +31,16 @@ def make_net(sd=None, nc=2):
     return net.to(DEV).eval()
 
 
-def check_logits(y, ref, name, min_agree=0.999):
+def check_logits(y, ref, name, min_agree=0.999, noise_ref=None):
+    """|y - ref| <= 1e-4 + 1e-3 |ref| element-wise.  `noise_ref` (the fp32 oracle = the reference's own fp32
+    arithmetic) widens the absolute term to 3x the reference's own distance from the fp64 truth on
+    ill-conditioned inputs, where no fp32 implementation can meet 1e-4."""
     y, ref = y.double().cpu(), ref.double().cpu()
     d = (y - ref).abs()
-    bad = d > ATOL + RTOL * ref.abs()
+    atol = ATOL
+    if noise_ref is not None:
+        atol = max(ATOL, 3.0 * float((noise_ref.double().cpu() - ref).abs().max()))
+    bad = d > atol + RTOL * ref.abs()
     agree = float((y.argmax(1) == ref.argmax(1)).float().mean())
     print(f"[parity] {name}: max|d|={float(d.max()):.3e} ref_absmax={float(ref.abs().max()):.3e} "
           f"out-of-tol={int(bad.sum())}/{bad.numel()} argmax_agree={agree:.6f}")
@@ -100,8 +106,12 @@ def test_edge_inputs(levir_template):
     with torch.no_grad():
         yz = net(z.to(DEV), z.to(DEV))
         ys = net(x1.to(DEV), x1.clone().to(DEV))
-    check_logits(yz, O.forward_levir(sd, z, z, dtype=torch.float64), "all-zero images")
-    check_logits(ys, O.forward_levir(sd, x1, x1, dtype=torch.float64), "identical pre/post")
+    # constant images make the spatial softmax near-uniform and amplify fp32 rounding: the fp32 oracle itself
+    # is several 1e-4 away from the fp64 one, so it is passed as the yardstick
+    check_logits(yz, O.forward_levir(sd, z, z, dtype=torch.float64), "all-zero images",
+                 noise_ref=O.forward_levir(sd, z, z))
+    check_logits(ys, O.forward_levir(sd, x1, x1, dtype=torch.float64), "identical pre/post",
+                 noise_ref=O.forward_levir(sd, x1, x1))
 
 
 def test_xbd_1024_golden(golden_dir):
@@ -131,7 +141,9 @@ def test_xbd_1024_golden(golden_dir):
     print(f"[parity] xbd 1024: max|d| vs fp64 ref {err:.3e}; reference fp32 noise {noise:.3e}; argmax agree {agree:.6f}")
     assert err <= max(2.0 * noise, ATOL + RTOL * float(ref64.abs().max()))
     assert agree >= 0.999
-    assert float(y.double().sum()) == pytest.approx(float(g["logits_f64ref_sum"]), rel=1e-4, abs=50.0)
+    mean_noise = float((ref32 - ref64).abs().mean())      # ~3.4e-4: the reference's own mean fp32 error here
+    assert float((sub - ref64).abs().mean()) <= 2.0 * mean_noise + 1e-5
+    assert float(y.double().sum()) == pytest.approx(float(g["logits_f64ref_sum"]), rel=2e-3)
     hist = np.bincount(y.argmax(1).flatten().numpy(), minlength=5)
     assert np.abs(hist - g["argmax_hist"]).sum() <= 0.002 * 1024 * 1024
 
@@ -173,6 +185,34 @@ def test_weight_updates_are_seen(levir_template):
         check_logits(yb, O.forward_levir(sd_b, x1.cpu(), x2.cpu(), dtype=torch.float64), "after load_state_dict")
         net.train(); net.eval()
         assert torch.equal(net(x1, x2), yb)
+
+
+@pytest.mark.parametrize("weights", ["defineG", "default"])
+def test_tensor_core_mode(weights, levir_template):
+    """DH_FLAG_CONV_TC: stride-1 convolutions on tcgen05 with TF32 operands (fp32 accumulate, fp32 storage).
+    Separately stated tolerance for this mode: |d| <= 2e-3 * max|ref| element-wise and >= 99.9 % argmax agreement
+    (eager PyTorch with TF32 enabled measures 7.6e-5 / 99.985 % on the define_G init)."""
+    from dahitra_b200.networks import define_G
+    if weights == "defineG":
+        torch.manual_seed(0)
+        net = define_G(Args(), gpu_ids=[0]).eval()
+        sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    else:
+        sd = synth.synth_state_dict(levir_template, seed=3, style="default")
+        net = make_net(sd)
+    net._engine.flags = 1
+    net.invalidate_native_cache()
+    x1, x2 = synth.synth_pair(2, 256, 256, seed=2, kind="uniform")
+    with torch.no_grad():
+        y = net(x1.to(DEV), x2.to(DEV)).double().cpu()
+    ref = O.forward_levir(sd, x1, x2, dtype=torch.float64)
+    d = (y - ref).abs()
+    agree = float((y.argmax(1) == ref.argmax(1)).float().mean())
+    strict_bad = int((d > ATOL + RTOL * ref.abs()).sum())
+    print(f"[parity] TF32 tensor-core mode ({weights}): max|d|={float(d.max()):.3e} ref_absmax={float(ref.abs().max()):.3e} "
+          f"argmax_agree={agree:.6f} outside-strict-fp32-tol={strict_bad}/{d.numel()}")
+    assert float(d.max()) <= 2e-3 * float(ref.abs().max())
+    assert agree >= 0.999
 
 
 def test_shape_errors():

@@ -37,7 +37,11 @@ def test_library_exports_every_declared_symbol(lib):
 def test_slot_table_matches_preparation(lib, levir_template):
     from dahitra_b200.engine import slot_names, prepare_weights
     names = slot_names()
-    assert names[0] == "DH_W_STEM_W" and names[-1] == "DH_W_CLS_B" and len(names) == len(set(names))
+    assert names[0] == "DH_W_STEM_W" and "DH_W_CLS_B" in names and len(names) == len(set(names))
+    hdr = open(os.path.join(ROOT, "include", "dahitra_b200.h")).read()
+    start = hdr.index("enum dh_weight_slot")
+    enum_body = hdr[start:hdr.index("DH_W_COUNT", start)]
+    assert names == re.findall(r"\b(DH_W_[A-Z0-9_]+)\b", re.sub(r"/\*.*?\*/", "", enum_body, flags=re.S))
     P = prepare_weights(levir_template, 0, 2)
     assert set(P) == set(names)
     assert P["DH_W_LV3_ENC"].numel() == 8 * 32 + 64 + 2 * 8 * 1024 + 32 + 64 + 1024 + 32 + 1024 + 32
@@ -53,7 +57,7 @@ def test_workspace_and_argument_checks_without_gpu(lib):
     # host-side validation happens before any CUDA call, so these are safe on a GPU-less box
     rc = lib.dahitra_forward(None, 60, None, None, 0, None, None, None, 0, 0, 1, 256, 256, 2, 0, None)
     assert rc == -1
-    rc = lib.dahitra_conv2d(None, None, 32, 0, 1, 8, 8, 1, 3, 3, 1, 1, 32, None, None, None, 0, None, 0, None)
+    rc = lib.dahitra_conv2d(None, None, 32, 0, 1, 8, 8, 1, 3, 3, 1, 1, 32, None, None, None, None, 0, None, 0, None)
     assert rc == -1
 
 
