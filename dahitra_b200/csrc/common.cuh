@@ -48,6 +48,10 @@ struct ConvArgs {
   const float* wt;               // [Cout][KH*KW*Cin]  (tcgen05 kernel), may be NULL
   const float* bias; const float* res; int relu;
   float* out;
+  // tcgen05 kernel only: "pixel-shuffle" store.  The conv has Cout = 4*32 channels = 4 output-pixel phases of
+  // a nearest-x2-upsampled 3x3 conv (see engine.py: upsample_phase_filter); block j of 32 channels goes to
+  // output pixel (2*oy + j/2, 2*ox + j%2) of a [N][2*inH][2*inW][32] tensor.
+  int ps = 0;
 };
 int dh_launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
 bool dh_conv_tc_eligible(const ConvArgs& a);

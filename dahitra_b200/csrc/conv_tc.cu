@@ -30,6 +30,8 @@ constexpr uint32_t TC_A_BYTES = TC_M * 128;    // 16 KB per stage
 struct TcEpilogue {
   const float* bias; const float* res; float* out;
   int OH, OW, Cout, relu, tilesX, nsteps, cchunks0, cchunks, KW, pad, Cin;
+  int stride;   // 1 or 2: the A tensor maps then carry elementStrides {1,s,s,1} and a box of 16s x 8s input pixels
+  int ps;       // pixel-shuffle store (ConvArgs::ps)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,8 +144,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t a_dst = tiles + st * Cfg::STAGE_BYTES, b_dst = a_dst + TC_A_BYTES;
         const uint32_t bar = smem_u32(&full_bar[st]);
         mbar_expect_tx(bar, Cfg::STAGE_BYTES);
-        if (cc < e.cchunks0) tma_load_4d(a_dst, &tmA0, bar, cc * 32, ox0 + s - e.pad, oy0 + r - e.pad, n);
-        else                 tma_load_4d(a_dst, &tmA1, bar, (cc - e.cchunks0) * 32, ox0 + s - e.pad, oy0 + r - e.pad, n);
+        const int ix = ox0 * e.stride + s - e.pad, iy = oy0 * e.stride + r - e.pad;
+        if (cc < e.cchunks0) tma_load_4d(a_dst, &tmA0, bar, cc * 32, ix, iy, n);
+        else                 tma_load_4d(a_dst, &tmA1, bar, (cc - e.cchunks0) * 32, ix, iy, n);
         tma_load_2d(b_dst, &tmB, bar, tap * e.Cin + cc * 32, n0);
       }
     }
@@ -176,6 +179,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
       if (valid) {
         float* op = e.out + row + j * 32;
+        if (e.ps)   // channel block j = output-pixel phase (j/2, j%2) of the x2-upsampled result, 32 channels each
+          op = e.out + ((size_t)(n * 2 * e.OH + 2 * oy + (j >> 1)) * (2 * e.OW) + 2 * ox + (j & 1)) * 32;
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           float4 o = make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
@@ -215,24 +220,25 @@ EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; int d0, d1, d2, d3, b1, b2;
+  const void* ptr; int d0, d1, d2, d3, b1, b2, es;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && b1 == o.b1 && b2 == o.b2;
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && b1 == o.b1 && b2 == o.b2 && es == o.es;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = (size_t)k.ptr;
-    for (int v : {k.d0, k.d1, k.d2, k.d3, k.b1, k.b2}) h = h * 1000003u ^ (size_t)v;
+    for (int v : {k.d0, k.d1, k.d2, k.d3, k.b1, k.b2, k.es}) h = h * 1000003u ^ (size_t)v;
     return h;
   }
 };
 std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// NHWC activation map: dims (C, W, H, N), box (32, 16, 8, 1).  rank-2 filter map: dims (K, Cout), box (32, NT).
-int get_map(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d2, int d3, int b1, int b2) {
-  MapKey key{ptr, d0, d1, d2, d3, b1, b2};
+// NHWC activation map: dims (C, W, H, N), box (32, 16*es, 8*es, 1) traversed with element strides (1, es, es, 1)
+// (es = conv stride: the box then lands as 16 x 8 pixels).  rank-2 filter map: dims (K, Cout), box (32, NT).
+int get_map(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d2, int d3, int b1, int b2, int es) {
+  MapKey key{ptr, d0, d1, d2, d3, b1, b2, es};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(key);
@@ -243,7 +249,7 @@ int get_map(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d2
   cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)d3};
   cuuint64_t strides[3] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4, (cuuint64_t)d0 * d1 * d2 * 4};
   cuuint32_t box[4] = {32, (cuuint32_t)b1, (cuuint32_t)b2, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)(rank == 4 ? es : 1), 1};
   CUtensorMap m;
   const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)ptr, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -259,8 +265,7 @@ int get_map(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d2
 }
 
 template <int NT>
-int launch(const ConvArgs& a, const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const TcEpilogue& e,
-           dim3 grid, cudaStream_t s) {
+int launch(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const TcEpilogue& e, dim3 grid, cudaStream_t s) {
   cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<NT>::SMEM);
   if (err != cudaSuccess) return (int)err;
   conv_tc_kernel<NT><<<grid, 192, TcCfg<NT>::SMEM, s>>>(A0, A1, Bm, e);
@@ -271,9 +276,12 @@ int launch(const ConvArgs& a, const CUtensorMap& A0, const CUtensorMap& A1, cons
 }  // namespace
 
 bool dh_conv_tc_eligible(const ConvArgs& a) {
-  return a.wt != nullptr && a.stride == 1 && a.up == 1 && a.KH == a.KW && (a.KH == 1 || a.KH == 3) && a.pad == a.KH / 2 &&
-         a.C0 > 0 && a.C0 % 32 == 0 && a.C1 % 32 == 0 && (a.Cout == 32 || a.Cout == 64 || a.Cout == 128 || a.Cout == 256) &&
-         a.inH >= 1 && a.inW >= 1;
+  const bool base = a.wt != nullptr && (a.stride == 1 || a.stride == 2) && a.up == 1 && a.KH == a.KW &&
+                    (a.KH == 1 || a.KH == 3) && a.pad == a.KH / 2 && a.C0 > 0 && a.C0 % 32 == 0 && a.C1 % 32 == 0 &&
+                    (a.Cout == 32 || a.Cout == 64 || a.Cout == 128 || a.Cout == 256) && a.inH >= 1 && a.inW >= 1;
+  if (!base) return false;
+  if (a.ps) return a.Cout == 128 && a.stride == 1 && a.res == nullptr;
+  return true;
 }
 
 int dh_launch_conv_tc(const ConvArgs& a, cudaStream_t s) {
@@ -284,22 +292,28 @@ int dh_launch_conv_tc(const ConvArgs& a, cudaStream_t s) {
              dh_aligned16(a.bias) && dh_aligned16(a.res), DH_E_ALIGN);
   const int Cin = a.C0 + a.C1, K = a.KH * a.KW * Cin;
   const int NT = a.Cout >= 128 ? 128 : a.Cout;
+  const int OH = (a.inH + 2 * a.pad - a.KH) / a.stride + 1, OW = (a.inW + 2 * a.pad - a.KW) / a.stride + 1;
   CUtensorMap A0, A1, Bm;
-  int rc = get_map(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, TC_TW, TC_TH);
+  int rc = get_map(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, TC_TW * a.stride, TC_TH * a.stride, a.stride);
   if (rc) return rc;
-  if (a.C1) { rc = get_map(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, TC_TW, TC_TH); if (rc) return rc; } else A1 = A0;
-  rc = get_map(&Bm, a.wt, 2, K, a.Cout, 1, 1, NT, 1);
+  if (a.C1) {
+    rc = get_map(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, TC_TW * a.stride, TC_TH * a.stride, a.stride);
+    if (rc) return rc;
+  } else {
+    A1 = A0;
+  }
+  rc = get_map(&Bm, a.wt, 2, K, a.Cout, 1, 1, NT, 1, 1);
   if (rc) return rc;
   TcEpilogue e;
   e.bias = a.bias; e.res = a.res; e.out = a.out;
-  e.OH = a.inH; e.OW = a.inW; e.Cout = a.Cout; e.relu = a.relu;
-  e.tilesX = dh_cdiv(a.inW, TC_TW);
+  e.OH = OH; e.OW = OW; e.Cout = a.Cout; e.relu = a.relu;
+  e.tilesX = dh_cdiv(OW, TC_TW);
   e.cchunks0 = a.C0 / 32; e.cchunks = Cin / 32; e.nsteps = a.KH * a.KW * e.cchunks;
-  e.KW = a.KW; e.pad = a.pad; e.Cin = Cin;
-  dim3 grid(e.tilesX * dh_cdiv(a.inH, TC_TH), a.Cout / NT, a.N);
+  e.KW = a.KW; e.pad = a.pad; e.Cin = Cin; e.stride = a.stride; e.ps = a.ps;
+  dim3 grid(e.tilesX * dh_cdiv(OH, TC_TH), a.Cout / NT, a.N);
   switch (NT) {
-    case 128: return launch<128>(a, A0, A1, Bm, e, grid, s);
-    case 64: return launch<64>(a, A0, A1, Bm, e, grid, s);
-    default: return launch<32>(a, A0, A1, Bm, e, grid, s);
+    case 128: return launch<128>(A0, A1, Bm, e, grid, s);
+    case 64: return launch<64>(A0, A1, Bm, e, grid, s);
+    default: return launch<32>(A0, A1, Bm, e, grid, s);
   }
 }

@@ -82,7 +82,9 @@ const char* kSlotNames[DH_W_COUNT] = {
   "DH_W_L1_0_C1_WT", "DH_W_L1_0_C2_WT", "DH_W_L1_1_C1_WT", "DH_W_L1_1_C2_WT",
   "DH_W_L2_0_C2_WT", "DH_W_L2_1_C1_WT", "DH_W_L2_1_C2_WT",
   "DH_W_L3_0_C1_WT", "DH_W_L3_0_C2_WT", "DH_W_L3_0_DS_WT", "DH_W_L3_1_C1_WT", "DH_W_L3_1_C2_WT",
-  "DH_W_LV5_DECODE_WT", "DH_W_LV4_DECODE_WT", "DH_W_LV3_DECODE_WT", "DH_W_CL20A_WT", "DH_W_CL20B_WT"};
+  "DH_W_LV5_DECODE_WT", "DH_W_LV4_DECODE_WT", "DH_W_LV3_DECODE_WT", "DH_W_CL20A_WT", "DH_W_CL20B_WT",
+  "DH_W_L2_0_C1_WT", "DH_W_L2_0_DS_WT",
+  "DH_W_CL4_PSWT", "DH_W_CL4_PSB", "DH_W_CL3_PSWT", "DH_W_CL3_PSB", "DH_W_CL2_PSWT", "DH_W_CL2_PSB"};
 
 // filter slot -> slot of its K-major copy (or -1)
 int wt_slot_of(int wslot) {
@@ -97,6 +99,7 @@ int wt_slot_of(int wslot) {
     case DH_W_LV5_DECODE: return DH_W_LV5_DECODE_WT; case DH_W_LV4_DECODE: return DH_W_LV4_DECODE_WT;
     case DH_W_LV3_DECODE: return DH_W_LV3_DECODE_WT;
     case DH_W_CL20A_W: return DH_W_CL20A_WT; case DH_W_CL20B_W: return DH_W_CL20B_WT;
+    case DH_W_L2_0_C1_W: return DH_W_L2_0_C1_WT; case DH_W_L2_0_DS_W: return DH_W_L2_0_DS_WT;
     default: return -1;
   }
 }
@@ -136,7 +139,8 @@ extern "C" size_t dahitra_workspace_bytes(int variant, int B, int H, int W, int 
 // C ABI — per-kernel entry points
 // ----------------------------------------------------------------------------------------------------
 static int conv_dispatch(const ConvArgs& a, int flags, cudaStream_t s) {
-  if ((flags & DH_FLAG_CONV_TC) && dh_conv_tc_eligible(a)) return dh_launch_conv_tc(a, s);
+  if ((flags & DH_FLAG_CONV_TC) && dh_conv_tc_eligible(a) && (a.stride == 1 || (flags & DH_FLAG_TC_STRIDE2)))
+    return dh_launch_conv_tc(a, s);
   return dh_launch_conv_ffma(a, s);
 }
 
@@ -145,6 +149,13 @@ extern "C" int dahitra_conv2d(const float* in0, const float* in1, int C0, int C1
                               const float* bias, const float* res, int relu, float* out, int flags, void* stream) {
   ConvArgs a{in0, in1, C0, C1, N, inH, inW, up, KH, KW, stride, pad, Cout, w, wt, bias, res, relu, out};
   return conv_dispatch(a, flags, (cudaStream_t)stream);
+}
+extern "C" int dahitra_conv2d_up2_tc(const float* in, int N, int inH, int inW, const float* pswt, const float* psb,
+                                     int relu, float* out, void* stream) {
+  ConvArgs a{in, nullptr, 32, 0, N, inH, inW, 1, 3, 3, 1, 1, 128, nullptr, pswt, psb, nullptr, relu, out};
+  a.ps = 1;
+  DH_REQUIRE(dh_conv_tc_eligible(a), DH_E_SHAPE);
+  return dh_launch_conv_tc(a, (cudaStream_t)stream);
 }
 extern "C" int dahitra_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* bias,
                             float* out, void* stream) {
@@ -236,6 +247,12 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
     const int wts = wt_slot_of(wslot);
     ConvArgs a{in0, in1, C0, C1, N, inH, inW, up, K, K, stride, K / 2, Cout, Wt(wslot), wts >= 0 ? Wt(wts) : nullptr,
                bslot >= 0 ? Wt(bslot) : nullptr, res, relu, out};
+    const int psw = (wslot == DH_W_CL4_W) ? DH_W_CL4_PSWT : (wslot == DH_W_CL3_W) ? DH_W_CL3_PSWT
+                  : (wslot == DH_W_CL2_W) ? DH_W_CL2_PSWT : -1;
+    if (up == 2 && psw >= 0 && (flags & DH_FLAG_CONV_TC)) {
+      // nearest-x2 upsample + 3x3 conv == 3x3 conv 32 -> 4x32 on the low-res map + pixel-shuffle store
+      a.up = 1; a.Cout = 128; a.w = nullptr; a.wt = Wt(psw); a.bias = Wt(psw + 1); a.ps = 1;
+    }
     const int rc = conv_dispatch(a, flags, s);
     if (rc != 0) return rc;
     const double OH = (double)(inH * up) / stride, OW = (double)(inW * up) / stride, Cin = C0 + C1;

@@ -53,6 +53,28 @@ def _khwc(w):
     return w.permute(2, 3, 1, 0).reshape(kh * kw * i, o)
 
 
+def upsample_phase_filter(w, b):
+    """nn.Upsample(x2, nearest) followed by a 3x3 pad-1 conv == four 2x2 convs on the low-res map, one per
+    output-pixel phase (py, px): rows r of the 3x3 filter that land on the same low-res row are summed.
+    out[2i+py, 2j+px] = sum_{u,v in {-1,0,1}} W3[(py,px)][u,v] . x[i+u, j+v]  with
+        py = 0: u=-1 <- r=0 ; u=0 <- r=1,2        py = 1: u=0 <- r=0,1 ; u=+1 <- r=2      (same for columns)
+    Returns the K-major filter [4*Cout][9*Cin] (row = phase*Cout + co, col = (u+1)*3*Cin + (v+1)*Cin + ci) and
+    the bias repeated per phase.  w: (Cout, Cin, 3, 3) float64."""
+    cout, cin = w.shape[:2]
+    rows = {0: {-1: [0], 0: [1, 2]}, 1: {0: [0, 1], 1: [2]}}
+    W3 = torch.zeros(4, cout, 3, 3, cin, dtype=w.dtype)
+    for py in (0, 1):
+        for px in (0, 1):
+            for u, rs in rows[py].items():
+                for v, ss in rows[px].items():
+                    acc = torch.zeros(cout, cin, dtype=w.dtype)
+                    for r in rs:
+                        for s in ss:
+                            acc += w[:, :, r, s]
+                    W3[py * 2 + px, :, u + 1, v + 1, :] = acc
+    return W3.reshape(4 * cout, 9 * cin), b.repeat(4)
+
+
 def _heads(w, h):                       # (h*64, 32) -> (h, 64, 32)
     return w.reshape(h, -1, w.shape[-1])
 
@@ -64,7 +86,7 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
 
     tc_slots = {"DH_W_L1_0_C1", "DH_W_L1_0_C2", "DH_W_L1_1_C1", "DH_W_L1_1_C2", "DH_W_L2_0_C2", "DH_W_L2_1_C1",
                 "DH_W_L2_1_C2", "DH_W_L3_0_C1", "DH_W_L3_0_C2", "DH_W_L3_0_DS", "DH_W_L3_1_C1", "DH_W_L3_1_C2",
-                "DH_W_CL20A", "DH_W_CL20B"}
+                "DH_W_CL20A", "DH_W_CL20B", "DH_W_L2_0_C1", "DH_W_L2_0_DS"}
 
     def put_conv(slot, conv, bn):
         w, b = _fold_conv_bn(sd, conv, bn)
@@ -131,6 +153,7 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
         P[s + "POS"] = None if pe is None else pe.double()[0].permute(1, 2, 0).reshape(-1, 32)
     for name, key in (("DH_W_CL4", "conv_layer4.0"), ("DH_W_CL3", "conv_layer3.0"), ("DH_W_CL2", "conv_layer2.0")):
         put_conv(name, key, None)
+        P[name + "_PSWT"], P[name + "_PSB"] = upsample_phase_filter(sd[key + ".weight"].double(), sd[key + ".bias"].double())
     put_conv("DH_W_CL20A", "conv_layer2_0.0", "conv_layer2_0.1")
     put_conv("DH_W_CL20B", "conv_layer2_0.3", None)
     wc = sd["classifier.weight"].double()

@@ -45,6 +45,7 @@ extern "C" {
 #define DH_FLAG_NONE        0
 #define DH_FLAG_CONV_TC     1   /* route eligible convolutions through the tcgen05/TMEM/TMA implicit-GEMM kernel */
 #define DH_FLAG_TC_3XTF32   2   /* with CONV_TC: error-compensated 3xTF32 (fp32-grade accuracy) instead of 1xTF32 */
+#define DH_FLAG_TC_STRIDE2  4   /* with CONV_TC: also route the stride-2 convolutions (TMA element strides) */
 
 /* ---- prepared-weight table -------------------------------------------------------------------
  * dahitra_forward takes `const void* const* weights` with DH_W_COUNT slots, each a device pointer to
@@ -77,6 +78,11 @@ enum dh_weight_slot {
   DH_W_L3_0_C1_WT, DH_W_L3_0_C2_WT, DH_W_L3_0_DS_WT, DH_W_L3_1_C1_WT, DH_W_L3_1_C2_WT,
   DH_W_LV5_DECODE_WT, DH_W_LV4_DECODE_WT, DH_W_LV3_DECODE_WT,
   DH_W_CL20A_WT, DH_W_CL20B_WT,
+  DH_W_L2_0_C1_WT, DH_W_L2_0_DS_WT,               /* the two stride-2 convs (TMA element strides) */
+  /* conv_layer4/3/2 act on a nearest-x2-upsampled map.  On the tensor-core path each becomes ONE 3x3 conv
+   * 32 -> 4*32 on the LOW-resolution map whose 4 channel blocks are the 4 output-pixel phases (filter taps
+   * that coincide on the low-res grid are summed on the host): _PSWT [128][9*32] K-major, _PSB [128] */
+  DH_W_CL4_PSWT, DH_W_CL4_PSB, DH_W_CL3_PSWT, DH_W_CL3_PSB, DH_W_CL2_PSWT, DH_W_CL2_PSB,
   DH_W_COUNT
 };
 
@@ -142,6 +148,13 @@ int dahitra_conv2d(const float* in0, const float* in1, int C0, int C1, int N, in
                    int KH, int KW, int stride, int pad, int Cout,
                    const float* w, const float* wt, const float* bias, const float* res, int relu,
                    float* out, int flags, void* stream);
+
+/* nn.Upsample(scale_factor=2) (nearest) followed by a 3x3 pad-1 conv 32->32 (+bias)(+ReLU) — conv_layer4/3/2,
+ * reference models/networks.py:1335-1336,1343-1344,1350-1351 — as ONE tcgen05 conv on the low-resolution map:
+ *   in NHWC [N][inH][inW][32] -> out NHWC [N][2*inH][2*inW][32]
+ *   pswt [128][9*32] K-major phase filter, psb [128] (see DH_W_CL*_PSWT / _PSB). */
+int dahitra_conv2d_up2_tc(const float* in, int N, int inH, int inW, const float* pswt, const float* psb,
+                          int relu, float* out, void* stream);
 
 /* Stem: 7x7 stride-2 pad-3 conv 3->64 + folded BN + ReLU, NCHW planes in, NHWC out
  * (reference models/networks.py:1120-1122, models/resnet.py:150-153). */

@@ -27,6 +27,15 @@ def conv2d(in0, in1, w, bias, res, relu, K, stride, pad, up=1, flags=0):
     return out
 
 
+def conv2d_up2_tc(x, pswt, psb, relu):
+    lib = _lib.load()
+    N, H, W, _ = x.shape
+    out = torch.empty((N, 2 * H, 2 * W, 32), device=x.device, dtype=torch.float32)
+    _lib.check(lib.dahitra_conv2d_up2_tc(_p(x), N, H, W, _p(pswt), _p(psb), int(relu), _p(out), _stream()),
+               "dahitra_conv2d_up2_tc")
+    return out
+
+
 def stem(x, w, b):
     lib = _lib.load()
     N, _, H, W = x.shape

@@ -70,6 +70,36 @@ TC_CONVS = [  # stride-1, un-upsampled shapes the tcgen05 kernel takes: (N, H, W
 ]
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 16), (1, 64, 64), (1, 24, 40)])
+def test_conv2d_up2_tcgen05(shape):
+    """nearest-x2 upsample + 3x3 conv (conv_layer4/3/2) as one low-res tcgen05 conv with a pixel-shuffle store."""
+    from dahitra_b200.engine import upsample_phase_filter
+    N, H, W = shape
+    x = rnd(N, H, W, 32, seed=1)
+    g = torch.Generator().manual_seed(2)
+    w = torch.randn(32, 32, 3, 3, generator=g, dtype=torch.float64) * (288 ** -0.5)
+    b = torch.randn(32, generator=g, dtype=torch.float64)
+    wt, pb = upsample_phase_filter(w, b)
+    y = abi.conv2d_up2_tc(x, wt.float().contiguous().to(DEV), pb.float().to(DEV), True)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.double().cpu().permute(0, 3, 1, 2).repeat_interleave(2, 2).repeat_interleave(2, 3), w, b, 1, 1))
+    close(y, ref.permute(0, 2, 3, 1), rtol=2e-3, atol=4e-3)
+
+
+@pytest.mark.parametrize("cfg", [(1, 64, 64, 64, 128, 3), (2, 32, 32, 64, 128, 1), (1, 24, 40, 32, 64, 3)])
+def test_conv2d_stride2_tcgen05(cfg):
+    """stride-2 convs (layer2.0 conv1 / downsample): the TMA box walks the input with element strides {1,2,2,1}."""
+    N, H, W, Cin, Cout, K = cfg
+    x = rnd(N, H, W, Cin, seed=1)
+    w = rnd(K * K * Cin, Cout, seed=3, scale=(K * K * Cin) ** -0.5)
+    b = rnd(Cout, seed=4)
+    y = abi.conv2d(x, None, w, b, None, True, K, 2, K // 2, 1, flags=5)
+    torch.cuda.synchronize()
+    ref = E.conv_nhwc(x.double(), w.double(), b.double(), K, 2, K // 2, None, True, 1)
+    assert y.shape == ref.shape
+    close(y, ref, rtol=2e-3, atol=4e-3)
+
+
 @pytest.mark.parametrize("cfg", TC_CONVS)
 def test_conv2d_tcgen05(cfg):
     """tcgen05/TMEM/TMA implicit GEMM vs fp64: TF32 operands (10-bit mantissa), fp32 accumulate."""

@@ -92,6 +92,22 @@ def test_prepared_weights_algebra_matches_oracle(variant, levir_template):
     assert float((y - e).abs().max()) < 5e-5 * float(y.abs().max())
 
 
+def test_upsample_phase_filter_algebra():
+    """upsample(x2, nearest) -> conv3x3  ==  conv3x3 (32 -> 4*32) on the low-res map -> pixel shuffle."""
+    import torch.nn.functional as F
+    from dahitra_b200.engine import upsample_phase_filter
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(32, 32, 3, 3, generator=g, dtype=torch.float64)
+    b = torch.randn(32, generator=g, dtype=torch.float64)
+    x = torch.randn(2, 32, 6, 10, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x.repeat_interleave(2, 2).repeat_interleave(2, 3), w, b, 1, 1)
+    wt, pb = upsample_phase_filter(w, b)                       # [128][9*32] K-major, [128]
+    w3 = wt.reshape(128, 3, 3, 32).permute(0, 3, 1, 2)         # -> OIHW
+    y = F.conv2d(x, w3, pb, 1, 1)                              # (2, 128, 6, 10): channel = phase*32 + co
+    y = y.reshape(2, 2, 2, 32, 6, 10).permute(0, 3, 4, 1, 5, 2).reshape(2, 32, 12, 20)
+    assert float((y - ref).abs().max()) < 1e-12
+
+
 def test_prepared_weights_algebra_xbd():
     from dahitra_b200.engine import prepare_weights
     from dahitra_b200.xbd import BASE_Transformer_UNet as X

@@ -1,0 +1,59 @@
+"""CPU: the launcher swaps the class inside the UNMODIFIED reference's define_G (build container only — needs
+/root/reference), and the world_size-2 gloo path of the pair sharding used by bench.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_reference_define_G_builds_the_native_class():
+    code = (
+        "import torch\n"
+        "from dahitra_b200.launch import install\n"
+        f"nets = install({REF!r}, stub_missing=True)\n"
+        "class A: net_G = 'newUNetTrans'\n"
+        "torch.manual_seed(0)\n"
+        "net = nets.define_G(A(), gpu_ids=[])\n"      # the reference's own factory, init_net and init_weights
+        "assert type(net).__module__ == 'dahitra_b200.networks', type(net)\n"
+        "sd = net.state_dict()\n"
+        "assert len(sd) == 425\n"
+        "print('OK', float(sd['classifier.weight'].double().sum()))\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "OK" in r.stdout
+
+
+SHARD_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DAHITRA_ROOT"])
+from dahitra_b200.sharding import shard_pairs, gather_max_ms
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+r = dist.get_rank()
+lo, hi = shard_pairs(11, r, 2)
+assert (lo, hi) == ((0, 6) if r == 0 else (6, 11)), (lo, hi)
+lo, hi = shard_pairs(64, r, 2)
+assert hi - lo == 32
+ms = gather_max_ms(10.0 + 5.0 * r, device="cpu")
+assert ms == 15.0, ms
+dist.destroy_process_group()
+print("rank", r, "ok")
+"""
+
+
+def test_pair_sharding_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(SHARD_WORKER)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), PORT="29641", DAHITRA_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err[-2000:]
+        assert "ok" in out
