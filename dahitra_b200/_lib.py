@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdahitra_b200.so")
-SOURCES = ["conv_ffma.cu", "conv_tc.cu", "tokens.cu", "decoder.cu", "aux.cu", "forward.cu"]
+SOURCES = ["conv_ffma.cu", "conv_tc.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "aux.cu", "forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -69,6 +69,8 @@ SIGNATURES = {
     "dahitra_token_encoder": (_I, [_P, _I, _I, _P, _I, _I, _P, _P]),
     "dahitra_decoder_tables": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "dahitra_pixel_decoder": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
+    "dahitra_decoder_tables_tc": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
+    "dahitra_pixel_decoder_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
     "dahitra_classifier": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 

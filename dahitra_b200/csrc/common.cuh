@@ -66,6 +66,10 @@ int dh_launch_token_encoder(const float* partials, int B, int nchunk, const floa
                             float* mem, cudaStream_t s);
 int dh_launch_decoder_tables(const float* mem, int B, int first_call, int ncalls, const float* dec, int heads, int depth,
                              float* tables, cudaStream_t s);
+int dh_launch_decoder_tables_tc(const float* mem, int B, int first_call, int ncalls, const float* dec, int heads, int depth,
+                                float* tables, cudaStream_t s);
+int dh_launch_pixel_decoder_tc(const float* x, const float* pos, const float* tables, const float* pack, int nimg, int h,
+                               int w, int heads, int depth, const float* skip, int skip_up, float* out, cudaStream_t s);
 int dh_launch_pixel_decoder(const float* x, const float* pos, const float* tables, const float* dec,
                             int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up, float* out,
                             cudaStream_t s);

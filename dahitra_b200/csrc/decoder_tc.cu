@@ -1,0 +1,318 @@
+// dahitra_b200 — pixel decoder on the tensor cores (tcgen05, TF32 operands, fp32 accumulate in TMEM).
+//
+// Same algebra as decoder.cu (collapsed cross-attention + MLP, reference models/help_funcs.py:66-114,170-186),
+// re-mapped so that the four 128x32x32 products of every layer run as tcgen05.mma and everything that is
+// per-pixel (LayerNorm statistics, the 4-key softmax per head, exact-erf GELU) is thread-local:
+//   * a CTA owns 128 pixels; thread t owns pixel t = TMEM lane t, so `tcgen05.ld.32x32b` hands each thread the
+//     32 channels of ITS pixel — no shuffles anywhere.
+//   * the running activation x lives in TMEM columns [0,32) for the whole call; attention and MLP outputs are
+//     accumulated INTO it by the MMA (x += P.Bv, x += G.W2).  Biases are pixel-independent, so they are applied
+//     as host-precomputed cumulative vectors when x is read back (no TMEM write-back).
+//   * A operands (xhat, P, xhat', G) are written by the threads into one 128-row K-major SWIZZLE_128B tile;
+//     B operands (per-image tables, shared MLP weights) arrive pre-swizzled from global memory through two
+//     1-D bulk copies per layer (double-buffered, prefetched one layer ahead).
+// Per layer: 4 x {write A row, fence.proxy.async, barrier, one thread issues 2-4 MMAs + commit, mbarrier wait,
+// tcgen05.ld}.  4 CTAs per SM overlap each other's serial chains.
+#include "tc_common.cuh"
+
+using namespace dhtc;
+
+// ----------------------------------------------------------------------------------------------------
+// table builder (TC layout): per (image-call, layer)  [TA swz 32x32][TB swz 32x32][cA 32]  = DH_TABTC_FLOATS
+//   TA[n = h*4+j][k = c] = g_c * sum_c' Mqk[h][c][c'] mn_j[c']       (B operand of  S = xhat . TA^T)
+//   TB[n = c][k = h*4+j] =       sum_c' Mov[h][c][c'] mn_j[c']       (B operand of  x += P . TB^T)
+//   cA[h*4+j]            = sum_c b_c * (TA/g)[h*4+j][c]
+// ----------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ float ln_lane32(float v, float g, float b) {
+  const float mu = warp_sum(v) * (1.f / 32.f);
+  const float d = v - mu;
+  const float var = warp_sum(d * d) * (1.f / 32.f);
+  return d * (1.0f / sqrtf(var + 1e-5f)) * g + b;
+}
+
+__global__ void __launch_bounds__(128)
+decoder_tables_tc_kernel(const float* __restrict__ mem, int B, int first_call, const float* __restrict__ dec, int heads,
+                         float* __restrict__ tables, int depth) {
+  __shared__ float MN[4][32];
+  const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int layer = blockIdx.x;
+  const int ci = blockIdx.y / B, pair = blockIdx.y % B;
+  const int call = first_call + ci;
+  const float* L = dec + (size_t)layer * DH_DEC_LAYER_FLOATS(heads);
+  const float* MqkT = L + 64;
+  const float* MovT = MqkT + (size_t)heads * 1024;
+  float* T = tables + ((size_t)blockIdx.y * depth + layer) * DH_TABTC_FLOATS;
+  float* TA = T; float* TB = T + 1024; float* cA = T + 2048;
+  const float g = __ldg(L + lane), b = __ldg(L + 32 + lane);
+  MN[j][lane] = ln_lane32(__ldg(mem + ((size_t)pair * 3 + call) * 128 + j * 32 + lane), g, b);
+  __syncwarp();
+  for (int h = 0; h < heads; ++h) {
+    const float* mq = MqkT + (size_t)h * 1024;
+    const float* mv = MovT + (size_t)h * 1024;
+    float a = 0.f, v = 0.f;
+#pragma unroll 8
+    for (int c2 = 0; c2 < 32; ++c2) {
+      const float mn = MN[j][c2];
+      a = fmaf(__ldg(mq + c2 * 32 + lane), mn, a);
+      v = fmaf(__ldg(mv + c2 * 32 + lane), mn, v);
+    }
+    const int hj = h * 4 + j;
+    TA[sw128_idx(hj, lane)] = g * a;
+    TB[sw128_idx(lane, hj)] = v;
+    const float ca = warp_sum(b * a);
+    if (lane == 0) cA[hj] = ca;
+  }
+  if (heads == 4 && j == 0 && lane >= 16) cA[lane] = 0.f;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// decoder
+// ----------------------------------------------------------------------------------------------------
+constexpr int PDT_ROWS = 128;
+constexpr uint32_t PDT_A_BYTES = 128 * 128;                 // A tile
+constexpr uint32_t PDT_TAB_BYTES = DH_TABTC_FLOATS * 4;     // 8320: TA | TB | cA
+constexpr uint32_t PDT_MLP_BYTES = DH_DECTC_LAYER_FLOATS * 4;   // 8576: W1 | W2 | b1f | cbA | cbM
+constexpr uint32_t PDT_BUF = 9216;                          // per-buffer stride (1024-aligned)
+constexpr uint32_t PDT_SMEM = PDT_A_BYTES + 4 * PDT_BUF + 1024;
+
+__device__ __forceinline__ void write_a_row(float* a_tile, int row, const float (&v)[32]) {
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch)
+    *reinterpret_cast<float4*>(a_tile + row * 32 + ((ch ^ (row & 7)) << 2)) =
+        make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+}
+
+template <int HEADS>
+__global__ void __launch_bounds__(PDT_ROWS, 4)
+pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const float* __restrict__ tables,
+                        const float* __restrict__ pack, int npix, int w, int depth, const float* __restrict__ skip,
+                        int skip_up, float* __restrict__ out) {
+  constexpr int H4 = HEADS * 4;
+  constexpr uint32_t IDESC_S = umma_idesc_tf32(128, H4);
+  constexpr uint32_t IDESC_32 = umma_idesc_tf32(128, 32);
+  extern __shared__ uint8_t pdt_raw[];
+  __shared__ __align__(8) uint64_t tab_bar[2], mma_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, img = blockIdx.y;
+  const int p = blockIdx.x * PDT_ROWS + tid;
+  const bool valid = p < npix;
+  const uint32_t base = (smem_u32(pdt_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = pdt_raw + (base - smem_u32(pdt_raw));
+  float* a_tile = reinterpret_cast<float*>(base_ptr);
+  const uint32_t a_addr = base;
+  auto tab_addr = [&](int b) { return base + PDT_A_BYTES + (uint32_t)b * PDT_BUF; };
+  auto mlp_addr = [&](int b) { return base + PDT_A_BYTES + 2 * PDT_BUF + (uint32_t)b * PDT_BUF; };
+  auto tab_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + PDT_A_BYTES + (size_t)b * PDT_BUF); };
+  auto mlp_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + PDT_A_BYTES + 2 * PDT_BUF + (size_t)b * PDT_BUF); };
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&tab_bar[0]), 1); mbar_init(smem_u32(&tab_bar[1]), 1); mbar_init(smem_u32(&mma_bar), 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot + ((uint32_t)(warp * 32) << 16);     // this warp's lane quarter
+  const uint32_t TM_X = 0, TM_S = 32, TM_H = 64;
+
+  auto issue_loads = [&](int layer) {
+    const int b = layer & 1;
+    const uint32_t bar = smem_u32(&tab_bar[b]);
+    mbar_expect_tx(bar, PDT_TAB_BYTES + PDT_MLP_BYTES);
+    bulk_load_1d(tab_addr(b), tables + ((size_t)img * depth + layer) * DH_TABTC_FLOATS, PDT_TAB_BYTES, bar);
+    bulk_load_1d(mlp_addr(b), pack + (size_t)layer * DH_DECTC_LAYER_FLOATS, PDT_MLP_BYTES, bar);
+  };
+  if (tid == 0) issue_loads(0);
+
+  // ---- x (+ pos) -> registers and TMEM
+  float xr[32];
+  if (valid) {
+    const float* xp = x + ((size_t)img * npix + p) * 32;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = ldg4(xp + q * 4);
+      xr[q * 4] = v.x; xr[q * 4 + 1] = v.y; xr[q * 4 + 2] = v.z; xr[q * 4 + 3] = v.w;
+    }
+    if (pos) {
+      const float* pp = pos + (size_t)p * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = ldg4(pp + q * 4);
+        xr[q * 4] += v.x; xr[q * 4 + 1] += v.y; xr[q * 4 + 2] += v.z; xr[q * 4 + 3] += v.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) xr[c] = 0.f;
+  }
+  {
+    uint32_t u[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) u[c] = __float_as_uint(xr[c]);
+    tmem_st32(tmem + TM_X, u);
+  }
+
+  uint32_t mma_phase = 0;
+  // one MMA round: all rows of the A tile are written -> thread 0 issues `nk` K-steps -> everyone waits for the commit
+  auto mma_round = [&](uint32_t b_addr, uint32_t idesc, uint32_t tm_col, int nk, bool accumulate, int prefetch_layer) {
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      if (prefetch_layer >= 0) issue_loads(prefetch_layer);
+      tc_fence_after();
+      const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(b_addr);
+      for (int k = 0; k < nk; ++k)
+        umma_tf32(tmem_slot + tm_col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (accumulate || k) ? 1u : 0u);
+      umma_commit(smem_u32(&mma_bar));
+    }
+    mbar_wait(smem_u32(&mma_bar), mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+  };
+
+  for (int layer = 0; layer < depth; ++layer) {
+    const int b = layer & 1;
+    mbar_wait(smem_u32(&tab_bar[b]), (uint32_t)((layer >> 1) & 1));
+    const float* tabp = tab_ptr(b);
+    const float* mlpp = mlp_ptr(b);
+    const float* cA = tabp + 2048;
+    const float* b1f = mlpp + 2048; const float* cbA = mlpp + 2080; const float* cbM = mlpp + 2112;
+    float t[32];
+    // ---- 1. S = xhat . TA^T
+    {
+      float mu = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) mu += xr[c];
+      mu *= (1.f / 32.f);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { const float d = xr[c] - mu; var = fmaf(d, d, var); }
+      const float rstd = 1.0f / sqrtf(var * (1.f / 32.f) + 1e-5f);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
+      write_a_row(a_tile, tid, t);
+    }
+    // the buffer of layer+1 was last read in layer-1; every thread is past that once it reaches this barrier
+    mma_round(tab_addr(b), IDESC_S, TM_S, 4, false, (layer + 1 < depth) ? layer + 1 : -1);
+    // ---- 2. P = softmax_j(S + cA) ; x += P . TB^T
+    {
+      if constexpr (HEADS == 8) {
+        uint32_t u[32];
+        tmem_ld32(tmem + TM_S, u);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) t[c] = __uint_as_float(u[c]) + cA[c];
+      } else {
+        uint32_t u[16];
+        tmem_ld16(tmem + TM_S, u);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) t[c] = __uint_as_float(u[c]) + cA[c];
+#pragma unroll
+        for (int c = 16; c < 32; ++c) t[c] = 0.f;
+      }
+#pragma unroll
+      for (int h = 0; h < HEADS; ++h) {
+        const float mx = fmaxf(fmaxf(t[h * 4], t[h * 4 + 1]), fmaxf(t[h * 4 + 2], t[h * 4 + 3]));
+        const float e0 = expf(t[h * 4] - mx), e1 = expf(t[h * 4 + 1] - mx), e2 = expf(t[h * 4 + 2] - mx), e3 = expf(t[h * 4 + 3] - mx);
+        const float inv = 1.0f / (e0 + e1 + e2 + e3);
+        t[h * 4] = e0 * inv; t[h * 4 + 1] = e1 * inv; t[h * 4 + 2] = e2 * inv; t[h * 4 + 3] = e3 * inv;
+      }
+      write_a_row(a_tile, tid, t);
+    }
+    mma_round(tab_addr(b) + 4096, IDESC_32, TM_X, H4 / 8, true, -1);
+    // ---- 3. Hid = xhat' . W1f^T
+    {
+      uint32_t u[32];
+      tmem_ld32(tmem + TM_X, u);
+      float mu = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { xr[c] = __uint_as_float(u[c]) + cbA[c]; mu += xr[c]; }
+      mu *= (1.f / 32.f);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { const float d = xr[c] - mu; var = fmaf(d, d, var); }
+      const float rstd = 1.0f / sqrtf(var * (1.f / 32.f) + 1e-5f);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
+      write_a_row(a_tile, tid, t);
+    }
+    mma_round(mlp_addr(b), IDESC_32, TM_H, 4, false, -1);
+    // ---- 4. x += gelu(Hid + b1f) . W2^T
+    {
+      uint32_t u[32];
+      tmem_ld32(tmem + TM_H, u);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) t[c] = gelu_erf(__uint_as_float(u[c]) + b1f[c]);
+      write_a_row(a_tile, tid, t);
+    }
+    mma_round(mlp_addr(b) + 4096, IDESC_32, TM_X, 4, true, -1);
+    {
+      uint32_t u[32];
+      tmem_ld32(tmem + TM_X, u);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) xr[c] = __uint_as_float(u[c]) + cbM[c];
+    }
+  }
+
+  if (valid) {
+    if (skip) {
+      const int py = p / w, px = p - py * w;
+      const float* sp = (skip_up == 2)
+          ? skip + (((size_t)img * (npix / w / 2) + (py >> 1)) * (w >> 1) + (px >> 1)) * 32
+          : skip + ((size_t)img * npix + p) * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = ldg4(sp + q * 4);
+        xr[q * 4] += v.x; xr[q * 4 + 1] += v.y; xr[q * 4 + 2] += v.z; xr[q * 4 + 3] += v.w;
+      }
+    }
+    float* op = out + ((size_t)img * npix + p) * 32;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) st4(op + q * 4, make_float4(xr[q * 4], xr[q * 4 + 1], xr[q * 4 + 2], xr[q * 4 + 3]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_slot, 128);
+  }
+}
+}  // namespace
+
+int dh_launch_decoder_tables_tc(const float* mem, int B, int first_call, int ncalls, const float* dec, int heads, int depth,
+                                float* tables, cudaStream_t s) {
+  DH_REQUIRE(mem && dec && tables, DH_E_NULL);
+  DH_REQUIRE(B > 0 && first_call >= 0 && ncalls >= 1 && first_call + ncalls <= 3 && (heads == 4 || heads == 8) && depth >= 1,
+             DH_E_SHAPE);
+  dim3 grid(depth, ncalls * B);
+  decoder_tables_tc_kernel<<<grid, 128, 0, s>>>(mem, B, first_call, dec, heads, tables, depth);
+  DH_CHECK_LAUNCH();
+  return 0;
+}
+
+int dh_launch_pixel_decoder_tc(const float* x, const float* pos, const float* tables, const float* pack, int nimg, int h,
+                               int w, int heads, int depth, const float* skip, int skip_up, float* out, cudaStream_t s) {
+  DH_REQUIRE(x && tables && pack && out, DH_E_NULL);
+  DH_REQUIRE(nimg > 0 && h > 0 && w > 0 && depth >= 1 && (heads == 4 || heads == 8), DH_E_SHAPE);
+  DH_REQUIRE(!skip || skip_up == 1 || (skip_up == 2 && h % 2 == 0 && w % 2 == 0), DH_E_SHAPE);
+  DH_REQUIRE(dh_aligned16(x) && dh_aligned16(pos) && dh_aligned16(tables) && dh_aligned16(pack) && dh_aligned16(skip) &&
+             dh_aligned16(out), DH_E_ALIGN);
+  const int npix = h * w;
+  dim3 grid(dh_cdiv(npix, PDT_ROWS), nimg);
+  cudaError_t e;
+  if (heads == 4) {
+    e = cudaFuncSetAttribute(pixel_decoder_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PDT_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    pixel_decoder_tc_kernel<4><<<grid, PDT_ROWS, PDT_SMEM, s>>>(x, pos, tables, pack, npix, w, depth, skip, skip_up, out);
+  } else {
+    e = cudaFuncSetAttribute(pixel_decoder_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PDT_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    pixel_decoder_tc_kernel<8><<<grid, PDT_ROWS, PDT_SMEM, s>>>(x, pos, tables, pack, npix, w, depth, skip, skip_up, out);
+  }
+  DH_CHECK_LAUNCH();
+  return 0;
+}

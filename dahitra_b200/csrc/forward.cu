@@ -55,7 +55,7 @@ bool make_plan(Plan& p, int variant, int B, int H, int W, int nc) {
     L.out = b.take((size_t)B * n * 32);
     L.part = b.take(N2 * L.nchunk * 4 * 34);
     L.mem = b.take((size_t)B * 3 * 128);
-    L.tab = b.take((size_t)3 * B * L.depth * DH_TAB_FLOATS(L.heads));
+    L.tab = b.take((size_t)3 * B * L.depth * (DH_TAB_FLOATS(L.heads) > DH_TABTC_FLOATS ? DH_TAB_FLOATS(L.heads) : DH_TABTC_FLOATS));
   }
   p.c4 = b.take((size_t)B * s4 * 32);
   p.c3 = b.take((size_t)B * s2 * 32);
@@ -84,7 +84,8 @@ const char* kSlotNames[DH_W_COUNT] = {
   "DH_W_L3_0_C1_WT", "DH_W_L3_0_C2_WT", "DH_W_L3_0_DS_WT", "DH_W_L3_1_C1_WT", "DH_W_L3_1_C2_WT",
   "DH_W_LV5_DECODE_WT", "DH_W_LV4_DECODE_WT", "DH_W_LV3_DECODE_WT", "DH_W_CL20A_WT", "DH_W_CL20B_WT",
   "DH_W_L2_0_C1_WT", "DH_W_L2_0_DS_WT",
-  "DH_W_CL4_PSWT", "DH_W_CL4_PSB", "DH_W_CL3_PSWT", "DH_W_CL3_PSB", "DH_W_CL2_PSWT", "DH_W_CL2_PSB"};
+  "DH_W_CL4_PSWT", "DH_W_CL4_PSB", "DH_W_CL3_PSWT", "DH_W_CL3_PSB", "DH_W_CL2_PSWT", "DH_W_CL2_PSB",
+  "DH_W_LV5_DECTC", "DH_W_LV4_DECTC", "DH_W_LV3_DECTC"};
 
 // filter slot -> slot of its K-major copy (or -1)
 int wt_slot_of(int wslot) {
@@ -181,6 +182,16 @@ extern "C" int dahitra_pixel_decoder(const float* x, const float* pos, const flo
                                      float* out, void* stream) {
   return dh_launch_pixel_decoder(x, pos, tables, dec_pack, nimg, h, w, heads, depth, skip, skip_up, out,
                                  (cudaStream_t)stream);
+}
+extern "C" int dahitra_decoder_tables_tc(const float* mem, int B, int first_call, int ncalls, const float* dec_pack,
+                                         int heads, int depth, float* tables, void* stream) {
+  return dh_launch_decoder_tables_tc(mem, B, first_call, ncalls, dec_pack, heads, depth, tables, (cudaStream_t)stream);
+}
+extern "C" int dahitra_pixel_decoder_tc(const float* x, const float* pos, const float* tables, const float* dectc_pack,
+                                        int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up,
+                                        float* out, void* stream) {
+  return dh_launch_pixel_decoder_tc(x, pos, tables, dectc_pack, nimg, h, w, heads, depth, skip, skip_up, out,
+                                    (cudaStream_t)stream);
 }
 extern "C" int dahitra_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* bias,
                                   float* logits, unsigned char* argmax_u8, void* stream) {
@@ -323,19 +334,30 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
     const int add_tok_pos = (variant == DH_VARIANT_LEVIR) ? 1 : (i == 0 ? 1 : 0);
     DH_STEP(nm[i][1], 0.0, 4.0 * N2 * L.nchunk * 136.0, dh_launch_token_encoder(PART, B, L.nchunk, enc, L.heads, add_tok_pos, MEM, s));
     const size_t half = (size_t)B * npix * 32;
+    // decoder launches: CUDA-core kernels, or the tcgen05 pair (DH_FLAG_DEC_TC) with its own table layout
+    const bool dtc = (flags & DH_FLAG_DEC_TC) != 0;
+    const float* dectc = Wt(DH_W_LV5_DECTC + i);
+    const size_t tabf = dtc ? (size_t)DH_TABTC_FLOATS : (size_t)DH_TAB_FLOATS(L.heads);
+    auto tables = [&](int first, int ncalls) -> int {
+      return dtc ? dh_launch_decoder_tables_tc(MEM, B, first, ncalls, dec, L.heads, L.depth, TAB, s)
+                 : dh_launch_decoder_tables(MEM, B, first, ncalls, dec, L.heads, L.depth, TAB, s);
+    };
+    auto decode = [&](const float* xin, const float* tab, int nimg, const float* sk, int sku, float* o) -> int {
+      return dtc ? dh_launch_pixel_decoder_tc(xin, pos, tab, dectc, nimg, L.h, L.w, L.heads, L.depth, sk, sku, o, s)
+                 : dh_launch_pixel_decoder(xin, pos, tab, dec, nimg, L.h, L.w, L.heads, L.depth, sk, sku, o, s);
+    };
     if (variant == DH_VARIANT_LEVIR) {
-      DH_STEP(nm[i][2], 0.0, 4.0 * 3 * B * L.depth * DH_TAB_FLOATS(L.heads), dh_launch_decoder_tables(MEM, B, 0, 3, dec, L.heads, L.depth, TAB, s));
-      DH_STEP(nm[i][3], dec_fl_px * N2 * npix, dec_by_px * N2 * npix,
-              dh_launch_pixel_decoder(XS, pos, TAB, dec, N2, L.h, L.w, L.heads, L.depth, nullptr, 1, XD, s));
+      DH_STEP(nm[i][2], 0.0, 4.0 * 3 * B * L.depth * tabf, tables(0, 3));
+      DH_STEP(nm[i][3], dec_fl_px * N2 * npix, dec_by_px * N2 * npix, decode(XS, TAB, N2, nullptr, 1, XD));
       DH_CONV(nm[i][4], XD, XD + half, 32, 32, B, L.h, L.w, 1, 3, 1, 32, base[i] + 5, -1, nullptr, 0, DX);
-      const float* tab2 = TAB + (size_t)2 * B * L.depth * DH_TAB_FLOATS(L.heads);
+      const float* tab2 = TAB + (size_t)2 * B * L.depth * tabf;
       DH_STEP(nm[i][5], dec_fl_px * B * npix, (dec_by_px + (skip ? 128.0 / (skip_up * skip_up) : 0.0)) * B * npix,
-              dh_launch_pixel_decoder(DX, pos, tab2, dec, B, L.h, L.w, L.heads, L.depth, skip, skip_up, OUT, s));
+              decode(DX, tab2, B, skip, skip_up, OUT));
     } else {
-      DH_STEP(nm[i][2], 0.0, 4.0 * B * L.depth * DH_TAB_FLOATS(L.heads), dh_launch_decoder_tables(MEM, B, 2, 1, dec, L.heads, L.depth, TAB, s));
+      DH_STEP(nm[i][2], 0.0, 4.0 * B * L.depth * tabf, tables(2, 1));
       DH_CONV(nm[i][4], XS, XS + half, 32, 32, B, L.h, L.w, 1, 3, 1, 32, base[i] + 5, -1, nullptr, 0, DX);
       DH_STEP(nm[i][5], dec_fl_px * B * npix, (dec_by_px + (skip ? 128.0 / (skip_up * skip_up) : 0.0)) * B * npix,
-              dh_launch_pixel_decoder(DX, pos, TAB, dec, B, L.h, L.w, L.heads, L.depth, skip, skip_up, OUT, s));
+              decode(DX, TAB, B, skip, skip_up, OUT));
     }
     if (i == 1)   // conv_layer4(up2(out_4)) -> C4 at H/4 (:1335-1336)
       DH_CONV(nm[i][6], OUT, nullptr, 32, 0, B, L.h, L.w, 2, 3, 1, 32, DH_W_CL4_W, DH_W_CL4_B, nullptr, 1, C4);

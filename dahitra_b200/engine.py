@@ -22,7 +22,8 @@ SCALE = 32 ** -0.5
 LEVELS = ((5, 256, 4, 4), (4, 128, 4, 4), (3, 64, 8, 8))   # (k, trunk channels, heads, decoder depth)
 
 DH_VARIANT_LEVIR, DH_VARIANT_XBD = 0, 1
-DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32 = 1, 2
+DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC = 1, 2, 4, 8
+MODES = {"fp32": 0, "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC}
 
 
 def slot_names():
@@ -73,6 +74,18 @@ def upsample_phase_filter(w, b):
                             acc += w[:, :, r, s]
                     W3[py * 2 + px, :, u + 1, v + 1, :] = acc
     return W3.reshape(4 * cout, 9 * cin), b.repeat(4)
+
+
+def swizzle128(m):
+    """[rows][32] matrix B[n][k] -> flat K-major SWIZZLE_128B shared-memory image (rows of 128 B, the 16-byte
+    chunk index XOR-ed with row % 8): element (n, k) lands at n*32 + (((k>>2) ^ (n&7)) << 2 | (k&3))."""
+    rows = m.shape[0]
+    n = torch.arange(rows)[:, None].expand(rows, 32)
+    k = torch.arange(32)[None, :].expand(rows, 32)
+    idx = n * 32 + ((((k >> 2) ^ (n & 7)) << 2) | (k & 3))
+    out = torch.empty(rows * 32, dtype=m.dtype)
+    out[idx.reshape(-1)] = m.reshape(-1)
+    return out
 
 
 def _heads(w, h):                       # (h*64, 32) -> (h, 64, 32)
@@ -145,6 +158,17 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
                        mqkT.reshape(-1), movT.reshape(-1), sd[d + ".0.fn.fn.to_out.0.bias"].double(),
                        (w1 * g2[None, :]).T.reshape(-1), b1 + w1 @ b2n, w2.T.reshape(-1), b2]
         P[s + "DEC"] = torch.cat(layers)
+        # ---- tensor-core decoder pack: pre-swizzled B operands + cumulative biases (include/dahitra_b200.h)
+        tc_layers, cum = [], torch.zeros(32, dtype=torch.float64)
+        for l in range(depth):
+            d = f"transformer_decoder_{k}.layers.{l}"
+            g2, b2n = sd[d + ".1.fn.norm.weight"].double(), sd[d + ".1.fn.norm.bias"].double()
+            w1, b1 = sd[d + ".1.fn.fn.net.0.weight"].double(), sd[d + ".1.fn.fn.net.0.bias"].double()
+            w2, b2 = sd[d + ".1.fn.fn.net.3.weight"].double(), sd[d + ".1.fn.fn.net.3.bias"].double()
+            cba = cum + sd[d + ".0.fn.fn.to_out.0.bias"].double()
+            cum = cba + b2
+            tc_layers += [swizzle128(w1 * g2[None, :]), swizzle128(w2), b1 + w1 @ b2n, cba, cum.clone()]
+        P[s + "DECTC"] = torch.cat(tc_layers)
         # ---- decoder positional embedding
         if variant == DH_VARIANT_LEVIR:
             pe = sd.get(f"pos_embedding_decoder_{k}")

@@ -46,6 +46,8 @@ extern "C" {
 #define DH_FLAG_CONV_TC     1   /* route eligible convolutions through the tcgen05/TMEM/TMA implicit-GEMM kernel */
 #define DH_FLAG_TC_3XTF32   2   /* with CONV_TC: error-compensated 3xTF32 (fp32-grade accuracy) instead of 1xTF32 */
 #define DH_FLAG_TC_STRIDE2  4   /* with CONV_TC: also route the stride-2 convolutions (TMA element strides) */
+#define DH_FLAG_DEC_TC      8   /* pixel decoder on tcgen05 (TF32 operands), decoder_tc.cu */
+#define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC)   /* the "tf32" mode */
 
 /* ---- prepared-weight table -------------------------------------------------------------------
  * dahitra_forward takes `const void* const* weights` with DH_W_COUNT slots, each a device pointer to
@@ -83,6 +85,10 @@ enum dh_weight_slot {
    * 32 -> 4*32 on the LOW-resolution map whose 4 channel blocks are the 4 output-pixel phases (filter taps
    * that coincide on the low-res grid are summed on the host): _PSWT [128][9*32] K-major, _PSB [128] */
   DH_W_CL4_PSWT, DH_W_CL4_PSB, DH_W_CL3_PSWT, DH_W_CL3_PSB, DH_W_CL2_PSWT, DH_W_CL2_PSB,
+  /* tensor-core pixel decoder: per layer [W1f swz 32x32][W2 swz 32x32][b1f 32][cbA 32][cbM 32]
+   * (DH_DECTC_LAYER_FLOATS), "swz" = K-major SWIZZLE_128B image of B[n][k] (W1f: n=hidden, k=channel, LN2
+   * gamma folded; W2: n=channel, k=hidden); cbA/cbM = cumulative biases after the attention / MLP of the layer */
+  DH_W_LV5_DECTC, DH_W_LV4_DECTC, DH_W_LV3_DECTC,
   DH_W_COUNT
 };
 
@@ -193,6 +199,17 @@ int dahitra_decoder_tables(const float* mem, int B, int first_call, int ncalls, 
 int dahitra_pixel_decoder(const float* x, const float* pos, const float* tables, const float* dec_pack,
                           int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up, float* out,
                           void* stream);
+
+/* Tensor-core variants of the two decoder kernels (tcgen05, TF32 operands, fp32 accumulate in TMEM).
+ *   tables: [nimg][depth][DH_TABTC_FLOATS] = per (image-call, layer) [TA swz 32x32][TB swz 32x32][cA 32]
+ *   pack:   DH_W_LVk_DECTC (depth x DH_DECTC_LAYER_FLOATS) */
+#define DH_TABTC_FLOATS        (1024 + 1024 + 32)
+#define DH_DECTC_LAYER_FLOATS  (1024 + 1024 + 32 + 32 + 32)
+int dahitra_decoder_tables_tc(const float* mem, int B, int first_call, int ncalls, const float* dec_pack, int heads,
+                              int depth, float* tables, void* stream);
+int dahitra_pixel_decoder_tc(const float* x, const float* pos, const float* tables, const float* dectc_pack,
+                             int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up, float* out,
+                             void* stream);
 
 /* Classifier 3x3 conv 32->nc (+bias), NHWC in, NCHW logits out, optional uint8 argmax map
  * (reference models/networks.py:1249,1355; harness argmax models/evaluator.py:89-92). */

@@ -195,6 +195,35 @@ def test_pixel_decoder(k, h, w, levir_template):
     assert torch.equal(y3, y0 + sk.reshape(B, h * w, 32))
 
 
+@pytest.mark.parametrize("k,h,w", [(5, 16, 16), (4, 32, 32), (3, 64, 64), (3, 24, 40)])
+def test_pixel_decoder_tcgen05(k, h, w, levir_template):
+    """tensor-core decoder (decoder_tc.cu) vs TransformerDecoder as written; TF32 operands -> 2e-3-level tolerance,
+    and the skip hooks."""
+    from dahitra_b200.engine import prepare_weights
+    sd = dict(synth.synth_state_dict(levir_template, seed=3, style="default"))
+    heads, depth = O.LEVELS[k]["heads"], O.LEVELS[k]["depth"]
+    sd[f"pos_embedding_decoder_{k}"] = torch.randn(1, 32, h, w, generator=torch.Generator().manual_seed(5))
+    P = {n: (None if v is None else v.to(DEV)) for n, v in prepare_weights(sd, 0, 2).items()}
+    B = 2
+    x = rnd(B, h * w, 32, seed=8)
+    mem = rnd(B, 3, 4, 32, seed=9)
+    s = f"DH_W_LV{k}_"
+    tab = abi.decoder_tables_tc(mem, 0, 3, P[s + "DEC"], heads, depth)
+    xn = x.cpu().double().transpose(1, 2).reshape(B, 32, h, w)
+    for call in range(3):
+        y = abi.pixel_decoder_tc(x, P[s + "POS"], tab[call * B:(call + 1) * B].contiguous(), P[s + "DECTC"], h, w, heads, depth)
+        torch.cuda.synchronize()
+        ref = O.pixel_decoder(sd, xn, mem[:, call].cpu().double(), k, torch.float64).flatten(2).transpose(1, 2)
+        d = (y.double().cpu() - ref).abs()
+        print(f"[dec-tc] level {k} {h}x{w} call {call}: max|d|={float(d.max()):.3e} mean|d|={float(d.mean()):.3e} "
+              f"ref_absmax={float(ref.abs().max()):.3e}")
+        close(y, ref, rtol=5e-3, atol=5e-3 * float(ref.abs().max()))
+    sk = rnd(B, h, w, 32, seed=11)
+    y3 = abi.pixel_decoder_tc(x, None, tab[:B].contiguous(), P[s + "DECTC"], h, w, heads, depth, sk, 1)
+    y0 = abi.pixel_decoder_tc(x, None, tab[:B].contiguous(), P[s + "DECTC"], h, w, heads, depth)
+    assert torch.equal(y3, y0 + sk.reshape(B, h * w, 32))
+
+
 @pytest.mark.parametrize("nc", [2, 5])
 def test_classifier_and_argmax(nc):
     x = rnd(2, 48, 80, 32, seed=1)

@@ -108,6 +108,29 @@ def test_upsample_phase_filter_algebra():
     assert float((y - ref).abs().max()) < 1e-12
 
 
+def test_tensor_core_decoder_pack(levir_template):
+    """DH_W_LVk_DECTC: swizzled W1f / W2 images and cumulative biases reproduce the CUDA-core pack's algebra."""
+    from dahitra_b200.engine import prepare_weights
+    sd = synth.synth_state_dict(levir_template, seed=3, style="default")
+    P = prepare_weights(sd, 0, 2)
+    r = torch.arange(32)[:, None].expand(32, 32)
+    k = torch.arange(32)[None, :].expand(32, 32)
+    idx = (r * 32 + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3))).reshape(-1)
+    for lvl, heads, depth in ((5, 4, 4), (3, 8, 8)):
+        tc = P[f"DH_W_LV{lvl}_DECTC"].view(depth, 2144)
+        cum = torch.zeros(32)
+        for l in range(depth):
+            p = E.unpack_dec_layer(P[f"DH_W_LV{lvl}_DEC"], heads, l)
+            w1 = tc[l, :1024][idx].view(32, 32)            # B[n=o][k=c]
+            w2 = tc[l, 1024:2048][idx].view(32, 32)        # B[n=c][k=o]
+            assert torch.allclose(w1, p["W1f"].T, atol=1e-7) and torch.allclose(w2, p["W2t"].T, atol=1e-7)
+            assert torch.allclose(tc[l, 2048:2080], p["b1f"], atol=1e-7)
+            cum = cum + p["bo"]
+            assert torch.allclose(tc[l, 2080:2112], cum, atol=1e-6)
+            cum = cum + p["b2"]
+            assert torch.allclose(tc[l, 2112:2144], cum, atol=1e-6)
+
+
 def test_prepared_weights_algebra_xbd():
     from dahitra_b200.engine import prepare_weights
     from dahitra_b200.xbd import BASE_Transformer_UNet as X
