@@ -57,6 +57,7 @@ int dh_launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
 bool dh_conv_tc_eligible(const ConvArgs& a);
 int dh_launch_conv_tc(const ConvArgs& a, cudaStream_t s);
 int dh_launch_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* b, float* out, cudaStream_t s);
+int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const float* wtc, const float* b, float* out, cudaStream_t s);
 int dh_launch_maxpool(const float* in, int N, int H, int W, int C, float* out, cudaStream_t s);
 int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* b,
                          float* logits, unsigned char* amax, cudaStream_t s);

@@ -85,7 +85,7 @@ const char* kSlotNames[DH_W_COUNT] = {
   "DH_W_LV5_DECODE_WT", "DH_W_LV4_DECODE_WT", "DH_W_LV3_DECODE_WT", "DH_W_CL20A_WT", "DH_W_CL20B_WT",
   "DH_W_L2_0_C1_WT", "DH_W_L2_0_DS_WT",
   "DH_W_CL4_PSWT", "DH_W_CL4_PSB", "DH_W_CL3_PSWT", "DH_W_CL3_PSB", "DH_W_CL2_PSWT", "DH_W_CL2_PSB",
-  "DH_W_LV5_DECTC", "DH_W_LV4_DECTC", "DH_W_LV3_DECTC"};
+  "DH_W_LV5_DECTC", "DH_W_LV4_DECTC", "DH_W_LV3_DECTC", "DH_W_STEM_WTC"};
 
 // filter slot -> slot of its K-major copy (or -1)
 int wt_slot_of(int wslot) {
@@ -161,6 +161,10 @@ extern "C" int dahitra_conv2d_up2_tc(const float* in, int N, int inH, int inW, c
 extern "C" int dahitra_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* bias,
                             float* out, void* stream) {
   return dh_launch_stem(x, xbs, N, H, W, w, bias, out, (cudaStream_t)stream);
+}
+extern "C" int dahitra_stem_tc(const float* x, long long xbs, int N, int H, int W, const float* wtc, const float* bias,
+                               float* out, void* stream) {
+  return dh_launch_stem_tc(x, xbs, N, H, W, wtc, bias, out, (cudaStream_t)stream);
 }
 extern "C" int dahitra_maxpool3x3s2(const float* in, int N, int H, int W, int C, float* out, void* stream) {
   return dh_launch_maxpool(in, N, H, W, C, out, (cudaStream_t)stream);
@@ -281,9 +285,12 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
   // ---- Siamese trunk on 2B images: [pre batch | post batch]  (reference networks.py:1118-1138, 1323-1324)
   float* F2 = ws + p.f2;
   const double stem_fl = 2.0 * B * h2 * w2 * 64 * 147, stem_by = 4.0 * B * ((double)3 * H * W + (double)h2 * w2 * 64);
-  DH_STEP("stem_pre", stem_fl, stem_by, dh_launch_stem(x1, x_batch_stride, B, H, W, Wt(DH_W_STEM_W), Wt(DH_W_STEM_B), F2, s));
-  DH_STEP("stem_post", stem_fl, stem_by,
-          dh_launch_stem(x2, x_batch_stride, B, H, W, Wt(DH_W_STEM_W), Wt(DH_W_STEM_B), F2 + (size_t)B * h2 * w2 * 64, s));
+  auto stem = [&](const float* xin, float* o) -> int {
+    return (flags & DH_FLAG_STEM_TC) ? dh_launch_stem_tc(xin, x_batch_stride, B, H, W, Wt(DH_W_STEM_WTC), Wt(DH_W_STEM_B), o, s)
+                                     : dh_launch_stem(xin, x_batch_stride, B, H, W, Wt(DH_W_STEM_W), Wt(DH_W_STEM_B), o, s);
+  };
+  DH_STEP("stem_pre", stem_fl, stem_by, stem(x1, F2));
+  DH_STEP("stem_post", stem_fl, stem_by, stem(x2, F2 + (size_t)B * h2 * w2 * 64));
   float* P2 = ws + p.p2;
   DH_STEP("maxpool_2", 0.0, 4.0 * N2 * 64 * ((double)h2 * w2 + (double)h4 * w4), dh_launch_maxpool(F2, N2, h2, w2, 64, P2, s));
   float *T4a = ws + p.t4a, *T4b = ws + p.t4b, *F4 = ws + p.f4;

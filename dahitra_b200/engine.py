@@ -22,8 +22,8 @@ SCALE = 32 ** -0.5
 LEVELS = ((5, 256, 4, 4), (4, 128, 4, 4), (3, 64, 8, 8))   # (k, trunk channels, heads, decoder depth)
 
 DH_VARIANT_LEVIR, DH_VARIANT_XBD = 0, 1
-DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC = 1, 2, 4, 8
-MODES = {"fp32": 0, "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC}
+DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC, DH_FLAG_STEM_TC = 1, 2, 4, 8, 16
+MODES = {"fp32": 0, "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC | DH_FLAG_STEM_TC}
 
 
 def slot_names():
@@ -109,6 +109,9 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
             P[slot + "_WT"] = _khwc(w).T.contiguous()          # [Cout][KH*KW*Cin], K-major B operand of tcgen05.mma
 
     put_conv("DH_W_STEM", "resnet.conv1", "resnet.bn1")
+    wk = torch.zeros(160, 64, dtype=torch.float64)                       # K = 147 padded to 5 steps of 32
+    wk[:147] = P["DH_W_STEM_W"]
+    P["DH_W_STEM_WTC"] = torch.cat([swizzle128(wk[kt * 32:(kt + 1) * 32].T.contiguous()) for kt in range(5)])
     for li in (1, 2, 3):
         for bi in (0, 1):
             p = f"resnet.layer{li}.{bi}"

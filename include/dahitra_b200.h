@@ -47,7 +47,8 @@ extern "C" {
 #define DH_FLAG_TC_3XTF32   2   /* with CONV_TC: error-compensated 3xTF32 (fp32-grade accuracy) instead of 1xTF32 */
 #define DH_FLAG_TC_STRIDE2  4   /* with CONV_TC: also route the stride-2 convolutions (TMA element strides) */
 #define DH_FLAG_DEC_TC      8   /* pixel decoder on tcgen05 (TF32 operands), decoder_tc.cu */
-#define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC)   /* the "tf32" mode */
+#define DH_FLAG_STEM_TC     16  /* 7x7 stem on tcgen05 (on-chip im2col), stem_tc.cu */
+#define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC | DH_FLAG_STEM_TC)   /* the "tf32" mode */
 
 /* ---- prepared-weight table -------------------------------------------------------------------
  * dahitra_forward takes `const void* const* weights` with DH_W_COUNT slots, each a device pointer to
@@ -89,6 +90,7 @@ enum dh_weight_slot {
    * (DH_DECTC_LAYER_FLOATS), "swz" = K-major SWIZZLE_128B image of B[n][k] (W1f: n=hidden, k=channel, LN2
    * gamma folded; W2: n=channel, k=hidden); cbA/cbM = cumulative biases after the attention / MLP of the layer */
   DH_W_LV5_DECTC, DH_W_LV4_DECTC, DH_W_LV3_DECTC,
+  DH_W_STEM_WTC,   /* stem filter for the tcgen05 stem: 5 K-step tiles of B[n=co 64][k 32] swz (K = 147 padded to 160) */
   DH_W_COUNT
 };
 
@@ -166,6 +168,10 @@ int dahitra_conv2d_up2_tc(const float* in, int N, int inH, int inW, const float*
  * (reference models/networks.py:1120-1122, models/resnet.py:150-153). */
 int dahitra_stem(const float* x, long long x_batch_stride, int N, int H, int W,
                  const float* w, const float* bias, float* out, void* stream);
+
+/* Same stem on the tensor cores (TF32 operands): wtc = DH_W_STEM_WTC image. */
+int dahitra_stem_tc(const float* x, long long x_batch_stride, int N, int H, int W,
+                    const float* wtc, const float* bias, float* out, void* stream);
 
 /* MaxPool2d(3, stride 2, pad 1) on NHWC (reference models/networks.py:1123,1128). */
 int dahitra_maxpool3x3s2(const float* in, int N, int H, int W, int C, float* out, void* stream);

@@ -133,6 +133,22 @@ def test_stem(shape):
     close(y, E.stem(x.double(), w.double(), b.double()))
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 96, 160), (1, 256, 256), (1, 40, 72)])
+def test_stem_tcgen05(shape):
+    """tensor-core stem (on-chip im2col + tcgen05, TF32) vs fp64."""
+    from dahitra_b200.engine import swizzle128
+    N, H, W = shape
+    x = rnd(N, 3, H, W, seed=1)
+    w = rnd(147, 64, seed=2, scale=147 ** -0.5)
+    b = rnd(64, seed=3)
+    wk = torch.zeros(160, 64)
+    wk[:147] = w.cpu()
+    wtc = torch.cat([swizzle128(wk[kt * 32:(kt + 1) * 32].T.contiguous()) for kt in range(5)]).to(DEV)
+    y = abi.stem_tc(x, wtc, b)
+    torch.cuda.synchronize()
+    close(y, E.stem(x.double(), w.double(), b.double()), rtol=2e-3, atol=4e-3)
+
+
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64), (1, 18, 30, 128)])
 def test_maxpool_bit_exact(shape):
     x = rnd(*shape, seed=1)
