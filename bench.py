@@ -272,6 +272,9 @@ def run_native(a, wl):
                                 algorithmic_mb=sum(r["bytes"] for r in prof) / 1e6,
                                 profiled_ms=sum(r["ms"] for r in prof)))
     kernels = sorted(prof, key=lambda r: -r["ms"])[:6]
+    if a.dump_kernels:
+        os.makedirs(os.path.dirname(os.path.abspath(a.dump_kernels)), exist_ok=True)
+        json.dump(dict(flags=net._engine.flags, pairs=Bp, H=H, W=W, peaks=peaks, launches=prof), open(a.dump_kernels, "w"), indent=1)
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count())
@@ -309,6 +312,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU per step (default: the workload's)")
     ap.add_argument("--flags", type=int, default=None, help="DH_FLAG_* bitmask for the native engine")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-kernels", default=None, help="write the per-launch table (name, ms, flops, bytes) to this JSON file")
     a = ap.parse_args()
     wl = WORKLOADS[a.workload]
     if a.impl == "reference":

@@ -71,7 +71,7 @@ SIGNATURES = {
     "dahitra_decoder_tables": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "dahitra_pixel_decoder": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
     "dahitra_decoder_tables_tc": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
-    "dahitra_pixel_decoder_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
+    "dahitra_pixel_decoder_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P]),
     "dahitra_classifier": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 

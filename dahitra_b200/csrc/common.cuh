@@ -70,7 +70,8 @@ int dh_launch_decoder_tables(const float* mem, int B, int first_call, int ncalls
 int dh_launch_decoder_tables_tc(const float* mem, int B, int first_call, int ncalls, const float* dec, int heads, int depth,
                                 float* tables, cudaStream_t s);
 int dh_launch_pixel_decoder_tc(const float* x, const float* pos, const float* tables, const float* pack, int nimg, int h,
-                               int w, int heads, int depth, const float* skip, int skip_up, float* out, cudaStream_t s);
+                               int w, int heads, int depth, const float* skip, int skip_up, int x3, float* out,
+                               cudaStream_t s);
 int dh_launch_pixel_decoder(const float* x, const float* pos, const float* tables, const float* dec,
                             int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up, float* out,
                             cudaStream_t s);

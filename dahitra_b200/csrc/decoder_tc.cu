@@ -8,23 +8,34 @@
 //   * the running activation x lives in TMEM columns [0,32) for the whole call; attention and MLP outputs are
 //     accumulated INTO it by the MMA (x += P.Bv, x += G.W2).  Biases are pixel-independent, so they are applied
 //     as host-precomputed cumulative vectors when x is read back (no TMEM write-back).
-//   * A operands (xhat, P, xhat', G) are written by the threads into one 128-row K-major SWIZZLE_128B tile;
-//     B operands (per-image tables, shared MLP weights) arrive pre-swizzled from global memory through two
-//     1-D bulk copies per layer (double-buffered, prefetched one layer ahead).
-// Per layer: 4 x {write A row, fence.proxy.async, barrier, one thread issues 2-4 MMAs + commit, mbarrier wait,
-// tcgen05.ld}.  4 CTAs per SM overlap each other's serial chains.
+//   * A operands (xhat, P, xhat', G) are written by the threads into a 128-row K-major SWIZZLE_128B tile;
+//     B operands (per-image tables, shared MLP weights) arrive pre-swizzled from global memory through 1-D bulk
+//     copies (double-buffered, prefetched one layer ahead).
+//   * X3 = true: error-compensated "3xTF32".  Every operand is split v = hi + lo with hi exactly representable
+//     in TF32 (A: cvt.rna on the fly, written to a second tile; B: split by the table kernel / on the host) and
+//     each product is issued as A_hi.B_hi + A_lo.B_hi + A_hi.B_lo — fp32-grade accuracy at 3x the (tiny) MMA cost.
+// Per layer: 4 x {write A row, fence.proxy.async, barrier, one thread issues the MMAs + commit, mbarrier wait,
+// tcgen05.ld}.  Several CTAs per SM overlap each other's serial chains.
 #include "tc_common.cuh"
 
 using namespace dhtc;
 
+namespace {
+
+__device__ __forceinline__ float tf32_hi(float v) {          // nearest TF32-representable value (low 13 bits zero)
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
 // ----------------------------------------------------------------------------------------------------
-// table builder (TC layout): per (image-call, layer)  [TA swz 32x32][TB swz 32x32][cA 32]  = DH_TABTC_FLOATS
+// table builder (TC layout): per (image-call, layer)  DH_TABTC_FLOATS =
+//     [TA_hi swz 32x32][TB_hi swz 32x32][cA 32] [TA_lo swz][TB_lo swz]
 //   TA[n = h*4+j][k = c] = g_c * sum_c' Mqk[h][c][c'] mn_j[c']       (B operand of  S = xhat . TA^T)
 //   TB[n = c][k = h*4+j] =       sum_c' Mov[h][c][c'] mn_j[c']       (B operand of  x += P . TB^T)
 //   cA[h*4+j]            = sum_c b_c * (TA/g)[h*4+j][c]
+//   hi = TF32-rounded value, lo = TF32-rounded remainder (used by the 3xTF32 decoder only)
 // ----------------------------------------------------------------------------------------------------
-namespace {
-
 __device__ __forceinline__ float ln_lane32(float v, float g, float b) {
   const float mu = warp_sum(v) * (1.f / 32.f);
   const float d = v - mu;
@@ -44,7 +55,7 @@ decoder_tables_tc_kernel(const float* __restrict__ mem, int B, int first_call, c
   const float* MqkT = L + 64;
   const float* MovT = MqkT + (size_t)heads * 1024;
   float* T = tables + ((size_t)blockIdx.y * depth + layer) * DH_TABTC_FLOATS;
-  float* TA = T; float* TB = T + 1024; float* cA = T + 2048;
+  float* TA = T; float* TB = T + 1024; float* cA = T + 2048; float* TAl = T + 2080; float* TBl = T + 2080 + 1024;
   const float g = __ldg(L + lane), b = __ldg(L + 32 + lane);
   MN[j][lane] = ln_lane32(__ldg(mem + ((size_t)pair * 3 + call) * 128 + j * 32 + lane), g, b);
   __syncwarp();
@@ -59,8 +70,12 @@ decoder_tables_tc_kernel(const float* __restrict__ mem, int B, int first_call, c
       v = fmaf(__ldg(mv + c2 * 32 + lane), mn, v);
     }
     const int hj = h * 4 + j;
-    TA[sw128_idx(hj, lane)] = g * a;
-    TB[sw128_idx(lane, hj)] = v;
+    const float ga = g * a;
+    const float ga_hi = tf32_hi(ga), v_hi = tf32_hi(v);
+    TA[sw128_idx(hj, lane)] = ga_hi;
+    TAl[sw128_idx(hj, lane)] = tf32_hi(ga - ga_hi);
+    TB[sw128_idx(lane, hj)] = v_hi;
+    TBl[sw128_idx(lane, hj)] = tf32_hi(v - v_hi);
     const float ca = warp_sum(b * a);
     if (lane == 0) cA[hj] = ca;
   }
@@ -71,24 +86,25 @@ decoder_tables_tc_kernel(const float* __restrict__ mem, int B, int first_call, c
 // decoder
 // ----------------------------------------------------------------------------------------------------
 constexpr int PDT_ROWS = 128;
-constexpr uint32_t PDT_A_BYTES = 128 * 128;                 // A tile
-constexpr uint32_t PDT_TAB_BYTES = DH_TABTC_FLOATS * 4;     // 8320: TA | TB | cA
-constexpr uint32_t PDT_MLP_BYTES = DH_DECTC_LAYER_FLOATS * 4;   // 8576: W1 | W2 | b1f | cbA | cbM
-constexpr uint32_t PDT_BUF = 9216;                          // per-buffer stride (1024-aligned)
-constexpr uint32_t PDT_SMEM = PDT_A_BYTES + 4 * PDT_BUF + 1024;
+constexpr uint32_t PDT_A_BYTES = 128 * 128;                 // one A tile
+constexpr uint32_t PDT_TAB_HI = 2080 * 4;                   // TA_hi | TB_hi | cA
+constexpr uint32_t PDT_MLP_HI = 2144 * 4;                   // W1_hi | W2_hi | b1f | cbA | cbM
+constexpr uint32_t PDT_LO = 2048 * 4;                       // two 32x32 lo tiles
+constexpr uint32_t PDT_HI_STRIDE = 9216;                    // 1024-aligned room for a hi block
 
-__device__ __forceinline__ void write_a_row(float* a_tile, int row, const float (&v)[32]) {
-#pragma unroll
-  for (int ch = 0; ch < 8; ++ch)
-    *reinterpret_cast<float4*>(a_tile + row * 32 + ((ch ^ (row & 7)) << 2)) =
-        make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
-}
+template <bool X3> struct PdtCfg {
+  static constexpr uint32_t BUF = PDT_HI_STRIDE + (X3 ? PDT_LO : 0);            // one table (or MLP) buffer
+  static constexpr uint32_t A_TILES = X3 ? 2 : 1;
+  static constexpr uint32_t SMEM = A_TILES * PDT_A_BYTES + 4 * BUF + 1024;
+  static constexpr int CTAS = X3 ? 2 : 4;
+};
 
-template <int HEADS>
-__global__ void __launch_bounds__(PDT_ROWS, 4)
+template <int HEADS, bool X3>
+__global__ void __launch_bounds__(PDT_ROWS, PdtCfg<X3>::CTAS)
 pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const float* __restrict__ tables,
                         const float* __restrict__ pack, int npix, int w, int depth, const float* __restrict__ skip,
                         int skip_up, float* __restrict__ out) {
+  using Cfg = PdtCfg<X3>;
   constexpr int H4 = HEADS * 4;
   constexpr uint32_t IDESC_S = umma_idesc_tf32(128, H4);
   constexpr uint32_t IDESC_32 = umma_idesc_tf32(128, 32);
@@ -101,12 +117,14 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   const bool valid = p < npix;
   const uint32_t base = (smem_u32(pdt_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = pdt_raw + (base - smem_u32(pdt_raw));
-  float* a_tile = reinterpret_cast<float*>(base_ptr);
+  float* a_hi = reinterpret_cast<float*>(base_ptr);
+  float* a_lo = reinterpret_cast<float*>(base_ptr + PDT_A_BYTES);       // X3 only
   const uint32_t a_addr = base;
-  auto tab_addr = [&](int b) { return base + PDT_A_BYTES + (uint32_t)b * PDT_BUF; };
-  auto mlp_addr = [&](int b) { return base + PDT_A_BYTES + 2 * PDT_BUF + (uint32_t)b * PDT_BUF; };
-  auto tab_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + PDT_A_BYTES + (size_t)b * PDT_BUF); };
-  auto mlp_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + PDT_A_BYTES + 2 * PDT_BUF + (size_t)b * PDT_BUF); };
+  constexpr uint32_t BUFS0 = Cfg::A_TILES * PDT_A_BYTES;
+  auto tab_addr = [&](int b) { return base + BUFS0 + (uint32_t)b * Cfg::BUF; };
+  auto mlp_addr = [&](int b) { return base + BUFS0 + 2 * Cfg::BUF + (uint32_t)b * Cfg::BUF; };
+  auto tab_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + BUFS0 + (size_t)b * Cfg::BUF); };
+  auto mlp_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + BUFS0 + 2 * Cfg::BUF + (size_t)b * Cfg::BUF); };
 
   if (tid == 0) {
     mbar_init(smem_u32(&tab_bar[0]), 1); mbar_init(smem_u32(&tab_bar[1]), 1); mbar_init(smem_u32(&mma_bar), 1);
@@ -122,9 +140,15 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   auto issue_loads = [&](int layer) {
     const int b = layer & 1;
     const uint32_t bar = smem_u32(&tab_bar[b]);
-    mbar_expect_tx(bar, PDT_TAB_BYTES + PDT_MLP_BYTES);
-    bulk_load_1d(tab_addr(b), tables + ((size_t)img * depth + layer) * DH_TABTC_FLOATS, PDT_TAB_BYTES, bar);
-    bulk_load_1d(mlp_addr(b), pack + (size_t)layer * DH_DECTC_LAYER_FLOATS, PDT_MLP_BYTES, bar);
+    const float* tg = tables + ((size_t)img * depth + layer) * DH_TABTC_FLOATS;
+    const float* pg = pack + (size_t)layer * DH_DECTC_LAYER_FLOATS;
+    mbar_expect_tx(bar, PDT_TAB_HI + PDT_MLP_HI + (X3 ? 2 * PDT_LO : 0));
+    bulk_load_1d(tab_addr(b), tg, PDT_TAB_HI, bar);
+    bulk_load_1d(mlp_addr(b), pg, PDT_MLP_HI, bar);
+    if (X3) {
+      bulk_load_1d(tab_addr(b) + PDT_HI_STRIDE, tg + 2080, PDT_LO, bar);
+      bulk_load_1d(mlp_addr(b) + PDT_HI_STRIDE, pg + 2144, PDT_LO, bar);
+    }
   };
   if (tid == 0) issue_loads(0);
 
@@ -156,18 +180,36 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     tmem_st32(tmem + TM_X, u);
   }
 
+  // this thread's row of the A operand: TF32-rounded values (hi tile) and, for X3, the remainders (lo tile)
+  auto write_a_row = [&](const float (&v)[32]) {
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      const int o = tid * 32 + ((ch ^ (tid & 7)) << 2);
+      const float h0 = tf32_hi(v[ch * 4]), h1 = tf32_hi(v[ch * 4 + 1]), h2 = tf32_hi(v[ch * 4 + 2]), h3 = tf32_hi(v[ch * 4 + 3]);
+      *reinterpret_cast<float4*>(a_hi + o) = make_float4(h0, h1, h2, h3);
+      if (X3) *reinterpret_cast<float4*>(a_lo + o) = make_float4(v[ch * 4] - h0, v[ch * 4 + 1] - h1, v[ch * 4 + 2] - h2, v[ch * 4 + 3] - h3);
+    }
+  };
+
   uint32_t mma_phase = 0;
-  // one MMA round: all rows of the A tile are written -> thread 0 issues `nk` K-steps -> everyone waits for the commit
-  auto mma_round = [&](uint32_t b_addr, uint32_t idesc, uint32_t tm_col, int nk, bool accumulate, int prefetch_layer) {
+  // one MMA round: all rows of the A tile(s) are written -> thread 0 issues `nk` K-steps -> everyone waits for the commit.
+  // b_hi_addr: hi tile of the B operand; its lo twin sits PDT_HI_STRIDE-relative at the same offset inside the lo block.
+  auto mma_round = [&](uint32_t b_hi_addr, uint32_t b_lo_addr, uint32_t idesc, uint32_t tm_col, int nk, bool accumulate,
+                       int prefetch_layer) {
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       if (prefetch_layer >= 0) issue_loads(prefetch_layer);
       tc_fence_after();
-      const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(b_addr);
-      for (int k = 0; k < nk; ++k)
-        umma_tf32(tmem_slot + tm_col, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (accumulate || k) ? 1u : 0u);
+      const uint64_t ah = umma_desc_sw128(a_addr), bh = umma_desc_sw128(b_hi_addr);
+      const uint32_t d = tmem_slot + tm_col;
+      for (int k = 0; k < nk; ++k) umma_tf32(d, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, (accumulate || k) ? 1u : 0u);
+      if (X3) {
+        const uint64_t al = umma_desc_sw128(a_addr + PDT_A_BYTES), bl = umma_desc_sw128(b_lo_addr);
+        for (int k = 0; k < nk; ++k) umma_tf32(d, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, 1u);
+        for (int k = 0; k < nk; ++k) umma_tf32(d, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
+      }
       umma_commit(smem_u32(&mma_bar));
     }
     mbar_wait(smem_u32(&mma_bar), mma_phase);
@@ -182,6 +224,8 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     const float* mlpp = mlp_ptr(b);
     const float* cA = tabp + 2048;
     const float* b1f = mlpp + 2048; const float* cbA = mlpp + 2080; const float* cbM = mlpp + 2112;
+    const uint32_t t_hi = tab_addr(b), t_lo = tab_addr(b) + PDT_HI_STRIDE;
+    const uint32_t m_hi = mlp_addr(b), m_lo = mlp_addr(b) + PDT_HI_STRIDE;
     float t[32];
     // ---- 1. S = xhat . TA^T
     {
@@ -195,10 +239,10 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       const float rstd = 1.0f / sqrtf(var * (1.f / 32.f) + 1e-5f);
 #pragma unroll
       for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
-      write_a_row(a_tile, tid, t);
+      write_a_row(t);
     }
     // the buffer of layer+1 was last read in layer-1; every thread is past that once it reaches this barrier
-    mma_round(tab_addr(b), IDESC_S, TM_S, 4, false, (layer + 1 < depth) ? layer + 1 : -1);
+    mma_round(t_hi, t_lo, IDESC_S, TM_S, 4, false, (layer + 1 < depth) ? layer + 1 : -1);
     // ---- 2. P = softmax_j(S + cA) ; x += P . TB^T
     {
       if constexpr (HEADS == 8) {
@@ -221,9 +265,9 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
         const float inv = 1.0f / (e0 + e1 + e2 + e3);
         t[h * 4] = e0 * inv; t[h * 4 + 1] = e1 * inv; t[h * 4 + 2] = e2 * inv; t[h * 4 + 3] = e3 * inv;
       }
-      write_a_row(a_tile, tid, t);
+      write_a_row(t);
     }
-    mma_round(tab_addr(b) + 4096, IDESC_32, TM_X, H4 / 8, true, -1);
+    mma_round(t_hi + 4096, t_lo + 4096, IDESC_32, TM_X, H4 / 8, true, -1);
     // ---- 3. Hid = xhat' . W1f^T
     {
       uint32_t u[32];
@@ -238,18 +282,18 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       const float rstd = 1.0f / sqrtf(var * (1.f / 32.f) + 1e-5f);
 #pragma unroll
       for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
-      write_a_row(a_tile, tid, t);
+      write_a_row(t);
     }
-    mma_round(mlp_addr(b), IDESC_32, TM_H, 4, false, -1);
+    mma_round(m_hi, m_lo, IDESC_32, TM_H, 4, false, -1);
     // ---- 4. x += gelu(Hid + b1f) . W2^T
     {
       uint32_t u[32];
       tmem_ld32(tmem + TM_H, u);
 #pragma unroll
       for (int c = 0; c < 32; ++c) t[c] = gelu_erf(__uint_as_float(u[c]) + b1f[c]);
-      write_a_row(a_tile, tid, t);
+      write_a_row(t);
     }
-    mma_round(mlp_addr(b) + 4096, IDESC_32, TM_X, 4, true, -1);
+    mma_round(m_hi + 4096, m_lo + 4096, IDESC_32, TM_X, 4, true, -1);
     {
       uint32_t u[32];
       tmem_ld32(tmem + TM_X, u);
@@ -281,6 +325,17 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     tmem_dealloc(tmem_slot, 128);
   }
 }
+
+template <int HEADS, bool X3>
+int launch_pdt(dim3 grid, const float* x, const float* pos, const float* tables, const float* pack, int npix, int w, int depth,
+               const float* skip, int skip_up, float* out, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(pixel_decoder_tc_kernel<HEADS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)PdtCfg<X3>::SMEM);
+  if (e != cudaSuccess) return (int)e;
+  pixel_decoder_tc_kernel<HEADS, X3><<<grid, PDT_ROWS, PdtCfg<X3>::SMEM, s>>>(x, pos, tables, pack, npix, w, depth, skip, skip_up, out);
+  DH_CHECK_LAUNCH();
+  return 0;
+}
 }  // namespace
 
 int dh_launch_decoder_tables_tc(const float* mem, int B, int first_call, int ncalls, const float* dec, int heads, int depth,
@@ -295,7 +350,8 @@ int dh_launch_decoder_tables_tc(const float* mem, int B, int first_call, int nca
 }
 
 int dh_launch_pixel_decoder_tc(const float* x, const float* pos, const float* tables, const float* pack, int nimg, int h,
-                               int w, int heads, int depth, const float* skip, int skip_up, float* out, cudaStream_t s) {
+                               int w, int heads, int depth, const float* skip, int skip_up, int x3, float* out,
+                               cudaStream_t s) {
   DH_REQUIRE(x && tables && pack && out, DH_E_NULL);
   DH_REQUIRE(nimg > 0 && h > 0 && w > 0 && depth >= 1 && (heads == 4 || heads == 8), DH_E_SHAPE);
   DH_REQUIRE(!skip || skip_up == 1 || (skip_up == 2 && h % 2 == 0 && w % 2 == 0), DH_E_SHAPE);
@@ -303,16 +359,9 @@ int dh_launch_pixel_decoder_tc(const float* x, const float* pos, const float* ta
              dh_aligned16(out), DH_E_ALIGN);
   const int npix = h * w;
   dim3 grid(dh_cdiv(npix, PDT_ROWS), nimg);
-  cudaError_t e;
-  if (heads == 4) {
-    e = cudaFuncSetAttribute(pixel_decoder_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PDT_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    pixel_decoder_tc_kernel<4><<<grid, PDT_ROWS, PDT_SMEM, s>>>(x, pos, tables, pack, npix, w, depth, skip, skip_up, out);
-  } else {
-    e = cudaFuncSetAttribute(pixel_decoder_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PDT_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    pixel_decoder_tc_kernel<8><<<grid, PDT_ROWS, PDT_SMEM, s>>>(x, pos, tables, pack, npix, w, depth, skip, skip_up, out);
-  }
-  DH_CHECK_LAUNCH();
-  return 0;
+  if (heads == 4)
+    return x3 ? launch_pdt<4, true>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, s)
+              : launch_pdt<4, false>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, s);
+  return x3 ? launch_pdt<8, true>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, s)
+            : launch_pdt<8, false>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, s);
 }

@@ -193,8 +193,8 @@ extern "C" int dahitra_decoder_tables_tc(const float* mem, int B, int first_call
 }
 extern "C" int dahitra_pixel_decoder_tc(const float* x, const float* pos, const float* tables, const float* dectc_pack,
                                         int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up,
-                                        float* out, void* stream) {
-  return dh_launch_pixel_decoder_tc(x, pos, tables, dectc_pack, nimg, h, w, heads, depth, skip, skip_up, out,
+                                        int x3, float* out, void* stream) {
+  return dh_launch_pixel_decoder_tc(x, pos, tables, dectc_pack, nimg, h, w, heads, depth, skip, skip_up, x3, out,
                                     (cudaStream_t)stream);
 }
 extern "C" int dahitra_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* bias,
@@ -350,7 +350,8 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
                  : dh_launch_decoder_tables(MEM, B, first, ncalls, dec, L.heads, L.depth, TAB, s);
     };
     auto decode = [&](const float* xin, const float* tab, int nimg, const float* sk, int sku, float* o) -> int {
-      return dtc ? dh_launch_pixel_decoder_tc(xin, pos, tab, dectc, nimg, L.h, L.w, L.heads, L.depth, sk, sku, o, s)
+      return dtc ? dh_launch_pixel_decoder_tc(xin, pos, tab, dectc, nimg, L.h, L.w, L.heads, L.depth, sk, sku,
+                                              (flags & DH_FLAG_DEC_TC_X3) ? 1 : 0, o, s)
                  : dh_launch_pixel_decoder(xin, pos, tab, dec, nimg, L.h, L.w, L.heads, L.depth, sk, sku, o, s);
     };
     if (variant == DH_VARIANT_LEVIR) {

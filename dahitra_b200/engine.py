@@ -22,8 +22,13 @@ SCALE = 32 ** -0.5
 LEVELS = ((5, 256, 4, 4), (4, 128, 4, 4), (3, 64, 8, 8))   # (k, trunk channels, heads, decoder depth)
 
 DH_VARIANT_LEVIR, DH_VARIANT_XBD = 0, 1
-DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC, DH_FLAG_STEM_TC = 1, 2, 4, 8, 16
-MODES = {"fp32": 0, "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC | DH_FLAG_STEM_TC}
+DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC, DH_FLAG_STEM_TC, DH_FLAG_DEC_TC_X3 = 1, 2, 4, 8, 16, 32
+MODES = {
+    "fp32": 0,                                             # every contraction in fp32 FMA (strict)
+    "fp32_tcdec": DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,      # strict + the 3xTF32 (fp32-grade) tensor-core decoder
+    "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
+    "tf32_fast": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC,   # 1xTF32 decoder too
+}
 
 
 def slot_names():
@@ -74,6 +79,19 @@ def upsample_phase_filter(w, b):
                             acc += w[:, :, r, s]
                     W3[py * 2 + px, :, u + 1, v + 1, :] = acc
     return W3.reshape(4 * cout, 9 * cin), b.repeat(4)
+
+
+def tf32_round(x):
+    """nearest TF32-representable value (10 explicit mantissa bits; ties away from zero like cvt.rna.tf32.f32)"""
+    b = x.to(torch.float32).contiguous().view(torch.int32)
+    return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def tf32_split(x):
+    """x (float64) -> (hi, lo) float64 with hi, lo exactly representable in TF32 and hi + lo = x to ~2^-22 relative."""
+    hi = tf32_round(x).double()
+    lo = tf32_round(x - hi).double()
+    return hi, lo
 
 
 def swizzle128(m):
@@ -170,7 +188,9 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
             w2, b2 = sd[d + ".1.fn.fn.net.3.weight"].double(), sd[d + ".1.fn.fn.net.3.bias"].double()
             cba = cum + sd[d + ".0.fn.fn.to_out.0.bias"].double()
             cum = cba + b2
-            tc_layers += [swizzle128(w1 * g2[None, :]), swizzle128(w2), b1 + w1 @ b2n, cba, cum.clone()]
+            w1h, w1l = tf32_split(w1 * g2[None, :])
+            w2h, w2l = tf32_split(w2)
+            tc_layers += [swizzle128(w1h), swizzle128(w2h), b1 + w1 @ b2n, cba, cum.clone(), swizzle128(w1l), swizzle128(w2l)]
         P[s + "DECTC"] = torch.cat(tc_layers)
         # ---- decoder positional embedding
         if variant == DH_VARIANT_LEVIR:

@@ -48,6 +48,7 @@ extern "C" {
 #define DH_FLAG_TC_STRIDE2  4   /* with CONV_TC: also route the stride-2 convolutions (TMA element strides) */
 #define DH_FLAG_DEC_TC      8   /* pixel decoder on tcgen05 (TF32 operands), decoder_tc.cu */
 #define DH_FLAG_STEM_TC     16  /* 7x7 stem on tcgen05 (on-chip im2col), stem_tc.cu */
+#define DH_FLAG_DEC_TC_X3   32  /* with DEC_TC: error-compensated 3xTF32 in the decoder (fp32-grade accuracy) */
 #define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC | DH_FLAG_STEM_TC)   /* the "tf32" mode */
 
 /* ---- prepared-weight table -------------------------------------------------------------------
@@ -208,14 +209,17 @@ int dahitra_pixel_decoder(const float* x, const float* pos, const float* tables,
 
 /* Tensor-core variants of the two decoder kernels (tcgen05, TF32 operands, fp32 accumulate in TMEM).
  *   tables: [nimg][depth][DH_TABTC_FLOATS] = per (image-call, layer) [TA swz 32x32][TB swz 32x32][cA 32]
- *   pack:   DH_W_LVk_DECTC (depth x DH_DECTC_LAYER_FLOATS) */
-#define DH_TABTC_FLOATS        (1024 + 1024 + 32)
-#define DH_DECTC_LAYER_FLOATS  (1024 + 1024 + 32 + 32 + 32)
+ *   pack:   DH_W_LVk_DECTC (depth x DH_DECTC_LAYER_FLOATS)
+ *   x3 != 0: error-compensated 3xTF32 (operands split hi + lo, three MMAs per product): fp32-grade accuracy.
+ *   Every B operand is stored as a TF32-rounded "hi" tile plus a "lo" remainder tile:
+ *     table record  [TA_hi][TB_hi][cA 32][TA_lo][TB_lo],  pack layer  [W1_hi][W2_hi][b1f][cbA][cbM][W1_lo][W2_lo] */
+#define DH_TABTC_FLOATS        (1024 + 1024 + 32 + 2048)
+#define DH_DECTC_LAYER_FLOATS  (1024 + 1024 + 32 + 32 + 32 + 2048)
 int dahitra_decoder_tables_tc(const float* mem, int B, int first_call, int ncalls, const float* dec_pack, int heads,
                               int depth, float* tables, void* stream);
 int dahitra_pixel_decoder_tc(const float* x, const float* pos, const float* tables, const float* dectc_pack,
-                             int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up, float* out,
-                             void* stream);
+                             int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up, int x3,
+                             float* out, void* stream);
 
 /* Classifier 3x3 conv 32->nc (+bias), NHWC in, NCHW logits out, optional uint8 argmax map
  * (reference models/networks.py:1249,1355; harness argmax models/evaluator.py:89-92). */

@@ -101,17 +101,17 @@ def pixel_decoder(x, pos, tab, dec, h, w, heads, depth, skip=None, skip_up=1):
 def decoder_tables_tc(mem, first_call, ncalls, dec, heads, depth):
     lib = _lib.load()
     B = mem.shape[0]
-    tab = torch.empty((ncalls * B, depth, 2080), device=mem.device, dtype=torch.float32)
+    tab = torch.empty((ncalls * B, depth, 4128), device=mem.device, dtype=torch.float32)
     _lib.check(lib.dahitra_decoder_tables_tc(_p(mem), B, first_call, ncalls, _p(dec), heads, depth, _p(tab), _stream()),
                "dahitra_decoder_tables_tc")
     return tab
 
 
-def pixel_decoder_tc(x, pos, tab, dectc, h, w, heads, depth, skip=None, skip_up=1):
+def pixel_decoder_tc(x, pos, tab, dectc, h, w, heads, depth, skip=None, skip_up=1, x3=0):
     lib = _lib.load()
     out = torch.empty_like(x)
     _lib.check(lib.dahitra_pixel_decoder_tc(_p(x), _p(pos), _p(tab), _p(dectc), x.shape[0], h, w, heads, depth, _p(skip),
-                                            skip_up, _p(out), _stream()), "dahitra_pixel_decoder_tc")
+                                            skip_up, x3, _p(out), _stream()), "dahitra_pixel_decoder_tc")
     return out
 
 

@@ -227,16 +227,21 @@ def test_pixel_decoder_tcgen05(k, h, w, levir_template):
     tab = abi.decoder_tables_tc(mem, 0, 3, P[s + "DEC"], heads, depth)
     xn = x.cpu().double().transpose(1, 2).reshape(B, 32, h, w)
     for call in range(3):
-        y = abi.pixel_decoder_tc(x, P[s + "POS"], tab[call * B:(call + 1) * B].contiguous(), P[s + "DECTC"], h, w, heads, depth)
-        torch.cuda.synchronize()
         ref = O.pixel_decoder(sd, xn, mem[:, call].cpu().double(), k, torch.float64).flatten(2).transpose(1, 2)
-        d = (y.double().cpu() - ref).abs()
-        print(f"[dec-tc] level {k} {h}x{w} call {call}: max|d|={float(d.max()):.3e} mean|d|={float(d.mean()):.3e} "
-              f"ref_absmax={float(ref.abs().max()):.3e}")
-        close(y, ref, rtol=5e-3, atol=5e-3 * float(ref.abs().max()))
+        for x3 in (1, 0):
+            y = abi.pixel_decoder_tc(x, P[s + "POS"], tab[call * B:(call + 1) * B].contiguous(), P[s + "DECTC"], h, w, heads,
+                                     depth, x3=x3)
+            torch.cuda.synchronize()
+            d = (y.double().cpu() - ref).abs()
+            print(f"[dec-tc] level {k} {h}x{w} call {call} {'3xTF32' if x3 else '1xTF32'}: max|d|={float(d.max()):.3e} "
+                  f"mean|d|={float(d.mean()):.3e} ref_absmax={float(ref.abs().max()):.3e}")
+            if x3:      # error-compensated: same tolerance as the fp32 CUDA-core decoder
+                close(y, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().max()))
+            else:       # single-pass TF32 on random (ill-conditioned) tables: percent-level worst case
+                assert float(d.mean()) < 2e-3 * float(ref.abs().max()) and float(d.max()) < 5e-2 * float(ref.abs().max())
     sk = rnd(B, h, w, 32, seed=11)
-    y3 = abi.pixel_decoder_tc(x, None, tab[:B].contiguous(), P[s + "DECTC"], h, w, heads, depth, sk, 1)
-    y0 = abi.pixel_decoder_tc(x, None, tab[:B].contiguous(), P[s + "DECTC"], h, w, heads, depth)
+    y3 = abi.pixel_decoder_tc(x, None, tab[:B].contiguous(), P[s + "DECTC"], h, w, heads, depth, sk, 1, x3=1)
+    y0 = abi.pixel_decoder_tc(x, None, tab[:B].contiguous(), P[s + "DECTC"], h, w, heads, depth, x3=1)
     assert torch.equal(y3, y0 + sk.reshape(B, h * w, 32))
 
 

@@ -117,13 +117,17 @@ def test_tensor_core_decoder_pack(levir_template):
     k = torch.arange(32)[None, :].expand(32, 32)
     idx = (r * 32 + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3))).reshape(-1)
     for lvl, heads, depth in ((5, 4, 4), (3, 8, 8)):
-        tc = P[f"DH_W_LV{lvl}_DECTC"].view(depth, 2144)
+        tc = P[f"DH_W_LV{lvl}_DECTC"].view(depth, 4192)
         cum = torch.zeros(32)
         for l in range(depth):
             p = E.unpack_dec_layer(P[f"DH_W_LV{lvl}_DEC"], heads, l)
-            w1 = tc[l, :1024][idx].view(32, 32)            # B[n=o][k=c]
-            w2 = tc[l, 1024:2048][idx].view(32, 32)        # B[n=c][k=o]
-            assert torch.allclose(w1, p["W1f"].T, atol=1e-7) and torch.allclose(w2, p["W2t"].T, atol=1e-7)
+            w1h, w2h = tc[l, :1024][idx].view(32, 32), tc[l, 1024:2048][idx].view(32, 32)      # B[n=o][k=c], B[n=c][k=o]
+            w1l, w2l = tc[l, 2144:3168][idx].view(32, 32), tc[l, 3168:4192][idx].view(32, 32)
+            for t in (w1h, w2h, w1l, w2l):                 # every tile is exactly TF32-representable
+                assert int((t.view(torch.int32) & 0x1FFF).abs().sum()) == 0
+            assert torch.allclose(w1h + w1l, p["W1f"].T, rtol=1e-6, atol=1e-9)
+            assert torch.allclose(w2h + w2l, p["W2t"].T, rtol=1e-6, atol=1e-9)
+            assert float((w1h - p["W1f"].T).abs().max()) <= 2 ** -11 * float(p["W1f"].abs().max())
             assert torch.allclose(tc[l, 2048:2080], p["b1f"], atol=1e-7)
             cum = cum + p["bo"]
             assert torch.allclose(tc[l, 2080:2112], cum, atol=1e-6)
