@@ -32,6 +32,7 @@ WORKLOADS = {
     "xbd1024": dict(H=1024, W=1024, pairs=8, nc=5, variant="xbd",
                     desc="xBD 1024x1024 pre/post pair 5-class forward, 8 pairs per GPU per step"),
 }
+DEFAULT_MODE = "tf32x3"
 FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0)
 
 
@@ -176,8 +177,9 @@ def run_native(a, wl):
     else:
         net = XNet(input_nc=3, output_nc=wl["nc"], token_len=4, resnet_stages_num=4, with_pos="learned",
                    with_decoder_pos="learned", enc_depth=1, dec_depth=8).to(dev).eval()
-    if a.flags is not None:
-        net._engine.flags = a.flags
+    from dahitra_b200.engine import MODES
+    net._engine.flags = a.flags if a.flags is not None else MODES[a.mode]
+    mode_name = next((k for k, v in MODES.items() if v == net._engine.flags), f"flags{net._engine.flags}")
     # rotating input sets so consecutive steps never re-read the same inputs from L2 (3 x 100 MB > 126 MB L2;
     # the ~3.5 GB of per-step intermediates stream through HBM regardless)
     nsets = 3
@@ -229,7 +231,24 @@ def run_native(a, wl):
         for i in range(a.steps):
             e2e_step(i)
         barrier()
-        e2e_sec = time.perf_counter() - t0
+        e2e_sync_sec = time.perf_counter() - t0
+        # same end-to-end work through the pipelined public API (dahitra_b200.pipeline.PairPipeline): the upload of
+        # batch i+1 overlaps the forward of batch i; the class map comes back as the fused uint8 argmax
+        e2e_sec, e2e_d2h = e2e_sync_sec, Bp * H * W * 8
+        if wl["variant"] == "levir":
+            from dahitra_b200.pipeline import PairPipeline
+            pipe = PairPipeline(net, out="argmax_u8")
+            for _ in pipe.run(hx[i % nsets] for i in range(3)):
+                pass
+            barrier()
+            t0 = time.perf_counter()
+            nres = 0
+            for pred in pipe.run(hx[i % nsets] for i in range(a.steps)):
+                nres += 1
+            barrier()
+            e2e_sec = time.perf_counter() - t0
+            e2e_d2h = Bp * H * W
+            assert nres == a.steps
         clocks = sampler.stop() if sampler else None
         # ---- per-launch profile (after the timed regions): roofline of the dominant kernel
         prof = None
@@ -237,10 +256,39 @@ def run_native(a, wl):
             runs = [net._engine.profile_pair(net, *sets[i % nsets]) for i in range(3)]
             prof = [dict(name=r["name"], flops=r["flops"], bytes=r["bytes"],
                          ms=statistics.mean(x[j]["ms"] for x in runs)) for j, r in enumerate(runs[0])]
-    tmax = torch.tensor([ms, e2e_sec * 1e3], device=dev, dtype=torch.float64)
+        # ---- in-run parity of the timed mode against the strict fp32 mode (same weights, same inputs), and the
+        #      strict mode's own throughput for reference
+        parity, strict = None, None
+        if rank == 0 and wl["variant"] == "levir":
+            nb = min(8, Bp)
+            xa, xb = sets[0][0][:nb].contiguous(), sets[0][1][:nb].contiguous()
+            y_mode = net(xa, xb).double()
+            saved = net._engine.flags
+            net._engine.flags = 0
+            net.invalidate_native_cache()
+            y_ref = net(xa, xb).double()
+            d = (y_mode - y_ref).abs()
+            parity = dict(against="strict fp32 mode (flags 0), same weights and inputs, %d pairs" % nb,
+                          max_abs=float(d.max()), mean_abs=float(d.mean()), ref_abs_max=float(y_ref.abs().max()),
+                          outside_tol=int((d > 1e-4 + 1e-3 * y_ref.abs()).sum()), tol="1e-4 + 1e-3*|ref|", elements=d.numel(),
+                          argmax_agree=float((y_mode.argmax(1) == y_ref.argmax(1)).float().mean()))
+            if saved != 0:
+                for i in range(2):
+                    step(i)
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                s0.record()
+                for i in range(5):
+                    step(i)
+                s1.record()
+                torch.cuda.synchronize()
+                strict = dict(mode="fp32", value=Bp / (s0.elapsed_time(s1) / 5 / 1e3), unit="pairs/s per GPU")
+            net._engine.flags = saved
+            net.invalidate_native_cache()
+    tmax = torch.tensor([ms, e2e_sec * 1e3, e2e_sync_sec * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(tmax[0]), float(tmax[1])
+    ms, e2e_ms, e2e_sync_ms = float(tmax[0]), float(tmax[1]), float(tmax[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -264,7 +312,7 @@ def run_native(a, wl):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")      # per-launch DRAM bytes from the committed ncu capture
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(top["name"])
+        traffic = json.load(open(tpath)).get(mode_name, {}).get(top["name"])
     roof.update(traffic=traffic, peak_source=f"MEASURED_PEAKS.json ({peak_src}; sustained bf16 for a kernel inside a step)",
                 ai_flop_per_byte=ai, launch_ms=top["ms"], share_of_step=top["ms"] / sum(r["ms"] for r in prof),
                 algorithmic_flops=top["flops"], algorithmic_bytes=top["bytes"],
@@ -283,15 +331,21 @@ def run_native(a, wl):
         cpu = dict(value=v, unit="pairs/s", cores=torch.get_num_threads(), kind="port",
                    sample=f"oracle port (torch CPU fp32), {cp} pairs per call, mean of 3 calls after 1 warm-up ({sec:.2f} s/call)")
     line = dict(metric="image-pairs/sec", value=value, unit="pairs/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
-                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype={"fp32": "f32", "tf32": "tf32", "tf32_fast": "tf32", "tf32x3": "tf32x3 (error-compensated, fp32-grade)"}.get(mode_name, "f32/tf32"),
+                data="synthetic",
                 config=dict(workload=wl["desc"], H=H, W=W, pairs_per_gpu=Bp, global_pairs_per_step=world * Bp,
                             sharding="by image pair, one process per GPU, no collective",
-                            weights="torch.manual_seed(0); define_G random init", flags=net._engine.flags,
+                            weights="torch.manual_seed(0); define_G random init", mode=mode_name, flags=net._engine.flags,
                             l2="3 rotating input sets (3x%.0f MB) + multi-GB per-step intermediates >> 126 MB L2" % (2 * Bp * 3 * H * W * 4 / 1e6)),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit="pairs/s", h2d_bytes_per_step=2 * Bp * 3 * H * W * 4,
-                         d2h_bytes_per_step=Bp * H * W * 8, ms_per_step=e2e_ms / a.steps,
-                         api="net(x1.to(dev), x2.to(dev)); torch.argmax(.,1) -> pinned host int64 map; per-step sync"),
+                         d2h_bytes_per_step=e2e_d2h, ms_per_step=e2e_ms / a.steps,
+                         api="dahitra_b200.pipeline.PairPipeline(net).run(pinned host batches): H2D of batch i+1 overlaps the "
+                             "forward of batch i; uint8 class map D2H every step",
+                         unpipelined=dict(value=world * Bp * a.steps / (e2e_sync_ms / 1e3), d2h_bytes_per_step=Bp * H * W * 8,
+                                          api="net(x1.to(dev), x2.to(dev)); torch.argmax(.,1) -> pinned host int64 map; per-step sync")),
+                parity=parity, strict_fp32=strict,
                 gpu_launches=len(prof) * a.steps, launches_per_step=len(prof),
                 roofline=roof, top_kernels=[dict(name=k["name"], ms=round(k["ms"], 4)) for k in kernels])
     if cpu:
@@ -310,7 +364,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="levir256", choices=list(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU per step (default: the workload's)")
-    ap.add_argument("--flags", type=int, default=None, help="DH_FLAG_* bitmask for the native engine")
+    ap.add_argument("--mode", default=DEFAULT_MODE, help="precision mode of the native engine: fp32 | tf32 | tf32_fast | tf32x3")
+    ap.add_argument("--flags", type=int, default=None, help="raw DH_FLAG_* bitmask (overrides --mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-kernels", default=None, help="write the per-launch table (name, ms, flops, bytes) to this JSON file")
     a = ap.parse_args()

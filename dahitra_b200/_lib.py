@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdahitra_b200.so")
-SOURCES = ["conv_ffma.cu", "conv_tc.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "aux.cu", "forward.cu"]
+SOURCES = ["conv_ffma.cu", "conv_tc.cu", "conv_tc2.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "aux.cu", "forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -62,7 +62,7 @@ SIGNATURES = {
     "dahitra_forward_profiled": (_I, [_P, _I, _P, _P, _LL, _P, _P, _P, _SZ, _I, _I, _I, _I, _I, _I, _P,
                                       _I, _P, _P, _P, _P]),
     "dahitra_conv2d": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P]),
-    "dahitra_conv2d_up2_tc": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "dahitra_conv2d_up2_tc": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
     "dahitra_stem": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P, _P]),
     "dahitra_stem_tc": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P, _P]),
     "dahitra_maxpool3x3s2": (_I, [_P, _I, _I, _I, _I, _P, _P]),

@@ -1,0 +1,325 @@
+// dahitra_b200 — implicit-GEMM convolution on tcgen05, halo-reuse variant (stride 1, 3x3 or 1x1), with an
+// optional error-compensated 3xTF32 mode that brings the tensor-core path to fp32-grade accuracy.
+//
+//   D[m][co] = sum_{chunk, tap, ci} X[pixel(m) + tap][chunk*32 + ci] * Wt[co][tap*Cin + chunk*32 + ci]
+//   M tile = 128 output pixels = 16 rows x 8 columns of one image  (row m = y*8 + x: every 8-row UMMA atom is
+//            8 horizontally adjacent pixels)
+//   For each 32-channel chunk the (16+2) x (8+2) input HALO is fetched ONCE by one 4-D TMA box {32ch,10,18,1}
+//   (zero-filled outside the image = the conv padding) and stays in shared memory for all 9 taps: the A operand
+//   of tap (r,s) is the SAME buffer addressed through a UMMA descriptor whose start is shifted by (r*10+s) pixels
+//   (x128 B) with a stride-byte-offset of 10 pixels.  tcgen05 applies the 128B-swizzle XOR on absolute
+//   shared-memory address bits, so a row-shifted window of a TMA-written tile is read back correctly
+//   (measured: tools/umma_probe.cu).  L2->SM activation traffic drops 9x -> 1.4x versus conv_tc.cu.
+//   The filter tile of each (chunk, tap) streams through a TMA ring (K-major [Cout][K], box {32, NT}).
+//
+// 3xTF32 (X3): activations are split in shared memory by four extra warps, once per halo chunk
+// (hi = cvt.rna.tf32(v) in place, lo = v - hi into a twin buffer); filters arrive pre-split (hi / lo arrays);
+// each K step issues A_hi.B_hi + A_lo.B_hi + A_hi.B_lo.  The split costs one smem pass per chunk, amortised
+// over 9 taps.
+//
+// Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue, 6..9 = splitter (X3 only).
+#include "tc_common.cuh"
+#include <mutex>
+#include <unordered_map>
+
+using namespace dhtc;
+
+namespace {
+
+constexpr int T2_TH = 16, T2_TW = 8;                    // output patch
+constexpr int T2_HW = T2_TW + 2, T2_HH = T2_TH + 2;     // halo 10 x 18
+constexpr uint32_t T2_HALO_BYTES = T2_HW * T2_HH * 128; // 23040
+constexpr uint32_t T2_HALO_STRIDE = 23552;              // 1024-aligned
+
+struct T2Args {
+  const float* bias; const float* res; float* out;
+  int OH, OW, Cout, relu, tilesX, cchunks0, cchunks, ntaps, KW, Cin, ps;
+  int halo_w, halo_h;        // 10 x 18 (3x3) or 8 x 16 (1x1)
+  uint32_t halo_bytes;
+};
+
+template <int NT, bool X3> struct T2Cfg {
+  static constexpr int STAGES = X3 ? 3 : 4;
+  static constexpr uint32_t B_TILE = NT * 128;
+  static constexpr uint32_t B_STAGE = B_TILE * (X3 ? 2 : 1);
+  static constexpr uint32_t HALO_BUFS = X3 ? 4 : 2;       // [hi0, hi1, lo0, lo1]
+  static constexpr uint32_t SMEM = HALO_BUFS * T2_HALO_STRIDE + STAGES * B_STAGE + 1024;
+  static constexpr int THREADS = X3 ? 320 : 192;
+  static constexpr uint32_t IDESC = umma_idesc_tf32(128, NT);
+};
+
+__device__ __forceinline__ float tf32_rna(float v) {        // nearest TF32-representable value
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+// shifted-window A descriptor: start = halo + (r*halo_w + s) pixels, SBO = halo_w pixels
+__device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+template <int NT, bool X3>
+__global__ void __launch_bounds__(T2Cfg<NT, X3>::THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmB, const T2Args e) {
+  using Cfg = T2Cfg<NT, X3>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t t2_raw[];
+  __shared__ __align__(8) uint64_t halo_full[2], halo_ready[2], halo_empty[2], b_full[STAGES], b_empty[STAGES], acc_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(t2_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = t2_raw + (base - smem_u32(t2_raw));
+  const uint32_t b_ring = base + Cfg::HALO_BUFS * T2_HALO_STRIDE;
+  const int n = blockIdx.z;
+  const int n0 = blockIdx.y * NT;
+  const int oy0 = (blockIdx.x / e.tilesX) * T2_TH, ox0 = (blockIdx.x % e.tilesX) * T2_TW;
+  const int pad = (e.ntaps == 9) ? 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&halo_full[i]), 1);
+      mbar_init(smem_u32(&halo_ready[i]), 128);       // X3: every splitter thread arrives
+      mbar_init(smem_u32(&halo_empty[i]), 1);
+    }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
+    mbar_init(smem_u32(&acc_bar), 1);
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                                            // ---------------- TMA producer
+      auto load_halo = [&](int cc) {
+        const int hb = cc & 1;
+        if (cc >= 2) mbar_wait(smem_u32(&halo_empty[hb]), (uint32_t)(((cc >> 1) - 1) & 1));
+        const uint32_t bar = smem_u32(&halo_full[hb]);
+        mbar_expect_tx(bar, e.halo_bytes);
+        const uint32_t dst = base + (uint32_t)hb * T2_HALO_STRIDE;
+        if (cc < e.cchunks0) tma_load_4d(dst, &tmA0, bar, cc * 32, ox0 - pad, oy0 - pad, n);
+        else                 tma_load_4d(dst, &tmA1, bar, (cc - e.cchunks0) * 32, ox0 - pad, oy0 - pad, n);
+      };
+      load_halo(0);
+      int step = 0;
+      for (int cc = 0; cc < e.cchunks; ++cc) {
+        if (cc + 1 < e.cchunks) load_halo(cc + 1);
+        for (int tap = 0; tap < e.ntaps; ++tap, ++step) {
+          const int st = step % STAGES, round = step / STAGES;
+          mbar_wait(smem_u32(&b_empty[st]), (uint32_t)((round & 1) ^ 1));
+          const uint32_t bar = smem_u32(&b_full[st]);
+          mbar_expect_tx(bar, Cfg::B_STAGE);
+          const uint32_t dst = b_ring + (uint32_t)st * Cfg::B_STAGE;
+          const int kcol = tap * e.Cin + cc * 32;
+          tma_load_2d(dst, &tmB, bar, kcol, n0);
+          if (X3) tma_load_2d(dst + Cfg::B_TILE, &tmB, bar, kcol, e.Cout + n0);      // lo rows follow the hi rows
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                            // ---------------- MMA issuer
+      const uint32_t sbo = (uint32_t)e.halo_w * 128u;
+      int step = 0;
+      for (int cc = 0; cc < e.cchunks; ++cc) {
+        const int hb = cc & 1;
+        if (X3) mbar_wait(smem_u32(&halo_ready[hb]), (uint32_t)((cc >> 1) & 1));
+        else    mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((cc >> 1) & 1));
+        tc_fence_after();
+        const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE, h_lo = h_hi + 2 * T2_HALO_STRIDE;
+        for (int tap = 0; tap < e.ntaps; ++tap, ++step) {
+          const int st = step % STAGES, round = step / STAGES;
+          mbar_wait(smem_u32(&b_full[st]), (uint32_t)(round & 1));
+          tc_fence_after();
+          const int r = tap / e.KW, s = tap - r * e.KW;
+          const uint32_t shift = (uint32_t)(r * e.halo_w + s) * 128u;
+          const uint64_t ah = halo_desc(h_hi + shift, sbo);
+          const uint32_t b_addr = b_ring + (uint32_t)st * Cfg::B_STAGE;
+          const uint64_t bh = umma_desc_sw128(b_addr);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (step | k) ? 1u : 0u);
+          if (X3) {
+            const uint64_t al = halo_desc(h_lo + shift, sbo), bl = umma_desc_sw128(b_addr + Cfg::B_TILE);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+          }
+          umma_commit(smem_u32(&b_empty[st]));
+        }
+        umma_commit(smem_u32(&halo_empty[hb]));                 // all taps of this chunk have read the halo
+      }
+      umma_commit(smem_u32(&acc_bar));
+    }
+  } else if (warp < 6) {                                        // ---------------- epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int oy = oy0 + m / T2_TW, ox = ox0 + m % T2_TW;
+    const bool valid = (oy < e.OH) && (ox < e.OW);
+    mbar_wait(smem_u32(&acc_bar), 0);
+    tc_fence_after();
+    const size_t row = ((size_t)(n * e.OH + oy) * e.OW + ox) * e.Cout + n0;
+#pragma unroll 1
+    for (int j = 0; j < NT / 32; ++j) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
+      if (valid) {
+        float* op = e.out + row + j * 32;
+        if (e.ps) op = e.out + ((size_t)(n * 2 * e.OH + 2 * oy + (j >> 1)) * (2 * e.OW) + 2 * ox + (j & 1)) * 32;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 o = make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
+                                 __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+          if (e.bias) { const float4 b = ldg4(e.bias + n0 + j * 32 + c4 * 4); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+          if (e.res) { const float4 rr = ldg4(e.res + row + j * 32 + c4 * 4); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+          if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          st4(op + c4 * 4, o);
+        }
+      }
+    }
+  } else if (X3) {                                              // ---------------- splitter (warps 6..9)
+    const int t = threadIdx.x - 192;
+    const int nvec = (int)(e.halo_bytes / 16);
+    for (int cc = 0; cc < e.cchunks; ++cc) {
+      const int hb = cc & 1;
+      mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((cc >> 1) & 1));
+      float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)hb * T2_HALO_STRIDE);
+      float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)(2 + hb) * T2_HALO_STRIDE);
+      for (int i = t; i < nvec; i += 128) {
+        const float4 v = hi[i];
+        const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+        hi[i] = h;
+        lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      }
+      fence_async_smem();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&halo_ready[hb])) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, NT);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode2() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+struct Key2 {
+  const void* ptr; int d0, d1, d2, d3, b1, b2;
+  bool operator==(const Key2& o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && b1 == o.b1 && b2 == o.b2; }
+};
+struct Key2Hash {
+  size_t operator()(const Key2& k) const {
+    size_t h = (size_t)k.ptr;
+    for (int v : {k.d0, k.d1, k.d2, k.d3, k.b1, k.b2}) h = h * 1000003u ^ (size_t)v;
+    return h;
+  }
+};
+std::mutex g_mu2;
+std::unordered_map<Key2, CUtensorMap, Key2Hash> g_maps2;
+
+int get_map2(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d2, int d3, int b1, int b2) {
+  Key2 key{ptr, d0, d1, d2, d3, b1, b2};
+  {
+    std::lock_guard<std::mutex> lk(g_mu2);
+    auto it = g_maps2.find(key);
+    if (it != g_maps2.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode2();
+  if (!enc) return DH_E_VARIANT;
+  cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)d3};
+  cuuint64_t strides[3] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4, (cuuint64_t)d0 * d1 * d2 * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)b1, (cuuint32_t)b2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)ptr, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return DH_E_SHAPE;
+  {
+    std::lock_guard<std::mutex> lk(g_mu2);
+    if (g_maps2.size() > 4096) g_maps2.clear();
+    g_maps2[key] = m;
+  }
+  *out = m;
+  return 0;
+}
+
+template <int NT, bool X3>
+int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
+  using Cfg = T2Cfg<NT, X3>;
+  cudaError_t err = cudaFuncSetAttribute(conv_tc2_kernel<NT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if (err != cudaSuccess) return (int)err;
+  conv_tc2_kernel<NT, X3><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, e);
+  DH_CHECK_LAUNCH();
+  return 0;
+}
+}  // namespace
+
+bool dh_conv_tc2_eligible(const ConvArgs& a) {
+  const bool base = a.wt != nullptr && a.stride == 1 && a.up == 1 && a.KH == a.KW && (a.KH == 1 || a.KH == 3) &&
+                    a.pad == a.KH / 2 && a.C0 > 0 && a.C0 % 32 == 0 && a.C1 % 32 == 0 &&
+                    (a.Cout == 32 || a.Cout == 64 || a.Cout == 128 || a.Cout == 256) && a.inH >= 1 && a.inW >= 1;
+  if (!base) return false;
+  if (a.ps) return a.Cout == 128 && a.res == nullptr;
+  return true;
+}
+
+// a.wt: [2][Cout][K] = TF32-rounded filter (hi) followed by its TF32-rounded remainder (lo); x3 uses both.
+int dh_launch_conv_tc2(const ConvArgs& a, int x3, cudaStream_t s) {
+  DH_REQUIRE(a.in0 && a.wt && a.out, DH_E_NULL);
+  DH_REQUIRE(a.C1 == 0 || a.in1, DH_E_NULL);
+  DH_REQUIRE(dh_conv_tc2_eligible(a), DH_E_SHAPE);
+  DH_REQUIRE(dh_aligned16(a.in0) && dh_aligned16(a.in1) && dh_aligned16(a.wt) && dh_aligned16(a.out) &&
+             dh_aligned16(a.bias) && dh_aligned16(a.res), DH_E_ALIGN);
+  const int Cin = a.C0 + a.C1, K = a.KH * a.KW * Cin;
+  const int NT = a.Cout >= 128 ? 128 : a.Cout;
+  const int hw = (a.KH == 3) ? T2_HW : T2_TW, hh = (a.KH == 3) ? T2_HH : T2_TH;
+  CUtensorMap A0, A1, Bm;
+  int rc = get_map2(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, hw, hh);
+  if (rc) return rc;
+  if (a.C1) { rc = get_map2(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, hw, hh); if (rc) return rc; } else A1 = A0;
+  rc = get_map2(&Bm, a.wt, 2, K, 2 * a.Cout, 1, 1, NT, 1);       // rows [0,Cout) = hi, [Cout,2Cout) = lo
+  if (rc) return rc;
+  T2Args e;
+  e.bias = a.bias; e.res = a.res; e.out = a.out;
+  e.OH = a.inH; e.OW = a.inW; e.Cout = a.Cout; e.relu = a.relu;
+  e.tilesX = dh_cdiv(a.inW, T2_TW);
+  e.cchunks0 = a.C0 / 32; e.cchunks = Cin / 32; e.ntaps = a.KH * a.KW; e.KW = a.KW; e.Cin = Cin; e.ps = a.ps;
+  e.halo_w = hw; e.halo_h = hh; e.halo_bytes = (uint32_t)(hw * hh * 128);
+  dim3 grid(e.tilesX * dh_cdiv(a.inH, T2_TH), a.Cout / NT, a.N);
+  if (x3) {
+    switch (NT) {
+      case 128: return launch2<128, true>(A0, A1, Bm, e, grid, s);
+      case 64: return launch2<64, true>(A0, A1, Bm, e, grid, s);
+      default: return launch2<32, true>(A0, A1, Bm, e, grid, s);
+    }
+  }
+  switch (NT) {
+    case 128: return launch2<128, false>(A0, A1, Bm, e, grid, s);
+    case 64: return launch2<64, false>(A0, A1, Bm, e, grid, s);
+    default: return launch2<32, false>(A0, A1, Bm, e, grid, s);
+  }
+}

@@ -140,8 +140,11 @@ extern "C" size_t dahitra_workspace_bytes(int variant, int B, int H, int W, int 
 // C ABI — per-kernel entry points
 // ----------------------------------------------------------------------------------------------------
 static int conv_dispatch(const ConvArgs& a, int flags, cudaStream_t s) {
-  if ((flags & DH_FLAG_CONV_TC) && dh_conv_tc_eligible(a) && (a.stride == 1 || (flags & DH_FLAG_TC_STRIDE2)))
-    return dh_launch_conv_tc(a, s);
+  if (flags & DH_FLAG_CONV_TC) {
+    // stride 1: halo-reuse kernel (1xTF32 or error-compensated 3xTF32); stride 2: per-tap TMA kernel (1xTF32)
+    if (!(flags & DH_FLAG_CONV_TC_V1) && dh_conv_tc2_eligible(a)) return dh_launch_conv_tc2(a, (flags & DH_FLAG_TC_3XTF32) ? 1 : 0, s);
+    if (dh_conv_tc_eligible(a) && (a.stride == 1 || (flags & DH_FLAG_TC_STRIDE2))) return dh_launch_conv_tc(a, s);
+  }
   return dh_launch_conv_ffma(a, s);
 }
 
@@ -152,11 +155,11 @@ extern "C" int dahitra_conv2d(const float* in0, const float* in1, int C0, int C1
   return conv_dispatch(a, flags, (cudaStream_t)stream);
 }
 extern "C" int dahitra_conv2d_up2_tc(const float* in, int N, int inH, int inW, const float* pswt, const float* psb,
-                                     int relu, float* out, void* stream) {
+                                     int relu, float* out, int flags, void* stream) {
   ConvArgs a{in, nullptr, 32, 0, N, inH, inW, 1, 3, 3, 1, 1, 128, nullptr, pswt, psb, nullptr, relu, out};
   a.ps = 1;
   DH_REQUIRE(dh_conv_tc_eligible(a), DH_E_SHAPE);
-  return dh_launch_conv_tc(a, (cudaStream_t)stream);
+  return conv_dispatch(a, flags | DH_FLAG_CONV_TC, (cudaStream_t)stream);
 }
 extern "C" int dahitra_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* bias,
                             float* out, void* stream) {

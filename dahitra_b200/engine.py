@@ -26,6 +26,9 @@ DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC, DH_FLAG_
 MODES = {
     "fp32": 0,                                             # every contraction in fp32 FMA (strict)
     "fp32_tcdec": DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,      # strict + the 3xTF32 (fp32-grade) tensor-core decoder
+    # fp32-grade accuracy on the tensor cores: error-compensated 3xTF32 for the stride-1 convolutions and the decoder;
+    # the stem and the two stride-2 convolutions stay on the fp32 CUDA-core kernels
+    "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32_fast": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC,   # 1xTF32 decoder too
 }
@@ -94,6 +97,13 @@ def tf32_split(x):
     return hi, lo
 
 
+def kmajor_split(wt):
+    """K-major filter [Cout][K] (float64) -> [2][Cout][K]: TF32-rounded values, then their TF32-rounded remainders.
+    The 1xTF32 kernels read only the first half; the 3xTF32 kernels use both (B_hi, B_lo)."""
+    hi, lo = tf32_split(wt.contiguous())
+    return torch.stack([hi, lo])
+
+
 def swizzle128(m):
     """[rows][32] matrix B[n][k] -> flat K-major SWIZZLE_128B shared-memory image (rows of 128 B, the 16-byte
     chunk index XOR-ed with row % 8): element (n, k) lands at n*32 + (((k>>2) ^ (n&7)) << 2 | (k&3))."""
@@ -124,7 +134,7 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
         P[slot + "_W"] = _khwc(w)
         P[slot + "_B"] = b
         if slot in tc_slots:
-            P[slot + "_WT"] = _khwc(w).T.contiguous()          # [Cout][KH*KW*Cin], K-major B operand of tcgen05.mma
+            P[slot + "_WT"] = kmajor_split(_khwc(w).T)           # [2][Cout][KH*KW*Cin]: K-major B operand, TF32 hi / lo
 
     put_conv("DH_W_STEM", "resnet.conv1", "resnet.bn1")
     wk = torch.zeros(160, 64, dtype=torch.float64)                       # K = 147 padded to 5 steps of 32
@@ -142,7 +152,7 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
         P[s + "SQ"] = sd[f"conv_squeeze_{k}.0.weight"].double()[:, :, 0, 0].T          # [Cin][32]
         P[s + "TOK"] = sd[f"conv_token_{k}.weight"].double()[:, :, 0, 0].T             # [32][4]
         P[s + "DECODE"] = _khwc(sd[f"conv_decode_{k}.weight"].double())
-        P[s + "DECODE_WT"] = P[s + "DECODE"].T.contiguous()
+        P[s + "DECODE_WT"] = kmajor_split(P[s + "DECODE"].T)
         # ---- token encoder pack
         t = f"transformer_{k}.layers.0"
         if variant == DH_VARIANT_LEVIR:
@@ -200,7 +210,8 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
         P[s + "POS"] = None if pe is None else pe.double()[0].permute(1, 2, 0).reshape(-1, 32)
     for name, key in (("DH_W_CL4", "conv_layer4.0"), ("DH_W_CL3", "conv_layer3.0"), ("DH_W_CL2", "conv_layer2.0")):
         put_conv(name, key, None)
-        P[name + "_PSWT"], P[name + "_PSB"] = upsample_phase_filter(sd[key + ".weight"].double(), sd[key + ".bias"].double())
+        pw, pb = upsample_phase_filter(sd[key + ".weight"].double(), sd[key + ".bias"].double())
+        P[name + "_PSWT"], P[name + "_PSB"] = kmajor_split(pw), pb
     put_conv("DH_W_CL20A", "conv_layer2_0.0", "conv_layer2_0.1")
     put_conv("DH_W_CL20B", "conv_layer2_0.3", None)
     wc = sd["classifier.weight"].double()

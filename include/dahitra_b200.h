@@ -49,6 +49,7 @@ extern "C" {
 #define DH_FLAG_DEC_TC      8   /* pixel decoder on tcgen05 (TF32 operands), decoder_tc.cu */
 #define DH_FLAG_STEM_TC     16  /* 7x7 stem on tcgen05 (on-chip im2col), stem_tc.cu */
 #define DH_FLAG_DEC_TC_X3   32  /* with DEC_TC: error-compensated 3xTF32 in the decoder (fp32-grade accuracy) */
+#define DH_FLAG_CONV_TC_V1  64  /* with CONV_TC: force the per-tap TMA kernel (conv_tc.cu) instead of the halo-reuse one */
 #define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC | DH_FLAG_STEM_TC)   /* the "tf32" mode */
 
 /* ---- prepared-weight table -------------------------------------------------------------------
@@ -161,9 +162,10 @@ int dahitra_conv2d(const float* in0, const float* in1, int C0, int C1, int N, in
 /* nn.Upsample(scale_factor=2) (nearest) followed by a 3x3 pad-1 conv 32->32 (+bias)(+ReLU) — conv_layer4/3/2,
  * reference models/networks.py:1335-1336,1343-1344,1350-1351 — as ONE tcgen05 conv on the low-resolution map:
  *   in NHWC [N][inH][inW][32] -> out NHWC [N][2*inH][2*inW][32]
- *   pswt [128][9*32] K-major phase filter, psb [128] (see DH_W_CL*_PSWT / _PSB). */
+ *   pswt [2][128][9*32] K-major phase filter (hi, lo), psb [128] (see DH_W_CL*_PSWT / _PSB);
+ *   flags: DH_FLAG_TC_3XTF32 and/or DH_FLAG_CONV_TC_V1 (DH_FLAG_CONV_TC is implied). */
 int dahitra_conv2d_up2_tc(const float* in, int N, int inH, int inW, const float* pswt, const float* psb,
-                          int relu, float* out, void* stream);
+                          int relu, float* out, int flags, void* stream);
 
 /* Stem: 7x7 stride-2 pad-3 conv 3->64 + folded BN + ReLU, NCHW planes in, NHWC out
  * (reference models/networks.py:1120-1122, models/resnet.py:150-153). */

@@ -20,18 +20,21 @@ def conv2d(in0, in1, w, bias, res, relu, K, stride, pad, up=1, flags=0):
     H, W = inH * up, inW * up
     OH, OW = (H + 2 * pad - K) // stride + 1, (W + 2 * pad - K) // stride + 1
     out = torch.empty((N, OH, OW, Cout), device=in0.device, dtype=torch.float32)
-    wt = w.t().contiguous() if flags else None             # K-major copy for the tcgen05 path
+    wt = None
+    if flags:                                              # K-major [2][Cout][K] (TF32 hi, lo) for the tcgen05 paths
+        from dahitra_b200.engine import kmajor_split
+        wt = kmajor_split(w.detach().cpu().double().t()).float().contiguous().to(w.device)
     rc = lib.dahitra_conv2d(_p(in0), _p(in1), C0, C1, N, inH, inW, up, K, K, stride, pad, Cout, _p(w), _p(wt), _p(bias),
                             _p(res), int(relu), _p(out), flags, _stream())
     _lib.check(rc, "dahitra_conv2d")
     return out
 
 
-def conv2d_up2_tc(x, pswt, psb, relu):
+def conv2d_up2_tc(x, pswt, psb, relu, flags=0):
     lib = _lib.load()
     N, H, W, _ = x.shape
     out = torch.empty((N, 2 * H, 2 * W, 32), device=x.device, dtype=torch.float32)
-    _lib.check(lib.dahitra_conv2d_up2_tc(_p(x), N, H, W, _p(pswt), _p(psb), int(relu), _p(out), _stream()),
+    _lib.check(lib.dahitra_conv2d_up2_tc(_p(x), N, H, W, _p(pswt), _p(psb), int(relu), _p(out), flags, _stream()),
                "dahitra_conv2d_up2_tc")
     return out
 
