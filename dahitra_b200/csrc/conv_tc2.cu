@@ -35,13 +35,18 @@ struct T2Args {
   const float* bias; const float* res; float* out;
   int OH, OW, Cout, relu, tilesX, cchunks0, cchunks, ntaps, KW, Cin, ps;
   int halo_w, halo_h;        // 10 x 18 (3x3) or 8 x 16 (1x1)
+  int tps;                   // filter taps per ring stage (<= Cfg::TPS; 1 for 1x1 convs)
   uint32_t halo_bytes;
 };
 
 template <int NT, bool X3> struct T2Cfg {
-  static constexpr int STAGES = X3 ? 3 : 4;
+  // one ring stage holds TPS filter taps (3 = one filter row) so the issuing thread waits / commits once per
+  // 12 (x3: 36) MMAs instead of once per 4; NT=128 with 3xTF32 is MMA-bound already and would not fit 3 taps
+  static constexpr int TPS = (X3 && NT == 128) ? 1 : 3;
+  static constexpr int STAGES = (X3 && NT == 128) ? 3 : ((X3 && NT == 64) || (!X3 && NT == 128) ? 2 : 3);
   static constexpr uint32_t B_TILE = NT * 128;
-  static constexpr uint32_t B_STAGE = B_TILE * (X3 ? 2 : 1);
+  static constexpr uint32_t B_TAP = B_TILE * (X3 ? 2 : 1);      // hi (+ lo) tile of one tap
+  static constexpr uint32_t B_STAGE = B_TAP * TPS;
   static constexpr uint32_t HALO_BUFS = X3 ? 4 : 2;       // [hi0, hi1, lo0, lo1]
   static constexpr uint32_t SMEM = HALO_BUFS * T2_HALO_STRIDE + STAGES * B_STAGE + 1024;
   static constexpr int THREADS = X3 ? 320 : 192;
@@ -112,15 +117,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       int step = 0;
       for (int cc = 0; cc < e.cchunks; ++cc) {
         if (cc + 1 < e.cchunks) load_halo(cc + 1);
-        for (int tap = 0; tap < e.ntaps; ++tap, ++step) {
+        for (int tap0 = 0; tap0 < e.ntaps; tap0 += e.tps, ++step) {      // one ring stage = e.tps filter taps
           const int st = step % STAGES, round = step / STAGES;
           mbar_wait(smem_u32(&b_empty[st]), (uint32_t)((round & 1) ^ 1));
           const uint32_t bar = smem_u32(&b_full[st]);
-          mbar_expect_tx(bar, Cfg::B_STAGE);
-          const uint32_t dst = b_ring + (uint32_t)st * Cfg::B_STAGE;
-          const int kcol = tap * e.Cin + cc * 32;
-          tma_load_2d(dst, &tmB, bar, kcol, n0);
-          if (X3) tma_load_2d(dst + Cfg::B_TILE, &tmB, bar, kcol, e.Cout + n0);      // lo rows follow the hi rows
+          mbar_expect_tx(bar, (uint32_t)e.tps * Cfg::B_TAP);
+          for (int t = 0; t < e.tps; ++t) {
+            const uint32_t dst = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)t * Cfg::B_TAP;
+            const int kcol = (tap0 + t) * e.Cin + cc * 32;
+            tma_load_2d(dst, &tmB, bar, kcol, n0);
+            if (X3) tma_load_2d(dst + Cfg::B_TILE, &tmB, bar, kcol, e.Cout + n0);    // lo rows follow the hi rows
+          }
         }
       }
     }
@@ -134,23 +141,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         else    mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((cc >> 1) & 1));
         tc_fence_after();
         const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE, h_lo = h_hi + 2 * T2_HALO_STRIDE;
-        for (int tap = 0; tap < e.ntaps; ++tap, ++step) {
+        for (int tap0 = 0; tap0 < e.ntaps; tap0 += e.tps, ++step) {
           const int st = step % STAGES, round = step / STAGES;
           mbar_wait(smem_u32(&b_full[st]), (uint32_t)(round & 1));
           tc_fence_after();
-          const int r = tap / e.KW, s = tap - r * e.KW;
-          const uint32_t shift = (uint32_t)(r * e.halo_w + s) * 128u;
-          const uint64_t ah = halo_desc(h_hi + shift, sbo);
-          const uint32_t b_addr = b_ring + (uint32_t)st * Cfg::B_STAGE;
-          const uint64_t bh = umma_desc_sw128(b_addr);
+          for (int t = 0; t < e.tps; ++t) {
+            const int tap = tap0 + t;
+            const int r = tap / e.KW, s = tap - r * e.KW;
+            const uint32_t shift = (uint32_t)(r * e.halo_w + s) * 128u;
+            const uint64_t ah = halo_desc(h_hi + shift, sbo);
+            const uint32_t b_addr = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)t * Cfg::B_TAP;
+            const uint64_t bh = umma_desc_sw128(b_addr);
+            const uint32_t first = (step | t) ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (step | k) ? 1u : 0u);
-          if (X3) {
-            const uint64_t al = halo_desc(h_lo + shift, sbo), bl = umma_desc_sw128(b_addr + Cfg::B_TILE);
+            for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (first | k) ? 1u : 0u);
+            if (X3) {
+              const uint64_t al = halo_desc(h_lo + shift, sbo), bl = umma_desc_sw128(b_addr + Cfg::B_TILE);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+              for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, 1u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+              for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+            }
           }
           umma_commit(smem_u32(&b_empty[st]));
         }
@@ -196,7 +207,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const float4 v = hi[i];
         const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
         hi[i] = h;
-        lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        lo[i] = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
       }
       fence_async_smem();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&halo_ready[hb])) : "memory");
@@ -268,8 +279,9 @@ int get_map2(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d
 }
 
 template <int NT, bool X3>
-int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
+int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, T2Args e, dim3 grid, cudaStream_t s) {
   using Cfg = T2Cfg<NT, X3>;
+  e.tps = (e.ntaps % Cfg::TPS == 0) ? Cfg::TPS : 1;
   cudaError_t err = cudaFuncSetAttribute(conv_tc2_kernel<NT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (err != cudaSuccess) return (int)err;
   conv_tc2_kernel<NT, X3><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, e);

@@ -187,12 +187,20 @@ def test_weight_updates_are_seen(levir_template):
         assert torch.equal(net(x1, x2), yb)
 
 
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
 @pytest.mark.parametrize("weights", ["defineG", "default"])
-def test_tensor_core_mode(weights, levir_template):
-    """DH_FLAG_CONV_TC: stride-1 convolutions on tcgen05 with TF32 operands (fp32 accumulate, fp32 storage).
-    Separately stated tolerance for this mode: |d| <= 2e-3 * max|ref| element-wise and >= 99.9 % argmax agreement
-    (eager PyTorch with TF32 enabled measures 7.6e-5 / 99.985 % on the define_G init)."""
+def test_tensor_core_modes(mode, weights, levir_template):
+    """The two tensor-core modes (dahitra_b200.engine.MODES), fp32 storage and fp32 accumulation in both:
+      tf32x3 — error-compensated 3xTF32 for the stride-1 convolutions and the pixel decoder (stem and the two stride-2
+               convolutions stay fp32 FMA).  Must meet the strict fp32 tolerance (1e-4 + 1e-3|ref|, >= 99.9 % argmax) on the
+               benchmark's define_G weights; on the ill-conditioned default-scale synthetic weights (where the reference's own
+               fp32 arithmetic is already 1.3e-4 off its fp64 self) it must stay within 1e-3 of the logit range and >= 99.99 %
+               argmax agreement.
+      tf32   — single-pass TF32 everywhere.  Strict tolerance on the define_G weights; on the ill-conditioned weights no worse
+               than 3x eager PyTorch with its TF32 switches on (cuDNN TF32 is PyTorch's default, i.e. what a reference user
+               gets on this GPU)."""
     from dahitra_b200.networks import define_G
+    from dahitra_b200.engine import MODES
     if weights == "defineG":
         torch.manual_seed(0)
         net = define_G(Args(), gpu_ids=[0]).eval()
@@ -200,15 +208,12 @@ def test_tensor_core_mode(weights, levir_template):
     else:
         sd = synth.synth_state_dict(levir_template, seed=3, style="default")
         net = make_net(sd)
-    from dahitra_b200.engine import MODES
-    net._engine.flags = MODES["tf32"]
+    net._engine.flags = MODES[mode]
     net.invalidate_native_cache()
     x1, x2 = synth.synth_pair(2, 256, 256, seed=2, kind="uniform")
     with torch.no_grad():
         y = net(x1.to(DEV), x2.to(DEV)).double().cpu()
     ref = O.forward_levir(sd, x1, x2, dtype=torch.float64)
-    # yardstick: the reference's own arithmetic on this GPU with PyTorch's TF32 switches on (cuDNN TF32 is the
-    # PyTorch default, so this is what a reference user actually gets on an Ampere-or-newer GPU)
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = True
     with torch.no_grad():
@@ -219,12 +224,14 @@ def test_tensor_core_mode(weights, levir_template):
     agree = float((y.argmax(1) == ref.argmax(1)).float().mean())
     agree_t = float((yt.argmax(1) == ref.argmax(1)).float().mean())
     strict_bad = int((d > ATOL + RTOL * ref.abs()).sum())
-    print(f"[parity] TF32 tensor-core mode ({weights}): max|d|={float(d.max()):.3e} mean|d|={float(d.mean()):.3e} "
+    print(f"[parity] mode {mode} ({weights}): max|d|={float(d.max()):.3e} mean|d|={float(d.mean()):.3e} "
           f"ref_absmax={float(ref.abs().max()):.3e} argmax_agree={agree:.6f} outside-strict-fp32-tol={strict_bad}/{d.numel()} "
           f"| eager-PyTorch-TF32: max|d|={float(dt.max()):.3e} mean|d|={float(dt.mean()):.3e} argmax_agree={agree_t:.6f}")
-    if weights == "defineG":      # the benchmark's weights: the strict fp32 tolerance holds in TF32 mode too
+    if weights == "defineG":
         assert strict_bad == 0 and agree >= 0.999
-    else:                         # ill-conditioned synthetic weights: no worse than 3x eager PyTorch TF32
+    elif mode == "tf32x3":
+        assert float(d.max()) <= 1e-3 * float(ref.abs().max()) and agree >= 0.9999
+    else:
         assert float(d.mean()) <= 3.0 * float(dt.mean()) + 1e-5
         assert agree >= min(0.999, agree_t - 0.002)
 
