@@ -36,21 +36,23 @@ struct T2Args {
   int OH, OW, Cout, relu, tilesX, cchunks0, cchunks, ntaps, KW, Cin, ps;
   int halo_w, halo_h;        // 10 x 18 (3x3) or 8 x 16 (1x1)
   int tps;                   // filter taps per ring stage (<= Cfg::TPS; 1 for 1x1 convs)
+  int tilesY, ncout_tiles, ntiles;
   uint32_t halo_bytes;
 };
 
 template <int NT, bool X3> struct T2Cfg {
-  // one ring stage holds TPS filter taps (3 = one filter row) so the issuing thread waits / commits once per
-  // 12 (x3: 36) MMAs instead of once per 4; NT=128 with 3xTF32 is MMA-bound already and would not fit 3 taps
+  // Persistent kernel, one CTA per SM: the ring stage holds TPS filter taps (3 = one filter row) so the issuing
+  // thread waits / commits once per 12 (x3: 36) MMAs; NT=128 with 3xTF32 is MMA-bound and would not fit 3 taps.
   static constexpr int TPS = (X3 && NT == 128) ? 1 : 3;
-  static constexpr int STAGES = (X3 && NT == 128) ? 3 : ((X3 && NT == 64) || (!X3 && NT == 128) ? 2 : 3);
+  static constexpr int STAGES = (X3 && NT == 128) ? 3 : ((X3 && NT == 64) ? 2 : 3);
   static constexpr uint32_t B_TILE = NT * 128;
   static constexpr uint32_t B_TAP = B_TILE * (X3 ? 2 : 1);      // hi (+ lo) tile of one tap
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
-  static constexpr uint32_t HALO_BUFS = X3 ? 4 : 2;       // [hi0, hi1, lo0, lo1]
+  static constexpr uint32_t HALO_BUFS = X3 ? 4 : 2;             // [hi0, hi1, lo0, lo1]
   static constexpr uint32_t SMEM = HALO_BUFS * T2_HALO_STRIDE + STAGES * B_STAGE + 1024;
   static constexpr int THREADS = X3 ? 320 : 192;
   static constexpr uint32_t IDESC = umma_idesc_tf32(128, NT);
+  static constexpr uint32_t TMEM_COLS = (2 * NT < 32) ? 32 : 2 * NT;   // two accumulators
 };
 
 __device__ __forceinline__ float tf32_rna(float v) {        // nearest TF32-representable value
@@ -65,6 +67,16 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes)
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+struct TileCoord { int n, oy0, ox0, n0; };
+__device__ __forceinline__ TileCoord tile_coord(int tile, const T2Args& e, int NT) {
+  TileCoord t;
+  const int ct = tile % e.ncout_tiles; tile /= e.ncout_tiles;
+  const int tx = tile % e.tilesX; tile /= e.tilesX;
+  const int ty = tile % e.tilesY;
+  t.n = tile / e.tilesY; t.oy0 = ty * T2_TH; t.ox0 = tx * T2_TW; t.n0 = ct * NT;
+  return t;
+}
+
 template <int NT, bool X3>
 __global__ void __launch_bounds__(T2Cfg<NT, X3>::THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -72,16 +84,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   using Cfg = T2Cfg<NT, X3>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t2_raw[];
-  __shared__ __align__(8) uint64_t halo_full[2], halo_ready[2], halo_empty[2], b_full[STAGES], b_empty[STAGES], acc_bar;
+  __shared__ __align__(8) uint64_t halo_full[2], halo_ready[2], halo_empty[2], b_full[STAGES], b_empty[STAGES],
+      acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(t2_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = t2_raw + (base - smem_u32(t2_raw));
   const uint32_t b_ring = base + Cfg::HALO_BUFS * T2_HALO_STRIDE;
-  const int n = blockIdx.z;
-  const int n0 = blockIdx.y * NT;
-  const int oy0 = (blockIdx.x / e.tilesX) * T2_TH, ox0 = (blockIdx.x % e.tilesX) * T2_TW;
   const int pad = (e.ntaps == 9) ? 1 : 0;
 
   if (threadIdx.x == 0) {
@@ -89,44 +99,54 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       mbar_init(smem_u32(&halo_full[i]), 1);
       mbar_init(smem_u32(&halo_ready[i]), 128);       // X3: every splitter thread arrives
       mbar_init(smem_u32(&halo_empty[i]), 1);
+      mbar_init(smem_u32(&acc_full[i]), 1);
+      mbar_init(smem_u32(&acc_empty[i]), 128);        // every epilogue thread arrives
     }
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
-    mbar_init(smem_u32(&acc_bar), 1);
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), NT);
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+  // Every role walks the same tile sequence tile = blockIdx.x, += gridDim.x and keeps its own running counters:
+  //   g  = halo chunks consumed so far (buffer g&1, use number g>>1), step = filter ring stages so far,
+  //   it = tiles so far (accumulator it&1, use number it>>1).
   if (warp == 0) {
     if (lane == 0) {                                            // ---------------- TMA producer
-      auto load_halo = [&](int cc) {
-        const int hb = cc & 1;
-        if (cc >= 2) mbar_wait(smem_u32(&halo_empty[hb]), (uint32_t)(((cc >> 1) - 1) & 1));
+      int g = 0, step = 0;
+      auto load_halo = [&](int gg, int cc, const TileCoord& t) {
+        const int hb = gg & 1;
+        if (gg >= 2) mbar_wait(smem_u32(&halo_empty[hb]), (uint32_t)(((gg >> 1) - 1) & 1));
         const uint32_t bar = smem_u32(&halo_full[hb]);
         mbar_expect_tx(bar, e.halo_bytes);
         const uint32_t dst = base + (uint32_t)hb * T2_HALO_STRIDE;
-        if (cc < e.cchunks0) tma_load_4d(dst, &tmA0, bar, cc * 32, ox0 - pad, oy0 - pad, n);
-        else                 tma_load_4d(dst, &tmA1, bar, (cc - e.cchunks0) * 32, ox0 - pad, oy0 - pad, n);
+        if (cc < e.cchunks0) tma_load_4d(dst, &tmA0, bar, cc * 32, t.ox0 - pad, t.oy0 - pad, t.n);
+        else                 tma_load_4d(dst, &tmA1, bar, (cc - e.cchunks0) * 32, t.ox0 - pad, t.oy0 - pad, t.n);
       };
-      load_halo(0);
-      int step = 0;
-      for (int cc = 0; cc < e.cchunks; ++cc) {
-        if (cc + 1 < e.cchunks) load_halo(cc + 1);
-        for (int tap0 = 0; tap0 < e.ntaps; tap0 += e.tps, ++step) {      // one ring stage = e.tps filter taps
-          const int st = step % STAGES, round = step / STAGES;
-          mbar_wait(smem_u32(&b_empty[st]), (uint32_t)((round & 1) ^ 1));
-          const uint32_t bar = smem_u32(&b_full[st]);
-          mbar_expect_tx(bar, (uint32_t)e.tps * Cfg::B_TAP);
-          for (int t = 0; t < e.tps; ++t) {
-            const uint32_t dst = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)t * Cfg::B_TAP;
-            const int kcol = (tap0 + t) * e.Cin + cc * 32;
-            tma_load_2d(dst, &tmB, bar, kcol, n0);
-            if (X3) tma_load_2d(dst + Cfg::B_TILE, &tmB, bar, kcol, e.Cout + n0);    // lo rows follow the hi rows
+      int tile = blockIdx.x;
+      if (tile < e.ntiles) load_halo(0, 0, tile_coord(tile, e, NT));
+      for (; tile < e.ntiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord(tile, e, NT);
+        for (int cc = 0; cc < e.cchunks; ++cc, ++g) {
+          // prefetch the next halo chunk (of this tile, or chunk 0 of the next tile) before streaming this chunk's filters
+          if (cc + 1 < e.cchunks) load_halo(g + 1, cc + 1, t);
+          else if (tile + (int)gridDim.x < e.ntiles) load_halo(g + 1, 0, tile_coord(tile + gridDim.x, e, NT));
+          for (int tap0 = 0; tap0 < e.ntaps; tap0 += e.tps, ++step) {      // one ring stage = e.tps filter taps
+            const int st = step % STAGES, round = step / STAGES;
+            mbar_wait(smem_u32(&b_empty[st]), (uint32_t)((round & 1) ^ 1));
+            const uint32_t bar = smem_u32(&b_full[st]);
+            mbar_expect_tx(bar, (uint32_t)e.tps * Cfg::B_TAP);
+            for (int tt = 0; tt < e.tps; ++tt) {
+              const uint32_t dst = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)tt * Cfg::B_TAP;
+              const int kcol = (tap0 + tt) * e.Cin + cc * 32;
+              tma_load_2d(dst, &tmB, bar, kcol, t.n0);
+              if (X3) tma_load_2d(dst + Cfg::B_TILE, &tmB, bar, kcol, e.Cout + t.n0);    // lo rows follow the hi rows
+            }
           }
         }
       }
@@ -134,90 +154,108 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {                                            // ---------------- MMA issuer
       const uint32_t sbo = (uint32_t)e.halo_w * 128u;
-      int step = 0;
-      for (int cc = 0; cc < e.cchunks; ++cc) {
-        const int hb = cc & 1;
-        if (X3) mbar_wait(smem_u32(&halo_ready[hb]), (uint32_t)((cc >> 1) & 1));
-        else    mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((cc >> 1) & 1));
+      int g = 0, step = 0, it = 0;
+      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
+        const int ab = it & 1;
+        mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));    // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE, h_lo = h_hi + 2 * T2_HALO_STRIDE;
-        for (int tap0 = 0; tap0 < e.ntaps; tap0 += e.tps, ++step) {
-          const int st = step % STAGES, round = step / STAGES;
-          mbar_wait(smem_u32(&b_full[st]), (uint32_t)(round & 1));
+        const uint32_t d_tmem = tmem_base + (uint32_t)ab * NT;
+        int kstep = 0;
+        for (int cc = 0; cc < e.cchunks; ++cc, ++g) {
+          const int hb = g & 1;
+          if (X3) mbar_wait(smem_u32(&halo_ready[hb]), (uint32_t)((g >> 1) & 1));
+          else    mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g >> 1) & 1));
           tc_fence_after();
-          for (int t = 0; t < e.tps; ++t) {
-            const int tap = tap0 + t;
-            const int r = tap / e.KW, s = tap - r * e.KW;
-            const uint32_t shift = (uint32_t)(r * e.halo_w + s) * 128u;
-            const uint64_t ah = halo_desc(h_hi + shift, sbo);
-            const uint32_t b_addr = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)t * Cfg::B_TAP;
-            const uint64_t bh = umma_desc_sw128(b_addr);
-            const uint32_t first = (step | t) ? 1u : 0u;
+          const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE, h_lo = h_hi + 2 * T2_HALO_STRIDE;
+          for (int tap0 = 0; tap0 < e.ntaps; tap0 += e.tps, ++step) {
+            const int st = step % STAGES, round = step / STAGES;
+            mbar_wait(smem_u32(&b_full[st]), (uint32_t)(round & 1));
+            tc_fence_after();
+            for (int tt = 0; tt < e.tps; ++tt, ++kstep) {
+              const int tap = tap0 + tt;
+              const int r = tap / e.KW, s = tap - r * e.KW;
+              const uint32_t shift = (uint32_t)(r * e.halo_w + s) * 128u;
+              const uint64_t ah = halo_desc(h_hi + shift, sbo);
+              const uint32_t b_addr = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)tt * Cfg::B_TAP;
+              const uint64_t bh = umma_desc_sw128(b_addr);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (first | k) ? 1u : 0u);
-            if (X3) {
-              const uint64_t al = halo_desc(h_lo + shift, sbo), bl = umma_desc_sw128(b_addr + Cfg::B_TILE);
+              for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (kstep | k) ? 1u : 0u);
+              if (X3) {
+                const uint64_t al = halo_desc(h_lo + shift, sbo), bl = umma_desc_sw128(b_addr + Cfg::B_TILE);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+                for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, 1u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+                for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+              }
             }
+            umma_commit(smem_u32(&b_empty[st]));
           }
-          umma_commit(smem_u32(&b_empty[st]));
+          umma_commit(smem_u32(&halo_empty[hb]));               // all taps of this chunk have read the halo
         }
-        umma_commit(smem_u32(&halo_empty[hb]));                 // all taps of this chunk have read the halo
+        umma_commit(smem_u32(&acc_full[ab]));
       }
-      umma_commit(smem_u32(&acc_bar));
     }
   } else if (warp < 6) {                                        // ---------------- epilogue (warps 2..5)
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int oy = oy0 + m / T2_TW, ox = ox0 + m % T2_TW;
-    const bool valid = (oy < e.OH) && (ox < e.OW);
-    mbar_wait(smem_u32(&acc_bar), 0);
-    tc_fence_after();
-    const size_t row = ((size_t)(n * e.OH + oy) * e.OW + ox) * e.Cout + n0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
+      const TileCoord t = tile_coord(tile, e, NT);
+      const int ab = it & 1;
+      const int oy = t.oy0 + m / T2_TW, ox = t.ox0 + m % T2_TW;
+      const bool valid = (oy < e.OH) && (ox < e.OW);
+      mbar_wait(smem_u32(&acc_full[ab]), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const size_t row = ((size_t)(t.n * e.OH + oy) * e.OW + ox) * e.Cout + t.n0;
 #pragma unroll 1
-    for (int j = 0; j < NT / 32; ++j) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), v);
-      if (valid) {
-        float* op = e.out + row + j * 32;
-        if (e.ps) op = e.out + ((size_t)(n * 2 * e.OH + 2 * oy + (j >> 1)) * (2 * e.OW) + 2 * ox + (j & 1)) * 32;
+      for (int j = 0; j < NT / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NT + j * 32), v);
+        if (j == NT / 32 - 1) {                                  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
+        }
+        if (valid) {
+          float* op = e.out + row + j * 32;
+          if (e.ps) op = e.out + ((size_t)(t.n * 2 * e.OH + 2 * oy + (j >> 1)) * (2 * e.OW) + 2 * ox + (j & 1)) * 32;
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float4 o = make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
-                                 __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
-          if (e.bias) { const float4 b = ldg4(e.bias + n0 + j * 32 + c4 * 4); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-          if (e.res) { const float4 rr = ldg4(e.res + row + j * 32 + c4 * 4); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-          if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          st4(op + c4 * 4, o);
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 o = make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
+                                   __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+            if (e.bias) { const float4 b = ldg4(e.bias + t.n0 + j * 32 + c4 * 4); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            if (e.res) { const float4 rr = ldg4(e.res + row + j * 32 + c4 * 4); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+            if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            st4(op + c4 * 4, o);
+          }
         }
       }
     }
   } else if (X3) {                                              // ---------------- splitter (warps 6..9)
-    const int t = threadIdx.x - 192;
+    const int tI = threadIdx.x - 192;
     const int nvec = (int)(e.halo_bytes / 16);
-    for (int cc = 0; cc < e.cchunks; ++cc) {
-      const int hb = cc & 1;
-      mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((cc >> 1) & 1));
-      float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)hb * T2_HALO_STRIDE);
-      float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)(2 + hb) * T2_HALO_STRIDE);
-      for (int i = t; i < nvec; i += 128) {
-        const float4 v = hi[i];
-        const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-        hi[i] = h;
-        lo[i] = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
+    int g = 0;
+    for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
+      for (int cc = 0; cc < e.cchunks; ++cc, ++g) {
+        const int hb = g & 1;
+        mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g >> 1) & 1));
+        float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)hb * T2_HALO_STRIDE);
+        float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)(2 + hb) * T2_HALO_STRIDE);
+        for (int i = tI; i < nvec; i += 128) {
+          const float4 v = hi[i];
+          const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+          hi[i] = h;
+          lo[i] = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
+        }
+        fence_async_smem();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&halo_ready[hb])) : "memory");
       }
-      fence_async_smem();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&halo_ready[hb])) : "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, NT);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -321,7 +359,12 @@ int dh_launch_conv_tc2(const ConvArgs& a, int x3, cudaStream_t s) {
   e.tilesX = dh_cdiv(a.inW, T2_TW);
   e.cchunks0 = a.C0 / 32; e.cchunks = Cin / 32; e.ntaps = a.KH * a.KW; e.KW = a.KW; e.Cin = Cin; e.ps = a.ps;
   e.halo_w = hw; e.halo_h = hh; e.halo_bytes = (uint32_t)(hw * hh * 128);
-  dim3 grid(e.tilesX * dh_cdiv(a.inH, T2_TH), a.Cout / NT, a.N);
+  e.tilesY = dh_cdiv(a.inH, T2_TH); e.ncout_tiles = a.Cout / NT;
+  e.ntiles = e.tilesX * e.tilesY * e.ncout_tiles * a.N;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);          // persistent: one CTA per SM
   if (x3) {
     switch (NT) {
       case 128: return launch2<128, true>(A0, A1, Bm, e, grid, s);
