@@ -17,7 +17,9 @@
 // each K step issues A_hi.B_hi + A_lo.B_hi + A_hi.B_lo.  The split costs one smem pass per chunk, amortised
 // over 9 taps.
 //
-// Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue, 6..9 = splitter (X3 only).
+// Persistent CTAs (one per SM) walk the tile list; two TMEM accumulators let the epilogue of tile i overlap the
+// main loop of tile i+1.  Warp roles: 0 = halo TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue,
+// 6 = filter TMA producer, 7..10 = splitter (X3 only).
 #include "tc_common.cuh"
 #include <mutex>
 #include <unordered_map>
@@ -41,16 +43,19 @@ struct T2Args {
 };
 
 template <int NT, bool X3> struct T2Cfg {
-  // Persistent kernel, one CTA per SM: the ring stage holds TPS filter taps (3 = one filter row) so the issuing
-  // thread waits / commits once per 12 (x3: 36) MMAs; NT=128 with 3xTF32 is MMA-bound and would not fit 3 taps.
-  static constexpr int TPS = (X3 && NT == 128) ? 1 : 3;
-  static constexpr int STAGES = (X3 && NT == 128) ? 3 : ((X3 && NT == 64) ? 2 : 3);
+  // Persistent kernel, one CTA per SM.  Pipeline depth is sized so that the MMA warp always has >= ~1500 cycles of
+  // operands in flight (L2 latency under load): the smaller the N tile, the faster a stage is consumed, so the more
+  // halo buffers (HB) and filter stages it gets.  A stage holds TPS filter taps so the issuing thread waits /
+  // commits once per 4*TPS (x3: 12*TPS) MMAs.
+  static constexpr int HB = X3 ? 2 : (NT == 128 ? 2 : (NT == 64 ? 3 : 4));          // halo chunk buffers (x3: hi + lo each)
+  static constexpr int TPS = X3 ? (NT == 32 ? 3 : 1) : 3;
+  static constexpr int STAGES = X3 ? (NT == 128 ? 3 : (NT == 64 ? 6 : 4)) : (NT == 128 ? 3 : (NT == 64 ? 5 : 8));
   static constexpr uint32_t B_TILE = NT * 128;
   static constexpr uint32_t B_TAP = B_TILE * (X3 ? 2 : 1);      // hi (+ lo) tile of one tap
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
-  static constexpr uint32_t HALO_BUFS = X3 ? 4 : 2;             // [hi0, hi1, lo0, lo1]
+  static constexpr uint32_t HALO_BUFS = X3 ? 2 * HB : HB;       // [hi 0..HB-1][lo 0..HB-1]
   static constexpr uint32_t SMEM = HALO_BUFS * T2_HALO_STRIDE + STAGES * B_STAGE + 1024;
-  static constexpr int THREADS = X3 ? 320 : 192;
+  static constexpr int THREADS = X3 ? 352 : 224;                // + 4 splitter warps
   static constexpr uint32_t IDESC = umma_idesc_tf32(128, NT);
   static constexpr uint32_t TMEM_COLS = (2 * NT < 32) ? 32 : 2 * NT;   // two accumulators
 };
@@ -84,7 +89,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   using Cfg = T2Cfg<NT, X3>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t2_raw[];
-  __shared__ __align__(8) uint64_t halo_full[2], halo_ready[2], halo_empty[2], b_full[STAGES], b_empty[STAGES],
+  constexpr int HB = Cfg::HB;
+  __shared__ __align__(8) uint64_t halo_full[HB], halo_ready[HB], halo_empty[HB], b_full[STAGES], b_empty[STAGES],
       acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
@@ -95,10 +101,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int pad = (e.ntaps == 9) ? 1 : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < HB; ++i) {
       mbar_init(smem_u32(&halo_full[i]), 1);
       mbar_init(smem_u32(&halo_ready[i]), 128);       // X3: every splitter thread arrives
       mbar_init(smem_u32(&halo_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&acc_full[i]), 1);
       mbar_init(smem_u32(&acc_empty[i]), 128);        // every epilogue thread arrives
     }
@@ -117,25 +125,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   //   g  = halo chunks consumed so far (buffer g&1, use number g>>1), step = filter ring stages so far,
   //   it = tiles so far (accumulator it&1, use number it>>1).
   if (warp == 0) {
-    if (lane == 0) {                                            // ---------------- TMA producer
-      int g = 0, step = 0;
-      auto load_halo = [&](int gg, int cc, const TileCoord& t) {
-        const int hb = gg & 1;
-        if (gg >= 2) mbar_wait(smem_u32(&halo_empty[hb]), (uint32_t)(((gg >> 1) - 1) & 1));
-        const uint32_t bar = smem_u32(&halo_full[hb]);
-        mbar_expect_tx(bar, e.halo_bytes);
-        const uint32_t dst = base + (uint32_t)hb * T2_HALO_STRIDE;
-        if (cc < e.cchunks0) tma_load_4d(dst, &tmA0, bar, cc * 32, t.ox0 - pad, t.oy0 - pad, t.n);
-        else                 tma_load_4d(dst, &tmA1, bar, (cc - e.cchunks0) * 32, t.ox0 - pad, t.oy0 - pad, t.n);
-      };
-      int tile = blockIdx.x;
-      if (tile < e.ntiles) load_halo(0, 0, tile_coord(tile, e, NT));
-      for (; tile < e.ntiles; tile += gridDim.x) {
+    if (lane == 0) {                                            // ---------------- halo TMA producer
+      int g = 0;
+      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
         const TileCoord t = tile_coord(tile, e, NT);
         for (int cc = 0; cc < e.cchunks; ++cc, ++g) {
-          // prefetch the next halo chunk (of this tile, or chunk 0 of the next tile) before streaming this chunk's filters
-          if (cc + 1 < e.cchunks) load_halo(g + 1, cc + 1, t);
-          else if (tile + (int)gridDim.x < e.ntiles) load_halo(g + 1, 0, tile_coord(tile + gridDim.x, e, NT));
+          const int hb = g % HB, use = g / HB;
+          mbar_wait(smem_u32(&halo_empty[hb]), (uint32_t)((use & 1) ^ 1));
+          const uint32_t bar = smem_u32(&halo_full[hb]);
+          mbar_expect_tx(bar, e.halo_bytes);
+          const uint32_t dst = base + (uint32_t)hb * T2_HALO_STRIDE;
+          if (cc < e.cchunks0) tma_load_4d(dst, &tmA0, bar, cc * 32, t.ox0 - pad, t.oy0 - pad, t.n);
+          else                 tma_load_4d(dst, &tmA1, bar, (cc - e.cchunks0) * 32, t.ox0 - pad, t.oy0 - pad, t.n);
+        }
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {                                            // ---------------- filter TMA producer
+      int step = 0;
+      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord(tile, e, NT);
+        for (int cc = 0; cc < e.cchunks; ++cc) {
           for (int tap0 = 0; tap0 < e.ntaps; tap0 += e.tps, ++step) {      // one ring stage = e.tps filter taps
             const int st = step % STAGES, round = step / STAGES;
             mbar_wait(smem_u32(&b_empty[st]), (uint32_t)((round & 1) ^ 1));
@@ -162,11 +172,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const uint32_t d_tmem = tmem_base + (uint32_t)ab * NT;
         int kstep = 0;
         for (int cc = 0; cc < e.cchunks; ++cc, ++g) {
-          const int hb = g & 1;
-          if (X3) mbar_wait(smem_u32(&halo_ready[hb]), (uint32_t)((g >> 1) & 1));
-          else    mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g >> 1) & 1));
+          const int hb = g % HB;
+          if (X3) mbar_wait(smem_u32(&halo_ready[hb]), (uint32_t)((g / HB) & 1));
+          else    mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g / HB) & 1));
           tc_fence_after();
-          const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE, h_lo = h_hi + 2 * T2_HALO_STRIDE;
+          const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE, h_lo = h_hi + (uint32_t)HB * T2_HALO_STRIDE;
           for (int tap0 = 0; tap0 < e.ntaps; tap0 += e.tps, ++step) {
             const int st = step % STAGES, round = step / STAGES;
             mbar_wait(smem_u32(&b_full[st]), (uint32_t)(round & 1));
@@ -230,16 +240,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
       }
     }
-  } else if (X3) {                                              // ---------------- splitter (warps 6..9)
-    const int tI = threadIdx.x - 192;
+  } else if (X3 && warp >= 7) {                                 // ---------------- splitter (warps 7..10)
+    const int tI = threadIdx.x - 224;
     const int nvec = (int)(e.halo_bytes / 16);
     int g = 0;
     for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
       for (int cc = 0; cc < e.cchunks; ++cc, ++g) {
-        const int hb = g & 1;
-        mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g >> 1) & 1));
+        const int hb = g % HB;
+        mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g / HB) & 1));
         float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)hb * T2_HALO_STRIDE);
-        float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)(2 + hb) * T2_HALO_STRIDE);
+        float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)(HB + hb) * T2_HALO_STRIDE);
         for (int i = tI; i < nvec; i += 128) {
           const float4 v = hi[i];
           const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
