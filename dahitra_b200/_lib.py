@@ -64,7 +64,7 @@ SIGNATURES = {
     "dahitra_conv2d": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P]),
     "dahitra_conv2d_up2_tc": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
     "dahitra_stem": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P, _P]),
-    "dahitra_stem_tc": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P, _P]),
+    "dahitra_stem_tc": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P, _I, _P]),
     "dahitra_maxpool3x3s2": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "dahitra_squeeze_tokens": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "dahitra_token_encoder": (_I, [_P, _I, _I, _P, _I, _I, _P, _P]),

@@ -166,8 +166,8 @@ extern "C" int dahitra_stem(const float* x, long long xbs, int N, int H, int W, 
   return dh_launch_stem(x, xbs, N, H, W, w, bias, out, (cudaStream_t)stream);
 }
 extern "C" int dahitra_stem_tc(const float* x, long long xbs, int N, int H, int W, const float* wtc, const float* bias,
-                               float* out, void* stream) {
-  return dh_launch_stem_tc(x, xbs, N, H, W, wtc, bias, out, (cudaStream_t)stream);
+                               float* out, int x3, void* stream) {
+  return dh_launch_stem_tc(x, xbs, N, H, W, wtc, bias, out, x3, (cudaStream_t)stream);
 }
 extern "C" int dahitra_maxpool3x3s2(const float* in, int N, int H, int W, int C, float* out, void* stream) {
   return dh_launch_maxpool(in, N, H, W, C, out, (cudaStream_t)stream);
@@ -289,7 +289,8 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
   float* F2 = ws + p.f2;
   const double stem_fl = 2.0 * B * h2 * w2 * 64 * 147, stem_by = 4.0 * B * ((double)3 * H * W + (double)h2 * w2 * 64);
   auto stem = [&](const float* xin, float* o) -> int {
-    return (flags & DH_FLAG_STEM_TC) ? dh_launch_stem_tc(xin, x_batch_stride, B, H, W, Wt(DH_W_STEM_WTC), Wt(DH_W_STEM_B), o, s)
+    return (flags & DH_FLAG_STEM_TC) ? dh_launch_stem_tc(xin, x_batch_stride, B, H, W, Wt(DH_W_STEM_WTC), Wt(DH_W_STEM_B), o,
+                                                         (flags & DH_FLAG_TC_3XTF32) ? 1 : 0, s)
                                      : dh_launch_stem(xin, x_batch_stride, B, H, W, Wt(DH_W_STEM_W), Wt(DH_W_STEM_B), o, s);
   };
   DH_STEP("stem_pre", stem_fl, stem_by, stem(x1, F2));

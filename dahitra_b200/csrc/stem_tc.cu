@@ -21,10 +21,21 @@ constexpr int SK_KSTEPS = 5;                         // 160 / 32
 constexpr uint32_t SK_A_BYTES = 128 * 128;           // one A tile
 constexpr uint32_t SK_B_BYTES = SK_KSTEPS * 64 * 128;    // 40 KB filter image
 constexpr uint32_t SK_HALO_BYTES = (3 * SK_PLANE + 8) * 4;   // + a zero slot for the K padding
-constexpr uint32_t SK_SMEM = 2 * SK_A_BYTES + SK_B_BYTES + 1024 + ((SK_HALO_BYTES + 15) & ~15u) + 160 * 4;
 constexpr uint32_t SK_IDESC = umma_idesc_tf32(128, 64);
+template <bool X3> struct SkCfg {       // X3: A tiles and the filter image come as TF32 hi + lo pairs (3 MMAs per product)
+  static constexpr uint32_t NA = X3 ? 4 : 2;                      // A tiles: [buf0 hi, buf1 hi, buf0 lo, buf1 lo]
+  static constexpr uint32_t NB = X3 ? 2 : 1;
+  static constexpr uint32_t SMEM = NA * SK_A_BYTES + NB * SK_B_BYTES + 1024 + ((SK_HALO_BYTES + 15) & ~15u) + 160 * 4;
+};
 
-__global__ void __launch_bounds__(128, 2)
+__device__ __forceinline__ float sk_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(128, X3 ? 1 : 2)
 stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH, int OW, int tilesX,
                const float* __restrict__ wtc, const float* __restrict__ bias, float* __restrict__ out) {
   extern __shared__ uint8_t sk_raw[];
@@ -35,11 +46,14 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
   const int oy0 = (blockIdx.x / tilesX) * SK_TH, ox0 = (blockIdx.x % tilesX) * SK_TW;
   const uint32_t base = (smem_u32(sk_raw) + 1023u) & ~1023u;
   uint8_t* bp = sk_raw + (base - smem_u32(sk_raw));
+  using Cfg = SkCfg<X3>;
   float* a_tile[2] = {reinterpret_cast<float*>(bp), reinterpret_cast<float*>(bp + SK_A_BYTES)};
   const uint32_t a_addr[2] = {base, base + SK_A_BYTES};
-  const uint32_t b_addr = base + 2 * SK_A_BYTES;
-  float* halo = reinterpret_cast<float*>(bp + 2 * SK_A_BYTES + SK_B_BYTES);
-  int* koff = reinterpret_cast<int*>(bp + 2 * SK_A_BYTES + SK_B_BYTES + ((SK_HALO_BYTES + 15) & ~15u));
+  constexpr uint32_t A_LO = 2 * SK_A_BYTES;                            // lo twins of the two A tiles (X3)
+  const uint32_t b_addr = base + Cfg::NA * SK_A_BYTES;
+  constexpr uint32_t OFF_H = Cfg::NA * SK_A_BYTES + Cfg::NB * SK_B_BYTES;
+  float* halo = reinterpret_cast<float*>(bp + OFF_H);
+  int* koff = reinterpret_cast<int*>(bp + OFF_H + ((SK_HALO_BYTES + 15) & ~15u));
 
   if (tid == 0) {
     mbar_init(smem_u32(&w_bar), 1); mbar_init(smem_u32(&free_bar[0]), 1); mbar_init(smem_u32(&free_bar[1]), 1);
@@ -51,8 +65,9 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
   __syncthreads();
   tc_fence_after();
   if (tid == 0) {
-    mbar_expect_tx(smem_u32(&w_bar), SK_B_BYTES);
+    mbar_expect_tx(smem_u32(&w_bar), Cfg::NB * SK_B_BYTES);
     bulk_load_1d(b_addr, wtc, SK_B_BYTES, smem_u32(&w_bar));
+    if (X3) bulk_load_1d(b_addr + SK_B_BYTES, wtc + SK_B_BYTES / 4, SK_B_BYTES, smem_u32(&w_bar));
   }
   // halo: input rows 2*oy0-3 .. +20, cols 2*ox0-3 .. +36, zero outside the image
   const float* xn = x + (size_t)n * xbs;
@@ -86,8 +101,13 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
     }
     float* at = a_tile[buf];
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch)
-      *reinterpret_cast<float4*>(at + tid * 32 + ((ch ^ (tid & 7)) << 2)) = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+    for (int ch = 0; ch < 8; ++ch) {
+      const int o = tid * 32 + ((ch ^ (tid & 7)) << 2);
+      const float h0 = sk_tf32(v[ch * 4]), h1 = sk_tf32(v[ch * 4 + 1]), h2 = sk_tf32(v[ch * 4 + 2]), h3 = sk_tf32(v[ch * 4 + 3]);
+      *reinterpret_cast<float4*>(at + o) = make_float4(h0, h1, h2, h3);
+      if (X3) *reinterpret_cast<float4*>(at + A_LO / 4 + o) = make_float4(sk_tf32(v[ch * 4] - h0), sk_tf32(v[ch * 4 + 1] - h1),
+                                                                        sk_tf32(v[ch * 4 + 2] - h2), sk_tf32(v[ch * 4 + 3] - h3));
+    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -97,6 +117,13 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
       const uint64_t ad = umma_desc_sw128(a_addr[buf]), bd = umma_desc_sw128(b_addr + (uint32_t)kt * 64 * 128);
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_tf32(tmem_slot, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), SK_IDESC, (kt | k) ? 1u : 0u);
+      if (X3) {
+        const uint64_t al = umma_desc_sw128(a_addr[buf] + A_LO), bl = umma_desc_sw128(b_addr + SK_B_BYTES + (uint32_t)kt * 64 * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(tmem_slot, al + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), SK_IDESC, 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(tmem_slot, ad + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), SK_IDESC, 1u);
+      }
       umma_commit(smem_u32(&free_bar[buf]));
       if (kt == SK_KSTEPS - 1) umma_commit(smem_u32(&acc_bar));
     }
@@ -130,16 +157,22 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
 }  // namespace
 
 int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const float* wtc, const float* b, float* out,
-                      cudaStream_t s) {
+                      int x3, cudaStream_t s) {
   DH_REQUIRE(x && wtc && b && out, DH_E_NULL);
   DH_REQUIRE(N > 0 && H >= 8 && W >= 8 && H % 2 == 0 && W % 2 == 0, DH_E_SHAPE);
   DH_REQUIRE(dh_aligned16(wtc) && dh_aligned16(b) && dh_aligned16(out), DH_E_ALIGN);
   const int OH = H / 2, OW = W / 2;
   const int tx = dh_cdiv(OW, SK_TW), ty = dh_cdiv(OH, SK_TH);
-  cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM);
-  if (e != cudaSuccess) return (int)e;
   dim3 grid(tx * ty, 1, N);
-  stem_tc_kernel<<<grid, 128, SK_SMEM, s>>>(x, xbs, H, W, OH, OW, tx, wtc, b, out);
+  if (x3) {
+    cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<true>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    stem_tc_kernel<true><<<grid, 128, SkCfg<true>::SMEM, s>>>(x, xbs, H, W, OH, OW, tx, wtc, b, out);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<false>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    stem_tc_kernel<false><<<grid, 128, SkCfg<false>::SMEM, s>>>(x, xbs, H, W, OH, OW, tx, wtc, b, out);
+  }
   DH_CHECK_LAUNCH();
   return 0;
 }

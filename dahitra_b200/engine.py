@@ -27,8 +27,8 @@ MODES = {
     "fp32": 0,                                             # every contraction in fp32 FMA (strict)
     "fp32_tcdec": DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,      # strict + the 3xTF32 (fp32-grade) tensor-core decoder
     # fp32-grade accuracy on the tensor cores: error-compensated 3xTF32 for the stride-1 convolutions and the decoder;
-    # the stem and the two stride-2 convolutions stay on the fp32 CUDA-core kernels
-    "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
+    # the 7x7 stem (3xTF32 too); the two stride-2 convolutions stay on the fp32 CUDA-core kernel
+    "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32_fast": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC,   # 1xTF32 decoder too
 }
@@ -104,6 +104,13 @@ def kmajor_split(wt):
     return torch.stack([hi, lo])
 
 
+def stem_tc_image(wk):
+    """[160][64] stem filter (K padded) -> [hi | lo] images, each 5 K-step tiles of the swizzled B[n=co][k] operand."""
+    hi, lo = tf32_split(wk.double())
+    img = lambda w: torch.cat([swizzle128(w[kt * 32:(kt + 1) * 32].T.contiguous()) for kt in range(5)])
+    return torch.cat([img(hi), img(lo)])
+
+
 def swizzle128(m):
     """[rows][32] matrix B[n][k] -> flat K-major SWIZZLE_128B shared-memory image (rows of 128 B, the 16-byte
     chunk index XOR-ed with row % 8): element (n, k) lands at n*32 + (((k>>2) ^ (n&7)) << 2 | (k&3))."""
@@ -139,7 +146,7 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
     put_conv("DH_W_STEM", "resnet.conv1", "resnet.bn1")
     wk = torch.zeros(160, 64, dtype=torch.float64)                       # K = 147 padded to 5 steps of 32
     wk[:147] = P["DH_W_STEM_W"]
-    P["DH_W_STEM_WTC"] = torch.cat([swizzle128(wk[kt * 32:(kt + 1) * 32].T.contiguous()) for kt in range(5)])
+    P["DH_W_STEM_WTC"] = stem_tc_image(wk)
     for li in (1, 2, 3):
         for bi in (0, 1):
             p = f"resnet.layer{li}.{bi}"

@@ -92,7 +92,7 @@ enum dh_weight_slot {
    * (DH_DECTC_LAYER_FLOATS), "swz" = K-major SWIZZLE_128B image of B[n][k] (W1f: n=hidden, k=channel, LN2
    * gamma folded; W2: n=channel, k=hidden); cbA/cbM = cumulative biases after the attention / MLP of the layer */
   DH_W_LV5_DECTC, DH_W_LV4_DECTC, DH_W_LV3_DECTC,
-  DH_W_STEM_WTC,   /* stem filter for the tcgen05 stem: 5 K-step tiles of B[n=co 64][k 32] swz (K = 147 padded to 160) */
+  DH_W_STEM_WTC,   /* stem filter for the tcgen05 stem: [hi, lo] x 5 K-step tiles of B[n=co 64][k 32] swz (K = 147 padded to 160) */
   DH_W_COUNT
 };
 
@@ -172,9 +172,9 @@ int dahitra_conv2d_up2_tc(const float* in, int N, int inH, int inW, const float*
 int dahitra_stem(const float* x, long long x_batch_stride, int N, int H, int W,
                  const float* w, const float* bias, float* out, void* stream);
 
-/* Same stem on the tensor cores (TF32 operands): wtc = DH_W_STEM_WTC image. */
+/* Same stem on the tensor cores (TF32 operands; x3 != 0: error-compensated 3xTF32): wtc = DH_W_STEM_WTC image. */
 int dahitra_stem_tc(const float* x, long long x_batch_stride, int N, int H, int W,
-                    const float* wtc, const float* bias, float* out, void* stream);
+                    const float* wtc, const float* bias, float* out, int x3, void* stream);
 
 /* MaxPool2d(3, stride 2, pad 1) on NHWC (reference models/networks.py:1123,1128). */
 int dahitra_maxpool3x3s2(const float* in, int N, int H, int W, int C, float* out, void* stream);

@@ -47,11 +47,11 @@ def stem(x, w, b):
     return out
 
 
-def stem_tc(x, wtc, b):
+def stem_tc(x, wtc, b, x3=0):
     lib = _lib.load()
     N, _, H, W = x.shape
     out = torch.empty((N, H // 2, W // 2, 64), device=x.device, dtype=torch.float32)
-    _lib.check(lib.dahitra_stem_tc(_p(x), 3 * H * W, N, H, W, _p(wtc), _p(b), _p(out), _stream()), "dahitra_stem_tc")
+    _lib.check(lib.dahitra_stem_tc(_p(x), 3 * H * W, N, H, W, _p(wtc), _p(b), _p(out), x3, _stream()), "dahitra_stem_tc")
     return out
 
 

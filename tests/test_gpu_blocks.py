@@ -139,17 +139,21 @@ def test_stem(shape):
 @pytest.mark.parametrize("shape", [(2, 64, 64), (1, 96, 160), (1, 256, 256), (1, 40, 72)])
 def test_stem_tcgen05(shape):
     """tensor-core stem (on-chip im2col + tcgen05, TF32) vs fp64."""
-    from dahitra_b200.engine import swizzle128
+    from dahitra_b200.engine import stem_tc_image
     N, H, W = shape
     x = rnd(N, 3, H, W, seed=1)
     w = rnd(147, 64, seed=2, scale=147 ** -0.5)
     b = rnd(64, seed=3)
     wk = torch.zeros(160, 64)
     wk[:147] = w.cpu()
-    wtc = torch.cat([swizzle128(wk[kt * 32:(kt + 1) * 32].T.contiguous()) for kt in range(5)]).to(DEV)
-    y = abi.stem_tc(x, wtc, b)
+    wtc = stem_tc_image(wk).float().to(DEV)
+    ref = E.stem(x.double(), w.double(), b.double())
+    y = abi.stem_tc(x, wtc, b, x3=0)
     torch.cuda.synchronize()
-    close(y, E.stem(x.double(), w.double(), b.double()), rtol=2e-3, atol=4e-3)
+    close(y, ref, rtol=2e-3, atol=4e-3)
+    y3 = abi.stem_tc(x, wtc, b, x3=1)                      # error-compensated: same bar as the fp32 CUDA-core stem
+    torch.cuda.synchronize()
+    close(y3, ref)
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64), (1, 18, 30, 128)])
