@@ -228,6 +228,15 @@ int dahitra_pixel_decoder_tc(const float* x, const float* pos, const float* tabl
 int dahitra_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* bias,
                        float* logits, unsigned char* argmax_u8, void* stream);
 
+/* ---- next to the hot path ------------------------------------------------------------ */
+
+/* Device-side confusion matrix: cm[g][p] += #{ i : gt[i] = g < nc, pred[i] = p } — replaces the per-batch
+ * argmax -> .cpu().numpy() -> np.bincount of reference models/evaluator.py:95-104 / misc/metric_tool.py:141-158.
+ *   pred, gt: uint8 class maps of n pixels (gt >= nc, e.g. 255, is ignored like the reference's mask);
+ *   cm: device int64 [nc][nc], ACCUMULATED (zero it before the first call). */
+int dahitra_confusion_matrix(const unsigned char* pred, const unsigned char* gt, long long n, int nc,
+                             long long* cm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
