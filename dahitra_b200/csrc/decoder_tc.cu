@@ -92,15 +92,19 @@ constexpr uint32_t PDT_MLP_HI = 2144 * 4;                   // W1_hi | W2_hi | b
 constexpr uint32_t PDT_LO = 2048 * 4;                       // two 32x32 lo tiles
 constexpr uint32_t PDT_HI_STRIDE = 9216;                    // 1024-aligned room for a hi block
 
+// A CTA holds G warpgroups; each owns one 128-pixel tile (its A tile(s), 96 TMEM columns, its own MMA barrier) of the
+// SAME image, so all of them share the per-layer table / MLP buffers.  G independent serial chains per CTA are what
+// hides the write-A -> MMA -> tcgen05.ld latency of each chain.
 template <bool X3> struct PdtCfg {
+  static constexpr int G = 4;
   static constexpr uint32_t BUF = PDT_HI_STRIDE + (X3 ? PDT_LO : 0);            // one table (or MLP) buffer
-  static constexpr uint32_t A_TILES = X3 ? 2 : 1;
-  static constexpr uint32_t SMEM = A_TILES * PDT_A_BYTES + 4 * BUF + 1024;
-  static constexpr int CTAS = X3 ? 2 : 4;
+  static constexpr uint32_t A_TILES = X3 ? 2 : 1;                               // per warpgroup
+  static constexpr uint32_t SMEM = G * A_TILES * PDT_A_BYTES + 4 * BUF + 1024;
+  static constexpr int CTAS = X3 ? 1 : 2;
 };
 
 template <int HEADS, bool X3>
-__global__ void __launch_bounds__(PDT_ROWS, PdtCfg<X3>::CTAS)
+__global__ void __launch_bounds__(PDT_ROWS * PdtCfg<X3>::G, PdtCfg<X3>::CTAS)
 pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const float* __restrict__ tables,
                         const float* __restrict__ pack, int npix, int w, int depth, const float* __restrict__ skip,
                         int skip_up, float* __restrict__ out) {
@@ -109,33 +113,39 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   constexpr uint32_t IDESC_S = umma_idesc_tf32(128, H4);
   constexpr uint32_t IDESC_32 = umma_idesc_tf32(128, 32);
   extern __shared__ uint8_t pdt_raw[];
-  __shared__ __align__(8) uint64_t tab_bar[2], mma_bar;
+  constexpr int G = Cfg::G;
+  __shared__ __align__(8) uint64_t tab_bar[2], mma_bar[G];
   __shared__ uint32_t tmem_slot;
 
-  const int tid = threadIdx.x, warp = tid >> 5, img = blockIdx.y;
-  const int p = blockIdx.x * PDT_ROWS + tid;
+  const int wg = threadIdx.x >> 7;                                      // warpgroup = tile within the CTA
+  const int tid = threadIdx.x & 127, warp = tid >> 5, img = blockIdx.y; // tid: row of this warpgroup's tile
+  const int p = (blockIdx.x * G + wg) * PDT_ROWS + tid;
   const bool valid = p < npix;
   const uint32_t base = (smem_u32(pdt_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = pdt_raw + (base - smem_u32(pdt_raw));
-  float* a_hi = reinterpret_cast<float*>(base_ptr);
-  float* a_lo = reinterpret_cast<float*>(base_ptr + PDT_A_BYTES);       // X3 only
-  const uint32_t a_addr = base;
-  constexpr uint32_t BUFS0 = Cfg::A_TILES * PDT_A_BYTES;
+  const uint32_t a_off = (uint32_t)wg * Cfg::A_TILES * PDT_A_BYTES;
+  float* a_hi = reinterpret_cast<float*>(base_ptr + a_off);
+  float* a_lo = reinterpret_cast<float*>(base_ptr + a_off + PDT_A_BYTES);       // X3 only
+  const uint32_t a_addr = base + a_off;
+  constexpr uint32_t BUFS0 = G * Cfg::A_TILES * PDT_A_BYTES;
   auto tab_addr = [&](int b) { return base + BUFS0 + (uint32_t)b * Cfg::BUF; };
   auto mlp_addr = [&](int b) { return base + BUFS0 + 2 * Cfg::BUF + (uint32_t)b * Cfg::BUF; };
   auto tab_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + BUFS0 + (size_t)b * Cfg::BUF); };
   auto mlp_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + BUFS0 + 2 * Cfg::BUF + (size_t)b * Cfg::BUF); };
 
-  if (tid == 0) {
-    mbar_init(smem_u32(&tab_bar[0]), 1); mbar_init(smem_u32(&tab_bar[1]), 1); mbar_init(smem_u32(&mma_bar), 1);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&tab_bar[0]), 1); mbar_init(smem_u32(&tab_bar[1]), 1);
+    for (int i = 0; i < G; ++i) mbar_init(smem_u32(&mma_bar[i]), 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 128);
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&tmem_slot), 512);          // G x 96 columns (power of two: 512)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_slot + ((uint32_t)(warp * 32) << 16);     // this warp's lane quarter
+  const uint32_t tmem_wg = tmem_slot + (uint32_t)wg * 96;               // this warpgroup's columns
+  const uint32_t tmem = tmem_wg + ((uint32_t)(warp * 32) << 16);       // ... and this warp's lane quarter
   const uint32_t TM_X = 0, TM_S = 32, TM_H = 64;
+  const uint32_t my_bar = smem_u32(&mma_bar[wg]);
 
   auto issue_loads = [&](int layer) {
     const int b = layer & 1;
@@ -150,7 +160,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       bulk_load_1d(mlp_addr(b) + PDT_HI_STRIDE, pg + 2144, PDT_LO, bar);
     }
   };
-  if (tid == 0) issue_loads(0);
+  if (threadIdx.x == 0) issue_loads(0);
 
   // ---- x (+ pos) -> registers and TMEM
   float xr[32];
@@ -194,31 +204,32 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   uint32_t mma_phase = 0;
   // one MMA round: all rows of the A tile(s) are written -> thread 0 issues `nk` K-steps -> everyone waits for the commit.
   // b_hi_addr: hi tile of the B operand; its lo twin sits PDT_HI_STRIDE-relative at the same offset inside the lo block.
-  auto mma_round = [&](uint32_t b_hi_addr, uint32_t b_lo_addr, uint32_t idesc, uint32_t tm_col, int nk, bool accumulate,
-                       int prefetch_layer) {
+  auto mma_round = [&](uint32_t b_hi_addr, uint32_t b_lo_addr, uint32_t idesc, uint32_t tm_col, int nk, bool accumulate) {
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
+    asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");         // this warpgroup's rows are all written
     if (tid == 0) {
-      if (prefetch_layer >= 0) issue_loads(prefetch_layer);
       tc_fence_after();
       const uint64_t ah = umma_desc_sw128(a_addr), bh = umma_desc_sw128(b_hi_addr);
-      const uint32_t d = tmem_slot + tm_col;
+      const uint32_t d = tmem_wg + tm_col;
       for (int k = 0; k < nk; ++k) umma_tf32(d, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, (accumulate || k) ? 1u : 0u);
       if (X3) {
         const uint64_t al = umma_desc_sw128(a_addr + PDT_A_BYTES), bl = umma_desc_sw128(b_lo_addr);
         for (int k = 0; k < nk; ++k) umma_tf32(d, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, 1u);
         for (int k = 0; k < nk; ++k) umma_tf32(d, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
       }
-      umma_commit(smem_u32(&mma_bar));
+      umma_commit(my_bar);
     }
-    mbar_wait(smem_u32(&mma_bar), mma_phase);
+    mbar_wait(my_bar, mma_phase);
     mma_phase ^= 1u;
     tc_fence_after();
   };
 
   for (int layer = 0; layer < depth; ++layer) {
     const int b = layer & 1;
+    // every warpgroup has finished layer-1 (the last reader of buffer (layer+1)&1): prefetch the next layer's tables
+    __syncthreads();
+    if (threadIdx.x == 0 && layer + 1 < depth) issue_loads(layer + 1);
     mbar_wait(smem_u32(&tab_bar[b]), (uint32_t)((layer >> 1) & 1));
     const float* tabp = tab_ptr(b);
     const float* mlpp = mlp_ptr(b);
@@ -241,8 +252,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
       write_a_row(t);
     }
-    // the buffer of layer+1 was last read in layer-1; every thread is past that once it reaches this barrier
-    mma_round(t_hi, t_lo, IDESC_S, TM_S, 4, false, (layer + 1 < depth) ? layer + 1 : -1);
+        mma_round(t_hi, t_lo, IDESC_S, TM_S, 4, false);
     // ---- 2. P = softmax_j(S + cA) ; x += P . TB^T
     {
       if constexpr (HEADS == 8) {
@@ -267,7 +277,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       }
       write_a_row(t);
     }
-    mma_round(t_hi + 4096, t_lo + 4096, IDESC_32, TM_X, H4 / 8, true, -1);
+    mma_round(t_hi + 4096, t_lo + 4096, IDESC_32, TM_X, H4 / 8, true);
     // ---- 3. Hid = xhat' . W1f^T
     {
       uint32_t u[32];
@@ -284,7 +294,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
       write_a_row(t);
     }
-    mma_round(m_hi, m_lo, IDESC_32, TM_H, 4, false, -1);
+    mma_round(m_hi, m_lo, IDESC_32, TM_H, 4, false);
     // ---- 4. x += gelu(Hid + b1f) . W2^T
     {
       uint32_t u[32];
@@ -293,7 +303,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       for (int c = 0; c < 32; ++c) t[c] = gelu_erf(__uint_as_float(u[c]) + b1f[c]);
       write_a_row(t);
     }
-    mma_round(m_hi + 4096, m_lo + 4096, IDESC_32, TM_X, 4, true, -1);
+    mma_round(m_hi + 4096, m_lo + 4096, IDESC_32, TM_X, 4, true);
     {
       uint32_t u[32];
       tmem_ld32(tmem + TM_X, u);
@@ -320,9 +330,9 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (threadIdx.x < 32) {
     tc_fence_after();
-    tmem_dealloc(tmem_slot, 128);
+    tmem_dealloc(tmem_slot, 512);
   }
 }
 
@@ -332,7 +342,7 @@ int launch_pdt(dim3 grid, const float* x, const float* pos, const float* tables,
   cudaError_t e = cudaFuncSetAttribute(pixel_decoder_tc_kernel<HEADS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)PdtCfg<X3>::SMEM);
   if (e != cudaSuccess) return (int)e;
-  pixel_decoder_tc_kernel<HEADS, X3><<<grid, PDT_ROWS, PdtCfg<X3>::SMEM, s>>>(x, pos, tables, pack, npix, w, depth, skip, skip_up, out);
+  pixel_decoder_tc_kernel<HEADS, X3><<<grid, PDT_ROWS * PdtCfg<X3>::G, PdtCfg<X3>::SMEM, s>>>(x, pos, tables, pack, npix, w, depth, skip, skip_up, out);
   DH_CHECK_LAUNCH();
   return 0;
 }
@@ -358,7 +368,7 @@ int dh_launch_pixel_decoder_tc(const float* x, const float* pos, const float* ta
   DH_REQUIRE(dh_aligned16(x) && dh_aligned16(pos) && dh_aligned16(tables) && dh_aligned16(pack) && dh_aligned16(skip) &&
              dh_aligned16(out), DH_E_ALIGN);
   const int npix = h * w;
-  dim3 grid(dh_cdiv(npix, PDT_ROWS), nimg);
+  dim3 grid(dh_cdiv(npix, PDT_ROWS * PdtCfg<true>::G), nimg);
   if (heads == 4)
     return x3 ? launch_pdt<4, true>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, s)
               : launch_pdt<4, false>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, s);

@@ -31,6 +31,8 @@ def confusion_matrix(pred: torch.Tensor, gt: torch.Tensor, n_class: int, out: to
     p8, g8 = p8.contiguous(), g8.contiguous()
     if out is None:
         out = torch.zeros((n_class, n_class), dtype=torch.int64, device=pred.device)
+    if p8.numel() == 0:
+        return out
     rc = _lib.load().dahitra_confusion_matrix(p8.data_ptr(), g8.data_ptr(), p8.numel(), n_class, out.data_ptr(),
                                               torch.cuda.current_stream(pred.device).cuda_stream)
     _lib.check(rc, "dahitra_confusion_matrix")
