@@ -32,7 +32,7 @@ WORKLOADS = {
     "xbd1024": dict(H=1024, W=1024, pairs=8, nc=5, variant="xbd",
                     desc="xBD 1024x1024 pre/post pair 5-class forward, 8 pairs per GPU per step"),
 }
-DEFAULT_MODE = "tf32x3"
+DEFAULT_MODE = "tf32x3"     # == dahitra_b200.engine.DEFAULT_MODE: what a user of the module gets without configuration
 FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0)
 
 
@@ -178,7 +178,7 @@ def run_native(a, wl):
         net = XNet(input_nc=3, output_nc=wl["nc"], token_len=4, resnet_stages_num=4, with_pos="learned",
                    with_decoder_pos="learned", enc_depth=1, dec_depth=8).to(dev).eval()
     from dahitra_b200.engine import MODES
-    net._engine.flags = a.flags if a.flags is not None else MODES[a.mode]
+    net.set_mode(a.flags if a.flags is not None else a.mode)
     mode_name = next((k for k, v in MODES.items() if v == net._engine.flags), f"flags{net._engine.flags}")
     # rotating input sets so consecutive steps never re-read the same inputs from L2 (3 x 100 MB > 126 MB L2;
     # the ~3.5 GB of per-step intermediates stream through HBM regardless)

@@ -82,7 +82,7 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, const T2Args& e, int N
   return t;
 }
 
-template <int NT, bool X3>
+template <int NT, bool X3, int KS>
 __global__ void __launch_bounds__(T2Cfg<NT, X3>::THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const T2Args e) {
@@ -98,7 +98,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const uint32_t base = (smem_u32(t2_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = t2_raw + (base - smem_u32(t2_raw));
   const uint32_t b_ring = base + Cfg::HALO_BUFS * T2_HALO_STRIDE;
-  const int pad = (e.ntaps == 9) ? 1 : 0;
+  constexpr int pad = (KS == 3) ? 1 : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < HB; ++i) {
@@ -142,16 +142,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
   } else if (warp == 6) {
     if (lane == 0) {                                            // ---------------- filter TMA producer
+      constexpr int NTAPS_ = KS * KS;
+      constexpr int TPS_ = (NTAPS_ % Cfg::TPS == 0) ? Cfg::TPS : 1;
       int step = 0;
       for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
         const TileCoord t = tile_coord(tile, e, NT);
         for (int cc = 0; cc < e.cchunks; ++cc) {
-          for (int tap0 = 0; tap0 < e.ntaps; tap0 += e.tps, ++step) {      // one ring stage = e.tps filter taps
+          for (int tap0 = 0; tap0 < NTAPS_; tap0 += TPS_, ++step) {        // one ring stage = TPS_ filter taps
             const int st = step % STAGES, round = step / STAGES;
             mbar_wait(smem_u32(&b_empty[st]), (uint32_t)((round & 1) ^ 1));
             const uint32_t bar = smem_u32(&b_full[st]);
-            mbar_expect_tx(bar, (uint32_t)e.tps * Cfg::B_TAP);
-            for (int tt = 0; tt < e.tps; ++tt) {
+            mbar_expect_tx(bar, (uint32_t)TPS_ * Cfg::B_TAP);
+#pragma unroll
+            for (int tt = 0; tt < TPS_; ++tt) {
               const uint32_t dst = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)tt * Cfg::B_TAP;
               const int kcol = (tap0 + tt) * e.Cin + cc * 32;
               tma_load_2d(dst, &tmB, bar, kcol, t.n0);
@@ -163,35 +166,44 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0) {                                            // ---------------- MMA issuer
-      const uint32_t sbo = (uint32_t)e.halo_w * 128u;
-      int g = 0, step = 0, it = 0;
+      // The issuing thread is the critical path of the whole kernel: everything between two tcgen05.mma's is
+      // compile-time (tap shifts, taps per stage) or a wrapping counter — no divisions, no runtime tap arithmetic.
+      constexpr int NTAPS = KS * KS;
+      constexpr int HALO_W = (KS == 3) ? T2_HW : T2_TW;
+      constexpr int TPS = (NTAPS % Cfg::TPS == 0) ? Cfg::TPS : 1;
+      constexpr uint32_t SBO = (uint32_t)HALO_W * 128u;
+      int hb = 0, st = 0;
+      uint32_t hphase = 0, bphase = 0;
+      int it = 0;
       for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
         const int ab = it & 1;
         mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));    // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)ab * NT;
-        int kstep = 0;
-        for (int cc = 0; cc < e.cchunks; ++cc, ++g) {
-          const int hb = g % HB;
-          if (X3) mbar_wait(smem_u32(&halo_ready[hb]), (uint32_t)((g / HB) & 1));
-          else    mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g / HB) & 1));
+        for (int cc = 0; cc < e.cchunks; ++cc) {
+          if (X3) mbar_wait(smem_u32(&halo_ready[hb]), hphase);
+          else    mbar_wait(smem_u32(&halo_full[hb]), hphase);
           tc_fence_after();
-          const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE, h_lo = h_hi + (uint32_t)HB * T2_HALO_STRIDE;
-          for (int tap0 = 0; tap0 < e.ntaps; tap0 += e.tps, ++step) {
-            const int st = step % STAGES, round = step / STAGES;
-            mbar_wait(smem_u32(&b_full[st]), (uint32_t)(round & 1));
-            tc_fence_after();
-            for (int tt = 0; tt < e.tps; ++tt, ++kstep) {
-              const int tap = tap0 + tt;
-              const int r = tap / e.KW, s = tap - r * e.KW;
-              const uint32_t shift = (uint32_t)(r * e.halo_w + s) * 128u;
-              const uint64_t ah = halo_desc(h_hi + shift, sbo);
-              const uint32_t b_addr = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)tt * Cfg::B_TAP;
-              const uint64_t bh = umma_desc_sw128(b_addr);
+          const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE;
+          const uint64_t ah0 = halo_desc(h_hi, SBO);
+          const uint64_t al0 = halo_desc(h_hi + (uint32_t)HB * T2_HALO_STRIDE, SBO);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (kstep | k) ? 1u : 0u);
+          for (int tap0 = 0; tap0 < NTAPS; tap0 += TPS) {
+            mbar_wait(smem_u32(&b_full[st]), bphase);
+            tc_fence_after();
+            const uint32_t b_stage = b_ring + (uint32_t)st * Cfg::B_STAGE;
+#pragma unroll
+            for (int tt = 0; tt < TPS; ++tt) {
+              constexpr int dummy = 0; (void)dummy;
+              const int tap = tap0 + tt;
+              const uint32_t shift16 = (uint32_t)(((tap / KS) * HALO_W + tap % KS) * 128) >> 4;     // compile-time after unrolling
+              const uint64_t ah = ah0 + (uint64_t)shift16;
+              const uint64_t bh = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (cc | tap | k) ? 1u : 0u);
               if (X3) {
-                const uint64_t al = halo_desc(h_lo + shift, sbo), bl = umma_desc_sw128(b_addr + Cfg::B_TILE);
+                const uint64_t al = al0 + (uint64_t)shift16;
+                const uint64_t bl = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP + Cfg::B_TILE);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, 1u);
 #pragma unroll
@@ -199,8 +211,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               }
             }
             umma_commit(smem_u32(&b_empty[st]));
+            if (++st == STAGES) { st = 0; bphase ^= 1u; }
           }
           umma_commit(smem_u32(&halo_empty[hb]));               // all taps of this chunk have read the halo
+          if (++hb == HB) { hb = 0; hphase ^= 1u; }
         }
         umma_commit(smem_u32(&acc_full[ab]));
       }
@@ -326,15 +340,18 @@ int get_map2(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d
   return 0;
 }
 
-template <int NT, bool X3>
-int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, T2Args e, dim3 grid, cudaStream_t s) {
+template <int NT, bool X3, int KS>
+int launch2k(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
   using Cfg = T2Cfg<NT, X3>;
-  e.tps = (e.ntaps % Cfg::TPS == 0) ? Cfg::TPS : 1;
-  cudaError_t err = cudaFuncSetAttribute(conv_tc2_kernel<NT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  cudaError_t err = cudaFuncSetAttribute(conv_tc2_kernel<NT, X3, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (err != cudaSuccess) return (int)err;
-  conv_tc2_kernel<NT, X3><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, e);
+  conv_tc2_kernel<NT, X3, KS><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, e);
   DH_CHECK_LAUNCH();
   return 0;
+}
+template <int NT, bool X3>
+int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
+  return e.ntaps == 9 ? launch2k<NT, X3, 3>(A0, A1, Bm, e, grid, s) : launch2k<NT, X3, 1>(A0, A1, Bm, e, grid, s);
 }
 }  // namespace
 

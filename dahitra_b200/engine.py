@@ -33,6 +33,17 @@ MODES = {
     "tf32_fast": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC,   # 1xTF32 decoder too
 }
 
+# fp32-grade accuracy on arbitrary checkpoints at tensor-core speed; "fp32" is the strict CUDA-core mode
+DEFAULT_MODE = "tf32x3"
+
+
+def resolve_mode(mode):
+    if isinstance(mode, int):
+        return mode
+    if mode not in MODES:
+        raise ValueError(f"dahitra_b200: unknown precision mode {mode!r}; choose from {sorted(MODES)}")
+    return MODES[mode]
+
 
 def slot_names():
     lib = _lib.load()
@@ -272,8 +283,21 @@ class NativeEngine:
         self._prep = None
         self._prep_key = None
         self._ws = {}
-        self.flags = int(os.environ.get("DAHITRA_FLAGS", "0"))
+        # precision mode: DAHITRA_FLAGS (raw DH_FLAG_* bitmask) > DAHITRA_MODE (a MODES name) > DEFAULT_MODE
+        if "DAHITRA_FLAGS" in os.environ:
+            self.flags = int(os.environ["DAHITRA_FLAGS"])
+        else:
+            self.flags = resolve_mode(os.environ.get("DAHITRA_MODE", DEFAULT_MODE))
         self.last_argmax = None
+
+    def set_mode(self, mode):
+        """mode: a key of MODES or a raw DH_FLAG_* bitmask.  Prepared weights / workspaces are keyed by the flags,
+        so switching back and forth does not rebuild anything."""
+        self.flags = resolve_mode(mode)
+
+    @property
+    def mode(self):
+        return next((k for k, v in MODES.items() if v == self.flags), f"flags{self.flags}")
 
     def invalidate(self):
         self._prep = None

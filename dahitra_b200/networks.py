@@ -113,6 +113,13 @@ class BASE_Transformer_UNet(nn.Module):
         self.invalidate_native_cache()
         return super().load_state_dict(*a, **kw)
 
+    def set_mode(self, mode):
+        """Precision mode of the native inference path: 'tf32x3' (default: tensor cores, error-compensated,
+        fp32-grade), 'tf32' (what eager PyTorch does on this GPU by default), 'fp32' (strict, CUDA cores) — see
+        dahitra_b200.engine.MODES.  Also settable per process with DAHITRA_MODE."""
+        self._engine.set_mode(mode)
+        return self
+
     def pos_shapes(self, H, W):
         """positions each decoder positional-embedding slot must cover for an HxW input"""
         if self.with_decoder_pos != 'learned':

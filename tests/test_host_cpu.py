@@ -150,3 +150,22 @@ def test_prepared_weights_algebra_xbd():
     y = O.forward_xbd(sd, x, dtype=torch.float64)
     e = E.forward(P, x[:, :3].double(), x[:, 3:].double(), "xbd", 5)
     assert float((y - e).abs().max()) < 5e-5 * float(y.abs().max())
+
+
+def test_precision_mode_selection(monkeypatch):
+    """engine default = tf32x3; DAHITRA_MODE / DAHITRA_FLAGS / set_mode() override it; unknown names are rejected."""
+    from dahitra_b200 import engine as E
+    monkeypatch.delenv("DAHITRA_MODE", raising=False)
+    monkeypatch.delenv("DAHITRA_FLAGS", raising=False)
+    e = E.NativeEngine()
+    assert E.DEFAULT_MODE == "tf32x3" and e.mode == "tf32x3" and e.flags == E.MODES["tf32x3"]
+    e.set_mode("fp32")
+    assert e.flags == 0 and e.mode == "fp32"
+    e.set_mode(29)
+    assert e.mode == "tf32_fast"
+    with pytest.raises(ValueError):
+        e.set_mode("bf16")
+    monkeypatch.setenv("DAHITRA_MODE", "tf32")
+    assert E.NativeEngine().flags == E.MODES["tf32"]
+    monkeypatch.setenv("DAHITRA_FLAGS", "0")
+    assert E.NativeEngine().mode == "fp32"
