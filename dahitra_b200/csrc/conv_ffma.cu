@@ -303,62 +303,89 @@ int dh_launch_maxpool(const float* in, int N, int H, int W, int C, float* out, c
 
 // =====================================================================================================
 // Classifier: 3x3 pad 1 conv 32 -> NC (NC <= 8) + bias.  NHWC in, NCHW logits out (+ optional uint8
-// argmax map, ties -> lowest class index like torch.argmax).  CTA = 16x16 pixels, 18x18x32 halo in smem
-// with the pixel stride padded to 36 floats so 128-bit reads of neighbouring pixels do not conflict.
+// argmax map, ties -> lowest class index like torch.argmax).  HBM-bound by design (32 floats in, NC out per
+// pixel); the work is arranged so that shared-memory traffic stays below the FMA time:
+//   CTA = 32 x 16 pixels, 128 threads; thread (lx, g) owns the 4 vertically adjacent pixels (lx, 4g..4g+3), so each
+//   128-bit halo read feeds up to 3 output rows and each filter read feeds 4 pixels (5.6 smem wavefronts per pixel
+//   instead of 20).  The 18 x 34 halo is staged in two passes of 16 channels with a pixel pitch of 20 floats:
+//   consecutive pixels land 20 banks apart, so the 8 threads of a quarter-warp read 8 disjoint 16-byte bank groups.
 // =====================================================================================================
 namespace {
-constexpr int CL_T = 16, CL_HALO = CL_T + 2, CL_PS = 36;
+constexpr int CL_TW = 32, CL_TH = 16, CL_HW = CL_TW + 2, CL_HH = CL_TH + 2, CL_PS = 20, CL_CH = 16;
 
 template <int NC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 classifier_kernel(const float* __restrict__ in, int H, int W, int tilesX, const float* __restrict__ w,
                   const float* __restrict__ bias, float* __restrict__ logits, unsigned char* __restrict__ amax) {
   extern __shared__ __align__(16) float cl_sm[];
-  float* halo = cl_sm;                                   // [18*18][36]
-  float* w_s = cl_sm + CL_HALO * CL_HALO * CL_PS;        // [9][NC][32]
+  float* halo = cl_sm;                                   // [18*34][20]
+  float* w_s = cl_sm + CL_HH * CL_HW * CL_PS;            // [9][NC][32]
   const int tid = threadIdx.x, n = blockIdx.z;
-  const int y0 = (blockIdx.x / tilesX) * CL_T, x0 = (blockIdx.x % tilesX) * CL_T;
-  for (int i = tid; i < 9 * NC * 8; i += 256) reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
-  for (int i = tid; i < CL_HALO * CL_HALO * 8; i += 256) {
-    const int c4 = i & 7, p = i >> 3;
-    const int yy = p / CL_HALO, xx = p - yy * CL_HALO;
-    const int iy = y0 + yy - 1, ix = x0 + xx - 1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = ldg4(in + (((size_t)n * H + iy) * W + ix) * 32 + c4 * 4);
-    *reinterpret_cast<float4*>(&halo[p * CL_PS + c4 * 4]) = v;
-  }
-  __syncthreads();
-  const int ly = tid / CL_T, lx = tid % CL_T;
-  float acc[NC];
+  const int y0 = (blockIdx.x / tilesX) * CL_TH, x0 = (blockIdx.x % tilesX) * CL_TW;
+  for (int i = tid; i < 9 * NC * 8; i += 128) reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  const int lx = tid & 31, g = tid >> 5;
+  float acc[4][NC];
 #pragma unroll
-  for (int k = 0; k < NC; ++k) acc[k] = __ldg(bias + k);
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int r = tap / 3, s = tap % 3;
-    const float* hp = &halo[((ly + r) * CL_HALO + lx + s) * CL_PS];
+    for (int k = 0; k < NC; ++k) acc[j][k] = __ldg(bias + k);
+
+#pragma unroll 1
+  for (int pass = 0; pass < 32 / CL_CH; ++pass) {
+    if (pass) __syncthreads();                           // everyone is done reading the previous 16 channels
+    for (int i = tid; i < CL_HH * CL_HW * (CL_CH / 4); i += 128) {
+      const int c4 = i & 3, p = i >> 2;
+      const int yy = p / CL_HW, xx = p - yy * CL_HW;
+      const int iy = y0 + yy - 1, ix = x0 + xx - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = ldg4(in + (((size_t)n * H + iy) * W + ix) * 32 + pass * CL_CH + c4 * 4);
+      *reinterpret_cast<float4*>(&halo[p * CL_PS + c4 * 4]) = v;
+    }
+    __syncthreads();
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 v = *reinterpret_cast<const float4*>(hp + c4 * 4);
+    for (int s = 0; s < 3; ++s) {
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        const float4 ww = *reinterpret_cast<const float4*>(&w_s[(tap * NC + k) * 32 + c4 * 4]);
-        acc[k] = fmaf(v.x, ww.x, acc[k]);
-        acc[k] = fmaf(v.y, ww.y, acc[k]);
-        acc[k] = fmaf(v.z, ww.z, acc[k]);
-        acc[k] = fmaf(v.w, ww.w, acc[k]);
+      for (int c4 = 0; c4 < CL_CH / 4; ++c4) {
+        float4 ww[3][NC];                                // the three filter rows of column s for these 4 channels
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int k = 0; k < NC; ++k)
+            ww[r][k] = *reinterpret_cast<const float4*>(&w_s[((r * 3 + s) * NC + k) * 32 + pass * CL_CH + c4 * 4]);
+#pragma unroll
+        for (int hr = 0; hr < 6; ++hr) {                 // halo row 4g + hr feeds output rows j = hr - r, r = 0..2
+          const float4 v = *reinterpret_cast<const float4*>(&halo[((4 * g + hr) * CL_HW + lx + s) * CL_PS + c4 * 4]);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const int j = hr - r;
+            if (j < 0 || j > 3) continue;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+              acc[j][k] = fmaf(v.x, ww[r][k].x, acc[j][k]);
+              acc[j][k] = fmaf(v.y, ww[r][k].y, acc[j][k]);
+              acc[j][k] = fmaf(v.z, ww[r][k].z, acc[j][k]);
+              acc[j][k] = fmaf(v.w, ww[r][k].w, acc[j][k]);
+            }
+          }
+        }
       }
     }
   }
-  const int y = y0 + ly, x = x0 + lx;
-  if (y < H && x < W) {
-    int best = 0;
-    float bv = acc[0];
+  const int x = x0 + lx;
+  if (x < W) {
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      logits[(((size_t)n * NC + k) * H + y) * W + x] = acc[k];
-      if (k > 0 && acc[k] > bv) { bv = acc[k]; best = k; }
+    for (int j = 0; j < 4; ++j) {
+      const int y = y0 + 4 * g + j;
+      if (y >= H) break;
+      int best = 0;
+      float bv = acc[j][0];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        logits[(((size_t)n * NC + k) * H + y) * W + x] = acc[j][k];
+        if (k > 0 && acc[j][k] > bv) { bv = acc[j][k]; best = k; }
+      }
+      if (amax) amax[((size_t)n * H + y) * W + x] = (unsigned char)best;
     }
-    if (amax) amax[((size_t)n * H + y) * W + x] = (unsigned char)best;
   }
 }
 }  // namespace
@@ -368,14 +395,14 @@ int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const flo
   DH_REQUIRE(in && w && b && logits, DH_E_NULL);
   DH_REQUIRE(N > 0 && H > 0 && W > 0 && nc >= 1 && nc <= 8, DH_E_SHAPE);
   DH_REQUIRE(dh_aligned16(in) && dh_aligned16(w), DH_E_ALIGN);
-  const int tx = dh_cdiv(W, CL_T), ty = dh_cdiv(H, CL_T);
+  const int tx = dh_cdiv(W, CL_TW), ty = dh_cdiv(H, CL_TH);
   dim3 grid(tx * ty, 1, N);
 #define DH_CLS_CASE(NC)                                                                                   \
   case NC: {                                                                                              \
-    const int smem = (CL_HALO * CL_HALO * CL_PS + 9 * NC * 32) * (int)sizeof(float);                      \
+    const int smem = (CL_HH * CL_HW * CL_PS + 9 * NC * 32) * (int)sizeof(float);                          \
     cudaError_t e = cudaFuncSetAttribute(classifier_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
     if (e != cudaSuccess) return (int)e;                                                                  \
-    classifier_kernel<NC><<<grid, 256, smem, s>>>(in, H, W, tx, w, b, logits, amax);                      \
+    classifier_kernel<NC><<<grid, 128, smem, s>>>(in, H, W, tx, w, b, logits, amax);                      \
   } break;
   switch (nc) {
     DH_CLS_CASE(1) DH_CLS_CASE(2) DH_CLS_CASE(3) DH_CLS_CASE(4)
