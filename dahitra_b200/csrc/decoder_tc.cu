@@ -3,19 +3,21 @@
 // Same algebra as decoder.cu (collapsed cross-attention + MLP, reference models/help_funcs.py:66-114,170-186),
 // re-mapped so that the four 128x32x32 products of every layer run as tcgen05.mma and everything that is
 // per-pixel (LayerNorm statistics, the 4-key softmax per head, exact-erf GELU) is thread-local:
-//   * a CTA owns 128 pixels; thread t owns pixel t = TMEM lane t, so `tcgen05.ld.32x32b` hands each thread the
+//   * a warpgroup owns 128 pixels; thread t owns pixel t = TMEM lane t, so `tcgen05.ld.32x32b` hands each thread the
 //     32 channels of ITS pixel — no shuffles anywhere.
 //   * the running activation x lives in TMEM columns [0,32) for the whole call; attention and MLP outputs are
 //     accumulated INTO it by the MMA (x += P.Bv, x += G.W2).  Biases are pixel-independent, so they are applied
 //     as host-precomputed cumulative vectors when x is read back (no TMEM write-back).
-//   * A operands (xhat, P, xhat', G) are written by the threads into a 128-row K-major SWIZZLE_128B tile;
-//     B operands (per-image tables, shared MLP weights) arrive pre-swizzled from global memory through 1-D bulk
-//     copies (double-buffered, prefetched one layer ahead).
+//   * A operands (xhat, P, xhat', G) never touch shared memory: each thread writes its row with ONE
+//     `tcgen05.st.32x32b.x32` into TMEM columns [32,64) (TF32 hi) / [64,96) (lo) and the MMA reads A from tensor
+//     memory (`tcgen05.mma [d], [a], bdesc`).  No swizzled stores, no proxy fence, and the MMA's shared-memory
+//     traffic is only the 1 KB B slice per K step.  B operands (per-image tables, shared MLP weights) arrive
+//     pre-swizzled from global memory through 1-D bulk copies (double-buffered, prefetched one layer ahead).
 //   * X3 = true: error-compensated "3xTF32".  Every operand is split v = hi + lo with hi exactly representable
-//     in TF32 (A: cvt.rna on the fly, written to a second tile; B: split by the table kernel / on the host) and
-//     each product is issued as A_hi.B_hi + A_lo.B_hi + A_hi.B_lo — fp32-grade accuracy at 3x the (tiny) MMA cost.
-// Per layer: 4 x {write A row, fence.proxy.async, barrier, one thread issues the MMAs + commit, mbarrier wait,
-// tcgen05.ld}.  Several CTAs per SM overlap each other's serial chains.
+//     in TF32 (A: cvt.rna on the fly, written to the second column block; B: split by the table kernel / on the
+//     host) and each product is issued as A_hi.B_hi + A_lo.B_hi + A_hi.B_lo — fp32-grade accuracy.
+// Per layer: 4 x {tcgen05.st A row, barrier, one thread issues the MMAs + commit, mbarrier wait, tcgen05.ld}.
+// A CTA holds four warpgroups (4 x 128 TMEM columns = the whole tensor memory) whose serial chains overlap.
 #include "tc_common.cuh"
 
 using namespace dhtc;
@@ -118,25 +120,25 @@ decoder_tables_tc_kernel(const float* __restrict__ mem, int B, int first_call, c
 // decoder
 // ----------------------------------------------------------------------------------------------------
 constexpr int PDT_ROWS = 128;
-constexpr uint32_t PDT_A_BYTES = 128 * 128;                 // one A tile
 constexpr uint32_t PDT_TAB_HI = 2080 * 4;                   // TA_hi | TB_hi | cA
 constexpr uint32_t PDT_MLP_HI = 2144 * 4;                   // W1_hi | W2_hi | b1f | cbA | cbM
 constexpr uint32_t PDT_LO = 2048 * 4;                       // two 32x32 lo tiles
 constexpr uint32_t PDT_HI_STRIDE = 9216;                    // 1024-aligned room for a hi block
+constexpr int PDT_G = 4;                                    // warpgroups (tiles) per CTA
+constexpr uint32_t PDT_WG_COLS = 128;                       // TMEM columns per warpgroup: x | A_hi | A_lo | D
+constexpr uint32_t TM_X = 0, TM_A = 32, TM_AL = 64, TM_D = 96;
 
-// A CTA holds G warpgroups; each owns one 128-pixel tile (its A tile(s), 96 TMEM columns, its own MMA barrier) of the
-// SAME image, so all of them share the per-layer table / MLP buffers.  G independent serial chains per CTA are what
-// hides the write-A -> MMA -> tcgen05.ld latency of each chain.
+// A CTA holds G warpgroups; each owns one 128-pixel tile (128 TMEM columns, its own MMA barrier) of the SAME image,
+// so all of them share the per-layer table / MLP buffers.  G independent serial chains per CTA are what hides the
+// st-A -> MMA -> tcgen05.ld latency of each chain.
 template <bool X3> struct PdtCfg {
-  static constexpr int G = 4;
+  static constexpr int G = PDT_G;
   static constexpr uint32_t BUF = PDT_HI_STRIDE + (X3 ? PDT_LO : 0);            // one table (or MLP) buffer
-  static constexpr uint32_t A_TILES = X3 ? 2 : 1;                               // per warpgroup
-  static constexpr uint32_t SMEM = G * A_TILES * PDT_A_BYTES + 4 * BUF + 1024;
-  static constexpr int CTAS = X3 ? 1 : 2;
+  static constexpr uint32_t SMEM = 4 * BUF + 1024;
 };
 
 template <int HEADS, bool X3>
-__global__ void __launch_bounds__(PDT_ROWS * PdtCfg<X3>::G, PdtCfg<X3>::CTAS)
+__global__ void __launch_bounds__(PDT_ROWS * PdtCfg<X3>::G, 1)
 pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const float* __restrict__ tables,
                         const float* __restrict__ pack, int npix, int w, int depth, const float* __restrict__ skip,
                         int skip_up, float* __restrict__ out) {
@@ -155,11 +157,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   const bool valid = p < npix;
   const uint32_t base = (smem_u32(pdt_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = pdt_raw + (base - smem_u32(pdt_raw));
-  const uint32_t a_off = (uint32_t)wg * Cfg::A_TILES * PDT_A_BYTES;
-  float* a_hi = reinterpret_cast<float*>(base_ptr + a_off);
-  float* a_lo = reinterpret_cast<float*>(base_ptr + a_off + PDT_A_BYTES);       // X3 only
-  const uint32_t a_addr = base + a_off;
-  constexpr uint32_t BUFS0 = G * Cfg::A_TILES * PDT_A_BYTES;
+  constexpr uint32_t BUFS0 = 0;
   auto tab_addr = [&](int b) { return base + BUFS0 + (uint32_t)b * Cfg::BUF; };
   auto mlp_addr = [&](int b) { return base + BUFS0 + 2 * Cfg::BUF + (uint32_t)b * Cfg::BUF; };
   auto tab_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + BUFS0 + (size_t)b * Cfg::BUF); };
@@ -170,13 +168,12 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     for (int i = 0; i < G; ++i) mbar_init(smem_u32(&mma_bar[i]), 1);
     mbar_fence_init();
   }
-  if (threadIdx.x < 32) tmem_alloc(smem_u32(&tmem_slot), 512);          // G x 96 columns (power of two: 512)
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(&tmem_slot), 512);          // G x 128 columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_wg = tmem_slot + (uint32_t)wg * 96;               // this warpgroup's columns
+  const uint32_t tmem_wg = tmem_slot + (uint32_t)wg * PDT_WG_COLS;      // this warpgroup's columns
   const uint32_t tmem = tmem_wg + ((uint32_t)(warp * 32) << 16);       // ... and this warp's lane quarter
-  const uint32_t TM_X = 0, TM_S = 32, TM_H = 64;
   const uint32_t my_bar = smem_u32(&mma_bar[wg]);
 
   auto issue_loads = [&](int layer) {
@@ -222,33 +219,34 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     tmem_st32(tmem + TM_X, u);
   }
 
-  // this thread's row of the A operand: TF32-rounded values (hi tile) and, for X3, the remainders (lo tile)
+  // this thread's row of the A operand -> tensor memory: TF32-rounded values and, for X3, the remainders
   auto write_a_row = [&](const float (&v)[32]) {
+    uint32_t hi[32];
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      const int o = tid * 32 + ((ch ^ (tid & 7)) << 2);
-      const float h0 = tf32_hi(v[ch * 4]), h1 = tf32_hi(v[ch * 4 + 1]), h2 = tf32_hi(v[ch * 4 + 2]), h3 = tf32_hi(v[ch * 4 + 3]);
-      *reinterpret_cast<float4*>(a_hi + o) = make_float4(h0, h1, h2, h3);
-      if (X3) *reinterpret_cast<float4*>(a_lo + o) = make_float4(v[ch * 4] - h0, v[ch * 4 + 1] - h1, v[ch * 4 + 2] - h2, v[ch * 4 + 3] - h3);
+    for (int c = 0; c < 32; ++c) hi[c] = __float_as_uint(tf32_hi(v[c]));
+    tmem_st32(tmem + TM_A, hi);
+    if (X3) {
+      uint32_t lo[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) lo[c] = __float_as_uint(v[c] - __uint_as_float(hi[c]));
+      tmem_st32(tmem + TM_AL, lo);
     }
   };
 
   uint32_t mma_phase = 0;
-  // one MMA round: all rows of the A tile(s) are written -> thread 0 issues `nk` K-steps -> everyone waits for the commit.
-  // b_hi_addr: hi tile of the B operand; its lo twin sits PDT_HI_STRIDE-relative at the same offset inside the lo block.
+  // one MMA round: all rows of the A block(s) are in TMEM -> thread 0 issues `nk` K-steps -> everyone waits for the commit.
   auto mma_round = [&](uint32_t b_hi_addr, uint32_t b_lo_addr, uint32_t idesc, uint32_t tm_col, int nk, bool accumulate) {
-    fence_async_smem();
     tc_fence_before();
     asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");         // this warpgroup's rows are all written
     if (tid == 0) {
       tc_fence_after();
-      const uint64_t ah = umma_desc_sw128(a_addr), bh = umma_desc_sw128(b_hi_addr);
-      const uint32_t d = tmem_wg + tm_col;
-      for (int k = 0; k < nk; ++k) umma_tf32(d, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, (accumulate || k) ? 1u : 0u);
+      const uint64_t bh = umma_desc_sw128(b_hi_addr);
+      const uint32_t d = tmem_wg + tm_col, ah = tmem_wg + TM_A, al = tmem_wg + TM_AL;
+      for (int k = 0; k < nk; ++k) umma_tf32_ts(d, ah + 8u * k, bh + (uint64_t)(2 * k), idesc, (accumulate || k) ? 1u : 0u);
       if (X3) {
-        const uint64_t al = umma_desc_sw128(a_addr + PDT_A_BYTES), bl = umma_desc_sw128(b_lo_addr);
-        for (int k = 0; k < nk; ++k) umma_tf32(d, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), idesc, 1u);
-        for (int k = 0; k < nk; ++k) umma_tf32(d, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), idesc, 1u);
+        const uint64_t bl = umma_desc_sw128(b_lo_addr);
+        for (int k = 0; k < nk; ++k) umma_tf32_ts(d, al + 8u * k, bh + (uint64_t)(2 * k), idesc, 1u);
+        for (int k = 0; k < nk; ++k) umma_tf32_ts(d, ah + 8u * k, bl + (uint64_t)(2 * k), idesc, 1u);
       }
       umma_commit(my_bar);
     }
@@ -284,17 +282,17 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
       write_a_row(t);
     }
-        mma_round(t_hi, t_lo, IDESC_S, TM_S, 4, false);
+        mma_round(t_hi, t_lo, IDESC_S, TM_D, 4, false);
     // ---- 2. P = softmax_j(S + cA) ; x += P . TB^T
     {
       if constexpr (HEADS == 8) {
         uint32_t u[32];
-        tmem_ld32(tmem + TM_S, u);
+        tmem_ld32(tmem + TM_D, u);
 #pragma unroll
         for (int c = 0; c < 32; ++c) t[c] = __uint_as_float(u[c]) + cA[c];
       } else {
         uint32_t u[16];
-        tmem_ld16(tmem + TM_S, u);
+        tmem_ld16(tmem + TM_D, u);
 #pragma unroll
         for (int c = 0; c < 16; ++c) t[c] = __uint_as_float(u[c]) + cA[c];
 #pragma unroll
@@ -327,11 +325,11 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
       write_a_row(t);
     }
-    mma_round(m_hi, m_lo, IDESC_32, TM_H, 4, false);
+    mma_round(m_hi, m_lo, IDESC_32, TM_D, 4, false);
     // ---- 4. x += gelu(Hid + b1f) . W2^T
     {
       uint32_t u[32];
-      tmem_ld32(tmem + TM_H, u);
+      tmem_ld32(tmem + TM_D, u);
 #pragma unroll
       for (int c = 0; c < 32; ++c) t[c] = gelu_phi8(__uint_as_float(u[c]) + b1f[c]);
       write_a_row(t);
