@@ -60,11 +60,7 @@ template <int NT, bool X3> struct T2Cfg {
   static constexpr uint32_t TMEM_COLS = (2 * NT < 32) ? 32 : 2 * NT;   // two accumulators
 };
 
-__device__ __forceinline__ float tf32_rna(float v) {        // nearest TF32-representable value
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
-}
+__device__ __forceinline__ float tf32_rna(float v) { return tf32_round(v); }
 
 // shifted-window A descriptor: start = halo + (r*halo_w + s) pixels, SBO = halo_w pixels
 __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes) {

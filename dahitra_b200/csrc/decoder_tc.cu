@@ -19,16 +19,13 @@
 // Per layer: 4 x {tcgen05.st A row, barrier, one thread issues the MMAs + commit, mbarrier wait, tcgen05.ld}.
 // A CTA holds four warpgroups (4 x 128 TMEM columns = the whole tensor memory) whose serial chains overlap.
 #include "tc_common.cuh"
+#include <type_traits>
 
 using namespace dhtc;
 
 namespace {
 
-__device__ __forceinline__ float tf32_hi(float v) {          // nearest TF32-representable value (low 13 bits zero)
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
-}
+__device__ __forceinline__ float tf32_hi(float v) { return tf32_round(v); }
 
 __device__ __forceinline__ float ex2_approx(float x) {      // MUFU.EX2, relative error <= 2^-22
   float y;
@@ -125,6 +122,9 @@ constexpr uint32_t PDT_MLP_HI = 2144 * 4;                   // W1_hi | W2_hi | b
 constexpr uint32_t PDT_LO = 2048 * 4;                       // two 32x32 lo tiles
 constexpr uint32_t PDT_HI_STRIDE = 9216;                    // 1024-aligned room for a hi block
 constexpr int PDT_G = 4;                                    // warpgroups (tiles) per CTA
+#ifndef PDT_TURN_D
+#define PDT_TURN_D 2
+#endif
 constexpr uint32_t PDT_WG_COLS = 128;                       // TMEM columns per warpgroup: x | A_hi | A_lo | D
 constexpr uint32_t TM_X = 0, TM_A = 32, TM_AL = 64, TM_D = 96;
 
@@ -134,7 +134,8 @@ constexpr uint32_t TM_X = 0, TM_A = 32, TM_AL = 64, TM_D = 96;
 template <bool X3> struct PdtCfg {
   static constexpr int G = PDT_G;
   static constexpr uint32_t BUF = PDT_HI_STRIDE + (X3 ? PDT_LO : 0);            // one table (or MLP) buffer
-  static constexpr uint32_t SMEM = 4 * BUF + 1024;
+  static constexpr int NB = 3;                                                  // table / MLP buffers (layers in flight)
+  static constexpr uint32_t SMEM = 2 * NB * BUF + 1024;
 };
 
 template <int HEADS, bool X3>
@@ -148,7 +149,8 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   constexpr uint32_t IDESC_32 = umma_idesc_tf32(128, 32);
   extern __shared__ uint8_t pdt_raw[];
   constexpr int G = Cfg::G;
-  __shared__ __align__(8) uint64_t tab_bar[2], mma_bar[G];
+  constexpr int NB = Cfg::NB;
+  __shared__ __align__(8) uint64_t tab_bar[NB], free_bar[NB], mma_bar[G];
   __shared__ uint32_t tmem_slot;
 
   const int wg = threadIdx.x >> 7;                                      // warpgroup = tile within the CTA
@@ -159,12 +161,12 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   uint8_t* base_ptr = pdt_raw + (base - smem_u32(pdt_raw));
   constexpr uint32_t BUFS0 = 0;
   auto tab_addr = [&](int b) { return base + BUFS0 + (uint32_t)b * Cfg::BUF; };
-  auto mlp_addr = [&](int b) { return base + BUFS0 + 2 * Cfg::BUF + (uint32_t)b * Cfg::BUF; };
+  auto mlp_addr = [&](int b) { return base + BUFS0 + NB * Cfg::BUF + (uint32_t)b * Cfg::BUF; };
   auto tab_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + BUFS0 + (size_t)b * Cfg::BUF); };
-  auto mlp_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + BUFS0 + 2 * Cfg::BUF + (size_t)b * Cfg::BUF); };
+  auto mlp_ptr = [&](int b) { return reinterpret_cast<const float*>(base_ptr + BUFS0 + NB * Cfg::BUF + (size_t)b * Cfg::BUF); };
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&tab_bar[0]), 1); mbar_init(smem_u32(&tab_bar[1]), 1);
+    for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&tab_bar[i]), 1); mbar_init(smem_u32(&free_bar[i]), G); }
     for (int i = 0; i < G; ++i) mbar_init(smem_u32(&mma_bar[i]), 1);
     mbar_fence_init();
   }
@@ -177,7 +179,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   const uint32_t my_bar = smem_u32(&mma_bar[wg]);
 
   auto issue_loads = [&](int layer) {
-    const int b = layer & 1;
+    const int b = layer % NB;
     const uint32_t bar = smem_u32(&tab_bar[b]);
     const float* tg = tables + ((size_t)img * depth + layer) * DH_TABTC_FLOATS;
     const float* pg = pack + (size_t)layer * DH_DECTC_LAYER_FLOATS;
@@ -189,7 +191,20 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       bulk_load_1d(mlp_addr(b) + PDT_HI_STRIDE, pg + 2144, PDT_LO, bar);
     }
   };
-  if (threadIdx.x == 0) issue_loads(0);
+  if (threadIdx.x == 0) {
+    issue_loads(0);
+    if (depth > 1) issue_loads(1);
+  }
+  // the MMA-issuing thread of warpgroup g sits in its warp g, so the four issuers run on four different schedulers
+  const bool issuer = (tid == 32 * wg);
+  // ALU turn-taking (named barriers 5..8, 128 arriving + 128 waiting threads): identical warpgroups otherwise run in
+  // lockstep — all in their ALU phase, then all waiting on the tensor pipe, then all on the TMEM read port — and the
+  // phases add up instead of overlapping.  Warpgroup g may enter an ALU phase only after warpgroup g-TURN_D has left
+  // its own; the rest of its chain (tcgen05.st drain, MMAs, commit, tcgen05.ld) runs while others hold the ALUs.
+  constexpr int TURN_D = PDT_TURN_D;
+  auto turn_wait = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(5 + wg) : "memory"); };
+  auto turn_pass = [&]() { asm volatile("bar.arrive %0, 256;" ::"r"(5 + ((wg + TURN_D) & 3)) : "memory"); };
+  if (wg >= G - TURN_D) turn_pass();                                   // the first TURN_D warpgroups start immediately
 
   // ---- x (+ pos) -> registers and TMEM
   float xr[32];
@@ -235,17 +250,21 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
 
   uint32_t mma_phase = 0;
   // one MMA round: all rows of the A block(s) are in TMEM -> thread 0 issues `nk` K-steps -> everyone waits for the commit.
-  auto mma_round = [&](uint32_t b_hi_addr, uint32_t b_lo_addr, uint32_t idesc, uint32_t tm_col, int nk, bool accumulate) {
+  auto mma_round = [&](uint32_t b_hi_addr, uint32_t b_lo_addr, uint32_t idesc, uint32_t tm_col, auto nk_c, bool accumulate) {
+    constexpr int nk = decltype(nk_c)::value;
     tc_fence_before();
     asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");         // this warpgroup's rows are all written
-    if (tid == 0) {
+    if (issuer) {
       tc_fence_after();
       const uint64_t bh = umma_desc_sw128(b_hi_addr);
       const uint32_t d = tmem_wg + tm_col, ah = tmem_wg + TM_A, al = tmem_wg + TM_AL;
+#pragma unroll
       for (int k = 0; k < nk; ++k) umma_tf32_ts(d, ah + 8u * k, bh + (uint64_t)(2 * k), idesc, (accumulate || k) ? 1u : 0u);
       if (X3) {
         const uint64_t bl = umma_desc_sw128(b_lo_addr);
+#pragma unroll
         for (int k = 0; k < nk; ++k) umma_tf32_ts(d, al + 8u * k, bh + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
         for (int k = 0; k < nk; ++k) umma_tf32_ts(d, ah + 8u * k, bl + (uint64_t)(2 * k), idesc, 1u);
       }
       umma_commit(my_bar);
@@ -254,13 +273,18 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     mma_phase ^= 1u;
     tc_fence_after();
   };
+  using K4 = std::integral_constant<int, 4>;
+  using KP = std::integral_constant<int, H4 / 8>;
 
   for (int layer = 0; layer < depth; ++layer) {
-    const int b = layer & 1;
-    // every warpgroup has finished layer-1 (the last reader of buffer (layer+1)&1): prefetch the next layer's tables
-    __syncthreads();
-    if (threadIdx.x == 0 && layer + 1 < depth) issue_loads(layer + 1);
-    mbar_wait(smem_u32(&tab_bar[b]), (uint32_t)((layer >> 1) & 1));
+    const int b = layer % NB;
+    // prefetch layer+2 into the buffer layer-1 used, once EVERY warpgroup has released it (free_bar counts G arrivals);
+    // the warpgroups are otherwise free to drift apart by up to two layers, which is what staggers their chains
+    if (threadIdx.x == 0 && layer + 2 < depth) {
+      if (layer >= 1) mbar_wait(smem_u32(&free_bar[(layer + 2) % NB]), (uint32_t)(((layer - 1) / NB) & 1));
+      issue_loads(layer + 2);
+    }
+    mbar_wait(smem_u32(&tab_bar[b]), (uint32_t)((layer / NB) & 1));
     const float* tabp = tab_ptr(b);
     const float* mlpp = mlp_ptr(b);
     const float* cA = tabp + 2048;
@@ -270,6 +294,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     float t[32];
     // ---- 1. S = xhat . TA^T
     {
+      turn_wait();
       float mu = 0.f;
 #pragma unroll
       for (int c = 0; c < 32; ++c) mu += xr[c];
@@ -281,8 +306,9 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
 #pragma unroll
       for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
       write_a_row(t);
+      turn_pass();
     }
-        mma_round(t_hi, t_lo, IDESC_S, TM_D, 4, false);
+    mma_round(t_hi, t_lo, IDESC_S, TM_D, K4{}, false);
     // ---- 2. P = softmax_j(S + cA) ; x += P . TB^T
     {
       if constexpr (HEADS == 8) {
@@ -298,6 +324,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
 #pragma unroll
         for (int c = 16; c < 32; ++c) t[c] = 0.f;
       }
+      turn_wait();
 #pragma unroll
       for (int h = 0; h < HEADS; ++h) {
         const float mx = fmaxf(fmaxf(t[h * 4], t[h * 4 + 1]), fmaxf(t[h * 4 + 2], t[h * 4 + 3]));
@@ -307,12 +334,14 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
         t[h * 4] = e0 * inv; t[h * 4 + 1] = e1 * inv; t[h * 4 + 2] = e2 * inv; t[h * 4 + 3] = e3 * inv;
       }
       write_a_row(t);
+      turn_pass();
     }
-    mma_round(t_hi + 4096, t_lo + 4096, IDESC_32, TM_X, H4 / 8, true);
+    mma_round(t_hi + 4096, t_lo + 4096, IDESC_32, TM_X, KP{}, true);
     // ---- 3. Hid = xhat' . W1f^T
     {
       uint32_t u[32];
       tmem_ld32(tmem + TM_X, u);
+      turn_wait();
       float mu = 0.f;
 #pragma unroll
       for (int c = 0; c < 32; ++c) { xr[c] = __uint_as_float(u[c]) + cbA[c]; mu += xr[c]; }
@@ -324,23 +353,29 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
 #pragma unroll
       for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
       write_a_row(t);
+      turn_pass();
     }
-    mma_round(m_hi, m_lo, IDESC_32, TM_D, 4, false);
+    mma_round(m_hi, m_lo, IDESC_32, TM_D, K4{}, false);
     // ---- 4. x += gelu(Hid + b1f) . W2^T
     {
       uint32_t u[32];
       tmem_ld32(tmem + TM_D, u);
+      turn_wait();
 #pragma unroll
       for (int c = 0; c < 32; ++c) t[c] = gelu_phi8(__uint_as_float(u[c]) + b1f[c]);
       write_a_row(t);
+      turn_pass();
     }
-    mma_round(m_hi + 4096, m_lo + 4096, IDESC_32, TM_X, 4, true);
+    mma_round(m_hi + 4096, m_lo + 4096, IDESC_32, TM_X, K4{}, true);
     {
       uint32_t u[32];
       tmem_ld32(tmem + TM_X, u);
 #pragma unroll
       for (int c = 0; c < 32; ++c) xr[c] = __uint_as_float(u[c]) + cbM[c];
     }
+    // this warpgroup is done with buffer b (its MMAs completed, its bias reads are in registers)
+    asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+    if (issuer) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&free_bar[b])) : "memory");
   }
 
   if (valid) {

@@ -38,11 +38,7 @@ template <bool X3> struct SkCfg {
   static constexpr uint32_t SMEM = OFF_K + 160 * 4 + 1024;
 };
 
-__device__ __forceinline__ float sk_tf32(float v) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
-}
+__device__ __forceinline__ float sk_tf32(float v) { return tf32_round(v); }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const float* src, bool valid) {
   const uint32_t n = valid ? 4u : 0u;                              // src-size 0 => the 4 destination bytes are zero-filled
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");

@@ -20,13 +20,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done, spins = 0;
   do {
+    // the suspend-time hint (ns) lets the thread sleep inside try_wait instead of burning issue slots in this loop
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done && ++spins > (1u << 24)) __trap();
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(10000u) : "memory");
+    if (!done && ++spins > (1u << 19)) __trap();
   } while (!done);
+}
+// nearest TF32-representable value, ties away from zero — what cvt.rna.tf32.f32 returns for finite inputs, in two
+// integer instructions (the cvt is emulated with four on sm_100a)
+__device__ __forceinline__ float tf32_round(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
