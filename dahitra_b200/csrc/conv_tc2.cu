@@ -17,6 +17,11 @@
 // each K step issues A_hi.B_hi + A_lo.B_hi + A_hi.B_lo.  The split costs one smem pass per chunk, amortised
 // over 9 taps.
 //
+// Stride 2 (SD = 2; resnet layer2.0): the input is read as its four 2x2 phase images P_ab(y,x) = X(2y+a, 2x+b),
+// each fetched by a TMA box with elementStrides {1,2,2,1}.  A 3x3 stride-2 tap (r,s) is the stride-1 tap of phase
+// (r odd ? 0 : 1, s odd ? 0 : 1) at offset (r == 0 ? -1 : 0, s == 0 ? -1 : 0), so every (chunk, phase) pair is one
+// 18x10 halo serving 1, 2, 2 or 4 taps through the same shifted-window descriptors.
+//
 // Persistent CTAs (one per SM) walk the tile list; two TMEM accumulators let the epilogue of tile i overlap the
 // main loop of tile i+1.  Warp roles: 0 = halo TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue,
 // 6 = filter TMA producer, 7..10 = splitter (X3 only).
@@ -30,14 +35,13 @@ namespace {
 
 constexpr int T2_TH = 16, T2_TW = 8;                    // output patch
 constexpr int T2_HW = T2_TW + 2, T2_HH = T2_TH + 2;     // halo 10 x 18
-constexpr uint32_t T2_HALO_BYTES = T2_HW * T2_HH * 128; // 23040
 constexpr uint32_t T2_HALO_STRIDE = 23552;              // 1024-aligned
 
 struct T2Args {
   const float* bias; const float* res; float* out;
   int OH, OW, Cout, relu, tilesX, cchunks0, cchunks, ntaps, KW, Cin, ps;
   int halo_w, halo_h;        // 10 x 18 (3x3) or 8 x 16 (1x1)
-  int tps;                   // filter taps per ring stage (<= Cfg::TPS; 1 for 1x1 convs)
+  int stride;                // 1 or 2
   int tilesY, ncout_tiles, ntiles;
   uint32_t halo_bytes;
 };
@@ -68,6 +72,23 @@ __device__ __forceinline__ uint64_t halo_desc(uint32_t addr, uint32_t sbo_bytes)
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+// Order in which the nine 3x3 taps are consumed and the halo-pixel shift of each.
+//   stride 1: one halo per chunk, taps 0..8, shift (r, s)
+//   stride 2: four halos per chunk (phase = 2a + b), taps grouped by phase, shift (r != 0, s != 0)
+template <int KS, int SD> struct TapSched {
+  static constexpr int NPH = (KS == 3 && SD == 2) ? 4 : 1;
+  static constexpr int NTAPS = KS * KS;
+  __host__ __device__ static constexpr int tap(int i) {
+    return (KS == 3 && SD == 2) ? (int)((0x862071534ULL >> (4 * i)) & 0xF) : i;   // {4, 3,5, 1,7, 0,2,6,8}, nibble-packed
+  }
+  __host__ __device__ static constexpr int first(int ph) {           // index of the first tap of phase ph (first(NPH) = NTAPS)
+    return (KS == 3 && SD == 2) ? (int)((0x95310u >> (4 * ph)) & 0xF) : (ph == 0 ? 0 : NTAPS);   // {0, 1, 3, 5, 9}
+  }
+  __host__ __device__ static constexpr int shift_px(int t, int halo_w) {
+    return KS == 1 ? 0 : (SD == 2 ? ((t / 3 != 0) ? halo_w : 0) + ((t % 3 != 0) ? 1 : 0) : (t / 3) * halo_w + t % 3);
+  }
+};
+
 struct TileCoord { int n, oy0, ox0, n0; };
 __device__ __forceinline__ TileCoord tile_coord(int tile, const T2Args& e, int NT) {
   TileCoord t;
@@ -78,7 +99,7 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, const T2Args& e, int N
   return t;
 }
 
-template <int NT, bool X3, int KS>
+template <int NT, bool X3, int KS, int SD>
 __global__ void __launch_bounds__(T2Cfg<NT, X3>::THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const T2Args e) {
@@ -95,6 +116,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint8_t* base_ptr = t2_raw + (base - smem_u32(t2_raw));
   const uint32_t b_ring = base + Cfg::HALO_BUFS * T2_HALO_STRIDE;
   constexpr int pad = (KS == 3) ? 1 : 0;
+  using Sched = TapSched<KS, SD>;
+  constexpr int NPH = Sched::NPH;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < HB; ++i) {
@@ -125,26 +148,33 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       int g = 0;
       for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
         const TileCoord t = tile_coord(tile, e, NT);
-        for (int cc = 0; cc < e.cchunks; ++cc, ++g) {
-          const int hb = g % HB, use = g / HB;
-          mbar_wait(smem_u32(&halo_empty[hb]), (uint32_t)((use & 1) ^ 1));
-          const uint32_t bar = smem_u32(&halo_full[hb]);
-          mbar_expect_tx(bar, e.halo_bytes);
-          const uint32_t dst = base + (uint32_t)hb * T2_HALO_STRIDE;
-          if (cc < e.cchunks0) tma_load_4d(dst, &tmA0, bar, cc * 32, t.ox0 - pad, t.oy0 - pad, t.n);
-          else                 tma_load_4d(dst, &tmA1, bar, (cc - e.cchunks0) * 32, t.ox0 - pad, t.oy0 - pad, t.n);
+        for (int cc = 0; cc < e.cchunks; ++cc) {
+#pragma unroll
+          for (int ph = 0; ph < NPH; ++ph, ++g) {
+            const int hb = g % HB, use = g / HB;
+            mbar_wait(smem_u32(&halo_empty[hb]), (uint32_t)((use & 1) ^ 1));
+            const uint32_t bar = smem_u32(&halo_full[hb]);
+            mbar_expect_tx(bar, e.halo_bytes);
+            const uint32_t dst = base + (uint32_t)hb * T2_HALO_STRIDE;
+            // input coordinates of the halo origin (stride 2: origin of phase (ph>>1, ph&1), in full-resolution pixels)
+            const int cx = SD == 1 ? t.ox0 - pad : 2 * (t.ox0 - pad) + (ph & 1);
+            const int cy = SD == 1 ? t.oy0 - pad : 2 * (t.oy0 - pad) + (ph >> 1);
+            if (cc < e.cchunks0) tma_load_4d(dst, &tmA0, bar, cc * 32, cx, cy, t.n);
+            else                 tma_load_4d(dst, &tmA1, bar, (cc - e.cchunks0) * 32, cx, cy, t.n);
+          }
         }
       }
     }
   } else if (warp == 6) {
     if (lane == 0) {                                            // ---------------- filter TMA producer
       constexpr int NTAPS_ = KS * KS;
-      constexpr int TPS_ = (NTAPS_ % Cfg::TPS == 0) ? Cfg::TPS : 1;
+      constexpr int TPS_ = (SD == 1 && NTAPS_ % Cfg::TPS == 0) ? Cfg::TPS : 1;
       int step = 0;
       for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
         const TileCoord t = tile_coord(tile, e, NT);
         for (int cc = 0; cc < e.cchunks; ++cc) {
-          for (int tap0 = 0; tap0 < NTAPS_; tap0 += TPS_, ++step) {        // one ring stage = TPS_ filter taps
+#pragma unroll
+          for (int i0 = 0; i0 < NTAPS_; i0 += TPS_, ++step) {              // one ring stage = TPS_ filter taps, in schedule order
             const int st = step % STAGES, round = step / STAGES;
             mbar_wait(smem_u32(&b_empty[st]), (uint32_t)((round & 1) ^ 1));
             const uint32_t bar = smem_u32(&b_full[st]);
@@ -152,7 +182,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
             for (int tt = 0; tt < TPS_; ++tt) {
               const uint32_t dst = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)tt * Cfg::B_TAP;
-              const int kcol = (tap0 + tt) * e.Cin + cc * 32;
+              const int kcol = Sched::tap(i0 + tt) * e.Cin + cc * 32;
               tma_load_2d(dst, &tmB, bar, kcol, t.n0);
               if (X3) tma_load_2d(dst + Cfg::B_TILE, &tmB, bar, kcol, e.Cout + t.n0);    // lo rows follow the hi rows
             }
@@ -166,7 +196,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       // compile-time (tap shifts, taps per stage) or a wrapping counter — no divisions, no runtime tap arithmetic.
       constexpr int NTAPS = KS * KS;
       constexpr int HALO_W = (KS == 3) ? T2_HW : T2_TW;
-      constexpr int TPS = (NTAPS % Cfg::TPS == 0) ? Cfg::TPS : 1;
+      constexpr int TPS = (SD == 1 && NTAPS % Cfg::TPS == 0) ? Cfg::TPS : 1;
       constexpr uint32_t SBO = (uint32_t)HALO_W * 128u;
       int hb = 0, st = 0;
       uint32_t hphase = 0, bphase = 0;
@@ -177,40 +207,42 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)ab * NT;
         for (int cc = 0; cc < e.cchunks; ++cc) {
-          if (X3) mbar_wait(smem_u32(&halo_ready[hb]), hphase);
-          else    mbar_wait(smem_u32(&halo_full[hb]), hphase);
-          tc_fence_after();
-          const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE;
-          const uint64_t ah0 = halo_desc(h_hi, SBO);
-          const uint64_t al0 = halo_desc(h_hi + (uint32_t)HB * T2_HALO_STRIDE, SBO);
 #pragma unroll
-          for (int tap0 = 0; tap0 < NTAPS; tap0 += TPS) {
-            mbar_wait(smem_u32(&b_full[st]), bphase);
+          for (int ph = 0; ph < NPH; ++ph) {
+            if (X3) mbar_wait(smem_u32(&halo_ready[hb]), hphase);
+            else    mbar_wait(smem_u32(&halo_full[hb]), hphase);
             tc_fence_after();
-            const uint32_t b_stage = b_ring + (uint32_t)st * Cfg::B_STAGE;
+            const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE;
+            const uint64_t ah0 = halo_desc(h_hi, SBO);
+            const uint64_t al0 = halo_desc(h_hi + (uint32_t)HB * T2_HALO_STRIDE, SBO);
 #pragma unroll
-            for (int tt = 0; tt < TPS; ++tt) {
-              constexpr int dummy = 0; (void)dummy;
-              const int tap = tap0 + tt;
-              const uint32_t shift16 = (uint32_t)(((tap / KS) * HALO_W + tap % KS) * 128) >> 4;     // compile-time after unrolling
-              const uint64_t ah = ah0 + (uint64_t)shift16;
-              const uint64_t bh = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP);
+            for (int i0 = Sched::first(ph); i0 < Sched::first(ph + 1); i0 += TPS) {
+              mbar_wait(smem_u32(&b_full[st]), bphase);
+              tc_fence_after();
+              const uint32_t b_stage = b_ring + (uint32_t)st * Cfg::B_STAGE;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (cc | tap | k) ? 1u : 0u);
-              if (X3) {
-                const uint64_t al = al0 + (uint64_t)shift16;
-                const uint64_t bl = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP + Cfg::B_TILE);
+              for (int tt = 0; tt < TPS; ++tt) {
+                const int i = i0 + tt;
+                const uint32_t shift16 = (uint32_t)(Sched::shift_px(Sched::tap(i), HALO_W) * 128) >> 4;   // compile-time after unrolling
+                const uint64_t ah = ah0 + (uint64_t)shift16;
+                const uint64_t bh = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+                for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (cc | i | k) ? 1u : 0u);
+                if (X3) {
+                  const uint64_t al = al0 + (uint64_t)shift16;
+                  const uint64_t bl = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP + Cfg::B_TILE);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+                  for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+                }
               }
+              umma_commit(smem_u32(&b_empty[st]));
+              if (++st == STAGES) { st = 0; bphase ^= 1u; }
             }
-            umma_commit(smem_u32(&b_empty[st]));
-            if (++st == STAGES) { st = 0; bphase ^= 1u; }
+            umma_commit(smem_u32(&halo_empty[hb]));             // all taps of this halo have been issued
+            if (++hb == HB) { hb = 0; hphase ^= 1u; }
           }
-          umma_commit(smem_u32(&halo_empty[hb]));               // all taps of this chunk have read the halo
-          if (++hb == HB) { hb = 0; hphase ^= 1u; }
         }
         umma_commit(smem_u32(&acc_full[ab]));
       }
@@ -255,7 +287,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int nvec = (int)(e.halo_bytes / 16);
     int g = 0;
     for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
-      for (int cc = 0; cc < e.cchunks; ++cc, ++g) {
+      for (int cq = 0; cq < e.cchunks * NPH; ++cq, ++g) {
         const int hb = g % HB;
         mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g / HB) & 1));
         float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)hb * T2_HALO_STRIDE);
@@ -309,8 +341,9 @@ struct Key2Hash {
 std::mutex g_mu2;
 std::unordered_map<Key2, CUtensorMap, Key2Hash> g_maps2;
 
-int get_map2(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d2, int d3, int b1, int b2) {
-  Key2 key{ptr, d0, d1, d2, d3, b1, b2};
+// b1, b2: box extent in ELEMENTS FETCHED along dims 1, 2; es = element stride along those dims (1 or 2)
+int get_map2(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d2, int d3, int b1, int b2, int es = 1) {
+  Key2 key{ptr, d0, d1, d2, d3, b1 * es, b2 * es + (es - 1)};
   {
     std::lock_guard<std::mutex> lk(g_mu2);
     auto it = g_maps2.find(key);
@@ -320,8 +353,8 @@ int get_map2(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d
   if (!enc) return DH_E_VARIANT;
   cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)d3};
   cuuint64_t strides[3] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4, (cuuint64_t)d0 * d1 * d2 * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)b1, (cuuint32_t)b2, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {32, (cuuint32_t)(b1 * es), (cuuint32_t)(b2 * es), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   CUtensorMap m;
   const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)ptr, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -336,23 +369,26 @@ int get_map2(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d
   return 0;
 }
 
-template <int NT, bool X3, int KS>
+template <int NT, bool X3, int KS, int SD>
 int launch2k(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
   using Cfg = T2Cfg<NT, X3>;
-  cudaError_t err = cudaFuncSetAttribute(conv_tc2_kernel<NT, X3, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  cudaError_t err = cudaFuncSetAttribute(conv_tc2_kernel<NT, X3, KS, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (err != cudaSuccess) return (int)err;
-  conv_tc2_kernel<NT, X3, KS><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, e);
+  conv_tc2_kernel<NT, X3, KS, SD><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, e);
   DH_CHECK_LAUNCH();
   return 0;
 }
 template <int NT, bool X3>
 int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
-  return e.ntaps == 9 ? launch2k<NT, X3, 3>(A0, A1, Bm, e, grid, s) : launch2k<NT, X3, 1>(A0, A1, Bm, e, grid, s);
+  if (e.stride == 2)
+    return e.ntaps == 9 ? launch2k<NT, X3, 3, 2>(A0, A1, Bm, e, grid, s) : launch2k<NT, X3, 1, 2>(A0, A1, Bm, e, grid, s);
+  return e.ntaps == 9 ? launch2k<NT, X3, 3, 1>(A0, A1, Bm, e, grid, s) : launch2k<NT, X3, 1, 1>(A0, A1, Bm, e, grid, s);
 }
 }  // namespace
 
 bool dh_conv_tc2_eligible(const ConvArgs& a) {
-  const bool base = a.wt != nullptr && a.stride == 1 && a.up == 1 && a.KH == a.KW && (a.KH == 1 || a.KH == 3) &&
+  const bool base = a.wt != nullptr && a.up == 1 &&
+                    (a.stride == 1 || (a.stride == 2 && a.inH % 2 == 0 && a.inW % 2 == 0 && !a.ps)) && a.KH == a.KW && (a.KH == 1 || a.KH == 3) &&
                     a.pad == a.KH / 2 && a.C0 > 0 && a.C0 % 32 == 0 && a.C1 % 32 == 0 &&
                     (a.Cout == 32 || a.Cout == 64 || a.Cout == 128 || a.Cout == 256) && a.inH >= 1 && a.inW >= 1;
   if (!base) return false;
@@ -371,18 +407,18 @@ int dh_launch_conv_tc2(const ConvArgs& a, int x3, cudaStream_t s) {
   const int NT = a.Cout >= 128 ? 128 : a.Cout;
   const int hw = (a.KH == 3) ? T2_HW : T2_TW, hh = (a.KH == 3) ? T2_HH : T2_TH;
   CUtensorMap A0, A1, Bm;
-  int rc = get_map2(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, hw, hh);
+  int rc = get_map2(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, hw, hh, a.stride);
   if (rc) return rc;
-  if (a.C1) { rc = get_map2(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, hw, hh); if (rc) return rc; } else A1 = A0;
+  if (a.C1) { rc = get_map2(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, hw, hh, a.stride); if (rc) return rc; } else A1 = A0;
   rc = get_map2(&Bm, a.wt, 2, K, 2 * a.Cout, 1, 1, NT, 1);       // rows [0,Cout) = hi, [Cout,2Cout) = lo
   if (rc) return rc;
   T2Args e;
   e.bias = a.bias; e.res = a.res; e.out = a.out;
-  e.OH = a.inH; e.OW = a.inW; e.Cout = a.Cout; e.relu = a.relu;
-  e.tilesX = dh_cdiv(a.inW, T2_TW);
+  e.OH = a.inH / a.stride; e.OW = a.inW / a.stride; e.Cout = a.Cout; e.relu = a.relu; e.stride = a.stride;
+  e.tilesX = dh_cdiv(e.OW, T2_TW);
   e.cchunks0 = a.C0 / 32; e.cchunks = Cin / 32; e.ntaps = a.KH * a.KW; e.KW = a.KW; e.Cin = Cin; e.ps = a.ps;
   e.halo_w = hw; e.halo_h = hh; e.halo_bytes = (uint32_t)(hw * hh * 128);
-  e.tilesY = dh_cdiv(a.inH, T2_TH); e.ncout_tiles = a.Cout / NT;
+  e.tilesY = dh_cdiv(e.OH, T2_TH); e.ncout_tiles = a.Cout / NT;
   e.ntiles = e.tilesX * e.tilesY * e.ncout_tiles * a.N;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -141,9 +141,12 @@ extern "C" size_t dahitra_workspace_bytes(int variant, int B, int H, int W, int 
 // ----------------------------------------------------------------------------------------------------
 static int conv_dispatch(const ConvArgs& a, int flags, cudaStream_t s) {
   if (flags & DH_FLAG_CONV_TC) {
-    // stride 1: halo-reuse kernel (1xTF32 or error-compensated 3xTF32); stride 2: per-tap TMA kernel (1xTF32)
-    if (!(flags & DH_FLAG_CONV_TC_V1) && dh_conv_tc2_eligible(a)) return dh_launch_conv_tc2(a, (flags & DH_FLAG_TC_3XTF32) ? 1 : 0, s);
-    if (dh_conv_tc_eligible(a) && (a.stride == 1 || (flags & DH_FLAG_TC_STRIDE2))) return dh_launch_conv_tc(a, s);
+    // halo-reuse kernel (1xTF32 or error-compensated 3xTF32; stride 2 through the four phase images), or the older
+    // per-tap TMA kernel (1xTF32) when DH_FLAG_CONV_TC_V1 asks for it.  Stride-2 convs need DH_FLAG_TC_STRIDE2.
+    const bool stride_ok = a.stride == 1 || (flags & DH_FLAG_TC_STRIDE2);
+    if (stride_ok && !(flags & DH_FLAG_CONV_TC_V1) && dh_conv_tc2_eligible(a))
+      return dh_launch_conv_tc2(a, (flags & DH_FLAG_TC_3XTF32) ? 1 : 0, s);
+    if (stride_ok && dh_conv_tc_eligible(a)) return dh_launch_conv_tc(a, s);
   }
   return dh_launch_conv_ffma(a, s);
 }
