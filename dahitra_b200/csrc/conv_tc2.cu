@@ -42,25 +42,27 @@ struct T2Args {
   int OH, OW, Cout, relu, tilesX, cchunks0, cchunks, ntaps, KW, Cin, ps;
   int halo_w, halo_h;        // 10 x 18 (3x3) or 8 x 16 (1x1)
   int stride;                // 1 or 2
-  int tilesY, ncout_tiles, ntiles;
+  int tilesY, ncout_tiles, ntiles;   // ntiles: work items = tiles (CG = 1) or tile pairs (CG = 2)
+  int N;                             // images
   uint32_t halo_bytes;
 };
 
-template <int NT, bool X3> struct T2Cfg {
+template <int NT, bool X3, int CG = 1> struct T2Cfg {
   // Persistent kernel, one CTA per SM.  Pipeline depth is sized so that the MMA warp always has >= ~1500 cycles of
   // operands in flight (L2 latency under load): the smaller the N tile, the faster a stage is consumed, so the more
   // halo buffers (HB) and filter stages it gets.  A stage holds TPS filter taps so the issuing thread waits /
   // commits once per 4*TPS (x3: 12*TPS) MMAs.
   static constexpr int HB = X3 ? 2 : (NT == 128 ? 2 : (NT == 64 ? 3 : 4));          // halo chunk buffers (x3: hi + lo each)
   static constexpr int TPS = X3 ? (NT == 32 ? 3 : 1) : 3;
-  static constexpr int STAGES = X3 ? (NT == 128 ? 3 : (NT == 64 ? 6 : 4)) : (NT == 128 ? 3 : (NT == 64 ? 5 : 8));
-  static constexpr uint32_t B_TILE = NT * 128;
+  static constexpr int STAGES1 = X3 ? (NT == 128 ? 3 : (NT == 64 ? 6 : 4)) : (NT == 128 ? 3 : (NT == 64 ? 5 : 8));
+  static constexpr int STAGES = CG == 2 ? (2 * STAGES1 > 8 ? 8 : 2 * STAGES1) : STAGES1;   // CTA pair: half-size B tiles
+  static constexpr uint32_t B_TILE = (NT / CG) * 128;           // a CTA of a pair holds N/2 rows of B
   static constexpr uint32_t B_TAP = B_TILE * (X3 ? 2 : 1);      // hi (+ lo) tile of one tap
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
   static constexpr uint32_t HALO_BUFS = X3 ? 2 * HB : HB;       // [hi 0..HB-1][lo 0..HB-1]
   static constexpr uint32_t SMEM = HALO_BUFS * T2_HALO_STRIDE + STAGES * B_STAGE + 1024;
   static constexpr int THREADS = X3 ? 352 : 224;                // + 4 splitter warps
-  static constexpr uint32_t IDESC = umma_idesc_tf32(128, NT);
+  static constexpr uint32_t IDESC = umma_idesc_tf32(128 * CG, NT);
   static constexpr uint32_t TMEM_COLS = (2 * NT < 32) ? 32 : 2 * NT;   // two accumulators
 };
 
@@ -90,20 +92,24 @@ template <int KS, int SD> struct TapSched {
 };
 
 struct TileCoord { int n, oy0, ox0, n0; };
-__device__ __forceinline__ TileCoord tile_coord(int tile, const T2Args& e, int NT) {
+// CG = 2: work item = (pair of consecutive M tiles, cout tile); CTA `rank` of the pair takes M tile 2*pair + rank.  The
+// odd tile of the last pair may not exist: then n == e.N, its TMA boxes are out of bounds (zero-filled) and its
+// epilogue stores nothing.
+__device__ __forceinline__ TileCoord tile_coord(int tile, const T2Args& e, int NT, int CG = 1, int rank = 0) {
   TileCoord t;
   const int ct = tile % e.ncout_tiles; tile /= e.ncout_tiles;
+  if (CG == 2) tile = 2 * tile + rank;
   const int tx = tile % e.tilesX; tile /= e.tilesX;
   const int ty = tile % e.tilesY;
   t.n = tile / e.tilesY; t.oy0 = ty * T2_TH; t.ox0 = tx * T2_TW; t.n0 = ct * NT;
   return t;
 }
 
-template <int NT, bool X3, int KS, int SD>
-__global__ void __launch_bounds__(T2Cfg<NT, X3>::THREADS, 1)
+template <int NT, bool X3, int KS, int SD, int CG>
+__global__ void __launch_bounds__(T2Cfg<NT, X3, CG>::THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const T2Args e) {
-  using Cfg = T2Cfg<NT, X3>;
+  using Cfg = T2Cfg<NT, X3, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t2_raw[];
   constexpr int HB = Cfg::HB;
@@ -118,25 +124,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   constexpr int pad = (KS == 3) ? 1 : 0;
   using Sched = TapSched<KS, SD>;
   constexpr int NPH = Sched::NPH;
+  // CTA pair (CG = 2): rank 0 is the leader — it alone issues the MMAs and owns the barriers the MMA warp waits on
+  // (halo_ready / halo_full in 1xTF32 / b_full / acc_empty); the peer's producers, splitters and epilogue signal them
+  // remotely, and the leader's multicast commits release the *_empty / acc_full barriers of both CTAs.
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int w0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // first work item, and the stride between items
+  const int wstep = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < HB; ++i) {
       mbar_init(smem_u32(&halo_full[i]), 1);
-      mbar_init(smem_u32(&halo_ready[i]), 128);       // X3: every splitter thread arrives
+      mbar_init(smem_u32(&halo_ready[i]), 128 * CG);  // X3: every splitter thread (of both CTAs) arrives
       mbar_init(smem_u32(&halo_empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&acc_full[i]), 1);
-      mbar_init(smem_u32(&acc_empty[i]), 128);        // every epilogue thread arrives
+      mbar_init(smem_u32(&acc_empty[i]), 128 * CG);   // every epilogue thread (of both CTAs) arrives
     }
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+    else         tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                      // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
@@ -146,21 +162,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {                                            // ---------------- halo TMA producer
       int g = 0;
-      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
-        const TileCoord t = tile_coord(tile, e, NT);
+      for (int tile = w0; tile < e.ntiles; tile += wstep) {
+        const TileCoord t = tile_coord(tile, e, NT, CG, rank);
         for (int cc = 0; cc < e.cchunks; ++cc) {
 #pragma unroll
           for (int ph = 0; ph < NPH; ++ph, ++g) {
             const int hb = g % HB, use = g / HB;
             mbar_wait(smem_u32(&halo_empty[hb]), (uint32_t)((use & 1) ^ 1));
+            // 1xTF32 pair: the MMA warp waits on the LEADER's halo_full, which counts the bytes of both halos
+            constexpr bool REMOTE = (CG == 2 && !X3);
             const uint32_t bar = smem_u32(&halo_full[hb]);
-            mbar_expect_tx(bar, e.halo_bytes);
+            if (!REMOTE) mbar_expect_tx(bar, e.halo_bytes);
+            else if (rank == 0) mbar_expect_tx(bar, 2 * e.halo_bytes);
             const uint32_t dst = base + (uint32_t)hb * T2_HALO_STRIDE;
             // input coordinates of the halo origin (stride 2: origin of phase (ph>>1, ph&1), in full-resolution pixels)
             const int cx = SD == 1 ? t.ox0 - pad : 2 * (t.ox0 - pad) + (ph & 1);
             const int cy = SD == 1 ? t.oy0 - pad : 2 * (t.oy0 - pad) + (ph >> 1);
-            if (cc < e.cchunks0) tma_load_4d(dst, &tmA0, bar, cc * 32, cx, cy, t.n);
-            else                 tma_load_4d(dst, &tmA1, bar, (cc - e.cchunks0) * 32, cx, cy, t.n);
+            const CUtensorMap* tm = cc < e.cchunks0 ? &tmA0 : &tmA1;
+            const int c0 = (cc < e.cchunks0 ? cc : cc - e.cchunks0) * 32;
+            if (REMOTE && rank == 1) tma_load_4d_2sm(dst, tm, mapa_u32(bar, 0), c0, cx, cy, t.n);
+            else                     tma_load_4d(dst, tm, bar, c0, cx, cy, t.n);
           }
         }
       }
@@ -170,47 +191,60 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       constexpr int NTAPS_ = KS * KS;
       constexpr int TPS_ = (SD == 1 && NTAPS_ % Cfg::TPS == 0) ? Cfg::TPS : 1;
       int step = 0;
-      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
-        const TileCoord t = tile_coord(tile, e, NT);
+      for (int tile = w0; tile < e.ntiles; tile += wstep) {
+        const TileCoord t = tile_coord(tile, e, NT, CG, rank);
         for (int cc = 0; cc < e.cchunks; ++cc) {
 #pragma unroll
           for (int i0 = 0; i0 < NTAPS_; i0 += TPS_, ++step) {              // one ring stage = TPS_ filter taps, in schedule order
             const int st = step % STAGES, round = step / STAGES;
             mbar_wait(smem_u32(&b_empty[st]), (uint32_t)((round & 1) ^ 1));
-            const uint32_t bar = smem_u32(&b_full[st]);
-            mbar_expect_tx(bar, (uint32_t)TPS_ * Cfg::B_TAP);
+            const uint32_t bar = smem_u32(&b_full[st]);                    // CG = 2: the leader's barrier counts both halves
+            if (rank == 0) mbar_expect_tx(bar, (uint32_t)(CG * TPS_) * Cfg::B_TAP);
+            const uint32_t lbar = (CG == 2 && rank == 1) ? mapa_u32(bar, 0) : bar;
+            const int nrow = t.n0 + rank * (NT / CG);
 #pragma unroll
             for (int tt = 0; tt < TPS_; ++tt) {
               const uint32_t dst = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)tt * Cfg::B_TAP;
               const int kcol = Sched::tap(i0 + tt) * e.Cin + cc * 32;
-              tma_load_2d(dst, &tmB, bar, kcol, t.n0);
-              if (X3) tma_load_2d(dst + Cfg::B_TILE, &tmB, bar, kcol, e.Cout + t.n0);    // lo rows follow the hi rows
+              if (CG == 2 && rank == 1) {
+                tma_load_2d_2sm(dst, &tmB, lbar, kcol, nrow);
+                if (X3) tma_load_2d_2sm(dst + Cfg::B_TILE, &tmB, lbar, kcol, e.Cout + nrow);
+              } else {
+                tma_load_2d(dst, &tmB, bar, kcol, nrow);
+                if (X3) tma_load_2d(dst + Cfg::B_TILE, &tmB, bar, kcol, e.Cout + nrow);  // lo rows follow the hi rows
+              }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {                                            // ---------------- MMA issuer
+    if (lane == 0 && rank == 0) {                               // ---------------- MMA issuer (pair: the leader only)
       // The issuing thread is the critical path of the whole kernel: everything between two tcgen05.mma's is
       // compile-time (tap shifts, taps per stage) or a wrapping counter — no divisions, no runtime tap arithmetic.
       constexpr int NTAPS = KS * KS;
       constexpr int HALO_W = (KS == 3) ? T2_HW : T2_TW;
       constexpr int TPS = (SD == 1 && NTAPS % Cfg::TPS == 0) ? Cfg::TPS : 1;
       constexpr uint32_t SBO = (uint32_t)HALO_W * 128u;
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if (CG == 2) umma_tf32_2sm(d, a, b, idesc, acc); else umma_tf32(d, a, b, idesc, acc);
+      };
+      auto commit = [](uint32_t bar) { if (CG == 2) umma_commit_2sm(bar); else umma_commit(bar); };
       int hb = 0, st = 0;
       uint32_t hphase = 0, bphase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
+      for (int tile = w0; tile < e.ntiles; tile += wstep, ++it) {
         const int ab = it & 1;
-        mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));    // epilogue drained this accumulator
+        if (CG == 2) mbar_wait_cluster(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));
+        else         mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));    // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)ab * NT;
         for (int cc = 0; cc < e.cchunks; ++cc) {
 #pragma unroll
           for (int ph = 0; ph < NPH; ++ph) {
-            if (X3) mbar_wait(smem_u32(&halo_ready[hb]), hphase);
-            else    mbar_wait(smem_u32(&halo_full[hb]), hphase);
+            if (X3 && CG == 2) mbar_wait_cluster(smem_u32(&halo_ready[hb]), hphase);
+            else if (X3)       mbar_wait(smem_u32(&halo_ready[hb]), hphase);
+            else               mbar_wait(smem_u32(&halo_full[hb]), hphase);
             tc_fence_after();
             const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE;
             const uint64_t ah0 = halo_desc(h_hi, SBO);
@@ -227,35 +261,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const uint64_t ah = ah0 + (uint64_t)shift16;
                 const uint64_t bh = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (cc | i | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) mma(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (cc | i | k) ? 1u : 0u);
                 if (X3) {
                   const uint64_t al = al0 + (uint64_t)shift16;
                   const uint64_t bl = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP + Cfg::B_TILE);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+                  for (int k = 0; k < 4; ++k) mma(d_tmem, al + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, 1u);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), Cfg::IDESC, 1u);
+                  for (int k = 0; k < 4; ++k) mma(d_tmem, ah + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), Cfg::IDESC, 1u);
                 }
               }
-              umma_commit(smem_u32(&b_empty[st]));
+              commit(smem_u32(&b_empty[st]));
               if (++st == STAGES) { st = 0; bphase ^= 1u; }
             }
-            umma_commit(smem_u32(&halo_empty[hb]));             // all taps of this halo have been issued
+            commit(smem_u32(&halo_empty[hb]));             // all taps of this halo have been issued
             if (++hb == HB) { hb = 0; hphase ^= 1u; }
           }
         }
-        umma_commit(smem_u32(&acc_full[ab]));
+        commit(smem_u32(&acc_full[ab]));
       }
     }
   } else if (warp < 6) {                                        // ---------------- epilogue (warps 2..5)
     const int q = warp & 3;
     const int m = q * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
-      const TileCoord t = tile_coord(tile, e, NT);
+    for (int tile = w0; tile < e.ntiles; tile += wstep, ++it) {
+      const TileCoord t = tile_coord(tile, e, NT, CG, rank);
       const int ab = it & 1;
       const int oy = t.oy0 + m / T2_TW, ox = t.ox0 + m % T2_TW;
-      const bool valid = (oy < e.OH) && (ox < e.OW);
+      const bool valid = (oy < e.OH) && (ox < e.OW) && (t.n < e.N);
       mbar_wait(smem_u32(&acc_full[ab]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const size_t row = ((size_t)(t.n * e.OH + oy) * e.OW + ox) * e.Cout + t.n0;
@@ -265,7 +299,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NT + j * 32), v);
         if (j == NT / 32 - 1) {                                  // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
+          if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[ab]), 0));
+          else         mbar_arrive_local(smem_u32(&acc_empty[ab]));
         }
         if (valid) {
           float* op = e.out + row + j * 32;
@@ -286,7 +321,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int tI = threadIdx.x - 224;
     const int nvec = (int)(e.halo_bytes / 16);
     int g = 0;
-    for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
+    for (int tile = w0; tile < e.ntiles; tile += wstep) {
       for (int cq = 0; cq < e.cchunks * NPH; ++cq, ++g) {
         const int hb = g % HB;
         mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g / HB) & 1));
@@ -299,15 +334,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           lo[i] = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
         }
         fence_async_smem();
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&halo_ready[hb])) : "memory");
+        if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&halo_ready[hb]), 0));
+        else         mbar_arrive_local(smem_u32(&halo_ready[hb]));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                      // the peer's shared memory / barriers stay alive until both are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -369,20 +407,47 @@ int get_map2(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d
   return 0;
 }
 
-template <int NT, bool X3, int KS, int SD>
+template <int NT, bool X3, int KS, int SD, int CG>
 int launch2k(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
-  using Cfg = T2Cfg<NT, X3>;
-  cudaError_t err = cudaFuncSetAttribute(conv_tc2_kernel<NT, X3, KS, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  using Cfg = T2Cfg<NT, X3, CG>;
+  auto kern = conv_tc2_kernel<NT, X3, KS, SD, CG>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (err != cudaSuccess) return (int)err;
-  conv_tc2_kernel<NT, X3, KS, SD><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, e);
+  if (CG == 1) {
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, e);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(Cfg::THREADS, 1, 1); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, kern, A0, A1, Bm, e);
+    if (err != cudaSuccess) return (int)err;
+  }
   DH_CHECK_LAUNCH();
   return 0;
 }
-template <int NT, bool X3>
+template <int NT, bool X3, int CG>
 int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
   if (e.stride == 2)
-    return e.ntaps == 9 ? launch2k<NT, X3, 3, 2>(A0, A1, Bm, e, grid, s) : launch2k<NT, X3, 1, 2>(A0, A1, Bm, e, grid, s);
-  return e.ntaps == 9 ? launch2k<NT, X3, 3, 1>(A0, A1, Bm, e, grid, s) : launch2k<NT, X3, 1, 1>(A0, A1, Bm, e, grid, s);
+    return e.ntaps == 9 ? launch2k<NT, X3, 3, 2, CG>(A0, A1, Bm, e, grid, s) : launch2k<NT, X3, 1, 2, CG>(A0, A1, Bm, e, grid, s);
+  return e.ntaps == 9 ? launch2k<NT, X3, 3, 1, CG>(A0, A1, Bm, e, grid, s) : launch2k<NT, X3, 1, 1, CG>(A0, A1, Bm, e, grid, s);
+}
+template <int CG>
+int launch2n(int NT, int x3, const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
+  if (x3) {
+    switch (NT) {
+      case 128: return launch2<128, true, CG>(A0, A1, Bm, e, grid, s);
+      case 64: return launch2<64, true, CG>(A0, A1, Bm, e, grid, s);
+      default: return launch2<32, true, CG>(A0, A1, Bm, e, grid, s);
+    }
+  }
+  switch (NT) {
+    case 128: return launch2<128, false, CG>(A0, A1, Bm, e, grid, s);
+    case 64: return launch2<64, false, CG>(A0, A1, Bm, e, grid, s);
+    default: return launch2<32, false, CG>(A0, A1, Bm, e, grid, s);
+  }
 }
 }  // namespace
 
@@ -397,7 +462,8 @@ bool dh_conv_tc2_eligible(const ConvArgs& a) {
 }
 
 // a.wt: [2][Cout][K] = TF32-rounded filter (hi) followed by its TF32-rounded remainder (lo); x3 uses both.
-int dh_launch_conv_tc2(const ConvArgs& a, int x3, cudaStream_t s) {
+// cg = 2: CTA pairs (tcgen05 cta_group::2): M = 256 per MMA, each CTA loads and reads only half of the filter tile
+int dh_launch_conv_tc2(const ConvArgs& a, int x3, int cg, cudaStream_t s) {
   DH_REQUIRE(a.in0 && a.wt && a.out, DH_E_NULL);
   DH_REQUIRE(a.C1 == 0 || a.in1, DH_E_NULL);
   DH_REQUIRE(dh_conv_tc2_eligible(a), DH_E_SHAPE);
@@ -410,7 +476,8 @@ int dh_launch_conv_tc2(const ConvArgs& a, int x3, cudaStream_t s) {
   int rc = get_map2(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, hw, hh, a.stride);
   if (rc) return rc;
   if (a.C1) { rc = get_map2(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, hw, hh, a.stride); if (rc) return rc; } else A1 = A0;
-  rc = get_map2(&Bm, a.wt, 2, K, 2 * a.Cout, 1, 1, NT, 1);       // rows [0,Cout) = hi, [Cout,2Cout) = lo
+  cg = (cg == 2) ? 2 : 1;
+  rc = get_map2(&Bm, a.wt, 2, K, 2 * a.Cout, 1, 1, NT / cg, 1);  // rows [0,Cout) = hi, [Cout,2Cout) = lo
   if (rc) return rc;
   T2Args e;
   e.bias = a.bias; e.res = a.res; e.out = a.out;
@@ -419,21 +486,17 @@ int dh_launch_conv_tc2(const ConvArgs& a, int x3, cudaStream_t s) {
   e.cchunks0 = a.C0 / 32; e.cchunks = Cin / 32; e.ntaps = a.KH * a.KW; e.KW = a.KW; e.Cin = Cin; e.ps = a.ps;
   e.halo_w = hw; e.halo_h = hh; e.halo_bytes = (uint32_t)(hw * hh * 128);
   e.tilesY = dh_cdiv(e.OH, T2_TH); e.ncout_tiles = a.Cout / NT;
-  e.ntiles = e.tilesX * e.tilesY * e.ncout_tiles * a.N;
+  e.N = a.N;
+  const int mtiles = e.tilesX * e.tilesY * a.N;
+  e.ntiles = (cg == 2 ? (mtiles + 1) / 2 : mtiles) * e.ncout_tiles;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cg == 2) {
+    const int pairs = sms / 2;
+    dim3 grid((unsigned)(2 * (e.ntiles < pairs ? e.ntiles : pairs)), 1, 1);       // persistent: one CTA pair per TPC
+    return launch2n<2>(NT, x3, A0, A1, Bm, e, grid, s);
+  }
   dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);          // persistent: one CTA per SM
-  if (x3) {
-    switch (NT) {
-      case 128: return launch2<128, true>(A0, A1, Bm, e, grid, s);
-      case 64: return launch2<64, true>(A0, A1, Bm, e, grid, s);
-      default: return launch2<32, true>(A0, A1, Bm, e, grid, s);
-    }
-  }
-  switch (NT) {
-    case 128: return launch2<128, false>(A0, A1, Bm, e, grid, s);
-    case 64: return launch2<64, false>(A0, A1, Bm, e, grid, s);
-    default: return launch2<32, false>(A0, A1, Bm, e, grid, s);
-  }
+  return launch2n<1>(NT, x3, A0, A1, Bm, e, grid, s);
 }

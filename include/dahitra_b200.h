@@ -50,6 +50,7 @@ extern "C" {
 #define DH_FLAG_STEM_TC     16  /* 7x7 stem on tcgen05 (on-chip im2col), stem_tc.cu */
 #define DH_FLAG_DEC_TC_X3   32  /* with DEC_TC: error-compensated 3xTF32 in the decoder (fp32-grade accuracy) */
 #define DH_FLAG_CONV_TC_V1  64  /* with CONV_TC: force the per-tap TMA kernel (conv_tc.cu) instead of the halo-reuse one */
+#define DH_FLAG_CONV_TC_2CTA 128 /* with CONV_TC: CTA pairs (tcgen05 cta_group::2, clusters of 2): M = 256 per MMA, half the filter traffic per SM */
 #define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC | DH_FLAG_STEM_TC)   /* the "tf32" mode */
 
 /* ---- prepared-weight table -------------------------------------------------------------------
