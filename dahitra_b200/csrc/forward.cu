@@ -48,7 +48,7 @@ bool make_plan(Plan& p, int variant, int B, int H, int W, int nc) {
     Level& L = p.lv[i];
     L.cin = cins[i]; L.heads = heads[i]; L.depth = depths[i]; L.h = H / div[i]; L.w = W / div[i];
     const size_t n = (size_t)L.h * L.w;
-    L.nchunk = (int)((n + 127) / 128);
+    L.nchunk = (int)((n + 255) / 256);
     L.xs = b.take(N2 * n * 32);
     L.xd = b.take(N2 * n * 32);
     L.dx = b.take((size_t)B * n * 32);
@@ -231,6 +231,35 @@ inline void prof_mark(cudaStream_t s, const char* name, double flops, double byt
 }  // namespace
 
 // ----------------------------------------------------------------------------------------------------
+// side streams: the token / decoder chains of levels 4 and 3 do not depend on level 5, and most of their kernels are
+// too small to fill 148 SMs, so they are forked onto two auxiliary streams after the trunk and joined before the
+// first launch that needs them (event record / wait only: asynchronous, graph-capturable, no host synchronisation).
+// One set per (host thread, device), created on first use and kept for the life of the thread.
+// ----------------------------------------------------------------------------------------------------
+namespace {
+struct AuxStreams {
+  bool ok = false;
+  cudaStream_t st[2];
+  cudaEvent_t fork, join[2];
+};
+AuxStreams* aux_streams() {
+  thread_local AuxStreams per_dev[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  AuxStreams& a = per_dev[dev];
+  if (!a.ok) {
+    bool good = cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && good; ++i)
+      good = cudaStreamCreateWithFlags(&a.st[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!good) { cudaGetLastError(); return nullptr; }
+    a.ok = true;
+  }
+  return &a;
+}
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------
 // whole forward
 // ----------------------------------------------------------------------------------------------------
 #define DH_STEP(name, fl, by, expr)        \
@@ -256,7 +285,8 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
     DH_REQUIRE(weights[i] || optional, DH_E_WEIGHTS);
     DH_REQUIRE(dh_aligned16(weights[i]), DH_E_ALIGN);
   }
-  cudaStream_t s = (cudaStream_t)stream;
+  const cudaStream_t s_main = (cudaStream_t)stream;
+  cudaStream_t s = s_main;                      // the stream the launch helpers below use; switched while a level is forked
   float* ws = (float*)workspace;
   auto Wt = [&](int slot) { return (const float*)weights[slot]; };
   const int N2 = 2 * B;
@@ -328,17 +358,13 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
       {"squeeze_tok_4", "token_enc_4", "dec_tables_4", "decoder_4_x12", "conv_decode_4", "decoder_4_diff", "conv_layer4"},
       {"squeeze_tok_3", "token_enc_3", "dec_tables_3", "decoder_3_x12", "conv_decode_3", "decoder_3_diff", "conv_layer4"}};
   float* C4 = ws + p.c4;
-  for (int i = 0; i < 3; ++i) {
+  // level_pre(i): everything of level i that depends only on the trunk; level_post(i): the part that needs the level above
+  auto level_pre = [&](int i) -> int {
     const Level& L = p.lv[i];
     const int npix = L.h * L.w;
     const float *wsq = Wt(base[i] + 0), *wtok = Wt(base[i] + 1), *enc = Wt(base[i] + 2), *dec = Wt(base[i] + 3),
                 *pos = Wt(base[i] + 4);
-    float *XS = ws + L.xs, *XD = ws + L.xd, *DX = ws + L.dx, *OUT = ws + L.out, *PART = ws + L.part, *MEM = ws + L.mem,
-          *TAB = ws + L.tab;
-    // what the reference adds to this level's result: nothing (level 5), up2(out_5) (level 4, :1333),
-    // conv_layer4(up2(out_4)) at the same resolution (level 3, :1340)
-    const float* skip = (i == 0) ? nullptr : (i == 1 ? ws + p.lv[0].out : C4);
-    const int skip_up = (i == 1) ? 2 : 1;
+    float *XS = ws + L.xs, *XD = ws + L.xd, *DX = ws + L.dx, *PART = ws + L.part, *MEM = ws + L.mem, *TAB = ws + L.tab;
     // as-written FLOPs per pixel of one decoder call (help_funcs.py:66-114): q proj + dots + attn.V + out proj + MLP
     const double inner = 64.0 * L.heads;
     const double dec_fl_px = L.depth * 2.0 * (32 * inner + 4 * inner + 4 * inner + inner * 32 + 2 * 32 * 32);
@@ -356,26 +382,62 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
       return dtc ? dh_launch_decoder_tables_tc(MEM, B, first, ncalls, dec, L.heads, L.depth, TAB, s)
                  : dh_launch_decoder_tables(MEM, B, first, ncalls, dec, L.heads, L.depth, TAB, s);
     };
-    auto decode = [&](const float* xin, const float* tab, int nimg, const float* sk, int sku, float* o) -> int {
-      return dtc ? dh_launch_pixel_decoder_tc(xin, pos, tab, dectc, nimg, L.h, L.w, L.heads, L.depth, sk, sku,
-                                              (flags & DH_FLAG_DEC_TC_X3) ? 1 : 0, o, s)
-                 : dh_launch_pixel_decoder(xin, pos, tab, dec, nimg, L.h, L.w, L.heads, L.depth, sk, sku, o, s);
-    };
     if (variant == DH_VARIANT_LEVIR) {
       DH_STEP(nm[i][2], 0.0, 4.0 * 3 * B * L.depth * tabf, tables(0, 3));
-      DH_STEP(nm[i][3], dec_fl_px * N2 * npix, dec_by_px * N2 * npix, decode(XS, TAB, N2, nullptr, 1, XD));
+      DH_STEP(nm[i][3], dec_fl_px * N2 * npix, dec_by_px * N2 * npix,
+              (dtc ? dh_launch_pixel_decoder_tc(XS, pos, TAB, dectc, N2, L.h, L.w, L.heads, L.depth, nullptr, 1,
+                                                (flags & DH_FLAG_DEC_TC_X3) ? 1 : 0, XD, s)
+                   : dh_launch_pixel_decoder(XS, pos, TAB, dec, N2, L.h, L.w, L.heads, L.depth, nullptr, 1, XD, s)));
       DH_CONV(nm[i][4], XD, XD + half, 32, 32, B, L.h, L.w, 1, 3, 1, 32, base[i] + 5, -1, nullptr, 0, DX);
-      const float* tab2 = TAB + (size_t)2 * B * L.depth * tabf;
-      DH_STEP(nm[i][5], dec_fl_px * B * npix, (dec_by_px + (skip ? 128.0 / (skip_up * skip_up) : 0.0)) * B * npix,
-              decode(DX, tab2, B, skip, skip_up, OUT));
     } else {
       DH_STEP(nm[i][2], 0.0, 4.0 * B * L.depth * tabf, tables(2, 1));
       DH_CONV(nm[i][4], XS, XS + half, 32, 32, B, L.h, L.w, 1, 3, 1, 32, base[i] + 5, -1, nullptr, 0, DX);
-      DH_STEP(nm[i][5], dec_fl_px * B * npix, (dec_by_px + (skip ? 128.0 / (skip_up * skip_up) : 0.0)) * B * npix,
-              decode(DX, TAB, B, skip, skip_up, OUT));
     }
+    return 0;
+  };
+  auto level_post = [&](int i) -> int {
+    const Level& L = p.lv[i];
+    const int npix = L.h * L.w;
+    const float *dec = Wt(base[i] + 3), *pos = Wt(base[i] + 4);
+    float *DX = ws + L.dx, *OUT = ws + L.out, *TAB = ws + L.tab;
+    // what the reference adds to this level's result: nothing (level 5), up2(out_5) (level 4, :1333),
+    // conv_layer4(up2(out_4)) at the same resolution (level 3, :1340)
+    const float* skip = (i == 0) ? nullptr : (i == 1 ? ws + p.lv[0].out : C4);
+    const int skip_up = (i == 1) ? 2 : 1;
+    const double inner = 64.0 * L.heads;
+    const double dec_fl_px = L.depth * 2.0 * (32 * inner + 4 * inner + 4 * inner + inner * 32 + 2 * 32 * 32);
+    const double dec_by_px = 4.0 * 32 * (pos ? 3 : 2);
+    const bool dtc = (flags & DH_FLAG_DEC_TC) != 0;
+    const float* dectc = Wt(DH_W_LV5_DECTC + i);
+    const size_t tabf = dtc ? (size_t)DH_TABTC_FLOATS : (size_t)DH_TAB_FLOATS(L.heads);
+    const float* tab2 = (variant == DH_VARIANT_LEVIR) ? TAB + (size_t)2 * B * L.depth * tabf : TAB;
+    DH_STEP(nm[i][5], dec_fl_px * B * npix, (dec_by_px + (skip ? 128.0 / (skip_up * skip_up) : 0.0)) * B * npix,
+            (dtc ? dh_launch_pixel_decoder_tc(DX, pos, tab2, dectc, B, L.h, L.w, L.heads, L.depth, skip, skip_up,
+                                              (flags & DH_FLAG_DEC_TC_X3) ? 1 : 0, OUT, s)
+                 : dh_launch_pixel_decoder(DX, pos, tab2, dec, B, L.h, L.w, L.heads, L.depth, skip, skip_up, OUT, s)));
     if (i == 1)   // conv_layer4(up2(out_4)) -> C4 at H/4 (:1335-1336)
       DH_CONV(nm[i][6], OUT, nullptr, 32, 0, B, L.h, L.w, 2, 3, 1, 32, DH_W_CL4_W, DH_W_CL4_B, nullptr, 1, C4);
+    return 0;
+  };
+  // fork levels 4 and 3 unless profiling (per-launch events want one stream) or DH_FLAG_SERIAL asks for one stream
+  AuxStreams* aux = (g_prof.on || (flags & DH_FLAG_SERIAL)) ? nullptr : aux_streams();
+  if (aux) {
+    if (cudaEventRecord(aux->fork, s_main) != cudaSuccess) return (int)cudaGetLastError();
+    for (int i = 1; i <= 2; ++i) {
+      s = aux->st[i - 1];
+      if (cudaStreamWaitEvent(s, aux->fork, 0) != cudaSuccess) return (int)cudaGetLastError();
+      const int rc = level_pre(i);
+      if (rc == 0 && cudaEventRecord(aux->join[i - 1], s) != cudaSuccess) { s = s_main; return (int)cudaGetLastError(); }
+      s = s_main;
+      if (rc != 0) return rc;
+    }
+  }
+  for (int i = 0; i < 3; ++i) {
+    int rc = 0;
+    if (i == 0 || !aux) rc = level_pre(i);
+    else if (cudaStreamWaitEvent(s_main, aux->join[i - 1], 0) != cudaSuccess) rc = (int)cudaGetLastError();
+    if (rc == 0) rc = level_post(i);
+    if (rc != 0) return rc;
   }
   // ---- UNet head (reference networks.py:1341-1357)
   float *C3 = ws + p.c3, *Y20 = ws + p.y20, *O2 = ws + p.o2, *C2 = ws + p.c2;

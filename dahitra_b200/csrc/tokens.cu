@@ -11,7 +11,9 @@
 // the per-CTA (m, s, t) triples with the usual log-sum-exp rescaling.
 // =====================================================================================================
 namespace {
-constexpr int SQ_T = 128;   // pixels (= threads) per CTA
+constexpr int SQ_T = 128;   // threads per CTA
+constexpr int SQ_P = 2;     // pixels per thread: every filter read from shared memory feeds two pixels
+constexpr int SQ_PX = SQ_T * SQ_P;
 
 __global__ void __launch_bounds__(SQ_T)
 squeeze_tokens_kernel(const float* __restrict__ feat, int npix, int Cin, int nchunk, const float* __restrict__ wsq,
@@ -19,75 +21,87 @@ squeeze_tokens_kernel(const float* __restrict__ feat, int npix, int Cin, int nch
   extern __shared__ __align__(16) float sm[];
   float* w_s = sm;                         // [Cin][32]
   float* wt_s = w_s + Cin * 32;            // [32][4]
-  float* tile = wt_s + 128;                // [128][33]
-  float* e_s = tile + SQ_T * 33;           // [128][4]
-  float* red = e_s + SQ_T * 4;             // [4 warps][4]
+  float* tile = wt_s + 128;                // [256][33]
+  float* e_s = tile + SQ_PX * 33;          // [256][4]
+  float* red = e_s + SQ_PX * 4;            // [4 warps][4]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int img = blockIdx.y, chunk = blockIdx.x;
   for (int i = tid; i < Cin * 8; i += SQ_T) reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(wsq) + i);
   if (tid < 32) reinterpret_cast<float4*>(wt_s)[tid] = __ldg(reinterpret_cast<const float4*>(wtok) + tid);
   __syncthreads();
 
-  const int p = chunk * SQ_T + tid;
-  const bool valid = p < npix;
-  float acc[32];
+  // thread t owns pixels chunk*256 + t and + t + 128 (both coalesce the same way across the warp)
+  int p[SQ_P];
+  bool valid[SQ_P];
+  float acc[SQ_P][32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-  if (valid) {
-    const float* fp = feat + ((size_t)img * npix + p) * Cin;
-    for (int c = 0; c < Cin; c += 4) {
-      const float4 f = ldg4(fp + c);
-      const float fv[4] = {f.x, f.y, f.z, f.w};
+  for (int u = 0; u < SQ_P; ++u) {
+    p[u] = chunk * SQ_PX + u * SQ_T + tid;
+    valid[u] = p[u] < npix;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float* wr = w_s + (c + e) * 32;
+    for (int j = 0; j < 32; ++j) acc[u][j] = 0.f;
+  }
+  const float* fp0 = feat + ((size_t)img * npix + (valid[0] ? p[0] : 0)) * Cin;
+  const float* fp1 = feat + ((size_t)img * npix + (valid[1] ? p[1] : 0)) * Cin;
+  for (int c = 0; c < Cin; c += 4) {
+    const float4 f0 = ldg4(fp0 + c), f1 = ldg4(fp1 + c);
+    const float fv[SQ_P][4] = {{f0.x, f0.y, f0.z, f0.w}, {f1.x, f1.y, f1.z, f1.w}};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 ww = *reinterpret_cast<const float4*>(wr + q * 4);
-          acc[q * 4 + 0] = fmaf(fv[e], ww.x, acc[q * 4 + 0]);
-          acc[q * 4 + 1] = fmaf(fv[e], ww.y, acc[q * 4 + 1]);
-          acc[q * 4 + 2] = fmaf(fv[e], ww.z, acc[q * 4 + 2]);
-          acc[q * 4 + 3] = fmaf(fv[e], ww.w, acc[q * 4 + 3]);
+    for (int e = 0; e < 4; ++e) {
+      const float* wr = w_s + (c + e) * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 ww = *reinterpret_cast<const float4*>(wr + q * 4);
+#pragma unroll
+        for (int u = 0; u < SQ_P; ++u) {
+          acc[u][q * 4 + 0] = fmaf(fv[u][e], ww.x, acc[u][q * 4 + 0]);
+          acc[u][q * 4 + 1] = fmaf(fv[u][e], ww.y, acc[u][q * 4 + 1]);
+          acc[u][q * 4 + 2] = fmaf(fv[u][e], ww.z, acc[u][q * 4 + 2]);
+          acc[u][q * 4 + 3] = fmaf(fv[u][e], ww.w, acc[u][q * 4 + 3]);
         }
       }
     }
   }
-  float lg[4] = {0.f, 0.f, 0.f, 0.f};
+  float lg[SQ_P][4];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    acc[j] = fmaxf(acc[j], 0.f);
-    const float4 wt = *reinterpret_cast<const float4*>(wt_s + j * 4);
-    lg[0] = fmaf(acc[j], wt.x, lg[0]);
-    lg[1] = fmaf(acc[j], wt.y, lg[1]);
-    lg[2] = fmaf(acc[j], wt.z, lg[2]);
-    lg[3] = fmaf(acc[j], wt.w, lg[3]);
-  }
-  if (valid) {
-    float* op = xs + ((size_t)img * npix + p) * 32;
+  for (int u = 0; u < SQ_P; ++u) {
+    lg[u][0] = lg[u][1] = lg[u][2] = lg[u][3] = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) st4(op + q * 4, make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]));
+    for (int j = 0; j < 32; ++j) {
+      acc[u][j] = fmaxf(acc[u][j], 0.f);
+      const float4 wt = *reinterpret_cast<const float4*>(wt_s + j * 4);
+      lg[u][0] = fmaf(acc[u][j], wt.x, lg[u][0]);
+      lg[u][1] = fmaf(acc[u][j], wt.y, lg[u][1]);
+      lg[u][2] = fmaf(acc[u][j], wt.z, lg[u][2]);
+      lg[u][3] = fmaf(acc[u][j], wt.w, lg[u][3]);
+    }
+    if (valid[u]) {
+      float* op = xs + ((size_t)img * npix + p[u]) * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) st4(op + q * 4, make_float4(acc[u][q * 4], acc[u][q * 4 + 1], acc[u][q * 4 + 2], acc[u][q * 4 + 3]));
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tile[(u * SQ_T + tid) * 33 + j] = acc[u][j];
   }
   // block max of each token's logits
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
-    const float m = warp_max(valid ? lg[l] : -INFINITY);
+    const float m = warp_max(fmaxf(valid[0] ? lg[0][l] : -INFINITY, valid[1] ? lg[1][l] : -INFINITY));
     if (lane == 0) red[wid * 4 + l] = m;
   }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) tile[tid * 33 + j] = acc[j];
   __syncthreads();
-  float mx[4];
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
-    mx[l] = fmaxf(fmaxf(red[l], red[4 + l]), fmaxf(red[8 + l], red[12 + l]));
-    e_s[tid * 4 + l] = valid ? expf(lg[l] - mx[l]) : 0.f;
+    const float mx = fmaxf(fmaxf(red[l], red[4 + l]), fmaxf(red[8 + l], red[12 + l]));
+#pragma unroll
+    for (int u = 0; u < SQ_P; ++u) e_s[(u * SQ_T + tid) * 4 + l] = valid[u] ? expf(lg[u][l] - mx) : 0.f;
   }
   __syncthreads();
   // thread (l, c): weighted sum over the CTA's pixels
   const int l = tid >> 5, c = tid & 31;
   float t = 0.f, ssum = 0.f;
 #pragma unroll 8
-  for (int q = 0; q < SQ_T; ++q) {
+  for (int q = 0; q < SQ_PX; ++q) {
     const float e = e_s[q * 4 + l];
     ssum += e;
     t = fmaf(e, tile[q * 33 + c], t);
@@ -106,8 +120,8 @@ int dh_launch_squeeze_tokens(const float* feat, int N, int npix, int Cin, const 
   DH_REQUIRE(feat && wsq && wtok && xs && partials, DH_E_NULL);
   DH_REQUIRE(N > 0 && npix > 0 && Cin % 4 == 0 && Cin >= 4 && Cin <= 256, DH_E_SHAPE);
   DH_REQUIRE(dh_aligned16(feat) && dh_aligned16(wsq) && dh_aligned16(wtok) && dh_aligned16(xs), DH_E_ALIGN);
-  const int nchunk = dh_cdiv(npix, SQ_T);
-  const int smem = (Cin * 32 + 128 + SQ_T * 33 + SQ_T * 4 + 16) * (int)sizeof(float);
+  const int nchunk = dh_cdiv(npix, SQ_PX);
+  const int smem = (Cin * 32 + 128 + SQ_PX * 33 + SQ_PX * 4 + 16) * (int)sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(squeeze_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(nchunk, N);

@@ -10,7 +10,10 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless stated; the caller owns all memory (inputs, outputs,
- *     prepared weights, workspace).  The library never allocates, frees or synchronises.
+ *     prepared weights, workspace).  The library never allocates or frees device memory and never synchronises.
+ *     dahitra_forward forks two internal side streams off the caller's stream (event record / wait only, created on
+ *     first use per host thread and device) and joins them before it returns control of the stream; DH_FLAG_SERIAL
+ *     keeps everything on the caller's stream.
  *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*), CUDA-graph capturable.
  *   - return value: 0 ok; <0 argument/shape/alignment error detected on the host before any launch
  *     (DH_E_*); >0 a cudaError_t reported by cudaGetLastError() after a launch.
@@ -51,6 +54,7 @@ extern "C" {
 #define DH_FLAG_DEC_TC_X3   32  /* with DEC_TC: error-compensated 3xTF32 in the decoder (fp32-grade accuracy) */
 #define DH_FLAG_CONV_TC_V1  64  /* with CONV_TC: force the per-tap TMA kernel (conv_tc.cu) instead of the halo-reuse one */
 #define DH_FLAG_CONV_TC_2CTA 128 /* with CONV_TC: CTA pairs (tcgen05 cta_group::2, clusters of 2): M = 256 per MMA, half the filter traffic per SM */
+#define DH_FLAG_SERIAL      256 /* keep every launch on the caller's stream (no fork of levels 4 / 3 onto the library's side streams) */
 #define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC | DH_FLAG_STEM_TC)   /* the "tf32" mode */
 
 /* ---- prepared-weight table -------------------------------------------------------------------
@@ -183,7 +187,7 @@ int dahitra_maxpool3x3s2(const float* in, int N, int H, int W, int C, float* out
 /* Squeeze (1x1 conv + ReLU) fused with the tokenizer's spatial-softmax partial sums
  * (reference models/networks.py:1177-1184, 1273-1280).
  *   feat NHWC [N][npix][Cin] -> xs NHWC [N][npix][32]; partials [N][nchunk][4][34] = {max, sum, t[32]} per token,
- *   nchunk = ceil(npix/128). */
+ *   nchunk = ceil(npix/256) (one CTA of 128 threads covers 256 pixels). */
 int dahitra_squeeze_tokens(const float* feat, int N, int npix, int Cin, const float* w_sq, const float* w_tok,
                            float* xs, float* partials, void* stream);
 

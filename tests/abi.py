@@ -66,7 +66,7 @@ def maxpool(x):
 def squeeze_tokens(feat, wsq, wtok):
     lib = _lib.load()
     N, npix, Cin = feat.shape
-    nchunk = (npix + 127) // 128
+    nchunk = (npix + 255) // 256
     xs = torch.empty((N, npix, 32), device=feat.device, dtype=torch.float32)
     parts = torch.empty((N, nchunk, 4, 34), device=feat.device, dtype=torch.float32)
     _lib.check(lib.dahitra_squeeze_tokens(_p(feat), N, npix, Cin, _p(wsq), _p(wtok), _p(xs), _p(parts), _stream()),

@@ -59,7 +59,7 @@ def unpack_dec_layer(dec, H, layer):
     return d
 
 
-def squeeze_tokens(feat, wsq, wtok, chunk=128):
+def squeeze_tokens(feat, wsq, wtok, chunk=256):
     """feat [N][npix][Cin] -> xs [N][npix][32], partials [N][nchunk][4][34]"""
     xs = F.relu(feat @ wsq)
     a = xs @ wtok                                   # [N][npix][4]
