@@ -1,16 +1,20 @@
 // dahitra_b200 — stem (7x7 stride-2 pad-3 conv 3 -> 64 + folded BN + ReLU) on the tensor cores.
 //
 // Replaces resnet.conv1 + bn1 + relu (reference models/networks.py:1120-1122, models/resnet.py:150-153).
-// GEMM view: D[128 pixels][64] = A[128][K=147 -> 160] . Wt[64][160]^T, K ordered (r, s, ci) like DH_W_STEM_W.
-// C_in = 3 cannot feed a TMA/UMMA row directly, so the im2col rows are assembled ON CHIP.
+// GEMM view: D[128 pixels][64] = A[128][K] . Wt[64][K]^T.  C_in = 3 cannot feed a TMA/UMMA row directly, so the im2col
+// rows are assembled ON CHIP from a planar (NCHW) halo.  K is ordered (ci, r, s8): the 7 taps of one filter row of one
+// channel plus one zero-weight pad = 8 CONSECUTIVE halo floats = four 8-byte shared-memory loads and two 16-byte stores
+// into the K-major SWIZZLE_128B A tile, with no index table.  K = 21 groups x 8 = 168, padded to 192 = 6 K steps of 32.
 //
-// Persistent kernel, one CTA per SM, 256 threads:
-//   warps 0-3 "builders": stage the 21x37x3 input halo of the NEXT 8x16-pixel tile with cp.async (zero-filled
-//       outside the image; the only HBM read), then each thread gathers the 160 taps of ITS pixel of the CURRENT
-//       tile into the K-major SWIZZLE_128B A tile, 32 taps (one 128-byte row) per K step, double-buffered against
-//       the MMAs; builder thread 0 issues the tcgen05.mma's.
-//   warps 4-7 "epilogue": drain the accumulator of the previous tile (two TMEM accumulators), bias + ReLU, NHWC stores.
-// The filter image (pre-swizzled, 5 K-step tiles of 64x32; hi [+ lo]) is loaded once per CTA by one bulk copy.
+// Persistent kernel, one CTA per SM, 13 warps:
+//   warps 0-3 / 4-7  two builder warpgroups; thread t of each owns pixel t of the 8x16 tile.  Group 0 builds the even
+//                    K steps into A buffer 0, group 1 the odd ones into buffer 1, so two steps are always in flight
+//                    (a single builder warp per scheduler is issue-latency bound: that was 3/4 of the old kernel's time).
+//                    All 256 builder threads also stage the 21x37x3 input halo of the NEXT tile with cp.async
+//                    (zero-filled outside the image; the only HBM read).
+//   warps 8-11       epilogue: drain the accumulator of the previous tile (two TMEM accumulators), bias + ReLU, NHWC stores.
+//   warp 12          one lane issues the tcgen05.mma's in K order as the A buffers fill (mbarriers a_full / a_free).
+// The filter image (pre-swizzled, 6 K-step tiles of 64x32; hi [+ lo]) is loaded once per CTA by one bulk copy.
 // X3: error-compensated 3xTF32 — A rows are written as TF32 hi + lo tiles, the filter comes pre-split.
 #include "tc_common.cuh"
 
@@ -20,22 +24,22 @@ namespace {
 constexpr int SK_TH = 8, SK_TW = 16;                 // output patch
 constexpr int SK_HR = 2 * SK_TH + 5;                 // 21 halo rows
 constexpr int SK_HC = 2 * SK_TW + 5;                 // 37 halo cols
-constexpr int SK_HCP = 40;                           // padded row stride
+constexpr int SK_HCP = 40;                           // padded row stride (cols 37..39 stay zero)
 constexpr int SK_PLANE = SK_HR * SK_HCP;             // 840 floats per channel
-constexpr int SK_KSTEPS = 5;                         // 160 / 32
+constexpr int SK_KSTEPS = 6;                         // 192 / 32
+constexpr int SK_GROUPS = 21;                        // (ci, r) groups that carry data
 constexpr uint32_t SK_A_BYTES = 128 * 128;           // one A tile
-constexpr uint32_t SK_B_BYTES = SK_KSTEPS * 64 * 128;    // 40 KB filter image
-constexpr uint32_t SK_HALO_FLOATS = 3 * SK_PLANE + 8;    // + a zero slot for the K padding
-constexpr uint32_t SK_HALO_BYTES = ((SK_HALO_FLOATS * 4 + 15) / 16) * 16;
+constexpr uint32_t SK_B_BYTES = SK_KSTEPS * 64 * 128;    // 48 KB filter image
+constexpr uint32_t SK_HALO_BYTES = 3 * SK_PLANE * 4; // 10080
 constexpr uint32_t SK_IDESC = umma_idesc_tf32(128, 64);
+constexpr int SK_THREADS = 13 * 32;
 
 template <bool X3> struct SkCfg {
   static constexpr uint32_t NA = X3 ? 4 : 2;                      // A tiles: [buf0 hi, buf1 hi, buf0 lo, buf1 lo]
   static constexpr uint32_t NB = X3 ? 2 : 1;                      // filter images: hi (+ lo)
   static constexpr uint32_t OFF_B = NA * SK_A_BYTES;
   static constexpr uint32_t OFF_H = OFF_B + NB * SK_B_BYTES;      // two halo buffers
-  static constexpr uint32_t OFF_K = OFF_H + 2 * SK_HALO_BYTES;    // tap offset table
-  static constexpr uint32_t SMEM = OFF_K + 160 * 4 + 1024;
+  static constexpr uint32_t SMEM = OFF_H + 2 * SK_HALO_BYTES + 1024;
 };
 
 __device__ __forceinline__ float sk_tf32(float v) { return tf32_round(v); }
@@ -54,23 +58,23 @@ __device__ __forceinline__ SkTile sk_tile(int t, int tilesX, int tilesY) {
 }
 
 template <bool X3>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(SK_THREADS, 1)
 stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH, int OW, int tilesX, int tilesY, int ntiles,
                const float* __restrict__ wtc, const float* __restrict__ bias, float* __restrict__ out) {
   using Cfg = SkCfg<X3>;
   extern __shared__ uint8_t sk_raw[];
-  __shared__ __align__(8) uint64_t w_bar, a_free[2], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t w_bar, a_full[2], a_free[2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t base = (smem_u32(sk_raw) + 1023u) & ~1023u;
   uint8_t* bp = sk_raw + (base - smem_u32(sk_raw));
   constexpr uint32_t A_LO = 2 * SK_A_BYTES;                            // lo twins of the two A tiles (X3)
   const uint32_t b_addr = base + Cfg::OFF_B;
-  int* koff = reinterpret_cast<int*>(bp + Cfg::OFF_K);
 
   if (tid == 0) {
     mbar_init(smem_u32(&w_bar), 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&a_full[i]), 128);
       mbar_init(smem_u32(&a_free[i]), 1);
       mbar_init(smem_u32(&acc_full[i]), 1);
       mbar_init(smem_u32(&acc_empty[i]), 128);
@@ -78,33 +82,22 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 128);               // two 64-column accumulators
-  for (int k = tid; k < 160; k += 256) {
-    int off = 3 * SK_PLANE;                                            // zero slot (K padding 147..159)
-    if (k < 147) { const int tap = k / 3, ci = k - tap * 3, r = tap / 7, s = tap - r * 7; off = ci * SK_PLANE + r * SK_HCP + s; }
-    koff[k] = off;
-  }
-  if (tid < 16) {                                                      // zero slots of both halo buffers
-    float* hz = reinterpret_cast<float*>(bp + Cfg::OFF_H + (tid >> 3) * SK_HALO_BYTES);
-    hz[3 * SK_PLANE + (tid & 7)] = 0.f;
-  }
+  // halo pad columns 37..39 are read (times a zero weight) but never written by the copies: clear both buffers once
+  for (int i = tid; i < 2 * 3 * SK_PLANE; i += SK_THREADS) reinterpret_cast<float*>(bp + Cfg::OFF_H)[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ builders (+ MMA issue by thread 0)
-    if (tid == 0) {
-      mbar_expect_tx(smem_u32(&w_bar), Cfg::NB * SK_B_BYTES);
-      bulk_load_1d(b_addr, wtc, SK_B_BYTES, smem_u32(&w_bar));
-      if (X3) bulk_load_1d(b_addr + SK_B_BYTES, wtc + SK_B_BYTES / 4, SK_B_BYTES, smem_u32(&w_bar));
-    }
+  if (warp < 8) {
+    // ------------------------------------------------------------------ builders: two warpgroups
+    const int wg = warp >> 2, t = tid & 127;                           // t = pixel of the tile
     auto issue_halo = [&](int tile, int hb) {                         // cp.async the 21x37x3 halo of `tile` into buffer hb
-      const SkTile t = sk_tile(tile, tilesX, tilesY);
-      const float* xn = x + (size_t)t.n * xbs;
-      const int iy0 = 2 * t.oy0 - 3, ix0 = 2 * t.ox0 - 3;
+      const SkTile tl = sk_tile(tile, tilesX, tilesY);
+      const float* xn = x + (size_t)tl.n * xbs;
+      const int iy0 = 2 * tl.oy0 - 3, ix0 = 2 * tl.ox0 - 3;
       const uint32_t hbase = base + Cfg::OFF_H + (uint32_t)hb * SK_HALO_BYTES;
-      for (int i = tid; i < 3 * SK_HR * SK_HC; i += 128) {
+      for (int i = tid; i < 3 * SK_HR * SK_HC; i += 256) {
         const int ci = i / (SK_HR * SK_HC), rem = i - ci * (SK_HR * SK_HC);
         const int yy = rem / SK_HC, xx = rem - yy * SK_HC;
         const int iy = iy0 + yy, ix = ix0 + xx;
@@ -113,66 +106,51 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const int py = tid / SK_TW, px = tid % SK_TW;
-    const int pbase = (2 * py) * SK_HCP + 2 * px;
-    int it = 0, abuf_use = 0;                                          // tiles done by this CTA, A-buffer uses so far
+    const int py = t / SK_TW, px = t % SK_TW;
+    const int pbase = (2 * py) * SK_HCP + 2 * px;                     // even: every 8-float group is 8-byte aligned
+    const int swz = t & 7;
+    int it = 0, use = 0;                                               // tiles done by this CTA; uses of this group's A buffer
     int tile = blockIdx.x;
     if (tile < ntiles) issue_halo(tile, 0);
     for (; tile < ntiles; tile += gridDim.x, ++it) {
-      const int hb = it & 1, ab = it & 1;
+      const int hb = it & 1;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");            // this tile's halo has landed (for this thread)
+      asm volatile("bar.sync 1, 256;" ::: "memory");                  // ... for all builders, and nobody reads buffer hb^1 any more
       const int next = tile + gridDim.x;
-      if (next < ntiles) issue_halo(next, hb ^ 1);                     // prefetch (buffer hb^1 was last read two tiles ago)
-      else asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 1;" ::: "memory");            // this tile's halo has landed (for this thread)
-      asm volatile("bar.sync 1, 128;" ::: "memory");                  // ... and for all builders
-      const float* halo = reinterpret_cast<const float*>(bp + Cfg::OFF_H + (size_t)hb * SK_HALO_BYTES);
-      if (tid == 0) {                                                  // accumulator `ab` must have been drained
-        mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));
-        if (it == 0) mbar_wait(smem_u32(&w_bar), 0);
-      }
-      for (int kt = 0; kt < SK_KSTEPS; ++kt, ++abuf_use) {
-        const int buf = abuf_use & 1;
-        if (abuf_use >= 2) mbar_wait(smem_u32(&a_free[buf]), (uint32_t)(((abuf_use >> 1) - 1) & 1));   // MMAs that read it are done
-        float v[32];
+      if (next < ntiles) issue_halo(next, hb ^ 1);                     // prefetch under the build of this tile
+      const float* halo = reinterpret_cast<const float*>(bp + Cfg::OFF_H + (size_t)hb * SK_HALO_BYTES) + pbase;
+      float* at = reinterpret_cast<float*>(bp + (size_t)wg * SK_A_BYTES) + t * 32;
+#pragma unroll 1
+      for (int kt = wg; kt < SK_KSTEPS; kt += 2, ++use) {
+        if (use >= 1) mbar_wait(smem_u32(&a_free[wg]), (uint32_t)((use - 1) & 1));   // the MMAs that read this buffer are done
 #pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-          const int off = koff[kt * 32 + kk];
-          v[kk] = halo[off + (off < 3 * SK_PLANE ? pbase : 0)];
-        }
-        float* at = reinterpret_cast<float*>(bp + (size_t)buf * SK_A_BYTES);
+        for (int j = 0; j < 4; ++j) {
+          const int g = kt * 4 + j;                                    // (ci, r) group; groups 21..23 are K padding
+          float v[8];
+          if (g < SK_GROUPS) {
+            const float2* src = reinterpret_cast<const float2*>(halo + (g / 7) * SK_PLANE + (g % 7) * SK_HCP);
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const int o = tid * 32 + ((ch ^ (tid & 7)) << 2);
-          const float h0 = sk_tf32(v[ch * 4]), h1 = sk_tf32(v[ch * 4 + 1]), h2 = sk_tf32(v[ch * 4 + 2]), h3 = sk_tf32(v[ch * 4 + 3]);
-          *reinterpret_cast<float4*>(at + o) = make_float4(h0, h1, h2, h3);
-          if (X3) *reinterpret_cast<float4*>(at + A_LO / 4 + o) = make_float4(sk_tf32(v[ch * 4] - h0), sk_tf32(v[ch * 4 + 1] - h1),
-                                                                            sk_tf32(v[ch * 4 + 2] - h2), sk_tf32(v[ch * 4 + 3] - h3));
+            for (int q = 0; q < 4; ++q) { const float2 f = src[q]; v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int o = ((2 * j + c) ^ swz) << 2;
+            const float h0 = sk_tf32(v[c * 4]), h1 = sk_tf32(v[c * 4 + 1]), h2 = sk_tf32(v[c * 4 + 2]), h3 = sk_tf32(v[c * 4 + 3]);
+            *reinterpret_cast<float4*>(at + o) = make_float4(h0, h1, h2, h3);
+            if (X3) *reinterpret_cast<float4*>(at + A_LO / 4 + o) = make_float4(sk_tf32(v[c * 4] - h0), sk_tf32(v[c * 4 + 1] - h1),
+                                                                              sk_tf32(v[c * 4 + 2] - h2), sk_tf32(v[c * 4 + 3] - h3));
+          }
         }
         fence_async_smem();
-        tc_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) {
-          tc_fence_after();
-          const uint32_t a_addr = base + (uint32_t)buf * SK_A_BYTES;
-          const uint32_t d = tmem_base + (uint32_t)ab * 64;
-          const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(b_addr + (uint32_t)kt * 64 * 128);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_tf32(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), SK_IDESC, (kt | k) ? 1u : 0u);
-          if (X3) {
-            const uint64_t al = umma_desc_sw128(a_addr + A_LO), bl = umma_desc_sw128(b_addr + SK_B_BYTES + (uint32_t)kt * 64 * 128);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d, al + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), SK_IDESC, 1u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), SK_IDESC, 1u);
-          }
-          umma_commit(smem_u32(&a_free[buf]));
-          if (kt == SK_KSTEPS - 1) umma_commit(smem_u32(&acc_full[ab]));
-        }
+        mbar_arrive_local(smem_u32(&a_full[wg]));
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-  } else {
-    // ------------------------------------------------------------------ epilogue warps 4..7
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ epilogue warps 8..11
     const int q = warp & 3, m = q * 32 + (tid & 31);
     const int py = m / SK_TW, px = m % SK_TW;
     int it = 0;
@@ -190,7 +168,7 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
         tmem_ld32(tm + (uint32_t)(j * 32), u);
         if (j == 1) {
           tc_fence_before();
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[ab])) : "memory");
+          mbar_arrive_local(smem_u32(&acc_empty[ab]));
         }
         if (valid) {
           float* op = out + ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32;
@@ -202,6 +180,40 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
           }
         }
       }
+    }
+  } else if ((tid & 31) == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp 12, one lane)
+    mbar_expect_tx(smem_u32(&w_bar), Cfg::NB * SK_B_BYTES);
+    bulk_load_1d(b_addr, wtc, SK_B_BYTES, smem_u32(&w_bar));
+    if (X3) bulk_load_1d(b_addr + SK_B_BYTES, wtc + SK_B_BYTES / 4, SK_B_BYTES, smem_u32(&w_bar));
+    mbar_wait(smem_u32(&w_bar), 0);
+    int it = 0;
+    uint32_t full_phase[2] = {0, 0};
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));    // the epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)ab * 64;
+#pragma unroll
+      for (int kt = 0; kt < SK_KSTEPS; ++kt) {
+        const int buf = kt & 1;
+        mbar_wait(smem_u32(&a_full[buf]), full_phase[buf]);
+        full_phase[buf] ^= 1u;
+        tc_fence_after();
+        const uint32_t a_addr = base + (uint32_t)buf * SK_A_BYTES;
+        const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(b_addr + (uint32_t)kt * 64 * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_tf32(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), SK_IDESC, (kt | k) ? 1u : 0u);
+        if (X3) {
+          const uint64_t al = umma_desc_sw128(a_addr + A_LO), bl = umma_desc_sw128(b_addr + SK_B_BYTES + (uint32_t)kt * 64 * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(d, al + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), SK_IDESC, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(d, ad + (uint64_t)(2 * k), bl + (uint64_t)(2 * k), SK_IDESC, 1u);
+        }
+        umma_commit(smem_u32(&a_free[buf]));
+      }
+      umma_commit(smem_u32(&acc_full[ab]));
     }
   }
   tc_fence_before();
@@ -229,11 +241,11 @@ int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const 
   if (x3) {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<true>::SMEM);
     if (e != cudaSuccess) return (int)e;
-    stem_tc_kernel<true><<<grid, 256, SkCfg<true>::SMEM, s>>>(x, xbs, H, W, OH, OW, tx, ty, ntiles, wtc, b, out);
+    stem_tc_kernel<true><<<grid, SK_THREADS, SkCfg<true>::SMEM, s>>>(x, xbs, H, W, OH, OW, tx, ty, ntiles, wtc, b, out);
   } else {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<false>::SMEM);
     if (e != cudaSuccess) return (int)e;
-    stem_tc_kernel<false><<<grid, 256, SkCfg<false>::SMEM, s>>>(x, xbs, H, W, OH, OW, tx, ty, ntiles, wtc, b, out);
+    stem_tc_kernel<false><<<grid, SK_THREADS, SkCfg<false>::SMEM, s>>>(x, xbs, H, W, OH, OW, tx, ty, ntiles, wtc, b, out);
   }
   DH_CHECK_LAUNCH();
   return 0;

@@ -115,10 +115,16 @@ def kmajor_split(wt):
     return torch.stack([hi, lo])
 
 
-def stem_tc_image(wk):
-    """[160][64] stem filter (K padded) -> [hi | lo] images, each 5 K-step tiles of the swizzled B[n=co][k] operand."""
-    hi, lo = tf32_split(wk.double())
-    img = lambda w: torch.cat([swizzle128(w[kt * 32:(kt + 1) * 32].T.contiguous()) for kt in range(5)])
+def stem_tc_image(w147):
+    """[147][64] stem filter, K ordered (r, s, ci) like DH_W_STEM_W -> the tcgen05 stem's B operand: K re-ordered to
+    (ci, r, s8) — 21 groups of 8 (7 taps + a zero) padded to 192 — then [hi | lo] images of 6 K-step tiles of the
+    swizzled B[n=co][k]."""
+    w = w147.double().reshape(7, 7, 3, 64)                                   # [r][s][ci][co]
+    wk = torch.zeros(24, 8, 64, dtype=torch.float64)
+    wk[:21, :7] = w.permute(2, 0, 1, 3).reshape(21, 7, 64)                   # group = ci*7 + r
+    wk = wk.reshape(192, 64)
+    hi, lo = tf32_split(wk)
+    img = lambda m: torch.cat([swizzle128(m[kt * 32:(kt + 1) * 32].T.contiguous()) for kt in range(6)])
     return torch.cat([img(hi), img(lo)])
 
 
@@ -155,9 +161,7 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
             P[slot + "_WT"] = kmajor_split(_khwc(w).T)           # [2][Cout][KH*KW*Cin]: K-major B operand, TF32 hi / lo
 
     put_conv("DH_W_STEM", "resnet.conv1", "resnet.bn1")
-    wk = torch.zeros(160, 64, dtype=torch.float64)                       # K = 147 padded to 5 steps of 32
-    wk[:147] = P["DH_W_STEM_W"]
-    P["DH_W_STEM_WTC"] = stem_tc_image(wk)
+    P["DH_W_STEM_WTC"] = stem_tc_image(P["DH_W_STEM_W"])
     for li in (1, 2, 3):
         for bi in (0, 1):
             p = f"resnet.layer{li}.{bi}"
