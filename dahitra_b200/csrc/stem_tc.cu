@@ -2,18 +2,20 @@
 //
 // Replaces resnet.conv1 + bn1 + relu (reference models/networks.py:1120-1122, models/resnet.py:150-153).
 // GEMM view: D[128 pixels][64] = A[128][K] . Wt[64][K]^T.  C_in = 3 cannot feed a TMA/UMMA row directly, so the im2col
-// rows are assembled ON CHIP from a planar (NCHW) halo.  K is ordered (ci, r, s8): the 7 taps of one filter row of one
-// channel plus one zero-weight pad = 8 CONSECUTIVE halo floats = four 8-byte shared-memory loads and two 16-byte stores
+// rows are assembled ON CHIP from a planar (NCHW) halo.  K is ordered (ci, r, s8): one zero-weight pad (the TMA box must
+// start on a 16-byte boundary, one column left of the first tap) plus the 7 taps of one filter row of one channel
+// = 8 CONSECUTIVE halo floats = four 8-byte shared-memory loads and two 16-byte stores
 // into the K-major SWIZZLE_128B A tile, with no index table.  K = 21 groups x 8 = 168, padded to 192 = 6 K steps of 32.
 //
 // Persistent kernel, one CTA per SM, 13 warps:
 //   warps 0-3 / 4-7  two builder warpgroups; thread t of each owns pixel t of the 8x16 tile.  Group 0 builds the even
 //                    K steps into A buffer 0, group 1 the odd ones into buffer 1, so two steps are always in flight
-//                    (a single builder warp per scheduler is issue-latency bound: that was 3/4 of the old kernel's time).
-//                    All 256 builder threads also stage the 21x37x3 input halo of the NEXT tile with cp.async
-//                    (zero-filled outside the image; the only HBM read).
+//                    (a single builder warp per scheduler is issue-latency bound).
 //   warps 8-11       epilogue: drain the accumulator of the previous tile (two TMEM accumulators), bias + ReLU, NHWC stores.
 //   warp 12          one lane issues the tcgen05.mma's in K order as the A buffers fill (mbarriers a_full / a_free).
+//   warp 13          one lane fetches the 3 x 21 x 40 input halo of the next tile with ONE TMA box over the NCHW tensor
+//                    (no swizzle: the box lands as the planar [ci][row][40] halo; out-of-image pixels are zero-filled =
+//                    the conv padding; the only HBM read), double-buffered through halo_full / halo_free.
 // The filter image (pre-swizzled, 6 K-step tiles of 64x32; hi [+ lo]) is loaded once per CTA by one bulk copy.
 // X3: error-compensated 3xTF32 — A rows are written as TF32 hi + lo tiles, the filter comes pre-split.
 #include "tc_common.cuh"
@@ -23,30 +25,26 @@ using namespace dhtc;
 namespace {
 constexpr int SK_TH = 8, SK_TW = 16;                 // output patch
 constexpr int SK_HR = 2 * SK_TH + 5;                 // 21 halo rows
-constexpr int SK_HC = 2 * SK_TW + 5;                 // 37 halo cols
-constexpr int SK_HCP = 40;                           // padded row stride (cols 37..39 stay zero)
+constexpr int SK_HCP = 40;                           // halo cols fetched (37 needed; 8-float groups read up to col 37)
 constexpr int SK_PLANE = SK_HR * SK_HCP;             // 840 floats per channel
 constexpr int SK_KSTEPS = 6;                         // 192 / 32
 constexpr int SK_GROUPS = 21;                        // (ci, r) groups that carry data
 constexpr uint32_t SK_A_BYTES = 128 * 128;           // one A tile
 constexpr uint32_t SK_B_BYTES = SK_KSTEPS * 64 * 128;    // 48 KB filter image
-constexpr uint32_t SK_HALO_BYTES = 3 * SK_PLANE * 4; // 10080
+constexpr uint32_t SK_HALO_BYTES = 3 * SK_PLANE * 4; // 10080 (one TMA box)
+constexpr uint32_t SK_HALO_STRIDE = 10112;           // 128-byte aligned buffer pitch (TMA destination alignment)
 constexpr uint32_t SK_IDESC = umma_idesc_tf32(128, 64);
-constexpr int SK_THREADS = 13 * 32;
+constexpr int SK_THREADS = 14 * 32;
 
 template <bool X3> struct SkCfg {
   static constexpr uint32_t NA = X3 ? 4 : 2;                      // A tiles: [buf0 hi, buf1 hi, buf0 lo, buf1 lo]
   static constexpr uint32_t NB = X3 ? 2 : 1;                      // filter images: hi (+ lo)
   static constexpr uint32_t OFF_B = NA * SK_A_BYTES;
   static constexpr uint32_t OFF_H = OFF_B + NB * SK_B_BYTES;      // two halo buffers
-  static constexpr uint32_t SMEM = OFF_H + 2 * SK_HALO_BYTES + 1024;
+  static constexpr uint32_t SMEM = OFF_H + 2 * SK_HALO_STRIDE + 1024;
 };
 
 __device__ __forceinline__ float sk_tf32(float v) { return tf32_round(v); }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src, bool valid) {
-  const uint32_t n = valid ? 4u : 0u;                              // src-size 0 => the 4 destination bytes are zero-filled
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
-}
 
 struct SkTile { int n, oy0, ox0; };
 __device__ __forceinline__ SkTile sk_tile(int t, int tilesX, int tilesY) {
@@ -59,11 +57,11 @@ __device__ __forceinline__ SkTile sk_tile(int t, int tilesX, int tilesY) {
 
 template <bool X3>
 __global__ void __launch_bounds__(SK_THREADS, 1)
-stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH, int OW, int tilesX, int tilesY, int ntiles,
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tilesX, int tilesY, int ntiles,
                const float* __restrict__ wtc, const float* __restrict__ bias, float* __restrict__ out) {
   using Cfg = SkCfg<X3>;
   extern __shared__ uint8_t sk_raw[];
-  __shared__ __align__(8) uint64_t w_bar, a_full[2], a_free[2], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t w_bar, a_full[2], a_free[2], acc_full[2], acc_empty[2], halo_full[2], halo_free[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t base = (smem_u32(sk_raw) + 1023u) & ~1023u;
@@ -78,12 +76,12 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
       mbar_init(smem_u32(&a_free[i]), 1);
       mbar_init(smem_u32(&acc_full[i]), 1);
       mbar_init(smem_u32(&acc_empty[i]), 128);
+      mbar_init(smem_u32(&halo_full[i]), 1);
+      mbar_init(smem_u32(&halo_free[i]), 256);
     }
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 128);               // two 64-column accumulators
-  // halo pad columns 37..39 are read (times a zero weight) but never written by the copies: clear both buffers once
-  for (int i = tid; i < 2 * 3 * SK_PLANE; i += SK_THREADS) reinterpret_cast<float*>(bp + Cfg::OFF_H)[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -92,33 +90,14 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
   if (warp < 8) {
     // ------------------------------------------------------------------ builders: two warpgroups
     const int wg = warp >> 2, t = tid & 127;                           // t = pixel of the tile
-    auto issue_halo = [&](int tile, int hb) {                         // cp.async the 21x37x3 halo of `tile` into buffer hb
-      const SkTile tl = sk_tile(tile, tilesX, tilesY);
-      const float* xn = x + (size_t)tl.n * xbs;
-      const int iy0 = 2 * tl.oy0 - 3, ix0 = 2 * tl.ox0 - 3;
-      const uint32_t hbase = base + Cfg::OFF_H + (uint32_t)hb * SK_HALO_BYTES;
-      for (int i = tid; i < 3 * SK_HR * SK_HC; i += 256) {
-        const int ci = i / (SK_HR * SK_HC), rem = i - ci * (SK_HR * SK_HC);
-        const int yy = rem / SK_HC, xx = rem - yy * SK_HC;
-        const int iy = iy0 + yy, ix = ix0 + xx;
-        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-        cp_async4(hbase + (uint32_t)(ci * SK_PLANE + yy * SK_HCP + xx) * 4u, ok ? xn + ((size_t)ci * H + iy) * W + ix : xn, ok);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
     const int py = t / SK_TW, px = t % SK_TW;
     const int pbase = (2 * py) * SK_HCP + 2 * px;                     // even: every 8-float group is 8-byte aligned
     const int swz = t & 7;
     int it = 0, use = 0;                                               // tiles done by this CTA; uses of this group's A buffer
-    int tile = blockIdx.x;
-    if (tile < ntiles) issue_halo(tile, 0);
-    for (; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int hb = it & 1;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");            // this tile's halo has landed (for this thread)
-      asm volatile("bar.sync 1, 256;" ::: "memory");                  // ... for all builders, and nobody reads buffer hb^1 any more
-      const int next = tile + gridDim.x;
-      if (next < ntiles) issue_halo(next, hb ^ 1);                     // prefetch under the build of this tile
-      const float* halo = reinterpret_cast<const float*>(bp + Cfg::OFF_H + (size_t)hb * SK_HALO_BYTES) + pbase;
+      mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((it >> 1) & 1)); // this tile's halo has landed
+      const float* halo = reinterpret_cast<const float*>(bp + Cfg::OFF_H + (size_t)hb * SK_HALO_STRIDE) + pbase;
       float* at = reinterpret_cast<float*>(bp + (size_t)wg * SK_A_BYTES) + t * 32;
 #pragma unroll 1
       for (int kt = wg; kt < SK_KSTEPS; kt += 2, ++use) {
@@ -147,8 +126,8 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
         fence_async_smem();
         mbar_arrive_local(smem_u32(&a_full[wg]));
       }
+      mbar_arrive_local(smem_u32(&halo_free[hb]));                     // this thread's reads of the halo are done
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp < 12) {
     // ------------------------------------------------------------------ epilogue warps 8..11
     const int q = warp & 3, m = q * 32 + (tid & 31);
@@ -179,6 +158,19 @@ stem_tc_kernel(const float* __restrict__ x, long long xbs, int H, int W, int OH,
                                          fmaxf(__uint_as_float(u[c4 * 4 + 2]) + b.z, 0.f), fmaxf(__uint_as_float(u[c4 * 4 + 3]) + b.w, 0.f)));
           }
         }
+      }
+    }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ halo producer (warp 13, one lane)
+    if ((tid & 31) == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int hb = it & 1;
+        if (it >= 2) mbar_wait(smem_u32(&halo_free[hb]), (uint32_t)(((it >> 1) - 1) & 1));   // all builders left this buffer
+        const SkTile tl = sk_tile(tile, tilesX, tilesY);
+        const uint32_t bar = smem_u32(&halo_full[hb]);
+        mbar_expect_tx(bar, SK_HALO_BYTES);
+        tma_load_4d(base + Cfg::OFF_H + (uint32_t)hb * SK_HALO_STRIDE, &tmX, bar, 2 * tl.ox0 - 4, 2 * tl.oy0 - 3, 0, tl.n);   // x start must be 16-byte aligned: one column early
       }
     }
   } else if ((tid & 31) == 0) {
@@ -238,14 +230,23 @@ int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   dim3 grid((unsigned)(ntiles < sms ? ntiles : sms), 1, 1);
+  DH_REQUIRE(W % 4 == 0 && xbs % 4 == 0 && dh_aligned16(x), DH_E_ALIGN);           // TMA: 16-byte global strides / base
+  CUtensorMap tmX;                                                                  // NCHW input as (W, H, 3, N)
+  {
+    const unsigned long long dims[4] = {(unsigned long long)W, (unsigned long long)H, 3ull, (unsigned long long)N};
+    const unsigned long long strides[3] = {(unsigned long long)W * 4, (unsigned long long)H * W * 4, (unsigned long long)xbs * 4};
+    const unsigned box[4] = {(unsigned)SK_HCP, (unsigned)SK_HR, 3u, 1u};
+    const int rc = dh_encode_tiled_f32(&tmX, x, 4, dims, strides, box, false);
+    if (rc) return rc;
+  }
   if (x3) {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<true>::SMEM);
     if (e != cudaSuccess) return (int)e;
-    stem_tc_kernel<true><<<grid, SK_THREADS, SkCfg<true>::SMEM, s>>>(x, xbs, H, W, OH, OW, tx, ty, ntiles, wtc, b, out);
+    stem_tc_kernel<true><<<grid, SK_THREADS, SkCfg<true>::SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out);
   } else {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<false>::SMEM);
     if (e != cudaSuccess) return (int)e;
-    stem_tc_kernel<false><<<grid, SK_THREADS, SkCfg<false>::SMEM, s>>>(x, xbs, H, W, OH, OW, tx, ty, ntiles, wtc, b, out);
+    stem_tc_kernel<false><<<grid, SK_THREADS, SkCfg<false>::SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out);
   }
   DH_CHECK_LAUNCH();
   return 0;

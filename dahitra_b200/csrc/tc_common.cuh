@@ -3,6 +3,11 @@
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdio>
+
+// conv_tc2.cu: fp32 tiled tensor map through the driver entry point (no -lcuda); strides in bytes for dims 1..rank-1
+int dh_encode_tiled_f32(CUtensorMap* out, const void* ptr, int rank, const unsigned long long* dims,
+                        const unsigned long long* strides, const unsigned* box, bool swizzle128);
 
 namespace dhtc {
 
@@ -26,7 +31,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity), "r"(10000u) : "memory");
-    if (!done && ++spins > (1u << 19)) __trap();
+    if (!done && ++spins > (1u << 19)) {
+#ifdef DH_MBAR_DEBUG
+      printf("[mbar timeout] block %d thread %d bar smem+0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+#endif
+      __trap();
+    }
   } while (!done);
 }
 // ---- CTA-pair (cta_group::2) helpers: cluster rank / sync, remote mbarrier arrive, TMA signalling the leader's barrier

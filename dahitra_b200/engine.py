@@ -117,11 +117,11 @@ def kmajor_split(wt):
 
 def stem_tc_image(w147):
     """[147][64] stem filter, K ordered (r, s, ci) like DH_W_STEM_W -> the tcgen05 stem's B operand: K re-ordered to
-    (ci, r, s8) — 21 groups of 8 (7 taps + a zero) padded to 192 — then [hi | lo] images of 6 K-step tiles of the
+    (ci, r, s8) — 21 groups of 8 (a zero + 7 taps) padded to 192 — then [hi | lo] images of 6 K-step tiles of the
     swizzled B[n=co][k]."""
     w = w147.double().reshape(7, 7, 3, 64)                                   # [r][s][ci][co]
     wk = torch.zeros(24, 8, 64, dtype=torch.float64)
-    wk[:21, :7] = w.permute(2, 0, 1, 3).reshape(21, 7, 64)                   # group = ci*7 + r
+    wk[:21, 1:8] = w.permute(2, 0, 1, 3).reshape(21, 7, 64)                  # group = ci*7 + r; slot 0 = the alignment pad
     wk = wk.reshape(192, 64)
     hi, lo = tf32_split(wk)
     img = lambda m: torch.cat([swizzle128(m[kt * 32:(kt + 1) * 32].T.contiguous()) for kt in range(6)])

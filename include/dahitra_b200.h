@@ -97,7 +97,7 @@ enum dh_weight_slot {
    * (DH_DECTC_LAYER_FLOATS), "swz" = K-major SWIZZLE_128B image of B[n][k] (W1f: n=hidden, k=channel, LN2
    * gamma folded; W2: n=channel, k=hidden); cbA/cbM = cumulative biases after the attention / MLP of the layer */
   DH_W_LV5_DECTC, DH_W_LV4_DECTC, DH_W_LV3_DECTC,
-  DH_W_STEM_WTC,   /* stem filter for the tcgen05 stem: [hi, lo] x 6 K-step tiles of B[n=co 64][k 32] swz; K ordered (ci, r, s8): 21 groups of 7 taps + 1 zero, padded to 192 */
+  DH_W_STEM_WTC,   /* stem filter for the tcgen05 stem: [hi, lo] x 6 K-step tiles of B[n=co 64][k 32] swz; K ordered (ci, r, s8): 21 groups of 1 zero + 7 taps, padded to 192 */
   DH_W_COUNT
 };
 
