@@ -202,9 +202,9 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   // phases add up instead of overlapping.  Warpgroup g may enter an ALU phase only after warpgroup g-TURN_D has left
   // its own; the rest of its chain (tcgen05.st drain, MMAs, commit, tcgen05.ld) runs while others hold the ALUs.
   constexpr int TURN_D = PDT_TURN_D;
-  auto turn_wait = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(5 + wg) : "memory"); };
-  auto turn_pass = [&]() { asm volatile("bar.arrive %0, 256;" ::"r"(5 + ((wg + TURN_D) & 3)) : "memory"); };
-  if (wg >= G - TURN_D) turn_pass();                                   // the first TURN_D warpgroups start immediately
+  auto turn_wait = [&]() { if (TURN_D) asm volatile("bar.sync %0, 256;" ::"r"(5 + wg) : "memory"); };
+  auto turn_pass = [&]() { if (TURN_D) asm volatile("bar.arrive %0, 256;" ::"r"(5 + ((wg + TURN_D) & 3)) : "memory"); };
+  if (TURN_D && wg >= G - TURN_D) turn_pass();                         // the first TURN_D warpgroups start immediately
 
   // ---- x (+ pos) -> registers and TMEM
   float xr[32];
