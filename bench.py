@@ -317,7 +317,7 @@ def run_native(a, wl):
                     unit="TFLOP/s", frac=achieved / peaks["bf16_tflops_sustained"])
         # what the tensor pipe actually executes: kind::tf32 runs at half the bf16 rate, and 3xTF32 issues three MMAs
         # per algorithmic product
-        mult = 3 if (net._engine.flags & 2) else 1
+        mult = (2 if (net._engine.flags & 512) else 3) if (net._engine.flags & 2) else 1    # TF32-equivalent MMAs per product
         roof["tensor_pipe"] = dict(mma_tflops=achieved * mult, mmas_per_product=mult,
                                    tf32_peak_tflops=peaks["bf16_tflops_sustained"] / 2,
                                    frac=achieved * mult / (peaks["bf16_tflops_sustained"] / 2),
@@ -349,7 +349,8 @@ def run_native(a, wl):
                    sample=f"oracle port (torch CPU fp32), {cp} pairs per call, mean of 3 calls after 1 warm-up ({sec:.2f} s/call)")
     line = dict(metric="image-pairs/sec", value=value, unit="pairs/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype={"fp32": "f32", "tf32": "tf32", "tf32_fast": "tf32", "tf32x3": "tf32x3 (error-compensated, fp32-grade)"}.get(mode_name, "f32/tf32"),
+                dtype={"fp32": "f32", "tf32": "tf32", "tf32_fast": "tf32", "tf32x3": "tf32x3 (error-compensated, fp32-grade)",
+                       "tf32x3_pure": "tf32x3 (error-compensated, fp32-grade)"}.get(mode_name, "f32/tf32"),
                 data="synthetic",
                 config=dict(workload=wl["desc"], H=H, W=W, pairs_per_gpu=Bp, global_pairs_per_step=world * Bp,
                             sharding="by image pair, one process per GPU, no collective",

@@ -57,7 +57,7 @@ int dh_launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
 bool dh_conv_tc_eligible(const ConvArgs& a);
 int dh_launch_conv_tc(const ConvArgs& a, cudaStream_t s);
 bool dh_conv_tc2_eligible(const ConvArgs& a);                     // stride-1 halo-reuse kernel (conv_tc2.cu)
-int dh_launch_conv_tc2(const ConvArgs& a, int x3, int cg, cudaStream_t s);
+int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s);
 int dh_launch_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* b, float* out, cudaStream_t s);
 int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const float* wtc, const float* b, float* out, int x3,
                       cudaStream_t s);

@@ -17,6 +17,13 @@
 // each K step issues A_hi.B_hi + A_lo.B_hi + A_hi.B_lo.  The split costs one smem pass per chunk, amortised
 // over 9 taps.
 //
+// XM = 2 ("3xTF32 with bf16 corrections"): the two correction products A_lo.B_hi and A_hi.B_lo only have to be right to
+// ~8 bits (they are 2^-11 of the main term), so they run as kind::f16 BF16 MMAs — K = 16 per instruction, i.e. half the
+// MMAs and half the operand bytes of their TF32 form.  The splitter then writes, next to the TF32-rounded fp32 halo, two
+// bf16 halos (bf16(a) and bf16(a - tf32(a)), 64-byte pixel rows in the SWIZZLE_64B pattern — the shifted-window trick
+// works there too, tools/umma_bf16_probe.cu), and the filter ring carries bf16(w) and bf16(w - tf32(w)) tiles.
+// Per (tap, 32-channel chunk): 4 TF32 + 2 + 2 BF16 MMAs instead of 12.
+//
 // Stride 2 (SD = 2; resnet layer2.0): the input is read as its four 2x2 phase images P_ab(y,x) = X(2y+a, 2x+b),
 // each fetched by a TMA box with elementStrides {1,2,2,1}.  A 3x3 stride-2 tap (r,s) is the stride-1 tap of phase
 // (r odd ? 0 : 1, s odd ? 0 : 1) at offset (r == 0 ? -1 : 0, s == 0 ? -1 : 0), so every (chunk, phase) pair is one
@@ -36,6 +43,7 @@ namespace {
 constexpr int T2_TH = 16, T2_TW = 8;                    // output patch
 constexpr int T2_HW = T2_TW + 2, T2_HH = T2_TH + 2;     // halo 10 x 18
 constexpr uint32_t T2_HALO_STRIDE = 23552;              // 1024-aligned
+constexpr uint32_t T2_HALO16_BYTES = T2_HW * T2_HH * 64; // one bf16 halo (11520 B); two of them share a "lo" buffer
 
 struct T2Args {
   const float* bias; const float* res; float* out;
@@ -47,7 +55,8 @@ struct T2Args {
   uint32_t halo_bytes;
 };
 
-template <int NT, bool X3, int CG = 1> struct T2Cfg {
+template <int NT, int XM, int CG = 1> struct T2Cfg {
+  static constexpr bool X3 = XM != 0;              // error-compensated modes: 1 = three TF32 MMAs, 2 = TF32 + two BF16
   // Persistent kernel, one CTA per SM.  Pipeline depth is sized so that the MMA warp always has >= ~1500 cycles of
   // operands in flight (L2 latency under load): the smaller the N tile, the faster a stage is consumed, so the more
   // halo buffers (HB) and filter stages it gets.  A stage holds TPS filter taps so the issuing thread waits /
@@ -57,7 +66,8 @@ template <int NT, bool X3, int CG = 1> struct T2Cfg {
   static constexpr int STAGES1 = X3 ? (NT == 128 ? 3 : (NT == 64 ? 6 : 4)) : (NT == 128 ? 3 : (NT == 64 ? 5 : 8));
   static constexpr int STAGES = CG == 2 ? (2 * STAGES1 > 8 ? 8 : 2 * STAGES1) : STAGES1;   // CTA pair: half-size B tiles
   static constexpr uint32_t B_TILE = (NT / CG) * 128;           // a CTA of a pair holds N/2 rows of B
-  static constexpr uint32_t B_TAP = B_TILE * (X3 ? 2 : 1);      // hi (+ lo) tile of one tap
+  static constexpr uint32_t B_TAP = B_TILE * (X3 ? 2 : 1);      // hi (+ lo) tile of one tap; XM = 2: [fp32 hi][bf16 hi][bf16 lo]
+  static constexpr uint32_t IDESC16 = umma_idesc_bf16(128 * CG, NT);
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
   static constexpr uint32_t HALO_BUFS = X3 ? 2 * HB : HB;       // [hi 0..HB-1][lo 0..HB-1]
   static constexpr uint32_t SMEM = HALO_BUFS * T2_HALO_STRIDE + STAGES * B_STAGE + 1024;
@@ -105,11 +115,13 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, const T2Args& e, int N
   return t;
 }
 
-template <int NT, bool X3, int KS, int SD, int CG>
-__global__ void __launch_bounds__(T2Cfg<NT, X3, CG>::THREADS, 1)
+template <int NT, int XM, int KS, int SD, int CG>
+__global__ void __launch_bounds__(T2Cfg<NT, XM, CG>::THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmB, const T2Args e) {
-  using Cfg = T2Cfg<NT, X3, CG>;
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB16, const T2Args e) {
+  using Cfg = T2Cfg<NT, XM, CG>;
+  constexpr bool X3 = XM != 0;
+  static_assert(XM != 2 || CG == 1, "bf16 corrections are implemented for single-CTA tiles");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t2_raw[];
   constexpr int HB = Cfg::HB;
@@ -209,6 +221,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               if (CG == 2 && rank == 1) {
                 tma_load_2d_2sm(dst, &tmB, lbar, kcol, nrow);
                 if (X3) tma_load_2d_2sm(dst + Cfg::B_TILE, &tmB, lbar, kcol, e.Cout + nrow);
+              } else if (XM == 2) {
+                tma_load_2d(dst, &tmB, bar, kcol, nrow);                                           // fp32 (TF32-rounded) filter
+                tma_load_2d(dst + Cfg::B_TILE, &tmB16, bar, kcol, nrow);                           // bf16(w)
+                tma_load_2d(dst + Cfg::B_TILE + Cfg::B_TILE / 2, &tmB16, bar, kcol, e.Cout + nrow); // bf16(w - tf32(w))
               } else {
                 tma_load_2d(dst, &tmB, bar, kcol, nrow);
                 if (X3) tma_load_2d(dst + Cfg::B_TILE, &tmB, bar, kcol, e.Cout + nrow);  // lo rows follow the hi rows
@@ -262,7 +278,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const uint64_t bh = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) mma(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (cc | i | k) ? 1u : 0u);
-                if (X3) {
+                if (XM == 2) {
+                  // corrections in bf16: A = the bf16 halos (64-byte pixel rows), B = the bf16 filter tiles; K = 16 per MMA
+                  constexpr uint32_t SBO16 = (uint32_t)HALO_W * 64u;
+                  const uint32_t px = (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;
+                  const uint32_t h16 = h_hi + (uint32_t)HB * T2_HALO_STRIDE;           // [bf16(a)][bf16(a - tf32(a))]
+                  const uint64_t a_hi16 = umma_desc_sw64(h16 + px, SBO16), a_lo16 = umma_desc_sw64(h16 + T2_HALO16_BYTES + px, SBO16);
+                  const uint32_t b16 = b_stage + (uint32_t)tt * Cfg::B_TAP + Cfg::B_TILE;
+                  const uint64_t b_hi16 = umma_desc_sw64(b16, 512u), b_lo16 = umma_desc_sw64(b16 + Cfg::B_TILE / 2, 512u);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, a_lo16 + (uint64_t)(2 * k), b_hi16 + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, a_hi16 + (uint64_t)(2 * k), b_lo16 + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
+                } else if (X3) {
                   const uint64_t al = al0 + (uint64_t)shift16;
                   const uint64_t bl = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP + Cfg::B_TILE);
 #pragma unroll
@@ -327,6 +355,36 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g / HB) & 1));
         float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)hb * T2_HALO_STRIDE);
         float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)(HB + hb) * T2_HALO_STRIDE);
+        if (XM == 2) {
+          // item = (pixel q, pair of adjacent 16-byte chunks): 8 channels.  The TMA wrote chunk c of pixel q at position
+          // c ^ (q & 7), so positions (2j, 2j+1) hold the logical chunks (2j ^ r, 2j ^ r ^ 1), r = q & 7: logical 8-channel
+          // group j ^ (r >> 1), halves swapped when r is odd.  Each group becomes one 16-byte chunk of the pixel's 64-byte
+          // bf16 row, stored at chunk position group ^ ((row address >> 7) & 3)  (SWIZZLE_64B on absolute address bits).
+          const uint32_t lo_base = base + (uint32_t)(HB + hb) * T2_HALO_STRIDE;
+          uint8_t* lo_ptr = reinterpret_cast<uint8_t*>(lo);
+          for (int i = tI; i < nvec / 2; i += 128) {
+            const int q = i >> 2, j = i & 3, r = q & 7;
+            float4 v0 = hi[q * 8 + 2 * j], v1 = hi[q * 8 + 2 * j + 1];
+            const float4 h0 = make_float4(tf32_rna(v0.x), tf32_rna(v0.y), tf32_rna(v0.z), tf32_rna(v0.w));
+            const float4 h1 = make_float4(tf32_rna(v1.x), tf32_rna(v1.y), tf32_rna(v1.z), tf32_rna(v1.w));
+            hi[q * 8 + 2 * j] = h0;
+            hi[q * 8 + 2 * j + 1] = h1;
+            uint4 a16, l16;                                   // bf16(a), bf16(a - tf32(a)) in position order
+            a16.x = pack_bf16x2(v0.x, v0.y); a16.y = pack_bf16x2(v0.z, v0.w); a16.z = pack_bf16x2(v1.x, v1.y); a16.w = pack_bf16x2(v1.z, v1.w);
+            l16.x = pack_bf16x2(v0.x - h0.x, v0.y - h0.y); l16.y = pack_bf16x2(v0.z - h0.z, v0.w - h0.w);
+            l16.z = pack_bf16x2(v1.x - h1.x, v1.y - h1.y); l16.w = pack_bf16x2(v1.z - h1.z, v1.w - h1.w);
+            if (r & 1) {                                      // position 2j holds the ODD logical chunk: swap the halves
+              a16 = make_uint4(a16.z, a16.w, a16.x, a16.y);
+              l16 = make_uint4(l16.z, l16.w, l16.x, l16.y);
+            }
+            const uint32_t grp = (uint32_t)(j ^ (r >> 1));
+            const uint32_t row_hi = (uint32_t)q * 64u, row_lo = T2_HALO16_BYTES + (uint32_t)q * 64u;
+            const uint32_t off_hi = row_hi + ((grp ^ (((lo_base + row_hi) >> 7) & 3u)) << 4);
+            const uint32_t off_lo = row_lo + ((grp ^ (((lo_base + row_lo) >> 7) & 3u)) << 4);
+            *reinterpret_cast<uint4*>(lo_ptr + off_hi) = a16;
+            *reinterpret_cast<uint4*>(lo_ptr + off_lo) = l16;
+          }
+        } else
         for (int i = tI; i < nvec; i += 128) {
           const float4 v = hi[i];
           const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
@@ -366,7 +424,7 @@ EncodeTiledFn get_encode2() {
   return fn;
 }
 struct Key2 {
-  const void* ptr; int d0, d1, d2, d3, b1, b2;
+  const void* ptr; int d0, d1, d2, d3, b1, b2;   // b2 also encodes element stride / bf16 (see get_map2)
   bool operator==(const Key2& o) const { return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && b1 == o.b1 && b2 == o.b2; }
 };
 struct Key2Hash {
@@ -380,8 +438,10 @@ std::mutex g_mu2;
 std::unordered_map<Key2, CUtensorMap, Key2Hash> g_maps2;
 
 // b1, b2: box extent in ELEMENTS FETCHED along dims 1, 2; es = element stride along those dims (1 or 2)
-int get_map2(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d2, int d3, int b1, int b2, int es = 1) {
-  Key2 key{ptr, d0, d1, d2, d3, b1 * es, b2 * es + (es - 1)};
+// bf16 = true: a [d1][d0] bf16 matrix read in {32, b1} boxes with SWIZZLE_64B (the filter's bf16 hi / lo images)
+int get_map2(CUtensorMap* out, const void* ptr, int rank, int d0, int d1, int d2, int d3, int b1, int b2, int es = 1,
+             bool bf16 = false) {
+  Key2 key{ptr, d0, d1, d2, d3, b1 * es, b2 * es + (es - 1) + (bf16 ? 1000 : 0)};
   {
     std::lock_guard<std::mutex> lk(g_mu2);
     auto it = g_maps2.find(key);
@@ -390,12 +450,14 @@ int get_map2(CUtensorMap* out, const float* ptr, int rank, int d0, int d1, int d
   EncodeTiledFn enc = get_encode2();
   if (!enc) return DH_E_VARIANT;
   cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)d3};
-  cuuint64_t strides[3] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4, (cuuint64_t)d0 * d1 * d2 * 4};
+  const cuuint64_t esz = bf16 ? 2 : 4;
+  cuuint64_t strides[3] = {(cuuint64_t)d0 * esz, (cuuint64_t)d0 * d1 * esz, (cuuint64_t)d0 * d1 * d2 * esz};
   cuuint32_t box[4] = {32, (cuuint32_t)(b1 * es), (cuuint32_t)(b2 * es), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   CUtensorMap m;
-  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)ptr, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUresult r = enc(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                         (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return DH_E_SHAPE;
   {
@@ -425,14 +487,15 @@ int dh_encode_tiled_f32(CUtensorMap* out, const void* ptr, int rank, const unsig
 }
 
 namespace {
-template <int NT, bool X3, int KS, int SD, int CG>
-int launch2k(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
-  using Cfg = T2Cfg<NT, X3, CG>;
-  auto kern = conv_tc2_kernel<NT, X3, KS, SD, CG>;
+template <int NT, int XM, int KS, int SD, int CG>
+int launch2k(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const CUtensorMap& B16, const T2Args& e, dim3 grid,
+             cudaStream_t s) {
+  using Cfg = T2Cfg<NT, XM, CG>;
+  auto kern = conv_tc2_kernel<NT, XM, KS, SD, CG>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (err != cudaSuccess) return (int)err;
   if (CG == 1) {
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, e);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, B16, e);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(Cfg::THREADS, 1, 1); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
@@ -440,31 +503,26 @@ int launch2k(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    err = cudaLaunchKernelEx(&cfg, kern, A0, A1, Bm, e);
+    err = cudaLaunchKernelEx(&cfg, kern, A0, A1, Bm, B16, e);
     if (err != cudaSuccess) return (int)err;
   }
   DH_CHECK_LAUNCH();
   return 0;
 }
-template <int NT, bool X3, int CG>
-int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
+template <int NT, int XM, int CG>
+int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const CUtensorMap& B16, const T2Args& e, dim3 grid,
+            cudaStream_t s) {
   if (e.stride == 2)
-    return e.ntaps == 9 ? launch2k<NT, X3, 3, 2, CG>(A0, A1, Bm, e, grid, s) : launch2k<NT, X3, 1, 2, CG>(A0, A1, Bm, e, grid, s);
-  return e.ntaps == 9 ? launch2k<NT, X3, 3, 1, CG>(A0, A1, Bm, e, grid, s) : launch2k<NT, X3, 1, 1, CG>(A0, A1, Bm, e, grid, s);
+    return e.ntaps == 9 ? launch2k<NT, XM, 3, 2, CG>(A0, A1, Bm, B16, e, grid, s) : launch2k<NT, XM, 1, 2, CG>(A0, A1, Bm, B16, e, grid, s);
+  return e.ntaps == 9 ? launch2k<NT, XM, 3, 1, CG>(A0, A1, Bm, B16, e, grid, s) : launch2k<NT, XM, 1, 1, CG>(A0, A1, Bm, B16, e, grid, s);
 }
-template <int CG>
-int launch2n(int NT, int x3, const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const T2Args& e, dim3 grid, cudaStream_t s) {
-  if (x3) {
-    switch (NT) {
-      case 128: return launch2<128, true, CG>(A0, A1, Bm, e, grid, s);
-      case 64: return launch2<64, true, CG>(A0, A1, Bm, e, grid, s);
-      default: return launch2<32, true, CG>(A0, A1, Bm, e, grid, s);
-    }
-  }
+template <int XM, int CG>
+int launch2n(int NT, const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const CUtensorMap& B16, const T2Args& e,
+             dim3 grid, cudaStream_t s) {
   switch (NT) {
-    case 128: return launch2<128, false, CG>(A0, A1, Bm, e, grid, s);
-    case 64: return launch2<64, false, CG>(A0, A1, Bm, e, grid, s);
-    default: return launch2<32, false, CG>(A0, A1, Bm, e, grid, s);
+    case 128: return launch2<128, XM, CG>(A0, A1, Bm, B16, e, grid, s);
+    case 64: return launch2<64, XM, CG>(A0, A1, Bm, B16, e, grid, s);
+    default: return launch2<32, XM, CG>(A0, A1, Bm, B16, e, grid, s);
   }
 }
 }  // namespace
@@ -480,8 +538,10 @@ bool dh_conv_tc2_eligible(const ConvArgs& a) {
 }
 
 // a.wt: [2][Cout][K] = TF32-rounded filter (hi) followed by its TF32-rounded remainder (lo); x3 uses both.
+// xm: 0 = 1xTF32, 1 = 3xTF32 (three TF32 MMAs), 2 = 3xTF32 with the two correction products in bf16.
 // cg = 2: CTA pairs (tcgen05 cta_group::2): M = 256 per MMA, each CTA loads and reads only half of the filter tile
-int dh_launch_conv_tc2(const ConvArgs& a, int x3, int cg, cudaStream_t s) {
+// a.wt: [hi fp32 Cout*K][lo fp32 Cout*K][bf16(w) Cout*K][bf16(w - hi) Cout*K]  (engine.kmajor_split)
+int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
   DH_REQUIRE(a.in0 && a.wt && a.out, DH_E_NULL);
   DH_REQUIRE(a.C1 == 0 || a.in1, DH_E_NULL);
   DH_REQUIRE(dh_conv_tc2_eligible(a), DH_E_SHAPE);
@@ -494,9 +554,14 @@ int dh_launch_conv_tc2(const ConvArgs& a, int x3, int cg, cudaStream_t s) {
   int rc = get_map2(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, hw, hh, a.stride);
   if (rc) return rc;
   if (a.C1) { rc = get_map2(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, hw, hh, a.stride); if (rc) return rc; } else A1 = A0;
-  cg = (cg == 2) ? 2 : 1;
+  cg = (cg == 2 && xm != 2) ? 2 : 1;
   rc = get_map2(&Bm, a.wt, 2, K, 2 * a.Cout, 1, 1, NT / cg, 1);  // rows [0,Cout) = hi, [Cout,2Cout) = lo
   if (rc) return rc;
+  CUtensorMap B16 = Bm;
+  if (xm == 2) {                                                 // bf16 images follow the two fp32 ones
+    rc = get_map2(&B16, a.wt + (size_t)2 * a.Cout * K, 2, K, 2 * a.Cout, 1, 1, NT, 1, 1, true);
+    if (rc) return rc;
+  }
   T2Args e;
   e.bias = a.bias; e.res = a.res; e.out = a.out;
   e.OH = a.inH / a.stride; e.OW = a.inW / a.stride; e.Cout = a.Cout; e.relu = a.relu; e.stride = a.stride;
@@ -513,8 +578,9 @@ int dh_launch_conv_tc2(const ConvArgs& a, int x3, int cg, cudaStream_t s) {
   if (cg == 2) {
     const int pairs = sms / 2;
     dim3 grid((unsigned)(2 * (e.ntiles < pairs ? e.ntiles : pairs)), 1, 1);       // persistent: one CTA pair per TPC
-    return launch2n<2>(NT, x3, A0, A1, Bm, e, grid, s);
+    return xm ? launch2n<1, 2>(NT, A0, A1, Bm, B16, e, grid, s) : launch2n<0, 2>(NT, A0, A1, Bm, B16, e, grid, s);
   }
   dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);          // persistent: one CTA per SM
-  return launch2n<1>(NT, x3, A0, A1, Bm, e, grid, s);
+  if (xm == 2) return launch2n<2, 1>(NT, A0, A1, Bm, B16, e, grid, s);
+  return xm ? launch2n<1, 1>(NT, A0, A1, Bm, B16, e, grid, s) : launch2n<0, 1>(NT, A0, A1, Bm, B16, e, grid, s);
 }

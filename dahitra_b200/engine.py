@@ -23,12 +23,16 @@ LEVELS = ((5, 256, 4, 4), (4, 128, 4, 4), (3, 64, 8, 8))   # (k, trunk channels,
 
 DH_VARIANT_LEVIR, DH_VARIANT_XBD = 0, 1
 DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC, DH_FLAG_STEM_TC, DH_FLAG_DEC_TC_X3 = 1, 2, 4, 8, 16, 32
+DH_FLAG_CONV_TC_V1, DH_FLAG_CONV_TC_2CTA, DH_FLAG_SERIAL, DH_FLAG_TC_X3_BF16 = 64, 128, 256, 512
 MODES = {
     "fp32": 0,                                             # every contraction in fp32 FMA (strict)
     "fp32_tcdec": DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,      # strict + the 3xTF32 (fp32-grade) tensor-core decoder
     # fp32-grade accuracy on the tensor cores: error-compensated 3xTF32 for every convolution (stride 2 included), the
     # 7x7 stem and the pixel decoder
-    "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
+    # (the convolutions' two correction products run as BF16 MMAs: same accuracy, a third fewer tensor-core cycles)
+    "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC
+              | DH_FLAG_DEC_TC_X3,
+    "tf32x3_pure": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32_fast": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC,   # 1xTF32 decoder too
 }
@@ -109,10 +113,16 @@ def tf32_split(x):
 
 
 def kmajor_split(wt):
-    """K-major filter [Cout][K] (float64) -> [2][Cout][K]: TF32-rounded values, then their TF32-rounded remainders.
-    The 1xTF32 kernels read only the first half; the 3xTF32 kernels use both (B_hi, B_lo)."""
-    hi, lo = tf32_split(wt.contiguous())
-    return torch.stack([hi, lo])
+    """K-major filter [Cout][K] (float64) -> float32 [3][Cout][K]:
+      plane 0  TF32-rounded values (B_hi; all the 1xTF32 kernels read)
+      plane 1  their TF32-rounded remainders (B_lo of the 3xTF32 kernels)
+      plane 2  raw bits of a bf16 [2][Cout][K] array: bf16(w) and bf16(w - B_hi), the filter operands of the two
+               correction products when they run as BF16 MMAs (DH_FLAG_TC_X3_BF16)."""
+    wt = wt.contiguous().double()
+    hi, lo = tf32_split(wt)
+    b16 = torch.stack([wt, wt - hi]).to(torch.float32).to(torch.bfloat16).contiguous()       # [2][Cout][K] bf16
+    packed = b16.view(torch.int16).reshape(-1).view(torch.float32).reshape(wt.shape)          # same bytes as [Cout][K] fp32
+    return torch.cat([torch.stack([hi, lo]).to(torch.float32), packed[None]])
 
 
 def stem_tc_image(w147):

@@ -55,6 +55,7 @@ extern "C" {
 #define DH_FLAG_CONV_TC_V1  64  /* with CONV_TC: force the per-tap TMA kernel (conv_tc.cu) instead of the halo-reuse one */
 #define DH_FLAG_CONV_TC_2CTA 128 /* with CONV_TC: CTA pairs (tcgen05 cta_group::2, clusters of 2): M = 256 per MMA, half the filter traffic per SM */
 #define DH_FLAG_SERIAL      256 /* keep every launch on the caller's stream (no fork of levels 4 / 3 onto the library's side streams) */
+#define DH_FLAG_TC_X3_BF16  512 /* with TC_3XTF32: the two correction products of every conv as BF16 MMAs (half their cost) */
 #define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC | DH_FLAG_STEM_TC)   /* the "tf32" mode */
 
 /* ---- prepared-weight table -------------------------------------------------------------------
@@ -81,8 +82,9 @@ enum dh_weight_slot {
   DH_W_CL20A_W, DH_W_CL20A_B,                      /* conv_layer2_0.0 + BN: [9*128][128],[128] */
   DH_W_CL20B_W, DH_W_CL20B_B,                      /* conv_layer2_0.3: [9*128][32],[32] */
   DH_W_CLS_W, DH_W_CLS_B,                          /* classifier: [9][output_nc][32], [output_nc] */
-  /* K-major ("[Cout][KH*KW*Cin]") copies of the filters the tcgen05 kernel takes as its B operand
-   * (stride-1 convolutions with Cin a multiple of 32); same values as the matching _W / _DECODE slot */
+  /* K-major copies of the filters the tcgen05 kernels take as their B operand (Cin a multiple of 32); same values
+   * as the matching _W / _DECODE slot.  Layout: float [3][Cout][KH*KW*Cin] = TF32-rounded w | TF32-rounded remainder |
+   * raw bits of a bf16 [2][Cout][K] array {bf16(w), bf16(w - plane 0)} (DH_FLAG_TC_X3_BF16) */
   DH_W_L1_0_C1_WT, DH_W_L1_0_C2_WT, DH_W_L1_1_C1_WT, DH_W_L1_1_C2_WT,
   DH_W_L2_0_C2_WT, DH_W_L2_1_C1_WT, DH_W_L2_1_C2_WT,
   DH_W_L3_0_C1_WT, DH_W_L3_0_C2_WT, DH_W_L3_0_DS_WT, DH_W_L3_1_C1_WT, DH_W_L3_1_C2_WT,
