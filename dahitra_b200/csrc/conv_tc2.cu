@@ -70,7 +70,8 @@ template <int NT, int XM, int CG = 1> struct T2Cfg {
   static constexpr uint32_t IDESC16 = umma_idesc_bf16(128 * CG, NT);
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
   static constexpr uint32_t HALO_BUFS = X3 ? 2 * HB : HB;       // [hi 0..HB-1][lo 0..HB-1]
-  static constexpr uint32_t SMEM = HALO_BUFS * T2_HALO_STRIDE + STAGES * B_STAGE + 1024;
+  static constexpr uint32_t EPI_OFF = HALO_BUFS * T2_HALO_STRIDE + STAGES * B_STAGE;   // epilogue staging: 4 warps x 4 KB
+  static constexpr uint32_t SMEM = EPI_OFF + 4 * 4096 + 1024;
   static constexpr int THREADS = X3 ? 352 : 224;                // + 4 splitter warps
   static constexpr uint32_t IDESC = umma_idesc_tf32(128 * CG, NT);
   static constexpr uint32_t TMEM_COLS = (2 * NT < 32) ? 32 : 2 * NT;   // two accumulators
@@ -310,19 +311,41 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
     }
   } else if (warp < 6) {                                        // ---------------- epilogue (warps 2..5)
+    // Each thread owns one accumulator row (pixel), but a store instruction in which every lane writes 16 bytes of a
+    // different 128-byte line costs 32 L1 passes — cycles taken from the same data pipe that feeds the MMA operands.
+    // So every 32-channel slab goes through a per-warp shared-memory transpose: rows in (8 conflict-free 16-byte
+    // stores), then 8 lanes per pixel row out, 4 whole 128-byte lines per instruction for the residual read and the store.
     const int q = warp & 3;
     const int m = q * 32 + lane;
+    float* stage = reinterpret_cast<float*>(base_ptr + Cfg::EPI_OFF + (size_t)q * 4096);   // [32 rows][8 chunks ^ (row & 7)][4]
+    const int c8 = lane & 7, r8 = lane >> 3;                    // phase 2: lane -> (chunk of 4 channels, row within a group of 4)
     int it = 0;
     for (int tile = w0; tile < e.ntiles; tile += wstep, ++it) {
       const TileCoord t = tile_coord(tile, e, NT, CG, rank);
       const int ab = it & 1;
-      const int oy = t.oy0 + m / T2_TW, ox = t.ox0 + m % T2_TW;
-      const bool valid = (oy < e.OH) && (ox < e.OW) && (t.n < e.N);
       mbar_wait(smem_u32(&acc_full[ab]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const size_t row = ((size_t)(t.n * e.OH + oy) * e.OW + ox) * e.Cout + t.n0;
+      // phase-2 coordinates of this lane's 8 rows (row r = g*4 + r8 of the warp's 32 = pixel (y = 4q + r/8, x = r%8))
+      size_t rowoff[8];
+      bool ok[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int mm = q * 32 + g * 4 + r8;
+        const int oy = t.oy0 + mm / T2_TW, ox = t.ox0 + mm % T2_TW;
+        ok[g] = (oy < e.OH) && (ox < e.OW) && (t.n < e.N);
+        rowoff[g] = e.ps ? ((size_t)(t.n * 2 * e.OH + 2 * oy) * (2 * e.OW) + 2 * ox) * 32 + c8 * 4
+                         : ((size_t)(t.n * e.OH + oy) * e.OW + ox) * e.Cout + t.n0 + c8 * 4;
+      }
 #pragma unroll 1
       for (int j = 0; j < NT / 32; ++j) {
+        // residual reads do not depend on the accumulator: issue them first, they land under the TMEM load + transpose
+        float4 rr[8];
+        if (e.res) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) rr[g] = ok[g] ? ldg4(e.res + rowoff[g] + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias) bia = ldg4(e.bias + t.n0 + j * 32 + c8 * 4);
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NT + j * 32), v);
         if (j == NT / 32 - 1) {                                  // accumulator fully read: hand it back to the MMA warp
@@ -330,21 +353,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[ab]), 0));
           else         mbar_arrive_local(smem_u32(&acc_empty[ab]));
         }
-        if (valid) {
-          float* op = e.out + row + j * 32;
-          if (e.ps) op = e.out + ((size_t)(t.n * 2 * e.OH + 2 * oy + (j >> 1)) * (2 * e.OW) + 2 * ox + (j & 1)) * 32;
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            float4 o = make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]),
-                                   __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
-            if (e.bias) { const float4 b = ldg4(e.bias + t.n0 + j * 32 + c4 * 4); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-            if (e.res) { const float4 rr = ldg4(e.res + row + j * 32 + c4 * 4); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-            if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            st4(op + c4 * 4, o);
-          }
+        for (int c4 = 0; c4 < 8; ++c4)
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]), __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int r = g * 4 + r8;
+          float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((c8 ^ (r & 7)) << 2));
+          o.x += bia.x; o.y += bia.y; o.z += bia.z; o.w += bia.w;
+          if (e.res) { o.x += rr[g].x; o.y += rr[g].y; o.z += rr[g].z; o.w += rr[g].w; }
+          if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          // pixel-shuffle store: slab j = (dy, dx) lands on output pixel (2oy + dy, 2ox + dx), 32 channels each
+          float* op = e.ps ? e.out + rowoff[g] + ((size_t)(j >> 1) * (2 * e.OW) + (j & 1)) * 32 : e.out + rowoff[g] + j * 32;
+          if (ok[g]) st4(op, o);
         }
+        __syncwarp();                                            // the staging rows are free for the next slab
       }
     }
+    (void)m;
   } else if (X3 && warp >= 7) {                                 // ---------------- splitter (warps 7..10)
     const int tI = threadIdx.x - 224;
     const int nvec = (int)(e.halo_bytes / 16);
