@@ -41,7 +41,8 @@ template <bool X3> struct SkCfg {
   static constexpr uint32_t NB = X3 ? 2 : 1;                      // filter images: hi (+ lo)
   static constexpr uint32_t OFF_B = NA * SK_A_BYTES;
   static constexpr uint32_t OFF_H = OFF_B + NB * SK_B_BYTES;      // two halo buffers
-  static constexpr uint32_t SMEM = OFF_H + 2 * SK_HALO_STRIDE + 1024;
+  static constexpr uint32_t OFF_E = OFF_H + 2 * SK_HALO_STRIDE;   // epilogue staging: 4 warps x 4 KB (offset is a multiple of 16)
+  static constexpr uint32_t SMEM = OFF_E + 4 * 4096 + 1024;
 };
 
 __device__ __forceinline__ float sk_tf32(float v) { return tf32_round(v); }
@@ -130,16 +131,17 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tile
     }
   } else if (warp < 12) {
     // ------------------------------------------------------------------ epilogue warps 8..11
-    const int q = warp & 3, m = q * 32 + (tid & 31);
-    const int py = m / SK_TW, px = m % SK_TW;
+    // rows out of TMEM, through a per-warp shared-memory transpose, so that each store instruction writes four whole
+    // 128-byte lines (8 lanes per pixel) instead of 16 bytes of 32 different lines (same scheme as conv_tc2.cu)
+    const int q = warp & 3, lane = tid & 31;
+    float* stage = reinterpret_cast<float*>(bp + Cfg::OFF_E + (size_t)q * 4096);
+    const int c8 = lane & 7, r8 = lane >> 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const SkTile t = sk_tile(tile, tilesX, tilesY);
       const int ab = it & 1;
       mbar_wait(smem_u32(&acc_full[ab]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const int oy = t.oy0 + py, ox = t.ox0 + px;
-      const bool valid = oy < OH && ox < OW;
       const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * 64;
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
@@ -149,15 +151,22 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tile
           tc_fence_before();
           mbar_arrive_local(smem_u32(&acc_empty[ab]));
         }
-        if (valid) {
-          float* op = out + ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32;
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 b = ldg4(bias + j * 32 + c4 * 4);
-            st4(op + c4 * 4, make_float4(fmaxf(__uint_as_float(u[c4 * 4]) + b.x, 0.f), fmaxf(__uint_as_float(u[c4 * 4 + 1]) + b.y, 0.f),
-                                         fmaxf(__uint_as_float(u[c4 * 4 + 2]) + b.z, 0.f), fmaxf(__uint_as_float(u[c4 * 4 + 3]) + b.w, 0.f)));
-          }
+        for (int c4 = 0; c4 < 8; ++c4)
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(u[c4 * 4]), __uint_as_float(u[c4 * 4 + 1]), __uint_as_float(u[c4 * 4 + 2]), __uint_as_float(u[c4 * 4 + 3]));
+        __syncwarp();
+        const float4 b = ldg4(bias + j * 32 + c8 * 4);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int r = g * 4 + r8, mm = q * 32 + r;             // tile pixel (py = mm / 16, px = mm % 16)
+          const int oy = t.oy0 + mm / SK_TW, ox = t.ox0 + mm % SK_TW;
+          const float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((c8 ^ (r & 7)) << 2));
+          if (oy < OH && ox < OW)
+            st4(out + ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32 + c8 * 4,
+                make_float4(fmaxf(o.x + b.x, 0.f), fmaxf(o.y + b.y, 0.f), fmaxf(o.z + b.z, 0.f), fmaxf(o.w + b.w, 0.f)));
         }
+        __syncwarp();
       }
     }
   } else if (warp == 13) {
