@@ -135,7 +135,8 @@ template <bool X3> struct PdtCfg {
   static constexpr int G = PDT_G;
   static constexpr uint32_t BUF = PDT_HI_STRIDE + (X3 ? PDT_LO : 0);            // one table (or MLP) buffer
   static constexpr int NB = 3;                                                  // table / MLP buffers (layers in flight)
-  static constexpr uint32_t SMEM = 2 * NB * BUF + 1024;
+  static constexpr uint32_t OFF_IO = 2 * NB * BUF;                 // per-warp 32 x 128 B transpose buffers for the global I/O
+  static constexpr uint32_t SMEM = OFF_IO + PDT_G * 4 * 4096 + 1024;
 };
 
 template <int HEADS, bool X3>
@@ -155,8 +156,6 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
 
   const int wg = threadIdx.x >> 7;                                      // warpgroup = tile within the CTA
   const int tid = threadIdx.x & 127, warp = tid >> 5, img = blockIdx.y; // tid: row of this warpgroup's tile
-  const int p = (blockIdx.x * G + wg) * PDT_ROWS + tid;
-  const bool valid = p < npix;
   const uint32_t base = (smem_u32(pdt_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = pdt_raw + (base - smem_u32(pdt_raw));
   constexpr uint32_t BUFS0 = 0;
@@ -206,27 +205,30 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   auto turn_pass = [&]() { if (TURN_D) asm volatile("bar.arrive %0, 256;" ::"r"(5 + ((wg + TURN_D) & 3)) : "memory"); };
   if (TURN_D && wg >= G - TURN_D) turn_pass();                         // the first TURN_D warpgroups start immediately
 
-  // ---- x (+ pos) -> registers and TMEM
+  // ---- x (+ pos) -> registers and TMEM.  Global I/O goes through a per-warp shared-memory transpose: 8 lanes read one
+  // pixel's 128-byte row (4 whole lines per instruction), then every thread picks up ITS row — a thread-per-row access
+  // would touch 32 different lines with every instruction.
+  float* io = reinterpret_cast<float*>(base_ptr + Cfg::OFF_IO + (size_t)(threadIdx.x >> 5) * 4096);
+  const int lane = threadIdx.x & 31, c8 = lane & 7, r8 = lane >> 3;
+  const int pw0 = (blockIdx.x * G + wg) * PDT_ROWS + warp * 32;         // first pixel of this warp
   float xr[32];
-  if (valid) {
-    const float* xp = x + ((size_t)img * npix + p) * 32;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 v = ldg4(xp + q * 4);
-      xr[q * 4] = v.x; xr[q * 4 + 1] = v.y; xr[q * 4 + 2] = v.z; xr[q * 4 + 3] = v.w;
+  for (int g = 0; g < 8; ++g) {
+    const int r = g * 4 + r8, pr = pw0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pr < npix) {
+      v = ldg4(x + ((size_t)img * npix + pr) * 32 + c8 * 4);
+      if (pos) { const float4 q = ldg4(pos + (size_t)pr * 32 + c8 * 4); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
     }
-    if (pos) {
-      const float* pp = pos + (size_t)p * 32;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = ldg4(pp + q * 4);
-        xr[q * 4] += v.x; xr[q * 4 + 1] += v.y; xr[q * 4 + 2] += v.z; xr[q * 4 + 3] += v.w;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) xr[c] = 0.f;
+    *reinterpret_cast<float4*>(io + r * 32 + ((c8 ^ (r & 7)) << 2)) = v;
   }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(io + lane * 32 + ((q ^ (lane & 7)) << 2));
+    xr[q * 4] = v.x; xr[q * 4 + 1] = v.y; xr[q * 4 + 2] = v.z; xr[q * 4 + 3] = v.w;
+  }
+  __syncwarp();
   {
     uint32_t u[32];
 #pragma unroll
@@ -378,21 +380,25 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     if (issuer) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&free_bar[b])) : "memory");
   }
 
-  if (valid) {
-    if (skip) {
-      const int py = p / w, px = p - py * w;
-      const float* sp = (skip_up == 2)
-          ? skip + (((size_t)img * (npix / w / 2) + (py >> 1)) * (w >> 1) + (px >> 1)) * 32
-          : skip + ((size_t)img * npix + p) * 32;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = ldg4(sp + q * 4);
-        xr[q * 4] += v.x; xr[q * 4 + 1] += v.y; xr[q * 4 + 2] += v.z; xr[q * 4 + 3] += v.w;
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(io + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(xr[q * 4], xr[q * 4 + 1], xr[q * 4 + 2], xr[q * 4 + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int r = g * 4 + r8, pr = pw0 + r;
+    if (pr < npix) {
+      float4 o = *reinterpret_cast<const float4*>(io + r * 32 + ((c8 ^ (r & 7)) << 2));
+      if (skip) {
+        const int py = pr / w, px = pr - py * w;
+        const float* sp = (skip_up == 2)
+            ? skip + (((size_t)img * (npix / w / 2) + (py >> 1)) * (w >> 1) + (px >> 1)) * 32
+            : skip + ((size_t)img * npix + pr) * 32;
+        const float4 v = ldg4(sp + c8 * 4);
+        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
       }
+      st4(out + ((size_t)img * npix + pr) * 32 + c8 * 4, o);
     }
-    float* op = out + ((size_t)img * npix + p) * 32;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) st4(op + q * 4, make_float4(xr[q * 4], xr[q * 4 + 1], xr[q * 4 + 2], xr[q * 4 + 3]));
   }
   tc_fence_before();
   __syncthreads();
