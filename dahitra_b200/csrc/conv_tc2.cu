@@ -122,7 +122,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB16, const T2Args e) {
   using Cfg = T2Cfg<NT, XM, CG>;
   constexpr bool X3 = XM != 0;
-  static_assert(XM != 2 || CG == 1, "bf16 corrections are implemented for single-CTA tiles");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t2_raw[];
   constexpr int HB = Cfg::HB;
@@ -221,7 +220,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               const int kcol = Sched::tap(i0 + tt) * e.Cin + cc * 32;
               if (CG == 2 && rank == 1) {
                 tma_load_2d_2sm(dst, &tmB, lbar, kcol, nrow);
-                if (X3) tma_load_2d_2sm(dst + Cfg::B_TILE, &tmB, lbar, kcol, e.Cout + nrow);
+                if (XM == 2) {
+                  tma_load_2d_2sm(dst + Cfg::B_TILE, &tmB16, lbar, kcol, nrow);
+                  tma_load_2d_2sm(dst + Cfg::B_TILE + Cfg::B_TILE / 2, &tmB16, lbar, kcol, e.Cout + nrow);
+                } else if (X3) {
+                  tma_load_2d_2sm(dst + Cfg::B_TILE, &tmB, lbar, kcol, e.Cout + nrow);
+                }
               } else if (XM == 2) {
                 tma_load_2d(dst, &tmB, bar, kcol, nrow);                                           // fp32 (TF32-rounded) filter
                 tma_load_2d(dst + Cfg::B_TILE, &tmB16, bar, kcol, nrow);                           // bf16(w)
@@ -245,6 +249,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       constexpr uint32_t SBO = (uint32_t)HALO_W * 128u;
       auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
         if (CG == 2) umma_tf32_2sm(d, a, b, idesc, acc); else umma_tf32(d, a, b, idesc, acc);
+      };
+      auto mma16 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if (CG == 2) umma_bf16_2sm(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc);
       };
       auto commit = [](uint32_t bar) { if (CG == 2) umma_commit_2sm(bar); else umma_commit(bar); };
       int hb = 0, st = 0;
@@ -288,9 +295,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                   const uint32_t b16 = b_stage + (uint32_t)tt * Cfg::B_TAP + Cfg::B_TILE;
                   const uint64_t b_hi16 = umma_desc_sw64(b16, 512u), b_lo16 = umma_desc_sw64(b16 + Cfg::B_TILE / 2, 512u);
 #pragma unroll
-                  for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, a_lo16 + (uint64_t)(2 * k), b_hi16 + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
+                  for (int k = 0; k < 2; ++k) mma16(d_tmem, a_lo16 + (uint64_t)(2 * k), b_hi16 + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
 #pragma unroll
-                  for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, a_hi16 + (uint64_t)(2 * k), b_lo16 + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
+                  for (int k = 0; k < 2; ++k) mma16(d_tmem, a_hi16 + (uint64_t)(2 * k), b_lo16 + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
                 } else if (X3) {
                   const uint64_t al = al0 + (uint64_t)shift16;
                   const uint64_t bl = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP + Cfg::B_TILE);
@@ -582,12 +589,12 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
   int rc = get_map2(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, hw, hh, a.stride);
   if (rc) return rc;
   if (a.C1) { rc = get_map2(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, hw, hh, a.stride); if (rc) return rc; } else A1 = A0;
-  cg = (cg == 2 && xm != 2) ? 2 : 1;
+  cg = (cg == 2) ? 2 : 1;
   rc = get_map2(&Bm, a.wt, 2, K, 2 * a.Cout, 1, 1, NT / cg, 1);  // rows [0,Cout) = hi, [Cout,2Cout) = lo
   if (rc) return rc;
   CUtensorMap B16 = Bm;
   if (xm == 2) {                                                 // bf16 images follow the two fp32 ones
-    rc = get_map2(&B16, a.wt + (size_t)2 * a.Cout * K, 2, K, 2 * a.Cout, 1, 1, NT, 1, 1, true);
+    rc = get_map2(&B16, a.wt + (size_t)2 * a.Cout * K, 2, K, 2 * a.Cout, 1, 1, NT / cg, 1, 1, true);
     if (rc) return rc;
   }
   T2Args e;
@@ -606,6 +613,7 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
   if (cg == 2) {
     const int pairs = sms / 2;
     dim3 grid((unsigned)(2 * (e.ntiles < pairs ? e.ntiles : pairs)), 1, 1);       // persistent: one CTA pair per TPC
+    if (xm == 2) return launch2n<2, 2>(NT, A0, A1, Bm, B16, e, grid, s);
     return xm ? launch2n<1, 2>(NT, A0, A1, Bm, B16, e, grid, s) : launch2n<0, 2>(NT, A0, A1, Bm, B16, e, grid, s);
   }
   dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);          // persistent: one CTA per SM
