@@ -260,6 +260,31 @@ def test_tensor_core_modes(mode, weights, levir_template):
         assert agree >= min(0.999, agree_t - 0.002)
 
 
+def test_cuda_graph_capture(levir_template):
+    """The whole forward (including the fork / join of the library's side streams) can be captured into a CUDA graph
+    and replayed on new inputs: nothing in it allocates, synchronises or depends on host state."""
+    sd = synth.synth_state_dict(levir_template, seed=3, style="default")
+    net = make_net(sd)
+    xs = [tuple(t.to(DEV) for t in synth.synth_pair(4, 256, 256, seed=40 + i, kind="uniform")) for i in range(3)]
+    with torch.no_grad():
+        eager = [net(a, b).clone() for a, b in xs]              # also warms up: weights prepared, workspace allocated
+        sa, sb = xs[0][0].clone(), xs[0][1].clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            net(sa, sb)                                          # warm-up on the capture stream
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = net(sa, sb)
+        for (a, b), ref in zip(xs, eager):
+            sa.copy_(a); sb.copy_(b)
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref)                         # bit-identical to the eager launch sequence
+
+
 def test_shape_errors():
     net = make_net()
     with torch.no_grad():
