@@ -399,11 +399,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           uint8_t* lo_ptr = reinterpret_cast<uint8_t*>(lo);
           for (int i = tI; i < nvec / 2; i += 128) {
             const int q = i >> 2, j = i & 3, r = q & 7;
-            float4 v0 = hi[q * 8 + 2 * j], v1 = hi[q * 8 + 2 * j + 1];
-            const float4 h0 = make_float4(tf32_rna(v0.x), tf32_rna(v0.y), tf32_rna(v0.z), tf32_rna(v0.w));
-            const float4 h1 = make_float4(tf32_rna(v1.x), tf32_rna(v1.y), tf32_rna(v1.z), tf32_rna(v1.w));
-            hi[q * 8 + 2 * j] = h0;
-            hi[q * 8 + 2 * j + 1] = h1;
+            // access order within the pair alternates with (thread, row) parity so that the 8 threads of a quarter-warp
+            // (two rows) touch 8 different 16-byte bank groups: {0,3,4,7} of the even row, {1,2,5,6} of the odd one
+            const int f = (i ^ q) & 1;
+            float4 va = hi[q * 8 + 2 * j + f], vb = hi[q * 8 + 2 * j + (f ^ 1)];
+            const float4 ha = make_float4(tf32_rna(va.x), tf32_rna(va.y), tf32_rna(va.z), tf32_rna(va.w));
+            const float4 hb = make_float4(tf32_rna(vb.x), tf32_rna(vb.y), tf32_rna(vb.z), tf32_rna(vb.w));
+            hi[q * 8 + 2 * j + f] = ha;
+            hi[q * 8 + 2 * j + (f ^ 1)] = hb;
+            const float4 v0 = f ? vb : va, v1 = f ? va : vb, h0 = f ? hb : ha, h1 = f ? ha : hb;
             uint4 a16, l16;                                   // bf16(a), bf16(a - tf32(a)) in position order
             a16.x = pack_bf16x2(v0.x, v0.y); a16.y = pack_bf16x2(v0.z, v0.w); a16.z = pack_bf16x2(v1.x, v1.y); a16.w = pack_bf16x2(v1.z, v1.w);
             l16.x = pack_bf16x2(v0.x - h0.x, v0.y - h0.y); l16.y = pack_bf16x2(v0.z - h0.z, v0.w - h0.w);

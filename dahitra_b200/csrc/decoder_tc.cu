@@ -293,7 +293,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     const float* b1f = mlpp + 2048; const float* cbA = mlpp + 2080; const float* cbM = mlpp + 2112;
     const uint32_t t_hi = tab_addr(b), t_lo = tab_addr(b) + PDT_HI_STRIDE;
     const uint32_t m_hi = mlp_addr(b), m_lo = mlp_addr(b) + PDT_HI_STRIDE;
-    float t[32];
+    float t[32], rstd;
     // ---- 1. S = xhat . TA^T
     {
       turn_wait();
@@ -304,9 +304,9 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       float var = 0.f;
 #pragma unroll
       for (int c = 0; c < 32; ++c) { const float d = xr[c] - mu; var = fmaf(d, d, var); }
-      const float rstd = rsqrtf(var * (1.f / 32.f) + 1e-5f);
+      rstd = rsqrtf(var * (1.f / 32.f) + 1e-5f);               // applied to the MMA result: S = rstd * ((x - mu) . TA) + cA
 #pragma unroll
-      for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
+      for (int c = 0; c < 32; ++c) t[c] = xr[c] - mu;
       write_a_row(t);
       turn_pass();
     }
@@ -317,12 +317,12 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
         uint32_t u[32];
         tmem_ld32(tmem + TM_D, u);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) t[c] = __uint_as_float(u[c]) + cA[c];
+        for (int c = 0; c < 32; ++c) t[c] = fmaf(__uint_as_float(u[c]), rstd, cA[c]);
       } else {
         uint32_t u[16];
         tmem_ld16(tmem + TM_D, u);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) t[c] = __uint_as_float(u[c]) + cA[c];
+        for (int c = 0; c < 16; ++c) t[c] = fmaf(__uint_as_float(u[c]), rstd, cA[c]);
 #pragma unroll
         for (int c = 16; c < 32; ++c) t[c] = 0.f;
       }
@@ -351,9 +351,9 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       float var = 0.f;
 #pragma unroll
       for (int c = 0; c < 32; ++c) { const float d = xr[c] - mu; var = fmaf(d, d, var); }
-      const float rstd = rsqrtf(var * (1.f / 32.f) + 1e-5f);
+      rstd = rsqrtf(var * (1.f / 32.f) + 1e-5f);               // Hid = rstd * ((x - mu) . W1f) + b1f
 #pragma unroll
-      for (int c = 0; c < 32; ++c) t[c] = (xr[c] - mu) * rstd;
+      for (int c = 0; c < 32; ++c) t[c] = xr[c] - mu;
       write_a_row(t);
       turn_pass();
     }
@@ -364,7 +364,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       tmem_ld32(tmem + TM_D, u);
       turn_wait();
 #pragma unroll
-      for (int c = 0; c < 32; ++c) t[c] = gelu_phi8(__uint_as_float(u[c]) + b1f[c]);
+      for (int c = 0; c < 32; ++c) t[c] = gelu_phi8(fmaf(__uint_as_float(u[c]), rstd, b1f[c]));
       write_a_row(t);
       turn_pass();
     }
