@@ -309,3 +309,44 @@ def test_autograd_route_matches_native(levir_template):
     yt = net._forward_autograd(x1, x2)
     assert yt.requires_grad
     check_logits(yn, yt.detach(), "native vs autograd route")
+
+
+def test_training_step_then_native_inference():
+    """configs[3] on one GPU: a few SGD steps on the stock-autograd route (train mode, BatchNorm batch statistics)
+    reduce the loss on a fixed batch, every parameter receives a finite gradient, and after eval() the native forward
+    runs on the UPDATED weights and BatchNorm statistics (prepared-weight cache invalidated) and agrees with the
+    autograd route."""
+    import torch.nn.functional as F
+    from dahitra_b200.networks import define_G
+    torch.manual_seed(3)
+    net = define_G(Args(), gpu_ids=[0]).train().set_mode(_MODE)
+    opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9)
+    x1, x2 = (t.to(DEV) for t in synth.synth_pair(4, 256, 256, seed=77, kind="uniform"))
+    y = (torch.rand(4, 256, 256, generator=torch.Generator().manual_seed(5)) < 0.15).long().to(DEV)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad(set_to_none=True)
+        out = net(x1, x2)
+        assert out.requires_grad
+        loss = F.cross_entropy(out, y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < losses[0]
+    # like the reference module, the net carries parameters its forward never touches (scale-2 transformer, conv_pred,
+    # resnet.layer4 / fc with resnet_stages_num=4): DDP therefore needs find_unused_parameters=True.  Everything else
+    # must have received a finite gradient.
+    unused = ("conv_decode_2", "conv_pred", "conv_squeeze_2", "conv_token_2", "pos_embedding_2", "pos_embedding_decoder_2",
+              "resnet.fc", "resnet.layer4", "transformer_2", "transformer_decoder_2")
+    for n, p in net.named_parameters():
+        if n.startswith(unused):
+            assert p.grad is None, n
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    net.eval()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        yn = net(x1, x2)
+    ya = net._forward_autograd(x1, x2).detach()
+    check_logits(yn, ya, "native vs autograd route after 6 SGD steps", defineG=True)
