@@ -73,6 +73,7 @@ SIGNATURES = {
     "dahitra_decoder_tables_tc": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "dahitra_pixel_decoder_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P]),
     "dahitra_confusion_matrix": (_I, [_P, _P, _LL, _I, _P, _P]),
+    "dahitra_prepare_input_u8": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "dahitra_classifier": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 

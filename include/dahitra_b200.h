@@ -244,6 +244,12 @@ int dahitra_classifier(const float* in, int N, int H, int W, int nc, const float
 int dahitra_confusion_matrix(const unsigned char* pred, const unsigned char* gt, long long n, int nc,
                              long long* cm, void* stream);
 
+/* Input path: uint8 HWC images [N][H][W][3] -> normalised fp32 NCHW on the device, bit-identical to the
+ * reference loaders: kind 0 = (x/255 - 0.5)/0.5 (datasets/data_utils.py:104-111), kind 1 = x/127 - 1
+ * (xBD_code/utils.py:112-116).  tile > 0 cuts every image into (H/tile)*(W/tile) square tiles in the reference's
+ * patch order (data_utils.py:65-66, patch 0 at the origin) -> out [N*T][3][tile][tile]; tile = 0 keeps whole images. */
+int dahitra_prepare_input_u8(const unsigned char* hwc, int N, int H, int W, int kind, int tile, float* nchw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

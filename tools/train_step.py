@@ -1,4 +1,4 @@
-"""configs[3] smoke: LEVIR-CD training step of the drop-in module (batch 8 per GPU, 256x256, synthetic labels, CE loss, SGD).
+"""configs[3] smoke: LEVIR-CD training step of the drop-in module (batch 8 per GPU, 256x256, synthetic labels, CE loss, AdamW).
 Training runs on the stock-autograd route (DESIGN.md "Training step"); under torchrun the module is wrapped in
 DistributedDataParallel (NCCL gradient all-reduce, as BASELINE.json's config 4 describes).  After the last step the
 module is switched to eval() and the NATIVE forward is checked against the autograd route on the updated weights.
@@ -33,7 +33,7 @@ model = net
 if world > 1:
     # like the reference, the module owns parameters its forward never uses (scale-2 transformer, conv_pred, layer4)
     model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
-opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
+opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01)           # models/trainer.py:39-40
 g = torch.Generator(device="cuda").manual_seed(100 + rank)
 x1 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 x2 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
@@ -43,7 +43,7 @@ torch.cuda.synchronize()
 t0 = time.time()
 for step in range(a.steps):
     opt.zero_grad(set_to_none=True)
-    loss = F.cross_entropy(model(x1, x2), y)
+    loss = F.cross_entropy(model(x1, x2), y, weight=torch.ones(2, device="cuda"), ignore_index=255)   # models/losses.py:9-26
     loss.backward()
     opt.step()
     losses.append(float(loss.detach()))
@@ -67,7 +67,7 @@ with torch.no_grad():
 y_auto = net._forward_autograd(x1, x2).detach()
 native_vs_autograd = float((y_native - y_auto).abs().max())
 if rank == 0:
-    print(json.dumps(dict(workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, SGD (autograd route"
+    print(json.dumps(dict(workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW (autograd route"
                                    + (", DDP/NCCL all-reduce)" if world > 1 else ")"),
                           steps=a.steps, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
                           loss_first=losses[0], loss_last=losses[-1], grad_norm_last=gnorm, params_without_grad=len(no_grad),
