@@ -24,6 +24,9 @@
 // works there too, tools/umma_bf16_probe.cu), and the filter ring carries bf16(w) and bf16(w - tf32(w)) tiles.
 // Per (tap, 32-channel chunk): 4 TF32 + 2 + 2 BF16 MMAs instead of 12.
 //
+// XM = 3 ("bf16"): single-pass BF16 operands (fp32 storage, fp32 accumulation): the splitter only converts the halo to
+// the bf16 tile, the ring only carries bf16(w); 2 MMAs per (tap, chunk).  Separately stated tolerance (tests).
+//
 // Stride 2 (SD = 2; resnet layer2.0): the input is read as its four 2x2 phase images P_ab(y,x) = X(2y+a, 2x+b),
 // each fetched by a TMA box with elementStrides {1,2,2,1}.  A 3x3 stride-2 tap (r,s) is the stride-1 tap of phase
 // (r odd ? 0 : 1, s odd ? 0 : 1) at offset (r == 0 ? -1 : 0, s == 0 ? -1 : 0), so every (chunk, phase) pair is one
@@ -56,17 +59,18 @@ struct T2Args {
 };
 
 template <int NT, int XM, int CG = 1> struct T2Cfg {
-  static constexpr bool X3 = XM != 0;              // error-compensated modes: 1 = three TF32 MMAs, 2 = TF32 + two BF16
+  static constexpr bool X3 = XM != 0;              // modes with a splitter pass: 1 = three TF32 MMAs, 2 = TF32 + two BF16, 3 = BF16 only
   // Persistent kernel, one CTA per SM.  Pipeline depth is sized so that the MMA warp always has >= ~1500 cycles of
   // operands in flight (L2 latency under load): the smaller the N tile, the faster a stage is consumed, so the more
   // halo buffers (HB) and filter stages it gets.  A stage holds TPS filter taps so the issuing thread waits /
   // commits once per 4*TPS (x3: 12*TPS) MMAs.
   static constexpr int HB = X3 ? 2 : (NT == 128 ? 2 : (NT == 64 ? 3 : 4));          // halo chunk buffers (x3: hi + lo each)
-  static constexpr int TPS = X3 ? (NT == 32 ? 3 : 1) : 3;
-  static constexpr int STAGES1 = X3 ? (NT == 128 ? 3 : (NT == 64 ? 6 : 4)) : (NT == 128 ? 3 : (NT == 64 ? 5 : 8));
+  static constexpr int TPS = XM == 3 ? 3 : (X3 ? (NT == 32 ? 3 : 1) : 3);
+  static constexpr int STAGES1 = XM == 3 ? (NT == 128 ? 4 : (NT == 64 ? 6 : 8))
+                               : (X3 ? (NT == 128 ? 3 : (NT == 64 ? 6 : 4)) : (NT == 128 ? 3 : (NT == 64 ? 5 : 8)));
   static constexpr int STAGES = CG == 2 ? (2 * STAGES1 > 8 ? 8 : 2 * STAGES1) : STAGES1;   // CTA pair: half-size B tiles
   static constexpr uint32_t B_TILE = (NT / CG) * 128;           // a CTA of a pair holds N/2 rows of B
-  static constexpr uint32_t B_TAP = B_TILE * (X3 ? 2 : 1);      // hi (+ lo) tile of one tap; XM = 2: [fp32 hi][bf16 hi][bf16 lo]
+  static constexpr uint32_t B_TAP = XM == 3 ? B_TILE / 2 : B_TILE * (X3 ? 2 : 1);   // XM 0: fp32 | 1: fp32 hi, lo | 2: fp32 hi, bf16 hi, lo | 3: bf16
   static constexpr uint32_t IDESC16 = umma_idesc_bf16(128 * CG, NT);
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
   static constexpr uint32_t HALO_BUFS = X3 ? 2 * HB : HB;       // [hi 0..HB-1][lo 0..HB-1]
@@ -122,6 +126,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB16, const T2Args e) {
   using Cfg = T2Cfg<NT, XM, CG>;
   constexpr bool X3 = XM != 0;
+  static_assert(XM != 3 || CG == 1, "the bf16-only mode is implemented for single-CTA tiles");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t2_raw[];
   constexpr int HB = Cfg::HB;
@@ -226,6 +231,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 } else if (X3) {
                   tma_load_2d_2sm(dst + Cfg::B_TILE, &tmB, lbar, kcol, e.Cout + nrow);
                 }
+              } else if (XM == 3) {
+                tma_load_2d(dst, &tmB16, bar, kcol, nrow);                                         // bf16(w) only
               } else if (XM == 2) {
                 tma_load_2d(dst, &tmB, bar, kcol, nrow);                                           // fp32 (TF32-rounded) filter
                 tma_load_2d(dst + Cfg::B_TILE, &tmB16, bar, kcol, nrow);                           // bf16(w)
@@ -284,8 +291,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const uint32_t shift16 = (uint32_t)(Sched::shift_px(Sched::tap(i), HALO_W) * 128) >> 4;   // compile-time after unrolling
                 const uint64_t ah = ah0 + (uint64_t)shift16;
                 const uint64_t bh = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP);
+                if (XM == 3) {
+                  // bf16 only: A = the bf16 halo (first tile of the "lo" buffer), B = the bf16 filter tile
+                  const uint32_t h16 = h_hi + (uint32_t)HB * T2_HALO_STRIDE + (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;
+                  const uint64_t a16 = umma_desc_sw64(h16, (uint32_t)HALO_W * 64u);
+                  const uint64_t b16 = umma_desc_sw64(b_stage + (uint32_t)tt * Cfg::B_TAP, 512u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (cc | i | k) ? 1u : 0u);
+                  for (int k = 0; k < 2; ++k) mma16(d_tmem, a16 + (uint64_t)(2 * k), b16 + (uint64_t)(2 * k), Cfg::IDESC16, (cc | i | k) ? 1u : 0u);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) mma(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (cc | i | k) ? 1u : 0u);
+                }
                 if (XM == 2) {
                   // corrections in bf16: A = the bf16 halos (64-byte pixel rows), B = the bf16 filter tiles; K = 16 per MMA
                   constexpr uint32_t SBO16 = (uint32_t)HALO_W * 64u;
@@ -298,7 +314,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                   for (int k = 0; k < 2; ++k) mma16(d_tmem, a_lo16 + (uint64_t)(2 * k), b_hi16 + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
 #pragma unroll
                   for (int k = 0; k < 2; ++k) mma16(d_tmem, a_hi16 + (uint64_t)(2 * k), b_lo16 + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
-                } else if (X3) {
+                } else if (XM == 1) {
                   const uint64_t al = al0 + (uint64_t)shift16;
                   const uint64_t bl = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP + Cfg::B_TILE);
 #pragma unroll
@@ -390,7 +406,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g / HB) & 1));
         float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)hb * T2_HALO_STRIDE);
         float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)(HB + hb) * T2_HALO_STRIDE);
-        if (XM == 2) {
+        if (XM >= 2) {
           // item = (pixel q, pair of adjacent 16-byte chunks): 8 channels.  The TMA wrote chunk c of pixel q at position
           // c ^ (q & 7), so positions (2j, 2j+1) hold the logical chunks (2j ^ r, 2j ^ r ^ 1), r = q & 7: logical 8-channel
           // group j ^ (r >> 1), halves swapped when r is odd.  Each group becomes one 16-byte chunk of the pixel's 64-byte
@@ -403,6 +419,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             // (two rows) touch 8 different 16-byte bank groups: {0,3,4,7} of the even row, {1,2,5,6} of the odd one
             const int f = (i ^ q) & 1;
             float4 va = hi[q * 8 + 2 * j + f], vb = hi[q * 8 + 2 * j + (f ^ 1)];
+            if (XM == 3) {                                     // bf16 only: convert, nothing else
+              const float4 w0 = f ? vb : va, w1 = f ? va : vb;
+              uint4 a16;
+              a16.x = pack_bf16x2(w0.x, w0.y); a16.y = pack_bf16x2(w0.z, w0.w); a16.z = pack_bf16x2(w1.x, w1.y); a16.w = pack_bf16x2(w1.z, w1.w);
+              if (r & 1) a16 = make_uint4(a16.z, a16.w, a16.x, a16.y);
+              const uint32_t grp3 = (uint32_t)(j ^ (r >> 1)), row3 = (uint32_t)q * 64u;
+              *reinterpret_cast<uint4*>(lo_ptr + row3 + ((grp3 ^ (((lo_base + row3) >> 7) & 3u)) << 4)) = a16;
+              continue;
+            }
             const float4 ha = make_float4(tf32_rna(va.x), tf32_rna(va.y), tf32_rna(va.z), tf32_rna(va.w));
             const float4 hb = make_float4(tf32_rna(vb.x), tf32_rna(vb.y), tf32_rna(vb.z), tf32_rna(vb.w));
             hi[q * 8 + 2 * j + f] = ha;
@@ -577,7 +602,7 @@ bool dh_conv_tc2_eligible(const ConvArgs& a) {
 }
 
 // a.wt: [2][Cout][K] = TF32-rounded filter (hi) followed by its TF32-rounded remainder (lo); x3 uses both.
-// xm: 0 = 1xTF32, 1 = 3xTF32 (three TF32 MMAs), 2 = 3xTF32 with the two correction products in bf16.
+// xm: 0 = 1xTF32, 1 = 3xTF32 (three TF32 MMAs), 2 = 3xTF32 with the two correction products in bf16, 3 = bf16 operands only.
 // cg = 2: CTA pairs (tcgen05 cta_group::2): M = 256 per MMA, each CTA loads and reads only half of the filter tile
 // a.wt: [hi fp32 Cout*K][lo fp32 Cout*K][bf16(w) Cout*K][bf16(w - hi) Cout*K]  (engine.kmajor_split)
 int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
@@ -593,11 +618,11 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
   int rc = get_map2(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, hw, hh, a.stride);
   if (rc) return rc;
   if (a.C1) { rc = get_map2(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, hw, hh, a.stride); if (rc) return rc; } else A1 = A0;
-  cg = (cg == 2) ? 2 : 1;
+  cg = (cg == 2 && xm != 3) ? 2 : 1;
   rc = get_map2(&Bm, a.wt, 2, K, 2 * a.Cout, 1, 1, NT / cg, 1);  // rows [0,Cout) = hi, [Cout,2Cout) = lo
   if (rc) return rc;
   CUtensorMap B16 = Bm;
-  if (xm == 2) {                                                 // bf16 images follow the two fp32 ones
+  if (xm >= 2) {                                                 // bf16 images follow the two fp32 ones
     rc = get_map2(&B16, a.wt + (size_t)2 * a.Cout * K, 2, K, 2 * a.Cout, 1, 1, NT / cg, 1, 1, true);
     if (rc) return rc;
   }
@@ -621,6 +646,7 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
     return xm ? launch2n<1, 2>(NT, A0, A1, Bm, B16, e, grid, s) : launch2n<0, 2>(NT, A0, A1, Bm, B16, e, grid, s);
   }
   dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);          // persistent: one CTA per SM
+  if (xm == 3) return launch2n<3, 1>(NT, A0, A1, Bm, B16, e, grid, s);
   if (xm == 2) return launch2n<2, 1>(NT, A0, A1, Bm, B16, e, grid, s);
   return xm ? launch2n<1, 1>(NT, A0, A1, Bm, B16, e, grid, s) : launch2n<0, 1>(NT, A0, A1, Bm, B16, e, grid, s);
 }

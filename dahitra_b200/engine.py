@@ -23,7 +23,7 @@ LEVELS = ((5, 256, 4, 4), (4, 128, 4, 4), (3, 64, 8, 8))   # (k, trunk channels,
 
 DH_VARIANT_LEVIR, DH_VARIANT_XBD = 0, 1
 DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC, DH_FLAG_STEM_TC, DH_FLAG_DEC_TC_X3 = 1, 2, 4, 8, 16, 32
-DH_FLAG_CONV_TC_V1, DH_FLAG_CONV_TC_2CTA, DH_FLAG_SERIAL, DH_FLAG_TC_X3_BF16 = 64, 128, 256, 512
+DH_FLAG_CONV_TC_V1, DH_FLAG_CONV_TC_2CTA, DH_FLAG_SERIAL, DH_FLAG_TC_X3_BF16, DH_FLAG_TC_BF16 = 64, 128, 256, 512, 1024
 MODES = {
     "fp32": 0,                                             # every contraction in fp32 FMA (strict)
     "fp32_tcdec": DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,      # strict + the 3xTF32 (fp32-grade) tensor-core decoder
@@ -34,6 +34,8 @@ MODES = {
               | DH_FLAG_DEC_TC_X3,
     "tf32x3_pure": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
+    # reduced precision: BF16 operands in every convolution (fp32 storage / accumulation), 1xTF32 stem, 3xTF32 decoder
+    "bf16": DH_FLAG_CONV_TC | DH_FLAG_TC_BF16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32_fast": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC,   # 1xTF32 decoder too
 }
 

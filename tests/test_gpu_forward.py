@@ -211,7 +211,7 @@ def test_weight_updates_are_seen(levir_template):
         assert torch.equal(net(x1, x2), yb)
 
 
-@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32", "bf16"])
 @pytest.mark.parametrize("weights", ["defineG", "default"])
 def test_tensor_core_modes(mode, weights, levir_template):
     """The two tensor-core modes (dahitra_b200.engine.MODES), fp32 storage and fp32 accumulation in both:
@@ -251,7 +251,15 @@ def test_tensor_core_modes(mode, weights, levir_template):
     print(f"[parity] mode {mode} ({weights}): max|d|={float(d.max()):.3e} mean|d|={float(d.mean()):.3e} "
           f"ref_absmax={float(ref.abs().max()):.3e} argmax_agree={agree:.6f} outside-strict-fp32-tol={strict_bad}/{d.numel()} "
           f"| eager-PyTorch-TF32: max|d|={float(dt.max()):.3e} mean|d|={float(dt.mean()):.3e} argmax_agree={agree_t:.6f}")
-    if weights == "defineG":
+    if mode == "bf16":
+        # reduced-precision mode (BF16 operands in the convolutions), separately stated tolerance:
+        # |d| <= 2e-3 + 2e-2 |ref| and >= 99.5 % argmax agreement on the random-init weights; on the ill-conditioned
+        # weights no worse than 5x eager PyTorch TF32 in the mean and >= 99 % argmax agreement
+        if weights == "defineG":
+            assert int((d > 2e-3 + 2e-2 * ref.abs()).sum()) == 0 and agree >= 0.995
+        else:
+            assert float(d.mean()) <= 5.0 * float(dt.mean()) + 1e-5 and agree >= 0.99
+    elif weights == "defineG":
         assert strict_bad == 0 and agree >= 0.999
     elif mode == "tf32x3":
         assert float(d.max()) <= 1e-3 * float(ref.abs().max()) and agree >= 0.9999
