@@ -307,8 +307,10 @@ int dh_launch_maxpool(const float* in, int N, int H, int W, int C, float* out, c
 // pixel); the work is arranged so that shared-memory traffic stays below the FMA time:
 //   CTA = 32 x 16 pixels, 128 threads; thread (lx, g) owns the 4 vertically adjacent pixels (lx, 4g..4g+3), so each
 //   128-bit halo read feeds up to 3 output rows and each filter read feeds 4 pixels (5.6 smem wavefronts per pixel
-//   instead of 20).  The 18 x 34 halo is staged in two passes of 16 channels with a pixel pitch of 20 floats:
-//   consecutive pixels land 20 banks apart, so the 8 threads of a quarter-warp read 8 disjoint 16-byte bank groups.
+//   instead of 20).  The 18 x 34 halo is staged as two 16-channel halves with a pixel pitch of 20 floats (consecutive
+//   pixels land 20 banks apart, so the 8 threads of a quarter-warp read 8 disjoint 16-byte bank groups).  Both halves
+//   are fetched up front with cp.async (zero-fill outside the image): every load of the CTA is in flight at once and
+//   the first half is computed while the second one lands; 2 CTAs per SM alternate load and compute phases.
 // =====================================================================================================
 namespace {
 constexpr int CL_TW = 32, CL_TH = 16, CL_HW = CL_TW + 2, CL_HH = CL_TH + 2, CL_PS = 20, CL_CH = 16;
@@ -318,8 +320,8 @@ __global__ void __launch_bounds__(128)
 classifier_kernel(const float* __restrict__ in, int H, int W, int tilesX, const float* __restrict__ w,
                   const float* __restrict__ bias, float* __restrict__ logits, unsigned char* __restrict__ amax) {
   extern __shared__ __align__(16) float cl_sm[];
-  float* halo = cl_sm;                                   // [18*34][20]
-  float* w_s = cl_sm + CL_HH * CL_HW * CL_PS;            // [9][NC][32]
+  float* halo0 = cl_sm;                                  // 2 x [18*34][20]
+  float* w_s = cl_sm + 2 * CL_HH * CL_HW * CL_PS;        // [9][NC][32]
   const int tid = threadIdx.x, n = blockIdx.z;
   const int y0 = (blockIdx.x / tilesX) * CL_TH, x0 = (blockIdx.x % tilesX) * CL_TW;
   for (int i = tid; i < 9 * NC * 8; i += 128) reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
@@ -330,18 +332,27 @@ classifier_kernel(const float* __restrict__ in, int H, int W, int tilesX, const 
 #pragma unroll
     for (int k = 0; k < NC; ++k) acc[j][k] = __ldg(bias + k);
 
+  // stage both 16-channel halves: one commit group each
 #pragma unroll 1
   for (int pass = 0; pass < 32 / CL_CH; ++pass) {
-    if (pass) __syncthreads();                           // everyone is done reading the previous 16 channels
+    const uint32_t hb = (uint32_t)__cvta_generic_to_shared(halo0 + pass * CL_HH * CL_HW * CL_PS);
     for (int i = tid; i < CL_HH * CL_HW * (CL_CH / 4); i += 128) {
       const int c4 = i & 3, p = i >> 2;
       const int yy = p / CL_HW, xx = p - yy * CL_HW;
       const int iy = y0 + yy - 1, ix = x0 + xx - 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = ldg4(in + (((size_t)n * H + iy) * W + ix) * 32 + pass * CL_CH + c4 * 4);
-      *reinterpret_cast<float4*>(&halo[p * CL_PS + c4 * 4]) = v;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      const float* src = ok ? in + (((size_t)n * H + iy) * W + ix) * 32 + pass * CL_CH + c4 * 4 : in;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(hb + (uint32_t)(p * CL_PS + c4 * 4) * 4u), "l"(src),
+                   "r"(ok ? 16u : 0u) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < 32 / CL_CH; ++pass) {
+    if (pass == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else           asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    const float* halo = halo0 + pass * CL_HH * CL_HW * CL_PS;
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
 #pragma unroll
@@ -399,7 +410,7 @@ int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const flo
   dim3 grid(tx * ty, 1, N);
 #define DH_CLS_CASE(NC)                                                                                   \
   case NC: {                                                                                              \
-    const int smem = (CL_HH * CL_HW * CL_PS + 9 * NC * 32) * (int)sizeof(float);                          \
+    const int smem = (2 * CL_HH * CL_HW * CL_PS + 9 * NC * 32) * (int)sizeof(float);                      \
     cudaError_t e = cudaFuncSetAttribute(classifier_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
     if (e != cudaSuccess) return (int)e;                                                                  \
     classifier_kernel<NC><<<grid, 128, smem, s>>>(in, H, W, tx, w, b, logits, amax);                      \
