@@ -317,7 +317,8 @@ def run_native(a, wl):
                     unit="TFLOP/s", frac=achieved / peaks["bf16_tflops_sustained"])
         # what the tensor pipe actually executes: kind::tf32 runs at half the bf16 rate, and 3xTF32 issues three MMAs
         # per algorithmic product
-        mult = (2 if (net._engine.flags & 512) else 3) if (net._engine.flags & 2) else 1    # TF32-equivalent MMAs per product
+        fl = net._engine.flags                              # TF32-equivalent MMAs per product (a 16-bit K=16 MMA counts 1/2)
+        mult = 0.5 if (fl & 1024) else ((1.5 if (fl & 2048) else 2 if (fl & 512) else 3) if (fl & 2) else 1)
         roof["tensor_pipe"] = dict(mma_tflops=achieved * mult, mmas_per_product=mult,
                                    tf32_peak_tflops=peaks["bf16_tflops_sustained"] / 2,
                                    frac=achieved * mult / (peaks["bf16_tflops_sustained"] / 2),
@@ -349,8 +350,9 @@ def run_native(a, wl):
                    sample=f"oracle port (torch CPU fp32), {cp} pairs per call, mean of 3 calls after 1 warm-up ({sec:.2f} s/call)")
     line = dict(metric="image-pairs/sec", value=value, unit="pairs/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype={"fp32": "f32", "tf32": "tf32", "tf32_fast": "tf32", "tf32x3": "tf32x3 (error-compensated, fp32-grade)",
-                       "tf32x3_pure": "tf32x3 (error-compensated, fp32-grade)"}.get(mode_name, "f32/tf32"),
+                dtype={"fp32": "f32", "tf32": "tf32", "tf32_fast": "tf32", "tf32x3": "x3 error-compensated (convs: f16 main + bf16 corrections; stem/decoder: 3xTF32), fp32 accumulate and storage",
+                       "tf32x3_tf32main": "x3 error-compensated (tf32 main + bf16 corrections), fp32 accumulate and storage",
+                       "tf32x3_pure": "3xTF32 (error-compensated), fp32 accumulate and storage", "bf16": "bf16 operands, fp32 accumulate and storage"}.get(mode_name, "f32/tf32"),
                 data="synthetic",
                 config=dict(workload=wl["desc"], H=H, W=W, pairs_per_gpu=Bp, global_pairs_per_step=world * Bp,
                             sharding="by image pair, one process per GPU, no collective",

@@ -24,6 +24,11 @@
 // works there too, tools/umma_bf16_probe.cu), and the filter ring carries bf16(w) and bf16(w - tf32(w)) tiles.
 // Per (tap, 32-channel chunk): 4 TF32 + 2 + 2 BF16 MMAs instead of 12.
 //
+// XM = 4: like XM = 2 with the MAIN product in FP16 (11-bit significand like TF32, but 16-bit operands: K = 16 per MMA,
+// half the operand bytes): a = f16(a) + r_a, w = f16(w) + r_w with the remainders carried in bf16 (fp32 range, so values
+// beyond the f16 range — saturated to +-65504 — or below its normal range only cost accuracy of the correction terms).
+// Per (tap, chunk): 2 FP16 + 2 + 2 BF16 MMAs.  The splitter writes three 16-bit halos: f16(a), bf16(a), bf16(a - f16(a)).
+//
 // XM = 3 ("bf16"): single-pass BF16 operands (fp32 storage, fp32 accumulation): the splitter only converts the halo to
 // the bf16 tile, the ring only carries bf16(w); 2 MMAs per (tap, chunk).  Separately stated tolerance (tests).
 //
@@ -70,11 +75,14 @@ template <int NT, int XM, int CG = 1> struct T2Cfg {
                                : (X3 ? (NT == 128 ? 3 : (NT == 64 ? 6 : 4)) : (NT == 128 ? 3 : (NT == 64 ? 5 : 8)));
   static constexpr int STAGES = CG == 2 ? (2 * STAGES1 > 8 ? 8 : 2 * STAGES1) : STAGES1;   // CTA pair: half-size B tiles
   static constexpr uint32_t B_TILE = (NT / CG) * 128;           // a CTA of a pair holds N/2 rows of B
-  static constexpr uint32_t B_TAP = XM == 3 ? B_TILE / 2 : B_TILE * (X3 ? 2 : 1);   // XM 0: fp32 | 1: fp32 hi, lo | 2: fp32 hi, bf16 hi, lo | 3: bf16
+  static constexpr uint32_t B_TAP = XM == 3 ? B_TILE / 2 : (XM == 4 ? 3 * (B_TILE / 2) : B_TILE * (X3 ? 2 : 1));
+  // XM 0: fp32 | 1: fp32 hi, lo | 2: fp32 hi, bf16 hi, lo | 3: bf16 | 4: f16, bf16 hi, bf16 lo
+  static constexpr uint32_t LO_STRIDE = XM == 4 ? 35840u : 23552u;   // the 16-bit halos of one buffer (XM = 4: three of 11520 B)
+  static constexpr uint32_t IDESCF = umma_idesc_f16(128 * CG, NT);
   static constexpr uint32_t IDESC16 = umma_idesc_bf16(128 * CG, NT);
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
-  static constexpr uint32_t HALO_BUFS = X3 ? 2 * HB : HB;       // [hi 0..HB-1][lo 0..HB-1]
-  static constexpr uint32_t EPI_OFF = HALO_BUFS * T2_HALO_STRIDE + STAGES * B_STAGE;   // epilogue staging: 4 warps x 4 KB
+  static constexpr uint32_t HALO_BYTES = HB * T2_HALO_STRIDE + (X3 ? HB * LO_STRIDE : 0);   // [hi 0..HB-1][lo 0..HB-1]
+  static constexpr uint32_t EPI_OFF = HALO_BYTES + STAGES * B_STAGE;   // epilogue staging: 4 warps x 4 KB
   static constexpr uint32_t SMEM = EPI_OFF + 4 * 4096 + 1024;
   static constexpr int THREADS = X3 ? 352 : 224;                // + 4 splitter warps
   static constexpr uint32_t IDESC = umma_idesc_tf32(128 * CG, NT);
@@ -123,10 +131,11 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, const T2Args& e, int N
 template <int NT, int XM, int KS, int SD, int CG>
 __global__ void __launch_bounds__(T2Cfg<NT, XM, CG>::THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB16, const T2Args e) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB16,
+                const __grid_constant__ CUtensorMap tmB16f, const T2Args e) {
   using Cfg = T2Cfg<NT, XM, CG>;
   constexpr bool X3 = XM != 0;
-  static_assert(XM != 3 || CG == 1, "the bf16-only mode is implemented for single-CTA tiles");
+  static_assert((XM != 3 && XM != 4) || CG == 1, "the 16-bit-main modes are implemented for single-CTA tiles");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t2_raw[];
   constexpr int HB = Cfg::HB;
@@ -137,7 +146,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(t2_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = t2_raw + (base - smem_u32(t2_raw));
-  const uint32_t b_ring = base + Cfg::HALO_BUFS * T2_HALO_STRIDE;
+  const uint32_t b_ring = base + Cfg::HALO_BYTES;
+  constexpr uint32_t LO0 = (uint32_t)Cfg::HB * T2_HALO_STRIDE;          // offset of the first "lo" buffer
   constexpr int pad = (KS == 3) ? 1 : 0;
   using Sched = TapSched<KS, SD>;
   constexpr int NPH = Sched::NPH;
@@ -231,6 +241,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 } else if (X3) {
                   tma_load_2d_2sm(dst + Cfg::B_TILE, &tmB, lbar, kcol, e.Cout + nrow);
                 }
+              } else if (XM == 4) {
+                tma_load_2d(dst, &tmB16f, bar, kcol, nrow);                                        // f16(w)
+                tma_load_2d(dst + Cfg::B_TILE / 2, &tmB16, bar, kcol, nrow);                       // bf16(w)
+                tma_load_2d(dst + Cfg::B_TILE, &tmB16f, bar, kcol, e.Cout + nrow);                 // bf16(w - f16(w))
               } else if (XM == 3) {
                 tma_load_2d(dst, &tmB16, bar, kcol, nrow);                                         // bf16(w) only
               } else if (XM == 2) {
@@ -279,7 +293,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             tc_fence_after();
             const uint32_t h_hi = base + (uint32_t)hb * T2_HALO_STRIDE;
             const uint64_t ah0 = halo_desc(h_hi, SBO);
-            const uint64_t al0 = halo_desc(h_hi + (uint32_t)HB * T2_HALO_STRIDE, SBO);
+            const uint32_t h_lo = base + LO0 + (uint32_t)hb * Cfg::LO_STRIDE;                     // this buffer's 16-bit halos / fp32 lo
+            const uint64_t al0 = halo_desc(h_lo, SBO);
 #pragma unroll
             for (int i0 = Sched::first(ph); i0 < Sched::first(ph + 1); i0 += TPS) {
               mbar_wait(smem_u32(&b_full[st]), bphase);
@@ -291,9 +306,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const uint32_t shift16 = (uint32_t)(Sched::shift_px(Sched::tap(i), HALO_W) * 128) >> 4;   // compile-time after unrolling
                 const uint64_t ah = ah0 + (uint64_t)shift16;
                 const uint64_t bh = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP);
-                if (XM == 3) {
+                if (XM == 4) {
+                  // f16 main product + two bf16 corrections; halos [f16(a)][bf16(a)][bf16(a - f16(a))], filter [f16 w][bf16 w][bf16 r_w]
+                  constexpr uint32_t SBO16 = (uint32_t)HALO_W * 64u;
+                  const uint32_t px = (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;
+                  const uint64_t a_f = umma_desc_sw64(h_lo + px, SBO16), a_b = umma_desc_sw64(h_lo + T2_HALO16_BYTES + px, SBO16),
+                                 a_r = umma_desc_sw64(h_lo + 2 * T2_HALO16_BYTES + px, SBO16);
+                  const uint32_t bt = b_stage + (uint32_t)tt * Cfg::B_TAP;
+                  const uint64_t b_f = umma_desc_sw64(bt, 512u), b_b = umma_desc_sw64(bt + Cfg::B_TILE / 2, 512u),
+                                 b_r = umma_desc_sw64(bt + Cfg::B_TILE, 512u);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) mma16(d_tmem, a_f + (uint64_t)(2 * k), b_f + (uint64_t)(2 * k), Cfg::IDESCF, (cc | i | k) ? 1u : 0u);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) mma16(d_tmem, a_r + (uint64_t)(2 * k), b_b + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) mma16(d_tmem, a_b + (uint64_t)(2 * k), b_r + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
+                } else if (XM == 3) {
                   // bf16 only: A = the bf16 halo (first tile of the "lo" buffer), B = the bf16 filter tile
-                  const uint32_t h16 = h_hi + (uint32_t)HB * T2_HALO_STRIDE + (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;
+                  const uint32_t h16 = h_lo + (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;
                   const uint64_t a16 = umma_desc_sw64(h16, (uint32_t)HALO_W * 64u);
                   const uint64_t b16 = umma_desc_sw64(b_stage + (uint32_t)tt * Cfg::B_TAP, 512u);
 #pragma unroll
@@ -306,7 +336,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                   // corrections in bf16: A = the bf16 halos (64-byte pixel rows), B = the bf16 filter tiles; K = 16 per MMA
                   constexpr uint32_t SBO16 = (uint32_t)HALO_W * 64u;
                   const uint32_t px = (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;
-                  const uint32_t h16 = h_hi + (uint32_t)HB * T2_HALO_STRIDE;           // [bf16(a)][bf16(a - tf32(a))]
+                  const uint32_t h16 = h_lo;                                           // [bf16(a)][bf16(a - tf32(a))]
                   const uint64_t a_hi16 = umma_desc_sw64(h16 + px, SBO16), a_lo16 = umma_desc_sw64(h16 + T2_HALO16_BYTES + px, SBO16);
                   const uint32_t b16 = b_stage + (uint32_t)tt * Cfg::B_TAP + Cfg::B_TILE;
                   const uint64_t b_hi16 = umma_desc_sw64(b16, 512u), b_lo16 = umma_desc_sw64(b16 + Cfg::B_TILE / 2, 512u);
@@ -405,13 +435,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int hb = g % HB;
         mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((g / HB) & 1));
         float4* hi = reinterpret_cast<float4*>(base_ptr + (size_t)hb * T2_HALO_STRIDE);
-        float4* lo = reinterpret_cast<float4*>(base_ptr + (size_t)(HB + hb) * T2_HALO_STRIDE);
+        float4* lo = reinterpret_cast<float4*>(base_ptr + LO0 + (size_t)hb * Cfg::LO_STRIDE);
         if (XM >= 2) {
           // item = (pixel q, pair of adjacent 16-byte chunks): 8 channels.  The TMA wrote chunk c of pixel q at position
           // c ^ (q & 7), so positions (2j, 2j+1) hold the logical chunks (2j ^ r, 2j ^ r ^ 1), r = q & 7: logical 8-channel
           // group j ^ (r >> 1), halves swapped when r is odd.  Each group becomes one 16-byte chunk of the pixel's 64-byte
           // bf16 row, stored at chunk position group ^ ((row address >> 7) & 3)  (SWIZZLE_64B on absolute address bits).
-          const uint32_t lo_base = base + (uint32_t)(HB + hb) * T2_HALO_STRIDE;
+          const uint32_t lo_base = base + LO0 + (uint32_t)hb * Cfg::LO_STRIDE;
           uint8_t* lo_ptr = reinterpret_cast<uint8_t*>(lo);
           for (int i = tI; i < nvec / 2; i += 128) {
             const int q = i >> 2, j = i & 3, r = q & 7;
@@ -419,6 +449,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             // (two rows) touch 8 different 16-byte bank groups: {0,3,4,7} of the even row, {1,2,5,6} of the odd one
             const int f = (i ^ q) & 1;
             float4 va = hi[q * 8 + 2 * j + f], vb = hi[q * 8 + 2 * j + (f ^ 1)];
+            if (XM == 4) {                                     // three 16-bit halos: f16(a) (saturating), bf16(a), bf16(a - f16(a))
+              const float4 w0 = f ? vb : va, w1 = f ? va : vb;
+              uint4 f16v, a16, r16;
+              f16v.x = pack_f16x2_sat(w0.x, w0.y); f16v.y = pack_f16x2_sat(w0.z, w0.w); f16v.z = pack_f16x2_sat(w1.x, w1.y); f16v.w = pack_f16x2_sat(w1.z, w1.w);
+              a16.x = pack_bf16x2(w0.x, w0.y); a16.y = pack_bf16x2(w0.z, w0.w); a16.z = pack_bf16x2(w1.x, w1.y); a16.w = pack_bf16x2(w1.z, w1.w);
+              r16.x = pack_bf16x2(w0.x - f16_lo(f16v.x), w0.y - f16_hi(f16v.x)); r16.y = pack_bf16x2(w0.z - f16_lo(f16v.y), w0.w - f16_hi(f16v.y));
+              r16.z = pack_bf16x2(w1.x - f16_lo(f16v.z), w1.y - f16_hi(f16v.z)); r16.w = pack_bf16x2(w1.z - f16_lo(f16v.w), w1.w - f16_hi(f16v.w));
+              if (r & 1) {
+                f16v = make_uint4(f16v.z, f16v.w, f16v.x, f16v.y);
+                a16 = make_uint4(a16.z, a16.w, a16.x, a16.y);
+                r16 = make_uint4(r16.z, r16.w, r16.x, r16.y);
+              }
+              const uint32_t grp4 = (uint32_t)(j ^ (r >> 1));
+#pragma unroll
+              for (int tl = 0; tl < 3; ++tl) {
+                const uint32_t row4 = (uint32_t)tl * T2_HALO16_BYTES + (uint32_t)q * 64u;
+                *reinterpret_cast<uint4*>(lo_ptr + row4 + ((grp4 ^ (((lo_base + row4) >> 7) & 3u)) << 4)) = tl == 0 ? f16v : (tl == 1 ? a16 : r16);
+              }
+              continue;
+            }
             if (XM == 3) {                                     // bf16 only: convert, nothing else
               const float4 w0 = f ? vb : va, w1 = f ? va : vb;
               uint4 a16;
@@ -552,14 +602,14 @@ int dh_encode_tiled_f32(CUtensorMap* out, const void* ptr, int rank, const unsig
 
 namespace {
 template <int NT, int XM, int KS, int SD, int CG>
-int launch2k(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const CUtensorMap& B16, const T2Args& e, dim3 grid,
+int launch2k(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const CUtensorMap& B16, const CUtensorMap& B16f, const T2Args& e, dim3 grid,
              cudaStream_t s) {
   using Cfg = T2Cfg<NT, XM, CG>;
   auto kern = conv_tc2_kernel<NT, XM, KS, SD, CG>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   if (err != cudaSuccess) return (int)err;
   if (CG == 1) {
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, B16, e);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(A0, A1, Bm, B16, B16f, e);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(Cfg::THREADS, 1, 1); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
@@ -567,26 +617,26 @@ int launch2k(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    err = cudaLaunchKernelEx(&cfg, kern, A0, A1, Bm, B16, e);
+    err = cudaLaunchKernelEx(&cfg, kern, A0, A1, Bm, B16, B16f, e);
     if (err != cudaSuccess) return (int)err;
   }
   DH_CHECK_LAUNCH();
   return 0;
 }
 template <int NT, int XM, int CG>
-int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const CUtensorMap& B16, const T2Args& e, dim3 grid,
+int launch2(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const CUtensorMap& B16, const CUtensorMap& B16f, const T2Args& e, dim3 grid,
             cudaStream_t s) {
   if (e.stride == 2)
-    return e.ntaps == 9 ? launch2k<NT, XM, 3, 2, CG>(A0, A1, Bm, B16, e, grid, s) : launch2k<NT, XM, 1, 2, CG>(A0, A1, Bm, B16, e, grid, s);
-  return e.ntaps == 9 ? launch2k<NT, XM, 3, 1, CG>(A0, A1, Bm, B16, e, grid, s) : launch2k<NT, XM, 1, 1, CG>(A0, A1, Bm, B16, e, grid, s);
+    return e.ntaps == 9 ? launch2k<NT, XM, 3, 2, CG>(A0, A1, Bm, B16, B16f, e, grid, s) : launch2k<NT, XM, 1, 2, CG>(A0, A1, Bm, B16, B16f, e, grid, s);
+  return e.ntaps == 9 ? launch2k<NT, XM, 3, 1, CG>(A0, A1, Bm, B16, B16f, e, grid, s) : launch2k<NT, XM, 1, 1, CG>(A0, A1, Bm, B16, B16f, e, grid, s);
 }
 template <int XM, int CG>
-int launch2n(int NT, const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const CUtensorMap& B16, const T2Args& e,
+int launch2n(int NT, const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& Bm, const CUtensorMap& B16, const CUtensorMap& B16f, const T2Args& e,
              dim3 grid, cudaStream_t s) {
   switch (NT) {
-    case 128: return launch2<128, XM, CG>(A0, A1, Bm, B16, e, grid, s);
-    case 64: return launch2<64, XM, CG>(A0, A1, Bm, B16, e, grid, s);
-    default: return launch2<32, XM, CG>(A0, A1, Bm, B16, e, grid, s);
+    case 128: return launch2<128, XM, CG>(A0, A1, Bm, B16, B16f, e, grid, s);
+    case 64: return launch2<64, XM, CG>(A0, A1, Bm, B16, B16f, e, grid, s);
+    default: return launch2<32, XM, CG>(A0, A1, Bm, B16, B16f, e, grid, s);
   }
 }
 }  // namespace
@@ -602,6 +652,7 @@ bool dh_conv_tc2_eligible(const ConvArgs& a) {
 }
 
 // a.wt: [2][Cout][K] = TF32-rounded filter (hi) followed by its TF32-rounded remainder (lo); x3 uses both.
+// xm = 4: f16 main product + bf16 corrections (a.wt then carries a fourth plane: f16(w) | bf16(w - f16(w))).
 // xm: 0 = 1xTF32, 1 = 3xTF32 (three TF32 MMAs), 2 = 3xTF32 with the two correction products in bf16, 3 = bf16 operands only.
 // cg = 2: CTA pairs (tcgen05 cta_group::2): M = 256 per MMA, each CTA loads and reads only half of the filter tile
 // a.wt: [hi fp32 Cout*K][lo fp32 Cout*K][bf16(w) Cout*K][bf16(w - hi) Cout*K]  (engine.kmajor_split)
@@ -618,12 +669,17 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
   int rc = get_map2(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, hw, hh, a.stride);
   if (rc) return rc;
   if (a.C1) { rc = get_map2(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, hw, hh, a.stride); if (rc) return rc; } else A1 = A0;
-  cg = (cg == 2 && xm != 3) ? 2 : 1;
+  cg = (cg == 2 && xm != 3 && xm != 4) ? 2 : 1;
   rc = get_map2(&Bm, a.wt, 2, K, 2 * a.Cout, 1, 1, NT / cg, 1);  // rows [0,Cout) = hi, [Cout,2Cout) = lo
   if (rc) return rc;
   CUtensorMap B16 = Bm;
   if (xm >= 2) {                                                 // bf16 images follow the two fp32 ones
     rc = get_map2(&B16, a.wt + (size_t)2 * a.Cout * K, 2, K, 2 * a.Cout, 1, 1, NT / cg, 1, 1, true);
+    if (rc) return rc;
+  }
+  CUtensorMap B16f = B16;
+  if (xm == 4) {                                                 // fourth plane: f16(w) | bf16(w - f16(w))
+    rc = get_map2(&B16f, a.wt + (size_t)3 * a.Cout * K, 2, K, 2 * a.Cout, 1, 1, NT, 1, 1, true);
     if (rc) return rc;
   }
   T2Args e;
@@ -642,11 +698,12 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
   if (cg == 2) {
     const int pairs = sms / 2;
     dim3 grid((unsigned)(2 * (e.ntiles < pairs ? e.ntiles : pairs)), 1, 1);       // persistent: one CTA pair per TPC
-    if (xm == 2) return launch2n<2, 2>(NT, A0, A1, Bm, B16, e, grid, s);
-    return xm ? launch2n<1, 2>(NT, A0, A1, Bm, B16, e, grid, s) : launch2n<0, 2>(NT, A0, A1, Bm, B16, e, grid, s);
+    if (xm == 2) return launch2n<2, 2>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
+    return xm ? launch2n<1, 2>(NT, A0, A1, Bm, B16, B16f, e, grid, s) : launch2n<0, 2>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   }
   dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);          // persistent: one CTA per SM
-  if (xm == 3) return launch2n<3, 1>(NT, A0, A1, Bm, B16, e, grid, s);
-  if (xm == 2) return launch2n<2, 1>(NT, A0, A1, Bm, B16, e, grid, s);
-  return xm ? launch2n<1, 1>(NT, A0, A1, Bm, B16, e, grid, s) : launch2n<0, 1>(NT, A0, A1, Bm, B16, e, grid, s);
+  if (xm == 4) return launch2n<4, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
+  if (xm == 3) return launch2n<3, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
+  if (xm == 2) return launch2n<2, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
+  return xm ? launch2n<1, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s) : launch2n<0, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
 }

@@ -24,14 +24,20 @@ LEVELS = ((5, 256, 4, 4), (4, 128, 4, 4), (3, 64, 8, 8))   # (k, trunk channels,
 DH_VARIANT_LEVIR, DH_VARIANT_XBD = 0, 1
 DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC, DH_FLAG_STEM_TC, DH_FLAG_DEC_TC_X3 = 1, 2, 4, 8, 16, 32
 DH_FLAG_CONV_TC_V1, DH_FLAG_CONV_TC_2CTA, DH_FLAG_SERIAL, DH_FLAG_TC_X3_BF16, DH_FLAG_TC_BF16 = 64, 128, 256, 512, 1024
+DH_FLAG_TC_MAIN_F16 = 2048
 MODES = {
     "fp32": 0,                                             # every contraction in fp32 FMA (strict)
     "fp32_tcdec": DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,      # strict + the 3xTF32 (fp32-grade) tensor-core decoder
-    # fp32-grade accuracy on the tensor cores: error-compensated 3xTF32 for every convolution (stride 2 included), the
-    # 7x7 stem and the pixel decoder
-    # (the convolutions' two correction products run as BF16 MMAs: same accuracy, a third fewer tensor-core cycles)
-    "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC
-              | DH_FLAG_DEC_TC_X3,
+    # fp32-grade accuracy on the tensor cores: every product is error-compensated (three partial products, fp32
+    # accumulation).  Convolutions: main product in FP16 (11-bit significand like TF32, 16-bit operands), the two
+    # correction products in BF16 (fp32 exponent range) — half the tensor-core cycles of three TF32 products and a
+    # slightly smaller error.  Operands beyond the FP16 range (|v| > 65504, or < 1e-7) fall back on the BF16 terms
+    # (bf16-grade accuracy for those values only).  7x7 stem and pixel decoder: 3xTF32.
+    "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC
+              | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
+    # the same with the main product in TF32 (no range caveat, ~10 % slower)
+    "tf32x3_tf32main": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC
+                       | DH_FLAG_DEC_TC_X3,
     "tf32x3_pure": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     # reduced precision: BF16 operands in every convolution (fp32 storage / accumulation), 1xTF32 stem, 3xTF32 decoder
@@ -115,7 +121,7 @@ def tf32_split(x):
 
 
 def kmajor_split(wt):
-    """K-major filter [Cout][K] (float64) -> float32 [3][Cout][K]:
+    """K-major filter [Cout][K] (float64) -> float32 [4][Cout][K]:
       plane 0  TF32-rounded values (B_hi; all the 1xTF32 kernels read)
       plane 1  their TF32-rounded remainders (B_lo of the 3xTF32 kernels)
       plane 2  raw bits of a bf16 [2][Cout][K] array: bf16(w) and bf16(w - B_hi), the filter operands of the two
@@ -124,7 +130,12 @@ def kmajor_split(wt):
     hi, lo = tf32_split(wt)
     b16 = torch.stack([wt, wt - hi]).to(torch.float32).to(torch.bfloat16).contiguous()       # [2][Cout][K] bf16
     packed = b16.view(torch.int16).reshape(-1).view(torch.float32).reshape(wt.shape)          # same bytes as [Cout][K] fp32
-    return torch.cat([torch.stack([hi, lo]).to(torch.float32), packed[None]])
+    # plane 3: f16(w) (saturated to the f16 range) and bf16(w - f16(w)) for the FP16-main-product mode
+    h16 = wt.clamp(-65504.0, 65504.0).to(torch.float32).to(torch.float16)
+    r16 = (wt - h16.double()).to(torch.float32).to(torch.bfloat16)
+    packed_f = torch.cat([h16.contiguous().view(torch.int16).reshape(-1), r16.contiguous().view(torch.int16).reshape(-1)]) \
+        .view(torch.float32).reshape(wt.shape)
+    return torch.cat([torch.stack([hi, lo]).to(torch.float32), packed[None], packed_f[None]])
 
 
 def stem_tc_image(w147):

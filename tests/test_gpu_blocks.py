@@ -84,7 +84,7 @@ def test_conv2d_up2_tcgen05(shape):
     wt, pb = upsample_phase_filter(w, b)
     wt = kmajor_split(wt).float().contiguous().to(DEV)
     ref = F.relu(F.conv2d(x.double().cpu().permute(0, 3, 1, 2).repeat_interleave(2, 2).repeat_interleave(2, 3), w, b, 1, 1))
-    for flags, tol in ((0, 4e-3), (64, 4e-3), (2, 2e-5), (128, 4e-3), (130, 2e-5), (514, 6e-5), (642, 6e-5), (1024, 4e-2)):   # halo-reuse 1xTF32, per-tap kernel, 3xTF32, CTA pairs, bf16 corrections, bf16 operands
+    for flags, tol in ((0, 4e-3), (64, 4e-3), (2, 2e-5), (128, 4e-3), (130, 2e-5), (514, 6e-5), (642, 6e-5), (1024, 4e-2), (2562, 6e-5)):   # halo-reuse 1xTF32, per-tap kernel, 3xTF32, CTA pairs, bf16 corrections, bf16 operands, f16 main
         y = abi.conv2d_up2_tc(x, wt, pb.float().to(DEV), True, flags)
         torch.cuda.synchronize()
         close(y, ref.permute(0, 2, 3, 1), rtol=tol / 2, atol=tol)
@@ -100,12 +100,31 @@ def test_conv2d_stride2_tcgen05(cfg):
     b = rnd(Cout, seed=4)
     ref = E.conv_nhwc(x.double(), w.double(), b.double(), K, 2, K // 2, None, True, 1)
     # flags: 1|4 = halo-reuse kernel on the four phase images (1xTF32), 1|4|2 = same with 3xTF32, 1|4|64 = per-tap kernel
-    for flags, tol in ((5, 4e-3), (7, 2e-5), (69, 4e-3), (133, 4e-3), (135, 2e-5), (519, 6e-5), (647, 6e-5), (1029, 4e-2)):   # + 128: CTA pairs; + 512: bf16 corrections; 1024: bf16 operands
+    for flags, tol in ((5, 4e-3), (7, 2e-5), (69, 4e-3), (133, 4e-3), (135, 2e-5), (519, 6e-5), (647, 6e-5), (1029, 4e-2), (2567, 6e-5)):   # + 128: CTA pairs; + 512: bf16 corrections; 1024: bf16 operands; 2048: f16 main product
         y = abi.conv2d(x, None, w, b, None, True, K, 2, K // 2, 1, flags=flags)
         torch.cuda.synchronize()
         assert y.shape == ref.shape
         print(f"[tc] stride-2 {cfg} flags={flags}: max|d|={float((y.double() - ref).abs().max()):.3e}")
         close(y, ref, rtol=tol / 2, atol=tol if not (flags & 2) else tol * float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("scale,tol", [(1.0, 6e-5), (1e-6, 6e-5), (3e4, 6e-3), (1e-9, 6e-3)])
+def test_conv2d_f16_main_operand_range(scale, tol):
+    """default error-compensated mode (FP16 main product + BF16 corrections): operands far outside the FP16 range stay
+    finite and fall back on the BF16 terms — fp32-grade inside [1e-7, 65504], bf16-grade (stated: 6e-3 of the output
+    range) beyond; the TF32-main variant (flags without 2048) has no such caveat."""
+    N, H, W, C, Cout, K = 1, 32, 32, 64, 64, 3
+    x = rnd(N, H, W, C, seed=1) * scale
+    w = rnd(K * K * C, Cout, seed=3, scale=(K * K * C) ** -0.5)
+    ref = E.conv_nhwc(x.double(), w.double(), None, K, 1, 1, None, False, 1)
+    y = abi.conv2d(x, None, w, None, None, False, K, 1, 1, 1, flags=2563)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    err = float((y.double().cpu() - ref.cpu()).abs().max()) / float(ref.abs().max())
+    print(f"[tc] f16-main operand scale {scale:g}: max|d| / max|ref| = {err:.3e}")
+    assert err <= tol
+    y2 = abi.conv2d(x, None, w, None, None, False, K, 1, 1, 1, flags=515)      # TF32 main product: range-independent
+    assert float((y2.double().cpu() - ref.cpu()).abs().max()) / float(ref.abs().max()) <= 6e-5
 
 
 @pytest.mark.parametrize("cfg", TC_CONVS)
@@ -124,7 +143,8 @@ def test_conv2d_tcgen05(cfg):
     # flags: 1 = halo-reuse kernel 1xTF32, 1|64 = per-tap kernel 1xTF32, 1|2 = halo-reuse kernel 3xTF32
     for flags, name, tol in ((1, "halo 1xTF32", 4e-3), (65, "per-tap 1xTF32", 4e-3), (3, "halo 3xTF32", 2e-5),
                              (129, "pair 1xTF32", 4e-3), (131, "pair 3xTF32", 2e-5), (515, "3xTF32 bf16-corr", 6e-5),
-                             (643, "pair 3xTF32 bf16-corr", 6e-5), (1025, "bf16 operands", 4e-2)):
+                             (643, "pair 3xTF32 bf16-corr", 6e-5), (1025, "bf16 operands", 4e-2),
+                             (2563, "f16 main + bf16 corr", 6e-5)):
         y = abi.conv2d(x0, x1, w, b, r, relu, K, 1, K // 2, 1, flags=flags)
         torch.cuda.synchronize()
         d = (y.double().cpu() - ref.cpu()).abs()

@@ -164,7 +164,7 @@ def test_precision_mode_selection(monkeypatch):
     e.set_mode(29)
     assert e.mode == "tf32_fast"
     with pytest.raises(ValueError):
-        e.set_mode("bf16")
+        e.set_mode("int8")
     monkeypatch.setenv("DAHITRA_MODE", "tf32")
     assert E.NativeEngine().flags == E.MODES["tf32"]
     monkeypatch.setenv("DAHITRA_FLAGS", "0")
