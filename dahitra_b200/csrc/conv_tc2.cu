@@ -70,12 +70,13 @@ template <int NT, int XM, int CG = 1> struct T2Cfg {
   // halo buffers (HB) and filter stages it gets.  A stage holds TPS filter taps so the issuing thread waits /
   // commits once per 4*TPS (x3: 12*TPS) MMAs.
   static constexpr int HB = X3 ? 2 : (NT == 128 ? 2 : (NT == 64 ? 3 : 4));          // halo chunk buffers (x3: hi + lo each)
-  static constexpr int TPS = XM == 3 ? 3 : (X3 ? (NT == 32 ? 3 : 1) : 3);
-  static constexpr int STAGES1 = XM == 3 ? (NT == 128 ? 4 : (NT == 64 ? 6 : 8))
+  static constexpr bool ONE16 = (XM == 3 || XM == 5);   // single-pass 16-bit operands: 3 = bf16, 5 = f16 (saturating)
+  static constexpr int TPS = ONE16 ? 3 : (X3 ? (NT == 32 ? 3 : 1) : 3);
+  static constexpr int STAGES1 = ONE16 ? (NT == 128 ? 4 : (NT == 64 ? 6 : 8))
                                : (X3 ? (NT == 128 ? 3 : (NT == 64 ? 6 : 4)) : (NT == 128 ? 3 : (NT == 64 ? 5 : 8)));
   static constexpr int STAGES = CG == 2 ? (2 * STAGES1 > 8 ? 8 : 2 * STAGES1) : STAGES1;   // CTA pair: half-size B tiles
   static constexpr uint32_t B_TILE = (NT / CG) * 128;           // a CTA of a pair holds N/2 rows of B
-  static constexpr uint32_t B_TAP = XM == 3 ? B_TILE / 2 : (XM == 4 ? 3 * (B_TILE / 2) : B_TILE * (X3 ? 2 : 1));
+  static constexpr uint32_t B_TAP = ONE16 ? B_TILE / 2 : (XM == 4 ? 3 * (B_TILE / 2) : B_TILE * (X3 ? 2 : 1));
   // XM 0: fp32 | 1: fp32 hi, lo | 2: fp32 hi, bf16 hi, lo | 3: bf16 | 4: f16, bf16 hi, bf16 lo
   static constexpr uint32_t LO_STRIDE = XM == 4 ? 35840u : 23552u;   // the 16-bit halos of one buffer (XM = 4: three of 11520 B)
   static constexpr uint32_t IDESCF = umma_idesc_f16(128 * CG, NT);
@@ -135,7 +136,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmB16f, const T2Args e) {
   using Cfg = T2Cfg<NT, XM, CG>;
   constexpr bool X3 = XM != 0;
-  static_assert((XM != 3 && XM != 4) || CG == 1, "the 16-bit-main modes are implemented for single-CTA tiles");
+  static_assert((XM != 3 && XM != 4 && XM != 5) || CG == 1, "the 16-bit-main modes are implemented for single-CTA tiles");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t2_raw[];
   constexpr int HB = Cfg::HB;
@@ -245,6 +246,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 tma_load_2d(dst, &tmB16f, bar, kcol, nrow);                                        // f16(w)
                 tma_load_2d(dst + Cfg::B_TILE / 2, &tmB16, bar, kcol, nrow);                       // bf16(w)
                 tma_load_2d(dst + Cfg::B_TILE, &tmB16f, bar, kcol, e.Cout + nrow);                 // bf16(w - f16(w))
+              } else if (XM == 5) {
+                tma_load_2d(dst, &tmB16f, bar, kcol, nrow);                                        // f16(w) only
               } else if (XM == 3) {
                 tma_load_2d(dst, &tmB16, bar, kcol, nrow);                                         // bf16(w) only
               } else if (XM == 2) {
@@ -321,13 +324,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                   for (int k = 0; k < 2; ++k) mma16(d_tmem, a_r + (uint64_t)(2 * k), b_b + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
 #pragma unroll
                   for (int k = 0; k < 2; ++k) mma16(d_tmem, a_b + (uint64_t)(2 * k), b_r + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
-                } else if (XM == 3) {
-                  // bf16 only: A = the bf16 halo (first tile of the "lo" buffer), B = the bf16 filter tile
+                } else if (XM == 3 || XM == 5) {
+                  // single-pass 16-bit operands: A = the bf16 / f16 halo (first tile of the "lo" buffer), B = the matching filter tile
                   const uint32_t h16 = h_lo + (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;
                   const uint64_t a16 = umma_desc_sw64(h16, (uint32_t)HALO_W * 64u);
                   const uint64_t b16 = umma_desc_sw64(b_stage + (uint32_t)tt * Cfg::B_TAP, 512u);
 #pragma unroll
-                  for (int k = 0; k < 2; ++k) mma16(d_tmem, a16 + (uint64_t)(2 * k), b16 + (uint64_t)(2 * k), Cfg::IDESC16, (cc | i | k) ? 1u : 0u);
+                  for (int k = 0; k < 2; ++k)
+                    mma16(d_tmem, a16 + (uint64_t)(2 * k), b16 + (uint64_t)(2 * k), XM == 5 ? Cfg::IDESCF : Cfg::IDESC16, (cc | i | k) ? 1u : 0u);
                 } else {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) mma(d_tmem, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), Cfg::IDESC, (cc | i | k) ? 1u : 0u);
@@ -469,10 +473,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               }
               continue;
             }
-            if (XM == 3) {                                     // bf16 only: convert, nothing else
+            if (XM == 3 || XM == 5) {                          // single-pass 16-bit operands: convert, nothing else
               const float4 w0 = f ? vb : va, w1 = f ? va : vb;
               uint4 a16;
-              a16.x = pack_bf16x2(w0.x, w0.y); a16.y = pack_bf16x2(w0.z, w0.w); a16.z = pack_bf16x2(w1.x, w1.y); a16.w = pack_bf16x2(w1.z, w1.w);
+              if (XM == 5) {
+                a16.x = pack_f16x2_sat(w0.x, w0.y); a16.y = pack_f16x2_sat(w0.z, w0.w); a16.z = pack_f16x2_sat(w1.x, w1.y); a16.w = pack_f16x2_sat(w1.z, w1.w);
+              } else {
+                a16.x = pack_bf16x2(w0.x, w0.y); a16.y = pack_bf16x2(w0.z, w0.w); a16.z = pack_bf16x2(w1.x, w1.y); a16.w = pack_bf16x2(w1.z, w1.w);
+              }
               if (r & 1) a16 = make_uint4(a16.z, a16.w, a16.x, a16.y);
               const uint32_t grp3 = (uint32_t)(j ^ (r >> 1)), row3 = (uint32_t)q * 64u;
               *reinterpret_cast<uint4*>(lo_ptr + row3 + ((grp3 ^ (((lo_base + row3) >> 7) & 3u)) << 4)) = a16;
@@ -652,6 +660,7 @@ bool dh_conv_tc2_eligible(const ConvArgs& a) {
 }
 
 // a.wt: [2][Cout][K] = TF32-rounded filter (hi) followed by its TF32-rounded remainder (lo); x3 uses both.
+// xm = 5: single-pass f16 operands (saturating; TF32-grade significand at bf16-mode cost).
 // xm = 4: f16 main product + bf16 corrections (a.wt then carries a fourth plane: f16(w) | bf16(w - f16(w))).
 // xm: 0 = 1xTF32, 1 = 3xTF32 (three TF32 MMAs), 2 = 3xTF32 with the two correction products in bf16, 3 = bf16 operands only.
 // cg = 2: CTA pairs (tcgen05 cta_group::2): M = 256 per MMA, each CTA loads and reads only half of the filter tile
@@ -669,7 +678,7 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
   int rc = get_map2(&A0, a.in0, 4, a.C0, a.inW, a.inH, a.N, hw, hh, a.stride);
   if (rc) return rc;
   if (a.C1) { rc = get_map2(&A1, a.in1, 4, a.C1, a.inW, a.inH, a.N, hw, hh, a.stride); if (rc) return rc; } else A1 = A0;
-  cg = (cg == 2 && xm != 3 && xm != 4) ? 2 : 1;
+  cg = (cg == 2 && xm < 3) ? 2 : 1;
   rc = get_map2(&Bm, a.wt, 2, K, 2 * a.Cout, 1, 1, NT / cg, 1);  // rows [0,Cout) = hi, [Cout,2Cout) = lo
   if (rc) return rc;
   CUtensorMap B16 = Bm;
@@ -678,7 +687,7 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
     if (rc) return rc;
   }
   CUtensorMap B16f = B16;
-  if (xm == 4) {                                                 // fourth plane: f16(w) | bf16(w - f16(w))
+  if (xm == 4 || xm == 5) {                                      // fourth plane: f16(w) | bf16(w - f16(w))
     rc = get_map2(&B16f, a.wt + (size_t)3 * a.Cout * K, 2, K, 2 * a.Cout, 1, 1, NT, 1, 1, true);
     if (rc) return rc;
   }
@@ -702,6 +711,7 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
     return xm ? launch2n<1, 2>(NT, A0, A1, Bm, B16, B16f, e, grid, s) : launch2n<0, 2>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   }
   dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);          // persistent: one CTA per SM
+  if (xm == 5) return launch2n<5, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   if (xm == 4) return launch2n<4, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   if (xm == 3) return launch2n<3, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   if (xm == 2) return launch2n<2, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);

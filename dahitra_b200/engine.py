@@ -40,6 +40,9 @@ MODES = {
                        | DH_FLAG_DEC_TC_X3,
     "tf32x3_pure": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
+    # single-pass FP16 operands in the convolutions (TF32-grade significand, half the operand bytes of "tf32";
+    # saturating outside +-65504), 1xTF32 stem, 3xTF32 decoder
+    "f16": DH_FLAG_CONV_TC | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     # reduced precision: BF16 operands in every convolution (fp32 storage / accumulation), 1xTF32 stem, 3xTF32 decoder
     "bf16": DH_FLAG_CONV_TC | DH_FLAG_TC_BF16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32_fast": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC,   # 1xTF32 decoder too

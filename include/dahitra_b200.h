@@ -57,7 +57,7 @@ extern "C" {
 #define DH_FLAG_SERIAL      256 /* keep every launch on the caller's stream (no fork of levels 4 / 3 onto the library's side streams) */
 #define DH_FLAG_TC_X3_BF16  512 /* with TC_3XTF32: the two correction products of every conv as BF16 MMAs (half their cost) */
 #define DH_FLAG_TC_BF16     1024 /* with CONV_TC: single-pass BF16 operands in the convolutions (fp32 storage and accumulation); overrides TC_3XTF32 */
-#define DH_FLAG_TC_MAIN_F16 2048 /* with TC_3XTF32: main product of every conv in FP16 (K = 16 MMAs), both corrections in BF16 */
+#define DH_FLAG_TC_MAIN_F16 2048 /* with TC_3XTF32: main product of every conv in FP16 (K = 16 MMAs), both corrections in BF16; without it: single-pass FP16 operands */
 #define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC | DH_FLAG_STEM_TC)   /* the "tf32" mode */
 
 /* ---- prepared-weight table -------------------------------------------------------------------

@@ -211,7 +211,7 @@ def test_weight_updates_are_seen(levir_template):
         assert torch.equal(net(x1, x2), yb)
 
 
-@pytest.mark.parametrize("mode", ["tf32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32", "f16", "bf16"])
 @pytest.mark.parametrize("weights", ["defineG", "default"])
 def test_tensor_core_modes(mode, weights, levir_template):
     """The two tensor-core modes (dahitra_b200.engine.MODES), fp32 storage and fp32 accumulation in both:
@@ -220,6 +220,7 @@ def test_tensor_core_modes(mode, weights, levir_template):
                benchmark's define_G weights; on the ill-conditioned default-scale synthetic weights (where the reference's own
                fp32 arithmetic is already 1.3e-4 off its fp64 self) it must stay within 1e-3 of the logit range and >= 99.99 %
                argmax agreement.
+      f16    — like tf32 with FP16 conv operands (same 11-bit significand, half the operand bytes); same bar as tf32.
       tf32   — single-pass TF32 everywhere.  Strict tolerance on the define_G weights; on the ill-conditioned weights no worse
                than 3x eager PyTorch with its TF32 switches on (cuDNN TF32 is PyTorch's default, i.e. what a reference user
                gets on this GPU)."""
