@@ -58,7 +58,12 @@ extern "C" {
 #define DH_FLAG_TC_X3_BF16  512 /* with TC_3XTF32: the two correction products of every conv as BF16 MMAs (half their cost) */
 #define DH_FLAG_TC_BF16     1024 /* with CONV_TC: single-pass BF16 operands in the convolutions (fp32 storage and accumulation); overrides TC_3XTF32 */
 #define DH_FLAG_TC_MAIN_F16 2048 /* with TC_3XTF32: main product of every conv in FP16 (K = 16 MMAs), both corrections in BF16; without it: single-pass FP16 operands */
-#define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_DEC_TC | DH_FLAG_STEM_TC)   /* the "tf32" mode */
+/* the modes dahitra_b200.engine.MODES names (DESIGN.md "Precision modes") */
+#define DH_FLAGS_TF32X3     (DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_STRIDE2 | \
+                             DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3)   /* default: every product error-compensated, fp32-grade */
+#define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3)   /* single-pass TF32 convs */
+#define DH_FLAGS_F16        (DH_FLAGS_TF32 | DH_FLAG_TC_MAIN_F16)                    /* single-pass FP16 conv operands */
+#define DH_FLAGS_BF16       (DH_FLAGS_TF32 | DH_FLAG_TC_BF16)                        /* single-pass BF16 conv operands */
 
 /* ---- prepared-weight table -------------------------------------------------------------------
  * dahitra_forward takes `const void* const* weights` with DH_W_COUNT slots, each a device pointer to

@@ -169,3 +169,22 @@ def test_precision_mode_selection(monkeypatch):
     assert E.NativeEngine().flags == E.MODES["tf32"]
     monkeypatch.setenv("DAHITRA_FLAGS", "0")
     assert E.NativeEngine().mode == "fp32"
+
+
+def test_header_is_plain_c_and_mode_macros_match_engine(tmp_path):
+    """include/dahitra_b200.h compiles as C (the drop-in boundary is a C ABI) and its DH_FLAGS_* mode macros are the
+    bitmasks dahitra_b200.engine.MODES uses."""
+    import shutil
+    import subprocess
+    from dahitra_b200 import engine as E
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "chk.c"
+    src.write_text('#include "dahitra_b200.h"\n#include <stdio.h>\n'
+                   'int main(void){ printf("%d %d %d %d %d\\n", DH_FLAGS_TF32X3, DH_FLAGS_TF32, DH_FLAGS_F16, DH_FLAGS_BF16, (int)DH_W_COUNT); return 0; }\n')
+    exe = tmp_path / "chk"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(v) for v in out[:4]] == [E.MODES["tf32x3"], E.MODES["tf32"], E.MODES["f16"], E.MODES["bf16"]]
+    assert int(out[4]) == len(E.slot_names())
