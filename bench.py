@@ -274,7 +274,7 @@ def run_native(a, wl):
                           argmax_agree=float((y_mode.argmax(1) == y_ref.argmax(1)).float().mean()))
             # the other shipped modes on the same workload (5 steps each): throughput + their own parity against fp32
             strict = {}
-            for other in ("fp32", "tf32"):
+            for other in ("fp32", "tf32", "f16"):
                 if MODES[other] == saved:
                     continue
                 net._engine.flags = MODES[other]
