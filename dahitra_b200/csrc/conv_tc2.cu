@@ -29,6 +29,12 @@
 // beyond the f16 range — saturated to +-65504 — or below its normal range only cost accuracy of the correction terms).
 // Per (tap, chunk): 2 FP16 + 2 + 2 BF16 MMAs.  The splitter writes three 16-bit halos: f16(a), bf16(a), bf16(a - f16(a)).
 //
+// XM = 6: XM = 4 with the third product folded into the first.  a.w = f16(a).f16(w) + r_a.bf16(w) + f16(a).r_w: the first
+// and third products share the A operand, so the filter tile is the 2N-row concatenation [f16(w) ; f16(2^11 r_w)] and ONE
+// N-doubled FP16 MMA produces both (the scaled remainder keeps r_w in the normal FP16 range); they land in two column
+// blocks of the accumulator and the epilogue adds them (main + 2^-11 corr).  Per (tap, chunk): 2 wide + 2 narrow MMAs
+// instead of 6 — a third fewer A-operand reads, which is what bounds the N = 32 / 64 tiles.  Two 16-bit halos only.
+//
 // XM = 3 ("bf16"): single-pass BF16 operands (fp32 storage, fp32 accumulation): the splitter only converts the halo to
 // the bf16 tile, the ring only carries bf16(w); 2 MMAs per (tap, chunk).  Separately stated tolerance (tests).
 //
@@ -76,10 +82,13 @@ template <int NT, int XM, int CG = 1> struct T2Cfg {
                                : (X3 ? (NT == 128 ? 3 : (NT == 64 ? 6 : 4)) : (NT == 128 ? 3 : (NT == 64 ? 5 : 8)));
   static constexpr int STAGES = CG == 2 ? (2 * STAGES1 > 8 ? 8 : 2 * STAGES1) : STAGES1;   // CTA pair: half-size B tiles
   static constexpr uint32_t B_TILE = (NT / CG) * 128;           // a CTA of a pair holds N/2 rows of B
-  static constexpr uint32_t B_TAP = ONE16 ? B_TILE / 2 : (XM == 4 ? 3 * (B_TILE / 2) : B_TILE * (X3 ? 2 : 1));
+  static constexpr bool WIDE = XM == 6;             // accumulator = [main + corr2 | 2^11 corr3]: 2 NT columns
+  static constexpr uint32_t B_TAP = ONE16 ? B_TILE / 2 : ((XM == 4 || XM == 6) ? 3 * (B_TILE / 2) : B_TILE * (X3 ? 2 : 1));
   // XM 0: fp32 | 1: fp32 hi, lo | 2: fp32 hi, bf16 hi, lo | 3: bf16 | 4: f16, bf16 hi, bf16 lo
   static constexpr uint32_t LO_STRIDE = XM == 4 ? 35840u : 23552u;   // the 16-bit halos of one buffer (XM = 4: three of 11520 B)
   static constexpr uint32_t IDESCF = umma_idesc_f16(128 * CG, NT);
+  static constexpr uint32_t IDESCF_WIDE = umma_idesc_f16(128 * CG, 2 * NT);
+  static constexpr int ACC_COLS = WIDE ? 2 * NT : NT;                       // TMEM columns of one accumulator
   static constexpr uint32_t IDESC16 = umma_idesc_bf16(128 * CG, NT);
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
   static constexpr uint32_t HALO_BYTES = HB * T2_HALO_STRIDE + (X3 ? HB * LO_STRIDE : 0);   // [hi 0..HB-1][lo 0..HB-1]
@@ -87,7 +96,7 @@ template <int NT, int XM, int CG = 1> struct T2Cfg {
   static constexpr uint32_t SMEM = EPI_OFF + 4 * 4096 + 1024;
   static constexpr int THREADS = X3 ? 352 : 224;                // + 4 splitter warps
   static constexpr uint32_t IDESC = umma_idesc_tf32(128 * CG, NT);
-  static constexpr uint32_t TMEM_COLS = (2 * NT < 32) ? 32 : 2 * NT;   // two accumulators
+  static constexpr uint32_t TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;   // two accumulators
 };
 
 __device__ __forceinline__ float tf32_rna(float v) { return tf32_round(v); }
@@ -136,7 +145,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmB16f, const T2Args e) {
   using Cfg = T2Cfg<NT, XM, CG>;
   constexpr bool X3 = XM != 0;
-  static_assert((XM != 3 && XM != 4 && XM != 5) || CG == 1, "the 16-bit-main modes are implemented for single-CTA tiles");
+  static_assert(XM < 3 || CG == 1, "the 16-bit-main modes are implemented for single-CTA tiles");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t2_raw[];
   constexpr int HB = Cfg::HB;
@@ -242,6 +251,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 } else if (X3) {
                   tma_load_2d_2sm(dst + Cfg::B_TILE, &tmB, lbar, kcol, e.Cout + nrow);
                 }
+              } else if (XM == 6) {
+                tma_load_2d(dst, &tmB16f, bar, kcol, nrow);                                        // f16(w)            \ one 2N-row
+                tma_load_2d(dst + Cfg::B_TILE / 2, &tmB, bar, kcol, nrow);                         // f16(2^11 r_w)     /  B tile   (tmB = plane 4 here)
+                tma_load_2d(dst + Cfg::B_TILE, &tmB16, bar, kcol, nrow);                           // bf16(w)
               } else if (XM == 4) {
                 tma_load_2d(dst, &tmB16f, bar, kcol, nrow);                                        // f16(w)
                 tma_load_2d(dst + Cfg::B_TILE / 2, &tmB16, bar, kcol, nrow);                       // bf16(w)
@@ -286,7 +299,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         if (CG == 2) mbar_wait_cluster(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));
         else         mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));    // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)ab * NT;
+        const uint32_t d_tmem = tmem_base + (uint32_t)ab * Cfg::ACC_COLS;
         for (int cc = 0; cc < e.cchunks; ++cc) {
 #pragma unroll
           for (int ph = 0; ph < NPH; ++ph) {
@@ -309,7 +322,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const uint32_t shift16 = (uint32_t)(Sched::shift_px(Sched::tap(i), HALO_W) * 128) >> 4;   // compile-time after unrolling
                 const uint64_t ah = ah0 + (uint64_t)shift16;
                 const uint64_t bh = umma_desc_sw128(b_stage + (uint32_t)tt * Cfg::B_TAP);
-                if (XM == 4) {
+                if (XM == 6) {
+                  // [f16(a)] x [f16 w ; f16 2^11 r_w] as one 2N-wide MMA, then [bf16 r_a] x [bf16 w] into the first N columns
+                  constexpr uint32_t SBO16 = (uint32_t)HALO_W * 64u;
+                  const uint32_t px = (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;
+                  const uint64_t a_f = umma_desc_sw64(h_lo + px, SBO16), a_r = umma_desc_sw64(h_lo + T2_HALO16_BYTES + px, SBO16);
+                  const uint32_t bt = b_stage + (uint32_t)tt * Cfg::B_TAP;
+                  const uint64_t b_w = umma_desc_sw64(bt, 512u), b_b = umma_desc_sw64(bt + Cfg::B_TILE, 512u);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) mma16(d_tmem, a_f + (uint64_t)(2 * k), b_w + (uint64_t)(2 * k), Cfg::IDESCF_WIDE, (cc | i | k) ? 1u : 0u);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) mma16(d_tmem, a_r + (uint64_t)(2 * k), b_b + (uint64_t)(2 * k), Cfg::IDESC16, 1u);
+                } else if (XM == 4) {
                   // f16 main product + two bf16 corrections; halos [f16(a)][bf16(a)][bf16(a - f16(a))], filter [f16 w][bf16 w][bf16 r_w]
                   constexpr uint32_t SBO16 = (uint32_t)HALO_W * 64u;
                   const uint32_t px = (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;
@@ -404,7 +428,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e.bias) bia = ldg4(e.bias + t.n0 + j * 32 + c8 * 4);
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * NT + j * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACC_COLS + j * 32), v);
+        if (Cfg::WIDE) {                                         // second column block: 2^11 x the f16(a).r_w correction
+          uint32_t u[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACC_COLS + NT + j * 32), u);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(fmaf(__uint_as_float(u[c]), 1.0f / 2048.0f, __uint_as_float(v[c])));
+        }
         if (j == NT / 32 - 1) {                                  // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[ab]), 0));
@@ -453,7 +483,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             // (two rows) touch 8 different 16-byte bank groups: {0,3,4,7} of the even row, {1,2,5,6} of the odd one
             const int f = (i ^ q) & 1;
             float4 va = hi[q * 8 + 2 * j + f], vb = hi[q * 8 + 2 * j + (f ^ 1)];
-            if (XM == 4) {                                     // three 16-bit halos: f16(a) (saturating), bf16(a), bf16(a - f16(a))
+            if (XM == 4 || XM == 6) {                          // 16-bit halos: f16(a) (saturating), [XM 4: bf16(a),] bf16(a - f16(a))
               const float4 w0 = f ? vb : va, w1 = f ? va : vb;
               uint4 f16v, a16, r16;
               f16v.x = pack_f16x2_sat(w0.x, w0.y); f16v.y = pack_f16x2_sat(w0.z, w0.w); f16v.z = pack_f16x2_sat(w1.x, w1.y); f16v.w = pack_f16x2_sat(w1.z, w1.w);
@@ -467,9 +497,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               }
               const uint32_t grp4 = (uint32_t)(j ^ (r >> 1));
 #pragma unroll
-              for (int tl = 0; tl < 3; ++tl) {
+              for (int tl = 0; tl < (XM == 6 ? 2 : 3); ++tl) {
                 const uint32_t row4 = (uint32_t)tl * T2_HALO16_BYTES + (uint32_t)q * 64u;
-                *reinterpret_cast<uint4*>(lo_ptr + row4 + ((grp4 ^ (((lo_base + row4) >> 7) & 3u)) << 4)) = tl == 0 ? f16v : (tl == 1 ? a16 : r16);
+                *reinterpret_cast<uint4*>(lo_ptr + row4 + ((grp4 ^ (((lo_base + row4) >> 7) & 3u)) << 4)) =
+                    tl == 0 ? f16v : ((tl == 1 && XM == 4) ? a16 : r16);
               }
               continue;
             }
@@ -660,6 +691,7 @@ bool dh_conv_tc2_eligible(const ConvArgs& a) {
 }
 
 // a.wt: [2][Cout][K] = TF32-rounded filter (hi) followed by its TF32-rounded remainder (lo); x3 uses both.
+// xm = 6: xm = 4 with the f16(a).r_w correction folded into the main MMA (fifth plane of a.wt: f16(2^11 (w - f16(w)))).
 // xm = 5: single-pass f16 operands (saturating; TF32-grade significand at bf16-mode cost).
 // xm = 4: f16 main product + bf16 corrections (a.wt then carries a fourth plane: f16(w) | bf16(w - f16(w))).
 // xm: 0 = 1xTF32, 1 = 3xTF32 (three TF32 MMAs), 2 = 3xTF32 with the two correction products in bf16, 3 = bf16 operands only.
@@ -687,8 +719,12 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
     if (rc) return rc;
   }
   CUtensorMap B16f = B16;
-  if (xm == 4 || xm == 5) {                                      // fourth plane: f16(w) | bf16(w - f16(w))
+  if (xm >= 4) {                                                 // fourth plane: f16(w) | bf16(w - f16(w))
     rc = get_map2(&B16f, a.wt + (size_t)3 * a.Cout * K, 2, K, 2 * a.Cout, 1, 1, NT, 1, 1, true);
+    if (rc) return rc;
+  }
+  if (xm == 6) {                                                 // fifth plane: f16(2^11 (w - f16(w))); rides in the fp32 map's slot
+    rc = get_map2(&Bm, a.wt + (size_t)4 * a.Cout * K, 2, K, 2 * a.Cout, 1, 1, NT, 1, 1, true);
     if (rc) return rc;
   }
   T2Args e;
@@ -711,6 +747,7 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
     return xm ? launch2n<1, 2>(NT, A0, A1, Bm, B16, B16f, e, grid, s) : launch2n<0, 2>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   }
   dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);          // persistent: one CTA per SM
+  if (xm == 6) return launch2n<6, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   if (xm == 5) return launch2n<5, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   if (xm == 4) return launch2n<4, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   if (xm == 3) return launch2n<3, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);

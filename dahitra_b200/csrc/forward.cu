@@ -145,7 +145,7 @@ static int conv_dispatch(const ConvArgs& a, int flags, cudaStream_t s) {
     // per-tap TMA kernel (1xTF32) when DH_FLAG_CONV_TC_V1 asks for it.  Stride-2 convs need DH_FLAG_TC_STRIDE2.
     const bool stride_ok = a.stride == 1 || (flags & DH_FLAG_TC_STRIDE2);
     if (stride_ok && !(flags & DH_FLAG_CONV_TC_V1) && dh_conv_tc2_eligible(a))
-      return dh_launch_conv_tc2(a, (flags & DH_FLAG_TC_BF16) ? 3 : (flags & DH_FLAG_TC_3XTF32) ? ((flags & DH_FLAG_TC_MAIN_F16) ? 4 : (flags & DH_FLAG_TC_X3_BF16) ? 2 : 1)
+      return dh_launch_conv_tc2(a, (flags & DH_FLAG_TC_BF16) ? 3 : (flags & DH_FLAG_TC_3XTF32) ? ((flags & DH_FLAG_TC_MAIN_F16) ? ((flags & DH_FLAG_TC_FOLD) ? 6 : 4) : (flags & DH_FLAG_TC_X3_BF16) ? 2 : 1)
                                                             : ((flags & DH_FLAG_TC_MAIN_F16) ? 5 : 0),
                                 (flags & DH_FLAG_CONV_TC_2CTA) ? 2 : 1, s);
     if (stride_ok && dh_conv_tc_eligible(a)) return dh_launch_conv_tc(a, s);

@@ -24,7 +24,7 @@ LEVELS = ((5, 256, 4, 4), (4, 128, 4, 4), (3, 64, 8, 8))   # (k, trunk channels,
 DH_VARIANT_LEVIR, DH_VARIANT_XBD = 0, 1
 DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC, DH_FLAG_STEM_TC, DH_FLAG_DEC_TC_X3 = 1, 2, 4, 8, 16, 32
 DH_FLAG_CONV_TC_V1, DH_FLAG_CONV_TC_2CTA, DH_FLAG_SERIAL, DH_FLAG_TC_X3_BF16, DH_FLAG_TC_BF16 = 64, 128, 256, 512, 1024
-DH_FLAG_TC_MAIN_F16 = 2048
+DH_FLAG_TC_MAIN_F16, DH_FLAG_TC_FOLD = 2048, 4096
 MODES = {
     "fp32": 0,                                             # every contraction in fp32 FMA (strict)
     "fp32_tcdec": DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,      # strict + the 3xTF32 (fp32-grade) tensor-core decoder
@@ -33,9 +33,14 @@ MODES = {
     # correction products in BF16 (fp32 exponent range) — half the tensor-core cycles of three TF32 products and a
     # slightly smaller error.  Operands beyond the FP16 range (|v| > 65504, or < 1e-7) fall back on the BF16 terms
     # (bf16-grade accuracy for those values only).  7x7 stem and pixel decoder: 3xTF32.
-    "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC
-              | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
-    # the same with the main product in TF32 (no range caveat, ~10 % slower)
+    # The f16(a).r_w correction shares its A operand with the main product, so both come out of ONE N-doubled FP16 MMA
+    # on the filter tile [f16(w) ; f16(2^11 r_w)] and are added in the epilogue (DH_FLAG_TC_FOLD).
+    "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_FOLD | DH_FLAG_TC_STRIDE2
+              | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
+    # ... with three separate products per (tap, chunk) (~7 % slower)
+    "tf32x3_unfolded": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC
+                       | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
+    # the same with the main product in TF32 (no range caveat, ~15 % slower)
     "tf32x3_tf32main": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC
                        | DH_FLAG_DEC_TC_X3,
     "tf32x3_pure": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
@@ -124,7 +129,7 @@ def tf32_split(x):
 
 
 def kmajor_split(wt):
-    """K-major filter [Cout][K] (float64) -> float32 [4][Cout][K]:
+    """K-major filter [Cout][K] (float64) -> float32 [5][Cout][K]:
       plane 0  TF32-rounded values (B_hi; all the 1xTF32 kernels read)
       plane 1  their TF32-rounded remainders (B_lo of the 3xTF32 kernels)
       plane 2  raw bits of a bf16 [2][Cout][K] array: bf16(w) and bf16(w - B_hi), the filter operands of the two
@@ -138,7 +143,12 @@ def kmajor_split(wt):
     r16 = (wt - h16.double()).to(torch.float32).to(torch.bfloat16)
     packed_f = torch.cat([h16.contiguous().view(torch.int16).reshape(-1), r16.contiguous().view(torch.int16).reshape(-1)]) \
         .view(torch.float32).reshape(wt.shape)
-    return torch.cat([torch.stack([hi, lo]).to(torch.float32), packed[None], packed_f[None]])
+    # plane 4: f16(2^11 (w - f16(w))) (the remainder scaled into the normal f16 range; second half unused) for the
+    # folded-correction mode
+    s16 = ((wt - h16.double()) * 2048.0).clamp(-65504.0, 65504.0).to(torch.float32).to(torch.float16)
+    packed_s = torch.cat([s16.contiguous().view(torch.int16).reshape(-1), torch.zeros(s16.numel(), dtype=torch.int16)]) \
+        .view(torch.float32).reshape(wt.shape)
+    return torch.cat([torch.stack([hi, lo]).to(torch.float32), packed[None], packed_f[None], packed_s[None]])
 
 
 def stem_tc_image(w147):

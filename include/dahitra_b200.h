@@ -58,8 +58,9 @@ extern "C" {
 #define DH_FLAG_TC_X3_BF16  512 /* with TC_3XTF32: the two correction products of every conv as BF16 MMAs (half their cost) */
 #define DH_FLAG_TC_BF16     1024 /* with CONV_TC: single-pass BF16 operands in the convolutions (fp32 storage and accumulation); overrides TC_3XTF32 */
 #define DH_FLAG_TC_MAIN_F16 2048 /* with TC_3XTF32: main product of every conv in FP16 (K = 16 MMAs), both corrections in BF16; without it: single-pass FP16 operands */
+#define DH_FLAG_TC_FOLD     4096 /* with TC_3XTF32 | TC_MAIN_F16: fold the f16(a).r_w correction into the main MMA (2N-wide filter tile) */
 /* the modes dahitra_b200.engine.MODES names (DESIGN.md "Precision modes") */
-#define DH_FLAGS_TF32X3     (DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_STRIDE2 | \
+#define DH_FLAGS_TF32X3     (DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_FOLD | DH_FLAG_TC_STRIDE2 | \
                              DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3)   /* default: every product error-compensated, fp32-grade */
 #define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3)   /* single-pass TF32 convs */
 #define DH_FLAGS_F16        (DH_FLAGS_TF32 | DH_FLAG_TC_MAIN_F16)                    /* single-pass FP16 conv operands */
@@ -90,9 +91,10 @@ enum dh_weight_slot {
   DH_W_CL20B_W, DH_W_CL20B_B,                      /* conv_layer2_0.3: [9*128][32],[32] */
   DH_W_CLS_W, DH_W_CLS_B,                          /* classifier: [9][output_nc][32], [output_nc] */
   /* K-major copies of the filters the tcgen05 kernels take as their B operand (Cin a multiple of 32); same values
-   * as the matching _W / _DECODE slot.  Layout: float [4][Cout][KH*KW*Cin] = TF32-rounded w | TF32-rounded remainder |
+   * as the matching _W / _DECODE slot.  Layout: float [5][Cout][KH*KW*Cin] = TF32-rounded w | TF32-rounded remainder |
    * raw bits of a bf16 [2][Cout][K] array {bf16(w), bf16(w - plane 0)} (DH_FLAG_TC_X3_BF16) | raw bits of
-   * {f16(w) saturated, bf16(w - f16(w))} (DH_FLAG_TC_MAIN_F16): float [4][Cout][K] in total */
+   * {f16(w) saturated, bf16(w - f16(w))} (DH_FLAG_TC_MAIN_F16) | raw bits of {f16(2^11 (w - f16(w))), zeros}
+   * (DH_FLAG_TC_FOLD): float [5][Cout][K] in total */
   DH_W_L1_0_C1_WT, DH_W_L1_0_C2_WT, DH_W_L1_1_C1_WT, DH_W_L1_1_C2_WT,
   DH_W_L2_0_C2_WT, DH_W_L2_1_C1_WT, DH_W_L2_1_C2_WT,
   DH_W_L3_0_C1_WT, DH_W_L3_0_C2_WT, DH_W_L3_0_DS_WT, DH_W_L3_1_C1_WT, DH_W_L3_1_C2_WT,

@@ -59,5 +59,5 @@ def test_export_prepared(tmp_path):
     names = slot_names()
     assert set(z.files) <= set(names) and "DH_W_STEM_W" in z.files and "DH_W_CL20A_WT" in z.files
     assert z["DH_W_STEM_W"].shape == (147, 64) and z["DH_W_STEM_W"].dtype == np.float32
-    assert z["DH_W_CL20A_WT"].shape == (4, 128, 1152)    # TF32 hi | TF32 lo | bf16 pair bits | f16 / bf16 pair bits
+    assert z["DH_W_CL20A_WT"].shape == (5, 128, 1152)    # TF32 hi | TF32 lo | bf16 pair | f16 / bf16 pair | scaled f16 remainder
     assert shapes["DH_W_CLS_W"] == tuple(z["DH_W_CLS_W"].shape)

@@ -84,7 +84,7 @@ def test_conv2d_up2_tcgen05(shape):
     wt, pb = upsample_phase_filter(w, b)
     wt = kmajor_split(wt).float().contiguous().to(DEV)
     ref = F.relu(F.conv2d(x.double().cpu().permute(0, 3, 1, 2).repeat_interleave(2, 2).repeat_interleave(2, 3), w, b, 1, 1))
-    for flags, tol in ((0, 4e-3), (64, 4e-3), (2, 2e-5), (128, 4e-3), (130, 2e-5), (514, 6e-5), (642, 6e-5), (1024, 4e-2), (2562, 6e-5)):   # halo-reuse 1xTF32, per-tap kernel, 3xTF32, CTA pairs, bf16 corrections, bf16 operands, f16 main
+    for flags, tol in ((0, 4e-3), (64, 4e-3), (2, 2e-5), (128, 4e-3), (130, 2e-5), (514, 6e-5), (642, 6e-5), (1024, 4e-2), (2562, 6e-5), (6658, 6e-5)):   # halo-reuse 1xTF32, per-tap kernel, 3xTF32, CTA pairs, bf16 corrections, bf16 operands, f16 main
         y = abi.conv2d_up2_tc(x, wt, pb.float().to(DEV), True, flags)
         torch.cuda.synchronize()
         close(y, ref.permute(0, 2, 3, 1), rtol=tol / 2, atol=tol)
@@ -100,7 +100,7 @@ def test_conv2d_stride2_tcgen05(cfg):
     b = rnd(Cout, seed=4)
     ref = E.conv_nhwc(x.double(), w.double(), b.double(), K, 2, K // 2, None, True, 1)
     # flags: 1|4 = halo-reuse kernel on the four phase images (1xTF32), 1|4|2 = same with 3xTF32, 1|4|64 = per-tap kernel
-    for flags, tol in ((5, 4e-3), (7, 2e-5), (69, 4e-3), (133, 4e-3), (135, 2e-5), (519, 6e-5), (647, 6e-5), (1029, 4e-2), (2567, 6e-5)):   # + 128: CTA pairs; + 512: bf16 corrections; 1024: bf16 operands; 2048: f16 main product
+    for flags, tol in ((5, 4e-3), (7, 2e-5), (69, 4e-3), (133, 4e-3), (135, 2e-5), (519, 6e-5), (647, 6e-5), (1029, 4e-2), (2567, 6e-5), (6663, 6e-5)):   # + 128: CTA pairs; + 512: bf16 corrections; 1024: bf16 operands; 2048: f16 main product
         y = abi.conv2d(x, None, w, b, None, True, K, 2, K // 2, 1, flags=flags)
         torch.cuda.synchronize()
         assert y.shape == ref.shape
@@ -117,7 +117,7 @@ def test_conv2d_f16_main_operand_range(scale, tol):
     x = rnd(N, H, W, C, seed=1) * scale
     w = rnd(K * K * C, Cout, seed=3, scale=(K * K * C) ** -0.5)
     ref = E.conv_nhwc(x.double(), w.double(), None, K, 1, 1, None, False, 1)
-    y = abi.conv2d(x, None, w, None, None, False, K, 1, 1, 1, flags=2563)
+    y = abi.conv2d(x, None, w, None, None, False, K, 1, 1, 1, flags=2563 | 4096)
     torch.cuda.synchronize()
     assert torch.isfinite(y).all()
     err = float((y.double().cpu() - ref.cpu()).abs().max()) / float(ref.abs().max())
@@ -144,7 +144,8 @@ def test_conv2d_tcgen05(cfg):
     for flags, name, tol in ((1, "halo 1xTF32", 4e-3), (65, "per-tap 1xTF32", 4e-3), (3, "halo 3xTF32", 2e-5),
                              (129, "pair 1xTF32", 4e-3), (131, "pair 3xTF32", 2e-5), (515, "3xTF32 bf16-corr", 6e-5),
                              (643, "pair 3xTF32 bf16-corr", 6e-5), (1025, "bf16 operands", 4e-2),
-                             (2563, "f16 main + bf16 corr", 6e-5), (2049, "f16 operands", 4e-3)):
+                             (2563, "f16 main + bf16 corr", 6e-5), (2049, "f16 operands", 4e-3),
+                             (6659, "f16 main, folded corr", 6e-5)):
         y = abi.conv2d(x0, x1, w, b, r, relu, K, 1, K // 2, 1, flags=flags)
         torch.cuda.synchronize()
         d = (y.double().cpu() - ref.cpu()).abs()
