@@ -52,6 +52,9 @@ struct ConvArgs {
   // a nearest-x2-upsampled 3x3 conv (see engine.py: upsample_phase_filter); block j of 32 channels goes to
   // output pixel (2*oy + j/2, 2*ox + j%2) of a [N][2*inH][2*inW][32] tensor.
   int ps = 0;
+  // tcgen05 kernel only: one tile per CTA instead of a persistent grid, so that the hardware scheduler can interleave
+  // this launch with others (used for the head convolution that runs under the transformer levels on a side stream)
+  int flat = 0;
 };
 int dh_launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
 bool dh_conv_tc_eligible(const ConvArgs& a);

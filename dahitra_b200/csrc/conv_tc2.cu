@@ -746,7 +746,7 @@ int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s) {
     if (xm == 2) return launch2n<2, 2>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
     return xm ? launch2n<1, 2>(NT, A0, A1, Bm, B16, B16f, e, grid, s) : launch2n<0, 2>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   }
-  dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);          // persistent: one CTA per SM
+  dim3 grid((unsigned)((e.ntiles < sms || a.flat) ? e.ntiles : sms), 1, 1);   // persistent: one CTA per SM (flat: one per tile)
   if (xm == 6) return launch2n<6, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   if (xm == 5) return launch2n<5, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);
   if (xm == 4) return launch2n<4, 1>(NT, A0, A1, Bm, B16, B16f, e, grid, s);

@@ -241,8 +241,8 @@ inline void prof_mark(cudaStream_t s, const char* name, double flops, double byt
 namespace {
 struct AuxStreams {
   bool ok = false;
-  cudaStream_t st[2];
-  cudaEvent_t fork, join[2];
+  cudaStream_t st[2], low;                 // low: lowest priority, for the head convolution that fills idle SMs
+  cudaEvent_t fork, join[2], fork_low, join_low;
 };
 AuxStreams* aux_streams() {
   thread_local AuxStreams per_dev[16];
@@ -254,6 +254,13 @@ AuxStreams* aux_streams() {
     for (int i = 0; i < 2 && good; ++i)
       good = cudaStreamCreateWithFlags(&a.st[i], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (good) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);                 // lo = numerically largest = least priority
+      good = cudaStreamCreateWithPriority(&a.low, cudaStreamNonBlocking, lo) == cudaSuccess &&
+             cudaEventCreateWithFlags(&a.fork_low, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&a.join_low, cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!good) { cudaGetLastError(); return nullptr; }
     a.ok = true;
   }
@@ -294,6 +301,7 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
   const int N2 = 2 * B;
   const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8, h16 = H / 16, w16 = W / 16;
 
+  int conv_flat = 0;                            // ConvArgs::flat of the next conv() calls
   // conv launch + its algorithmic cost (2*MACs as written; one read of the stored inputs/weights, one write)
   auto conv = [&](const char* name, const float* in0, const float* in1, int C0, int C1, int N, int inH, int inW, int up,
                   int K, int stride, int Cout, int wslot, int bslot, const float* res, int relu, float* out) -> int {
@@ -302,6 +310,7 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
                bslot >= 0 ? Wt(bslot) : nullptr, res, relu, out};
     const int psw = (wslot == DH_W_CL4_W) ? DH_W_CL4_PSWT : (wslot == DH_W_CL3_W) ? DH_W_CL3_PSWT
                   : (wslot == DH_W_CL2_W) ? DH_W_CL2_PSWT : -1;
+    a.flat = conv_flat;
     if (up == 2 && psw >= 0 && (flags & DH_FLAG_CONV_TC)) {
       // nearest-x2 upsample + 3x3 conv == 3x3 conv 32 -> 4x32 on the low-res map + pixel-shuffle store
       a.up = 1; a.Cout = 128; a.w = nullptr; a.wt = Wt(psw); a.bias = Wt(psw + 1); a.ps = 1;
@@ -330,6 +339,23 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
   };
   DH_STEP("stem_pre", stem_fl, stem_by, stem(x1, F2));
   DH_STEP("stem_post", stem_fl, stem_by, stem(x2, F2 + (size_t)B * h2 * w2 * 64));
+  // conv_layer2_0.0 (the largest launch of the head) needs nothing but the two stem outputs: with DH_FLAG_EARLY_HEAD it is
+  // issued now on a lowest-priority side stream, one tile per CTA, so that the hardware scheduler drops its CTAs onto
+  // SMs the small token / level-5 / level-4 kernels leave idle; it is joined before conv_layer2_0.3.
+  AuxStreams* aux_head = (!g_prof.on && !(flags & DH_FLAG_SERIAL) && (flags & DH_FLAG_EARLY_HEAD) && (flags & DH_FLAG_CONV_TC))
+                             ? aux_streams() : nullptr;
+  float* Y20 = ws + p.y20;
+  if (aux_head) {
+    if (cudaEventRecord(aux_head->fork_low, s_main) != cudaSuccess ||
+        cudaStreamWaitEvent(aux_head->low, aux_head->fork_low, 0) != cudaSuccess) return (int)cudaGetLastError();
+    s = aux_head->low; conv_flat = 1;
+    const int rc = conv("conv_layer2_0.0", F2, F2 + (size_t)B * h2 * w2 * 64, 64, 64, B, h2, w2, 1, 3, 1, 128, DH_W_CL20A_W, DH_W_CL20A_B,
+                        nullptr, 1, Y20);
+    conv_flat = 0;
+    const bool ok = rc == 0 && cudaEventRecord(aux_head->join_low, s) == cudaSuccess;
+    s = s_main;
+    if (!ok) return rc != 0 ? rc : (int)cudaGetLastError();
+  }
   float* P2 = ws + p.p2;
   DH_STEP("maxpool_2", 0.0, 4.0 * N2 * 64 * ((double)h2 * w2 + (double)h4 * w4), dh_launch_maxpool(F2, N2, h2, w2, 64, P2, s));
   float *T4a = ws + p.t4a, *T4b = ws + p.t4b, *F4 = ws + p.f4;
@@ -442,12 +468,16 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
     if (rc != 0) return rc;
   }
   // ---- UNet head (reference networks.py:1341-1357)
-  float *C3 = ws + p.c3, *Y20 = ws + p.y20, *O2 = ws + p.o2, *C2 = ws + p.c2;
+  float *C3 = ws + p.c3, *O2 = ws + p.o2, *C2 = ws + p.c2;
   const float* OUT3 = ws + p.lv[2].out;                                   // out_3 = level3 + C4
   DH_CONV("conv_layer3", OUT3, nullptr, 32, 0, B, h4, w4, 2, 3, 1, 32, DH_W_CL3_W, DH_W_CL3_B, nullptr, 1, C3);   // on up2(out_3)
   const float* A128 = F2;
   const float* B128 = F2 + (size_t)B * h2 * w2 * 64;
-  DH_CONV("conv_layer2_0.0", A128, B128, 64, 64, B, h2, w2, 1, 3, 1, 128, DH_W_CL20A_W, DH_W_CL20A_B, nullptr, 1, Y20);  // conv+BN+ReLU
+  if (aux_head) {
+    if (cudaStreamWaitEvent(s_main, aux_head->join_low, 0) != cudaSuccess) return (int)cudaGetLastError();
+  } else {
+    DH_CONV("conv_layer2_0.0", A128, B128, 64, 64, B, h2, w2, 1, 3, 1, 128, DH_W_CL20A_W, DH_W_CL20A_B, nullptr, 1, Y20);  // conv+BN+ReLU
+  }
   DH_CONV("conv_layer2_0.3", Y20, nullptr, 128, 0, B, h2, w2, 1, 3, 1, 32, DH_W_CL20B_W, DH_W_CL20B_B, C3, 0, O2);       // + out_3
   DH_CONV("conv_layer2", O2, nullptr, 32, 0, B, h2, w2, 2, 3, 1, 32, DH_W_CL2_W, DH_W_CL2_B, nullptr, 1, C2);            // on up2(out_2)
   DH_STEP("classifier", 2.0 * B * H * W * 9 * 32 * output_nc, 4.0 * B * H * W * (32.0 + output_nc) + (argmax_u8 ? (double)B * H * W : 0.0),
