@@ -359,3 +359,19 @@ def test_training_step_then_native_inference():
         yn = net(x1, x2)
     ya = net._forward_autograd(x1, x2).detach()
     check_logits(yn, ya, "native vs autograd route after 6 SGD steps", defineG=True)
+
+
+def test_scheduling_flags_do_not_change_results(levir_template):
+    """DH_FLAG_SERIAL (no side streams) and DH_FLAG_EARLY_HEAD (head conv issued early on a low-priority stream, one tile
+    per CTA) only change WHEN kernels run: logits must be bit-identical to the default schedule."""
+    from dahitra_b200.engine import MODES
+    sd = synth.synth_state_dict(levir_template, seed=3, style="default")
+    net = make_net(sd)
+    x1, x2 = (t.to(DEV) for t in synth.synth_pair(5, 256, 256, seed=61, kind="uniform"))
+    base = MODES[_MODE]
+    with torch.no_grad():
+        y0 = net(x1, x2).clone()
+        for extra in (256, 8192):
+            net.set_mode(base | extra)
+            assert torch.equal(net(x1, x2), y0), extra
+    net.set_mode(_MODE)
