@@ -37,16 +37,32 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared object for sm_100a (cross-compiles without a GPU)."""
+    """Compile every .cu under csrc/ for sm_100a (objects in parallel, then one link) into the in-tree shared object;
+    cross-compiles without a GPU."""
     if not force and not needs_build():
         return LIB_PATH
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + _sources() + ["-o", LIB_PATH + ".tmp"]
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    with tempfile.TemporaryDirectory(prefix="_build_", dir=_HERE) as tmp:            # in-tree scratch (objects are git-ignored)
+        def compile_one(src):
+            obj = os.path.join(tmp, os.path.basename(src) + ".o")
+            cmd = [nvcc] + cflags + ["-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, r.stdout, r.stderr))
+            return obj
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            objs = list(ex.map(compile_one, _sources()))
+        cmd = [nvcc] + NVCC_FLAGS + objs + ["-o", LIB_PATH + ".tmp"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
     return LIB_PATH
 
