@@ -77,18 +77,28 @@ __global__ void __launch_bounds__(128)
 decoder_tables_tc_kernel(const float* __restrict__ mem, int B, int first_call, const float* __restrict__ dec, int heads,
                          float* __restrict__ tables, int depth) {
   __shared__ float MN[4][32];
+  extern __shared__ __align__(16) float dt_w[];               // Mqk | Mov of this layer: 2 * heads * 1024 floats
   const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
   const int layer = blockIdx.x;
   const int ci = blockIdx.y / B, pair = blockIdx.y % B;
   const int call = first_call + ci;
   const float* L = dec + (size_t)layer * DH_DEC_LAYER_FLOATS(heads);
-  const float* MqkT = L + 64;
+  // the layer's matrices are cold in L2 (see token_encoder_kernel): one asynchronous fetch instead of 4 * heads
+  // dependent batches of loads
+  {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dt_w);
+    for (int i = threadIdx.x; i < heads * 512; i += 128)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(L + 64 + (size_t)i * 4) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const float* MqkT = dt_w;
   const float* MovT = MqkT + (size_t)heads * 1024;
   float* T = tables + ((size_t)blockIdx.y * depth + layer) * DH_TABTC_FLOATS;
   float* TA = T; float* TB = T + 1024; float* cA = T + 2048; float* TAl = T + 2080; float* TBl = T + 2080 + 1024;
   const float g = __ldg(L + lane), b = __ldg(L + 32 + lane);
   MN[j][lane] = ln_lane32(__ldg(mem + ((size_t)pair * 3 + call) * 128 + j * 32 + lane), g, b);
-  __syncwarp();
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   for (int h = 0; h < heads; ++h) {
     const float* mq = MqkT + (size_t)h * 1024;
     const float* mv = MovT + (size_t)h * 1024;
@@ -96,8 +106,8 @@ decoder_tables_tc_kernel(const float* __restrict__ mem, int B, int first_call, c
 #pragma unroll 8
     for (int c2 = 0; c2 < 32; ++c2) {
       const float mn = MN[j][c2];
-      a = fmaf(__ldg(mq + c2 * 32 + lane), mn, a);
-      v = fmaf(__ldg(mv + c2 * 32 + lane), mn, v);
+      a = fmaf(mq[c2 * 32 + lane], mn, a);
+      v = fmaf(mv[c2 * 32 + lane], mn, v);
     }
     const int hj = h * 4 + j;
     a *= 1.4426950408889634f;                               // log2(e)
@@ -426,7 +436,10 @@ int dh_launch_decoder_tables_tc(const float* mem, int B, int first_call, int nca
   DH_REQUIRE(B > 0 && first_call >= 0 && ncalls >= 1 && first_call + ncalls <= 3 && (heads == 4 || heads == 8) && depth >= 1,
              DH_E_SHAPE);
   dim3 grid(depth, ncalls * B);
-  decoder_tables_tc_kernel<<<grid, 128, 0, s>>>(mem, B, first_call, dec, heads, tables, depth);
+  const int smem = heads * 2048 * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(decoder_tables_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  decoder_tables_tc_kernel<<<grid, 128, smem, s>>>(mem, B, first_call, dec, heads, tables, depth);
   DH_CHECK_LAUNCH();
   return 0;
 }

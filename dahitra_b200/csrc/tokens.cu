@@ -151,10 +151,21 @@ __global__ void __launch_bounds__(256)
 token_encoder_kernel(const float* __restrict__ partials, int B, int nchunk, const float* __restrict__ enc, int heads,
                      int add_pos, float* __restrict__ mem) {
   __shared__ float X[8][32], XN[8][32], Y[8][32], Hh[8][32];
+  extern __shared__ __align__(16) float te_w[];                 // the whole encoder pack (DH_ENC_FLOATS(heads) floats)
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;   // warp w <-> token w; lane <-> channel
   const int pair = blockIdx.x;
-  const float* pos = enc;
-  const float* ln1g = enc + 256; const float* ln1b = ln1g + 32;
+  // The pack is cold in L2 by the time this kernel runs (GBs of activations have streamed through since the last
+  // forward), and the attention loop below would otherwise walk it in 32 dependent batches of loads — 60 of the 70 us
+  // this kernel took.  Fetch it once, asynchronously, while the partial softmax sums are merged.
+  {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(te_w);
+    const int nvec = DH_ENC_FLOATS(heads) / 4;
+    for (int i = tid; i < nvec; i += 256)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(enc + (size_t)i * 4) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const float* pos = te_w;
+  const float* ln1g = te_w + 256; const float* ln1b = ln1g + 32;
   const float* Mqk = ln1b + 32;
   const float* MvoT = Mqk + (size_t)heads * 1024;
   const float* bo = MvoT + (size_t)heads * 1024;
@@ -176,10 +187,12 @@ token_encoder_kernel(const float* __restrict__ partials, int B, int nchunk, cons
       S = fmaf(__ldg(q + 1), sc, S);
       T = fmaf(__ldg(q + 2 + lane), sc, T);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                            // the encoder pack is in shared memory
     float v = T / S;
-    if (add_pos) v += __ldg(pos + w * 32 + lane);
+    if (add_pos) v += pos[w * 32 + lane];
     X[w][lane] = v;
-    XN[w][lane] = ln_lane(v, __ldg(ln1g + lane), __ldg(ln1b + lane));
+    XN[w][lane] = ln_lane(v, ln1g[lane], ln1b[lane]);
   }
   __syncthreads();
   // 2. attention, head by head
@@ -191,8 +204,8 @@ token_encoder_kernel(const float* __restrict__ partials, int B, int nchunk, cons
 #pragma unroll 8
     for (int c = 0; c < 32; ++c) {
       const float xv = XN[w][c];
-      u = fmaf(xv, __ldg(mq + c * 32 + lane), u);
-      y = fmaf(xv, __ldg(mv + c * 32 + lane), y);
+      u = fmaf(xv, mq[c * 32 + lane], u);
+      y = fmaf(xv, mv[c * 32 + lane], y);
     }
     __syncthreads();            // previous head's readers of Y are done
     Y[w][lane] = y;
@@ -210,20 +223,20 @@ token_encoder_kernel(const float* __restrict__ partials, int B, int nchunk, cons
 #pragma unroll
     for (int j = 0; j < 8; ++j) att_out = fmaf(d[j] * inv, Y[j][lane], att_out);
   }
-  float x = X[w][lane] + att_out + __ldg(bo + lane);
+  float x = X[w][lane] + att_out + bo[lane];
   // 3. MLP
-  const float xn2 = ln_lane(x, __ldg(ln2g + lane), __ldg(ln2b + lane));
+  const float xn2 = ln_lane(x, ln2g[lane], ln2b[lane]);
   __syncthreads();
   XN[w][lane] = xn2;
   __syncwarp();
-  float hsum = __ldg(b1 + lane);
+  float hsum = b1[lane];
 #pragma unroll 8
-  for (int c = 0; c < 32; ++c) hsum = fmaf(XN[w][c], __ldg(W1t + c * 32 + lane), hsum);
+  for (int c = 0; c < 32; ++c) hsum = fmaf(XN[w][c], W1t[c * 32 + lane], hsum);
   Hh[w][lane] = gelu_erf(hsum);
   __syncwarp();
-  float o = __ldg(b2 + lane);
+  float o = b2[lane];
 #pragma unroll 8
-  for (int k = 0; k < 32; ++k) o = fmaf(Hh[w][k], __ldg(W2t + k * 32 + lane), o);
+  for (int k = 0; k < 32; ++k) o = fmaf(Hh[w][k], W2t[k * 32 + lane], o);
   x += o;
   __syncthreads();
   X[w][lane] = x;
@@ -238,7 +251,10 @@ int dh_launch_token_encoder(const float* partials, int B, int nchunk, const floa
                             float* mem, cudaStream_t s) {
   DH_REQUIRE(partials && enc && mem, DH_E_NULL);
   DH_REQUIRE(B > 0 && nchunk > 0 && heads >= 1 && heads <= 16, DH_E_SHAPE);
-  token_encoder_kernel<<<B, 256, 0, s>>>(partials, B, nchunk, enc, heads, add_pos, mem);
+  const int smem = DH_ENC_FLOATS(heads) * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(token_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  token_encoder_kernel<<<B, 256, smem, s>>>(partials, B, nchunk, enc, heads, add_pos, mem);
   DH_CHECK_LAUNCH();
   return 0;
 }
