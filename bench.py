@@ -350,7 +350,7 @@ def run_native(a, wl):
                    sample=f"oracle port (torch CPU fp32), {cp} pairs per call, mean of 3 calls after 1 warm-up ({sec:.2f} s/call)")
     line = dict(metric="image-pairs/sec", value=value, unit="pairs/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype={"fp32": "f32", "tf32": "tf32", "tf32_fast": "tf32", "tf32x3": "x3 error-compensated (convs: f16 main + bf16 corrections; stem/decoder: 3xTF32), fp32 accumulate and storage",
+                dtype={"fp32": "f32", "tf32": "tf32", "tf32_fast": "tf32", "tf32x3": "x3 error-compensated (convs and stem: f16 main + bf16 corrections; decoder: 3xTF32), fp32 accumulate and storage",
                        "tf32x3_unfolded": "x3 error-compensated (convs: f16 main + bf16 corrections; stem/decoder: 3xTF32), fp32 accumulate and storage",
                        "tf32x3_tf32main": "x3 error-compensated (tf32 main + bf16 corrections), fp32 accumulate and storage",
                        "tf32x3_pure": "3xTF32 (error-compensated), fp32 accumulate and storage", "bf16": "bf16 operands, fp32 accumulate and storage"}.get(mode_name, "f32/tf32"),

@@ -18,6 +18,7 @@
 //                    the conv padding; the only HBM read), double-buffered through halo_full / halo_free.
 // The filter image (pre-swizzled, 6 K-step tiles of 64x32; hi [+ lo]) is loaded once per CTA by one bulk copy.
 // X3: error-compensated 3xTF32 — A rows are written as TF32 hi + lo tiles, the filter comes pre-split.
+// The default fp32-grade mode runs stem_f16_kernel below (folded FP16 operands) instead.
 #include "tc_common.cuh"
 
 using namespace dhtc;
@@ -224,6 +225,199 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tile
     tmem_dealloc(tmem_base, 128);
   }
 }
+// ------------------------------------------------------------------------------------------------------------------
+// Folded FP16 stem (mode 2; the default fp32-grade mode): the same on-chip im2col, 16-bit operands.
+//   a.w ~= f16(a).f16(w) + f16(a).r_w + r_a.bf16(w),   r_w = w - f16(w),  r_a = a - f16(a)
+// as in conv_tc2.cu's folded mode: ONE N = 128 FP16 MMA on the filter image [f16(w) ; f16(2^11 r_w)] gives the main
+// product (accumulator columns 0..63) and the scaled filter-remainder product (columns 64..127); a N = 64 BF16 MMA adds
+// bf16(r_a).bf16(w) onto columns 0..63; the epilogue returns col[c] + 2^-11 col[64 + c].  A K step is one 128-byte
+// row of 16-bit values = 64 K elements = 8 (ci, r) groups: 3 K steps per tile (21 groups + 3 pad groups; the last
+// step issues 3 of its 4 K = 16 MMAs).  Against the 3xTF32 form this halves the bytes the builders write and cuts the
+// operand bytes the MMAs read from shared memory by 2.5x — the shared-memory port is what bounds this kernel.
+// Three A buffers [f16 hi | bf16 lo] form a ring over the global K-step sequence; the two builder warpgroups take
+// alternate steps.
+constexpr int SF_KSTEPS = 3;
+constexpr int SF_NBUF = 3;
+constexpr uint32_t SF_A_BUF = 2 * SK_A_BYTES;                        // hi + lo tiles of one step
+constexpr uint32_t SF_BM_STEP = 128 * 128;                           // main filter tile of one step: 128 rows x 128 B
+constexpr uint32_t SF_BC_STEP = 64 * 128;                            // correction filter tile (bf16 w)
+constexpr uint32_t SF_BM_BYTES = SF_KSTEPS * SF_BM_STEP, SF_BC_BYTES = SF_KSTEPS * SF_BC_STEP;
+constexpr uint32_t SF_OFF_B = SF_NBUF * SF_A_BUF;
+constexpr uint32_t SF_OFF_H = SF_OFF_B + SF_BM_BYTES + SF_BC_BYTES;
+constexpr uint32_t SF_OFF_E = SF_OFF_H + 2 * SK_HALO_STRIDE;
+constexpr uint32_t SF_SMEM = SF_OFF_E + 4 * 4096 + 1024;
+constexpr uint32_t SF_IDESC_MAIN = umma_idesc_f16(128, 128), SF_IDESC_CORR = umma_idesc_bf16(128, 64);
+constexpr size_t SF_IMAGE_OFFSET_FLOATS = 2 * (SK_B_BYTES / 4);      // the 16-bit images follow the TF32 [hi | lo] images in DH_W_STEM_WTC
+
+__global__ void __launch_bounds__(SK_THREADS, 1)
+stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tilesX, int tilesY, int ntiles,
+                const float* __restrict__ wtc, const float* __restrict__ bias, float* __restrict__ out) {
+  extern __shared__ uint8_t sk_raw[];
+  __shared__ __align__(8) uint64_t w_bar, a_full[SF_NBUF], a_free[SF_NBUF], acc_full[2], acc_empty[2], halo_full[2], halo_free[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t base = (smem_u32(sk_raw) + 1023u) & ~1023u;
+  uint8_t* bp = sk_raw + (base - smem_u32(sk_raw));
+  const uint32_t b_addr = base + SF_OFF_B;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&w_bar), 1);
+    for (int i = 0; i < SF_NBUF; ++i) {
+      mbar_init(smem_u32(&a_full[i]), 128);
+      mbar_init(smem_u32(&a_free[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&acc_full[i]), 1);
+      mbar_init(smem_u32(&acc_empty[i]), 128);
+      mbar_init(smem_u32(&halo_full[i]), 1);
+      mbar_init(smem_u32(&halo_free[i]), 256);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 256);               // two 128-column accumulators [main | scaled remainder]
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ builders: two warpgroups, alternate global K steps
+    const int wg = warp >> 2, t = tid & 127;
+    const int py = t / SK_TW, px = t % SK_TW;
+    const int pbase = (2 * py) * SK_HCP + 2 * px;
+    const int swz = t & 7;
+    int it = 0, c = wg, buf = wg, use = 0;                             // c = global step (3 per tile); buf = c % 3; use = c / 3
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int hb = it & 1;
+      mbar_wait(smem_u32(&halo_full[hb]), (uint32_t)((it >> 1) & 1));
+      const float* halo = reinterpret_cast<const float*>(bp + SF_OFF_H + (size_t)hb * SK_HALO_STRIDE) + pbase;
+#pragma unroll 1
+      for (; c < SF_KSTEPS * (it + 1); c += 2) {
+        const int kt = c - SF_KSTEPS * it;
+        if (use >= 1) mbar_wait(smem_u32(&a_free[buf]), (uint32_t)((use - 1) & 1));   // the MMAs that read this buffer are done
+        uint8_t* row = bp + (size_t)buf * SF_A_BUF + t * 128;
+        const int ng = kt == 2 ? 6 : 8;                                // last step: groups 16..20 + one zero group (chunks 6, 7 are never read)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < ng) {
+            const int g = kt * 8 + j;
+            uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+            if (g < SK_GROUPS) {
+              const float2* src = reinterpret_cast<const float2*>(halo + (g / 7) * SK_PLANE + (g % 7) * SK_HCP);
+              const float2 f0 = src[0], f1 = src[1], f2 = src[2], f3 = src[3];
+              hi.x = pack_f16x2_sat(f0.x, f0.y); hi.y = pack_f16x2_sat(f1.x, f1.y);
+              hi.z = pack_f16x2_sat(f2.x, f2.y); hi.w = pack_f16x2_sat(f3.x, f3.y);
+              lo.x = pack_bf16x2(f0.x - f16_lo(hi.x), f0.y - f16_hi(hi.x)); lo.y = pack_bf16x2(f1.x - f16_lo(hi.y), f1.y - f16_hi(hi.y));
+              lo.z = pack_bf16x2(f2.x - f16_lo(hi.z), f2.y - f16_hi(hi.z)); lo.w = pack_bf16x2(f3.x - f16_lo(hi.w), f3.y - f16_hi(hi.w));
+            }
+            const int o = (j ^ swz) << 4;
+            *reinterpret_cast<uint4*>(row + o) = hi;
+            *reinterpret_cast<uint4*>(row + SK_A_BYTES + o) = lo;
+          }
+        }
+        fence_async_smem();
+        mbar_arrive_local(smem_u32(&a_full[buf]));
+        buf += 2;
+        if (buf >= SF_NBUF) { buf -= SF_NBUF; ++use; }
+      }
+      mbar_arrive_local(smem_u32(&halo_free[hb]));
+    }
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ epilogue warps 8..11 (coalesced through a per-warp transpose)
+    const int q = warp & 3, lane = tid & 31;
+    float* stage = reinterpret_cast<float*>(bp + SF_OFF_E + (size_t)q * 4096);
+    const int c8 = lane & 7, r8 = lane >> 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const SkTile t = sk_tile(tile, tilesX, tilesY);
+      const int ab = it & 1;
+      mbar_wait(smem_u32(&acc_full[ab]), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * 128;
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        uint32_t u[32], r[32];
+        tmem_ld32(tm + (uint32_t)(j * 32), u);
+        tmem_ld32(tm + (uint32_t)(64 + j * 32), r);
+        if (j == 1) {
+          tc_fence_before();
+          mbar_arrive_local(smem_u32(&acc_empty[ab]));
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+              make_float4(fmaf(__uint_as_float(r[c4 * 4]), 0x1p-11f, __uint_as_float(u[c4 * 4])),
+                          fmaf(__uint_as_float(r[c4 * 4 + 1]), 0x1p-11f, __uint_as_float(u[c4 * 4 + 1])),
+                          fmaf(__uint_as_float(r[c4 * 4 + 2]), 0x1p-11f, __uint_as_float(u[c4 * 4 + 2])),
+                          fmaf(__uint_as_float(r[c4 * 4 + 3]), 0x1p-11f, __uint_as_float(u[c4 * 4 + 3])));
+        __syncwarp();
+        const float4 b = ldg4(bias + j * 32 + c8 * 4);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int rr = g * 4 + r8, mm = q * 32 + rr;
+          const int oy = t.oy0 + mm / SK_TW, ox = t.ox0 + mm % SK_TW;
+          const float4 o = *reinterpret_cast<const float4*>(stage + rr * 32 + ((c8 ^ (rr & 7)) << 2));
+          if (oy < OH && ox < OW)
+            st4(out + ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32 + c8 * 4,
+                make_float4(fmaxf(o.x + b.x, 0.f), fmaxf(o.y + b.y, 0.f), fmaxf(o.z + b.z, 0.f), fmaxf(o.w + b.w, 0.f)));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ halo producer
+    if ((tid & 31) == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int hb = it & 1;
+        if (it >= 2) mbar_wait(smem_u32(&halo_free[hb]), (uint32_t)(((it >> 1) - 1) & 1));
+        const SkTile tl = sk_tile(tile, tilesX, tilesY);
+        const uint32_t bar = smem_u32(&halo_full[hb]);
+        mbar_expect_tx(bar, SK_HALO_BYTES);
+        tma_load_4d(base + SF_OFF_H + (uint32_t)hb * SK_HALO_STRIDE, &tmX, bar, 2 * tl.ox0 - 4, 2 * tl.oy0 - 3, 0, tl.n);
+      }
+    }
+  } else if ((tid & 31) == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp 12, one lane)
+    mbar_expect_tx(smem_u32(&w_bar), SF_BM_BYTES + SF_BC_BYTES);
+    bulk_load_1d(b_addr, wtc + SF_IMAGE_OFFSET_FLOATS, SF_BM_BYTES, smem_u32(&w_bar));
+    bulk_load_1d(b_addr + SF_BM_BYTES, wtc + SF_IMAGE_OFFSET_FLOATS + SF_BM_BYTES / 4, SF_BC_BYTES, smem_u32(&w_bar));
+    mbar_wait(smem_u32(&w_bar), 0);
+    int it = 0, buf = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)ab * 128;
+#pragma unroll
+      for (int kt = 0; kt < SF_KSTEPS; ++kt) {
+        mbar_wait(smem_u32(&a_full[buf]), ph);
+        tc_fence_after();
+        const uint32_t a_addr = base + (uint32_t)buf * SF_A_BUF;
+        const uint64_t ah = umma_desc_sw128(a_addr), al = umma_desc_sw128(a_addr + SK_A_BYTES);
+        const uint64_t bm = umma_desc_sw128(b_addr + (uint32_t)kt * SF_BM_STEP);
+        const uint64_t bc = umma_desc_sw128(b_addr + SF_BM_BYTES + (uint32_t)kt * SF_BC_STEP);
+        constexpr int NK = 4;
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+          if (kt < 2 || k < 3) umma_bf16(d, ah + (uint64_t)(2 * k), bm + (uint64_t)(2 * k), SF_IDESC_MAIN, (kt | k) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
+          if (kt < 2 || k < 3) umma_bf16(d, al + (uint64_t)(2 * k), bc + (uint64_t)(2 * k), SF_IDESC_CORR, 1u);
+        umma_commit(smem_u32(&a_free[buf]));
+        if (++buf == SF_NBUF) { buf = 0; ph ^= 1u; }
+      }
+      umma_commit(smem_u32(&acc_full[ab]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
 }  // namespace
 
 int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const float* wtc, const float* b, float* out,
@@ -248,7 +442,11 @@ int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const 
     const int rc = dh_encode_tiled_f32(&tmX, x, 4, dims, strides, box, false);
     if (rc) return rc;
   }
-  if (x3) {
+  if (x3 == 2) {
+    cudaError_t e = cudaFuncSetAttribute(stem_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    stem_f16_kernel<<<grid, SK_THREADS, SF_SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out);
+  } else if (x3) {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<true>::SMEM);
     if (e != cudaSuccess) return (int)e;
     stem_tc_kernel<true><<<grid, SK_THREADS, SkCfg<true>::SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out);

@@ -152,16 +152,36 @@ def kmajor_split(wt):
 
 
 def stem_tc_image(w147):
-    """[147][64] stem filter, K ordered (r, s, ci) like DH_W_STEM_W -> the tcgen05 stem's B operand: K re-ordered to
-    (ci, r, s8) — 21 groups of 8 (a zero + 7 taps) padded to 192 — then [hi | lo] images of 6 K-step tiles of the
-    swizzled B[n=co][k]."""
+    """[147][64] stem filter, K ordered (r, s, ci) like DH_W_STEM_W -> the tcgen05 stem's B operands (float32 buffer):
+    K re-ordered to (ci, r, s8) — 21 groups of 8 (a zero + 7 taps) padded to 192 — then
+      [0, 24576)       TF32 [hi | lo] images of 6 K-step tiles of the swizzled B[n=co][k 32]   (1xTF32 / 3xTF32 stem)
+      [24576, 36864)   raw bits of the folded FP16 image: 3 K-step tiles of 128 rows x 64 k 16-bit, rows 0..63 = f16(w),
+                       rows 64..127 = f16(2^11 (w - f16(w)))
+      [36864, 43008)   raw bits of 3 K-step tiles of 64 rows x 64 k bf16(w)                    (folded FP16 stem)"""
     w = w147.double().reshape(7, 7, 3, 64)                                   # [r][s][ci][co]
     wk = torch.zeros(24, 8, 64, dtype=torch.float64)
     wk[:21, 1:8] = w.permute(2, 0, 1, 3).reshape(21, 7, 64)                  # group = ci*7 + r; slot 0 = the alignment pad
     wk = wk.reshape(192, 64)
     hi, lo = tf32_split(wk)
     img = lambda m: torch.cat([swizzle128(m[kt * 32:(kt + 1) * 32].T.contiguous()) for kt in range(6)])
-    return torch.cat([img(hi), img(lo)])
+    h16 = wk.clamp(-65504.0, 65504.0).to(torch.float32).to(torch.float16)
+    s16 = ((wk - h16.double()) * 2048.0).clamp(-65504.0, 65504.0).to(torch.float32).to(torch.float16)
+    main = torch.cat([h16, s16], dim=1).view(torch.int16)                    # [192][128]: f16 w | scaled remainder
+    corr = wk.to(torch.float32).to(torch.bfloat16).view(torch.int16)         # [192][64]
+    img16 = lambda m: torch.cat([swizzle128_16(m[kt * 64:(kt + 1) * 64].T.contiguous()) for kt in range(3)]).view(torch.float32)
+    return torch.cat([img(hi).to(torch.float32), img(lo).to(torch.float32), img16(main), img16(corr)])
+
+
+def swizzle128_16(m):
+    """[rows][64] matrix of 16-bit values B[n][k] -> flat K-major SWIZZLE_128B image (rows of 128 B, the 16-byte chunk
+    index XOR-ed with row % 8): element (n, k) lands at n*64 + (((k>>3) ^ (n&7)) << 3 | (k&7))."""
+    rows = m.shape[0]
+    n = torch.arange(rows)[:, None].expand(rows, 64)
+    k = torch.arange(64)[None, :].expand(rows, 64)
+    idx = n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))
+    out = torch.empty(rows * 64, dtype=m.dtype)
+    out[idx.reshape(-1)] = m.reshape(-1)
+    return out
 
 
 def swizzle128(m):

@@ -110,7 +110,7 @@ enum dh_weight_slot {
    * (DH_DECTC_LAYER_FLOATS), "swz" = K-major SWIZZLE_128B image of B[n][k] (W1f: n=hidden, k=channel, LN2
    * gamma folded; W2: n=channel, k=hidden); cbA/cbM = cumulative biases after the attention / MLP of the layer */
   DH_W_LV5_DECTC, DH_W_LV4_DECTC, DH_W_LV3_DECTC,
-  DH_W_STEM_WTC,   /* stem filter for the tcgen05 stem: [hi, lo] x 6 K-step tiles of B[n=co 64][k 32] swz; K ordered (ci, r, s8): 21 groups of 1 zero + 7 taps, padded to 192 */
+  DH_W_STEM_WTC,   /* stem filter for the tcgen05 stem; K ordered (ci, r, s8): 21 groups of 1 zero + 7 taps, padded to 192.  [0, 24576) floats: TF32 [hi, lo] x 6 K-step tiles of B[n=co 64][k 32] swz; [24576, 36864): bits of 3 K-step tiles of [f16(w) 64 rows ; f16(2^11 (w - f16 w)) 64 rows][k 64] swz; [36864, 43008): bits of 3 tiles of bf16(w)[64][k 64] swz */
   DH_W_COUNT
 };
 
@@ -190,7 +190,7 @@ int dahitra_conv2d_up2_tc(const float* in, int N, int inH, int inW, const float*
 int dahitra_stem(const float* x, long long x_batch_stride, int N, int H, int W,
                  const float* w, const float* bias, float* out, void* stream);
 
-/* Same stem on the tensor cores (TF32 operands; x3 != 0: error-compensated 3xTF32): wtc = DH_W_STEM_WTC image. */
+/* Same stem on the tensor cores: x3 = 0 TF32 operands, 1 error-compensated 3xTF32, 2 folded FP16 (fp32-grade for |x| <= 65504; the default mode's stem); wtc = DH_W_STEM_WTC image. */
 int dahitra_stem_tc(const float* x, long long x_batch_stride, int N, int H, int W,
                     const float* wtc, const float* bias, float* out, int x3, void* stream);
 

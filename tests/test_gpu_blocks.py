@@ -180,6 +180,9 @@ def test_stem_tcgen05(shape):
     y3 = abi.stem_tc(x, wtc, b, x3=1)                      # error-compensated: same bar as the fp32 CUDA-core stem
     torch.cuda.synchronize()
     close(y3, ref)
+    yf = abi.stem_tc(x, wtc, b, x3=2)                      # folded FP16 operands (the default mode's stem): same bar
+    torch.cuda.synchronize()
+    close(yf, ref)
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64), (1, 18, 30, 128)])

@@ -108,6 +108,40 @@ def test_upsample_phase_filter_algebra():
     assert float((y - ref).abs().max()) < 1e-12
 
 
+def test_stem_folded_fp16_image_algebra():
+    """DH_W_STEM_WTC 16-bit images: de-swizzled, the three products of the folded FP16 stem
+    f16(a).f16(w) + 2^-11 f16(a).f16(2^11 r_w) + bf16(r_a).bf16(w) over K = (ci, r, s8) reproduce the 7x7 stride-2 conv."""
+    import torch.nn.functional as F
+    from dahitra_b200.engine import stem_tc_image
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(7, 7, 3, 64, generator=g, dtype=torch.float64) * 147 ** -0.5            # [r][s][ci][co]
+    x = torch.randn(1, 3, 20, 24, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, w.permute(3, 2, 0, 1), None, 2, 3)                                      # (1, 64, 10, 12)
+    img = stem_tc_image(w.reshape(147, 64))
+    assert img.shape == (43008,) and img.dtype == torch.float32
+    n = torch.arange(128)[:, None].expand(128, 64)
+    k = torch.arange(64)[None, :].expand(128, 64)
+    idx = n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))
+    main = img[24576:36864].view(torch.int16).view(3, 128 * 64)
+    corr = img[36864:43008].view(torch.int16).view(3, 64 * 64)
+    wm = torch.cat([main[kt][idx.reshape(-1)].view(128, 64).view(torch.float16).double() for kt in range(3)], 1)    # [128][192]
+    wc = torch.cat([corr[kt][idx[:64].reshape(-1)].view(64, 64).view(torch.bfloat16).double() for kt in range(3)], 1)  # [64][192]
+    # im2col rows in the kernel's K order: group = ci*7 + r, 8 consecutive columns starting one left of the first tap
+    xp = F.pad(x, (4, 4, 3, 3))[0]                                                            # col 0 = image col -4
+    A = torch.zeros(10 * 12, 192, dtype=torch.float64)
+    for oy in range(10):
+        for ox in range(12):
+            for ci in range(3):
+                for r in range(7):
+                    A[oy * 12 + ox, (ci * 7 + r) * 8:(ci * 7 + r) * 8 + 8] = xp[ci, 2 * oy + r, 2 * ox:2 * ox + 8]
+    ah = A.float().half().double()
+    al = (A - ah).float().bfloat16().double()
+    y = ah @ wm[:64].T + (ah @ wm[64:].T) / 2048.0 + al @ wc.T
+    y = y.T.reshape(1, 64, 10, 12)
+    assert float((y - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+    assert float((y - ref).abs().max()) < 0.02 * float((ah @ wm[:64].T - ref.reshape(64, -1).T).abs().max())   # the corrections do the work
+
+
 def test_tensor_core_decoder_pack(levir_template):
     """DH_W_LVk_DECTC: swizzled W1f / W2 images and cumulative biases reproduce the CUDA-core pack's algebra."""
     from dahitra_b200.engine import prepare_weights
