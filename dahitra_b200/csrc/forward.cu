@@ -332,9 +332,11 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
   // ---- Siamese trunk on 2B images: [pre batch | post batch]  (reference networks.py:1118-1138, 1323-1324)
   float* F2 = ws + p.f2;
   const double stem_fl = 2.0 * B * h2 * w2 * 64 * 147, stem_by = 4.0 * B * ((double)3 * H * W + (double)h2 * w2 * 64);
-  // stem operands: 0 = 1xTF32, 1 = 3xTF32, 2 = folded FP16 (whenever the convolutions run folded: the default mode)
-  const int stem_mode = !(flags & DH_FLAG_TC_3XTF32) ? 0
-                        : ((flags & DH_FLAG_TC_FOLD) && (flags & DH_FLAG_TC_MAIN_F16) && (flags & DH_FLAG_TC_X3_BF16)) ? 2 : 1;
+  // stem operands: 0 = 1xTF32, 1 = 3xTF32, 2 = folded FP16 (whenever the convolutions run folded: the default mode),
+  // 3 = single-pass FP16 (the single-pass 16-bit conv modes; the stem's input is an image, so BF16's range is not needed)
+  const int stem_mode = !(flags & DH_FLAG_TC_3XTF32)
+                            ? ((flags & (DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_BF16)) ? 3 : 0)
+                            : ((flags & DH_FLAG_TC_FOLD) && (flags & DH_FLAG_TC_MAIN_F16) && (flags & DH_FLAG_TC_X3_BF16)) ? 2 : 1;
   auto stem = [&](const float* xin, float* o) -> int {
     return (flags & DH_FLAG_STEM_TC) ? dh_launch_stem_tc(xin, x_batch_stride, B, H, W, Wt(DH_W_STEM_WTC), Wt(DH_W_STEM_B), o,
                                                          stem_mode, s)

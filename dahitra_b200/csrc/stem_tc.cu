@@ -246,9 +246,10 @@ constexpr uint32_t SF_OFF_B = SF_NBUF * SF_A_BUF;
 constexpr uint32_t SF_OFF_H = SF_OFF_B + SF_BM_BYTES + SF_BC_BYTES;
 constexpr uint32_t SF_OFF_E = SF_OFF_H + 2 * SK_HALO_STRIDE;
 constexpr uint32_t SF_SMEM = SF_OFF_E + 4 * 4096 + 1024;
-constexpr uint32_t SF_IDESC_MAIN = umma_idesc_f16(128, 128), SF_IDESC_CORR = umma_idesc_bf16(128, 64);
+constexpr uint32_t SF_IDESC_MAIN = umma_idesc_f16(128, 128), SF_IDESC_CORR = umma_idesc_bf16(128, 64), SF_IDESC_ONE = umma_idesc_f16(128, 64);
 constexpr size_t SF_IMAGE_OFFSET_FLOATS = 2 * (SK_B_BYTES / 4);      // the 16-bit images follow the TF32 [hi | lo] images in DH_W_STEM_WTC
 
+template <bool FOLD>   // FOLD = false: single-pass FP16 operands (rows 0..63 of the same filter tiles, no remainder products)
 __global__ void __launch_bounds__(SK_THREADS, 1)
 stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tilesX, int tilesY, int ntiles,
                 const float* __restrict__ wtc, const float* __restrict__ bias, float* __restrict__ out) {
@@ -312,7 +313,7 @@ stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int til
             }
             const int o = (j ^ swz) << 4;
             *reinterpret_cast<uint4*>(row + o) = hi;
-            *reinterpret_cast<uint4*>(row + SK_A_BYTES + o) = lo;
+            if (FOLD) *reinterpret_cast<uint4*>(row + SK_A_BYTES + o) = lo;
           }
         }
         fence_async_smem();
@@ -338,7 +339,12 @@ stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int til
       for (int j = 0; j < 2; ++j) {
         uint32_t u[32], r[32];
         tmem_ld32(tm + (uint32_t)(j * 32), u);
-        tmem_ld32(tm + (uint32_t)(64 + j * 32), r);
+        if (FOLD) {
+          tmem_ld32(tm + (uint32_t)(64 + j * 32), r);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
         if (j == 1) {
           tc_fence_before();
           mbar_arrive_local(smem_u32(&acc_empty[ab]));
@@ -401,10 +407,12 @@ stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int til
         constexpr int NK = 4;
 #pragma unroll
         for (int k = 0; k < NK; ++k)
-          if (kt < 2 || k < 3) umma_bf16(d, ah + (uint64_t)(2 * k), bm + (uint64_t)(2 * k), SF_IDESC_MAIN, (kt | k) ? 1u : 0u);
+          if (kt < 2 || k < 3) umma_bf16(d, ah + (uint64_t)(2 * k), bm + (uint64_t)(2 * k), FOLD ? SF_IDESC_MAIN : SF_IDESC_ONE, (kt | k) ? 1u : 0u);
+        if (FOLD) {
 #pragma unroll
-        for (int k = 0; k < NK; ++k)
-          if (kt < 2 || k < 3) umma_bf16(d, al + (uint64_t)(2 * k), bc + (uint64_t)(2 * k), SF_IDESC_CORR, 1u);
+          for (int k = 0; k < NK; ++k)
+            if (kt < 2 || k < 3) umma_bf16(d, al + (uint64_t)(2 * k), bc + (uint64_t)(2 * k), SF_IDESC_CORR, 1u);
+        }
         umma_commit(smem_u32(&a_free[buf]));
         if (++buf == SF_NBUF) { buf = 0; ph ^= 1u; }
       }
@@ -443,9 +451,13 @@ int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const 
     if (rc) return rc;
   }
   if (x3 == 2) {
-    cudaError_t e = cudaFuncSetAttribute(stem_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(stem_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
     if (e != cudaSuccess) return (int)e;
-    stem_f16_kernel<<<grid, SK_THREADS, SF_SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out);
+    stem_f16_kernel<true><<<grid, SK_THREADS, SF_SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out);
+  } else if (x3 == 3) {
+    cudaError_t e = cudaFuncSetAttribute(stem_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    stem_f16_kernel<false><<<grid, SK_THREADS, SF_SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out);
   } else if (x3) {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<true>::SMEM);
     if (e != cudaSuccess) return (int)e;

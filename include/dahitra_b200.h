@@ -190,7 +190,7 @@ int dahitra_conv2d_up2_tc(const float* in, int N, int inH, int inW, const float*
 int dahitra_stem(const float* x, long long x_batch_stride, int N, int H, int W,
                  const float* w, const float* bias, float* out, void* stream);
 
-/* Same stem on the tensor cores: x3 = 0 TF32 operands, 1 error-compensated 3xTF32, 2 folded FP16 (fp32-grade for |x| <= 65504; the default mode's stem); wtc = DH_W_STEM_WTC image. */
+/* Same stem on the tensor cores: x3 = 0 TF32 operands, 1 error-compensated 3xTF32, 2 folded FP16 (fp32-grade for |x| <= 65504; the default mode's stem), 3 single-pass FP16 (the f16 / bf16 modes' stem); wtc = DH_W_STEM_WTC image. */
 int dahitra_stem_tc(const float* x, long long x_batch_stride, int N, int H, int W,
                     const float* wtc, const float* bias, float* out, int x3, void* stream);
 

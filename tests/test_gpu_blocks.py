@@ -183,6 +183,9 @@ def test_stem_tcgen05(shape):
     yf = abi.stem_tc(x, wtc, b, x3=2)                      # folded FP16 operands (the default mode's stem): same bar
     torch.cuda.synchronize()
     close(yf, ref)
+    y1 = abi.stem_tc(x, wtc, b, x3=3)                      # single-pass FP16 (round-to-nearest operands: tighter than TF32)
+    torch.cuda.synchronize()
+    close(y1, ref, rtol=1e-3, atol=2e-3)
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64), (1, 18, 30, 128)])
