@@ -1,5 +1,5 @@
 """Host-to-host inference pipeline: pinned host batches in, class maps (or logits) out, with the H2D upload of
-batch i+1 overlapped with the forward of batch i.
+batch i+1 and the D2H download of result i-1 overlapped with the forward of batch i.
 
 This is the end-to-end path of the evaluator loop (reference models/evaluator.py:156-180 + :89-103:
 ``batch.to(device)`` -> ``net_G(x1, x2)`` -> ``argmax`` -> ``.cpu()``) written once, with the copies on a side
@@ -29,6 +29,7 @@ class PairPipeline:
         if self.dev.type != "cuda":
             raise RuntimeError("dahitra_b200: PairPipeline needs the module on a CUDA device")
         self.copy_stream = torch.cuda.Stream(self.dev)
+        self.out_stream = torch.cuda.Stream(self.dev)       # D2H of the results: the next forward does not queue behind it
         self._slots = None
         self._host = None
 
@@ -93,13 +94,15 @@ class PairPipeline:
                 res = torch.argmax(y, dim=1) if self.out == "argmax" else y
             free.record(main)
             host = self._host[cur_i % self.depth]
-            host.copy_(res, non_blocking=True)
             done = torch.cuda.Event()
-            done.record(main)
+            with torch.cuda.stream(self.out_stream):
+                self.out_stream.wait_event(free)        # recorded right after the forward: the result is complete
+                host.copy_(res, non_blocking=True)
+                done.record(self.out_stream)
             if pending is not None:
                 pending[1].synchronize()
                 yield pending[0]
-            pending = (host, done)
+            pending = (host, done, res)                 # `res` stays referenced until its copy has completed
             i += 1
         if pending is not None:
             pending[1].synchronize()

@@ -52,3 +52,26 @@ def test_pipeline_with_u8_inputs(levir_template):
             xb = torch.from_numpy(np.stack([IO.normalize_levir(i) for i in b.numpy()])).cuda()
             ref = net(xa, xb).argmax(1).to(torch.uint8).cpu()
             assert torch.equal(g, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("out", ["argmax_u8", "argmax", "logits"])
+def test_pipeline_results_equal_module_calls(levir_template, out):
+    """The three-stream pipeline (upload | forward | download) returns, batch for batch, what calling the module on each
+    batch returns — seven distinct batches through two slots, so every buffer is reused at least three times."""
+    from dahitra_b200.networks import BASE_Transformer_UNet
+    from dahitra_b200.pipeline import PairPipeline
+    from oracle import synth
+    net = BASE_Transformer_UNet(3, 2, 'learned', resnet_stages_num=4, with_decoder_pos='learned', enc_depth=1, dec_depth=8)
+    net.load_state_dict(synth.synth_state_dict(levir_template, seed=3, style="default"))
+    net = net.cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(2, 3, 256, 256, generator=g).pin_memory(), torch.randn(2, 3, 256, 256, generator=g).pin_memory())
+               for _ in range(7)]
+    got = [p.clone() for p in PairPipeline(net, out=out).run(batches)]
+    assert len(got) == 7
+    with torch.no_grad():
+        for (a, b), r in zip(batches, got):
+            y = net(a.cuda(), b.cuda())
+            ref = y if out == "logits" else y.argmax(1)
+            assert torch.equal(r.to(ref.dtype), ref.cpu())

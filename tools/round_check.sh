@@ -12,7 +12,7 @@ mkdir -p gpurun_out
 (timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1) > gpurun_out/bench_reference_$TAG.json 2>&1
 (timeout 300 python tools/latency_small_batch.py 2>&1 | tail -1) > gpurun_out/latency_b4_$TAG.json 2>&1
 (timeout 300 python tools/latency_small_batch.py --mode tf32 2>&1 | tail -1) >> gpurun_out/latency_b4_$TAG.json 2>&1
-tools/ncu_capture.sh tf32x3 $TAG "conv_tc2_kernel pixel_decoder_tc_kernel stem_tc_kernel" > gpurun_out/ncu_capture_stdout_$TAG.log 2>&1
+tools/ncu_capture.sh tf32x3 $TAG "conv_tc2_kernel pixel_decoder_tc_kernel stem_f16_kernel" > gpurun_out/ncu_capture_stdout_$TAG.log 2>&1
 tail -3 gpurun_out/pytest_gpu_$TAG.log gpurun_out/smoke_$TAG.log
 for f in default tf32 xbd1024 reference; do cut -c1-330 gpurun_out/bench_${f}_$TAG.json; done
 cat gpurun_out/latency_b4_$TAG.json
