@@ -241,14 +241,32 @@ def run_native(a, wl):
             for _ in pipe.run(hx[i % nsets] for i in range(3)):
                 pass
             barrier()
-            t0 = time.perf_counter()
+            # steady state of one pipe.run over K + 3 batches: the clock starts when result #3 is handed out and stops at
+            # result #K+3, so K uploads, K forwards and K downloads lie inside it; the run including the pipeline fill
+            # (first upload not overlapped) is reported next to it
+            t_fill = time.perf_counter()
             nres = 0
-            for pred in pipe.run(hx[i % nsets] for i in range(a.steps)):
+            for pred in pipe.run(hx[i % nsets] for i in range(a.steps + 3)):
                 nres += 1
-            barrier()
+                if nres == 3:
+                    t0 = time.perf_counter()
             e2e_sec = time.perf_counter() - t0
+            barrier()
+            e2e_fill_sec = (time.perf_counter() - t_fill) * a.steps / (a.steps + 3)
             e2e_d2h = Bp * H * W
-            assert nres == a.steps
+            assert nres == a.steps + 3
+            # the upload alone (what PCIe allows for fp32 inputs)
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d1, d2 = torch.empty_like(sets[0][0]), torch.empty_like(sets[0][1])
+            torch.cuda.synchronize()
+            h0.record()
+            for i in range(3):
+                d1.copy_(hx[i % nsets][0], non_blocking=True)
+                d2.copy_(hx[i % nsets][1], non_blocking=True)
+            h1.record()
+            torch.cuda.synchronize()
+            h2d_ms = h0.elapsed_time(h1) / 3
+            del d1, d2
         clocks = sampler.stop() if sampler else None
         # ---- per-launch profile (after the timed regions): roofline of the dominant kernel
         prof = None
@@ -362,6 +380,8 @@ def run_native(a, wl):
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit="pairs/s", h2d_bytes_per_step=2 * Bp * 3 * H * W * 4,
                          d2h_bytes_per_step=e2e_d2h, ms_per_step=e2e_ms / a.steps,
+                         timing="steady state of one PairPipeline.run: K results between the 3rd and the (K+3)th hand-out (wall clock)",
+                         ms_per_step_including_fill=e2e_fill_sec * 1e3 / a.steps, h2d_alone_ms_per_step=h2d_ms,
                          api="dahitra_b200.pipeline.PairPipeline(net).run(pinned host batches): H2D of batch i+1 overlaps the "
                              "forward of batch i; uint8 class map D2H every step",
                          unpipelined=dict(value=world * Bp * a.steps / (e2e_sync_ms / 1e3), d2h_bytes_per_step=Bp * H * W * 8,
