@@ -57,6 +57,44 @@ __device__ __forceinline__ SkTile sk_tile(int t, int tilesX, int tilesY) {
   return r;
 }
 
+// Halo producer (one lane): ONE TMA box per tile over the NCHW tensor, double-buffered through halo_full / halo_free.
+// x start must be 16-byte aligned: the box starts one column left of the first tap.
+__device__ __forceinline__ void sk_halo_producer(const CUtensorMap* tmX, uint32_t halo_addr, uint64_t* halo_full, uint64_t* halo_free,
+                                                 int tilesX, int tilesY, int ntiles) {
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int hb = it & 1;
+    if (it >= 2) mbar_wait(smem_u32(&halo_free[hb]), (uint32_t)(((it >> 1) - 1) & 1));   // all builders left this buffer
+    const SkTile tl = sk_tile(tile, tilesX, tilesY);
+    const uint32_t bar = smem_u32(&halo_full[hb]);
+    mbar_expect_tx(bar, SK_HALO_BYTES);
+    tma_load_4d(halo_addr + (uint32_t)hb * SK_HALO_STRIDE, tmX, bar, 2 * tl.ox0 - 4, 2 * tl.oy0 - 3, 0, tl.n);
+  }
+}
+
+// Epilogue of one 32-column slice of one warp's 32 accumulator rows: through a per-warp shared-memory transpose so that
+// each store instruction writes four whole 128-byte lines (8 lanes per pixel) instead of 16 bytes of 32 different
+// lines (same scheme as conv_tc2.cu); + bias, ReLU, NHWC.
+__device__ __forceinline__ void sk_store_slice(const float (&v)[32], float* stage, int lane, int q, int j, const SkTile& t,
+                                               int OH, int OW, const float* __restrict__ bias, float* __restrict__ out) {
+  const int c8 = lane & 7, r8 = lane >> 3;
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4)
+    *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+  __syncwarp();
+  const float4 b = ldg4(bias + j * 32 + c8 * 4);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int r = g * 4 + r8, mm = q * 32 + r;             // tile pixel (py = mm / 16, px = mm % 16)
+    const int oy = t.oy0 + mm / SK_TW, ox = t.ox0 + mm % SK_TW;
+    const float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((c8 ^ (r & 7)) << 2));
+    if (oy < OH && ox < OW)
+      st4(out + ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32 + c8 * 4,
+          make_float4(fmaxf(o.x + b.x, 0.f), fmaxf(o.y + b.y, 0.f), fmaxf(o.z + b.z, 0.f), fmaxf(o.w + b.w, 0.f)));
+  }
+  __syncwarp();
+}
+
 template <bool X3>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tilesX, int tilesY, int ntiles,
@@ -132,11 +170,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tile
     }
   } else if (warp < 12) {
     // ------------------------------------------------------------------ epilogue warps 8..11
-    // rows out of TMEM, through a per-warp shared-memory transpose, so that each store instruction writes four whole
-    // 128-byte lines (8 lanes per pixel) instead of 16 bytes of 32 different lines (same scheme as conv_tc2.cu)
     const int q = warp & 3, lane = tid & 31;
     float* stage = reinterpret_cast<float*>(bp + Cfg::OFF_E + (size_t)q * 4096);
-    const int c8 = lane & 7, r8 = lane >> 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const SkTile t = sk_tile(tile, tilesX, tilesY);
@@ -147,42 +182,20 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tile
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
         uint32_t u[32];
+        float v[32];
         tmem_ld32(tm + (uint32_t)(j * 32), u);
         if (j == 1) {
           tc_fence_before();
           mbar_arrive_local(smem_u32(&acc_empty[ab]));
         }
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4)
-          *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
-              make_float4(__uint_as_float(u[c4 * 4]), __uint_as_float(u[c4 * 4 + 1]), __uint_as_float(u[c4 * 4 + 2]), __uint_as_float(u[c4 * 4 + 3]));
-        __syncwarp();
-        const float4 b = ldg4(bias + j * 32 + c8 * 4);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int r = g * 4 + r8, mm = q * 32 + r;             // tile pixel (py = mm / 16, px = mm % 16)
-          const int oy = t.oy0 + mm / SK_TW, ox = t.ox0 + mm % SK_TW;
-          const float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((c8 ^ (r & 7)) << 2));
-          if (oy < OH && ox < OW)
-            st4(out + ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32 + c8 * 4,
-                make_float4(fmaxf(o.x + b.x, 0.f), fmaxf(o.y + b.y, 0.f), fmaxf(o.z + b.z, 0.f), fmaxf(o.w + b.w, 0.f)));
-        }
-        __syncwarp();
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+        sk_store_slice(v, stage, lane, q, j, t, OH, OW, bias, out);
       }
     }
   } else if (warp == 13) {
     // ------------------------------------------------------------------ halo producer (warp 13, one lane)
-    if ((tid & 31) == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int hb = it & 1;
-        if (it >= 2) mbar_wait(smem_u32(&halo_free[hb]), (uint32_t)(((it >> 1) - 1) & 1));   // all builders left this buffer
-        const SkTile tl = sk_tile(tile, tilesX, tilesY);
-        const uint32_t bar = smem_u32(&halo_full[hb]);
-        mbar_expect_tx(bar, SK_HALO_BYTES);
-        tma_load_4d(base + Cfg::OFF_H + (uint32_t)hb * SK_HALO_STRIDE, &tmX, bar, 2 * tl.ox0 - 4, 2 * tl.oy0 - 3, 0, tl.n);   // x start must be 16-byte aligned: one column early
-      }
-    }
+    if ((tid & 31) == 0) sk_halo_producer(&tmX, base + Cfg::OFF_H, halo_full, halo_free, tilesX, tilesY, ntiles);
   } else if ((tid & 31) == 0) {
     // ------------------------------------------------------------------ MMA issuer (warp 12, one lane)
     mbar_expect_tx(smem_u32(&w_bar), Cfg::NB * SK_B_BYTES);
@@ -324,10 +337,9 @@ stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int til
       mbar_arrive_local(smem_u32(&halo_free[hb]));
     }
   } else if (warp < 12) {
-    // ------------------------------------------------------------------ epilogue warps 8..11 (coalesced through a per-warp transpose)
+    // ------------------------------------------------------------------ epilogue warps 8..11: main + 2^-11 scaled remainder
     const int q = warp & 3, lane = tid & 31;
     float* stage = reinterpret_cast<float*>(bp + SF_OFF_E + (size_t)q * 4096);
-    const int c8 = lane & 7, r8 = lane >> 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const SkTile t = sk_tile(tile, tilesX, tilesY);
@@ -338,51 +350,21 @@ stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int til
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
         uint32_t u[32], r[32];
+        float v[32];
         tmem_ld32(tm + (uint32_t)(j * 32), u);
-        if (FOLD) {
-          tmem_ld32(tm + (uint32_t)(64 + j * 32), r);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0u;
-        }
+        if (FOLD) tmem_ld32(tm + (uint32_t)(64 + j * 32), r);
         if (j == 1) {
           tc_fence_before();
           mbar_arrive_local(smem_u32(&acc_empty[ab]));
         }
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4)
-          *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
-              make_float4(fmaf(__uint_as_float(r[c4 * 4]), 0x1p-11f, __uint_as_float(u[c4 * 4])),
-                          fmaf(__uint_as_float(r[c4 * 4 + 1]), 0x1p-11f, __uint_as_float(u[c4 * 4 + 1])),
-                          fmaf(__uint_as_float(r[c4 * 4 + 2]), 0x1p-11f, __uint_as_float(u[c4 * 4 + 2])),
-                          fmaf(__uint_as_float(r[c4 * 4 + 3]), 0x1p-11f, __uint_as_float(u[c4 * 4 + 3])));
-        __syncwarp();
-        const float4 b = ldg4(bias + j * 32 + c8 * 4);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int rr = g * 4 + r8, mm = q * 32 + rr;
-          const int oy = t.oy0 + mm / SK_TW, ox = t.ox0 + mm % SK_TW;
-          const float4 o = *reinterpret_cast<const float4*>(stage + rr * 32 + ((c8 ^ (rr & 7)) << 2));
-          if (oy < OH && ox < OW)
-            st4(out + ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32 + c8 * 4,
-                make_float4(fmaxf(o.x + b.x, 0.f), fmaxf(o.y + b.y, 0.f), fmaxf(o.z + b.z, 0.f), fmaxf(o.w + b.w, 0.f)));
-        }
-        __syncwarp();
+        for (int i = 0; i < 32; ++i) v[i] = FOLD ? fmaf(__uint_as_float(r[i]), 0x1p-11f, __uint_as_float(u[i])) : __uint_as_float(u[i]);
+        sk_store_slice(v, stage, lane, q, j, t, OH, OW, bias, out);
       }
     }
   } else if (warp == 13) {
-    // ------------------------------------------------------------------ halo producer
-    if ((tid & 31) == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int hb = it & 1;
-        if (it >= 2) mbar_wait(smem_u32(&halo_free[hb]), (uint32_t)(((it >> 1) - 1) & 1));
-        const SkTile tl = sk_tile(tile, tilesX, tilesY);
-        const uint32_t bar = smem_u32(&halo_full[hb]);
-        mbar_expect_tx(bar, SK_HALO_BYTES);
-        tma_load_4d(base + SF_OFF_H + (uint32_t)hb * SK_HALO_STRIDE, &tmX, bar, 2 * tl.ox0 - 4, 2 * tl.oy0 - 3, 0, tl.n);
-      }
-    }
+    // ------------------------------------------------------------------ halo producer (warp 13, one lane)
+    if ((tid & 31) == 0) sk_halo_producer(&tmX, base + SF_OFF_H, halo_full, halo_free, tilesX, tilesY, ntiles);
   } else if ((tid & 31) == 0) {
     // ------------------------------------------------------------------ MMA issuer (warp 12, one lane)
     mbar_expect_tx(smem_u32(&w_bar), SF_BM_BYTES + SF_BC_BYTES);

@@ -32,12 +32,12 @@ MODES = {
     # accumulation).  Convolutions: main product in FP16 (11-bit significand like TF32, 16-bit operands), the two
     # correction products in BF16 (fp32 exponent range) — half the tensor-core cycles of three TF32 products and a
     # slightly smaller error.  Operands beyond the FP16 range (|v| > 65504, or < 1e-7) fall back on the BF16 terms
-    # (bf16-grade accuracy for those values only).  7x7 stem and pixel decoder: 3xTF32.
+    # (bf16-grade accuracy for those values only).  The 7x7 stem runs the same way; pixel decoder: 3xTF32.
     # The f16(a).r_w correction shares its A operand with the main product, so both come out of ONE N-doubled FP16 MMA
     # on the filter tile [f16(w) ; f16(2^11 r_w)] and are added in the epilogue (DH_FLAG_TC_FOLD).
     "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_FOLD | DH_FLAG_TC_STRIDE2
               | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
-    # ... with three separate products per (tap, chunk) (~7 % slower)
+    # ... with three separate products per (tap, chunk) and the 3xTF32 stem (~10 % slower)
     "tf32x3_unfolded": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC
                        | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     # the same with the main product in TF32 (no range caveat, ~15 % slower)
@@ -46,9 +46,10 @@ MODES = {
     "tf32x3_pure": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     # single-pass FP16 operands in the convolutions (TF32-grade significand, half the operand bytes of "tf32";
-    # saturating outside +-65504), 1xTF32 stem, 3xTF32 decoder
+    # saturating outside +-65504) and in the stem, 3xTF32 decoder
     "f16": DH_FLAG_CONV_TC | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
-    # reduced precision: BF16 operands in every convolution (fp32 storage / accumulation), 1xTF32 stem, 3xTF32 decoder
+    # reduced precision: BF16 operands in every convolution (fp32 storage / accumulation), single-pass FP16 stem (its input is an
+    # image), 3xTF32 decoder
     "bf16": DH_FLAG_CONV_TC | DH_FLAG_TC_BF16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     "tf32_fast": DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC,   # 1xTF32 decoder too
 }

@@ -58,7 +58,7 @@ extern "C" {
 #define DH_FLAG_TC_X3_BF16  512 /* with TC_3XTF32: the two correction products of every conv as BF16 MMAs (half their cost) */
 #define DH_FLAG_TC_BF16     1024 /* with CONV_TC: single-pass BF16 operands in the convolutions (fp32 storage and accumulation); overrides TC_3XTF32 */
 #define DH_FLAG_TC_MAIN_F16 2048 /* with TC_3XTF32: main product of every conv in FP16 (K = 16 MMAs), both corrections in BF16; without it: single-pass FP16 operands */
-#define DH_FLAG_TC_FOLD     4096 /* with TC_3XTF32 | TC_MAIN_F16: fold the f16(a).r_w correction into the main MMA (2N-wide filter tile) */
+#define DH_FLAG_TC_FOLD     4096 /* with TC_3XTF32 | TC_MAIN_F16: fold the f16(a).r_w correction into the main MMA (2N-wide filter tile); with TC_X3_BF16 the stem runs the same folded FP16 form */
 #define DH_FLAG_EARLY_HEAD  8192 /* issue conv_layer2_0.0 right after the stem on a lowest-priority side stream, one tile per CTA */
 /* the modes dahitra_b200.engine.MODES names (DESIGN.md "Precision modes") */
 #define DH_FLAGS_TF32X3     (DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_FOLD | DH_FLAG_TC_STRIDE2 | \
