@@ -108,6 +108,36 @@ def test_upsample_phase_filter_algebra():
     assert float((y - ref).abs().max()) < 1e-12
 
 
+def test_filter_planes_of_the_precision_modes():
+    """engine.kmajor_split: every plane decodes to what its mode's MMAs expect, and the products each mode issues
+    reproduce a.w to that mode's accuracy (emulated in fp64 on operands rounded like the kernels round them)."""
+    from dahitra_b200.engine import kmajor_split, tf32_split
+    g = torch.Generator().manual_seed(1)
+    cout, K, M = 64, 9 * 64, 200
+    w = torch.randn(cout, K, generator=g, dtype=torch.float64) * K ** -0.5
+    a = torch.randn(M, K, generator=g, dtype=torch.float64)
+    ref = a @ w.T
+    P = kmajor_split(w)
+    assert P.shape == (5, cout, K) and P.dtype == torch.float32
+    hi, lo = P[0].double(), P[1].double()
+    assert torch.equal(hi, tf32_split(w)[0]) and float((w - hi - lo).abs().max()) < 2 ** -21 * float(w.abs().max())
+    b16 = P[2].contiguous().view(torch.int16).reshape(2, cout, K).view(torch.bfloat16).double()       # {bf16(w), bf16(w - hi)}
+    f16 = P[3].contiguous().view(torch.int16).reshape(2, cout, K)
+    wh, wr = f16[0].view(torch.float16).double(), f16[1].view(torch.bfloat16).double()               # {f16(w), bf16(w - f16 w)}
+    ws = P[4].contiguous().view(torch.int16).reshape(2, cout, K)[0].view(torch.float16).double()      # f16(2^11 (w - f16 w))
+    assert torch.equal(b16[0], w.float().bfloat16().double()) and torch.equal(wh, w.float().half().double())
+    ah, a_t = a.float().half().double(), tf32_split(a)[0]
+    ar = (a - ah).float().bfloat16().double()
+    err = lambda y: float((y - ref).abs().max()) / float(ref.abs().max())
+    e_f16 = err(ah @ wh.T)                                                       # single-pass FP16 (mode "f16")
+    e_x3 = err(a_t @ hi.T + (a - a_t).float().bfloat16().double() @ b16[0].T + a.float().bfloat16().double() @ b16[1].T)   # XM = 2
+    e_main16 = err(ah @ wh.T + ar @ b16[0].T + ah.float().bfloat16().double() @ wr.T)          # XM = 4
+    e_fold = err(ah @ wh.T + (ah @ ws.T) / 2048.0 + ar @ b16[0].T)                              # XM = 6 (default)
+    assert 1e-5 < e_f16 < 2e-3
+    assert e_x3 < 3e-6 and e_main16 < 3e-6 and e_fold < 2e-6
+    assert e_fold <= e_main16 * 1.05                          # 11-bit scaled remainder beats the 8-bit bf16 one
+
+
 def test_stem_folded_fp16_image_algebra():
     """DH_W_STEM_WTC 16-bit images: de-swizzled, the three products of the folded FP16 stem
     f16(a).f16(w) + 2^-11 f16(a).f16(2^11 r_w) + bf16(r_a).bf16(w) over K = (ci, r, s8) reproduce the 7x7 stride-2 conv."""
