@@ -238,7 +238,8 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
             pos = sd[f"pos_embedding_{k}"].double().reshape(-1) if f"pos_embedding_{k}" in sd \
                 else torch.zeros(256, dtype=torch.float64)
         else:   # xBD: only the H/16 level adds one, and it is pos_embedding_3 (model_transformer_encoding.py:358-366)
-            pos = sd["pos_embedding_3"].double().reshape(-1) if k == 5 else torch.zeros(256, dtype=torch.float64)
+            pos = sd["pos_embedding_3"].double().reshape(-1) if (k == 5 and "pos_embedding_3" in sd) \
+                else torch.zeros(256, dtype=torch.float64)      # with_pos=None builds no token embeddings (reference default)
         wqkv = sd[t + ".0.fn.fn.to_qkv.weight"].double()
         inner = heads * 64
         wq, wk, wv = (_heads(wqkv[i * inner:(i + 1) * inner], heads) for i in range(3))
@@ -341,9 +342,10 @@ class PreparedWeights:
 # ----------------------------------------------------------------------------- engine
 class NativeEngine:
     def __init__(self):
-        self._prep = None
-        self._prep_key = None
-        self._ws = {}
+        self._preps = {}            # (device, variant) -> PreparedWeights; all dropped when the live tensors change
+        self._tensors = None        # the module's parameters + buffers (cached walk of the module tree)
+        self._fingerprint = None
+        self._ws = {}               # (device, stream, variant, B, H, W, nc) -> workspace; released only explicitly
         # precision mode: DAHITRA_FLAGS (raw DH_FLAG_* bitmask) > DAHITRA_MODE (a MODES name) > DEFAULT_MODE
         if "DAHITRA_FLAGS" in os.environ:
             self.flags = int(os.environ["DAHITRA_FLAGS"])
@@ -351,9 +353,23 @@ class NativeEngine:
             self.flags = resolve_mode(os.environ.get("DAHITRA_MODE", DEFAULT_MODE))
         self.last_argmax = None
 
+    # an engine holds device pointers (ctypes table) and scratch memory: copies / pickles of the owning module get a fresh,
+    # empty engine that carries only the precision mode (copy.deepcopy(net) for EMA / SWA, torch.save(net))
+    def __deepcopy__(self, memo):
+        e = NativeEngine.__new__(NativeEngine)
+        e.__setstate__(self.__getstate__())
+        return e
+
+    def __getstate__(self):
+        return {"flags": self.flags}
+
+    def __setstate__(self, st):
+        self._preps, self._tensors, self._fingerprint, self._ws, self.last_argmax = {}, None, None, {}, None
+        self.flags = st.get("flags", MODES[DEFAULT_MODE])
+
     def set_mode(self, mode):
-        """mode: a key of MODES or a raw DH_FLAG_* bitmask.  Prepared weights / workspaces are keyed by the flags,
-        so switching back and forth does not rebuild anything."""
+        """mode: a key of MODES or a raw DH_FLAG_* bitmask.  Every mode runs from the same prepared weights, so switching
+        back and forth does not rebuild or re-upload anything."""
         self.flags = resolve_mode(mode)
 
     @property
@@ -361,26 +377,50 @@ class NativeEngine:
         return next((k for k, v in MODES.items() if v == self.flags), f"flags{self.flags}")
 
     def invalidate(self):
-        self._prep = None
-        self._prep_key = None
+        """Forget the prepared weights AND the cached list of the module's tensors (call after replacing a Parameter
+        object; in-place updates, load_state_dict, .to() and optimizer steps are detected without it)."""
+        self._preps = {}
+        self._tensors = None
+        self._fingerprint = None
+
+    def release_workspaces(self):
+        """Free the scratch buffers (one per (device, stream, shape)).  Never done implicitly: a captured CUDA graph keeps
+        pointing at the workspace it was captured with."""
+        self._ws = {}
+
+    def _live_fingerprint(self, module):
+        # cheap staleness check on every forward (~25 us): the version counter of every parameter / buffer changes on any
+        # in-place write (optimizer.step, copy_, load_state_dict on this module or on a parent, EMA updates), the storage
+        # address on .to() / .cuda()
+        ts = self._tensors
+        if ts is None:
+            ts = self._tensors = [t for t in list(module.parameters()) + list(module.buffers())]
+        return (tuple(t._version for t in ts), ts[0].data_ptr() if ts else 0, len(ts))
 
     def _prepared(self, module, device):
-        key = (str(device), module.VARIANT, self.flags)
-        if self._prep is None or self._prep_key != key:
+        fp = self._live_fingerprint(module)
+        if fp != self._fingerprint:
+            self._preps = {}
+            self._fingerprint = fp
+        key = (str(device), module.VARIANT)
+        prep = self._preps.get(key)
+        if prep is None:
             variant = DH_VARIANT_LEVIR if module.VARIANT == "levir" else DH_VARIANT_XBD
-            self._prep = PreparedWeights(module.state_dict(), variant, module.output_nc, device)
-            self._prep_key = key
-        return self._prep
+            prep = self._preps[key] = PreparedWeights(module.state_dict(), variant, module.output_nc, device)
+        return prep
 
     def _workspace(self, lib, device, variant, B, H, W, nc):
-        key = (str(device), variant, B, H, W, nc, self.flags)
+        stream = torch.cuda.current_stream(device)
+        capturing = torch.cuda.is_current_stream_capturing()
+        # one workspace per stream: two forwards issued on different streams must not share scratch memory.  A workspace
+        # first needed while a graph is being captured is allocated from that graph's pool and is never handed to eager
+        # launches (key "capture"); entries are only freed by release_workspaces().
+        key = (str(device), "capture" if capturing else stream.cuda_stream, variant, B, H, W, nc)
         ws = self._ws.get(key)
         if ws is None:
             nbytes = lib.dahitra_workspace_bytes(variant, B, H, W, nc, self.flags)
             if nbytes == 0:
                 raise RuntimeError(f"dahitra_b200: unsupported shape B={B} H={H} W={W} (H, W must be multiples of 32)")
-            if len(self._ws) > 4:
-                self._ws.clear()
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._ws[key] = ws
         return ws
@@ -401,9 +441,10 @@ class NativeEngine:
         logits = torch.empty((B, nc, H, W), dtype=torch.float32, device=dev)
         amax = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_argmax else None
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.dahitra_forward(prep.table, prep.n, x1.data_ptr(), x2.data_ptr(), batch_stride,
-                                 logits.data_ptr(), amax.data_ptr() if amax is not None else None,
-                                 ws.data_ptr(), ws.numel(), variant, B, H, W, nc, self.flags, stream)
+        with torch.cuda.device(dev):        # the library sizes grids / creates its side streams on the CURRENT device
+            rc = lib.dahitra_forward(prep.table, prep.n, x1.data_ptr(), x2.data_ptr(), batch_stride,
+                                     logits.data_ptr(), amax.data_ptr() if amax is not None else None,
+                                     ws.data_ptr(), ws.numel(), variant, B, H, W, nc, self.flags, stream)
         _lib.check(rc, "dahitra_forward")
         self.last_argmax = amax
         return logits
@@ -425,9 +466,10 @@ class NativeEngine:
         ms, fl, by = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
         names = (C.c_char_p * cap)()
         stream = torch.cuda.current_stream(dev).cuda_stream
-        n = lib.dahitra_forward_profiled(prep.table, prep.n, x1.data_ptr(), x2.data_ptr(), 3 * H * W, logits.data_ptr(),
-                                         None, ws.data_ptr(), ws.numel(), variant, B, H, W, nc, self.flags, stream,
-                                         cap, ms, fl, by, names)
+        with torch.cuda.device(dev):
+            n = lib.dahitra_forward_profiled(prep.table, prep.n, x1.data_ptr(), x2.data_ptr(), 3 * H * W, logits.data_ptr(),
+                                             None, ws.data_ptr(), ws.numel(), variant, B, H, W, nc, self.flags, stream,
+                                             cap, ms, fl, by, names)
         if n <= 0:
             _lib.check(n if n > -1000 else -(n + 1000), "dahitra_forward_profiled")
         return [dict(name=names[i].decode(), ms=float(ms[i]), flops=float(fl[i]), bytes=float(by[i])) for i in range(n)]

@@ -22,7 +22,8 @@ def normalize_u8(img: torch.Tensor, kind: str = "levir", tile: int = 0, out: tor
     T = (H // th) * (W // tw)
     if out is None:
         out = torch.empty((N * T, 3, th, tw), dtype=torch.float32, device=img.device)
-    rc = _lib.load().dahitra_prepare_input_u8(img.data_ptr(), N, H, W, KINDS[kind], tile, out.data_ptr(),
-                                              torch.cuda.current_stream(img.device).cuda_stream)
+    with torch.cuda.device(img.device):
+        rc = _lib.load().dahitra_prepare_input_u8(img.data_ptr(), N, H, W, KINDS[kind], tile, out.data_ptr(),
+                                                  torch.cuda.current_stream(img.device).cuda_stream)
     _lib.check(rc, "dahitra_prepare_input_u8")
     return out

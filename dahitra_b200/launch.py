@@ -33,9 +33,10 @@ def _stub(name, **attrs):
         setattr(sys.modules[name], k, v)
 
 
-def install(ref_root: str, stub_missing: bool = False, offline_trunk: bool = False):
-    """Import the reference's ``models.networks`` from ``ref_root`` and rebind the network class.
-    Returns the reference ``models.networks`` module."""
+def install(ref_root: str, stub_missing: bool = False, offline_trunk: bool = False, rebind: bool = True):
+    """Import the reference's ``models.networks`` from ``ref_root`` and rebind the network class (``rebind=False``
+    leaves the reference's own class in place: only the import shims are applied — used by the reference arm of
+    bench.py and the harness tests).  Returns the reference ``models.networks`` module."""
     import torch
     ref_root = os.path.abspath(ref_root)
     if ref_root not in sys.path:
@@ -66,8 +67,9 @@ def install(ref_root: str, stub_missing: bool = False, offline_trunk: bool = Fal
     if offline_trunk:
         res = importlib.import_module("models.resnet")
         res._resnet = lambda arch, block, layers, pretrained, progress, **kw: res.ResNet(block, layers, **kw)
-    from dahitra_b200.networks import BASE_Transformer_UNet
-    nets.BASE_Transformer_UNet = BASE_Transformer_UNet
+    if rebind:
+        from dahitra_b200.networks import BASE_Transformer_UNet
+        nets.BASE_Transformer_UNet = BASE_Transformer_UNet
     return nets
 
 

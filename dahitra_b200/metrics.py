@@ -33,8 +33,9 @@ def confusion_matrix(pred: torch.Tensor, gt: torch.Tensor, n_class: int, out: to
         out = torch.zeros((n_class, n_class), dtype=torch.int64, device=pred.device)
     if p8.numel() == 0:
         return out
-    rc = _lib.load().dahitra_confusion_matrix(p8.data_ptr(), g8.data_ptr(), p8.numel(), n_class, out.data_ptr(),
-                                              torch.cuda.current_stream(pred.device).cuda_stream)
+    with torch.cuda.device(pred.device):
+        rc = _lib.load().dahitra_confusion_matrix(p8.data_ptr(), g8.data_ptr(), p8.numel(), n_class, out.data_ptr(),
+                                                  torch.cuda.current_stream(pred.device).cuda_stream)
     _lib.check(rc, "dahitra_confusion_matrix")
     return out
 

@@ -172,6 +172,77 @@ def test_xbd_1024_golden(golden_dir):
     assert np.abs(hist - g["argmax_hist"]).sum() <= 0.002 * 1024 * 1024
 
 
+def test_xbd_1024_batch8_vs_oracle():
+    """config 3 at the shape bench.py times — (8,6,1024,1024), 5 classes: pairs 1 and 6 of the batch against the fp64
+    oracle (same yardstick as the B=1 golden test: the reference arithmetic's own fp32 noise on this case), and every pair
+    bit-identical to the same pair run alone (batch offsets / x_batch_stride = 6*H*W / workspace plan at B=8)."""
+    from dahitra_b200.xbd import BASE_Transformer_UNet as X
+    net = X(input_nc=3, output_nc=5, token_len=4, resnet_stages_num=4, with_pos="learned",
+            with_decoder_pos="learned", enc_depth=1, dec_depth=8)
+    sd = synth.synth_state_dict(net.state_dict(), seed=6, style="default")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).eval().set_mode(_MODE)
+    gen = torch.Generator().manual_seed(70)
+    x = torch.randint(0, 256, (8, 6, 1024, 1024), generator=gen).float() / 127 - 1
+    xd = x.to(DEV)
+    with torch.no_grad():
+        y = net(xd)
+        assert y.shape == (8, 5, 1024, 1024) and torch.isfinite(y).all()
+        for i in (0, 3, 7):
+            assert torch.equal(net(xd[i:i + 1].contiguous())[0], y[i]), i
+    pick = [1, 6]
+    ref64 = O.forward_xbd(sd, x[pick], dtype=torch.float64)
+    ref32 = O.forward_xbd(sd, x[pick]).double()
+    got = y[pick].double().cpu()
+    noise = float((ref32 - ref64).abs().max())
+    err = float((got - ref64).abs().max())
+    agree = float((got.argmax(1) == ref64.argmax(1)).float().mean())
+    print(f"[parity] [{_MODE}] xbd 1024 B=8 pairs {pick}: max|d| vs fp64 oracle {err:.3e}; fp32 noise {noise:.3e}; argmax agree {agree:.6f}")
+    k = 2.0 if _MODE == "fp32" else 4.0
+    assert err <= max(k * noise, ATOL + RTOL * float(ref64.abs().max()))
+    assert agree >= 0.999
+    assert float((got - ref64).abs().mean()) <= k * float((ref32 - ref64).abs().mean()) + 1e-5
+
+
+def test_module_on_non_current_device(levir_template):
+    """net.to('cuda:1') with cuda:0 current (works with the reference module): launches, side streams and grid sizes must
+    follow the tensors' device, not the current one."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sd = synth.synth_state_dict(levir_template, seed=3, style="default")
+    net0 = make_net(sd)
+    from dahitra_b200.networks import BASE_Transformer_UNet
+    net1 = BASE_Transformer_UNet(3, 2, 'learned', resnet_stages_num=4, with_decoder_pos='learned', enc_depth=1, dec_depth=8)
+    net1.load_state_dict(sd)
+    net1 = net1.to("cuda:1").eval().set_mode(_MODE)
+    x1, x2 = synth.synth_pair(2, 256, 256, seed=2, kind="uniform")
+    torch.cuda.set_device(0)
+    with torch.no_grad():
+        y0 = net0(x1.to("cuda:0"), x2.to("cuda:0"))
+        y1 = net1(x1.to("cuda:1"), x2.to("cuda:1"))
+    assert y1.device.index == 1 and torch.equal(y0.cpu(), y1.cpu())
+
+
+def test_two_streams_do_not_share_scratch(levir_template):
+    """Two forwards of one module issued on two CUDA streams run concurrently on separate workspaces."""
+    sd = synth.synth_state_dict(levir_template, seed=3, style="default")
+    net = make_net(sd)
+    xs = [tuple(t.to(DEV) for t in synth.synth_pair(6, 256, 256, seed=80 + i, kind="uniform")) for i in range(2)]
+    with torch.no_grad():
+        ref = [net(a, b).clone() for a, b in xs]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        outs = [None, None]
+        for rep in range(3):
+            for i, st in enumerate(streams):
+                with torch.cuda.stream(st):
+                    outs[i] = net(*xs[i])
+            torch.cuda.synchronize()
+            for i in range(2):
+                assert torch.equal(outs[i], ref[i]), (rep, i)
+    assert len(net._engine._ws) == 3          # default stream + the two side streams
+
+
 def test_full_size_properties(levir_template):
     """At the benchmark size (64 pairs): per-pair independence (bit-exact), batch-permutation equivariance
     (bit-exact), fused uint8 argmax == torch.argmax(logits), finite outputs."""

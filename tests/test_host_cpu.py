@@ -252,3 +252,61 @@ def test_header_is_plain_c_and_mode_macros_match_engine(tmp_path):
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert [int(v) for v in out[:4]] == [E.MODES["tf32x3"], E.MODES["tf32"], E.MODES["f16"], E.MODES["bf16"]]
     assert int(out[4]) == len(E.slot_names())
+
+
+# ---------------------------------------------------------------------------------------------- engine cache hygiene
+def test_prepared_weight_cache_sees_every_in_place_update():
+    """The prepared-weight cache is keyed on the live tensors' version counters: load_state_dict on a PARENT module,
+    in-place copies in eval mode (EMA / SWA), optimizer steps and requires_grad_ toggles + writes all change the key."""
+    import torch
+    from dahitra_b200.networks import BASE_Transformer_UNet
+    net = BASE_Transformer_UNet(3, 2, 'learned', resnet_stages_num=4, with_decoder_pos='learned', enc_depth=1, dec_depth=8).eval()
+    eng = net._engine
+    fp0 = eng._live_fingerprint(net)
+    assert eng._live_fingerprint(net) == fp0                       # stable while nothing changes
+    wrapper = torch.nn.Sequential(net)
+    wrapper.load_state_dict({k: v.clone() for k, v in wrapper.state_dict().items()})
+    fp1 = eng._live_fingerprint(net)
+    assert fp1 != fp0
+    with torch.no_grad():
+        net.classifier.weight.copy_(net.classifier.weight * 0.5)   # EMA-style update in eval mode
+    fp2 = eng._live_fingerprint(net)
+    assert fp2 != fp1
+    opt = torch.optim.SGD([net.classifier.bias], lr=0.1)
+    net.classifier.bias.grad = torch.ones_like(net.classifier.bias)
+    opt.step()
+    assert eng._live_fingerprint(net) != fp2
+    fp3 = eng._live_fingerprint(net)
+    with torch.no_grad():
+        net.resnet.bn1.running_mean.add_(1.0)                      # buffers count too
+    assert eng._live_fingerprint(net) != fp3
+
+
+def test_engine_survives_deepcopy_and_pickle():
+    import copy
+    import ctypes as C
+    import pickle
+    import torch
+    from dahitra_b200.networks import BASE_Transformer_UNet
+    net = BASE_Transformer_UNet(3, 2, 'learned', resnet_stages_num=4, with_decoder_pos='learned', enc_depth=1, dec_depth=8).eval()
+    net.set_mode("tf32")
+    # what the engine holds after a GPU forward: a ctypes pointer table (not picklable by itself)
+    net._engine._preps[("cuda:0", "levir")] = type("P", (), {"table": (C.c_void_p * 3)()})()
+    net._engine._ws[("cuda:0", 0)] = torch.zeros(4)
+    twin = copy.deepcopy(net)
+    assert twin._engine is not net._engine and twin._engine._preps == {} and twin._engine._ws == {}
+    assert twin._engine.mode == "tf32"
+    blob = pickle.dumps(net)
+    back = pickle.loads(blob)
+    assert back._engine._preps == {} and back._engine.mode == "tf32"
+    assert len(back.state_dict()) == 425
+
+
+def test_xbd_variant_without_token_pos_prepares():
+    """reference default with_pos=None (xBD_code/zoo/model_transformer_encoding.py constructor): no pos_embedding_3."""
+    from dahitra_b200.xbd import BASE_Transformer_UNet as X
+    from dahitra_b200.engine import prepare_weights
+    net = X(3, 5, None, with_decoder_pos='learned')
+    assert "pos_embedding_3" not in net.state_dict()
+    P = prepare_weights(net.state_dict(), 1, 5)
+    assert float(P["DH_W_LV5_ENC"][:256].abs().sum()) == 0.0
