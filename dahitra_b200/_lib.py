@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdahitra_b200.so")
-SOURCES = ["conv_ffma.cu", "conv_tc.cu", "conv_tc2.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "aux.cu", "forward.cu"]
+SOURCES = ["conv_ffma.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "split.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "aux.cu", "forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -45,6 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
     cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    if os.environ.get("DAHITRA_DEBUG_BUILD") == "1":      # bounded mbarrier waits that trap + printf instead of hanging
+        cflags.append("-DDH_MBAR_TIMEOUT")
     with tempfile.TemporaryDirectory(prefix="_build_", dir=_HERE) as tmp:            # in-tree scratch (objects are git-ignored)
         def compile_one(src):
             obj = os.path.join(tmp, os.path.basename(src) + ".o")
@@ -91,6 +93,10 @@ SIGNATURES = {
     "dahitra_confusion_matrix": (_I, [_P, _P, _LL, _I, _P, _P]),
     "dahitra_prepare_input_u8": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "dahitra_classifier": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "dahitra_split_pack": (_I, [_P, _LL, _P, _P]),
+    "dahitra_split_unpack": (_I, [_P, _LL, _P, _P]),
+    "dahitra_maxpool3x3s2_split": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "dahitra_conv2d_split": (_I, [_P, _P, _I, _I, _LL, _LL, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _P]),
 }
 
 

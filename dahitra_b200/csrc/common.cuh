@@ -56,6 +56,33 @@ struct ConvArgs {
   // this launch with others (used for the head convolution that runs under the transformer levels on a side stream)
   int flat = 0;
 };
+// conv_tc3.cu: convolution over split16 activations (two FP16 planes hi | lo, see the file header)
+struct Conv3Args {
+  const void* in0; const void* in1; int C0, C1;      // split16 inputs (virtual concat of in0 | in1 along channels)
+  int N, inH, inW;
+  long long in0_plane = 0, in1_plane = 0;            // elements between the hi and lo planes (0: N*inH*inW*C; larger when in0 / in1
+                                                     // are the first / second half of the images of one tensor)
+  long long res_plane = 0, out_plane = 0;            // same for a split16 residual / output (0: N*OH*OW*Cout)
+  int K, stride, Cout;                               // K = 1 or 3 (pad K/2); stride 1 or 2
+  const void* wt16;                                  // FP16 filter planes h_w | l_w, each [Cout][K*K*Cin] (K-major)
+  long long wt_plane_bytes;                          // bytes between the two planes
+  const float* bias; const void* res; int res_split; // residual: fp32 NHWC or split16 (same shape as the output)
+  int relu;
+  void* out; int out_split;                          // fp32 NHWC or split16
+  int ps = 0;                                        // pixel-shuffle store of a 32 -> 4x32 upsample convolution (fp32 output only)
+  int tok = 0;                                       // tokenizer epilogue (1x1, Cout 32): ReLU + store + per-tile softmax partials
+  const float* wtok = nullptr; float* partials = nullptr;
+};
+bool dh_conv_tc3_eligible(const Conv3Args& a);
+int dh_launch_conv_tc3(const Conv3Args& a, cudaStream_t s);
+int dh_conv_tc3_tok_chunks(int H, int W);            // partial-softmax chunks per image the tok epilogue writes
+// split.cu: fp32 NHWC <-> split16 planes, 3x3/s2 max pool on split16
+int dh_launch_split_pack(const float* in, size_t n, void* out, cudaStream_t s);
+int dh_launch_split_unpack(const void* in, size_t n, float* out, cudaStream_t s);
+int dh_launch_maxpool_split(const void* in, int N, int H, int W, int C, void* out, cudaStream_t s);
+// programmatic dependent launch: attribute for cudaLaunchKernelEx (returns the number of attributes written: 0 or 1)
+int dh_pdl_attr(cudaLaunchAttribute* at);
+void dh_set_pdl(int on);
 int dh_launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
 bool dh_conv_tc_eligible(const ConvArgs& a);
 int dh_launch_conv_tc(const ConvArgs& a, cudaStream_t s);
@@ -63,7 +90,7 @@ bool dh_conv_tc2_eligible(const ConvArgs& a);                     // stride-1 ha
 int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s);
 int dh_launch_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* b, float* out, cudaStream_t s);
 int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const float* wtc, const float* b, float* out, int x3,
-                      cudaStream_t s);
+                      cudaStream_t s, long long split_plane_pitch = 0);
 int dh_launch_maxpool(const float* in, int N, int H, int W, int C, float* out, cudaStream_t s);
 int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* b,
                          float* logits, unsigned char* amax, cudaStream_t s);

@@ -1,0 +1,543 @@
+// dahitra_b200 — implicit-GEMM convolution on tcgen05 over PRE-SPLIT activations (the default fp32-grade mode).
+//
+// Storage format "split16" of an activation tensor [N][H][W][C]: two FP16 planes of the same shape,
+//     hi = f16(a)  (round to nearest, saturating),   lo = f16(2^11 (a - hi))            a ~= hi + 2^-11 lo
+// (4 bytes per element like fp32; 22 significant bits while a is in the normal FP16 range, absolute error <= 3e-11 below
+// it).  Every producer epilogue writes this pair, so a consumer's TMA lands MMA operands directly: no fp32 halo, no
+// splitter pass, no conversion warps (conv_tc2.cu pays one shared-memory pass per halo chunk for that).
+// Filters come pre-split the same way: h_w = f16(w), l_w = f16(2^11 (w - h_w))   (planes 3 and 4 of the *_WT slots).
+//
+//   a.w = h_a.h_w + 2^-11 (h_a.l_w + l_a.h_w) + O(2^-22)
+//
+// Per (tap, 32-channel chunk, K = 16 step) two MMAs, all operands FP16, fp32 accumulation in tensor memory:
+//   wide    [h_a] x [h_w ; l_w]   N = 2 NT   -> accumulator columns [0, NT) = main, [NT, 2 NT) = 2^11 x correction
+//   narrow  [l_a] x [h_w]         N = NT     -> added onto columns [NT, 2 NT)      (B = the first NT rows of the wide tile)
+// and the epilogue returns main + 2^-11 corr.  The filter ring therefore carries two 16-bit planes per tap (conv_tc2's
+// folded mode: three), and the halo ring two 16-bit halos per chunk.
+//
+// Geometry as conv_tc2.cu: M tile = 16 x 8 output pixels of one image; per 32-channel chunk the (16+2) x (8+2) halo of
+// each plane is fetched ONCE by a 4-D TMA box {32 ch, 10, 18, 1} (SWIZZLE_64B, zero fill outside the image = the conv
+// padding) and serves all nine taps through shifted-window UMMA descriptors (start + (r*10+s) pixels, SBO = 10 pixels);
+// stride 2 reads the four phase images with TMA element strides; persistent CTAs, two TMEM accumulators.
+// Warp roles: 0 = halo TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue, 6 = filter TMA producer.
+//
+// Epilogue outputs: fp32 NHWC (optionally as the pixel-shuffle scatter of the upsample convolutions) or split16 planes;
+// the residual may be fp32 or split16.  TOK epilogue (1x1 squeeze convolution of the tokenizer, reference
+// models/networks.py:1177-1189, 1273-1280): ReLU, store, and the per-tile online-softmax partials (m, s, t[32]) of the four
+// semantic tokens — what squeeze_tokens_kernel (tokens.cu) computes on CUDA cores in the other modes.
+#include "tc_common.cuh"
+#include <mutex>
+#include <unordered_map>
+
+using namespace dhtc;
+
+namespace {
+
+constexpr int T3_TH = 16, T3_TW = 8;                    // output patch
+constexpr int T3_HW = T3_TW + 2, T3_HH = T3_TH + 2;     // halo 10 x 18
+constexpr uint32_t T3_PLANE = 12288;                    // one 16-bit halo (180 px x 64 B = 11520), 1024-aligned pitch
+constexpr uint32_t T3_HALO = 2 * T3_PLANE;              // hi + lo
+
+struct T3Args {
+  const float* bias;
+  const void* res; void* out;
+  const float* wtok; float* partials;                   // TOK epilogue
+  long long res_plane, out_plane;                       // elements between the hi and lo planes of res / out
+  int OH, OW, Cout, relu, tilesX, tilesY, cchunks0, cchunks, Cin, ps, N, ncout_tiles, ntiles;
+  int res_split, out_split, tok, tiles_per_img;
+  uint32_t halo_plane_bytes;                            // bytes one TMA box delivers (hw * hh * 64)
+};
+
+template <int NT> struct T3Cfg {
+  static constexpr int HB = 4;                                           // halo chunk buffers (hi + lo each)
+  static constexpr int TPS = NT == 128 ? 1 : 3;                          // filter taps per ring stage
+  static constexpr int STAGES = NT == 128 ? 6 : (NT == 64 ? 4 : 8);
+  static constexpr uint32_t B_TAP = 2u * NT * 64u;                       // [h_w (NT rows) ; l_w (NT rows)] x 64 B
+  static constexpr uint32_t B_STAGE = B_TAP * TPS;
+  static constexpr uint32_t HALO_BYTES = HB * T3_HALO;
+  static constexpr uint32_t EPI_OFF = HALO_BYTES + STAGES * B_STAGE;     // epilogue staging: 4 warps x 4 KB
+  static constexpr uint32_t TOK_OFF = EPI_OFF + 4 * 4096;                // TOK: wtok [32][4] + per-warp (m, s, t) 4 x 4 x 34 floats
+  static constexpr uint32_t SMEM = TOK_OFF + 512 + 4 * 4 * 34 * 4 + 1024;
+  static constexpr int THREADS = 224;
+  static constexpr uint32_t IDESC_WIDE = umma_idesc_f16(128, 2 * NT);
+  static constexpr uint32_t IDESC_NARROW = umma_idesc_f16(128, NT);
+  static constexpr int ACC_COLS = 2 * NT;
+  static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+};
+
+template <int KS, int SD> struct Tap3 {                                   // tap order / halo shifts (see conv_tc2.cu TapSched)
+  static constexpr int NPH = (KS == 3 && SD == 2) ? 4 : 1;
+  static constexpr int NTAPS = KS * KS;
+  __host__ __device__ static constexpr int tap(int i) {
+    return (KS == 3 && SD == 2) ? (int)((0x862071534ULL >> (4 * i)) & 0xF) : i;   // stride 2: {4, 3,5, 1,7, 0,2,6,8} grouped by phase
+  }
+  __host__ __device__ static constexpr int first(int ph) {
+    return (KS == 3 && SD == 2) ? (int)((0x95310u >> (4 * ph)) & 0xF) : (ph == 0 ? 0 : NTAPS);
+  }
+  __host__ __device__ static constexpr int shift_px(int t, int halo_w) {
+    return KS == 1 ? 0 : (SD == 2 ? ((t / 3 != 0) ? halo_w : 0) + ((t % 3 != 0) ? 1 : 0) : (t / 3) * halo_w + t % 3);
+  }
+};
+
+struct Tile3 { int n, oy0, ox0, n0; };
+__device__ __forceinline__ Tile3 tile3(int tile, const T3Args& e, int NT) {
+  Tile3 t;
+  const int ct = tile % e.ncout_tiles; tile /= e.ncout_tiles;
+  const int tx = tile % e.tilesX; tile /= e.tilesX;
+  const int ty = tile % e.tilesY;
+  t.n = tile / e.tilesY; t.oy0 = ty * T3_TH; t.ox0 = tx * T3_TW; t.n0 = ct * NT;
+  return t;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// split16 pack / unpack of four values (8 bytes per plane)
+__device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
+  hi.x = pack_f16x2_sat(v.x, v.y); hi.y = pack_f16x2_sat(v.z, v.w);
+  lo.x = pack_f16x2_sat((v.x - f16_lo(hi.x)) * 2048.f, (v.y - f16_hi(hi.x)) * 2048.f);
+  lo.y = pack_f16x2_sat((v.z - f16_lo(hi.y)) * 2048.f, (v.w - f16_hi(hi.y)) * 2048.f);
+}
+__device__ __forceinline__ float4 join4(uint2 hi, uint2 lo) {
+  constexpr float S = 1.0f / 2048.0f;
+  return make_float4(fmaf(f16_lo(lo.x), S, f16_lo(hi.x)), fmaf(f16_hi(lo.x), S, f16_hi(hi.x)),
+                     fmaf(f16_lo(lo.y), S, f16_lo(hi.y)), fmaf(f16_hi(lo.y), S, f16_hi(hi.y)));
+}
+
+template <int NT, int KS, int SD>
+__global__ void __launch_bounds__(T3Cfg<NT>::THREADS, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant__ CUtensorMap tmA0l,
+                const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
+                const __grid_constant__ CUtensorMap tmB, const T3Args e) {
+  using Cfg = T3Cfg<NT>;
+  constexpr int STAGES = Cfg::STAGES, HB = Cfg::HB;
+  extern __shared__ uint8_t t3_raw[];
+  __shared__ __align__(8) uint64_t halo_full[HB], halo_empty[HB], b_full[STAGES], b_empty[STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(t3_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = t3_raw + (base - smem_u32(t3_raw));
+  const uint32_t b_ring = base + Cfg::HALO_BYTES;
+  constexpr int pad = (KS == 3) ? 1 : 0;
+  using Sched = Tap3<KS, SD>;
+  constexpr int NPH = Sched::NPH;
+  constexpr int NTAPS = KS * KS;
+  constexpr int TPS = (SD == 1 && NTAPS % Cfg::TPS == 0) ? Cfg::TPS : 1;
+  constexpr int HALO_W = (KS == 3) ? T3_HW : T3_TW;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < HB; ++i) { mbar_init(smem_u32(&halo_full[i]), 1); mbar_init(smem_u32(&halo_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 128); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0h) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0l) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+  if (e.tok && threadIdx.x >= 64 && threadIdx.x < 96)          // wtok [32][4] -> shared (weights: not produced by the previous launch)
+    reinterpret_cast<float4*>(base_ptr + Cfg::TOK_OFF)[threadIdx.x - 64] = __ldg(reinterpret_cast<const float4*>(e.wtok) + (threadIdx.x - 64));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  // everything above overlaps the tail of the previous launch under programmatic dependent launch; its outputs (this
+  // launch's activations / residual) are only touched below
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {                                            // ---------------- halo TMA producer: hi + lo boxes per chunk
+      int g = 0;
+      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
+        const Tile3 t = tile3(tile, e, NT);
+        for (int cc = 0; cc < e.cchunks; ++cc) {
+#pragma unroll
+          for (int ph = 0; ph < NPH; ++ph, ++g) {
+            const int hb = g % HB, use = g / HB;
+            mbar_wait(smem_u32(&halo_empty[hb]), (uint32_t)((use & 1) ^ 1));
+            const uint32_t bar = smem_u32(&halo_full[hb]);
+            mbar_expect_tx(bar, 2u * e.halo_plane_bytes);
+            const uint32_t dst = base + (uint32_t)hb * T3_HALO;
+            const int cx = SD == 1 ? t.ox0 - pad : 2 * (t.ox0 - pad) + (ph & 1);
+            const int cy = SD == 1 ? t.oy0 - pad : 2 * (t.oy0 - pad) + (ph >> 1);
+            const bool first = cc < e.cchunks0;
+            const int c0 = (first ? cc : cc - e.cchunks0) * 32;
+            tma_load_4d(dst, first ? &tmA0h : &tmA1h, bar, c0, cx, cy, t.n);
+            tma_load_4d(dst + T3_PLANE, first ? &tmA0l : &tmA1l, bar, c0, cx, cy, t.n);
+          }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {                                            // ---------------- filter TMA producer: one 3-D box [2][NT][32] per tap
+      int step = 0;
+      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
+        const Tile3 t = tile3(tile, e, NT);
+        for (int cc = 0; cc < e.cchunks; ++cc) {
+#pragma unroll
+          for (int i0 = 0; i0 < NTAPS; i0 += TPS, ++step) {
+            const int st = step % STAGES, round = step / STAGES;
+            mbar_wait(smem_u32(&b_empty[st]), (uint32_t)((round & 1) ^ 1));
+            const uint32_t bar = smem_u32(&b_full[st]);
+            mbar_expect_tx(bar, (uint32_t)TPS * Cfg::B_TAP);
+#pragma unroll
+            for (int tt = 0; tt < TPS; ++tt)
+              tma_load_3d(b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)tt * Cfg::B_TAP, &tmB, bar,
+                          Sched::tap(i0 + tt) * e.Cin + cc * 32, t.n0, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                            // ---------------- MMA issuer
+      constexpr uint32_t SBO = (uint32_t)HALO_W * 64u;
+      int hb = 0, st = 0, it = 0;
+      uint32_t hphase = 0, bphase = 0;
+      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
+        const int ab = it & 1;
+        mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));    // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + (uint32_t)ab * Cfg::ACC_COLS, d_corr = d_main + NT;
+        for (int cc = 0; cc < e.cchunks; ++cc) {
+#pragma unroll
+          for (int ph = 0; ph < NPH; ++ph) {
+            mbar_wait(smem_u32(&halo_full[hb]), hphase);
+            tc_fence_after();
+            const uint32_t h_hi = base + (uint32_t)hb * T3_HALO, h_lo = h_hi + T3_PLANE;
+#pragma unroll
+            for (int i0 = Sched::first(ph); i0 < Sched::first(ph + 1); i0 += TPS) {
+              mbar_wait(smem_u32(&b_full[st]), bphase);
+              tc_fence_after();
+              const uint32_t b_stage = b_ring + (uint32_t)st * Cfg::B_STAGE;
+#pragma unroll
+              for (int tt = 0; tt < TPS; ++tt) {
+                const int i = i0 + tt;
+                const uint32_t px = (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;      // compile-time after unrolling
+                const uint64_t a_h = umma_desc_sw64(h_hi + px, SBO), a_l = umma_desc_sw64(h_lo + px, SBO);
+                const uint64_t b_w = umma_desc_sw64(b_stage + (uint32_t)tt * Cfg::B_TAP, 512u);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) umma_bf16(d_main, a_h + (uint64_t)(2 * k), b_w + (uint64_t)(2 * k), Cfg::IDESC_WIDE, (cc | i | k) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) umma_bf16(d_corr, a_l + (uint64_t)(2 * k), b_w + (uint64_t)(2 * k), Cfg::IDESC_NARROW, 1u);
+              }
+              umma_commit(smem_u32(&b_empty[st]));
+              if (++st == STAGES) { st = 0; bphase ^= 1u; }
+            }
+            umma_commit(smem_u32(&halo_empty[hb]));
+            if (++hb == HB) { hb = 0; hphase ^= 1u; }
+          }
+        }
+        umma_commit(smem_u32(&acc_full[ab]));
+      }
+    }
+  } else if (warp < 6) {                                        // ---------------- epilogue (warps 2..5)
+    // Thread = accumulator row (pixel).  Every 32-channel slab goes through a per-warp shared-memory transpose so that
+    // the global accesses are 8 lanes per pixel row (whole 128-byte lines for fp32, 64-byte segments per split16 plane).
+    const int q = warp & 3;
+    float* stage = reinterpret_cast<float*>(base_ptr + Cfg::EPI_OFF + (size_t)q * 4096);   // [32 rows][8 chunks ^ (row & 7)][4]
+    const float* wtok_s = reinterpret_cast<const float*>(base_ptr + Cfg::TOK_OFF);        // [32][4]
+    float* tokred = reinterpret_cast<float*>(base_ptr + Cfg::TOK_OFF + 512);              // [4 warps][4 tokens][34]
+    const int c8 = lane & 7, r8 = lane >> 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
+      const Tile3 t = tile3(tile, e, NT);
+      const int ab = it & 1;
+      mbar_wait(smem_u32(&acc_full[ab]), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      size_t rowoff[8];                                          // element offset of (pixel, channel c8*4) for this lane's 8 rows
+      bool ok[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int mm = q * 32 + g * 4 + r8;
+        const int oy = t.oy0 + mm / T3_TW, ox = t.ox0 + mm % T3_TW;
+        ok[g] = (oy < e.OH) && (ox < e.OW);
+        rowoff[g] = e.ps ? ((size_t)(t.n * 2 * e.OH + 2 * oy) * (2 * e.OW) + 2 * ox) * 32 + c8 * 4
+                         : ((size_t)(t.n * e.OH + oy) * e.OW + ox) * e.Cout + t.n0 + c8 * 4;
+      }
+#pragma unroll 1
+      for (int j = 0; j < NT / 32; ++j) {
+        float4 rr[8];                                            // residual reads first: they land under the TMEM load + transpose
+        if (e.res) {
+          if (e.res_split) {
+            const uint2* rh = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(e.res));
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (ok[g]) {
+                const size_t o = rowoff[g] + j * 32;
+                const uint2 h = __ldg(rh + (o >> 2)), l = __ldg(rh + ((o + (size_t)e.res_plane) >> 2));
+                rr[g] = join4(h, l);
+              } else rr[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              rr[g] = ok[g] ? ldg4(reinterpret_cast<const float*>(e.res) + rowoff[g] + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias) bia = ldg4(e.bias + t.n0 + j * 32 + c8 * 4);
+        uint32_t v[32], u[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACC_COLS + j * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACC_COLS + NT + j * 32), u);
+        if (j == NT / 32 - 1) {                                  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive_local(smem_u32(&acc_empty[ab]));
+        }
+        float tl[4] = {0.f, 0.f, 0.f, 0.f};                      // TOK: this pixel's four token logits
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          float x = fmaf(__uint_as_float(u[c]), 1.0f / 2048.0f, __uint_as_float(v[c]));
+          if (e.tok) {                                           // squeeze: no bias, ReLU; logits from the ReLU-ed value
+            x = fmaxf(x, 0.f);
+            const float4 wt = *reinterpret_cast<const float4*>(wtok_s + c * 4);
+            tl[0] = fmaf(x, wt.x, tl[0]); tl[1] = fmaf(x, wt.y, tl[1]); tl[2] = fmaf(x, wt.z, tl[2]); tl[3] = fmaf(x, wt.w, tl[3]);
+          }
+          v[c] = __float_as_uint(x);
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4)
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]), __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int r = g * 4 + r8;
+          float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((c8 ^ (r & 7)) << 2));
+          o.x += bia.x; o.y += bia.y; o.z += bia.z; o.w += bia.w;
+          if (e.res) { o.x += rr[g].x; o.y += rr[g].y; o.z += rr[g].z; o.w += rr[g].w; }
+          if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (!ok[g]) continue;
+          if (e.out_split) {
+            uint2 h, l;
+            split4(o, h, l);
+            uint2* oh = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(e.out));
+            const size_t off = rowoff[g] + j * 32;
+            oh[off >> 2] = h;
+            oh[(off + (size_t)e.out_plane) >> 2] = l;
+          } else {
+            // pixel-shuffle store: slab j = (dy, dx) lands on output pixel (2oy + dy, 2ox + dx), 32 channels each
+            float* ob = reinterpret_cast<float*>(e.out);
+            float* op = e.ps ? ob + rowoff[g] + ((size_t)(j >> 1) * (2 * e.OW) + (j & 1)) * 32 : ob + rowoff[g] + j * 32;
+            st4(op, o);
+          }
+        }
+        if (e.tok) {
+          // per-warp online-softmax partials over this warp's 32 pixels (rows still in `stage`), then merged per tile:
+          //   m_l = max_p a_pl ; s_l = sum_p exp(a_pl - m_l) ; t_l[c] = sum_p exp(a_pl - m_l) xs_p[c]
+          const int mm = q * 32 + lane;
+          const bool valid = (t.oy0 + mm / T3_TW < e.OH) && (t.ox0 + mm % T3_TW < e.OW);
+          float ew[4];
+#pragma unroll
+          for (int l = 0; l < 4; ++l) {
+            const float a = valid ? tl[l] : -INFINITY;
+            const float mx = warp_max(a);
+            ew[l] = valid ? expf(a - mx) : 0.f;
+            const float sw = warp_sum(ew[l]);
+            if (lane == 0) { tokred[(q * 4 + l) * 34] = mx; tokred[(q * 4 + l) * 34 + 1] = sw; }
+          }
+          // lane = channel: t_l[c] = sum over the 32 rows; e of row r is fetched with a shuffle
+          float ts[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const float xv = stage[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) ts[l] = fmaf(__shfl_sync(0xffffffffu, ew[l], r), xv, ts[l]);
+          }
+#pragma unroll
+          for (int l = 0; l < 4; ++l) tokred[(q * 4 + l) * 34 + 2 + lane] = ts[l];
+          asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+          // warp q merges token l = q across the four warps and writes the tile's partial
+          {
+            const int l = q;
+            float m4[4], M = -INFINITY;
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) { m4[w4] = tokred[(w4 * 4 + l) * 34]; M = fmaxf(M, m4[w4]); }
+            float S = 0.f, T = 0.f;
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) {
+              const float sc = (m4[w4] == -INFINITY) ? 0.f : expf(m4[w4] - M);
+              S = fmaf(tokred[(w4 * 4 + l) * 34 + 1], sc, S);
+              T = fmaf(tokred[(w4 * 4 + l) * 34 + 2 + lane], sc, T);
+            }
+            const int tile_in_img = (tile / e.ncout_tiles) % e.tiles_per_img;
+            float* pp = e.partials + (((size_t)t.n * e.tiles_per_img + tile_in_img) * 4 + l) * 34;
+            if (lane == 0) { pp[0] = M; pp[1] = S; }
+            pp[2 + lane] = T;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");          // tokred is free for the next tile
+        }
+        __syncwarp();                                            // the staging rows are free for the next slab
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn3 get_encode3() {
+  static EncodeTiledFn3 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn3)p;
+  });
+  return fn;
+}
+struct Key3 {
+  const void* ptr; long long d[5];
+  bool operator==(const Key3& o) const { return ptr == o.ptr && d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2] && d[3] == o.d[3] && d[4] == o.d[4]; }
+};
+struct Key3Hash {
+  size_t operator()(const Key3& k) const {
+    size_t h = (size_t)k.ptr;
+    for (long long v : k.d) h = h * 1000003u ^ (size_t)v;
+    return h;
+  }
+};
+std::mutex g_mu3;
+std::unordered_map<Key3, CUtensorMap, Key3Hash> g_maps3;
+
+// FP16 activation plane [N][H][W][C] read in {32 ch, bw, bh, 1} boxes (es = element stride along W and H), SWIZZLE_64B
+int act_map(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int bw, int bh, int es) {
+  Key3 key{ptr, {C, W, H, ((long long)N << 8) | es, ((long long)bw << 16) | bh}};
+  {
+    std::lock_guard<std::mutex> lk(g_mu3);
+    auto it = g_maps3.find(key);
+    if (it != g_maps3.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn3 enc = get_encode3();
+  if (!enc) return DH_E_VARIANT;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * W * 2, (cuuint64_t)C * W * H * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return DH_E_SHAPE;
+  {
+    std::lock_guard<std::mutex> lk(g_mu3);
+    if (g_maps3.size() > 4096) g_maps3.clear();
+    g_maps3[key] = m;
+  }
+  *out = m;
+  return 0;
+}
+// filter planes h_w / l_w: [2][Cout][K] FP16 with `plane_bytes` between the planes, read in {32 k, NT rows, 2 planes} boxes
+int filt_map(CUtensorMap* out, const void* ptr, int K, int Cout, long long plane_bytes, int NT) {
+  Key3 key{ptr, {K, Cout, plane_bytes, NT, -3}};
+  {
+    std::lock_guard<std::mutex> lk(g_mu3);
+    auto it = g_maps3.find(key);
+    if (it != g_maps3.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn3 enc = get_encode3();
+  if (!enc) return DH_E_VARIANT;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)plane_bytes};
+  cuuint32_t box[3] = {32, (cuuint32_t)NT, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return DH_E_SHAPE;
+  {
+    std::lock_guard<std::mutex> lk(g_mu3);
+    g_maps3[key] = m;
+  }
+  *out = m;
+  return 0;
+}
+
+template <int NT, int KS, int SD>
+int launch3k(const CUtensorMap* A, const CUtensorMap& Bm, const T3Args& e, dim3 grid, cudaStream_t s) {
+  using Cfg = T3Cfg<NT>;
+  auto kern = conv_tc3_kernel<NT, KS, SD>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if (err != cudaSuccess) return (int)err;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(Cfg::THREADS, 1, 1); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  cfg.attrs = at; cfg.numAttrs = dh_pdl_attr(at);
+  err = cudaLaunchKernelEx(&cfg, kern, A[0], A[1], A[2], A[3], Bm, e);
+  if (err != cudaSuccess) return (int)err;
+  DH_CHECK_LAUNCH();
+  return 0;
+}
+template <int NT>
+int launch3(const CUtensorMap* A, const CUtensorMap& Bm, const T3Args& e, int ks, int stride, dim3 grid, cudaStream_t s) {
+  if (stride == 2) return ks == 3 ? launch3k<NT, 3, 2>(A, Bm, e, grid, s) : launch3k<NT, 1, 2>(A, Bm, e, grid, s);
+  return ks == 3 ? launch3k<NT, 3, 1>(A, Bm, e, grid, s) : launch3k<NT, 1, 1>(A, Bm, e, grid, s);
+}
+}  // namespace
+
+bool dh_conv_tc3_eligible(const Conv3Args& a) {
+  const bool base = a.in0 && a.wt16 && a.out && (a.stride == 1 || (a.stride == 2 && a.inH % 2 == 0 && a.inW % 2 == 0 && !a.ps)) &&
+                    (a.K == 1 || a.K == 3) && a.C0 > 0 && a.C0 % 32 == 0 && a.C1 % 32 == 0 && (a.C1 == 0 || a.in1) &&
+                    (a.Cout == 32 || a.Cout == 64 || a.Cout == 128 || a.Cout == 256) && a.inH >= 1 && a.inW >= 1 && a.N >= 1;
+  if (!base) return false;
+  if (a.ps) return a.Cout == 128 && a.res == nullptr && !a.out_split && a.K == 3;
+  if (a.tok) return a.Cout == 32 && a.K == 1 && a.stride == 1 && a.wtok && a.partials && !a.res && !a.bias;
+  return true;
+}
+
+int dh_conv_tc3_tok_chunks(int H, int W) { return dh_cdiv(H, T3_TH) * dh_cdiv(W, T3_TW); }
+
+int dh_launch_conv_tc3(const Conv3Args& a, cudaStream_t s) {
+  DH_REQUIRE(dh_conv_tc3_eligible(a), DH_E_SHAPE);
+  DH_REQUIRE(dh_aligned16(a.in0) && dh_aligned16(a.in1) && dh_aligned16(a.wt16) && dh_aligned16(a.out) &&
+             dh_aligned16(a.bias) && dh_aligned16(a.res) && dh_aligned16(a.wtok), DH_E_ALIGN);
+  const int Cin = a.C0 + a.C1, K = a.K * a.K * Cin;
+  const int NT = a.Cout >= 128 ? 128 : a.Cout;
+  const int hw = (a.K == 3) ? T3_HW : T3_TW, hh = (a.K == 3) ? T3_HH : T3_TH;
+  CUtensorMap A[4], Bm;
+  const size_t plane0 = a.in0_plane ? (size_t)a.in0_plane : (size_t)a.N * a.inH * a.inW * a.C0;
+  const size_t plane1 = a.in1_plane ? (size_t)a.in1_plane : (size_t)a.N * a.inH * a.inW * a.C1;
+  int rc = act_map(&A[0], a.in0, a.C0, a.inW, a.inH, a.N, hw, hh, a.stride);
+  if (!rc) rc = act_map(&A[1], reinterpret_cast<const uint16_t*>(a.in0) + plane0, a.C0, a.inW, a.inH, a.N, hw, hh, a.stride);
+  if (rc) return rc;
+  if (a.C1) {
+    rc = act_map(&A[2], a.in1, a.C1, a.inW, a.inH, a.N, hw, hh, a.stride);
+    if (!rc) rc = act_map(&A[3], reinterpret_cast<const uint16_t*>(a.in1) + plane1, a.C1, a.inW, a.inH, a.N, hw, hh, a.stride);
+    if (rc) return rc;
+  } else { A[2] = A[0]; A[3] = A[1]; }
+  rc = filt_map(&Bm, a.wt16, K, a.Cout, a.wt_plane_bytes, NT);
+  if (rc) return rc;
+  T3Args e;
+  e.bias = a.bias; e.res = a.res; e.out = a.out; e.wtok = a.wtok; e.partials = a.partials;
+  e.OH = a.inH / a.stride; e.OW = a.inW / a.stride; e.Cout = a.Cout; e.relu = a.relu;
+  e.tilesX = dh_cdiv(e.OW, T3_TW); e.tilesY = dh_cdiv(e.OH, T3_TH);
+  e.cchunks0 = a.C0 / 32; e.cchunks = Cin / 32; e.Cin = Cin; e.ps = a.ps; e.N = a.N;
+  e.ncout_tiles = a.Cout / NT;
+  e.tiles_per_img = e.tilesX * e.tilesY;
+  e.ntiles = e.tiles_per_img * a.N * e.ncout_tiles;
+  e.res_split = a.res_split; e.out_split = a.out_split; e.tok = a.tok;
+  e.res_plane = a.res_plane ? a.res_plane : (long long)a.N * e.OH * e.OW * a.Cout;
+  e.out_plane = a.out_plane ? a.out_plane : (long long)a.N * e.OH * e.OW * a.Cout;
+  e.halo_plane_bytes = (uint32_t)(hw * hh * 64);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);            // persistent: one CTA per SM
+  switch (NT) {
+    case 128: return launch3<128>(A, Bm, e, a.K, a.stride, grid, s);
+    case 64: return launch3<64>(A, Bm, e, a.K, a.stride, grid, s);
+    default: return launch3<32>(A, Bm, e, a.K, a.stride, grid, s);
+  }
+}

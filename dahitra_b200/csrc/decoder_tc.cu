@@ -153,7 +153,7 @@ template <int HEADS, bool X3>
 __global__ void __launch_bounds__(PDT_ROWS * PdtCfg<X3>::G, 1)
 pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ pos, const float* __restrict__ tables,
                         const float* __restrict__ pack, int npix, int w, int depth, const float* __restrict__ skip,
-                        int skip_up, float* __restrict__ out) {
+                        int skip_up, float* __restrict__ out, long long out_split_plane) {
   using Cfg = PdtCfg<X3>;
   constexpr int H4 = HEADS * 4;
   constexpr uint32_t IDESC_S = umma_idesc_tf32(128, H4);
@@ -407,7 +407,18 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
         const float4 v = ldg4(sp + c8 * 4);
         o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
       }
-      st4(out + ((size_t)img * npix + pr) * 32 + c8 * 4, o);
+      const size_t off = ((size_t)img * npix + pr) * 32 + c8 * 4;
+      if (out_split_plane) {             // split16 planes for conv_tc3.cu: hi = f16(o), lo = f16(2^11 (o - hi))
+        uint2 hi, lo;
+        hi.x = pack_f16x2_sat(o.x, o.y); hi.y = pack_f16x2_sat(o.z, o.w);
+        lo.x = pack_f16x2_sat((o.x - f16_lo(hi.x)) * 2048.f, (o.y - f16_hi(hi.x)) * 2048.f);
+        lo.y = pack_f16x2_sat((o.z - f16_lo(hi.y)) * 2048.f, (o.w - f16_hi(hi.y)) * 2048.f);
+        uint2* o16 = reinterpret_cast<uint2*>(out);
+        o16[off >> 2] = hi;
+        o16[(off + (size_t)out_split_plane) >> 2] = lo;
+      } else {
+        st4(out + off, o);
+      }
     }
   }
   tc_fence_before();
@@ -420,11 +431,11 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
 
 template <int HEADS, bool X3>
 int launch_pdt(dim3 grid, const float* x, const float* pos, const float* tables, const float* pack, int npix, int w, int depth,
-               const float* skip, int skip_up, float* out, cudaStream_t s) {
+               const float* skip, int skip_up, float* out, long long osp, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(pixel_decoder_tc_kernel<HEADS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)PdtCfg<X3>::SMEM);
   if (e != cudaSuccess) return (int)e;
-  pixel_decoder_tc_kernel<HEADS, X3><<<grid, PDT_ROWS * PdtCfg<X3>::G, PdtCfg<X3>::SMEM, s>>>(x, pos, tables, pack, npix, w, depth, skip, skip_up, out);
+  pixel_decoder_tc_kernel<HEADS, X3><<<grid, PDT_ROWS * PdtCfg<X3>::G, PdtCfg<X3>::SMEM, s>>>(x, pos, tables, pack, npix, w, depth, skip, skip_up, out, osp);
   DH_CHECK_LAUNCH();
   return 0;
 }
@@ -444,9 +455,12 @@ int dh_launch_decoder_tables_tc(const float* mem, int B, int first_call, int nca
   return 0;
 }
 
+// x3: bit 0 = error-compensated 3xTF32; bit 8 (x3 | 256): `out` receives split16 planes (conv_tc3.cu's input format)
 int dh_launch_pixel_decoder_tc(const float* x, const float* pos, const float* tables, const float* pack, int nimg, int h,
                                int w, int heads, int depth, const float* skip, int skip_up, int x3, float* out,
                                cudaStream_t s) {
+  const long long osp = (x3 & 256) ? (long long)nimg * h * w * 32 : 0;
+  x3 &= 1;
   DH_REQUIRE(x && tables && pack && out, DH_E_NULL);
   DH_REQUIRE(nimg > 0 && h > 0 && w > 0 && depth >= 1 && (heads == 4 || heads == 8), DH_E_SHAPE);
   DH_REQUIRE(!skip || skip_up == 1 || (skip_up == 2 && h % 2 == 0 && w % 2 == 0), DH_E_SHAPE);
@@ -455,8 +469,8 @@ int dh_launch_pixel_decoder_tc(const float* x, const float* pos, const float* ta
   const int npix = h * w;
   dim3 grid(dh_cdiv(npix, PDT_ROWS * PdtCfg<true>::G), nimg);
   if (heads == 4)
-    return x3 ? launch_pdt<4, true>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, s)
-              : launch_pdt<4, false>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, s);
-  return x3 ? launch_pdt<8, true>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, s)
-            : launch_pdt<8, false>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, s);
+    return x3 ? launch_pdt<4, true>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, osp, s)
+              : launch_pdt<4, false>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, osp, s);
+  return x3 ? launch_pdt<8, true>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, osp, s)
+            : launch_pdt<8, false>(grid, x, pos, tables, pack, npix, w, depth, skip, skip_up, out, osp, s);
 }

@@ -10,7 +10,7 @@ namespace {
 struct Level {           // per transformer level (5, 4, 3)
   int cin, heads, depth, h, w;
   size_t xs, xd, dx, out, part, mem, tab;    // float offsets into the workspace
-  int nchunk;
+  int nchunk, nchunk3;
 };
 
 struct Plan {
@@ -48,12 +48,13 @@ bool make_plan(Plan& p, int variant, int B, int H, int W, int nc) {
     Level& L = p.lv[i];
     L.cin = cins[i]; L.heads = heads[i]; L.depth = depths[i]; L.h = H / div[i]; L.w = W / div[i];
     const size_t n = (size_t)L.h * L.w;
-    L.nchunk = (int)((n + 255) / 256);
+    L.nchunk = (int)((n + 255) / 256);                           // squeeze_tokens_kernel: one partial per 256 pixels
+    L.nchunk3 = dh_conv_tc3_tok_chunks(L.h, L.w);                // conv_tc3 tok epilogue: one per 16 x 8 tile
     L.xs = b.take(N2 * n * 32);
     L.xd = b.take(N2 * n * 32);
     L.dx = b.take((size_t)B * n * 32);
     L.out = b.take((size_t)B * n * 32);
-    L.part = b.take(N2 * L.nchunk * 4 * 34);
+    L.part = b.take(N2 * (size_t)(L.nchunk3 > L.nchunk ? L.nchunk3 : L.nchunk) * 4 * 34);
     L.mem = b.take((size_t)B * 3 * 128);
     L.tab = b.take((size_t)3 * B * L.depth * (DH_TAB_FLOATS(L.heads) > DH_TABTC_FLOATS ? DH_TAB_FLOATS(L.heads) : DH_TABTC_FLOATS));
   }
@@ -85,7 +86,8 @@ const char* kSlotNames[DH_W_COUNT] = {
   "DH_W_LV5_DECODE_WT", "DH_W_LV4_DECODE_WT", "DH_W_LV3_DECODE_WT", "DH_W_CL20A_WT", "DH_W_CL20B_WT",
   "DH_W_L2_0_C1_WT", "DH_W_L2_0_DS_WT",
   "DH_W_CL4_PSWT", "DH_W_CL4_PSB", "DH_W_CL3_PSWT", "DH_W_CL3_PSB", "DH_W_CL2_PSWT", "DH_W_CL2_PSB",
-  "DH_W_LV5_DECTC", "DH_W_LV4_DECTC", "DH_W_LV3_DECTC", "DH_W_STEM_WTC"};
+  "DH_W_LV5_DECTC", "DH_W_LV4_DECTC", "DH_W_LV3_DECTC", "DH_W_STEM_WTC",
+  "DH_W_LV5_SQ_WT", "DH_W_LV4_SQ_WT", "DH_W_LV3_SQ_WT"};
 
 // filter slot -> slot of its K-major copy (or -1)
 int wt_slot_of(int wslot) {
@@ -205,9 +207,45 @@ extern "C" int dahitra_pixel_decoder_tc(const float* x, const float* pos, const 
   return dh_launch_pixel_decoder_tc(x, pos, tables, dectc_pack, nimg, h, w, heads, depth, skip, skip_up, x3, out,
                                     (cudaStream_t)stream);
 }
+extern "C" int dahitra_split_pack(const float* in, long long n, void* out, void* stream) {
+  return dh_launch_split_pack(in, (size_t)n, out, (cudaStream_t)stream);
+}
+extern "C" int dahitra_split_unpack(const void* in, long long n, float* out, void* stream) {
+  return dh_launch_split_unpack(in, (size_t)n, out, (cudaStream_t)stream);
+}
+extern "C" int dahitra_maxpool3x3s2_split(const void* in, int N, int H, int W, int C, void* out, void* stream) {
+  return dh_launch_maxpool_split(in, N, H, W, C, out, (cudaStream_t)stream);
+}
+extern "C" int dahitra_conv2d_split(const void* in0, const void* in1, int C0, int C1, long long in0_plane, long long in1_plane,
+                                    int N, int inH, int inW, int K, int stride, int Cout, const float* wt, const float* bias,
+                                    const void* res, int res_split, int relu, void* out, int out_split, int mode,
+                                    const float* w_tok, float* partials, void* stream) {
+  DH_REQUIRE(wt, DH_E_NULL);
+  DH_REQUIRE(mode >= 0 && mode <= 2, DH_E_VARIANT);
+  Conv3Args a{};
+  a.in0 = in0; a.in1 = in1; a.C0 = C0; a.C1 = C1; a.N = N; a.inH = inH; a.inW = inW; a.in0_plane = in0_plane; a.in1_plane = in1_plane;
+  a.K = K; a.stride = stride; a.Cout = Cout;
+  const size_t plane = (size_t)Cout * K * K * (C0 + C1);            // floats per plane of the *_WT slot
+  a.wt16 = wt + 3 * plane; a.wt_plane_bytes = (long long)plane * 4;
+  a.bias = bias; a.res = res; a.res_split = res_split; a.relu = relu; a.out = out; a.out_split = out_split;
+  a.ps = mode == 1; a.tok = mode == 2; a.wtok = w_tok; a.partials = partials;
+  return dh_launch_conv_tc3(a, (cudaStream_t)stream);
+}
 extern "C" int dahitra_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* bias,
                                   float* logits, unsigned char* argmax_u8, void* stream) {
   return dh_launch_classifier(in, N, H, W, nc, w, bias, logits, argmax_u8, (cudaStream_t)stream);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// programmatic dependent launch switch (per host thread; set by dahitra_forward from DH_FLAG_PDL for its own launches)
+// ----------------------------------------------------------------------------------------------------
+namespace { thread_local int g_pdl = 0; }
+void dh_set_pdl(int on) { g_pdl = on; }
+int dh_pdl_attr(cudaLaunchAttribute* at) {
+  if (!g_pdl) return 0;
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  return 1;
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -278,6 +316,179 @@ AuxStreams* aux_streams() {
     prof_mark(s, name, (fl), (by));        \
   } while (0)
 
+// ----------------------------------------------------------------------------------------------------
+// Whole forward on split16 activations (DH_FLAG_ACT_SPLIT, the default fp32-grade mode).  Same launch order and the same
+// reference semantics as the fp32-storage path below; what differs is the storage format of every tensor a convolution
+// reads (two FP16 planes hi | lo in the buffer an fp32 tensor of that shape would occupy — the workspace plan is shared)
+// and the kernels: conv_tc3 for every convolution including the tokenizer's 1x1 squeeze, the split16 max pool, and the
+// stem / pixel decoder writing split16 where a convolution consumes their output.
+//   split16: F2, P2, T4*, F4, T8*, F8, P8, T16*, F16, Y20, O2, decoder outputs read by a conv (XD; OUT of levels 4, 3),
+//            XS in the xBD variant (read by conv_decode)
+//   fp32:    XS (LEVIR: read by the decoder), DX, OUT of level 5 (a decoder skip), C4, C3, C2, logits
+// ----------------------------------------------------------------------------------------------------
+namespace {
+int forward_split(const Plan& p, const void* const* weights, const float* x1, const float* x2, long long x_batch_stride,
+                  float* logits, unsigned char* argmax_u8, float* ws, int variant, int B, int H, int W, int output_nc, int flags,
+                  cudaStream_t s_main) {
+  cudaStream_t s = s_main;
+  auto Wt = [&](int slot) { return (const float*)weights[slot]; };
+  const int N2 = 2 * B;
+  const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8, h16 = H / 16, w16 = W / 16;
+  // conv over split16 inputs.  wts: the filter's *_WT (or _PSWT) slot; in_plane: elements between the hi / lo planes of in0 / in1
+  auto conv3 = [&](const char* name, const float* in0, const float* in1, int C0, int C1, long long in_plane, int N, int inH, int inW,
+                   int K, int stride, int Cout, int wts, int bslot, const float* res, int res_split, int relu, float* out,
+                   int out_split, int ps) -> int {
+    Conv3Args a{};
+    a.in0 = in0; a.in1 = in1; a.C0 = C0; a.C1 = C1; a.N = N; a.inH = inH; a.inW = inW; a.in0_plane = in_plane; a.in1_plane = in_plane;
+    a.K = K; a.stride = stride; a.Cout = Cout;
+    const size_t plane = (size_t)Cout * K * K * (C0 + C1);
+    a.wt16 = Wt(wts) + 3 * plane; a.wt_plane_bytes = (long long)plane * 4;
+    a.bias = bslot >= 0 ? Wt(bslot) : nullptr; a.res = res; a.res_split = res_split; a.relu = relu; a.out = out; a.out_split = out_split;
+    a.ps = ps;
+    const int rc = dh_launch_conv_tc3(a, s);
+    if (rc != 0) return rc;
+    const double OH = (double)inH / stride, OW = (double)inW / stride, Cin = C0 + C1;
+    const double cout_alg = ps ? 32.0 : Cout, up = ps ? 2.0 : 1.0;       // as written: a 3x3 conv 32 -> 32 on the upsampled map
+    const double fl = 2.0 * N * OH * up * OW * up * cout_alg * K * K * Cin;
+    const double by = 4.0 * ((double)N * inH * inW * Cin + (double)N * OH * up * OW * up * cout_alg * (res ? 2 : 1) + (double)K * K * Cin * cout_alg);
+    prof_mark(s, name, fl, by);
+    return 0;
+  };
+#define DH_CONV3(...)                     \
+  do {                                    \
+    const int rc__ = conv3(__VA_ARGS__);  \
+    if (rc__ != 0) return rc__;           \
+  } while (0)
+
+  // ---- Siamese trunk on 2B images: [pre batch | post batch]  (reference networks.py:1118-1138, 1323-1324)
+  // F2 is ONE split16 tensor of 2B images; the stem runs once per image set and writes its half of both planes.
+  auto H16 = [](float* p) { return reinterpret_cast<uint16_t*>(p); };
+  float* F2 = ws + p.f2;
+  const size_t f2_half = (size_t)B * h2 * w2 * 64;
+  const long long f2_plane = (long long)N2 * h2 * w2 * 64;
+  float* F2post = reinterpret_cast<float*>(H16(F2) + f2_half);             // hi plane of the post images
+  const double stem_fl = 2.0 * B * h2 * w2 * 64 * 147, stem_by = 4.0 * B * ((double)3 * H * W + (double)h2 * w2 * 64);
+  const int stem_mode = ((flags & DH_FLAG_TC_3XTF32) ? 2 : 3) | 256;
+  DH_STEP("stem_pre", stem_fl, stem_by, dh_launch_stem_tc(x1, x_batch_stride, B, H, W, Wt(DH_W_STEM_WTC), Wt(DH_W_STEM_B), F2, stem_mode, s, f2_plane));
+  DH_STEP("stem_post", stem_fl, stem_by, dh_launch_stem_tc(x2, x_batch_stride, B, H, W, Wt(DH_W_STEM_WTC), Wt(DH_W_STEM_B), F2post, stem_mode, s, f2_plane));
+  float* P2 = ws + p.p2;
+  DH_STEP("maxpool_2", 0.0, 4.0 * N2 * 64 * ((double)h2 * w2 + (double)h4 * w4), dh_launch_maxpool_split(F2, N2, h2, w2, 64, P2, s));
+  float *T4a = ws + p.t4a, *T4b = ws + p.t4b, *F4 = ws + p.f4;
+  DH_CONV3("layer1.0.conv1", P2, nullptr, 64, 0, 0, N2, h4, w4, 3, 1, 64, DH_W_L1_0_C1_WT, DH_W_L1_0_C1_B, nullptr, 0, 1, T4a, 1, 0);
+  DH_CONV3("layer1.0.conv2", T4a, nullptr, 64, 0, 0, N2, h4, w4, 3, 1, 64, DH_W_L1_0_C2_WT, DH_W_L1_0_C2_B, P2, 1, 1, T4b, 1, 0);
+  DH_CONV3("layer1.1.conv1", T4b, nullptr, 64, 0, 0, N2, h4, w4, 3, 1, 64, DH_W_L1_1_C1_WT, DH_W_L1_1_C1_B, nullptr, 0, 1, T4a, 1, 0);
+  DH_CONV3("layer1.1.conv2", T4a, nullptr, 64, 0, 0, N2, h4, w4, 3, 1, 64, DH_W_L1_1_C2_WT, DH_W_L1_1_C2_B, T4b, 1, 1, F4, 1, 0);
+  float *T8a = ws + p.t8a, *T8b = ws + p.t8b, *T8c = ws + p.t8c, *F8 = ws + p.f8;
+  DH_CONV3("layer2.0.conv1", F4, nullptr, 64, 0, 0, N2, h4, w4, 3, 2, 128, DH_W_L2_0_C1_WT, DH_W_L2_0_C1_B, nullptr, 0, 1, T8a, 1, 0);
+  DH_CONV3("layer2.0.down", F4, nullptr, 64, 0, 0, N2, h4, w4, 1, 2, 128, DH_W_L2_0_DS_WT, DH_W_L2_0_DS_B, nullptr, 0, 0, T8b, 1, 0);
+  DH_CONV3("layer2.0.conv2", T8a, nullptr, 128, 0, 0, N2, h8, w8, 3, 1, 128, DH_W_L2_0_C2_WT, DH_W_L2_0_C2_B, T8b, 1, 1, T8c, 1, 0);
+  DH_CONV3("layer2.1.conv1", T8c, nullptr, 128, 0, 0, N2, h8, w8, 3, 1, 128, DH_W_L2_1_C1_WT, DH_W_L2_1_C1_B, nullptr, 0, 1, T8a, 1, 0);
+  DH_CONV3("layer2.1.conv2", T8a, nullptr, 128, 0, 0, N2, h8, w8, 3, 1, 128, DH_W_L2_1_C2_WT, DH_W_L2_1_C2_B, T8c, 1, 1, F8, 1, 0);
+  float* P8 = ws + p.p8;
+  DH_STEP("maxpool_8", 0.0, 4.0 * N2 * 128 * ((double)h8 * w8 + (double)h16 * w16), dh_launch_maxpool_split(F8, N2, h8, w8, 128, P8, s));
+  float *T16a = ws + p.t16a, *T16b = ws + p.t16b, *T16c = ws + p.t16c, *F16 = ws + p.f16;
+  DH_CONV3("layer3.0.conv1", P8, nullptr, 128, 0, 0, N2, h16, w16, 3, 1, 256, DH_W_L3_0_C1_WT, DH_W_L3_0_C1_B, nullptr, 0, 1, T16a, 1, 0);
+  DH_CONV3("layer3.0.down", P8, nullptr, 128, 0, 0, N2, h16, w16, 1, 1, 256, DH_W_L3_0_DS_WT, DH_W_L3_0_DS_B, nullptr, 0, 0, T16b, 1, 0);
+  DH_CONV3("layer3.0.conv2", T16a, nullptr, 256, 0, 0, N2, h16, w16, 3, 1, 256, DH_W_L3_0_C2_WT, DH_W_L3_0_C2_B, T16b, 1, 1, T16c, 1, 0);
+  DH_CONV3("layer3.1.conv1", T16c, nullptr, 256, 0, 0, N2, h16, w16, 3, 1, 256, DH_W_L3_1_C1_WT, DH_W_L3_1_C1_B, nullptr, 0, 1, T16a, 1, 0);
+  DH_CONV3("layer3.1.conv2", T16a, nullptr, 256, 0, 0, N2, h16, w16, 3, 1, 256, DH_W_L3_1_C2_WT, DH_W_L3_1_C2_B, T16c, 1, 1, F16, 1, 0);
+
+  // ---- transformer levels 5, 4, 3  (reference networks.py:1297-1318; xBD: model_transformer_encoding.py:385-406)
+  float* feats[3] = {F16, F8, F4};
+  const int base[3] = {DH_W_LV5_SQ, DH_W_LV4_SQ, DH_W_LV3_SQ};
+  static const char* const nm[3][7] = {
+      {"squeeze_tok_5", "token_enc_5", "dec_tables_5", "decoder_5_x12", "conv_decode_5", "decoder_5_diff", "conv_layer4"},
+      {"squeeze_tok_4", "token_enc_4", "dec_tables_4", "decoder_4_x12", "conv_decode_4", "decoder_4_diff", "conv_layer4"},
+      {"squeeze_tok_3", "token_enc_3", "dec_tables_3", "decoder_3_x12", "conv_decode_3", "decoder_3_diff", "conv_layer4"}};
+  float* C4 = ws + p.c4;
+  const int x3 = (flags & DH_FLAG_DEC_TC_X3) ? 1 : 0;
+  auto level_pre = [&](int i) -> int {
+    const Level& L = p.lv[i];
+    const int npix = L.h * L.w;
+    const float *wtok = Wt(base[i] + 1), *enc = Wt(base[i] + 2), *dec = Wt(base[i] + 3), *pos = Wt(base[i] + 4);
+    float *XS = ws + L.xs, *XD = ws + L.xd, *DX = ws + L.dx, *PART = ws + L.part, *MEM = ws + L.mem, *TAB = ws + L.tab;
+    const double inner = 64.0 * L.heads;
+    const double dec_fl_px = L.depth * 2.0 * (32 * inner + 4 * inner + 4 * inner + inner * 32 + 2 * 32 * 32);
+    const double dec_by_px = 4.0 * 32 * (pos ? 3 : 2);
+    const bool levir = variant == DH_VARIANT_LEVIR;
+    {   // squeeze 1x1 + ReLU + tokenizer partials on the tensor cores; xs fp32 for the decoder (LEVIR) / split16 for conv_decode (xBD)
+      Conv3Args a{};
+      a.in0 = feats[i]; a.C0 = L.cin; a.N = N2; a.inH = L.h; a.inW = L.w; a.K = 1; a.stride = 1; a.Cout = 32;
+      const size_t plane = (size_t)32 * L.cin;
+      a.wt16 = Wt(DH_W_LV5_SQ_WT + i) + 3 * plane; a.wt_plane_bytes = (long long)plane * 4;
+      a.out = XS; a.out_split = levir ? 0 : 1; a.tok = 1; a.wtok = wtok; a.partials = PART;
+      DH_STEP(nm[i][0], 2.0 * N2 * npix * 32 * (L.cin + 4 + 4), 4.0 * N2 * npix * (L.cin + 32.0), dh_launch_conv_tc3(a, s));
+    }
+    const int add_tok_pos = levir ? 1 : (i == 0 ? 1 : 0);
+    DH_STEP(nm[i][1], 0.0, 4.0 * N2 * L.nchunk3 * 136.0, dh_launch_token_encoder(PART, B, L.nchunk3, enc, L.heads, add_tok_pos, MEM, s));
+    const size_t half = (size_t)B * npix * 32;
+    const long long plane2 = (long long)N2 * npix * 32;
+    const float* dectc = Wt(DH_W_LV5_DECTC + i);
+    if (levir) {
+      DH_STEP(nm[i][2], 0.0, 4.0 * 3 * B * L.depth * (double)DH_TABTC_FLOATS, dh_launch_decoder_tables_tc(MEM, B, 0, 3, dec, L.heads, L.depth, TAB, s));
+      DH_STEP(nm[i][3], dec_fl_px * N2 * npix, dec_by_px * N2 * npix,
+              dh_launch_pixel_decoder_tc(XS, pos, TAB, dectc, N2, L.h, L.w, L.heads, L.depth, nullptr, 1, x3 | 256, XD, s));
+      DH_CONV3(nm[i][4], XD, reinterpret_cast<float*>(H16(XD) + half), 32, 32, plane2, B, L.h, L.w, 3, 1, 32, DH_W_LV5_DECODE_WT + i, -1,
+               nullptr, 0, 0, DX, 0, 0);
+    } else {
+      DH_STEP(nm[i][2], 0.0, 4.0 * B * L.depth * (double)DH_TABTC_FLOATS, dh_launch_decoder_tables_tc(MEM, B, 2, 1, dec, L.heads, L.depth, TAB, s));
+      DH_CONV3(nm[i][4], XS, reinterpret_cast<float*>(H16(XS) + half), 32, 32, plane2, B, L.h, L.w, 3, 1, 32, DH_W_LV5_DECODE_WT + i, -1,
+               nullptr, 0, 0, DX, 0, 0);
+    }
+    return 0;
+  };
+  auto level_post = [&](int i) -> int {
+    const Level& L = p.lv[i];
+    const int npix = L.h * L.w;
+    const float* pos = Wt(base[i] + 4);
+    float *DX = ws + L.dx, *OUT = ws + L.out, *TAB = ws + L.tab;
+    const float* skip = (i == 0) ? nullptr : (i == 1 ? ws + p.lv[0].out : C4);     // both fp32
+    const int skip_up = (i == 1) ? 2 : 1;
+    const double inner = 64.0 * L.heads;
+    const double dec_fl_px = L.depth * 2.0 * (32 * inner + 4 * inner + 4 * inner + inner * 32 + 2 * 32 * 32);
+    const double dec_by_px = 4.0 * 32 * (pos ? 3 : 2);
+    const float* dectc = Wt(DH_W_LV5_DECTC + i);
+    const float* tab2 = (variant == DH_VARIANT_LEVIR) ? TAB + (size_t)2 * B * L.depth * DH_TABTC_FLOATS : TAB;
+    const int out_split = i == 0 ? 0 : 256;                 // level 5's result is only a decoder skip; levels 4 / 3 feed conv_layer4 / 3
+    DH_STEP(nm[i][5], dec_fl_px * B * npix, (dec_by_px + (skip ? 128.0 / (skip_up * skip_up) : 0.0)) * B * npix,
+            dh_launch_pixel_decoder_tc(DX, pos, tab2, dectc, B, L.h, L.w, L.heads, L.depth, skip, skip_up, x3 | out_split, OUT, s));
+    if (i == 1)   // conv_layer4(up2(out_4)) -> C4 at H/4 (:1335-1336), pixel-shuffle form
+      DH_CONV3(nm[i][6], OUT, nullptr, 32, 0, 0, B, L.h, L.w, 3, 1, 128, DH_W_CL4_PSWT, DH_W_CL4_PSB, nullptr, 0, 1, C4, 0, 1);
+    return 0;
+  };
+  AuxStreams* aux = (g_prof.on || (flags & DH_FLAG_SERIAL)) ? nullptr : aux_streams();
+  if (aux) {
+    if (cudaEventRecord(aux->fork, s_main) != cudaSuccess) return (int)cudaGetLastError();
+    for (int i = 1; i <= 2; ++i) {
+      s = aux->st[i - 1];
+      if (cudaStreamWaitEvent(s, aux->fork, 0) != cudaSuccess) return (int)cudaGetLastError();
+      const int rc = level_pre(i);
+      if (rc == 0 && cudaEventRecord(aux->join[i - 1], s) != cudaSuccess) { s = s_main; return (int)cudaGetLastError(); }
+      s = s_main;
+      if (rc != 0) return rc;
+    }
+  }
+  for (int i = 0; i < 3; ++i) {
+    int rc = 0;
+    if (i == 0 || !aux) rc = level_pre(i);
+    else if (cudaStreamWaitEvent(s_main, aux->join[i - 1], 0) != cudaSuccess) rc = (int)cudaGetLastError();
+    if (rc == 0) rc = level_post(i);
+    if (rc != 0) return rc;
+  }
+  // ---- UNet head (reference networks.py:1341-1357)
+  float *C3 = ws + p.c3, *Y20 = ws + p.y20, *O2 = ws + p.o2, *C2 = ws + p.c2;
+  float* OUT3 = ws + p.lv[2].out;                                           // out_3 = level3 + C4 (split16)
+  DH_CONV3("conv_layer3", OUT3, nullptr, 32, 0, 0, B, h4, w4, 3, 1, 128, DH_W_CL3_PSWT, DH_W_CL3_PSB, nullptr, 0, 1, C3, 0, 1);
+  DH_CONV3("conv_layer2_0.0", F2, F2post, 64, 64, f2_plane, B, h2, w2, 3, 1, 128, DH_W_CL20A_WT, DH_W_CL20A_B, nullptr, 0, 1, Y20, 1, 0);
+  DH_CONV3("conv_layer2_0.3", Y20, nullptr, 128, 0, 0, B, h2, w2, 3, 1, 32, DH_W_CL20B_WT, DH_W_CL20B_B, C3, 0, 0, O2, 1, 0);
+  DH_CONV3("conv_layer2", O2, nullptr, 32, 0, 0, B, h2, w2, 3, 1, 128, DH_W_CL2_PSWT, DH_W_CL2_PSB, nullptr, 0, 1, C2, 0, 1);
+  DH_STEP("classifier", 2.0 * B * H * W * 9 * 32 * output_nc, 4.0 * B * H * W * (32.0 + output_nc) + (argmax_u8 ? (double)B * H * W : 0.0),
+          dh_launch_classifier(C2, B, H, W, output_nc, Wt(DH_W_CLS_W), Wt(DH_W_CLS_B), logits, argmax_u8, s));
+  return 0;
+}
+}  // namespace
+
+
 extern "C" int dahitra_forward(const void* const* weights, int n_weights, const float* x1, const float* x2,
                                long long x_batch_stride, float* logits, unsigned char* argmax_u8, void* workspace,
                                size_t workspace_bytes, int variant, int B, int H, int W, int output_nc, int flags,
@@ -297,6 +508,12 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
   const cudaStream_t s_main = (cudaStream_t)stream;
   cudaStream_t s = s_main;                      // the stream the launch helpers below use; switched while a level is forked
   float* ws = (float*)workspace;
+  dh_set_pdl((flags & DH_FLAG_PDL) ? 1 : 0);
+  if (flags & DH_FLAG_ACT_SPLIT) {              // split16 activation storage: needs the FP16 conv operands, the tcgen05 stem and decoder
+    constexpr int need = DH_FLAG_CONV_TC | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC;
+    DH_REQUIRE((flags & need) == need && !(flags & (DH_FLAG_TC_BF16 | DH_FLAG_CONV_TC_V1)), DH_E_VARIANT);
+    return forward_split(p, weights, x1, x2, x_batch_stride, logits, argmax_u8, ws, variant, B, H, W, output_nc, flags, s_main);
+  }
   auto Wt = [&](int slot) { return (const float*)weights[slot]; };
   const int N2 = 2 * B;
   const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8, h16 = H / 16, w16 = W / 16;

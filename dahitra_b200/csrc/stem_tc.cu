@@ -76,7 +76,8 @@ __device__ __forceinline__ void sk_halo_producer(const CUtensorMap* tmX, uint32_
 // each store instruction writes four whole 128-byte lines (8 lanes per pixel) instead of 16 bytes of 32 different
 // lines (same scheme as conv_tc2.cu); + bias, ReLU, NHWC.
 __device__ __forceinline__ void sk_store_slice(const float (&v)[32], float* stage, int lane, int q, int j, const SkTile& t,
-                                               int OH, int OW, const float* __restrict__ bias, float* __restrict__ out) {
+                                               int OH, int OW, const float* __restrict__ bias, float* __restrict__ out,
+                                               long long split_plane = 0) {
   const int c8 = lane & 7, r8 = lane >> 3;
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4)
@@ -88,9 +89,21 @@ __device__ __forceinline__ void sk_store_slice(const float (&v)[32], float* stag
     const int r = g * 4 + r8, mm = q * 32 + r;             // tile pixel (py = mm / 16, px = mm % 16)
     const int oy = t.oy0 + mm / SK_TW, ox = t.ox0 + mm % SK_TW;
     const float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((c8 ^ (r & 7)) << 2));
-    if (oy < OH && ox < OW)
-      st4(out + ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32 + c8 * 4,
-          make_float4(fmaxf(o.x + b.x, 0.f), fmaxf(o.y + b.y, 0.f), fmaxf(o.z + b.z, 0.f), fmaxf(o.w + b.w, 0.f)));
+    if (oy < OH && ox < OW) {
+      const float4 r = make_float4(fmaxf(o.x + b.x, 0.f), fmaxf(o.y + b.y, 0.f), fmaxf(o.z + b.z, 0.f), fmaxf(o.w + b.w, 0.f));
+      const size_t off = ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32 + c8 * 4;
+      if (split_plane) {                 // split16 planes for conv_tc3.cu: hi = f16(r), lo = f16(2^11 (r - hi))
+        uint2 hi, lo;
+        hi.x = pack_f16x2_sat(r.x, r.y); hi.y = pack_f16x2_sat(r.z, r.w);
+        lo.x = pack_f16x2_sat((r.x - f16_lo(hi.x)) * 2048.f, (r.y - f16_hi(hi.x)) * 2048.f);
+        lo.y = pack_f16x2_sat((r.z - f16_lo(hi.y)) * 2048.f, (r.w - f16_hi(hi.y)) * 2048.f);
+        uint2* o16 = reinterpret_cast<uint2*>(out);
+        o16[off >> 2] = hi;
+        o16[(off + (size_t)split_plane) >> 2] = lo;
+      } else {
+        st4(out + off, r);
+      }
+    }
   }
   __syncwarp();
 }
@@ -265,7 +278,7 @@ constexpr size_t SF_IMAGE_OFFSET_FLOATS = 2 * (SK_B_BYTES / 4);      // the 16-b
 template <bool FOLD>   // FOLD = false: single-pass FP16 operands (rows 0..63 of the same filter tiles, no remainder products)
 __global__ void __launch_bounds__(SK_THREADS, 1)
 stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tilesX, int tilesY, int ntiles,
-                const float* __restrict__ wtc, const float* __restrict__ bias, float* __restrict__ out) {
+                const float* __restrict__ wtc, const float* __restrict__ bias, float* __restrict__ out, long long split_plane) {
   extern __shared__ uint8_t sk_raw[];
   __shared__ __align__(8) uint64_t w_bar, a_full[SF_NBUF], a_free[SF_NBUF], acc_full[2], acc_empty[2], halo_full[2], halo_free[2];
   __shared__ uint32_t tmem_slot;
@@ -359,7 +372,7 @@ stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int til
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = FOLD ? fmaf(__uint_as_float(r[i]), 0x1p-11f, __uint_as_float(u[i])) : __uint_as_float(u[i]);
-        sk_store_slice(v, stage, lane, q, j, t, OH, OW, bias, out);
+        sk_store_slice(v, stage, lane, q, j, t, OH, OW, bias, out, split_plane);
       }
     }
   } else if (warp == 13) {
@@ -410,8 +423,13 @@ stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int til
 }
 }  // namespace
 
+// x3: 0 = 1xTF32, 1 = 3xTF32, 2 = folded FP16, 3 = single-pass FP16; bit 8 (x3 | 256, modes 2 / 3 only): `out` receives the
+// split16 planes conv_tc3.cu consumes instead of fp32
 int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const float* wtc, const float* b, float* out,
-                      int x3, cudaStream_t s) {
+                      int x3, cudaStream_t s, long long split_plane_pitch) {
+  const bool split = (x3 & 256) != 0;
+  x3 &= 255;
+  DH_REQUIRE(!split || x3 == 2 || x3 == 3, DH_E_VARIANT);
   DH_REQUIRE(x && wtc && b && out, DH_E_NULL);
   DH_REQUIRE(N > 0 && H >= 8 && W >= 8 && H % 2 == 0 && W % 2 == 0, DH_E_SHAPE);
   DH_REQUIRE(dh_aligned16(wtc) && dh_aligned16(b) && dh_aligned16(out), DH_E_ALIGN);
@@ -419,6 +437,8 @@ int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const 
   const int OH = H / 2, OW = W / 2;
   const int tx = dh_cdiv(OW, SK_TW), ty = dh_cdiv(OH, SK_TH);
   const int ntiles = tx * ty * N;
+  // elements between the hi and lo planes: this call's own N images, or the pitch of a larger tensor it writes a part of
+  const long long split_plane = split ? (split_plane_pitch ? split_plane_pitch : (long long)N * OH * OW * 64) : 0;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -435,11 +455,11 @@ int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const 
   if (x3 == 2) {
     cudaError_t e = cudaFuncSetAttribute(stem_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
     if (e != cudaSuccess) return (int)e;
-    stem_f16_kernel<true><<<grid, SK_THREADS, SF_SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out);
+    stem_f16_kernel<true><<<grid, SK_THREADS, SF_SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out, split_plane);
   } else if (x3 == 3) {
     cudaError_t e = cudaFuncSetAttribute(stem_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
     if (e != cudaSuccess) return (int)e;
-    stem_f16_kernel<false><<<grid, SK_THREADS, SF_SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out);
+    stem_f16_kernel<false><<<grid, SK_THREADS, SF_SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out, split_plane);
   } else if (x3) {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<true>::SMEM);
     if (e != cudaSuccess) return (int)e;

@@ -20,10 +20,20 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a pipeline that cannot make progress (bad tensor map, lost arrive) traps after a few seconds
-// instead of hanging the GPU; the launch then reports cudaErrorLaunchFailure to the caller.
+// programmatic dependent launch (no-ops when the launch does not carry the attribute): everything above `pdl_wait` overlaps
+// the tail of the previous launch in the stream; its results are visible after it
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// mbarrier wait.  Release builds wait for as long as it takes (no trap, no printf on the hot path).  A debug build
+// (-DDH_MBAR_TIMEOUT, `DAHITRA_DEBUG_BUILD=1` for _lib.build) bounds the wait: a pipeline that cannot make progress (bad
+// tensor map, lost arrive) then traps after a few seconds instead of hanging, and the launch reports
+// cudaErrorLaunchFailure to the caller.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done, spins = 0;
+  uint32_t done;
+#ifdef DH_MBAR_TIMEOUT
+  uint32_t spins = 0;
+#endif
   do {
     // the suspend-time hint (ns) lets the thread sleep inside try_wait instead of burning issue slots in this loop
     asm volatile(
@@ -31,12 +41,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity), "r"(10000u) : "memory");
+#ifdef DH_MBAR_TIMEOUT
     if (!done && ++spins > (1u << 19)) {
-#ifdef DH_MBAR_DEBUG
       printf("[mbar timeout] block %d thread %d bar smem+0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
-#endif
       __trap();
     }
+#endif
   } while (!done);
 }
 // ---- CTA-pair (cta_group::2) helpers: cluster rank / sync, remote mbarrier arrive, TMA signalling the leader's barrier
@@ -59,14 +69,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {     
 }
 // wait on a LOCAL barrier whose arrivals may come from the peer CTA (acquire at cluster scope)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t done, spins = 0;
+  uint32_t done;
+#ifdef DH_MBAR_TIMEOUT
+  uint32_t spins = 0;
+#endif
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity), "r"(10000u) : "memory");
+#ifdef DH_MBAR_TIMEOUT
     if (!done && ++spins > (1u << 19)) __trap();
+#endif
   } while (!done);
 }
 // TMA loads issued by either CTA of a pair whose completion bytes are counted on `cluster_bar` (normally the leader's)

@@ -24,7 +24,7 @@ LEVELS = ((5, 256, 4, 4), (4, 128, 4, 4), (3, 64, 8, 8))   # (k, trunk channels,
 DH_VARIANT_LEVIR, DH_VARIANT_XBD = 0, 1
 DH_FLAG_CONV_TC, DH_FLAG_TC_3XTF32, DH_FLAG_TC_STRIDE2, DH_FLAG_DEC_TC, DH_FLAG_STEM_TC, DH_FLAG_DEC_TC_X3 = 1, 2, 4, 8, 16, 32
 DH_FLAG_CONV_TC_V1, DH_FLAG_CONV_TC_2CTA, DH_FLAG_SERIAL, DH_FLAG_TC_X3_BF16, DH_FLAG_TC_BF16 = 64, 128, 256, 512, 1024
-DH_FLAG_TC_MAIN_F16, DH_FLAG_TC_FOLD = 2048, 4096
+DH_FLAG_TC_MAIN_F16, DH_FLAG_TC_FOLD, DH_FLAG_EARLY_HEAD, DH_FLAG_ACT_SPLIT, DH_FLAG_PDL = 2048, 4096, 8192, 16384, 32768
 MODES = {
     "fp32": 0,                                             # every contraction in fp32 FMA (strict)
     "fp32_tcdec": DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,      # strict + the 3xTF32 (fp32-grade) tensor-core decoder
@@ -35,8 +35,14 @@ MODES = {
     # (bf16-grade accuracy for those values only).  The 7x7 stem runs the same way; pixel decoder: 3xTF32.
     # The f16(a).r_w correction shares its A operand with the main product, so both come out of ONE N-doubled FP16 MMA
     # on the filter tile [f16(w) ; f16(2^11 r_w)] and are added in the epilogue (DH_FLAG_TC_FOLD).
+    # Activations that feed a convolution are STORED as the pair the MMAs consume — hi = f16(a), lo = f16(2^11 (a - hi)), the
+    # same 4 bytes per element as fp32 (DH_FLAG_ACT_SPLIT, csrc/conv_tc3.cu): a.w = h_a.h_w + 2^-11 (h_a.l_w + l_a.h_w), all
+    # three products on FP16 MMAs, TMA lands the operands directly, and the tokenizer's 1x1 squeeze runs on the tensor cores.
     "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_FOLD | DH_FLAG_TC_STRIDE2
-              | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
+              | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3 | DH_FLAG_ACT_SPLIT,
+    # ... with fp32 activation storage and an in-kernel splitter pass (round 1's default; f16 main + bf16 remainders)
+    "tf32x3_fp32act": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_FOLD | DH_FLAG_TC_STRIDE2
+                      | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
     # ... with three separate products per (tap, chunk) and the 3xTF32 stem (~10 % slower)
     "tf32x3_unfolded": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC
                        | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,
@@ -230,6 +236,7 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
         s = f"DH_W_LV{k}_"
         P[s + "SQ"] = sd[f"conv_squeeze_{k}.0.weight"].double()[:, :, 0, 0].T          # [Cin][32]
         P[s + "TOK"] = sd[f"conv_token_{k}.weight"].double()[:, :, 0, 0].T             # [32][4]
+        P[s + "SQ_WT"] = kmajor_split(P[s + "SQ"].T)                                   # [32][Cin] K-major planes (conv_tc3 tok launch)
         P[s + "DECODE"] = _khwc(sd[f"conv_decode_{k}.weight"].double())
         P[s + "DECODE_WT"] = kmajor_split(P[s + "DECODE"].T)
         # ---- token encoder pack

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DAHITRA_ABI_VERSION 1
+#define DAHITRA_ABI_VERSION 2
 
 /* error codes (negative) */
 #define DH_E_NULL      (-1)   /* a required pointer is NULL */
@@ -60,9 +60,15 @@ extern "C" {
 #define DH_FLAG_TC_MAIN_F16 2048 /* with TC_3XTF32: main product of every conv in FP16 (K = 16 MMAs), both corrections in BF16; without it: single-pass FP16 operands */
 #define DH_FLAG_TC_FOLD     4096 /* with TC_3XTF32 | TC_MAIN_F16: fold the f16(a).r_w correction into the main MMA (2N-wide filter tile); with TC_X3_BF16 the stem runs the same folded FP16 form */
 #define DH_FLAG_EARLY_HEAD  8192 /* issue conv_layer2_0.0 right after the stem on a lowest-priority side stream, one tile per CTA */
+#define DH_FLAG_ACT_SPLIT   16384 /* with the folded FP16 mode (TC_3XTF32 | TC_MAIN_F16 | TC_FOLD | STEM_TC | DEC_TC): activations that feed a
+                                   * convolution are STORED as the split16 pair the MMAs consume (hi = f16(a), lo = f16(2^11 (a - hi)); 4 bytes
+                                   * per element like fp32) and every convolution runs conv_tc3.cu: no splitter pass, TMA lands the operands;
+                                   * the tokenizer's 1x1 squeeze runs on the tensor cores with the softmax partials in its epilogue */
+#define DH_FLAG_PDL         32768 /* programmatic dependent launch between consecutive launches of a stream (prologues overlap the previous
+                                   * launch's tail; every kernel waits with griddepcontrol.wait before touching its inputs) */
 /* the modes dahitra_b200.engine.MODES names (DESIGN.md "Precision modes") */
 #define DH_FLAGS_TF32X3     (DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_FOLD | DH_FLAG_TC_STRIDE2 | \
-                             DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3)   /* default: every product error-compensated, fp32-grade */
+                             DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3 | DH_FLAG_ACT_SPLIT)   /* default: every product error-compensated, fp32-grade */
 #define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3)   /* single-pass TF32 convs */
 #define DH_FLAGS_F16        (DH_FLAGS_TF32 | DH_FLAG_TC_MAIN_F16)                    /* single-pass FP16 conv operands */
 #define DH_FLAGS_BF16       (DH_FLAGS_TF32 | DH_FLAG_TC_BF16)                        /* single-pass BF16 conv operands */
@@ -111,6 +117,9 @@ enum dh_weight_slot {
    * gamma folded; W2: n=channel, k=hidden); cbA/cbM = cumulative biases after the attention / MLP of the layer */
   DH_W_LV5_DECTC, DH_W_LV4_DECTC, DH_W_LV3_DECTC,
   DH_W_STEM_WTC,   /* stem filter for the tcgen05 stem; K ordered (ci, r, s8): 21 groups of 1 zero + 7 taps, padded to 192.  [0, 24576) floats: TF32 [hi, lo] x 6 K-step tiles of B[n=co 64][k 32] swz; [24576, 36864): bits of 3 K-step tiles of [f16(w) 64 rows ; f16(2^11 (w - f16 w)) 64 rows][k 64] swz; [36864, 43008): bits of 3 tiles of bf16(w)[64][k 64] swz */
+  /* K-major split filters of the three 1x1 squeeze convolutions (same five planes as the other *_WT slots, [32][Cin]):
+   * with DH_FLAG_ACT_SPLIT the squeeze + tokenizer partials run as a conv_tc3 launch */
+  DH_W_LV5_SQ_WT, DH_W_LV4_SQ_WT, DH_W_LV3_SQ_WT,
   DH_W_COUNT
 };
 
@@ -190,7 +199,8 @@ int dahitra_conv2d_up2_tc(const float* in, int N, int inH, int inW, const float*
 int dahitra_stem(const float* x, long long x_batch_stride, int N, int H, int W,
                  const float* w, const float* bias, float* out, void* stream);
 
-/* Same stem on the tensor cores: x3 = 0 TF32 operands, 1 error-compensated 3xTF32, 2 folded FP16 (fp32-grade for |x| <= 65504; the default mode's stem), 3 single-pass FP16 (the f16 / bf16 modes' stem); wtc = DH_W_STEM_WTC image. */
+/* Same stem on the tensor cores: x3 = 0 TF32 operands, 1 error-compensated 3xTF32, 2 folded FP16 (fp32-grade for |x| <= 65504; the default mode's stem), 3 single-pass FP16 (the f16 / bf16 modes' stem); wtc = DH_W_STEM_WTC image.
+ * x3 | 256 (forms 2 and 3): out receives split16 planes instead of fp32. */
 int dahitra_stem_tc(const float* x, long long x_batch_stride, int N, int H, int W,
                     const float* wtc, const float* bias, float* out, int x3, void* stream);
 
@@ -237,9 +247,31 @@ int dahitra_pixel_decoder(const float* x, const float* pos, const float* tables,
 #define DH_DECTC_LAYER_FLOATS  (1024 + 1024 + 32 + 32 + 32 + 2048)
 int dahitra_decoder_tables_tc(const float* mem, int B, int first_call, int ncalls, const float* dec_pack, int heads,
                               int depth, float* tables, void* stream);
+/* x3 | 256: out receives split16 planes instead of fp32 */
 int dahitra_pixel_decoder_tc(const float* x, const float* pos, const float* tables, const float* dectc_pack,
                              int nimg, int h, int w, int heads, int depth, const float* skip, int skip_up, int x3,
                              float* out, void* stream);
+
+/* ---- split16 activation format (DH_FLAG_ACT_SPLIT; conv_tc3.cu) --------------------------------------------------
+ * A split16 tensor of n elements is two FP16 planes, hi at the pointer and lo n elements (2n bytes) later:
+ *   hi = f16(a) saturating, lo = f16(2^11 (a - hi)),  a ~= hi + 2^-11 lo   (the same 4 bytes per element as fp32). */
+int dahitra_split_pack(const float* in, long long n, void* out_split, void* stream);      /* n % 8 == 0 */
+int dahitra_split_unpack(const void* in_split, long long n, float* out, void* stream);
+/* MaxPool2d(3, 2, 1) on a split16 NHWC tensor (compares reconstructed values; the winner's planes are reproduced exactly) */
+int dahitra_maxpool3x3s2_split(const void* in_split, int N, int H, int W, int C, void* out_split, void* stream);
+/* Convolution over split16 inputs with all three partial products on FP16 MMAs (file header of conv_tc3.cu):
+ *   in0 / in1      split16 NHWC sources (virtual channel concat, C1 may be 0); in*_plane = elements between their hi and lo
+ *                  planes (0 = N*inH*inW*C; larger when they are sub-ranges of the images of one tensor)
+ *   K in {1,3}, pad K/2, stride in {1,2}, Cout in {32,64,128,256}, C0 % 32 == C1 % 32 == 0
+ *   wt             the conv's *_WT slot (float [5][Cout][K*K*Cin]); planes 3 and 4 hold h_w and l_w
+ *   res            NULL, fp32 NHWC (res_split = 0) or split16 (res_split = 1); out fp32 NHWC or split16 (out_split)
+ *   mode           0 plain | 1 pixel-shuffle store of a 32 -> 4x32 upsample conv (fp32 out [N][2inH][2inW][32]) |
+ *                  2 tokenizer epilogue: no bias, ReLU, out = xs, partials [N][nchunk][4][34] with
+ *                    nchunk = ceil(inH/16) * ceil(inW/8), w_tok [32][4]  (see dahitra_squeeze_tokens) */
+int dahitra_conv2d_split(const void* in0, const void* in1, int C0, int C1, long long in0_plane, long long in1_plane,
+                         int N, int inH, int inW, int K, int stride, int Cout, const float* wt, const float* bias,
+                         const void* res, int res_split, int relu, void* out, int out_split, int mode,
+                         const float* w_tok, float* partials, void* stream);
 
 /* Classifier 3x3 conv 32->nc (+bias), NHWC in, NCHW logits out, optional uint8 argmax map
  * (reference models/networks.py:1249,1355; harness argmax models/evaluator.py:89-92). */

@@ -125,3 +125,51 @@ def classifier(x, w, b, nc, want_argmax=True):
     am = torch.empty((N, H, W), device=x.device, dtype=torch.uint8) if want_argmax else None
     _lib.check(lib.dahitra_classifier(_p(x), N, H, W, nc, _p(w), _p(b), _p(logits), _p(am), _stream()), "dahitra_classifier")
     return logits, am
+
+
+# ---- split16 activation format (conv_tc3.cu): a tensor of n elements = two FP16 planes (hi | lo) in a buffer of n floats
+def split_pack(x):
+    lib = _lib.load()
+    x = x.contiguous()
+    out = torch.empty_like(x)                       # same bytes: 2 planes x 2 bytes per element
+    _lib.check(lib.dahitra_split_pack(_p(x), x.numel(), _p(out), _stream()), "dahitra_split_pack")
+    return out
+
+
+def split_unpack(s):
+    lib = _lib.load()
+    out = torch.empty_like(s)
+    _lib.check(lib.dahitra_split_unpack(_p(s), s.numel(), _p(out), _stream()), "dahitra_split_unpack")
+    return out
+
+
+def maxpool_split(s):
+    lib = _lib.load()
+    N, H, W, C = s.shape
+    out = torch.empty((N, H // 2, W // 2, C), device=s.device, dtype=torch.float32)
+    _lib.check(lib.dahitra_maxpool3x3s2_split(_p(s), N, H, W, C, _p(out), _stream()), "dahitra_maxpool3x3s2_split")
+    return out
+
+
+def conv2d_split(in0, in1, w, bias, res, relu, K, stride, res_split=False, out_split=False, mode=0, wtok=None):
+    """in0 / in1: split16 buffers shaped like their fp32 tensors (N, H, W, C); w: [K*K*Cin][Cout] fp32 (split on the host
+    exactly as the engine does).  mode 1: w is the [128][288] phase filter already K-major.  Returns out (fp32 NHWC, or a
+    split16 buffer of that shape) and, in mode 2, the partials."""
+    lib = _lib.load()
+    from dahitra_b200.engine import kmajor_split
+    N, inH, inW, C0 = in0.shape
+    C1 = 0 if in1 is None else in1.shape[-1]
+    wk = w.detach().cpu().double()
+    wt = kmajor_split(wk if mode == 1 else wk.t()).float().contiguous().to(in0.device)
+    Cout = wt.shape[1]
+    OH, OW = inH // stride, inW // stride
+    shape = (N, 2 * OH, 2 * OW, 32) if mode == 1 else (N, OH, OW, Cout)
+    out = torch.empty(shape, device=in0.device, dtype=torch.float32)
+    parts = None
+    if mode == 2:
+        nchunk = ((inH + 15) // 16) * ((inW + 7) // 8)
+        parts = torch.empty((N, nchunk, 4, 34), device=in0.device, dtype=torch.float32)
+    rc = lib.dahitra_conv2d_split(_p(in0), _p(in1), C0, C1, 0, 0, N, inH, inW, K, stride, Cout, _p(wt), _p(bias), _p(res),
+                                  int(res_split), int(relu), _p(out), int(out_split), mode, _p(wtok), _p(parts), _stream())
+    _lib.check(rc, "dahitra_conv2d_split")
+    return (out, parts) if mode == 2 else out

@@ -310,3 +310,129 @@ def test_argument_errors():
     assert rc == -3
     with pytest.raises(RuntimeError, match="code -2"):
         _lib.check(-2, "x")
+
+
+# ------------------------------------------------------------------------------------------------ split16 path (conv_tc3.cu)
+def f16_split_ref(x):
+    """host statement of the split16 format: hi = f16(a) saturating, lo = f16(2^11 (a - hi)); returns hi + 2^-11 lo (fp64)"""
+    x = x.detach().cpu().float()
+    hi = x.clamp(-65504.0, 65504.0).half()
+    lo = ((x - hi.float()) * 2048.0).clamp(-65504.0, 65504.0).half()
+    return hi.double() + lo.double() / 2048.0
+
+
+def test_split16_pack_roundtrip():
+    g = torch.Generator().manual_seed(1)
+    x = torch.cat([torch.randn(4096, generator=g) * s for s in (1.0, 1e-3, 30.0, 1e-6, 3e4)] + [torch.zeros(64), torch.tensor([7e4, -7e4, 65504.0, 1e-9] * 2)])
+    xd = x.to(DEV)
+    s = abi.split_pack(xd)
+    y = abi.split_unpack(s)
+    ref = f16_split_ref(x)
+    assert torch.equal(y.double().cpu(), ref)                     # bit-exact against the host statement of the format
+    inr = (x.abs() > 6.2e-5) & (x.abs() < 6.5e4)
+    rel = ((y.cpu() - x).abs() / x.abs().clamp_min(1e-30))[inr]
+    assert float(rel.max()) <= 2.0 ** -21                          # 22 significant bits inside the normal FP16 range
+    assert float((y.cpu() - x).abs()[x.abs() <= 6.2e-5].max()) <= 3.1e-11
+    assert torch.equal(abi.split_unpack(abi.split_pack(y)), y)     # idempotent
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 20, 28, 128), (3, 64, 64, 64)])
+def test_maxpool_split16(shape):
+    x = rnd(*shape, seed=3)
+    xq = abi.split_unpack(abi.split_pack(x))                       # representable values: the pool must be exact on them
+    y = abi.split_unpack(abi.maxpool_split(abi.split_pack(x)))
+    ref = F.max_pool2d(xq.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(y, ref)
+
+
+SPLIT_CONVS = [  # (N, H, W, C0, C1, Cout, K, stride, res ('', 'f32', 'split'), relu, bias, out_split)
+    (2, 16, 16, 32, 0, 32, 1, 1, '', False, False, False),         # smallest: one chunk, one tap
+    (1, 16, 16, 32, 0, 32, 3, 1, '', False, False, False),         # 9 taps, zero padding through TMA OOB fill
+    (2, 64, 64, 64, 0, 64, 3, 1, 'split', True, True, True),       # layer1 conv2 (+identity, ReLU), split16 in / res / out
+    (2, 32, 32, 128, 0, 128, 3, 1, 'split', True, True, True),     # layer2
+    (1, 64, 64, 64, 0, 128, 3, 2, '', True, True, True),           # layer2.0.conv1 (stride 2: four phase halos)
+    (2, 32, 32, 64, 0, 128, 1, 2, '', False, True, True),          # layer2.0 downsample (1x1 stride 2)
+    (2, 16, 16, 128, 0, 256, 1, 1, '', False, True, True),         # layer3.0 downsample (two N tiles)
+    (1, 16, 16, 256, 0, 256, 3, 1, 'split', True, True, True),     # layer3 (72 (tap, chunk) steps)
+    (2, 32, 32, 32, 32, 32, 3, 1, '', False, False, False),        # conv_decode on a virtual concat -> fp32
+    (1, 64, 64, 64, 64, 128, 3, 1, '', True, True, True),          # conv_layer2_0.0
+    (1, 64, 64, 128, 0, 32, 3, 1, 'f32', False, True, True),       # conv_layer2_0.3 + out_3 (fp32 residual)
+    (1, 20, 28, 32, 0, 64, 3, 1, '', True, True, False),           # ragged edges
+    (3, 36, 20, 64, 0, 32, 3, 2, '', False, False, True),          # ragged + stride 2
+    (5, 48, 40, 64, 0, 64, 3, 1, 'split', True, True, True),       # more tiles than one wave of a small grid
+]
+
+
+@pytest.mark.parametrize("cfg", SPLIT_CONVS)
+def test_conv2d_split16(cfg):
+    """conv_tc3: split16 operands, three FP16 partial products, vs fp64 on the SAME representable inputs / weights."""
+    N, H, W, C0, C1, Cout, K, stride, res, relu, bias, out_split = cfg
+    x0 = rnd(N, H, W, C0, seed=1)
+    x1 = rnd(N, H, W, C1, seed=2) if C1 else None
+    Kt = K * K * (C0 + C1)
+    w = rnd(Kt, Cout, seed=3, scale=Kt ** -0.5)
+    b = rnd(Cout, seed=4) if bias else None
+    OH, OW = H // stride, W // stride
+    r = rnd(N, OH, OW, Cout, seed=5) if res else None
+    s0, s1 = abi.split_pack(x0), (abi.split_pack(x1) if C1 else None)
+    rs = None if r is None else (abi.split_pack(r) if res == 'split' else r)
+    y = abi.conv2d_split(s0, s1, w, b, rs, relu, K, stride, res_split=(res == 'split'), out_split=out_split)
+    torch.cuda.synchronize()
+    xq = f16_split_ref(x0) if x1 is None else torch.cat([f16_split_ref(x0), f16_split_ref(x1)], -1)
+    rq = None if r is None else (f16_split_ref(r) if res == 'split' else r.double().cpu())
+    ref = E.conv_nhwc(xq, f16_split_ref(w), None if b is None else b.double().cpu(), K, stride, K // 2, rq, relu, 1)
+    if out_split:
+        ref = f16_split_ref(ref)
+        y = abi.split_unpack(y)
+    assert y.shape == ref.shape
+    d = (y.double().cpu() - ref).abs()
+    print(f"[tc3] {cfg}: max|d|={float(d.max()):.3e} mean|d|={float(d.mean()):.3e} ref_absmax={float(ref.abs().max()):.3e}")
+    close(y, ref, rtol=1e-5, atol=2e-5 * float(ref.abs().max()))    # fp32 accumulation over up to 2304 terms (same bar as 3xTF32)
+    # and against the un-quantised fp64 convolution: the format itself costs ~2^-22 per operand
+    full = E.conv_nhwc((x0 if x1 is None else torch.cat([x0, x1], -1)).double().cpu(), w.double().cpu(),
+                       None if b is None else b.double().cpu(), K, stride, K // 2, None if r is None else r.double().cpu(), relu, 1)
+    close(y, full, rtol=1e-5, atol=2e-5 * float(full.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16), (1, 64, 64), (1, 24, 40)])
+def test_conv2d_up2_split16(shape):
+    """nearest-x2 upsample + 3x3 conv (conv_layer4/3/2) on a split16 input, pixel-shuffle store to fp32."""
+    from dahitra_b200.engine import upsample_phase_filter
+    N, H, W = shape
+    x = rnd(N, H, W, 32, seed=1)
+    g = torch.Generator().manual_seed(2)
+    w = torch.randn(32, 32, 3, 3, generator=g, dtype=torch.float64) * (288 ** -0.5)
+    b = torch.randn(32, generator=g, dtype=torch.float64)
+    wt, pb = upsample_phase_filter(w, b)
+    y = abi.conv2d_split(abi.split_pack(x), None, wt, pb.float().to(DEV), None, True, 3, 1, mode=1)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.double().cpu().permute(0, 3, 1, 2).repeat_interleave(2, 2).repeat_interleave(2, 3), w, b, 1, 1))
+    close(y, ref.permute(0, 2, 3, 1), rtol=1e-5, atol=2e-5 * float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("cfg", [(2, 16, 16, 256), (2, 32, 32, 128), (2, 64, 64, 64), (1, 24, 40, 64), (1, 256, 256, 64)])
+@pytest.mark.parametrize("xs_split", [False, True])
+def test_squeeze_tokens_split16(cfg, xs_split):
+    """conv_tc3 tok epilogue: 1x1 squeeze + ReLU + per-tile softmax partials, merged by the token encoder's rule, vs fp64
+    (reference models/networks.py:1177-1189, 1273-1280)."""
+    N, H, W, Cin = cfg
+    feat = rnd(N, H, W, Cin, seed=1)
+    wsq = rnd(Cin, 32, seed=2, scale=Cin ** -0.5)
+    wtok = rnd(32, 4, seed=3, scale=1.0)
+    xs, parts = abi.conv2d_split(abi.split_pack(feat), None, wsq, None, None, False, 1, 1, out_split=xs_split, mode=2, wtok=wtok)
+    torch.cuda.synchronize()
+    if xs_split:
+        xs = abi.split_unpack(xs)
+    fq = f16_split_ref(feat).reshape(N, H * W, Cin)
+    xr = torch.relu(fq @ f16_split_ref(wsq))
+    close(xs.reshape(N, H * W, 32), f16_split_ref(xr) if xs_split else xr, rtol=1e-5, atol=2e-5 * float(xr.abs().max()))
+    # merge the partials as token_encoder_kernel does and compare with the fp64 tokenizer
+    p = parts.double().cpu()                                       # [N][nchunk][4][34]
+    M = p[..., 0].max(dim=1, keepdim=True).values
+    sc = torch.exp(p[..., 0] - M)
+    S = (p[..., 1] * sc).sum(1)
+    T = (p[..., 2:] * sc[..., None]).sum(1)
+    tok = T / S[..., None]                                         # [N][4][32]
+    a = torch.softmax(torch.einsum("npc,cl->nlp", xr, wtok.double().cpu()), dim=-1)
+    ref = torch.einsum("nlp,npc->nlc", a, xr)
+    close(tok, ref, rtol=2e-5, atol=2e-5 * float(ref.abs().max()))

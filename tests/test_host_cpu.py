@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dahitra_version() == 1
+    assert lib.dahitra_version() == 2
     assert b"ok" == lib.dahitra_error_string(0)
     assert b"workspace" in lib.dahitra_error_string(-4)
 
