@@ -26,6 +26,7 @@
 // models/networks.py:1177-1189, 1273-1280): ReLU, store, and the per-tile online-softmax partials (m, s, t[32]) of the four
 // semantic tokens — what squeeze_tokens_kernel (tokens.cu) computes on CUDA cores in the other modes.
 #include "tc_common.cuh"
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -35,8 +36,10 @@ namespace {
 
 constexpr int T3_TH = 16, T3_TW = 8;                    // output patch
 constexpr int T3_HW = T3_TW + 2, T3_HH = T3_TH + 2;     // halo 10 x 18
-constexpr uint32_t T3_PLANE = 12288;                    // one 16-bit halo (180 px x 64 B = 11520), 1024-aligned pitch
-constexpr uint32_t T3_HALO = 2 * T3_PLANE;              // hi + lo
+constexpr uint32_t T3_PLANE = 11776;                    // one 16-bit halo (180 px x 64 B = 11520), padded to the 512-B swizzle period
+constexpr uint32_t T3_HALO = 2 * T3_PLANE;              // hi + lo = 23552 (1024-aligned)
+constexpr int T3_MAX_HB = 4;
+enum { EPI_F32 = 0, EPI_SPLIT = 1, EPI_TOK = 2 };        // output: fp32 NHWC / pixel-shuffle | split16 planes | tokenizer (xs + partials)
 
 struct T3Args {
   const float* bias;
@@ -44,20 +47,23 @@ struct T3Args {
   const float* wtok; float* partials;                   // TOK epilogue
   long long res_plane, out_plane;                       // elements between the hi and lo planes of res / out
   int OH, OW, Cout, relu, tilesX, tilesY, cchunks0, cchunks, Cin, ps, N, ncout_tiles, ntiles;
-  int res_split, out_split, tok, tiles_per_img;
+  int res_split, out_split, tiles_per_img;
+  int hb;                                               // halo buffers in use (2..T3_MAX_HB; what fits next to a resident filter)
   uint32_t halo_plane_bytes;                            // bytes one TMA box delivers (hw * hh * 64)
 };
 
-template <int NT> struct T3Cfg {
-  static constexpr int HB = 4;                                           // halo chunk buffers (hi + lo each)
-  static constexpr int TPS = NT == 128 ? 1 : 3;                          // filter taps per ring stage
-  static constexpr int STAGES = NT == 128 ? 6 : (NT == 64 ? 4 : 8);
+// RES = false: the filter tile of every (tap, chunk) streams from L2 through a TMA ring, once per M tile.
+// RES = true:  the WHOLE filter ([ncout_tiles][cchunks][taps] tiles of [h_w ; l_w], <= 144 KB) is loaded into shared
+//              memory once per CTA and stays there while the persistent CTA walks its tiles — the L2 -> SM path
+//              (~43 B/clk per SM with every SM pulling, B300_MICROARCH "LTS throughput cap") is what bounds the
+//              streaming form on the small-K layers: layer1 re-reads 144 KB of filter for every 46 KB halo.
+template <int NT, bool RES> struct T3Cfg {
+  static constexpr int TPS = NT == 128 ? 1 : 3;                          // filter taps per ring stage (streaming form)
+  static constexpr int STAGES = RES ? 1 : (NT == 128 ? 6 : (NT == 64 ? 4 : 8));
   static constexpr uint32_t B_TAP = 2u * NT * 64u;                       // [h_w (NT rows) ; l_w (NT rows)] x 64 B
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
-  static constexpr uint32_t HALO_BYTES = HB * T3_HALO;
-  static constexpr uint32_t EPI_OFF = HALO_BYTES + STAGES * B_STAGE;     // epilogue staging: 4 warps x 4 KB
-  static constexpr uint32_t TOK_OFF = EPI_OFF + 4 * 4096;                // TOK: wtok [32][4] + per-warp (m, s, t) 4 x 4 x 34 floats
-  static constexpr uint32_t SMEM = TOK_OFF + 512 + 4 * 4 * 34 * 4 + 1024;
+  static constexpr uint32_t RING_BYTES = RES ? 0u : STAGES * B_STAGE;    // RES: the filter image follows the halo buffers instead
+  static constexpr uint32_t FIXED = 4 * 4096 + 512 + 4 * 4 * 34 * 4 + 1024;   // epilogue staging + tok scratch + alignment slack
   static constexpr int THREADS = 224;
   static constexpr uint32_t IDESC_WIDE = umma_idesc_f16(128, 2 * NT);
   static constexpr uint32_t IDESC_NARROW = umma_idesc_f16(128, NT);
@@ -79,13 +85,13 @@ template <int KS, int SD> struct Tap3 {                                   // tap
   }
 };
 
-struct Tile3 { int n, oy0, ox0, n0; };
-__device__ __forceinline__ Tile3 tile3(int tile, const T3Args& e, int NT) {
+struct Tile3 { int n, oy0, ox0, ct; };
+__device__ __forceinline__ Tile3 tile3(int tile, const T3Args& e) {
   Tile3 t;
-  const int ct = tile % e.ncout_tiles; tile /= e.ncout_tiles;
+  t.ct = tile % e.ncout_tiles; tile /= e.ncout_tiles;
   const int tx = tile % e.tilesX; tile /= e.tilesX;
   const int ty = tile % e.tilesY;
-  t.n = tile / e.tilesY; t.oy0 = ty * T3_TH; t.ox0 = tx * T3_TW; t.n0 = ct * NT;
+  t.n = tile / e.tilesY; t.oy0 = ty * T3_TH; t.ox0 = tx * T3_TW;
   return t;
 }
 
@@ -94,42 +100,51 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// split16 pack / unpack of four values (8 bytes per plane)
-__device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
-  hi.x = pack_f16x2_sat(v.x, v.y); hi.y = pack_f16x2_sat(v.z, v.w);
-  lo.x = pack_f16x2_sat((v.x - f16_lo(hi.x)) * 2048.f, (v.y - f16_hi(hi.x)) * 2048.f);
-  lo.y = pack_f16x2_sat((v.z - f16_lo(hi.y)) * 2048.f, (v.w - f16_hi(hi.y)) * 2048.f);
+// split16 pack / unpack of eight values (16 bytes per plane)
+__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  hi.x = pack_f16x2_sat(a.x, a.y); hi.y = pack_f16x2_sat(a.z, a.w); hi.z = pack_f16x2_sat(b.x, b.y); hi.w = pack_f16x2_sat(b.z, b.w);
+  lo.x = pack_f16x2_sat((a.x - f16_lo(hi.x)) * 2048.f, (a.y - f16_hi(hi.x)) * 2048.f);
+  lo.y = pack_f16x2_sat((a.z - f16_lo(hi.y)) * 2048.f, (a.w - f16_hi(hi.y)) * 2048.f);
+  lo.z = pack_f16x2_sat((b.x - f16_lo(hi.z)) * 2048.f, (b.y - f16_hi(hi.z)) * 2048.f);
+  lo.w = pack_f16x2_sat((b.z - f16_lo(hi.w)) * 2048.f, (b.w - f16_hi(hi.w)) * 2048.f);
 }
-__device__ __forceinline__ float4 join4(uint2 hi, uint2 lo) {
+__device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float4& a, float4& b) {
   constexpr float S = 1.0f / 2048.0f;
-  return make_float4(fmaf(f16_lo(lo.x), S, f16_lo(hi.x)), fmaf(f16_hi(lo.x), S, f16_hi(hi.x)),
-                     fmaf(f16_lo(lo.y), S, f16_lo(hi.y)), fmaf(f16_hi(lo.y), S, f16_hi(hi.y)));
+  a = make_float4(fmaf(f16_lo(lo.x), S, f16_lo(hi.x)), fmaf(f16_hi(lo.x), S, f16_hi(hi.x)),
+                  fmaf(f16_lo(lo.y), S, f16_lo(hi.y)), fmaf(f16_hi(lo.y), S, f16_hi(hi.y)));
+  b = make_float4(fmaf(f16_lo(lo.z), S, f16_lo(hi.z)), fmaf(f16_hi(lo.z), S, f16_hi(hi.z)),
+                  fmaf(f16_lo(lo.w), S, f16_lo(hi.w)), fmaf(f16_hi(lo.w), S, f16_hi(hi.w)));
 }
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ float4 as_f4(const uint4& u) { return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)); }
 
-template <int NT, int KS, int SD>
-__global__ void __launch_bounds__(T3Cfg<NT>::THREADS, 1)
+template <int NT, int KS, int SD, int EPI, bool RES>
+__global__ void __launch_bounds__(T3Cfg<NT, RES>::THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant__ CUtensorMap tmA0l,
                 const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
                 const __grid_constant__ CUtensorMap tmB, const T3Args e) {
-  using Cfg = T3Cfg<NT>;
-  constexpr int STAGES = Cfg::STAGES, HB = Cfg::HB;
+  using Cfg = T3Cfg<NT, RES>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t3_raw[];
-  __shared__ __align__(8) uint64_t halo_full[HB], halo_empty[HB], b_full[STAGES], b_empty[STAGES], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t halo_full[T3_MAX_HB], halo_empty[T3_MAX_HB], b_full[STAGES], b_empty[STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(t3_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = t3_raw + (base - smem_u32(t3_raw));
-  const uint32_t b_ring = base + Cfg::HALO_BYTES;
+  const int HB = e.hb;
+  const uint32_t b_ring = base + (uint32_t)HB * T3_HALO;                 // filter ring, or the resident filter image
   constexpr int pad = (KS == 3) ? 1 : 0;
   using Sched = Tap3<KS, SD>;
   constexpr int NPH = Sched::NPH;
   constexpr int NTAPS = KS * KS;
   constexpr int TPS = (SD == 1 && NTAPS % Cfg::TPS == 0) ? Cfg::TPS : 1;
   constexpr int HALO_W = (KS == 3) ? T3_HW : T3_TW;
+  const uint32_t w_bytes = RES ? (uint32_t)(e.ncout_tiles * e.cchunks * NTAPS) * Cfg::B_TAP : Cfg::RING_BYTES;
+  const uint32_t epi_off = (uint32_t)HB * T3_HALO + w_bytes;            // epilogue staging (4 warps x 4 KB), then the tok scratch
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < HB; ++i) { mbar_init(smem_u32(&halo_full[i]), 1); mbar_init(smem_u32(&halo_empty[i]), 1); }
+    for (int i = 0; i < T3_MAX_HB; ++i) { mbar_init(smem_u32(&halo_full[i]), 1); mbar_init(smem_u32(&halo_empty[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 128); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
     mbar_fence_init();
@@ -138,12 +153,24 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
-  if (e.tok && threadIdx.x >= 64 && threadIdx.x < 96)          // wtok [32][4] -> shared (weights: not produced by the previous launch)
-    reinterpret_cast<float4*>(base_ptr + Cfg::TOK_OFF)[threadIdx.x - 64] = __ldg(reinterpret_cast<const float4*>(e.wtok) + (threadIdx.x - 64));
+  if (EPI == EPI_TOK && threadIdx.x >= 64 && threadIdx.x < 96)          // wtok [32][4] -> shared (weights: not produced by the previous launch)
+    reinterpret_cast<float4*>(base_ptr + epi_off + 4 * 4096)[threadIdx.x - 64] = __ldg(reinterpret_cast<const float4*>(e.wtok) + (threadIdx.x - 64));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (RES && warp == 6 && lane == 0) {
+    // resident filter: every (cout tile, chunk, tap) tile, once.  Weights are not written by the previous launch, so this
+    // goes out before griddepcontrol.wait and overlaps that launch's tail under programmatic dependent launch.
+    const uint32_t bar = smem_u32(&b_full[0]);
+    mbar_expect_tx(bar, w_bytes);
+    uint32_t dst = b_ring;
+    for (int ct = 0; ct < e.ncout_tiles; ++ct)
+      for (int cc = 0; cc < e.cchunks; ++cc)
+#pragma unroll
+        for (int i = 0; i < NTAPS; ++i, dst += Cfg::B_TAP)
+          tma_load_3d(dst, &tmB, bar, Sched::tap(i) * e.Cin + cc * 32, ct * NT, 0);
+  }
   // everything above overlaps the tail of the previous launch under programmatic dependent launch; its outputs (this
   // launch's activations / residual) are only touched below
   pdl_wait();
@@ -151,14 +178,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {                                            // ---------------- halo TMA producer: hi + lo boxes per chunk
-      int g = 0;
+      int hb = 0;
+      uint32_t ephase = 1;                                      // first pass over the ring: the buffers are free
       for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
-        const Tile3 t = tile3(tile, e, NT);
+        const Tile3 t = tile3(tile, e);
         for (int cc = 0; cc < e.cchunks; ++cc) {
 #pragma unroll
-          for (int ph = 0; ph < NPH; ++ph, ++g) {
-            const int hb = g % HB, use = g / HB;
-            mbar_wait(smem_u32(&halo_empty[hb]), (uint32_t)((use & 1) ^ 1));
+          for (int ph = 0; ph < NPH; ++ph) {
+            mbar_wait(smem_u32(&halo_empty[hb]), ephase);
             const uint32_t bar = smem_u32(&halo_full[hb]);
             mbar_expect_tx(bar, 2u * e.halo_plane_bytes);
             const uint32_t dst = base + (uint32_t)hb * T3_HALO;
@@ -168,15 +195,16 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
             const int c0 = (first ? cc : cc - e.cchunks0) * 32;
             tma_load_4d(dst, first ? &tmA0h : &tmA1h, bar, c0, cx, cy, t.n);
             tma_load_4d(dst + T3_PLANE, first ? &tmA0l : &tmA1l, bar, c0, cx, cy, t.n);
+            if (++hb == HB) { hb = 0; ephase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 6) {
-    if (lane == 0) {                                            // ---------------- filter TMA producer: one 3-D box [2][NT][32] per tap
+    if (!RES && lane == 0) {                                    // ---------------- filter TMA producer: one 3-D box [2][NT][32] per tap
       int step = 0;
       for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
-        const Tile3 t = tile3(tile, e, NT);
+        const Tile3 t = tile3(tile, e);
         for (int cc = 0; cc < e.cchunks; ++cc) {
 #pragma unroll
           for (int i0 = 0; i0 < NTAPS; i0 += TPS, ++step) {
@@ -187,7 +215,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
 #pragma unroll
             for (int tt = 0; tt < TPS; ++tt)
               tma_load_3d(b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)tt * Cfg::B_TAP, &tmB, bar,
-                          Sched::tap(i0 + tt) * e.Cin + cc * 32, t.n0, 0);
+                          Sched::tap(i0 + tt) * e.Cin + cc * 32, t.ct * NT, 0);
           }
         }
       }
@@ -197,11 +225,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
       constexpr uint32_t SBO = (uint32_t)HALO_W * 64u;
       int hb = 0, st = 0, it = 0;
       uint32_t hphase = 0, bphase = 0;
+      if (RES) { mbar_wait(smem_u32(&b_full[0]), 0); tc_fence_after(); }     // the whole filter has landed
       for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
         const int ab = it & 1;
         mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));    // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)ab * Cfg::ACC_COLS, d_corr = d_main + NT;
+        const uint32_t w_tile = RES ? b_ring + (uint32_t)((tile % e.ncout_tiles) * e.cchunks * NTAPS) * Cfg::B_TAP : 0u;
         for (int cc = 0; cc < e.cchunks; ++cc) {
 #pragma unroll
           for (int ph = 0; ph < NPH; ++ph) {
@@ -210,9 +240,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
             const uint32_t h_hi = base + (uint32_t)hb * T3_HALO, h_lo = h_hi + T3_PLANE;
 #pragma unroll
             for (int i0 = Sched::first(ph); i0 < Sched::first(ph + 1); i0 += TPS) {
-              mbar_wait(smem_u32(&b_full[st]), bphase);
-              tc_fence_after();
-              const uint32_t b_stage = b_ring + (uint32_t)st * Cfg::B_STAGE;
+              uint32_t b_stage;
+              if (RES) {
+                b_stage = w_tile + (uint32_t)(cc * NTAPS + i0) * Cfg::B_TAP;
+              } else {
+                mbar_wait(smem_u32(&b_full[st]), bphase);
+                tc_fence_after();
+                b_stage = b_ring + (uint32_t)st * Cfg::B_STAGE;
+              }
 #pragma unroll
               for (int tt = 0; tt < TPS; ++tt) {
                 const int i = i0 + tt;
@@ -224,8 +259,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < 2; ++k) umma_bf16(d_corr, a_l + (uint64_t)(2 * k), b_w + (uint64_t)(2 * k), Cfg::IDESC_NARROW, 1u);
               }
-              umma_commit(smem_u32(&b_empty[st]));
-              if (++st == STAGES) { st = 0; bphase ^= 1u; }
+              if (!RES) {
+                umma_commit(smem_u32(&b_empty[st]));
+                if (++st == STAGES) { st = 0; bphase ^= 1u; }
+              }
             }
             umma_commit(smem_u32(&halo_empty[hb]));
             if (++hb == HB) { hb = 0; hphase ^= 1u; }
@@ -235,55 +272,56 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
       }
     }
   } else if (warp < 6) {                                        // ---------------- epilogue (warps 2..5)
-    // Thread = accumulator row (pixel).  Every 32-channel slab goes through a per-warp shared-memory transpose so that
-    // the global accesses are 8 lanes per pixel row (whole 128-byte lines for fp32, 64-byte segments per split16 plane).
+    // Thread = accumulator row (pixel).  Every 32-channel slab goes through a per-warp shared-memory transpose so that the
+    // global accesses are 4 lanes x 8 channels per pixel row: whole 128-byte lines of an fp32 tensor, 64-byte segments of
+    // each split16 plane, 16 bytes per lane either way, 8 pixel rows per instruction.
     const int q = warp & 3;
-    float* stage = reinterpret_cast<float*>(base_ptr + Cfg::EPI_OFF + (size_t)q * 4096);   // [32 rows][8 chunks ^ (row & 7)][4]
-    const float* wtok_s = reinterpret_cast<const float*>(base_ptr + Cfg::TOK_OFF);        // [32][4]
-    float* tokred = reinterpret_cast<float*>(base_ptr + Cfg::TOK_OFF + 512);              // [4 warps][4 tokens][34]
-    const int c8 = lane & 7, r8 = lane >> 3;
+    float* stage = reinterpret_cast<float*>(base_ptr + epi_off + (size_t)q * 4096);        // [32 rows][8 chunks ^ (row & 7)][4]
+    const float* wtok_s = reinterpret_cast<const float*>(base_ptr + epi_off + 4 * 4096);   // [32][4]
+    float* tokred = reinterpret_cast<float*>(base_ptr + epi_off + 4 * 4096 + 512);         // [4 warps][4 tokens][34]
+    const int c4 = lane & 3, r4 = lane >> 2;                    // lane -> (8-channel group, row within a group of 8)
+    constexpr int NSLAB = NT / 32;
+    const char* resb = reinterpret_cast<const char*>(e.res);
     int it = 0;
     for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
-      const Tile3 t = tile3(tile, e, NT);
+      const Tile3 t = tile3(tile, e);
+      const int n0 = t.ct * NT;
+      size_t rowoff[4];                                          // element offset of (pixel, channel group) for this lane's 4 rows
+      bool ok[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int mm = q * 32 + g * 8 + r4;
+        const int oy = t.oy0 + mm / T3_TW, ox = t.ox0 + mm % T3_TW;
+        ok[g] = (oy < e.OH) && (ox < e.OW);
+        rowoff[g] = e.ps ? ((size_t)(t.n * 2 * e.OH + 2 * oy) * (2 * e.OW) + 2 * ox) * 32 + c4 * 8
+                         : ((size_t)(t.n * e.OH + oy) * e.OW + ox) * e.Cout + n0 + c4 * 8;
+      }
+      // residual of slab j: two 16-byte loads per row, raw (converted only when added, so that they stay in flight under
+      // the accumulator wait, the TMEM loads and the transpose).  fp32: the two float4 of the 8 channels; split16: hi, lo.
+      uint4 ra[4], rb[4];
+      auto load_res = [&](int j) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          ra[g] = make_uint4(0u, 0u, 0u, 0u); rb[g] = ra[g];
+          if (ok[g]) {
+            const size_t o = rowoff[g] + (size_t)j * 32;
+            if (e.res_split) { ra[g] = ldg16(resb + o * 2); rb[g] = ldg16(resb + (o + (size_t)e.res_plane) * 2); }
+            else             { ra[g] = ldg16(resb + o * 4); rb[g] = ldg16(resb + o * 4 + 16); }
+          }
+        }
+      };
+      if (e.res) load_res(0);
       const int ab = it & 1;
       mbar_wait(smem_u32(&acc_full[ab]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      size_t rowoff[8];                                          // element offset of (pixel, channel c8*4) for this lane's 8 rows
-      bool ok[8];
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int mm = q * 32 + g * 4 + r8;
-        const int oy = t.oy0 + mm / T3_TW, ox = t.ox0 + mm % T3_TW;
-        ok[g] = (oy < e.OH) && (ox < e.OW);
-        rowoff[g] = e.ps ? ((size_t)(t.n * 2 * e.OH + 2 * oy) * (2 * e.OW) + 2 * ox) * 32 + c8 * 4
-                         : ((size_t)(t.n * e.OH + oy) * e.OW + ox) * e.Cout + t.n0 + c8 * 4;
-      }
 #pragma unroll 1
-      for (int j = 0; j < NT / 32; ++j) {
-        float4 rr[8];                                            // residual reads first: they land under the TMEM load + transpose
-        if (e.res) {
-          if (e.res_split) {
-            const uint2* rh = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(e.res));
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              if (ok[g]) {
-                const size_t o = rowoff[g] + j * 32;
-                const uint2 h = __ldg(rh + (o >> 2)), l = __ldg(rh + ((o + (size_t)e.res_plane) >> 2));
-                rr[g] = join4(h, l);
-              } else rr[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          } else {
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              rr[g] = ok[g] ? ldg4(reinterpret_cast<const float*>(e.res) + rowoff[g] + j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias) bia = ldg4(e.bias + t.n0 + j * 32 + c8 * 4);
+      for (int j = 0; j < NSLAB; ++j) {
+        float4 bia0 = make_float4(0.f, 0.f, 0.f, 0.f), bia1 = bia0;
+        if (e.bias) { bia0 = ldg4(e.bias + n0 + j * 32 + c4 * 8); bia1 = ldg4(e.bias + n0 + j * 32 + c4 * 8 + 4); }
         uint32_t v[32], u[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACC_COLS + j * 32), v);
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACC_COLS + NT + j * 32), u);
-        if (j == NT / 32 - 1) {                                  // accumulator fully read: hand it back to the MMA warp
+        if (j == NSLAB - 1) {                                    // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive_local(smem_u32(&acc_empty[ab]));
         }
@@ -291,7 +329,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           float x = fmaf(__uint_as_float(u[c]), 1.0f / 2048.0f, __uint_as_float(v[c]));
-          if (e.tok) {                                           // squeeze: no bias, ReLU; logits from the ReLU-ed value
+          if (EPI == EPI_TOK) {                                  // squeeze: no bias, ReLU; logits from the ReLU-ed value
             x = fmaxf(x, 0.f);
             const float4 wt = *reinterpret_cast<const float4*>(wtok_s + c * 4);
             tl[0] = fmaf(x, wt.x, tl[0]); tl[1] = fmaf(x, wt.y, tl[1]); tl[2] = fmaf(x, wt.z, tl[2]); tl[3] = fmaf(x, wt.w, tl[3]);
@@ -299,33 +337,45 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
           v[c] = __float_as_uint(x);
         }
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4)
-          *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
-              make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]), __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+        for (int k4 = 0; k4 < 8; ++k4)
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((k4 ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(v[k4 * 4]), __uint_as_float(v[k4 * 4 + 1]), __uint_as_float(v[k4 * 4 + 2]), __uint_as_float(v[k4 * 4 + 3]));
         __syncwarp();
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int r = g * 4 + r8;
-          float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((c8 ^ (r & 7)) << 2));
-          o.x += bia.x; o.y += bia.y; o.z += bia.z; o.w += bia.w;
-          if (e.res) { o.x += rr[g].x; o.y += rr[g].y; o.z += rr[g].z; o.w += rr[g].w; }
-          if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          if (!ok[g]) continue;
-          if (e.out_split) {
-            uint2 h, l;
-            split4(o, h, l);
-            uint2* oh = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(e.out));
-            const size_t off = rowoff[g] + j * 32;
-            oh[off >> 2] = h;
-            oh[(off + (size_t)e.out_plane) >> 2] = l;
-          } else {
-            // pixel-shuffle store: slab j = (dy, dx) lands on output pixel (2oy + dy, 2ox + dx), 32 channels each
-            float* ob = reinterpret_cast<float*>(e.out);
-            float* op = e.ps ? ob + rowoff[g] + ((size_t)(j >> 1) * (2 * e.OW) + (j & 1)) * 32 : ob + rowoff[g] + j * 32;
-            st4(op, o);
+        for (int g = 0; g < 4; ++g) {
+          const int r = g * 8 + r4;
+          float4 o0 = *reinterpret_cast<const float4*>(stage + r * 32 + (((2 * c4) ^ (r & 7)) << 2));
+          float4 o1 = *reinterpret_cast<const float4*>(stage + r * 32 + (((2 * c4 + 1) ^ (r & 7)) << 2));
+          o0.x += bia0.x; o0.y += bia0.y; o0.z += bia0.z; o0.w += bia0.w;
+          o1.x += bia1.x; o1.y += bia1.y; o1.z += bia1.z; o1.w += bia1.w;
+          if (e.res) {
+            float4 x0, x1;
+            if (e.res_split) join8(ra[g], rb[g], x0, x1); else { x0 = as_f4(ra[g]); x1 = as_f4(rb[g]); }
+            o0.x += x0.x; o0.y += x0.y; o0.z += x0.z; o0.w += x0.w;
+            o1.x += x1.x; o1.y += x1.y; o1.z += x1.z; o1.w += x1.w;
+          }
+          if (e.relu) {
+            o0.x = fmaxf(o0.x, 0.f); o0.y = fmaxf(o0.y, 0.f); o0.z = fmaxf(o0.z, 0.f); o0.w = fmaxf(o0.w, 0.f);
+            o1.x = fmaxf(o1.x, 0.f); o1.y = fmaxf(o1.y, 0.f); o1.z = fmaxf(o1.z, 0.f); o1.w = fmaxf(o1.w, 0.f);
+          }
+          if (ok[g]) {
+            if (EPI == EPI_SPLIT || (EPI == EPI_TOK && e.out_split)) {
+              uint4 h, l;
+              split8(o0, o1, h, l);
+              uint16_t* o16 = reinterpret_cast<uint16_t*>(e.out);
+              const size_t off = rowoff[g] + (size_t)j * 32;
+              *reinterpret_cast<uint4*>(o16 + off) = h;
+              *reinterpret_cast<uint4*>(o16 + off + (size_t)e.out_plane) = l;
+            } else {
+              // pixel-shuffle store: slab j = (dy, dx) lands on output pixel (2oy + dy, 2ox + dx), 32 channels each
+              float* ob = reinterpret_cast<float*>(e.out);
+              float* op = e.ps ? ob + rowoff[g] + ((size_t)(j >> 1) * (2 * e.OW) + (j & 1)) * 32 : ob + rowoff[g] + (size_t)j * 32;
+              st4(op, o0); st4(op + 4, o1);
+            }
           }
         }
-        if (e.tok) {
+        if (e.res && j + 1 < NSLAB) load_res(j + 1);            // next slab's residual: in flight under its TMEM loads
+        if (EPI == EPI_TOK) {
           // per-warp online-softmax partials over this warp's 32 pixels (rows still in `stage`), then merged per tile:
           //   m_l = max_p a_pl ; s_l = sum_p exp(a_pl - m_l) ; t_l[c] = sum_p exp(a_pl - m_l) xs_p[c]
           const int mm = q * 32 + lane;
@@ -465,14 +515,16 @@ int filt_map(CUtensorMap* out, const void* ptr, int K, int Cout, long long plane
   return 0;
 }
 
-template <int NT, int KS, int SD>
-int launch3k(const CUtensorMap* A, const CUtensorMap& Bm, const T3Args& e, dim3 grid, cudaStream_t s) {
-  using Cfg = T3Cfg<NT>;
-  auto kern = conv_tc3_kernel<NT, KS, SD>;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+constexpr uint32_t T3_SMEM_MAX = 232448 - 1024;         // 227 KB opt-in limit minus the static shared memory (barriers)
+
+template <int NT, int KS, int SD, int EPI, bool RES>
+int launch3k(const CUtensorMap* A, const CUtensorMap& Bm, const T3Args& e, uint32_t smem, dim3 grid, cudaStream_t s) {
+  using Cfg = T3Cfg<NT, RES>;
+  auto kern = conv_tc3_kernel<NT, KS, SD, EPI, RES>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM_MAX);
   if (err != cudaSuccess) return (int)err;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(Cfg::THREADS, 1, 1); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+  cfg.gridDim = grid; cfg.blockDim = dim3(Cfg::THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[1];
   cfg.attrs = at; cfg.numAttrs = dh_pdl_attr(at);
   err = cudaLaunchKernelEx(&cfg, kern, A[0], A[1], A[2], A[3], Bm, e);
@@ -480,10 +532,20 @@ int launch3k(const CUtensorMap* A, const CUtensorMap& Bm, const T3Args& e, dim3 
   DH_CHECK_LAUNCH();
   return 0;
 }
-template <int NT>
-int launch3(const CUtensorMap* A, const CUtensorMap& Bm, const T3Args& e, int ks, int stride, dim3 grid, cudaStream_t s) {
-  if (stride == 2) return ks == 3 ? launch3k<NT, 3, 2>(A, Bm, e, grid, s) : launch3k<NT, 1, 2>(A, Bm, e, grid, s);
-  return ks == 3 ? launch3k<NT, 3, 1>(A, Bm, e, grid, s) : launch3k<NT, 1, 1>(A, Bm, e, grid, s);
+// the instantiations the network uses: tok = 1x1 / NT 32; stride 2 only with a split16 output (layer2.0); everything else
+// by (NT, K) with fp32 or split16 output
+template <int NT, bool RES>
+int launch3(const CUtensorMap* A, const CUtensorMap& Bm, const T3Args& e, int ks, int stride, int epi, uint32_t smem, dim3 grid, cudaStream_t s) {
+  if (epi == EPI_TOK) {
+    if constexpr (NT == 32) return launch3k<32, 1, 1, EPI_TOK, RES>(A, Bm, e, smem, grid, s);
+    return DH_E_SHAPE;
+  }
+  if (stride == 2) {
+    if (epi == EPI_SPLIT) return ks == 3 ? launch3k<NT, 3, 2, EPI_SPLIT, RES>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 2, EPI_SPLIT, RES>(A, Bm, e, smem, grid, s);
+    return ks == 3 ? launch3k<NT, 3, 2, EPI_F32, RES>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 2, EPI_F32, RES>(A, Bm, e, smem, grid, s);
+  }
+  if (epi == EPI_SPLIT) return ks == 3 ? launch3k<NT, 3, 1, EPI_SPLIT, RES>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 1, EPI_SPLIT, RES>(A, Bm, e, smem, grid, s);
+  return ks == 3 ? launch3k<NT, 3, 1, EPI_F32, RES>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 1, EPI_F32, RES>(A, Bm, e, smem, grid, s);
 }
 }  // namespace
 
@@ -527,17 +589,35 @@ int dh_launch_conv_tc3(const Conv3Args& a, cudaStream_t s) {
   e.ncout_tiles = a.Cout / NT;
   e.tiles_per_img = e.tilesX * e.tilesY;
   e.ntiles = e.tiles_per_img * a.N * e.ncout_tiles;
-  e.res_split = a.res_split; e.out_split = a.out_split; e.tok = a.tok;
+  e.res_split = a.res_split; e.out_split = a.out_split;
   e.res_plane = a.res_plane ? a.res_plane : (long long)a.N * e.OH * e.OW * a.Cout;
   e.out_plane = a.out_plane ? a.out_plane : (long long)a.N * e.OH * e.OW * a.Cout;
   e.halo_plane_bytes = (uint32_t)(hw * hh * 64);
+  const int epi = a.tok ? EPI_TOK : (a.out_split ? EPI_SPLIT : EPI_F32);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);            // persistent: one CTA per SM
+  // resident filter when the whole [h_w ; l_w] image fits next to two halo buffers, and every CTA walks enough tiles to
+  // amortise loading it (otherwise the streaming ring, which starts the first MMA after one stage instead of the whole image)
+  const uint32_t w_bytes = (uint32_t)K * (uint32_t)a.Cout * 4u;            // = ncout_tiles * cchunks * taps * B_TAP
+  const uint32_t fixed = 4 * 4096 + 512 + 4 * 4 * 34 * 4 + 1024;
+  static const bool env_stream = [] { const char* v = getenv("DAHITRA_TC3_STREAM"); return v && v[0] == '1'; }();   // A/B switch
+  const bool res_ok = w_bytes + 2 * T3_HALO + fixed <= T3_SMEM_MAX && !a.force_stream && !env_stream && e.ntiles >= 2 * (int)grid.x;
+  if (res_ok) {
+    int hb = (int)((T3_SMEM_MAX - fixed - w_bytes) / T3_HALO);
+    e.hb = hb > T3_MAX_HB ? T3_MAX_HB : hb;
+    const uint32_t smem = (uint32_t)e.hb * T3_HALO + w_bytes + fixed;
+    switch (NT) {
+      case 128: return launch3<128, true>(A, Bm, e, a.K, a.stride, epi, smem, grid, s);
+      case 64: return launch3<64, true>(A, Bm, e, a.K, a.stride, epi, smem, grid, s);
+      default: return launch3<32, true>(A, Bm, e, a.K, a.stride, epi, smem, grid, s);
+    }
+  }
+  e.hb = T3_MAX_HB;
   switch (NT) {
-    case 128: return launch3<128>(A, Bm, e, a.K, a.stride, grid, s);
-    case 64: return launch3<64>(A, Bm, e, a.K, a.stride, grid, s);
-    default: return launch3<32>(A, Bm, e, a.K, a.stride, grid, s);
+    case 128: return launch3<128, false>(A, Bm, e, a.K, a.stride, epi, T3_MAX_HB * T3_HALO + T3Cfg<128, false>::RING_BYTES + fixed, grid, s);
+    case 64: return launch3<64, false>(A, Bm, e, a.K, a.stride, epi, T3_MAX_HB * T3_HALO + T3Cfg<64, false>::RING_BYTES + fixed, grid, s);
+    default: return launch3<32, false>(A, Bm, e, a.K, a.stride, epi, T3_MAX_HB * T3_HALO + T3Cfg<32, false>::RING_BYTES + fixed, grid, s);
   }
 }

@@ -394,30 +394,52 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   for (int q = 0; q < 8; ++q)
     *reinterpret_cast<float4*>(io + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(xr[q * 4], xr[q * 4 + 1], xr[q * 4 + 2], xr[q * 4 + 3]);
   __syncwarp();
+  if (out_split_plane) {
+    // split16 planes for conv_tc3.cu (hi = f16(o), lo = f16(2^11 (o - hi))): 4 lanes x 8 channels per pixel row, 16 bytes per
+    // lane and plane
+    const int c4 = lane & 3, r4 = lane >> 2;
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const int r = g * 4 + r8, pr = pw0 + r;
-    if (pr < npix) {
-      float4 o = *reinterpret_cast<const float4*>(io + r * 32 + ((c8 ^ (r & 7)) << 2));
-      if (skip) {
-        const int py = pr / w, px = pr - py * w;
-        const float* sp = (skip_up == 2)
-            ? skip + (((size_t)img * (npix / w / 2) + (py >> 1)) * (w >> 1) + (px >> 1)) * 32
-            : skip + ((size_t)img * npix + pr) * 32;
-        const float4 v = ldg4(sp + c8 * 4);
-        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+    for (int g = 0; g < 4; ++g) {
+      const int r = g * 8 + r4, pr = pw0 + r;
+      if (pr < npix) {
+        float4 o0 = *reinterpret_cast<const float4*>(io + r * 32 + (((2 * c4) ^ (r & 7)) << 2));
+        float4 o1 = *reinterpret_cast<const float4*>(io + r * 32 + (((2 * c4 + 1) ^ (r & 7)) << 2));
+        if (skip) {
+          const int py = pr / w, px = pr - py * w;
+          const float* sp = (skip_up == 2)
+              ? skip + (((size_t)img * (npix / w / 2) + (py >> 1)) * (w >> 1) + (px >> 1)) * 32
+              : skip + ((size_t)img * npix + pr) * 32;
+          const float4 v0 = ldg4(sp + c4 * 8), v1 = ldg4(sp + c4 * 8 + 4);
+          o0.x += v0.x; o0.y += v0.y; o0.z += v0.z; o0.w += v0.w;
+          o1.x += v1.x; o1.y += v1.y; o1.z += v1.z; o1.w += v1.w;
+        }
+        uint4 hi, lo;
+        hi.x = pack_f16x2_sat(o0.x, o0.y); hi.y = pack_f16x2_sat(o0.z, o0.w); hi.z = pack_f16x2_sat(o1.x, o1.y); hi.w = pack_f16x2_sat(o1.z, o1.w);
+        lo.x = pack_f16x2_sat((o0.x - f16_lo(hi.x)) * 2048.f, (o0.y - f16_hi(hi.x)) * 2048.f);
+        lo.y = pack_f16x2_sat((o0.z - f16_lo(hi.y)) * 2048.f, (o0.w - f16_hi(hi.y)) * 2048.f);
+        lo.z = pack_f16x2_sat((o1.x - f16_lo(hi.z)) * 2048.f, (o1.y - f16_hi(hi.z)) * 2048.f);
+        lo.w = pack_f16x2_sat((o1.z - f16_lo(hi.w)) * 2048.f, (o1.w - f16_hi(hi.w)) * 2048.f);
+        uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
+        const size_t off = ((size_t)img * npix + pr) * 32 + c4 * 8;
+        *reinterpret_cast<uint4*>(o16 + off) = hi;
+        *reinterpret_cast<uint4*>(o16 + off + (size_t)out_split_plane) = lo;
       }
-      const size_t off = ((size_t)img * npix + pr) * 32 + c8 * 4;
-      if (out_split_plane) {             // split16 planes for conv_tc3.cu: hi = f16(o), lo = f16(2^11 (o - hi))
-        uint2 hi, lo;
-        hi.x = pack_f16x2_sat(o.x, o.y); hi.y = pack_f16x2_sat(o.z, o.w);
-        lo.x = pack_f16x2_sat((o.x - f16_lo(hi.x)) * 2048.f, (o.y - f16_hi(hi.x)) * 2048.f);
-        lo.y = pack_f16x2_sat((o.z - f16_lo(hi.y)) * 2048.f, (o.w - f16_hi(hi.y)) * 2048.f);
-        uint2* o16 = reinterpret_cast<uint2*>(out);
-        o16[off >> 2] = hi;
-        o16[(off + (size_t)out_split_plane) >> 2] = lo;
-      } else {
-        st4(out + off, o);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int r = g * 4 + r8, pr = pw0 + r;
+      if (pr < npix) {
+        float4 o = *reinterpret_cast<const float4*>(io + r * 32 + ((c8 ^ (r & 7)) << 2));
+        if (skip) {
+          const int py = pr / w, px = pr - py * w;
+          const float* sp = (skip_up == 2)
+              ? skip + (((size_t)img * (npix / w / 2) + (py >> 1)) * (w >> 1) + (px >> 1)) * 32
+              : skip + ((size_t)img * npix + pr) * 32;
+          const float4 v = ldg4(sp + c8 * 4);
+          o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+        }
+        st4(out + ((size_t)img * npix + pr) * 32 + c8 * 4, o);
       }
     }
   }

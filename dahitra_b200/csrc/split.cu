@@ -2,9 +2,10 @@
 // FP16 planes of the tensor's shape, the lo plane `n` elements after the hi plane):
 //   * fp32 <-> split16 conversion (block tests, and the boundary of code that keeps fp32 tensors),
 //   * MaxPool2d(3, 2, 1) on a split16 NHWC tensor (reference models/networks.py:1123,1128 — the same module applied after the
-//     stem and after layer2).  max commutes with the monotone map a -> (hi, lo) only up to ties in hi, so the pool
-//     compares the reconstructed values hi + 2^-11 lo and re-splits the winner (which reproduces its own planes exactly).
+//     stem and after layer2): the order of the values is the lexicographic order of their (hi, lo) pairs, so the pool runs
+//     on packed halves and copies the winner's planes.
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 using namespace dhtc;
 
@@ -45,6 +46,16 @@ __global__ void __launch_bounds__(256) split_unpack_kernel(const uint16_t* __res
   }
 }
 
+// lexicographic max on (hi, lo) pairs of packed halves: a > b  <=>  hi_a > hi_b, or hi_a == hi_b and lo_a > lo_b (|lo| / 2048 never
+// exceeds half an ulp of hi), so the pool needs no conversion to fp32 and no re-split: 7 packed instructions per two elements
+__device__ __forceinline__ void lexmax2(uint32_t& mh, uint32_t& ml, uint32_t h, uint32_t l) {
+  const __half2 a = *reinterpret_cast<const __half2*>(&h), m = *reinterpret_cast<const __half2*>(&mh);
+  const uint32_t gt = __hgt2_mask(a, m), eq = __heq2_mask(a, m);
+  const __half2 lm = __hmax2(*reinterpret_cast<const __half2*>(&l), *reinterpret_cast<const __half2*>(&ml));
+  ml = (gt & l) | (eq & *reinterpret_cast<const uint32_t*>(&lm)) | (~(gt | eq) & ml);
+  mh = (gt & h) | (~gt & mh);
+}
+
 // one thread = 8 channels of one output pixel (16-byte loads / stores per plane)
 __global__ void __launch_bounds__(256)
 maxpool_split_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, uint16_t* __restrict__ out) {
@@ -52,37 +63,30 @@ maxpool_split_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C
   const size_t total = (size_t)N * OH * OW * C8, plane_in = (size_t)N * H * W * C, plane_out = (size_t)N * OH * OW * C;
   pdl_wait();
   pdl_launch_dependents();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    size_t p = i / C8;
-    const int ox = (int)(p % OW); p /= OW;
-    const int oy = (int)(p % OH);
-    const int n = (int)(p / OH);
-    float m[8];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  size_t p = i / C8;
+  const int ox = (int)(p % OW); p /= OW;
+  const int oy = (int)(p % OH);
+  const int n = (int)(p / OH);
+  uint4 mh = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u), ml = mh;      // -inf
 #pragma unroll
-    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int iy = 2 * oy + dy;
+    if (iy < 0 || iy >= H) continue;
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int iy = 2 * oy + dy;
-      if (iy < 0 || iy >= H) continue;
-#pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int ix = 2 * ox + dx;
-        if (ix < 0 || ix >= W) continue;
-        const size_t o = (((size_t)n * H + iy) * W + ix) * C + c8 * 8;
-        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(in + o)), lo = __ldg(reinterpret_cast<const uint4*>(in + plane_in + o));
-        float v[8];
-        sp_join8(hi, lo, v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
-      }
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ix = 2 * ox + dx;
+      if (ix < 0 || ix >= W) continue;
+      const size_t o = (((size_t)n * H + iy) * W + ix) * C + c8 * 8;
+      const uint4 hi = __ldg(reinterpret_cast<const uint4*>(in + o)), lo = __ldg(reinterpret_cast<const uint4*>(in + plane_in + o));
+      lexmax2(mh.x, ml.x, hi.x, lo.x); lexmax2(mh.y, ml.y, hi.y, lo.y); lexmax2(mh.z, ml.z, hi.z, lo.z); lexmax2(mh.w, ml.w, hi.w, lo.w);
     }
-    uint4 hi, lo;
-    sp_split8(m, hi, lo);
-    const size_t o = (((size_t)n * OH + oy) * OW + ox) * C + c8 * 8;
-    *reinterpret_cast<uint4*>(out + o) = hi;
-    *reinterpret_cast<uint4*>(out + plane_out + o) = lo;
   }
+  const size_t o = (((size_t)n * OH + oy) * OW + ox) * C + c8 * 8;
+  *reinterpret_cast<uint4*>(out + o) = mh;
+  *reinterpret_cast<uint4*>(out + plane_out + o) = ml;
 }
 
 int grid_for(size_t items) {
@@ -116,7 +120,7 @@ int dh_launch_maxpool_split(const void* in, int N, int H, int W, int C, void* ou
   DH_REQUIRE(dh_aligned16(in) && dh_aligned16(out), DH_E_ALIGN);
   const size_t items = (size_t)N * (H / 2) * (W / 2) * (C / 8);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid_for(items)); cfg.blockDim = dim3(256); cfg.stream = s;
+  cfg.gridDim = dim3((unsigned)((items + 255) / 256)); cfg.blockDim = dim3(256); cfg.stream = s;
   cudaLaunchAttribute at[1];
   cfg.attrs = at; cfg.numAttrs = dh_pdl_attr(at);
   const cudaError_t e = cudaLaunchKernelEx(&cfg, maxpool_split_kernel, reinterpret_cast<const uint16_t*>(in), N, H, W, C,

@@ -78,30 +78,34 @@ __device__ __forceinline__ void sk_halo_producer(const CUtensorMap* tmX, uint32_
 __device__ __forceinline__ void sk_store_slice(const float (&v)[32], float* stage, int lane, int q, int j, const SkTile& t,
                                                int OH, int OW, const float* __restrict__ bias, float* __restrict__ out,
                                                long long split_plane = 0) {
-  const int c8 = lane & 7, r8 = lane >> 3;
+  const int c4 = lane & 3, r4 = lane >> 2;              // lane -> (8-channel group, row within a group of 8): 16 bytes per lane and plane
 #pragma unroll
-  for (int c4 = 0; c4 < 8; ++c4)
-    *reinterpret_cast<float4*>(stage + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+  for (int k4 = 0; k4 < 8; ++k4)
+    *reinterpret_cast<float4*>(stage + lane * 32 + ((k4 ^ (lane & 7)) << 2)) = make_float4(v[k4 * 4], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
   __syncwarp();
-  const float4 b = ldg4(bias + j * 32 + c8 * 4);
+  const float4 b0 = ldg4(bias + j * 32 + c4 * 8), b1 = ldg4(bias + j * 32 + c4 * 8 + 4);
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const int r = g * 4 + r8, mm = q * 32 + r;             // tile pixel (py = mm / 16, px = mm % 16)
+  for (int g = 0; g < 4; ++g) {
+    const int r = g * 8 + r4, mm = q * 32 + r;             // tile pixel (py = mm / 16, px = mm % 16)
     const int oy = t.oy0 + mm / SK_TW, ox = t.ox0 + mm % SK_TW;
-    const float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((c8 ^ (r & 7)) << 2));
+    const float4 o0 = *reinterpret_cast<const float4*>(stage + r * 32 + (((2 * c4) ^ (r & 7)) << 2));
+    const float4 o1 = *reinterpret_cast<const float4*>(stage + r * 32 + (((2 * c4 + 1) ^ (r & 7)) << 2));
     if (oy < OH && ox < OW) {
-      const float4 r = make_float4(fmaxf(o.x + b.x, 0.f), fmaxf(o.y + b.y, 0.f), fmaxf(o.z + b.z, 0.f), fmaxf(o.w + b.w, 0.f));
-      const size_t off = ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32 + c8 * 4;
+      const float4 r0 = make_float4(fmaxf(o0.x + b0.x, 0.f), fmaxf(o0.y + b0.y, 0.f), fmaxf(o0.z + b0.z, 0.f), fmaxf(o0.w + b0.w, 0.f));
+      const float4 r1 = make_float4(fmaxf(o1.x + b1.x, 0.f), fmaxf(o1.y + b1.y, 0.f), fmaxf(o1.z + b1.z, 0.f), fmaxf(o1.w + b1.w, 0.f));
+      const size_t off = ((size_t)(t.n * OH + oy) * OW + ox) * 64 + j * 32 + c4 * 8;
       if (split_plane) {                 // split16 planes for conv_tc3.cu: hi = f16(r), lo = f16(2^11 (r - hi))
-        uint2 hi, lo;
-        hi.x = pack_f16x2_sat(r.x, r.y); hi.y = pack_f16x2_sat(r.z, r.w);
-        lo.x = pack_f16x2_sat((r.x - f16_lo(hi.x)) * 2048.f, (r.y - f16_hi(hi.x)) * 2048.f);
-        lo.y = pack_f16x2_sat((r.z - f16_lo(hi.y)) * 2048.f, (r.w - f16_hi(hi.y)) * 2048.f);
-        uint2* o16 = reinterpret_cast<uint2*>(out);
-        o16[off >> 2] = hi;
-        o16[(off + (size_t)split_plane) >> 2] = lo;
+        uint4 hi, lo;
+        hi.x = pack_f16x2_sat(r0.x, r0.y); hi.y = pack_f16x2_sat(r0.z, r0.w); hi.z = pack_f16x2_sat(r1.x, r1.y); hi.w = pack_f16x2_sat(r1.z, r1.w);
+        lo.x = pack_f16x2_sat((r0.x - f16_lo(hi.x)) * 2048.f, (r0.y - f16_hi(hi.x)) * 2048.f);
+        lo.y = pack_f16x2_sat((r0.z - f16_lo(hi.y)) * 2048.f, (r0.w - f16_hi(hi.y)) * 2048.f);
+        lo.z = pack_f16x2_sat((r1.x - f16_lo(hi.z)) * 2048.f, (r1.y - f16_hi(hi.z)) * 2048.f);
+        lo.w = pack_f16x2_sat((r1.z - f16_lo(hi.w)) * 2048.f, (r1.w - f16_hi(hi.w)) * 2048.f);
+        uint16_t* o16 = reinterpret_cast<uint16_t*>(out);
+        *reinterpret_cast<uint4*>(o16 + off) = hi;
+        *reinterpret_cast<uint4*>(o16 + off + (size_t)split_plane) = lo;
       } else {
-        st4(out + off, r);
+        st4(out + off, r0); st4(out + off + 4, r1);
       }
     }
   }
