@@ -73,6 +73,7 @@ struct Conv3Args {
   int tok = 0;                                       // tokenizer epilogue (1x1, Cout 32): ReLU + store + per-tile softmax partials
   const float* wtok = nullptr; float* partials = nullptr;
   int force_stream = 0;                              // 1: never keep the filter resident in shared memory (A/B tests)
+  int cg = 0;                                        // 0 = auto, 1 = single CTAs, 2 = CTA pairs (tcgen05 cta_group::2)
 };
 bool dh_conv_tc3_eligible(const Conv3Args& a);
 int dh_launch_conv_tc3(const Conv3Args& a, cudaStream_t s);

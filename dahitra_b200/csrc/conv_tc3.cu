@@ -57,16 +57,16 @@ struct T3Args {
 //              memory once per CTA and stays there while the persistent CTA walks its tiles — the L2 -> SM path
 //              (~43 B/clk per SM with every SM pulling, B300_MICROARCH "LTS throughput cap") is what bounds the
 //              streaming form on the small-K layers: layer1 re-reads 144 KB of filter for every 46 KB halo.
-template <int NT, bool RES> struct T3Cfg {
+template <int NT, bool RES, int CG = 1> struct T3Cfg {
   static constexpr int TPS = NT == 128 ? 1 : 3;                          // filter taps per ring stage (streaming form)
-  static constexpr int STAGES = RES ? 1 : (NT == 128 ? 6 : (NT == 64 ? 4 : 8));
-  static constexpr uint32_t B_TAP = 2u * NT * 64u;                       // [h_w (NT rows) ; l_w (NT rows)] x 64 B
+  static constexpr int STAGES = RES ? 1 : (NT == 128 ? 6 : (NT == 64 ? 4 : 8)) * CG;   // a CTA of a pair holds half-size tiles
+  static constexpr uint32_t B_TAP = 2u * NT * 64u / CG;                  // [h_w ; l_w] x 64 B: NT rows each, NT / 2 in a CTA of a pair
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
   static constexpr uint32_t RING_BYTES = RES ? 0u : STAGES * B_STAGE;    // RES: the filter image follows the halo buffers instead
   static constexpr uint32_t FIXED = 4 * 4096 + 512 + 4 * 4 * 34 * 4 + 1024;   // epilogue staging + tok scratch + alignment slack
   static constexpr int THREADS = 224;
   static constexpr uint32_t IDESC_WIDE = umma_idesc_f16(128, 2 * NT);
-  static constexpr uint32_t IDESC_NARROW = umma_idesc_f16(128, NT);
+  static constexpr uint32_t IDESC_NARROW = umma_idesc_f16(128 * CG, NT);
   static constexpr int ACC_COLS = 2 * NT;
   static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
 };
@@ -86,15 +86,25 @@ template <int KS, int SD> struct Tap3 {                                   // tap
 };
 
 struct Tile3 { int n, oy0, ox0, ct; };
-__device__ __forceinline__ Tile3 tile3(int tile, const T3Args& e) {
+// CG = 2: work item = (pair of consecutive M tiles, cout tile); CTA `rank` of the pair takes M tile 2 * pair + rank.  The odd
+// tile of the last pair may not exist: then n == e.N, its TMA boxes lie outside the tensor (zero fill) and its epilogue
+// stores nothing.
+__device__ __forceinline__ Tile3 tile3(int tile, const T3Args& e, int CG = 1, int rank = 0) {
   Tile3 t;
   t.ct = tile % e.ncout_tiles; tile /= e.ncout_tiles;
+  if (CG == 2) tile = 2 * tile + rank;
   const int tx = tile % e.tilesX; tile /= e.tilesX;
   const int ty = tile % e.tilesY;
   t.n = tile / e.tilesY; t.oy0 = ty * T3_TH; t.ox0 = tx * T3_TW;
   return t;
 }
 
+// (pair) issued by either CTA, completion bytes counted on `cluster_bar` (the leader's barrier)
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t cluster_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -118,12 +128,19 @@ __device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float4& 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ float4 as_f4(const uint4& u) { return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)); }
 
-template <int NT, int KS, int SD, int EPI, bool RES>
-__global__ void __launch_bounds__(T3Cfg<NT, RES>::THREADS, 1)
+// CG = 2: CTA pairs (tcgen05 cta_group::2, cluster of two).  The leader (rank 0) issues M = 256 MMAs over both CTAs' halos;
+// every B operand is split across the pair by N halves, so each CTA loads, stores and reads only half of every filter tile —
+// half the L2 -> SM filter traffic and half the B reads from shared memory per pixel.  With B split by rows the N-doubled
+// "wide" tile cannot be used (its two halves would need different partners), so the three partial products are issued as
+// three N = NT MMAs: h_a.h_w -> main; h_a.l_w, l_a.h_w -> corr — the same tensor-core cycles as wide + narrow.
+// Barriers the MMA warp waits on live in the leader and count both CTAs (the peer's TMA / threads signal them remotely);
+// the leader's commits are multicast to both CTAs' barriers.
+template <int NT, int KS, int SD, int EPI, bool RES, int CG>
+__global__ void __launch_bounds__(T3Cfg<NT, RES, CG>::THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant__ CUtensorMap tmA0l,
                 const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
                 const __grid_constant__ CUtensorMap tmB, const T3Args e) {
-  using Cfg = T3Cfg<NT, RES>;
+  using Cfg = T3Cfg<NT, RES, CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t t3_raw[];
   __shared__ __align__(8) uint64_t halo_full[T3_MAX_HB], halo_empty[T3_MAX_HB], b_full[STAGES], b_empty[STAGES], acc_full[2], acc_empty[2];
@@ -134,6 +151,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
   uint8_t* base_ptr = t3_raw + (base - smem_u32(t3_raw));
   const int HB = e.hb;
   const uint32_t b_ring = base + (uint32_t)HB * T3_HALO;                 // filter ring, or the resident filter image
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int w0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item, and the stride between items
+  const int wstep = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int pad = (KS == 3) ? 1 : 0;
   using Sched = Tap3<KS, SD>;
   constexpr int NPH = Sched::NPH;
@@ -145,31 +165,39 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < T3_MAX_HB; ++i) { mbar_init(smem_u32(&halo_full[i]), 1); mbar_init(smem_u32(&halo_empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 128 * CG); }
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
     mbar_fence_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0h) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0l) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+    else         tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+  }
   if (EPI == EPI_TOK && threadIdx.x >= 64 && threadIdx.x < 96)          // wtok [32][4] -> shared (weights: not produced by the previous launch)
     reinterpret_cast<float4*>(base_ptr + epi_off + 4 * 4096)[threadIdx.x - 64] = __ldg(reinterpret_cast<const float4*>(e.wtok) + (threadIdx.x - 64));
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                      // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (RES && warp == 6 && lane == 0) {
-    // resident filter: every (cout tile, chunk, tap) tile, once.  Weights are not written by the previous launch, so this
-    // goes out before griddepcontrol.wait and overlaps that launch's tail under programmatic dependent launch.
+    // resident filter: every (cout tile, chunk, tap) tile, once (pair: this CTA's N half of each).  Weights are not written
+    // by the previous launch, so this goes out before griddepcontrol.wait and overlaps that launch's tail under
+    // programmatic dependent launch.
     const uint32_t bar = smem_u32(&b_full[0]);
-    mbar_expect_tx(bar, w_bytes);
+    if (rank == 0) mbar_expect_tx(bar, (uint32_t)CG * w_bytes);             // pair: the leader's barrier counts both halves
+    const uint32_t lbar = (CG == 2 && rank == 1) ? mapa_u32(bar, 0) : bar;
     uint32_t dst = b_ring;
     for (int ct = 0; ct < e.ncout_tiles; ++ct)
       for (int cc = 0; cc < e.cchunks; ++cc)
 #pragma unroll
-        for (int i = 0; i < NTAPS; ++i, dst += Cfg::B_TAP)
-          tma_load_3d(dst, &tmB, bar, Sched::tap(i) * e.Cin + cc * 32, ct * NT, 0);
+        for (int i = 0; i < NTAPS; ++i, dst += Cfg::B_TAP) {
+          if (CG == 2) tma_load_3d_2sm(dst, &tmB, lbar, Sched::tap(i) * e.Cin + cc * 32, ct * NT + rank * (NT / 2), 0);
+          else         tma_load_3d(dst, &tmB, bar, Sched::tap(i) * e.Cin + cc * 32, ct * NT, 0);
+        }
   }
   // everything above overlaps the tail of the previous launch under programmatic dependent launch; its outputs (this
   // launch's activations / residual) are only touched below
@@ -180,21 +208,27 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
     if (lane == 0) {                                            // ---------------- halo TMA producer: hi + lo boxes per chunk
       int hb = 0;
       uint32_t ephase = 1;                                      // first pass over the ring: the buffers are free
-      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
-        const Tile3 t = tile3(tile, e);
+      for (int tile = w0; tile < e.ntiles; tile += wstep) {
+        const Tile3 t = tile3(tile, e, CG, rank);
         for (int cc = 0; cc < e.cchunks; ++cc) {
 #pragma unroll
           for (int ph = 0; ph < NPH; ++ph) {
             mbar_wait(smem_u32(&halo_empty[hb]), ephase);
             const uint32_t bar = smem_u32(&halo_full[hb]);
-            mbar_expect_tx(bar, 2u * e.halo_plane_bytes);
+            if (rank == 0) mbar_expect_tx(bar, (uint32_t)CG * 2u * e.halo_plane_bytes);     // pair: the leader's barrier counts both halos
             const uint32_t dst = base + (uint32_t)hb * T3_HALO;
             const int cx = SD == 1 ? t.ox0 - pad : 2 * (t.ox0 - pad) + (ph & 1);
             const int cy = SD == 1 ? t.oy0 - pad : 2 * (t.oy0 - pad) + (ph >> 1);
             const bool first = cc < e.cchunks0;
             const int c0 = (first ? cc : cc - e.cchunks0) * 32;
-            tma_load_4d(dst, first ? &tmA0h : &tmA1h, bar, c0, cx, cy, t.n);
-            tma_load_4d(dst + T3_PLANE, first ? &tmA0l : &tmA1l, bar, c0, cx, cy, t.n);
+            if (CG == 2 && rank == 1) {
+              const uint32_t lbar = mapa_u32(bar, 0);
+              tma_load_4d_2sm(dst, first ? &tmA0h : &tmA1h, lbar, c0, cx, cy, t.n);
+              tma_load_4d_2sm(dst + T3_PLANE, first ? &tmA0l : &tmA1l, lbar, c0, cx, cy, t.n);
+            } else {
+              tma_load_4d(dst, first ? &tmA0h : &tmA1h, bar, c0, cx, cy, t.n);
+              tma_load_4d(dst + T3_PLANE, first ? &tmA0l : &tmA1l, bar, c0, cx, cy, t.n);
+            }
             if (++hb == HB) { hb = 0; ephase ^= 1u; }
           }
         }
@@ -203,32 +237,37 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
   } else if (warp == 6) {
     if (!RES && lane == 0) {                                    // ---------------- filter TMA producer: one 3-D box [2][NT][32] per tap
       int step = 0;
-      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x) {
-        const Tile3 t = tile3(tile, e);
+      for (int tile = w0; tile < e.ntiles; tile += wstep) {
+        const Tile3 t = tile3(tile, e, CG, rank);
         for (int cc = 0; cc < e.cchunks; ++cc) {
 #pragma unroll
           for (int i0 = 0; i0 < NTAPS; i0 += TPS, ++step) {
             const int st = step % STAGES, round = step / STAGES;
             mbar_wait(smem_u32(&b_empty[st]), (uint32_t)((round & 1) ^ 1));
             const uint32_t bar = smem_u32(&b_full[st]);
-            mbar_expect_tx(bar, (uint32_t)TPS * Cfg::B_TAP);
+            if (rank == 0) mbar_expect_tx(bar, (uint32_t)(CG * TPS) * Cfg::B_TAP);          // pair: both halves
+            const uint32_t lbar = (CG == 2 && rank == 1) ? mapa_u32(bar, 0) : bar;
 #pragma unroll
-            for (int tt = 0; tt < TPS; ++tt)
-              tma_load_3d(b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)tt * Cfg::B_TAP, &tmB, bar,
-                          Sched::tap(i0 + tt) * e.Cin + cc * 32, t.ct * NT, 0);
+            for (int tt = 0; tt < TPS; ++tt) {
+              const uint32_t dst = b_ring + (uint32_t)st * Cfg::B_STAGE + (uint32_t)tt * Cfg::B_TAP;
+              const int kcol = Sched::tap(i0 + tt) * e.Cin + cc * 32;
+              if (CG == 2) tma_load_3d_2sm(dst, &tmB, lbar, kcol, t.ct * NT + rank * (NT / 2), 0);
+              else         tma_load_3d(dst, &tmB, bar, kcol, t.ct * NT, 0);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {                                            // ---------------- MMA issuer
+    if (lane == 0 && rank == 0) {                               // ---------------- MMA issuer (pair: the leader only)
       constexpr uint32_t SBO = (uint32_t)HALO_W * 64u;
       int hb = 0, st = 0, it = 0;
       uint32_t hphase = 0, bphase = 0;
       if (RES) { mbar_wait(smem_u32(&b_full[0]), 0); tc_fence_after(); }     // the whole filter has landed
-      for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
+      for (int tile = w0; tile < e.ntiles; tile += wstep, ++it) {
         const int ab = it & 1;
-        mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));    // epilogue drained this accumulator
+        if (CG == 2) mbar_wait_cluster(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));
+        else         mbar_wait(smem_u32(&acc_empty[ab]), (uint32_t)(((it >> 1) & 1) ^ 1));    // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)ab * Cfg::ACC_COLS, d_corr = d_main + NT;
         const uint32_t w_tile = RES ? b_ring + (uint32_t)((tile % e.ncout_tiles) * e.cchunks * NTAPS) * Cfg::B_TAP : 0u;
@@ -254,21 +293,32 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
                 const uint32_t px = (uint32_t)Sched::shift_px(Sched::tap(i), HALO_W) * 64u;      // compile-time after unrolling
                 const uint64_t a_h = umma_desc_sw64(h_hi + px, SBO), a_l = umma_desc_sw64(h_lo + px, SBO);
                 const uint64_t b_w = umma_desc_sw64(b_stage + (uint32_t)tt * Cfg::B_TAP, 512u);
+                if (CG == 2) {
+                  // this CTA's tile = [h_w half (NT/2 rows) ; l_w half]; the pair's halves form the N = NT operands
+                  const uint64_t b_l = umma_desc_sw64(b_stage + (uint32_t)tt * Cfg::B_TAP + (NT / 2) * 64u, 512u);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) umma_bf16(d_main, a_h + (uint64_t)(2 * k), b_w + (uint64_t)(2 * k), Cfg::IDESC_WIDE, (cc | i | k) ? 1u : 0u);
+                  for (int k = 0; k < 2; ++k) umma_bf16_2sm(d_main, a_h + (uint64_t)(2 * k), b_w + (uint64_t)(2 * k), Cfg::IDESC_NARROW, (cc | i | k) ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) umma_bf16(d_corr, a_l + (uint64_t)(2 * k), b_w + (uint64_t)(2 * k), Cfg::IDESC_NARROW, 1u);
+                  for (int k = 0; k < 2; ++k) umma_bf16_2sm(d_corr, a_h + (uint64_t)(2 * k), b_l + (uint64_t)(2 * k), Cfg::IDESC_NARROW, (cc | i | k) ? 1u : 0u);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) umma_bf16_2sm(d_corr, a_l + (uint64_t)(2 * k), b_w + (uint64_t)(2 * k), Cfg::IDESC_NARROW, 1u);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) umma_bf16(d_main, a_h + (uint64_t)(2 * k), b_w + (uint64_t)(2 * k), Cfg::IDESC_WIDE, (cc | i | k) ? 1u : 0u);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) umma_bf16(d_corr, a_l + (uint64_t)(2 * k), b_w + (uint64_t)(2 * k), Cfg::IDESC_NARROW, 1u);
+                }
               }
               if (!RES) {
-                umma_commit(smem_u32(&b_empty[st]));
+                if (CG == 2) umma_commit_2sm(smem_u32(&b_empty[st])); else umma_commit(smem_u32(&b_empty[st]));
                 if (++st == STAGES) { st = 0; bphase ^= 1u; }
               }
             }
-            umma_commit(smem_u32(&halo_empty[hb]));
+            if (CG == 2) umma_commit_2sm(smem_u32(&halo_empty[hb])); else umma_commit(smem_u32(&halo_empty[hb]));
             if (++hb == HB) { hb = 0; hphase ^= 1u; }
           }
         }
-        umma_commit(smem_u32(&acc_full[ab]));
+        if (CG == 2) umma_commit_2sm(smem_u32(&acc_full[ab])); else umma_commit(smem_u32(&acc_full[ab]));
       }
     }
   } else if (warp < 6) {                                        // ---------------- epilogue (warps 2..5)
@@ -283,8 +333,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
     constexpr int NSLAB = NT / 32;
     const char* resb = reinterpret_cast<const char*>(e.res);
     int it = 0;
-    for (int tile = blockIdx.x; tile < e.ntiles; tile += gridDim.x, ++it) {
-      const Tile3 t = tile3(tile, e);
+    for (int tile = w0; tile < e.ntiles; tile += wstep, ++it) {
+      const Tile3 t = tile3(tile, e, CG, rank);
       const int n0 = t.ct * NT;
       size_t rowoff[4];                                          // element offset of (pixel, channel group) for this lane's 4 rows
       bool ok[4];
@@ -292,7 +342,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
       for (int g = 0; g < 4; ++g) {
         const int mm = q * 32 + g * 8 + r4;
         const int oy = t.oy0 + mm / T3_TW, ox = t.ox0 + mm % T3_TW;
-        ok[g] = (oy < e.OH) && (ox < e.OW);
+        ok[g] = (oy < e.OH) && (ox < e.OW) && (t.n < e.N);
         rowoff[g] = e.ps ? ((size_t)(t.n * 2 * e.OH + 2 * oy) * (2 * e.OW) + 2 * ox) * 32 + c4 * 8
                          : ((size_t)(t.n * e.OH + oy) * e.OW + ox) * e.Cout + n0 + c4 * 8;
       }
@@ -323,7 +373,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::ACC_COLS + NT + j * 32), u);
         if (j == NSLAB - 1) {                                    // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
-          mbar_arrive_local(smem_u32(&acc_empty[ab]));
+          if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[ab]), 0));
+          else         mbar_arrive_local(smem_u32(&acc_empty[ab]));
         }
         float tl[4] = {0.f, 0.f, 0.f, 0.f};                      // TOK: this pixel's four token logits
 #pragma unroll
@@ -379,7 +430,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
           // per-warp online-softmax partials over this warp's 32 pixels (rows still in `stage`), then merged per tile:
           //   m_l = max_p a_pl ; s_l = sum_p exp(a_pl - m_l) ; t_l[c] = sum_p exp(a_pl - m_l) xs_p[c]
           const int mm = q * 32 + lane;
-          const bool valid = (t.oy0 + mm / T3_TW < e.OH) && (t.ox0 + mm % T3_TW < e.OW);
+          const bool valid = (t.oy0 + mm / T3_TW < e.OH) && (t.ox0 + mm % T3_TW < e.OW) && (t.n < e.N);
           float ew[4];
 #pragma unroll
           for (int l = 0; l < 4; ++l) {
@@ -413,10 +464,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
               S = fmaf(tokred[(w4 * 4 + l) * 34 + 1], sc, S);
               T = fmaf(tokred[(w4 * 4 + l) * 34 + 2 + lane], sc, T);
             }
-            const int tile_in_img = (tile / e.ncout_tiles) % e.tiles_per_img;
-            float* pp = e.partials + (((size_t)t.n * e.tiles_per_img + tile_in_img) * 4 + l) * 34;
-            if (lane == 0) { pp[0] = M; pp[1] = S; }
-            pp[2 + lane] = T;
+            const int mtile = CG == 2 ? 2 * (tile / e.ncout_tiles) + rank : tile / e.ncout_tiles;
+            float* pp = e.partials + (((size_t)t.n * e.tiles_per_img + mtile % e.tiles_per_img) * 4 + l) * 34;
+            if (t.n < e.N) {
+              if (lane == 0) { pp[0] = M; pp[1] = S; }
+              pp[2 + lane] = T;
+            }
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");          // tokred is free for the next tile
         }
@@ -426,9 +479,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                      // the peer's shared memory / barriers stay alive until both are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -517,35 +572,48 @@ int filt_map(CUtensorMap* out, const void* ptr, int K, int Cout, long long plane
 
 constexpr uint32_t T3_SMEM_MAX = 232448 - 1024;         // 227 KB opt-in limit minus the static shared memory (barriers)
 
-template <int NT, int KS, int SD, int EPI, bool RES>
+template <int NT, int KS, int SD, int EPI, bool RES, int CG>
 int launch3k(const CUtensorMap* A, const CUtensorMap& Bm, const T3Args& e, uint32_t smem, dim3 grid, cudaStream_t s) {
-  using Cfg = T3Cfg<NT, RES>;
-  auto kern = conv_tc3_kernel<NT, KS, SD, EPI, RES>;
+  using Cfg = T3Cfg<NT, RES, CG>;
+  auto kern = conv_tc3_kernel<NT, KS, SD, EPI, RES, CG>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM_MAX);
   if (err != cudaSuccess) return (int)err;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(Cfg::THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  cfg.attrs = at; cfg.numAttrs = dh_pdl_attr(at);
+  cudaLaunchAttribute at[2];
+  int na = dh_pdl_attr(at);
+  if (CG == 2) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
   err = cudaLaunchKernelEx(&cfg, kern, A[0], A[1], A[2], A[3], Bm, e);
   if (err != cudaSuccess) return (int)err;
   DH_CHECK_LAUNCH();
   return 0;
 }
-// the instantiations the network uses: tok = 1x1 / NT 32; stride 2 only with a split16 output (layer2.0); everything else
-// by (NT, K) with fp32 or split16 output
-template <int NT, bool RES>
+// the instantiations the network uses: tok = 1x1 / NT 32 / single CTA; everything else by (NT, K, stride, output format)
+template <int NT, bool RES, int CG>
 int launch3(const CUtensorMap* A, const CUtensorMap& Bm, const T3Args& e, int ks, int stride, int epi, uint32_t smem, dim3 grid, cudaStream_t s) {
   if (epi == EPI_TOK) {
-    if constexpr (NT == 32) return launch3k<32, 1, 1, EPI_TOK, RES>(A, Bm, e, smem, grid, s);
+    if constexpr (NT == 32 && CG == 1) return launch3k<32, 1, 1, EPI_TOK, RES, 1>(A, Bm, e, smem, grid, s);
     return DH_E_SHAPE;
   }
   if (stride == 2) {
-    if (epi == EPI_SPLIT) return ks == 3 ? launch3k<NT, 3, 2, EPI_SPLIT, RES>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 2, EPI_SPLIT, RES>(A, Bm, e, smem, grid, s);
-    return ks == 3 ? launch3k<NT, 3, 2, EPI_F32, RES>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 2, EPI_F32, RES>(A, Bm, e, smem, grid, s);
+    if (epi == EPI_SPLIT) return ks == 3 ? launch3k<NT, 3, 2, EPI_SPLIT, RES, CG>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 2, EPI_SPLIT, RES, CG>(A, Bm, e, smem, grid, s);
+    return ks == 3 ? launch3k<NT, 3, 2, EPI_F32, RES, CG>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 2, EPI_F32, RES, CG>(A, Bm, e, smem, grid, s);
   }
-  if (epi == EPI_SPLIT) return ks == 3 ? launch3k<NT, 3, 1, EPI_SPLIT, RES>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 1, EPI_SPLIT, RES>(A, Bm, e, smem, grid, s);
-  return ks == 3 ? launch3k<NT, 3, 1, EPI_F32, RES>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 1, EPI_F32, RES>(A, Bm, e, smem, grid, s);
+  if (epi == EPI_SPLIT) return ks == 3 ? launch3k<NT, 3, 1, EPI_SPLIT, RES, CG>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 1, EPI_SPLIT, RES, CG>(A, Bm, e, smem, grid, s);
+  return ks == 3 ? launch3k<NT, 3, 1, EPI_F32, RES, CG>(A, Bm, e, smem, grid, s) : launch3k<NT, 1, 1, EPI_F32, RES, CG>(A, Bm, e, smem, grid, s);
+}
+template <bool RES, int CG>
+int launch3n(int NT, const CUtensorMap* A, const CUtensorMap& Bm, const T3Args& e, int ks, int stride, int epi, uint32_t smem, dim3 grid, cudaStream_t s) {
+  switch (NT) {
+    case 128: return launch3<128, RES, CG>(A, Bm, e, ks, stride, epi, smem, grid, s);
+    case 64: return launch3<64, RES, CG>(A, Bm, e, ks, stride, epi, smem, grid, s);
+    default: return launch3<32, RES, CG>(A, Bm, e, ks, stride, epi, smem, grid, s);
+  }
 }
 }  // namespace
 
@@ -579,7 +647,13 @@ int dh_launch_conv_tc3(const Conv3Args& a, cudaStream_t s) {
     if (!rc) rc = act_map(&A[3], reinterpret_cast<const uint16_t*>(a.in1) + plane1, a.C1, a.inW, a.inH, a.N, hw, hh, a.stride);
     if (rc) return rc;
   } else { A[2] = A[0]; A[3] = A[1]; }
-  rc = filt_map(&Bm, a.wt16, K, a.Cout, a.wt_plane_bytes, NT);
+  // CTA pairs: DAHITRA_TC3_CG = 0 (default) never — measured 15-50 % slower on every layer of this network, see DESIGN.md — | 1 on the N = 128 tiles and the K = 1152 -> 32 head conv | 2 always
+  static const int env_cg = [] { const char* v = getenv("DAHITRA_TC3_CG"); return v ? atoi(v) : 0; }();
+  static const bool env_stream = [] { const char* v = getenv("DAHITRA_TC3_STREAM"); return v && v[0] == '1'; }();   // A/B switch
+  const int mtiles = dh_cdiv(a.inW / a.stride, T3_TW) * dh_cdiv(a.inH / a.stride, T3_TH) * a.N;
+  int cg = a.tok ? 1 : (a.cg ? a.cg : (env_cg == 2 ? 2 : (env_cg == 1 && (NT == 128 || (a.Cout == 32 && K >= 1152)) ? 2 : 1)));
+  if (mtiles < 2) cg = 1;
+  rc = filt_map(&Bm, a.wt16, K, a.Cout, a.wt_plane_bytes, NT / cg);
   if (rc) return rc;
   T3Args e;
   e.bias = a.bias; e.res = a.res; e.out = a.out; e.wtok = a.wtok; e.partials = a.partials;
@@ -588,7 +662,7 @@ int dh_launch_conv_tc3(const Conv3Args& a, cudaStream_t s) {
   e.cchunks0 = a.C0 / 32; e.cchunks = Cin / 32; e.Cin = Cin; e.ps = a.ps; e.N = a.N;
   e.ncout_tiles = a.Cout / NT;
   e.tiles_per_img = e.tilesX * e.tilesY;
-  e.ntiles = e.tiles_per_img * a.N * e.ncout_tiles;
+  e.ntiles = (cg == 2 ? (mtiles + 1) / 2 : mtiles) * e.ncout_tiles;        // work items: tiles, or tile pairs
   e.res_split = a.res_split; e.out_split = a.out_split;
   e.res_plane = a.res_plane ? a.res_plane : (long long)a.N * e.OH * e.OW * a.Cout;
   e.out_plane = a.out_plane ? a.out_plane : (long long)a.N * e.OH * e.OW * a.Cout;
@@ -597,27 +671,24 @@ int dh_launch_conv_tc3(const Conv3Args& a, cudaStream_t s) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  dim3 grid((unsigned)(e.ntiles < sms ? e.ntiles : sms), 1, 1);            // persistent: one CTA per SM
-  // resident filter when the whole [h_w ; l_w] image fits next to two halo buffers, and every CTA walks enough tiles to
-  // amortise loading it (otherwise the streaming ring, which starts the first MMA after one stage instead of the whole image)
-  const uint32_t w_bytes = (uint32_t)K * (uint32_t)a.Cout * 4u;            // = ncout_tiles * cchunks * taps * B_TAP
+  const int slots = sms / cg;                                                // persistent: one CTA (pair) per SM (TPC)
+  const int nwork = e.ntiles < slots ? e.ntiles : slots;
+  dim3 grid((unsigned)(nwork * cg), 1, 1);
+  // resident filter when the whole [h_w ; l_w] image (a CTA of a pair: its half) fits next to two halo buffers, and every
+  // CTA walks enough tiles to amortise loading it (otherwise the streaming ring, whose first MMA starts after one stage)
+  const uint32_t w_bytes = (uint32_t)K * (uint32_t)a.Cout * 4u / (uint32_t)cg;   // = ncout_tiles * cchunks * taps * B_TAP
   const uint32_t fixed = 4 * 4096 + 512 + 4 * 4 * 34 * 4 + 1024;
-  static const bool env_stream = [] { const char* v = getenv("DAHITRA_TC3_STREAM"); return v && v[0] == '1'; }();   // A/B switch
-  const bool res_ok = w_bytes + 2 * T3_HALO + fixed <= T3_SMEM_MAX && !a.force_stream && !env_stream && e.ntiles >= 2 * (int)grid.x;
+  const bool res_ok = w_bytes + 2 * T3_HALO + fixed <= T3_SMEM_MAX && !a.force_stream && !env_stream && e.ntiles >= 2 * nwork;
   if (res_ok) {
     int hb = (int)((T3_SMEM_MAX - fixed - w_bytes) / T3_HALO);
     e.hb = hb > T3_MAX_HB ? T3_MAX_HB : hb;
     const uint32_t smem = (uint32_t)e.hb * T3_HALO + w_bytes + fixed;
-    switch (NT) {
-      case 128: return launch3<128, true>(A, Bm, e, a.K, a.stride, epi, smem, grid, s);
-      case 64: return launch3<64, true>(A, Bm, e, a.K, a.stride, epi, smem, grid, s);
-      default: return launch3<32, true>(A, Bm, e, a.K, a.stride, epi, smem, grid, s);
-    }
+    return cg == 2 ? launch3n<true, 2>(NT, A, Bm, e, a.K, a.stride, epi, smem, grid, s)
+                   : launch3n<true, 1>(NT, A, Bm, e, a.K, a.stride, epi, smem, grid, s);
   }
   e.hb = T3_MAX_HB;
-  switch (NT) {
-    case 128: return launch3<128, false>(A, Bm, e, a.K, a.stride, epi, T3_MAX_HB * T3_HALO + T3Cfg<128, false>::RING_BYTES + fixed, grid, s);
-    case 64: return launch3<64, false>(A, Bm, e, a.K, a.stride, epi, T3_MAX_HB * T3_HALO + T3Cfg<64, false>::RING_BYTES + fixed, grid, s);
-    default: return launch3<32, false>(A, Bm, e, a.K, a.stride, epi, T3_MAX_HB * T3_HALO + T3Cfg<32, false>::RING_BYTES + fixed, grid, s);
-  }
+  const uint32_t ring = NT == 128 ? T3Cfg<128, false>::RING_BYTES : (NT == 64 ? T3Cfg<64, false>::RING_BYTES : T3Cfg<32, false>::RING_BYTES);
+  const uint32_t smem = T3_MAX_HB * T3_HALO + ring + fixed;               // the pair's ring has twice the stages of half the size
+  return cg == 2 ? launch3n<false, 2>(NT, A, Bm, e, a.K, a.stride, epi, smem, grid, s)
+                 : launch3n<false, 1>(NT, A, Bm, e, a.K, a.stride, epi, smem, grid, s);
 }

@@ -221,8 +221,12 @@ extern "C" int dahitra_conv2d_split(const void* in0, const void* in1, int C0, in
                                     const void* res, int res_split, int relu, void* out, int out_split, int mode,
                                     const float* w_tok, float* partials, void* stream) {
   DH_REQUIRE(wt, DH_E_NULL);
-  DH_REQUIRE(mode >= 0 && mode <= 2, DH_E_VARIANT);
+  const int sched = mode & ~3;                                       // scheduling bits (do not change results)
+  mode &= 3;
+  DH_REQUIRE(mode <= 2 && !(sched & ~(16 | 32 | 64)), DH_E_VARIANT);
   Conv3Args a{};
+  a.cg = (sched & 32) ? 2 : ((sched & 16) ? 1 : 0);
+  a.force_stream = (sched & 64) ? 1 : 0;
   a.in0 = in0; a.in1 = in1; a.C0 = C0; a.C1 = C1; a.N = N; a.inH = inH; a.inW = inW; a.in0_plane = in0_plane; a.in1_plane = in1_plane;
   a.K = K; a.stride = stride; a.Cout = Cout;
   const size_t plane = (size_t)Cout * K * K * (C0 + C1);            // floats per plane of the *_WT slot

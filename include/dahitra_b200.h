@@ -267,7 +267,10 @@ int dahitra_maxpool3x3s2_split(const void* in_split, int N, int H, int W, int C,
  *   res            NULL, fp32 NHWC (res_split = 0) or split16 (res_split = 1); out fp32 NHWC or split16 (out_split)
  *   mode           0 plain | 1 pixel-shuffle store of a 32 -> 4x32 upsample conv (fp32 out [N][2inH][2inW][32]) |
  *                  2 tokenizer epilogue: no bias, ReLU, out = xs, partials [N][nchunk][4][34] with
- *                    nchunk = ceil(inH/16) * ceil(inW/8), w_tok [32][4]  (see dahitra_squeeze_tokens) */
+ *                    nchunk = ceil(inH/16) * ceil(inW/8), w_tok [32][4]  (see dahitra_squeeze_tokens)
+ *                  scheduling bits, OR-ed in (results do not depend on them): 16 = single CTAs, 32 = CTA pairs
+ *                  (tcgen05 cta_group::2; default: chosen per shape), 64 = stream the filter from L2 even where it
+ *                  would fit in shared memory */
 int dahitra_conv2d_split(const void* in0, const void* in1, int C0, int C1, long long in0_plane, long long in1_plane,
                          int N, int inH, int inW, int K, int stride, int Cout, const float* wt, const float* bias,
                          const void* res, int res_split, int relu, void* out, int out_split, int mode,

@@ -151,7 +151,7 @@ def maxpool_split(s):
     return out
 
 
-def conv2d_split(in0, in1, w, bias, res, relu, K, stride, res_split=False, out_split=False, mode=0, wtok=None):
+def conv2d_split(in0, in1, w, bias, res, relu, K, stride, res_split=False, out_split=False, mode=0, wtok=None, sched=0):
     """in0 / in1: split16 buffers shaped like their fp32 tensors (N, H, W, C); w: [K*K*Cin][Cout] fp32 (split on the host
     exactly as the engine does).  mode 1: w is the [128][288] phase filter already K-major.  Returns out (fp32 NHWC, or a
     split16 buffer of that shape) and, in mode 2, the partials."""
@@ -170,6 +170,6 @@ def conv2d_split(in0, in1, w, bias, res, relu, K, stride, res_split=False, out_s
         nchunk = ((inH + 15) // 16) * ((inW + 7) // 8)
         parts = torch.empty((N, nchunk, 4, 34), device=in0.device, dtype=torch.float32)
     rc = lib.dahitra_conv2d_split(_p(in0), _p(in1), C0, C1, 0, 0, N, inH, inW, K, stride, Cout, _p(wt), _p(bias), _p(res),
-                                  int(res_split), int(relu), _p(out), int(out_split), mode, _p(wtok), _p(parts), _stream())
+                                  int(res_split), int(relu), _p(out), int(out_split), mode | sched, _p(wtok), _p(parts), _stream())
     _lib.check(rc, "dahitra_conv2d_split")
     return (out, parts) if mode == 2 else out

@@ -366,9 +366,19 @@ SPLIT_CONVS = [  # (N, H, W, C0, C1, Cout, K, stride, res ('', 'f32', 'split'), 
 ]
 
 
+SPLIT_CONVS += [
+    (9, 32, 24, 128, 0, 128, 3, 1, 'split', True, True, True),     # 54 M tiles: resident / streaming, pairs with several tiles each
+    (3, 16, 24, 64, 0, 128, 3, 1, '', True, True, True),           # 9 M tiles: the last CTA pair has a tile without a partner
+    (40, 64, 64, 64, 0, 64, 3, 1, 'split', True, True, True),      # 1280 tiles: every CTA walks many tiles with the filter resident
+    (24, 64, 64, 128, 0, 32, 3, 1, 'f32', False, True, True),      # K = 1152 -> 32 (conv_layer2_0.3): resident in a pair, 2 halo buffers alone
+]
+
+
+@pytest.mark.parametrize("sched", [0, 16, 32, 64, 32 | 64], ids=["auto", "cg1", "cg2", "stream", "cg2-stream"])
 @pytest.mark.parametrize("cfg", SPLIT_CONVS)
-def test_conv2d_split16(cfg):
-    """conv_tc3: split16 operands, three FP16 partial products, vs fp64 on the SAME representable inputs / weights."""
+def test_conv2d_split16(cfg, sched):
+    """conv_tc3: split16 operands, three FP16 partial products, vs fp64 on the SAME representable inputs / weights; every
+    scheduling variant (single CTAs / CTA pairs, filter resident in shared memory / streamed)."""
     N, H, W, C0, C1, Cout, K, stride, res, relu, bias, out_split = cfg
     x0 = rnd(N, H, W, C0, seed=1)
     x1 = rnd(N, H, W, C1, seed=2) if C1 else None
@@ -379,7 +389,7 @@ def test_conv2d_split16(cfg):
     r = rnd(N, OH, OW, Cout, seed=5) if res else None
     s0, s1 = abi.split_pack(x0), (abi.split_pack(x1) if C1 else None)
     rs = None if r is None else (abi.split_pack(r) if res == 'split' else r)
-    y = abi.conv2d_split(s0, s1, w, b, rs, relu, K, stride, res_split=(res == 'split'), out_split=out_split)
+    y = abi.conv2d_split(s0, s1, w, b, rs, relu, K, stride, res_split=(res == 'split'), out_split=out_split, sched=sched)
     torch.cuda.synchronize()
     xq = f16_split_ref(x0) if x1 is None else torch.cat([f16_split_ref(x0), f16_split_ref(x1)], -1)
     rq = None if r is None else (f16_split_ref(r) if res == 'split' else r.double().cpu())
@@ -397,7 +407,7 @@ def test_conv2d_split16(cfg):
     close(y, full, rtol=1e-5, atol=2e-5 * float(full.abs().max()))
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 16), (1, 64, 64), (1, 24, 40)])
+@pytest.mark.parametrize("shape", [(2, 16, 16), (1, 64, 64), (1, 24, 40), (12, 64, 64)])
 def test_conv2d_up2_split16(shape):
     """nearest-x2 upsample + 3x3 conv (conv_layer4/3/2) on a split16 input, pixel-shuffle store to fp32."""
     from dahitra_b200.engine import upsample_phase_filter
@@ -407,10 +417,11 @@ def test_conv2d_up2_split16(shape):
     w = torch.randn(32, 32, 3, 3, generator=g, dtype=torch.float64) * (288 ** -0.5)
     b = torch.randn(32, generator=g, dtype=torch.float64)
     wt, pb = upsample_phase_filter(w, b)
-    y = abi.conv2d_split(abi.split_pack(x), None, wt, pb.float().to(DEV), None, True, 3, 1, mode=1)
-    torch.cuda.synchronize()
     ref = F.relu(F.conv2d(x.double().cpu().permute(0, 3, 1, 2).repeat_interleave(2, 2).repeat_interleave(2, 3), w, b, 1, 1))
-    close(y, ref.permute(0, 2, 3, 1), rtol=1e-5, atol=2e-5 * float(ref.abs().max()))
+    for sched in (0, 16, 32, 64):
+        y = abi.conv2d_split(abi.split_pack(x), None, wt, pb.float().to(DEV), None, True, 3, 1, mode=1, sched=sched)
+        torch.cuda.synchronize()
+        close(y, ref.permute(0, 2, 3, 1), rtol=1e-5, atol=2e-5 * float(ref.abs().max()))
 
 
 @pytest.mark.parametrize("cfg", [(2, 16, 16, 256), (2, 32, 32, 128), (2, 64, 64, 64), (1, 24, 40, 64), (1, 256, 256, 64)])
