@@ -85,6 +85,23 @@ int dh_launch_maxpool_split(const void* in, int N, int H, int W, int C, void* ou
 // programmatic dependent launch: attribute for cudaLaunchKernelEx (returns the number of attributes written: 0 or 1)
 int dh_pdl_attr(cudaLaunchAttribute* at);
 void dh_set_pdl(int on);
+// launch with the programmatic-dependent-launch attribute when dahitra_forward asked for it (DH_FLAG_PDL): the kernel may
+// start while its predecessor in the stream drains and must call pdl_wait() before touching anything that launch wrote
+template <typename... KArgs, typename... Args>
+static inline int dh_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  cfg.attrs = at; cfg.numAttrs = dh_pdl_attr(at);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  if (e != cudaSuccess) return (int)e;
+  DH_CHECK_LAUNCH();
+  return 0;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void dh_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void dh_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 int dh_launch_conv_ffma(const ConvArgs& a, cudaStream_t s);
 bool dh_conv_tc_eligible(const ConvArgs& a);
 int dh_launch_conv_tc(const ConvArgs& a, cudaStream_t s);

@@ -325,6 +325,8 @@ classifier_kernel(const float* __restrict__ in, int H, int W, int tilesX, const 
   const int tid = threadIdx.x, n = blockIdx.z;
   const int y0 = (blockIdx.x / tilesX) * CL_TH, x0 = (blockIdx.x % tilesX) * CL_TW;
   for (int i = tid; i < 9 * NC * 8; i += 128) reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  dh_pdl_wait();                       // the input map comes from the previous launch (the filter above does not)
+  dh_pdl_launch_dependents();
   const int lx = tid & 31, g = tid >> 5;
   float acc[4][NC];
 #pragma unroll
@@ -413,13 +415,12 @@ int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const flo
     const int smem = (2 * CL_HH * CL_HW * CL_PS + 9 * NC * 32) * (int)sizeof(float);                      \
     cudaError_t e = cudaFuncSetAttribute(classifier_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
     if (e != cudaSuccess) return (int)e;                                                                  \
-    classifier_kernel<NC><<<grid, 128, smem, s>>>(in, H, W, tx, w, b, logits, amax);                      \
-  } break;
+    return dh_launch(classifier_kernel<NC>, grid, dim3(128), (size_t)smem, s, in, H, W, tx, w, b, logits, amax); \
+  }
   switch (nc) {
     DH_CLS_CASE(1) DH_CLS_CASE(2) DH_CLS_CASE(3) DH_CLS_CASE(4)
     DH_CLS_CASE(5) DH_CLS_CASE(6) DH_CLS_CASE(7) DH_CLS_CASE(8)
   }
 #undef DH_CLS_CASE
-  DH_CHECK_LAUNCH();
-  return 0;
+  return DH_E_SHAPE;
 }

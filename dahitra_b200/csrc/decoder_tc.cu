@@ -96,6 +96,8 @@ decoder_tables_tc_kernel(const float* __restrict__ mem, int B, int first_call, c
   float* T = tables + ((size_t)blockIdx.y * depth + layer) * DH_TABTC_FLOATS;
   float* TA = T; float* TB = T + 1024; float* cA = T + 2048; float* TAl = T + 2080; float* TBl = T + 2080 + 1024;
   const float g = __ldg(L + lane), b = __ldg(L + 32 + lane);
+  dh_pdl_wait();                       // `mem` comes from the token encoder launched just before
+  dh_pdl_launch_dependents();
   MN[j][lane] = ln_lane32(__ldg(mem + ((size_t)pair * 3 + call) * 128 + j * 32 + lane), g, b);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -183,6 +185,8 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  dh_pdl_wait();                       // tables / x / skip come from earlier launches of the stream
+  dh_pdl_launch_dependents();
   const uint32_t tmem_wg = tmem_slot + (uint32_t)wg * PDT_WG_COLS;      // this warpgroup's columns
   const uint32_t tmem = tmem_wg + ((uint32_t)(warp * 32) << 16);       // ... and this warp's lane quarter
   const uint32_t my_bar = smem_u32(&mma_bar[wg]);
@@ -457,9 +461,8 @@ int launch_pdt(dim3 grid, const float* x, const float* pos, const float* tables,
   cudaError_t e = cudaFuncSetAttribute(pixel_decoder_tc_kernel<HEADS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)PdtCfg<X3>::SMEM);
   if (e != cudaSuccess) return (int)e;
-  pixel_decoder_tc_kernel<HEADS, X3><<<grid, PDT_ROWS * PdtCfg<X3>::G, PdtCfg<X3>::SMEM, s>>>(x, pos, tables, pack, npix, w, depth, skip, skip_up, out, osp);
-  DH_CHECK_LAUNCH();
-  return 0;
+  return dh_launch(pixel_decoder_tc_kernel<HEADS, X3>, grid, dim3(PDT_ROWS * PdtCfg<X3>::G), (size_t)PdtCfg<X3>::SMEM, s, x, pos, tables, pack,
+                   npix, w, depth, skip, skip_up, out, (long long)osp);
 }
 }  // namespace
 
@@ -472,9 +475,7 @@ int dh_launch_decoder_tables_tc(const float* mem, int B, int first_call, int nca
   const int smem = heads * 2048 * (int)sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(decoder_tables_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  decoder_tables_tc_kernel<<<grid, 128, smem, s>>>(mem, B, first_call, dec, heads, tables, depth);
-  DH_CHECK_LAUNCH();
-  return 0;
+  return dh_launch(decoder_tables_tc_kernel, grid, dim3(128), (size_t)smem, s, mem, B, first_call, dec, heads, tables, depth);
 }
 
 // x3: bit 0 = error-compensated 3xTF32; bit 8 (x3 | 256): `out` receives split16 planes (conv_tc3.cu's input format)

@@ -310,6 +310,10 @@ stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int til
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // barrier init and the TMEM allocation above overlap the previous launch's tail; the images (possibly written by the launch
+  // just before: device-side normalisation) and the output buffer (possibly still read by it) are only touched after this
+  dh_pdl_wait();
+  dh_pdl_launch_dependents();
 
   if (warp < 8) {
     // ------------------------------------------------------------------ builders: two warpgroups, alternate global K steps
@@ -459,11 +463,11 @@ int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const 
   if (x3 == 2) {
     cudaError_t e = cudaFuncSetAttribute(stem_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
     if (e != cudaSuccess) return (int)e;
-    stem_f16_kernel<true><<<grid, SK_THREADS, SF_SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out, split_plane);
+    return dh_launch(stem_f16_kernel<true>, grid, dim3(SK_THREADS), SF_SMEM, s, tmX, OH, OW, tx, ty, ntiles, wtc, b, out, split_plane);
   } else if (x3 == 3) {
     cudaError_t e = cudaFuncSetAttribute(stem_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
     if (e != cudaSuccess) return (int)e;
-    stem_f16_kernel<false><<<grid, SK_THREADS, SF_SMEM, s>>>(tmX, OH, OW, tx, ty, ntiles, wtc, b, out, split_plane);
+    return dh_launch(stem_f16_kernel<false>, grid, dim3(SK_THREADS), SF_SMEM, s, tmX, OH, OW, tx, ty, ntiles, wtc, b, out, split_plane);
   } else if (x3) {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<true>::SMEM);
     if (e != cudaSuccess) return (int)e;

@@ -164,6 +164,8 @@ token_encoder_kernel(const float* __restrict__ partials, int B, int nchunk, cons
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(enc + (size_t)i * 4) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  dh_pdl_wait();                       // the partials come from the previous launch; the weight fetch above does not
+  dh_pdl_launch_dependents();
   const float* pos = te_w;
   const float* ln1g = te_w + 256; const float* ln1b = ln1g + 32;
   const float* Mqk = ln1b + 32;
@@ -254,9 +256,7 @@ int dh_launch_token_encoder(const float* partials, int B, int nchunk, const floa
   const int smem = DH_ENC_FLOATS(heads) * (int)sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(token_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
-  token_encoder_kernel<<<B, 256, smem, s>>>(partials, B, nchunk, enc, heads, add_pos, mem);
-  DH_CHECK_LAUNCH();
-  return 0;
+  return dh_launch(token_encoder_kernel, dim3(B), dim3(256), (size_t)smem, s, partials, B, nchunk, enc, heads, add_pos, mem);
 }
 
 // =====================================================================================================

@@ -39,7 +39,7 @@ MODES = {
     # same 4 bytes per element as fp32 (DH_FLAG_ACT_SPLIT, csrc/conv_tc3.cu): a.w = h_a.h_w + 2^-11 (h_a.l_w + l_a.h_w), all
     # three products on FP16 MMAs, TMA lands the operands directly, and the tokenizer's 1x1 squeeze runs on the tensor cores.
     "tf32x3": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_FOLD | DH_FLAG_TC_STRIDE2
-              | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3 | DH_FLAG_ACT_SPLIT,
+              | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3 | DH_FLAG_ACT_SPLIT | DH_FLAG_PDL,
     # ... with fp32 activation storage and an in-kernel splitter pass (round 1's default; f16 main + bf16 remainders)
     "tf32x3_fp32act": DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_FOLD | DH_FLAG_TC_STRIDE2
                       | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3,

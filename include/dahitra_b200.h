@@ -68,7 +68,7 @@ extern "C" {
                                    * launch's tail; every kernel waits with griddepcontrol.wait before touching its inputs) */
 /* the modes dahitra_b200.engine.MODES names (DESIGN.md "Precision modes") */
 #define DH_FLAGS_TF32X3     (DH_FLAG_CONV_TC | DH_FLAG_TC_3XTF32 | DH_FLAG_TC_X3_BF16 | DH_FLAG_TC_MAIN_F16 | DH_FLAG_TC_FOLD | DH_FLAG_TC_STRIDE2 | \
-                             DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3 | DH_FLAG_ACT_SPLIT)   /* default: every product error-compensated, fp32-grade */
+                             DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3 | DH_FLAG_ACT_SPLIT | DH_FLAG_PDL)   /* default: every product error-compensated, fp32-grade */
 #define DH_FLAGS_TF32       (DH_FLAG_CONV_TC | DH_FLAG_TC_STRIDE2 | DH_FLAG_STEM_TC | DH_FLAG_DEC_TC | DH_FLAG_DEC_TC_X3)   /* single-pass TF32 convs */
 #define DH_FLAGS_F16        (DH_FLAGS_TF32 | DH_FLAG_TC_MAIN_F16)                    /* single-pass FP16 conv operands */
 #define DH_FLAGS_BF16       (DH_FLAGS_TF32 | DH_FLAG_TC_BF16)                        /* single-pass BF16 conv operands */

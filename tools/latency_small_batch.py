@@ -13,9 +13,11 @@ class Args:
 ap = argparse.ArgumentParser()
 ap.add_argument("--mode", default="tf32x3")
 ap.add_argument("--batch", type=int, default=4)
+ap.add_argument("--extra-flags", type=int, default=0, help="OR-ed into the mode's DH_FLAG_* bitmask (32768 = PDL, 256 = one stream)")
 a = ap.parse_args()
 torch.manual_seed(0)
-net = define_G(Args(), gpu_ids=[0]).eval().set_mode(a.mode)
+from dahitra_b200.engine import MODES
+net = define_G(Args(), gpu_ids=[0]).eval().set_mode(MODES[a.mode] | a.extra_flags)
 x1 = torch.rand(a.batch, 3, 256, 256, device="cuda") * 2 - 1
 x2 = torch.rand(a.batch, 3, 256, 256, device="cuda") * 2 - 1
 
@@ -44,5 +46,5 @@ with torch.no_grad():
     with torch.cuda.graph(g):
         y = net(x1, x2)
     graph_ms = timed(g.replay)
-print(json.dumps(dict(workload=f"LEVIR 256x256 batch {a.batch} (configs[0])", mode=a.mode, eager_ms=eager_ms, graph_ms=graph_ms,
+print(json.dumps(dict(workload=f"LEVIR 256x256 batch {a.batch} (configs[0])", mode=a.mode, extra_flags=a.extra_flags, eager_ms=eager_ms, graph_ms=graph_ms,
                       eager_pairs_per_s=a.batch / eager_ms * 1e3, graph_pairs_per_s=a.batch / graph_ms * 1e3)))
