@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdahitra_b200.so")
-SOURCES = ["conv_ffma.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "split.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "aux.cu", "forward.cu"]
+SOURCES = ["conv_ffma.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "split.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "classifier.cu", "aux.cu", "forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -113,6 +113,8 @@ int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const 
 int dh_launch_maxpool(const float* in, int N, int H, int W, int C, float* out, cudaStream_t s);
 int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* b,
                          float* logits, unsigned char* amax, cudaStream_t s);
+int dh_launch_classifier_tma(const float* in, int N, int H, int W, int nc, const float* w, const float* b,
+                             float* logits, unsigned char* amax, cudaStream_t s);
 int dh_launch_squeeze_tokens(const float* feat, int N, int npix, int Cin, const float* wsq, const float* wtok,
                              float* xs, float* partials, cudaStream_t s);
 int dh_launch_token_encoder(const float* partials, int B, int nchunk, const float* enc, int heads, int add_pos,

@@ -2,6 +2,7 @@
 // 3x3/s2 max-pool and the classifier head.  These are the strict-fp32 path and the fallback for the
 // shapes the tcgen05 kernel (conv_tc.cu) does not take (strided convs, Cin=3, tiny Cout).
 #include "common.cuh"
+#include <cstdlib>
 
 // =====================================================================================================
 // Generic conv: out[n,oy,ox,co] = act( sum_{r,s,ci} in[n, oy*st+r-pad, ox*st+s-pad, ci] * w[(r*KW+s)*Cin+ci][co]
@@ -405,6 +406,10 @@ classifier_kernel(const float* __restrict__ in, int H, int W, int tilesX, const 
 
 int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* b,
                          float* logits, unsigned char* amax, cudaStream_t s) {
+  // default: the TMA-fed persistent kernel (classifier.cu); DAHITRA_CLS_V1=1 keeps the cp.async-staged kernel below (same
+  // arithmetic in the same order: bit-identical logits)
+  static const bool v1 = [] { const char* v = getenv("DAHITRA_CLS_V1"); return v && v[0] == '1'; }();
+  if (!v1) return dh_launch_classifier_tma(in, N, H, W, nc, w, b, logits, amax, s);
   DH_REQUIRE(in && w && b && logits, DH_E_NULL);
   DH_REQUIRE(N > 0 && H > 0 && W > 0 && nc >= 1 && nc <= 8, DH_E_SHAPE);
   DH_REQUIRE(dh_aligned16(in) && dh_aligned16(w), DH_E_ALIGN);

@@ -627,6 +627,11 @@ int get_map2(CUtensorMap* out, const void* ptr, int rank, int d0, int d1, int d2
 // generic fp32 tiled tensor map (used by the stem for its planar NCHW halo); strides in bytes for dims 1..rank-1
 int dh_encode_tiled_f32(CUtensorMap* out, const void* ptr, int rank, const unsigned long long* dims,
                         const unsigned long long* strides, const unsigned* box, bool swizzle128) {
+  return dh_encode_tiled_f32_sw(out, ptr, rank, dims, strides, box, swizzle128 ? 128 : 0);
+}
+// swizzle_bytes: 0 (none), 64 or 128
+int dh_encode_tiled_f32_sw(CUtensorMap* out, const void* ptr, int rank, const unsigned long long* dims,
+                           const unsigned long long* strides, const unsigned* box, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode2();
   if (!enc) return DH_E_VARIANT;
   cuuint64_t d[5], st[4];
@@ -634,7 +639,8 @@ int dh_encode_tiled_f32(CUtensorMap* out, const void* ptr, int rank, const unsig
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) st[i] = strides[i];
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, b, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : DH_E_SHAPE;
 }

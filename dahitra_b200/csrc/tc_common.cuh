@@ -8,6 +8,8 @@
 // conv_tc2.cu: fp32 tiled tensor map through the driver entry point (no -lcuda); strides in bytes for dims 1..rank-1
 int dh_encode_tiled_f32(CUtensorMap* out, const void* ptr, int rank, const unsigned long long* dims,
                         const unsigned long long* strides, const unsigned* box, bool swizzle128);
+int dh_encode_tiled_f32_sw(CUtensorMap* out, const void* ptr, int rank, const unsigned long long* dims,
+                           const unsigned long long* strides, const unsigned* box, int swizzle_bytes);
 
 namespace dhtc {
 
