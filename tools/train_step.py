@@ -5,7 +5,7 @@ module is switched to eval() and the NATIVE forward is checked against the autog
    python tools/train_step.py [--steps 10]                                   (1 GPU)
    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_step.py    (DDP)
 Prints one JSON line from rank 0."""
-import argparse, json, os, sys, time
+import argparse, contextlib, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
@@ -39,18 +39,39 @@ x1 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 x2 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 y = (torch.rand(a.batch, 256, 256, device="cuda", generator=g) < 0.1).long()
 losses = []
-torch.cuda.synchronize()
-t0 = time.time()
-for step in range(a.steps):
+w2 = torch.ones(2, device="cuda")
+
+
+def one_step(sync=True):
     opt.zero_grad(set_to_none=True)
-    loss = F.cross_entropy(model(x1, x2), y, weight=torch.ones(2, device="cuda"), ignore_index=255)   # models/losses.py:9-26
-    loss.backward()
+    ctx = model.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
+    with ctx:
+        loss = F.cross_entropy(model(x1, x2), y, weight=w2, ignore_index=255)   # models/losses.py:9-26
+        loss.backward()
     opt.step()
-    losses.append(float(loss.detach()))
-torch.cuda.synchronize()
-dt = time.time() - t0
-no_grad = [n for n, p in net.named_parameters() if p.requires_grad and p.grad is None]
-gnorm = float(torch.sqrt(sum((p.grad.float() ** 2).sum() for p in net.parameters() if p.grad is not None)))
+    return loss
+
+
+def timed(n, sync=True):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        losses.append(one_step(sync).detach())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / n], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms)
+
+
+for _ in range(3):                               # warm-up (cuDNN autotune, allocator, DDP bucket rebuild)
+    losses.append(one_step().detach())
+step_ms = timed(a.steps)
+dt = step_ms * a.steps / 1e3
 if world > 1:                                   # replicas must hold identical weights after the all-reduced steps
     w = torch.cat([p.detach().flatten()[:64] for p in net.parameters()])
     ref = w.clone()
@@ -61,6 +82,27 @@ if world > 1:                                   # replicas must hold identical w
     replicas_equal = bool(flag.item())
 else:
     replicas_equal = None
+# (measured AFTER the replica check: steps without the all-reduce let the replicas drift apart on purpose)
+# the gradient all-reduce: (a) exposed share = step with - step without the all-reduce (DDP no_sync), (b) the collective
+# alone on a flat fp32 buffer of the gradients' size
+nosync_ms, ar_ms, grad_bytes = None, None, 4 * sum(p.numel() for p in net.parameters() if p.requires_grad)
+if world > 1:
+    nosync_ms = timed(max(3, a.steps // 2), sync=False)
+    one_step()                                   # re-synchronise the replicas' gradients / weights path
+    flat = torch.zeros(grad_bytes // 4, device="cuda")
+    for _ in range(2):
+        dist.all_reduce(flat)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); dist.barrier()
+    e0.record()
+    for _ in range(5):
+        dist.all_reduce(flat)
+    e1.record()
+    torch.cuda.synchronize()
+    ar_ms = e0.elapsed_time(e1) / 5
+losses = [float(l) for l in losses]
+no_grad = [n for n, p in net.named_parameters() if p.requires_grad and p.grad is None]
+gnorm = float(torch.sqrt(sum((p.grad.float() ** 2).sum() for p in net.parameters() if p.grad is not None)))
 net.eval()
 with torch.no_grad():
     y_native = net(x1, x2)                      # native sm_100a forward on the UPDATED weights
@@ -69,7 +111,12 @@ native_vs_autograd = float((y_native - y_auto).abs().max())
 if rank == 0:
     print(json.dumps(dict(workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW (autograd route"
                                    + (", DDP/NCCL all-reduce)" if world > 1 else ")"),
-                          steps=a.steps, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
+                          steps=a.steps, step_ms=step_ms, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
+                          pairs_per_s_per_gpu=a.steps * a.batch / dt,
+                          step_ms_without_allreduce=nosync_ms, exposed_allreduce_share=(None if nosync_ms is None else max(0.0, 1 - nosync_ms / step_ms)),
+                          allreduce_alone_ms=ar_ms, gradient_bytes=grad_bytes,
+                          allreduce_alone_share_of_step=(None if ar_ms is None else ar_ms / step_ms),
+                          optimizer="AdamW(lr=1e-3, weight_decay=0.01)", timing="CUDA events over the timed steps after 3 warm-up steps, max over ranks",
                           loss_first=losses[0], loss_last=losses[-1], grad_norm_last=gnorm, params_without_grad=len(no_grad),
                           replicas_equal=replicas_equal, native_vs_autograd_after_training_max_abs=native_vs_autograd)))
 if world > 1:
