@@ -57,6 +57,23 @@ __device__ __forceinline__ float gelu_phi8(float h) {
   return h * (h >= 0.f ? 1.0f - q : q);
 }
 
+// the same on a pair of values: the Horner chain and the final products are packed FFMA2 / FMUL2 (one issued instruction per
+// two values; this kernel is bound by instruction issue), |h|, 2^g and the sign select stay scalar
+__device__ __forceinline__ float2 gelu_phi8_2(float2 h) {
+  const float2 u = make_float2(fminf(fabsf(h.x), 6.0f), fminf(fabsf(h.y), 6.0f));
+  float2 g = f2_bcast(-1.966050149e-06f);
+  g = ffma2(g, u, f2_bcast(2.892093107e-05f));
+  g = ffma2(g, u, f2_bcast(-1.361643517e-04f));
+  g = ffma2(g, u, f2_bcast(-2.589166979e-04f));
+  g = ffma2(g, u, f2_bcast(7.225090638e-03f));
+  g = ffma2(g, u, f2_bcast(-5.261069164e-02f));
+  g = ffma2(g, u, f2_bcast(-4.591687918e-01f));
+  g = ffma2(g, u, f2_bcast(-1.151110411e+00f));
+  g = ffma2(g, u, f2_bcast(-9.999998808e-01f));
+  const float qx = ex2_approx(g.x), qy = ex2_approx(g.y);
+  return fmul2(h, make_float2(h.x >= 0.f ? 1.0f - qx : qx, h.y >= 0.f ? 1.0f - qy : qy));
+}
+
 // ----------------------------------------------------------------------------------------------------
 // table builder (TC layout): per (image-call, layer)  DH_TABTC_FLOATS =
 //     [TA_hi swz 32x32][TB_hi swz 32x32][cA 32] [TA_lo swz][TB_lo swz]
@@ -225,7 +242,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
   float* io = reinterpret_cast<float*>(base_ptr + Cfg::OFF_IO + (size_t)(threadIdx.x >> 5) * 4096);
   const int lane = threadIdx.x & 31, c8 = lane & 7, r8 = lane >> 3;
   const int pw0 = (blockIdx.x * G + wg) * PDT_ROWS + warp * 32;         // first pixel of this warp
-  float xr[32];
+  float2 xr[16];                                                        // this thread's pixel: 32 channels as 16 packed pairs
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const int r = g * 4 + r8, pr = pw0 + r;
@@ -240,28 +257,43 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 v = *reinterpret_cast<const float4*>(io + lane * 32 + ((q ^ (lane & 7)) << 2));
-    xr[q * 4] = v.x; xr[q * 4 + 1] = v.y; xr[q * 4 + 2] = v.z; xr[q * 4 + 3] = v.w;
+    xr[q * 2] = make_float2(v.x, v.y); xr[q * 2 + 1] = make_float2(v.z, v.w);
   }
   __syncwarp();
   {
     uint32_t u[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) u[c] = __float_as_uint(xr[c]);
+    for (int c = 0; c < 16; ++c) { u[2 * c] = __float_as_uint(xr[c].x); u[2 * c + 1] = __float_as_uint(xr[c].y); }
     tmem_st32(tmem + TM_X, u);
   }
 
   // this thread's row of the A operand -> tensor memory: TF32-rounded values and, for X3, the remainders
-  auto write_a_row = [&](const float (&v)[32]) {
+  auto write_a_row = [&](const float2 (&v)[16]) {
     uint32_t hi[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) hi[c] = __float_as_uint(tf32_hi(v[c]));
+    for (int c = 0; c < 16; ++c) { hi[2 * c] = __float_as_uint(tf32_hi(v[c].x)); hi[2 * c + 1] = __float_as_uint(tf32_hi(v[c].y)); }
     tmem_st32(tmem + TM_A, hi);
     if (X3) {
       uint32_t lo[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) lo[c] = __float_as_uint(v[c] - __uint_as_float(hi[c]));
+      for (int c = 0; c < 16; ++c) {
+        const float2 l = fsub2(v[c], make_float2(__uint_as_float(hi[2 * c]), __uint_as_float(hi[2 * c + 1])));
+        lo[2 * c] = __float_as_uint(l.x); lo[2 * c + 1] = __float_as_uint(l.y);
+      }
       tmem_st32(tmem + TM_AL, lo);
     }
+  };
+  // LayerNorm statistics of this thread's pixel: t = x - mean (packed), returns 1 / sqrt(var + eps)
+  auto center = [&](const float2 (&x)[16], float2 (&t)[16]) -> float {
+    float2 s2 = x[0];
+#pragma unroll
+    for (int c = 1; c < 16; ++c) s2 = fadd2(s2, x[c]);
+    const float mu = (s2.x + s2.y) * (1.f / 32.f);
+    const float2 nmu = f2_bcast(-mu);
+    float2 v2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { t[c] = fadd2(x[c], nmu); v2 = ffma2(t[c], t[c], v2); }
+    return rsqrtf((v2.x + v2.y) * (1.f / 32.f) + 1e-5f);
   };
 
   uint32_t mma_phase = 0;
@@ -307,67 +339,59 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
     const float* b1f = mlpp + 2048; const float* cbA = mlpp + 2080; const float* cbM = mlpp + 2112;
     const uint32_t t_hi = tab_addr(b), t_lo = tab_addr(b) + PDT_HI_STRIDE;
     const uint32_t m_hi = mlp_addr(b), m_lo = mlp_addr(b) + PDT_HI_STRIDE;
-    float t[32], rstd;
-    // ---- 1. S = xhat . TA^T
+    float2 t[16];
+    float rstd;
+    const float2* cA2 = reinterpret_cast<const float2*>(cA);
+    const float2* b1f2 = reinterpret_cast<const float2*>(b1f);
+    const float2* cbA2 = reinterpret_cast<const float2*>(cbA);
+    const float2* cbM2 = reinterpret_cast<const float2*>(cbM);
+    // ---- 1. S = xhat . TA^T            (rstd is applied to the MMA result: S = rstd * ((x - mu) . TA) + cA)
     {
       turn_wait();
-      float mu = 0.f;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) mu += xr[c];
-      mu *= (1.f / 32.f);
-      float var = 0.f;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) { const float d = xr[c] - mu; var = fmaf(d, d, var); }
-      rstd = rsqrtf(var * (1.f / 32.f) + 1e-5f);               // applied to the MMA result: S = rstd * ((x - mu) . TA) + cA
-#pragma unroll
-      for (int c = 0; c < 32; ++c) t[c] = xr[c] - mu;
+      rstd = center(xr, t);
       write_a_row(t);
       turn_pass();
     }
     mma_round(t_hi, t_lo, IDESC_S, TM_D, K4{}, false);
     // ---- 2. P = softmax_j(S + cA) ; x += P . TB^T
     {
+      const float2 rs2 = f2_bcast(rstd);
       if constexpr (HEADS == 8) {
         uint32_t u[32];
         tmem_ld32(tmem + TM_D, u);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) t[c] = fmaf(__uint_as_float(u[c]), rstd, cA[c]);
+        for (int c = 0; c < 16; ++c) t[c] = ffma2(make_float2(__uint_as_float(u[2 * c]), __uint_as_float(u[2 * c + 1])), rs2, cA2[c]);
       } else {
         uint32_t u[16];
         tmem_ld16(tmem + TM_D, u);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) t[c] = fmaf(__uint_as_float(u[c]), rstd, cA[c]);
+        for (int c = 0; c < 8; ++c) t[c] = ffma2(make_float2(__uint_as_float(u[2 * c]), __uint_as_float(u[2 * c + 1])), rs2, cA2[c]);
 #pragma unroll
-        for (int c = 16; c < 32; ++c) t[c] = 0.f;
+        for (int c = 8; c < 16; ++c) t[c] = make_float2(0.f, 0.f);
       }
       turn_wait();
 #pragma unroll
-      for (int h = 0; h < HEADS; ++h) {
-        const float mx = fmaxf(fmaxf(t[h * 4], t[h * 4 + 1]), fmaxf(t[h * 4 + 2], t[h * 4 + 3]));
-        const float e0 = ex2_approx(t[h * 4] - mx), e1 = ex2_approx(t[h * 4 + 1] - mx), e2 = ex2_approx(t[h * 4 + 2] - mx),
-                    e3 = ex2_approx(t[h * 4 + 3] - mx);               // scores are in log2 units (tables kernel)
-        const float inv = rcp_approx(e0 + e1 + e2 + e3);
-        t[h * 4] = e0 * inv; t[h * 4 + 1] = e1 * inv; t[h * 4 + 2] = e2 * inv; t[h * 4 + 3] = e3 * inv;
+      for (int h = 0; h < HEADS; ++h) {                          // scores are in log2 units (tables kernel): 2^(s - max)
+        const float2 a = t[2 * h], b = t[2 * h + 1];
+        const float2 nmx = f2_bcast(-fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)));
+        const float2 da = fadd2(a, nmx), db = fadd2(b, nmx);
+        const float2 ea = make_float2(ex2_approx(da.x), ex2_approx(da.y)), eb = make_float2(ex2_approx(db.x), ex2_approx(db.y));
+        const float2 sm = fadd2(ea, eb);
+        const float2 inv = f2_bcast(rcp_approx(sm.x + sm.y));
+        t[2 * h] = fmul2(ea, inv); t[2 * h + 1] = fmul2(eb, inv);
       }
       write_a_row(t);
       turn_pass();
     }
     mma_round(t_hi + 4096, t_lo + 4096, IDESC_32, TM_X, KP{}, true);
-    // ---- 3. Hid = xhat' . W1f^T
+    // ---- 3. Hid = xhat' . W1f^T        (Hid = rstd * ((x - mu) . W1f) + b1f)
     {
       uint32_t u[32];
       tmem_ld32(tmem + TM_X, u);
       turn_wait();
-      float mu = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) { xr[c] = __uint_as_float(u[c]) + cbA[c]; mu += xr[c]; }
-      mu *= (1.f / 32.f);
-      float var = 0.f;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) { const float d = xr[c] - mu; var = fmaf(d, d, var); }
-      rstd = rsqrtf(var * (1.f / 32.f) + 1e-5f);               // Hid = rstd * ((x - mu) . W1f) + b1f
-#pragma unroll
-      for (int c = 0; c < 32; ++c) t[c] = xr[c] - mu;
+      for (int c = 0; c < 16; ++c) xr[c] = fadd2(make_float2(__uint_as_float(u[2 * c]), __uint_as_float(u[2 * c + 1])), cbA2[c]);
+      rstd = center(xr, t);
       write_a_row(t);
       turn_pass();
     }
@@ -377,8 +401,10 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       uint32_t u[32];
       tmem_ld32(tmem + TM_D, u);
       turn_wait();
+      const float2 rs2 = f2_bcast(rstd);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) t[c] = gelu_phi8(fmaf(__uint_as_float(u[c]), rstd, b1f[c]));
+      for (int c = 0; c < 16; ++c)
+        t[c] = gelu_phi8_2(ffma2(make_float2(__uint_as_float(u[2 * c]), __uint_as_float(u[2 * c + 1])), rs2, b1f2[c]));
       write_a_row(t);
       turn_pass();
     }
@@ -387,7 +413,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
       uint32_t u[32];
       tmem_ld32(tmem + TM_X, u);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) xr[c] = __uint_as_float(u[c]) + cbM[c];
+      for (int c = 0; c < 16; ++c) xr[c] = fadd2(make_float2(__uint_as_float(u[2 * c]), __uint_as_float(u[2 * c + 1])), cbM2[c]);
     }
     // this warpgroup is done with buffer b (its MMAs completed, its bias reads are in registers)
     asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
@@ -396,7 +422,7 @@ pixel_decoder_tc_kernel(const float* __restrict__ x, const float* __restrict__ p
 
 #pragma unroll
   for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<float4*>(io + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(xr[q * 4], xr[q * 4 + 1], xr[q * 4 + 2], xr[q * 4 + 3]);
+    *reinterpret_cast<float4*>(io + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(xr[q * 2].x, xr[q * 2].y, xr[q * 2 + 1].x, xr[q * 2 + 1].y);
   __syncwarp();
   if (out_split_plane) {
     // split16 planes for conv_tc3.cu (hi = f16(o), lo = f16(2^11 (o - hi))): 4 lanes x 8 channels per pixel row, 16 bytes per

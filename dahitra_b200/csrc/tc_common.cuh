@@ -251,6 +251,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 — two IEEE fp32 operations per issued instruction; the results are the
+// same as the scalar instructions', lane by lane)
+__device__ __forceinline__ unsigned long long f2_pack(float2 a) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ float2 f2_unpack(unsigned long long r) { float2 d; asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r)); return d; }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c))); return f2_unpack(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b))); return f2_unpack(d); }
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) { unsigned long long d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b))); return f2_unpack(d); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b))); return f2_unpack(d); }
+__device__ __forceinline__ float2 f2_bcast(float s) { return make_float2(s, s); }
+
 // float index of element (row r, column k) inside a K-major SWIZZLE_128B tile of 32-float rows
 __host__ __device__ __forceinline__ int sw128_idx(int r, int k) { return r * 32 + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3)); }
 
