@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdahitra_b200.so")
-SOURCES = ["conv_ffma.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "split.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "classifier.cu", "aux.cu", "forward.cu"]
+SOURCES = ["conv_ffma.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "split.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "classifier.cu", "prepare.cu", "aux.cu", "forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -76,6 +76,7 @@ SIGNATURES = {
     "dahitra_error_string": (C.c_char_p, [_I]),
     "dahitra_weight_slot_name": (C.c_char_p, [_I]),
     "dahitra_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
+    "dahitra_prepare_weights": (_LL, [_P, _I, _I, _I, _P, _LL, _P]),
     "dahitra_forward": (_I, [_P, _I, _P, _P, _LL, _P, _P, _P, _SZ, _I, _I, _I, _I, _I, _I, _P]),
     "dahitra_forward_profiled": (_I, [_P, _I, _P, _P, _LL, _P, _P, _P, _SZ, _I, _I, _I, _I, _I, _I, _P,
                                       _I, _P, _P, _P, _P]),
@@ -98,6 +99,11 @@ SIGNATURES = {
     "dahitra_maxpool3x3s2_split": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "dahitra_conv2d_split": (_I, [_P, _P, _I, _I, _LL, _LL, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _P]),
 }
+
+
+class DhTensor(C.Structure):
+    """struct dh_tensor of include/dahitra_b200.h"""
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("dtype", C.c_int), ("ndim", C.c_int), ("shape", C.c_longlong * 4)]
 
 
 def load():

@@ -308,39 +308,73 @@ def prepare_weights(sd: dict, variant: int, out_nc: int) -> dict:
     return {k: (None if v is None else v.to(torch.float32).contiguous()) for k, v in P.items()}
 
 
+def prepare_weights_c(sd: dict, variant: int, out_nc: int):
+    """The same preparation through the C ABI (`dahitra_prepare_weights`, csrc/prepare.cu — host code, no PyTorch inside):
+    -> (flat fp32 CPU tensor holding every slot, list of float offsets per slot, -1 = absent).  What a C / C++ consumer of
+    the library runs; engine.prepare_weights above is the executable specification it is tested against."""
+    lib = _lib.load()
+    keep, recs = [], []
+    for k, v in sd.items():
+        if not torch.is_tensor(v) or not v.dtype.is_floating_point or v.dim() > 4:
+            continue
+        t = v.detach().cpu().contiguous()
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.float()
+        keep.append((k.encode(), t))
+    arr = (_lib.DhTensor * len(keep))()
+    for i, (name, t) in enumerate(keep):
+        arr[i].name, arr[i].data = name, t.data_ptr()
+        arr[i].dtype, arr[i].ndim = (0 if t.dtype == torch.float32 else 1), t.dim()
+        for j, d in enumerate(t.shape):
+            arr[i].shape[j] = d
+    n = lib.dahitra_prepare_weights(arr, len(keep), variant, out_nc, None, 0, None)
+    if n <= 0:
+        _lib.check(int(n), "dahitra_prepare_weights")
+    flat = torch.zeros(n, dtype=torch.float32)
+    offs = (C.c_longlong * len(slot_names()))()
+    n2 = lib.dahitra_prepare_weights(arr, len(keep), variant, out_nc, flat.data_ptr(), n, offs)
+    if n2 != n:
+        _lib.check(int(n2) if n2 < 0 else -6, "dahitra_prepare_weights")
+    return flat, list(offs)
+
+
 class PreparedWeights:
-    """Device copies of the prepared tensors + the C pointer table handed to dahitra_forward."""
+    """Device copy of the prepared slots + the C pointer table handed to dahitra_forward.
+
+    The preparation itself runs in the library (`dahitra_prepare_weights`, csrc/prepare.cu: plain host C++, what a consumer
+    without PyTorch runs); DAHITRA_PREPARE=py selects the Python specification above instead (bit-identical slots,
+    tests/test_host_cpu.py)."""
 
     def __init__(self, sd, variant, out_nc, device):
         names = slot_names()
-        host = prepare_weights(sd, variant, out_nc)
-        missing = [n for n in names if n not in host]
-        if missing:
-            raise RuntimeError(f"weight preparation does not produce slots {missing}")
-        # one flat buffer, every slot 256-byte aligned
-        offs, total = {}, 0
-        for n in names:
-            if host[n] is not None:
-                offs[n] = total
-                total += (host[n].numel() + 63) // 64 * 64
-        flat = torch.zeros(total, dtype=torch.float32)
-        for n, o in offs.items():
-            flat[o:o + host[n].numel()] = host[n].reshape(-1)
+        if os.environ.get("DAHITRA_PREPARE", "c") == "py":
+            host = prepare_weights(sd, variant, out_nc)
+            missing = [n for n in names if n not in host]
+            if missing:
+                raise RuntimeError(f"weight preparation does not produce slots {missing}")
+            offs, total = {}, 0                     # one flat buffer, every slot 256-byte aligned
+            for n in names:
+                if host[n] is not None:
+                    offs[n] = total
+                    total += (host[n].numel() + 63) // 64 * 64
+            flat = torch.zeros(total, dtype=torch.float32)
+            for n, o in offs.items():
+                flat[o:o + host[n].numel()] = host[n].reshape(-1)
+        else:
+            flat, off_list = prepare_weights_c(sd, variant, out_nc)
+            offs = {n: o for n, o in zip(names, off_list) if o >= 0}
         self.flat = flat.to(device)
-        self.shapes = {n: (None if host[n] is None else tuple(host[n].shape)) for n in names}
         base = self.flat.data_ptr()
         self.table = (C.c_void_p * len(names))(*[(base + 4 * offs[n]) if n in offs else None for n in names])
         self.n = len(names)
         self.names = names
         self.offs = offs
-
-    def view(self, name):
-        o = self.offs[name]
-        shp = self.shapes[name]
-        n = 1
-        for d in shp:
-            n *= d
-        return self.flat[o:o + n].view(shp)
+        # positions each decoder positional-embedding slot covers (the forward checks them against the input size)
+        self.pos_positions = {}
+        for k in (5, 4, 3):
+            key = f"pos_embedding_decoder_{k}" if variant == DH_VARIANT_LEVIR else ("pos_embedding_decoder_3" if k == 5 else None)
+            if key is not None and key in sd and f"DH_W_LV{k}_POS" in offs:
+                self.pos_positions[f"DH_W_LV{k}_POS"] = int(sd[key].shape[2] * sd[key].shape[3])
 
     def ptr(self, name):
         return self.flat.data_ptr() + 4 * self.offs[name] if name in self.offs else None
@@ -438,10 +472,10 @@ class NativeEngine:
         variant = DH_VARIANT_LEVIR if module.VARIANT == "levir" else DH_VARIANT_XBD
         prep = self._prepared(module, dev)
         for name, hw in module.pos_shapes(H, W).items():
-            shp = prep.shapes.get(name)
-            if shp is not None and shp[0] != hw:
+            have = prep.pos_positions.get(name)
+            if have is not None and have != hw:
                 raise RuntimeError(
-                    f"dahitra_b200: decoder positional embedding {name} has {shp[0]} positions but the input needs {hw} "
+                    f"dahitra_b200: decoder positional embedding {name} has {have} positions but the input needs {hw} "
                     f"(the {module.VARIANT} variant only runs at the resolution its embeddings were built for, like the reference)")
         nc = module.output_nc
         ws = self._workspace(lib, dev, variant, B, H, W, nc)

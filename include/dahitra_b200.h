@@ -139,6 +139,21 @@ int         dahitra_version(void);
 const char* dahitra_error_string(int code);
 const char* dahitra_weight_slot_name(int slot);          /* "DH_W_STEM_W", ... ; NULL if out of range */
 
+/* ---- host-side weight preparation (no CUDA calls) ------------------------------------------------------------------
+ * Reference-layout state_dict tensors -> the prepared slot table above: BatchNorm folding, filter re-layout and operand
+ * planes, decoder collapse, swizzled images (csrc/prepare.cu; the same algebra as dahitra_b200/engine.py, in fp64).
+ *   tensors        the checkpoint's tensors by their reference key (models/networks.py state_dict; xBD variant:
+ *                  xBD_code/zoo/model_transformer_encoding.py), HOST pointers, contiguous, fp32 or fp64; unused keys ignored
+ *   out            host buffer for all slots (fp32), or NULL to query the size
+ *   slot_offsets   [DH_W_COUNT] float offset of every slot inside `out` (-1: slot absent, e.g. no positional embedding)
+ * Returns the number of floats needed / written (> 0), or a negative DH_E_* code (DH_E_WEIGHTS: a required key is missing
+ * or has the wrong number of elements).  Upload `out` with one copy; weights[i] = device_base + 4 * slot_offsets[i]. */
+#define DH_DTYPE_F32 0
+#define DH_DTYPE_F64 1
+typedef struct dh_tensor { const char* name; const void* data; int dtype; int ndim; long long shape[4]; } dh_tensor;
+long long dahitra_prepare_weights(const dh_tensor* tensors, int n_tensors, int variant, int output_nc,
+                                  float* out, long long out_floats, long long* slot_offsets);
+
 /* Bytes of scratch dahitra_forward needs for B pairs of HxW images (H, W multiples of 32). */
 size_t dahitra_workspace_bytes(int variant, int B, int H, int W, int output_nc, int flags);
 

@@ -446,3 +446,45 @@ def test_scheduling_flags_do_not_change_results(levir_template):
             net.set_mode(base | extra)
             assert torch.equal(net(x1, x2), y0), extra
     net.set_mode(_MODE)
+
+
+def test_forward_through_the_c_abi_only(levir_template):
+    """What a consumer without dahitra_b200/engine.py does (ctypes stub): checkpoint tensors ->
+    dahitra_prepare_weights (host) -> one upload -> dahitra_workspace_bytes -> dahitra_forward.  torch only owns memory."""
+    import ctypes as C
+    from dahitra_b200 import _lib
+    from dahitra_b200.engine import MODES
+    lib = _lib.load()
+    sd = synth.synth_state_dict(levir_template, seed=3, style="default")
+    keep = [(k.encode(), v.float().contiguous()) for k, v in sd.items() if v.dtype.is_floating_point]
+    arr = (_lib.DhTensor * len(keep))()
+    for i, (name, t) in enumerate(keep):
+        arr[i].name, arr[i].data, arr[i].dtype, arr[i].ndim = name, t.data_ptr(), 0, t.dim()
+        for j, d in enumerate(t.shape):
+            arr[i].shape[j] = d
+    n = lib.dahitra_prepare_weights(arr, len(keep), 0, 2, None, 0, None)
+    assert n > 0
+    host = torch.empty(n, dtype=torch.float32).pin_memory()
+    nslots = 0
+    while lib.dahitra_weight_slot_name(nslots) is not None:
+        nslots += 1
+    offs = (C.c_longlong * nslots)()
+    assert lib.dahitra_prepare_weights(arr, len(keep), 0, 2, host.data_ptr(), n, offs) == n
+    dev_w = host.to(DEV)
+    table = (C.c_void_p * nslots)(*[(dev_w.data_ptr() + 4 * o) if o >= 0 else None for o in offs])
+    B, H, W = 3, 256, 256
+    flags = MODES[_MODE]
+    ws = torch.empty(lib.dahitra_workspace_bytes(0, B, H, W, 2, flags), dtype=torch.uint8, device=DEV)
+    x1, x2 = synth.synth_pair(B, H, W, seed=2, kind="uniform")
+    d1, d2 = x1.to(DEV), x2.to(DEV)
+    logits = torch.empty((B, 2, H, W), dtype=torch.float32, device=DEV)
+    amax = torch.empty((B, H, W), dtype=torch.uint8, device=DEV)
+    rc = lib.dahitra_forward(table, nslots, d1.data_ptr(), d2.data_ptr(), 3 * H * W, logits.data_ptr(), amax.data_ptr(),
+                             ws.data_ptr(), ws.numel(), 0, B, H, W, 2, flags, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.dahitra_error_string(rc)
+    torch.cuda.synchronize()
+    check_logits(logits, O.forward_levir(sd, x1, x2, dtype=torch.float64), "C-ABI-only forward vs fp64 oracle")
+    assert torch.equal(amax.long(), logits.argmax(1))
+    net = make_net(sd)                                           # and identical to the module's own path
+    with torch.no_grad():
+        assert torch.equal(net(d1, d2), logits)

@@ -310,3 +310,44 @@ def test_xbd_variant_without_token_pos_prepares():
     assert "pos_embedding_3" not in net.state_dict()
     P = prepare_weights(net.state_dict(), 1, 5)
     assert float(P["DH_W_LV5_ENC"][:256].abs().sum()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------- C-ABI weight preparation
+@pytest.mark.parametrize("variant", ["levir", "xbd"])
+def test_c_prepare_weights_matches_python_specification(lib, variant):
+    """dahitra_prepare_weights (csrc/prepare.cu, plain C++ on the host) against engine.prepare_weights slot by slot: bit-exact
+    for everything that is a re-layout / fold / format conversion, <= 1 ulp(fp32) for the fp64 matrix products whose
+    summation order differs from torch's einsum."""
+    import torch
+    from dahitra_b200 import synth
+    from dahitra_b200.engine import prepare_weights, prepare_weights_c, slot_names
+    if variant == "levir":
+        from dahitra_b200.networks import BASE_Transformer_UNet
+        net = BASE_Transformer_UNet(3, 2, 'learned', resnet_stages_num=4, with_decoder_pos='learned', enc_depth=1, dec_depth=8)
+        vid, nc = 0, 2
+    else:
+        from dahitra_b200.xbd import BASE_Transformer_UNet as X
+        net = X(input_nc=3, output_nc=5, token_len=4, resnet_stages_num=4, with_pos="learned", with_decoder_pos="learned", enc_depth=1, dec_depth=8)
+        vid, nc = 1, 5
+    sd = synth.synth_state_dict(net.state_dict(), seed=21, style="default")
+    P = prepare_weights(sd, vid, nc)
+    flat, offs = prepare_weights_c(sd, vid, nc)
+    names = slot_names()
+    assert len(offs) == len(names)
+    products = ("_ENC", "_DEC", "_DECTC")                  # slots containing fp64 matrix products
+    for name, off in zip(names, offs):
+        ref = P[name]
+        if ref is None:
+            assert off == -1, name
+            continue
+        assert off >= 0 and off % 64 == 0, name
+        got = flat[off:off + ref.numel()].view(ref.shape)
+        if name.endswith(products):
+            assert torch.allclose(got, ref, rtol=3e-7, atol=1e-30), (name, float((got - ref).abs().max()))
+            assert float((got != ref).float().mean()) < 1e-3, name
+        else:
+            assert torch.equal(got.view(torch.int32), ref.view(torch.int32)), (name, float((got - ref).abs().max()))
+    # errors: a missing key is reported, not papered over
+    sd2 = {k: v for k, v in sd.items() if k != "resnet.layer2.0.bn1.running_var"}
+    with pytest.raises(RuntimeError, match="weight"):
+        prepare_weights_c(sd2, vid, nc)

@@ -20,6 +20,7 @@ class Args:
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--graph", action="store_true", help="capture forward + backward + AdamW step in ONE CUDA graph and replay it (1 GPU)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -33,7 +34,7 @@ model = net
 if world > 1:
     # like the reference, the module owns parameters its forward never uses (scale-2 transformer, conv_pred, layer4)
     model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
-opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01)           # models/trainer.py:39-40
+opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, capturable=a.graph)           # models/trainer.py:39-40
 g = torch.Generator(device="cuda").manual_seed(100 + rank)
 x1 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 x2 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
@@ -42,7 +43,13 @@ losses = []
 w2 = torch.ones(2, device="cuda")
 
 
+graph, static_loss = None, None
+
+
 def one_step(sync=True):
+    if graph is not None:
+        graph.replay()
+        return static_loss
     opt.zero_grad(set_to_none=True)
     ctx = model.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
     with ctx:
@@ -70,6 +77,23 @@ def timed(n, sync=True):
 
 for _ in range(3):                               # warm-up (cuDNN autotune, allocator, DDP bucket rebuild)
     losses.append(one_step().detach())
+if a.graph:
+    # whole-iteration capture: the ~3000 small launches of the stock-autograd route (the decoders work on (B*N, 32) token
+    # matrices) are replayed from one graph instead of being issued one by one from Python
+    assert world == 1, "--graph is the single-GPU variant"
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            one_step()
+    torch.cuda.current_stream().wait_stream(side)
+    g_ = torch.cuda.CUDAGraph()
+    opt.zero_grad(set_to_none=True)
+    with torch.cuda.graph(g_):
+        static_loss = F.cross_entropy(model(x1, x2), y, weight=w2, ignore_index=255)
+        static_loss.backward()
+        opt.step()
+    graph = g_
 step_ms = timed(a.steps)
 dt = step_ms * a.steps / 1e3
 if world > 1:                                   # replicas must hold identical weights after the all-reduced steps
@@ -109,7 +133,7 @@ with torch.no_grad():
 y_auto = net._forward_autograd(x1, x2).detach()
 native_vs_autograd = float((y_native - y_auto).abs().max())
 if rank == 0:
-    print(json.dumps(dict(workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW (autograd route"
+    print(json.dumps(dict(workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW ({'one CUDA graph per iteration, ' if a.graph else ''}autograd route"
                                    + (", DDP/NCCL all-reduce)" if world > 1 else ")"),
                           steps=a.steps, step_ms=step_ms, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
                           pairs_per_s_per_gpu=a.steps * a.batch / dt,
