@@ -10,7 +10,8 @@ reference with the reference's own fp32 noise as the yardstick.
 Every test runs in both shipped precision modes: "fp32" (strict, CUDA cores) and "tf32x3" (the default:
 tensor cores with error-compensated 3xTF32).  In tf32x3 mode the north-star tolerance is asserted unchanged on
 the define_G random-init weights it is stated for; on the ill-conditioned synthetic weights the absolute term is
-widened to 1e-3 of the logit range (tensor-core accumulation truncates instead of rounding; measured ~3e-4).
+widened to 2e-4 of the logit range (measured <= 7e-5 of the range; what remains is the tensor core's non-rounding fp32
+accumulation: tests/test_gpu_blocks.py::test_conv2d_split16 isolates it on exactly representable operands).
 """
 import json
 import os
@@ -26,7 +27,7 @@ from test_oracle_golden import CASES, case_inputs, Args
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 ATOL, RTOL = 1e-4, 1e-3
-X3_RANGE_TOL = 1e-3          # tf32x3 on ill-conditioned weights: |d| <= 1e-3 * max|ref|
+X3_RANGE_TOL = 2e-4          # tf32x3 on ill-conditioned weights: |d| <= 2e-4 * max|ref| (measured <= 7e-5; round 1: 1e-3)
 _MODE = "fp32"
 
 
@@ -334,7 +335,7 @@ def test_tensor_core_modes(mode, weights, levir_template):
     elif weights == "defineG":
         assert strict_bad == 0 and agree >= 0.999
     elif mode.startswith("tf32x3"):
-        assert float(d.max()) <= 1e-3 * float(ref.abs().max()) and agree >= 0.9999
+        assert float(d.max()) <= 2e-4 * float(ref.abs().max()) and agree >= 0.9999
     else:
         assert float(d.mean()) <= 3.0 * float(dt.mean()) + 1e-5
         assert agree >= min(0.999, agree_t - 0.002)

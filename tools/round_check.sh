@@ -1,18 +1,19 @@
 #!/bin/bash
-# Round-end style check in one gpurun call: full GPU suite, smoke(), default bench, tf32 bench, reference arm,
-# ncu launch list + full capture of the dominant kernels (default mode).  Everything lands in gpurun_out/.
-TAG=${1:-r01}
+# Round-end style check in one gpurun call (release build): full GPU suite, smoke(), default bench (+ kernel dump), xBD bench,
+# reference arm, small-batch latency, precision ablation.  Everything lands in gpurun_out/.
+TAG=${1:-r02}
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -4) > gpurun_out/pytest_gpu_$TAG.log 2>&1
-(timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3) > gpurun_out/smoke_$TAG.log 2>&1
-(timeout 600 python bench.py 2>&1 | tail -1) > gpurun_out/bench_default_$TAG.json 2>&1
-(timeout 600 python bench.py --mode tf32 --no-cpu-baseline --dump-kernels gpurun_out/kernels_tf32_$TAG.json 2>&1 | tail -1) > gpurun_out/bench_tf32_$TAG.json 2>&1
-(timeout 600 python bench.py --no-cpu-baseline --dump-kernels gpurun_out/kernels_tf32x3_$TAG.json 2>&1 | tail -1) > /dev/null 2>&1
-(timeout 600 python bench.py --workload xbd1024 --no-cpu-baseline 2>&1 | tail -1) > gpurun_out/bench_xbd1024_$TAG.json 2>&1
-(timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1) > gpurun_out/bench_reference_$TAG.json 2>&1
-(timeout 300 python tools/latency_small_batch.py 2>&1 | tail -1) > gpurun_out/latency_b4_$TAG.json 2>&1
-(timeout 300 python tools/latency_small_batch.py --mode tf32 2>&1 | tail -1) >> gpurun_out/latency_b4_$TAG.json 2>&1
-tools/ncu_capture.sh tf32x3 $TAG "conv_tc2_kernel pixel_decoder_tc_kernel stem_f16_kernel" > gpurun_out/ncu_capture_stdout_$TAG.log 2>&1
-tail -3 gpurun_out/pytest_gpu_$TAG.log gpurun_out/smoke_$TAG.log
-for f in default tf32 xbd1024 reference; do cut -c1-330 gpurun_out/bench_${f}_$TAG.json; done
-cat gpurun_out/latency_b4_$TAG.json
+(timeout 1800 python -m pytest tests -q -m gpu 2>&1 | tail -6) > gpurun_out/${TAG}_pytest_gpu.log 2>&1
+(timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3) > gpurun_out/${TAG}_smoke.log 2>&1
+(timeout 600 python bench.py --dump-kernels gpurun_out/${TAG}_kernels_tf32x3.json 2>gpurun_out/${TAG}_bench.err | tail -1) > gpurun_out/${TAG}_bench_default_tf32x3.json
+(timeout 600 python bench.py --workload xbd1024 --dump-kernels gpurun_out/${TAG}_kernels_xbd1024_tf32x3.json 2>/dev/null | tail -1) > gpurun_out/${TAG}_bench_xbd1024_tf32x3.json
+for m in tf32x3_fp32act f16 bf16 tf32; do
+(timeout 600 python bench.py --mode $m --no-cpu-baseline --no-parity 2>/dev/null | tail -1) > gpurun_out/${TAG}_bench_$m.json
+done
+(timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1) > gpurun_out/${TAG}_bench_reference_cpu.json
+rm -f gpurun_out/${TAG}_latency_small_batch.jsonl
+for b in 1 4 8 16; do (timeout 300 python tools/latency_small_batch.py --batch $b 2>/dev/null | tail -1) >> gpurun_out/${TAG}_latency_small_batch.jsonl; done
+(timeout 600 python tools/ablate_flags.py 2>/dev/null) > gpurun_out/${TAG}_precision_ablation.txt
+tail -3 gpurun_out/${TAG}_pytest_gpu.log gpurun_out/${TAG}_smoke.log
+for f in default_tf32x3 xbd1024_tf32x3 tf32x3_fp32act f16 bf16 tf32 reference_cpu; do cut -c1-200 gpurun_out/${TAG}_bench_$f.json; done
+cat gpurun_out/${TAG}_latency_small_batch.jsonl | cut -c1-260
