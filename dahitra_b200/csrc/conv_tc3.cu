@@ -19,7 +19,9 @@
 // each plane is fetched ONCE by a 4-D TMA box {32 ch, 10, 18, 1} (SWIZZLE_64B, zero fill outside the image = the conv
 // padding) and serves all nine taps through shifted-window UMMA descriptors (start + (r*10+s) pixels, SBO = 10 pixels);
 // stride 2 reads the four phase images with TMA element strides; persistent CTAs, two TMEM accumulators.
-// Warp roles: 0 = halo TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue, 6 = filter TMA producer.
+// Warp roles: 0 = halo TMA producer, 1 = TMEM alloc + MMA issuer, 6 = filter TMA producer, 2..5 and 7..10 = two epilogue
+// warpgroups: group g drains accumulator g (the even / odd tiles of the CTA), so two epilogues are in flight under the main
+// loop — the epilogue-heavy shapes (tokenizer squeeze, pixel-shuffle convs, residual + split16 stores) were bound by one.
 //
 // Epilogue outputs: fp32 NHWC (optionally as the pixel-shuffle scatter of the upsample convolutions) or split16 planes;
 // the residual may be fp32 or split16.  TOK epilogue (1x1 squeeze convolution of the tokenizer, reference
@@ -63,8 +65,7 @@ template <int NT, bool RES, int CG = 1> struct T3Cfg {
   static constexpr uint32_t B_TAP = 2u * NT * 64u / CG;                  // [h_w ; l_w] x 64 B: NT rows each, NT / 2 in a CTA of a pair
   static constexpr uint32_t B_STAGE = B_TAP * TPS;
   static constexpr uint32_t RING_BYTES = RES ? 0u : STAGES * B_STAGE;    // RES: the filter image follows the halo buffers instead
-  static constexpr uint32_t FIXED = 4 * 4096 + 512 + 4 * 4 * 34 * 4 + 1024;   // epilogue staging + tok scratch + alignment slack
-  static constexpr int THREADS = 224;
+  static constexpr int THREADS = 352;                                    // 11 warps: halo, MMA, epilogue A x4, filter, epilogue B x4
   static constexpr uint32_t IDESC_WIDE = umma_idesc_f16(128, 2 * NT);
   static constexpr uint32_t IDESC_NARROW = umma_idesc_f16(128 * CG, NT);
   static constexpr int ACC_COLS = 2 * NT;
@@ -161,7 +162,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
   constexpr int TPS = (SD == 1 && NTAPS % Cfg::TPS == 0) ? Cfg::TPS : 1;
   constexpr int HALO_W = (KS == 3) ? T3_HW : T3_TW;
   const uint32_t w_bytes = RES ? (uint32_t)(e.ncout_tiles * e.cchunks * NTAPS) * Cfg::B_TAP : Cfg::RING_BYTES;
-  const uint32_t epi_off = (uint32_t)HB * T3_HALO + w_bytes;            // epilogue staging (4 warps x 4 KB), then the tok scratch
+  const uint32_t epi_off = (uint32_t)HB * T3_HALO + w_bytes;            // epilogue staging (8 warps x 4 KB), then the tok scratch
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < T3_MAX_HB; ++i) { mbar_init(smem_u32(&halo_full[i]), 1); mbar_init(smem_u32(&halo_empty[i]), 1); }
@@ -177,7 +178,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
     else         tmem_alloc(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
   }
   if (EPI == EPI_TOK && threadIdx.x >= 64 && threadIdx.x < 96)          // wtok [32][4] -> shared (weights: not produced by the previous launch)
-    reinterpret_cast<float4*>(base_ptr + epi_off + 4 * 4096)[threadIdx.x - 64] = __ldg(reinterpret_cast<const float4*>(e.wtok) + (threadIdx.x - 64));
+    reinterpret_cast<float4*>(base_ptr + epi_off + 8 * 4096)[threadIdx.x - 64] = __ldg(reinterpret_cast<const float4*>(e.wtok) + (threadIdx.x - 64));
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();                      // the peer's barriers are initialised before anything signals them
@@ -321,19 +322,20 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
         if (CG == 2) umma_commit_2sm(smem_u32(&acc_full[ab])); else umma_commit(smem_u32(&acc_full[ab]));
       }
     }
-  } else if (warp < 6) {                                        // ---------------- epilogue (warps 2..5)
+  } else {                                                      // ---------------- epilogue (warps 2..5 = group 0, 7..10 = group 1)
     // Thread = accumulator row (pixel).  Every 32-channel slab goes through a per-warp shared-memory transpose so that the
     // global accesses are 4 lanes x 8 channels per pixel row: whole 128-byte lines of an fp32 tensor, 64-byte segments of
     // each split16 plane, 16 bytes per lane either way, 8 pixel rows per instruction.
-    const int q = warp & 3;
-    float* stage = reinterpret_cast<float*>(base_ptr + epi_off + (size_t)q * 4096);        // [32 rows][8 chunks ^ (row & 7)][4]
-    const float* wtok_s = reinterpret_cast<const float*>(base_ptr + epi_off + 4 * 4096);   // [32][4]
-    float* tokred = reinterpret_cast<float*>(base_ptr + epi_off + 4 * 4096 + 512);         // [4 warps][4 tokens][34]
+    const int q = warp & 3, grp = warp >= 7 ? 1 : 0;            // q: the TMEM lane quarter this warp may read (warp id mod 4)
+    float* stage = reinterpret_cast<float*>(base_ptr + epi_off + (size_t)(grp * 4 + q) * 4096);   // [32 rows][8 chunks ^ (row & 7)][4]
+    const float* wtok_s = reinterpret_cast<const float*>(base_ptr + epi_off + 8 * 4096);          // [32][4]
+    float* tokred = reinterpret_cast<float*>(base_ptr + epi_off + 8 * 4096 + 512 + grp * 2176);   // [4 warps][4 tokens][34] per group
     const int c4 = lane & 3, r4 = lane >> 2;                    // lane -> (8-channel group, row within a group of 8)
     constexpr int NSLAB = NT / 32;
     const char* resb = reinterpret_cast<const char*>(e.res);
     int it = 0;
     for (int tile = w0; tile < e.ntiles; tile += wstep, ++it) {
+      if ((it & 1) != grp) continue;                             // this group owns accumulator `grp`
       const Tile3 t = tile3(tile, e, CG, rank);
       const int n0 = t.ct * NT;
       size_t rowoff[4];                                          // element offset of (pixel, channel group) for this lane's 4 rows
@@ -450,7 +452,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
           }
 #pragma unroll
           for (int l = 0; l < 4; ++l) tokred[(q * 4 + l) * 34 + 2 + lane] = ts[l];
-          asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the four warps of this epilogue group
           // warp q merges token l = q across the four warps and writes the tile's partial
           {
             const int l = q;
@@ -471,7 +473,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant
               pp[2 + lane] = T;
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");          // tokred is free for the next tile
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // tokred is free for the next tile
         }
         __syncwarp();                                            // the staging rows are free for the next slab
       }
@@ -677,7 +679,7 @@ int dh_launch_conv_tc3(const Conv3Args& a, cudaStream_t s) {
   // resident filter when the whole [h_w ; l_w] image (a CTA of a pair: its half) fits next to two halo buffers, and every
   // CTA walks enough tiles to amortise loading it (otherwise the streaming ring, whose first MMA starts after one stage)
   const uint32_t w_bytes = (uint32_t)K * (uint32_t)a.Cout * 4u / (uint32_t)cg;   // = ncout_tiles * cchunks * taps * B_TAP
-  const uint32_t fixed = 4 * 4096 + 512 + 4 * 4 * 34 * 4 + 1024;
+  const uint32_t fixed = 8 * 4096 + 1024 + (a.tok ? 512 + 2 * 2176 : 0);   // epilogue staging (8 warps) + alignment slack (+ tok scratch)
   const bool res_ok = w_bytes + 2 * T3_HALO + fixed <= T3_SMEM_MAX && !a.force_stream && !env_stream && e.ntiles >= 2 * nwork;
   if (res_ok) {
     int hb = (int)((T3_SMEM_MAX - fixed - w_bytes) / T3_HALO);
