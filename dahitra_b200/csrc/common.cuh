@@ -109,7 +109,7 @@ bool dh_conv_tc2_eligible(const ConvArgs& a);                     // stride-1 ha
 int dh_launch_conv_tc2(const ConvArgs& a, int xm, int cg, cudaStream_t s);
 int dh_launch_stem(const float* x, long long xbs, int N, int H, int W, const float* w, const float* b, float* out, cudaStream_t s);
 int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const float* wtc, const float* b, float* out, int x3,
-                      cudaStream_t s, long long split_plane_pitch = 0);
+                      cudaStream_t s, long long split_plane_pitch = 0, const float* x_second = nullptr);
 int dh_launch_maxpool(const float* in, int N, int H, int W, int C, float* out, cudaStream_t s);
 int dh_launch_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* b,
                          float* logits, unsigned char* amax, cudaStream_t s);

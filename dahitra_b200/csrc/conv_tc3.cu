@@ -636,7 +636,16 @@ int dh_launch_conv_tc3(const Conv3Args& a, cudaStream_t s) {
   DH_REQUIRE(dh_aligned16(a.in0) && dh_aligned16(a.in1) && dh_aligned16(a.wt16) && dh_aligned16(a.out) &&
              dh_aligned16(a.bias) && dh_aligned16(a.res) && dh_aligned16(a.wtok), DH_E_ALIGN);
   const int Cin = a.C0 + a.C1, K = a.K * a.K * Cin;
-  const int NT = a.Cout >= 128 ? 128 : a.Cout;
+  int sms_ = 148, dev_ = 0;
+  cudaGetDevice(&dev_);
+  cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
+  // N tile: 128 output channels — unless that leaves SMs without a tile (small batches: layer3 at 8 pairs has 64 tiles of
+  // 128 channels, each a serial chain of 72 (tap, chunk) steps): then 64-channel tiles spread the same work over twice the CTAs
+  int NT = a.Cout >= 128 ? 128 : a.Cout;
+  if (NT == 128 && !a.ps) {
+    const int mt = dh_cdiv(a.inW / a.stride, T3_TW) * dh_cdiv(a.inH / a.stride, T3_TH) * a.N;
+    if (mt * (a.Cout / 128) < sms_) NT = 64;
+  }
   const int hw = (a.K == 3) ? T3_HW : T3_TW, hh = (a.K == 3) ? T3_HH : T3_TH;
   CUtensorMap A[4], Bm;
   const size_t plane0 = a.in0_plane ? (size_t)a.in0_plane : (size_t)a.N * a.inH * a.inW * a.C0;

@@ -373,8 +373,9 @@ int forward_split(const Plan& p, const void* const* weights, const float* x1, co
   float* F2post = reinterpret_cast<float*>(H16(F2) + f2_half);             // hi plane of the post images
   const double stem_fl = 2.0 * B * h2 * w2 * 64 * 147, stem_by = 4.0 * B * ((double)3 * H * W + (double)h2 * w2 * 64);
   const int stem_mode = ((flags & DH_FLAG_TC_3XTF32) ? 2 : 3) | 256;
-  DH_STEP("stem_pre", stem_fl, stem_by, dh_launch_stem_tc(x1, x_batch_stride, B, H, W, Wt(DH_W_STEM_WTC), Wt(DH_W_STEM_B), F2, stem_mode, s, f2_plane));
-  DH_STEP("stem_post", stem_fl, stem_by, dh_launch_stem_tc(x2, x_batch_stride, B, H, W, Wt(DH_W_STEM_WTC), Wt(DH_W_STEM_B), F2post, stem_mode, s, f2_plane));
+  // one launch over both image sets (pre images first): x2 is addressed through a second tensor map
+  DH_STEP("stem", 2.0 * stem_fl, 2.0 * stem_by,
+          dh_launch_stem_tc(x1, x_batch_stride, B, H, W, Wt(DH_W_STEM_WTC), Wt(DH_W_STEM_B), F2, stem_mode, s, f2_plane, x2));
   float* P2 = ws + p.p2;
   DH_STEP("maxpool_2", 0.0, 4.0 * N2 * 64 * ((double)h2 * w2 + (double)h4 * w4), dh_launch_maxpool_split(F2, N2, h2, w2, 64, P2, s));
   float *T4a = ws + p.t4a, *T4b = ws + p.t4b, *F4 = ws + p.f4;

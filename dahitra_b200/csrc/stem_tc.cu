@@ -59,8 +59,9 @@ __device__ __forceinline__ SkTile sk_tile(int t, int tilesX, int tilesY) {
 
 // Halo producer (one lane): ONE TMA box per tile over the NCHW tensor, double-buffered through halo_full / halo_free.
 // x start must be 16-byte aligned: the box starts one column left of the first tap.
+// Images 0..nfirst-1 come from tmX, the rest from tmX2 (the pre / post image sets of one forward in ONE launch).
 __device__ __forceinline__ void sk_halo_producer(const CUtensorMap* tmX, uint32_t halo_addr, uint64_t* halo_full, uint64_t* halo_free,
-                                                 int tilesX, int tilesY, int ntiles) {
+                                                 int tilesX, int tilesY, int ntiles, const CUtensorMap* tmX2 = nullptr, int nfirst = 1 << 30) {
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int hb = it & 1;
@@ -68,7 +69,8 @@ __device__ __forceinline__ void sk_halo_producer(const CUtensorMap* tmX, uint32_
     const SkTile tl = sk_tile(tile, tilesX, tilesY);
     const uint32_t bar = smem_u32(&halo_full[hb]);
     mbar_expect_tx(bar, SK_HALO_BYTES);
-    tma_load_4d(halo_addr + (uint32_t)hb * SK_HALO_STRIDE, tmX, bar, 2 * tl.ox0 - 4, 2 * tl.oy0 - 3, 0, tl.n);
+    const bool second = tl.n >= nfirst;
+    tma_load_4d(halo_addr + (uint32_t)hb * SK_HALO_STRIDE, second ? tmX2 : tmX, bar, 2 * tl.ox0 - 4, 2 * tl.oy0 - 3, 0, second ? tl.n - nfirst : tl.n);
   }
 }
 
@@ -281,8 +283,9 @@ constexpr size_t SF_IMAGE_OFFSET_FLOATS = 2 * (SK_B_BYTES / 4);      // the 16-b
 
 template <bool FOLD>   // FOLD = false: single-pass FP16 operands (rows 0..63 of the same filter tiles, no remainder products)
 __global__ void __launch_bounds__(SK_THREADS, 1)
-stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int tilesX, int tilesY, int ntiles,
-                const float* __restrict__ wtc, const float* __restrict__ bias, float* __restrict__ out, long long split_plane) {
+stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2, int nfirst, int OH, int OW, int tilesX,
+                int tilesY, int ntiles, const float* __restrict__ wtc, const float* __restrict__ bias, float* __restrict__ out,
+                long long split_plane) {
   extern __shared__ uint8_t sk_raw[];
   __shared__ __align__(8) uint64_t w_bar, a_full[SF_NBUF], a_free[SF_NBUF], acc_full[2], acc_empty[2], halo_full[2], halo_free[2];
   __shared__ uint32_t tmem_slot;
@@ -385,7 +388,7 @@ stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int til
     }
   } else if (warp == 13) {
     // ------------------------------------------------------------------ halo producer (warp 13, one lane)
-    if ((tid & 31) == 0) sk_halo_producer(&tmX, base + SF_OFF_H, halo_full, halo_free, tilesX, tilesY, ntiles);
+    if ((tid & 31) == 0) sk_halo_producer(&tmX, base + SF_OFF_H, halo_full, halo_free, tilesX, tilesY, ntiles, &tmX2, nfirst);
   } else if ((tid & 31) == 0) {
     // ------------------------------------------------------------------ MMA issuer (warp 12, one lane)
     mbar_expect_tx(smem_u32(&w_bar), SF_BM_BYTES + SF_BC_BYTES);
@@ -434,9 +437,12 @@ stem_f16_kernel(const __grid_constant__ CUtensorMap tmX, int OH, int OW, int til
 // x3: 0 = 1xTF32, 1 = 3xTF32, 2 = folded FP16, 3 = single-pass FP16; bit 8 (x3 | 256, modes 2 / 3 only): `out` receives the
 // split16 planes conv_tc3.cu consumes instead of fp32
 int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const float* wtc, const float* b, float* out,
-                      int x3, cudaStream_t s, long long split_plane_pitch) {
+                      int x3, cudaStream_t s, long long split_plane_pitch, const float* x_second) {
+  // x_second != NULL (forms 2 / 3): ONE launch over 2N images — N from x, then N from x_second (same strides) — writing one
+  // [2N]-image output tensor: the pre and post image sets of a forward without a second launch
   const bool split = (x3 & 256) != 0;
   x3 &= 255;
+  DH_REQUIRE(!x_second || x3 == 2 || x3 == 3, DH_E_VARIANT);
   DH_REQUIRE(!split || x3 == 2 || x3 == 3, DH_E_VARIANT);
   DH_REQUIRE(x && wtc && b && out, DH_E_NULL);
   DH_REQUIRE(N > 0 && H >= 8 && W >= 8 && H % 2 == 0 && W % 2 == 0, DH_E_SHAPE);
@@ -444,9 +450,10 @@ int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const 
   DH_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3u) == 0, DH_E_ALIGN);
   const int OH = H / 2, OW = W / 2;
   const int tx = dh_cdiv(OW, SK_TW), ty = dh_cdiv(OH, SK_TH);
-  const int ntiles = tx * ty * N;
-  // elements between the hi and lo planes: this call's own N images, or the pitch of a larger tensor it writes a part of
-  const long long split_plane = split ? (split_plane_pitch ? split_plane_pitch : (long long)N * OH * OW * 64) : 0;
+  const int nimg = x_second ? 2 * N : N;
+  const int ntiles = tx * ty * nimg;
+  // elements between the hi and lo planes: this call's own images, or the pitch of a larger tensor it writes a part of
+  const long long split_plane = split ? (split_plane_pitch ? split_plane_pitch : (long long)nimg * OH * OW * 64) : 0;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -460,14 +467,24 @@ int dh_launch_stem_tc(const float* x, long long xbs, int N, int H, int W, const 
     const int rc = dh_encode_tiled_f32(&tmX, x, 4, dims, strides, box, false);
     if (rc) return rc;
   }
+  CUtensorMap tmX2 = tmX;
+  if (x_second) {
+    DH_REQUIRE(dh_aligned16(x_second), DH_E_ALIGN);
+    const unsigned long long dims[4] = {(unsigned long long)W, (unsigned long long)H, 3ull, (unsigned long long)N};
+    const unsigned long long strides[3] = {(unsigned long long)W * 4, (unsigned long long)H * W * 4, (unsigned long long)xbs * 4};
+    const unsigned box[4] = {(unsigned)SK_HCP, (unsigned)SK_HR, 3u, 1u};
+    const int rc = dh_encode_tiled_f32(&tmX2, x_second, 4, dims, strides, box, false);
+    if (rc) return rc;
+  }
+  const int nfirst = x_second ? N : (1 << 30);
   if (x3 == 2) {
     cudaError_t e = cudaFuncSetAttribute(stem_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
     if (e != cudaSuccess) return (int)e;
-    return dh_launch(stem_f16_kernel<true>, grid, dim3(SK_THREADS), SF_SMEM, s, tmX, OH, OW, tx, ty, ntiles, wtc, b, out, split_plane);
+    return dh_launch(stem_f16_kernel<true>, grid, dim3(SK_THREADS), SF_SMEM, s, tmX, tmX2, nfirst, OH, OW, tx, ty, ntiles, wtc, b, out, split_plane);
   } else if (x3 == 3) {
     cudaError_t e = cudaFuncSetAttribute(stem_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
     if (e != cudaSuccess) return (int)e;
-    return dh_launch(stem_f16_kernel<false>, grid, dim3(SK_THREADS), SF_SMEM, s, tmX, OH, OW, tx, ty, ntiles, wtc, b, out, split_plane);
+    return dh_launch(stem_f16_kernel<false>, grid, dim3(SK_THREADS), SF_SMEM, s, tmX, tmX2, nfirst, OH, OW, tx, ty, ntiles, wtc, b, out, split_plane);
   } else if (x3) {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SkCfg<true>::SMEM);
     if (e != cudaSuccess) return (int)e;

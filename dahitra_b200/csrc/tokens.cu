@@ -182,13 +182,37 @@ token_encoder_kernel(const float* __restrict__ partials, int B, int nchunk, cons
     float M = -INFINITY;
     for (int k = lane; k < nchunk; k += 32) M = fmaxf(M, __ldg(pp + (size_t)k * 4 * 34));
     M = warp_max(M);
-    float S = 0.f, T = 0.f;
-    for (int k = 0; k < nchunk; ++k) {
-      const float* q = pp + (size_t)k * 4 * 34;
-      const float sc = expf(__ldg(q) - M);
-      S = fmaf(__ldg(q + 1), sc, S);
-      T = fmaf(__ldg(q + 2 + lane), sc, T);
+    // merge in groups of 32 chunks: lane j evaluates the rescaling factor of chunk k0 + j once (one exp per chunk instead of
+    // one per chunk AND lane), then every lane (= channel) accumulates its t over the group with the factors broadcast by
+    // shuffle; 16 loads per lane are in flight at a time (the 1024^2 inputs have 512 chunks)
+    float S = 0.f, T0 = 0.f, T1 = 0.f, T2 = 0.f, T3 = 0.f;
+    for (int k0 = 0; k0 < nchunk; k0 += 32) {
+      const int kk = k0 + lane;
+      float sc = 0.f;
+      if (kk < nchunk) {
+        const float* q = pp + (size_t)kk * 4 * 34;
+        sc = expf(__ldg(q) - M);
+        S = fmaf(__ldg(q + 1), sc, S);
+      }
+      const int n = min(32, nchunk - k0);
+      const float* tq = pp + (size_t)k0 * 4 * 34 + 2 + lane;
+      int j = 0;
+      for (; j + 16 <= n; j += 16) {                            // 16 loads in flight per lane (each an L2 round trip)
+        float a[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) a[u] = __ldg(tq + (size_t)(j + u) * 136);
+#pragma unroll
+        for (int u = 0; u < 16; u += 4) {
+          T0 = fmaf(a[u + 0], __shfl_sync(0xffffffffu, sc, j + u + 0), T0);
+          T1 = fmaf(a[u + 1], __shfl_sync(0xffffffffu, sc, j + u + 1), T1);
+          T2 = fmaf(a[u + 2], __shfl_sync(0xffffffffu, sc, j + u + 2), T2);
+          T3 = fmaf(a[u + 3], __shfl_sync(0xffffffffu, sc, j + u + 3), T3);
+        }
+      }
+      for (; j < n; ++j) T0 = fmaf(__ldg(tq + (size_t)j * 136), __shfl_sync(0xffffffffu, sc, j), T0);
     }
+    S = warp_sum(S);
+    const float T = (T0 + T1) + (T2 + T3);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                            // the encoder pack is in shared memory
     float v = T / S;
