@@ -195,6 +195,35 @@ class PixelDecoder(nn.Module):
             x = ff(attn(x, m))
         return x
 
+    def forward_collapsed(self, x, m):
+        """The same function (reference models/help_funcs.py:66-114,170-186) evaluated in the collapsed algebra the native
+        kernel uses, with plain differentiable torch ops — the training route's default.  The 4 memory tokens are constant
+        over the pixels, so per image and head the key / value projections fold into two small matrices:
+            dots = LN0(x) @ (g * A) + b @ A,   A[c, (h, j)] = dim^-0.5 sum_d Wq[hd, c] k[j, hd]
+            x   += softmax_j(dots) @ Bv + b_o,  Bv[(h, j), c] = sum_d Wo[c, hd] v[j, hd]
+        and the LayerNorm affine of the pixel side folds into A / W1 (LN0 = normalisation without affine), so nothing of size
+        (B, N, heads * 64) is ever formed and no LayerNorm weight gradient is reduced over the B * N pixel rows: gradients
+        reach Wq, Wk, Wv, Wo and the LayerNorm parameters through the small matrices.  x: (B, N, 32), m: (B, 4, 32)."""
+        B, N, C = x.shape
+        for attn, ff in self.layers:
+            norm, ca = attn.fn.norm, attn.fn.fn
+            H = ca.heads
+            mn = norm(m)                                                     # (B, 4, C): PreNorm2 shares the layer's LayerNorm
+            k = ca.to_k(mn).view(B, -1, H, ca.to_k.out_features // H)       # (B, 4, H, D)
+            v = ca.to_v(mn).view(B, -1, H, ca.to_v.out_features // H)
+            D = k.shape[-1]
+            A = torch.einsum("hdc,bjhd->bchj", ca.to_q.weight.view(H, D, C), k).reshape(B, C, -1) * ca.scale    # (B, C, 4H)
+            Bv = torch.einsum("chd,bjhd->bhjc", ca.to_out[0].weight.view(C, H, D), v).reshape(B, -1, C)         # (B, 4H, C)
+            xn = torch.nn.functional.layer_norm(x, (C,), None, None, norm.eps)
+            dots = torch.baddbmm((norm.bias @ A).unsqueeze(1), xn, norm.weight[None, :, None] * A)              # (B, N, 4H)
+            p = dots.view(B, N, H, -1).softmax(-1).view(B, N, -1)
+            x = x + torch.baddbmm(ca.to_out[0].bias.view(1, 1, C), p, Bv)
+            norm2, l1, l2 = ff.fn.norm, ff.fn.fn.net[0], ff.fn.fn.net[3]
+            xn2 = torch.nn.functional.layer_norm(x, (C,), None, None, norm2.eps)
+            h = torch.addmm(l1.bias + l1.weight @ norm2.bias, xn2.reshape(B * N, C), (l1.weight * norm2.weight[None, :]).t())
+            x = x + torch.addmm(l2.bias, torch.nn.functional.gelu(h), l2.weight.t()).view(B, N, C)
+        return x
+
 
 def two_layer_head(cin: int, cout: int) -> nn.Sequential:
     """keys 0.weight, 1.*, 3.{weight,bias}  (models/help_funcs.py:7-15)."""

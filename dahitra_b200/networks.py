@@ -89,6 +89,9 @@ class BASE_Transformer_UNet(nn.Module):
         self.conv_layer4 = nn.Sequential(nn.Conv2d(32, 32, 3, padding=1), nn.ReLU())
         self.classifier = nn.Conv2d(32, output_nc, 3, padding=1)
         self.output_nc = output_nc
+        # training route: evaluate the pixel decoders in the collapsed algebra (modules.PixelDecoder.forward_collapsed: the same
+        # function, ~16x smaller intermediates); False = the reference's as-written projections
+        self.collapsed_training = True
         # native engine (lazy: weights are folded / re-laid-out on the first inference call)
         self._engine = NativeEngine()
 
@@ -155,7 +158,8 @@ class BASE_Transformer_UNet(nn.Module):
             b, c, h, w = x.shape
             if self.with_decoder_pos == 'learned':
                 x = x + getattr(self, f"pos_embedding_decoder_{k}")
-            return dec(x.flatten(2).transpose(1, 2), m).transpose(1, 2).reshape(b, c, h, w)
+            run = dec.forward_collapsed if getattr(self, "collapsed_training", True) else dec
+            return run(x.flatten(2).transpose(1, 2), m).transpose(1, 2).reshape(b, c, h, w)
 
         x1, x2 = sq(f1), sq(f2)
         tok = torch.cat([tokens(x1), tokens(x2)], dim=1)

@@ -76,6 +76,7 @@ class BASE_Transformer_UNet(_LevirNet):
         self.conv_layer4 = nn.Sequential(nn.Conv2d(32, 32, 3, padding=1), nn.ReLU())
         self.classifier = nn.Conv2d(32, output_nc, 3, padding=1)
         self.output_nc = output_nc
+        self.collapsed_training = True          # training route: pixel decoders in the collapsed algebra (see networks.py)
         self._engine = NativeEngine()
 
     def pos_shapes(self, H, W):
@@ -107,4 +108,5 @@ class BASE_Transformer_UNet(_LevirNet):
         if self.with_decoder_pos == 'learned' and k == 5:
             dx = dx + self.pos_embedding_decoder_3
         b, c, h, w = dx.shape
-        return dec(dx.flatten(2).transpose(1, 2), (t2 - t1).abs()).transpose(1, 2).reshape(b, c, h, w)
+        run = dec.forward_collapsed if getattr(self, "collapsed_training", True) else dec
+        return run(dx.flatten(2).transpose(1, 2), (t2 - t1).abs()).transpose(1, 2).reshape(b, c, h, w)

@@ -351,3 +351,28 @@ def test_c_prepare_weights_matches_python_specification(lib, variant):
     sd2 = {k: v for k, v in sd.items() if k != "resnet.layer2.0.bn1.running_var"}
     with pytest.raises(RuntimeError, match="weight"):
         prepare_weights_c(sd2, vid, nc)
+
+
+def test_collapsed_decoder_training_route_equals_as_written():
+    """modules.PixelDecoder.forward_collapsed (the training route's default) is the same function as the reference's
+    as-written decoder (help_funcs.py:66-114,170-186): outputs and ALL parameter / input gradients agree in fp64."""
+    import torch
+    from dahitra_b200 import modules as M
+    torch.manual_seed(3)
+    for heads, depth in ((4, 2), (8, 3)):
+        dec = M.PixelDecoder(32, depth, heads, 64, 32).double()
+        for p in dec.parameters():                       # non-trivial LayerNorm affine / biases
+            p.data.add_(0.1 * torch.randn_like(p))
+        x = torch.randn(2, 50, 32, dtype=torch.float64, requires_grad=True)
+        m = torch.randn(2, 4, 32, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(2, 50, 32, dtype=torch.float64)
+        outs = []
+        for fn in (dec, dec.forward_collapsed):
+            for t in list(dec.parameters()) + [x, m]:
+                t.grad = None
+            y = fn(x, m)
+            (y * w).sum().backward()
+            outs.append((y.detach().clone(), [t.grad.clone() for t in list(dec.parameters()) + [x, m]]))
+        assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-11, atol=1e-12)
+        for ga, gb in zip(outs[0][1], outs[1][1]):
+            assert torch.allclose(ga, gb, rtol=1e-9, atol=1e-11), float((ga - gb).abs().max())

@@ -1,4 +1,4 @@
-"""configs[3] smoke: LEVIR-CD training step of the drop-in module (batch 8 per GPU, 256x256, synthetic labels, CE loss, AdamW).
+"""configs[3]: LEVIR-CD training step of the drop-in module (batch 8 per GPU, 256x256, synthetic labels, CE loss, AdamW).
 Training runs on the stock-autograd route (DESIGN.md "Training step"); under torchrun the module is wrapped in
 DistributedDataParallel (NCCL gradient all-reduce, as BASELINE.json's config 4 describes).  After the last step the
 module is switched to eval() and the NATIVE forward is checked against the autograd route on the updated weights.
@@ -20,6 +20,7 @@ class Args:
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--as-written", action="store_true", help="pixel decoders as the reference writes them (q / k / v / out projections) instead of the collapsed algebra")
 ap.add_argument("--graph", action="store_true", help="capture forward + backward + AdamW step in ONE CUDA graph and replay it (1 GPU)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -30,8 +31,9 @@ if world > 1:
     dist.init_process_group("nccl")
 torch.manual_seed(0)
 net = define_G(Args(), gpu_ids=[local]).train()
+net.collapsed_training = not a.as_written
 model = net
-if world > 1:
+if world > 1 and not a.graph:
     # like the reference, the module owns parameters its forward never uses (scale-2 transformer, conv_pred, layer4)
     model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
 opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, capturable=a.graph)           # models/trainer.py:39-40
@@ -43,12 +45,17 @@ losses = []
 w2 = torch.ones(2, device="cuda")
 
 
-graph, static_loss = None, None
+graph, graph_opt, static_loss, flat_grad = None, None, None, None
 
 
 def one_step(sync=True):
     if graph is not None:
+        # graph 1: zero the flat gradient buffer, forward, loss, backward (gradients accumulate in place into views of the flat
+        # buffer); NCCL all-reduce of that ONE buffer; graph 2: the AdamW step
         graph.replay()
+        if world > 1 and sync:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+        graph_opt.replay()
         return static_loss
     opt.zero_grad(set_to_none=True)
     ctx = model.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
@@ -76,24 +83,48 @@ def timed(n, sync=True):
 
 
 for _ in range(3):                               # warm-up (cuDNN autotune, allocator, DDP bucket rebuild)
-    losses.append(one_step().detach())
+    if a.graph:                                  # forward + backward only: the replicas must not step before their gradients are shared
+        F.cross_entropy(model(x1, x2), y, weight=w2, ignore_index=255).backward()
+    else:
+        losses.append(one_step().detach())
 if a.graph:
-    # whole-iteration capture: the ~3000 small launches of the stock-autograd route (the decoders work on (B*N, 32) token
-    # matrices) are replayed from one graph instead of being issued one by one from Python
-    assert world == 1, "--graph is the single-GPU variant"
+    # The ~2500 small launches of the stock-autograd step are replayed from CUDA graphs instead of being issued one by one
+    # from Python (the eager step is bound by that issue rate once the decoders run in the collapsed algebra).  Multi-GPU: no
+    # DDP wrapper — every parameter that receives a gradient gets a view into ONE flat buffer as its .grad, the backward
+    # graph accumulates into it in place, and a single NCCL all-reduce (mean) of the buffer runs between the two graphs.
+    live = [p for p in net.parameters() if p.grad is not None]             # the warm-up steps above marked them
+    flat_grad = torch.zeros(sum(p.numel() for p in live), device="cuda")
+    off = 0
+    for p in live:
+        p.grad = flat_grad[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    for p in net.parameters():
+        if p.grad is None:
+            p.requires_grad_(False)                                         # the 48 tensors the forward never touches
+    opt = torch.optim.AdamW(live, lr=1e-3, weight_decay=0.01, capturable=True)
+
+    def fwd_bwd():
+        flat_grad.zero_()
+        loss = F.cross_entropy(net(x1, x2), y, weight=w2, ignore_index=255)
+        loss.backward()
+        return loss
+
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for _ in range(3):
-            one_step()
+            fwd_bwd()
+            if world > 1:
+                dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+            opt.step()
     torch.cuda.current_stream().wait_stream(side)
-    g_ = torch.cuda.CUDAGraph()
-    opt.zero_grad(set_to_none=True)
+    torch.cuda.synchronize()
+    g_, g2_ = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
     with torch.cuda.graph(g_):
-        static_loss = F.cross_entropy(model(x1, x2), y, weight=w2, ignore_index=255)
-        static_loss.backward()
+        static_loss = fwd_bwd()
+    with torch.cuda.graph(g2_):
         opt.step()
-    graph = g_
+    graph, graph_opt = g_, g2_
 step_ms = timed(a.steps)
 dt = step_ms * a.steps / 1e3
 if world > 1:                                   # replicas must hold identical weights after the all-reduced steps
@@ -112,7 +143,6 @@ else:
 nosync_ms, ar_ms, grad_bytes = None, None, 4 * sum(p.numel() for p in net.parameters() if p.requires_grad)
 if world > 1:
     nosync_ms = timed(max(3, a.steps // 2), sync=False)
-    one_step()                                   # re-synchronise the replicas' gradients / weights path
     flat = torch.zeros(grad_bytes // 4, device="cuda")
     for _ in range(2):
         dist.all_reduce(flat)
@@ -125,7 +155,7 @@ if world > 1:
     torch.cuda.synchronize()
     ar_ms = e0.elapsed_time(e1) / 5
 losses = [float(l) for l in losses]
-no_grad = [n for n, p in net.named_parameters() if p.requires_grad and p.grad is None]
+no_grad = [n for n, p in net.named_parameters() if p.grad is None]
 gnorm = float(torch.sqrt(sum((p.grad.float() ** 2).sum() for p in net.parameters() if p.grad is not None)))
 net.eval()
 with torch.no_grad():
@@ -133,8 +163,9 @@ with torch.no_grad():
 y_auto = net._forward_autograd(x1, x2).detach()
 native_vs_autograd = float((y_native - y_auto).abs().max())
 if rank == 0:
-    print(json.dumps(dict(workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW ({'one CUDA graph per iteration, ' if a.graph else ''}autograd route"
-                                   + (", DDP/NCCL all-reduce)" if world > 1 else ")"),
+    print(json.dumps(dict(decoder="as written" if a.as_written else "collapsed algebra (modules.PixelDecoder.forward_collapsed)",
+                      workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW ({'one CUDA graph per iteration, ' if a.graph else ''}autograd route"
+                                   + ((", one flat NCCL all-reduce of the live gradients)" if a.graph else ", DDP/NCCL all-reduce)") if world > 1 else ")"),
                           steps=a.steps, step_ms=step_ms, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
                           pairs_per_s_per_gpu=a.steps * a.batch / dt,
                           step_ms_without_allreduce=nosync_ms, exposed_allreduce_share=(None if nosync_ms is None else max(0.0, 1 - nosync_ms / step_ms)),
