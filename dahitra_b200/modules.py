@@ -184,6 +184,7 @@ class TokenEncoder(nn.Module):
 class PixelDecoder(nn.Module):
     def __init__(self, dim, depth, heads, dim_head, mlp_dim):
         super().__init__()
+        self.heads = heads
         self.layers = nn.ModuleList([])
         for _ in range(depth):
             self.layers.append(nn.ModuleList([
@@ -223,6 +224,34 @@ class PixelDecoder(nn.Module):
             h = torch.addmm(l1.bias + l1.weight @ norm2.bias, xn2.reshape(B * N, C), (l1.weight * norm2.weight[None, :]).t())
             x = x + torch.addmm(l2.bias, torch.nn.functional.gelu(h), l2.weight.t()).view(B, N, C)
         return x
+
+    def train_tables(self, m):
+        """Per (image, layer) tables of the native training kernels (csrc/train_decoder.cu; layout DH_TRAIN_TAB_FLOATS of
+        include/dahitra_b200.h) from the parameters and the memory tokens m (B, 4, 32), with plain differentiable torch ops on
+        tensors of a few KB: the same folding as ``forward_collapsed`` (k = head * 4 + token; LayerNorm affines folded into
+        A / c0 and W1 / b1).  All layers are built together (the op count does not grow with the depth).  Returns (B, depth, T)."""
+        B, J, C = m.shape
+        L, H = len(self.layers), self.heads
+        st = lambda f: torch.stack([f(attn.fn, ff.fn) for attn, ff in self.layers])          # noqa: E731
+        nw, nb = st(lambda a, f: a.norm.weight), st(lambda a, f: a.norm.bias)               # (L, C)
+        wq, wk, wv = (st(lambda a, f, n=n: getattr(a.fn, n).weight) for n in ("to_q", "to_k", "to_v"))   # (L, H*D, C)
+        wo, bo = st(lambda a, f: a.fn.to_out[0].weight), st(lambda a, f: a.fn.to_out[0].bias)            # (L, C, H*D), (L, C)
+        n2w, n2b = st(lambda a, f: f.norm.weight), st(lambda a, f: f.norm.bias)
+        w1, b1 = st(lambda a, f: f.fn.net[0].weight), st(lambda a, f: f.fn.net[0].bias)
+        w2, b2 = st(lambda a, f: f.fn.net[3].weight), st(lambda a, f: f.fn.net[3].bias)
+        D = wq.shape[1] // H
+        eps, scale = self.layers[0][0].fn.norm.eps, self.layers[0][0].fn.fn.scale
+        mh = torch.nn.functional.layer_norm(m, (C,), None, None, eps)                        # PreNorm2 shares the layer's LayerNorm
+        mn = mh[None] * nw[:, None, None, :] + nb[:, None, None, :]                          # (L, B, 4, C)
+        k = torch.einsum("lbjc,lec->lbje", mn, wk).view(L, B, J, H, D)
+        v = torch.einsum("lbjc,lec->lbje", mn, wv).view(L, B, J, H, D)
+        A = torch.einsum("lhdc,lbjhd->lbchj", wq.view(L, H, D, C), k).reshape(L, B, C, H * J) * scale
+        Bv = torch.einsum("lchd,lbjhd->lbhjc", wo.view(L, C, H, D), v).reshape(L, B, H * J * C)
+        c0 = torch.einsum("lc,lbck->lbk", nb, A)
+        shared = torch.cat([bo, (w1 * n2w[:, None, :]).transpose(1, 2).reshape(L, C * C), b1 + torch.einsum("ljc,lc->lj", w1, n2b),
+                            w2.transpose(1, 2).reshape(L, C * C), b2], dim=1)
+        tab = torch.cat([(nw[:, None, :, None] * A).reshape(L, B, -1), c0, Bv, shared[:, None, :].expand(L, B, -1)], dim=2)
+        return tab.transpose(0, 1).contiguous()
 
 
 def two_layer_head(cin: int, cout: int) -> nn.Sequential:

@@ -22,6 +22,7 @@ from torch.nn import init
 import torch.nn.functional as F
 
 from . import modules as M
+from . import training as T
 from .engine import NativeEngine
 
 __all__ = ["BASE_Transformer_UNet", "define_G", "init_net", "init_weights"]
@@ -92,6 +93,9 @@ class BASE_Transformer_UNet(nn.Module):
         # training route: evaluate the pixel decoders in the collapsed algebra (modules.PixelDecoder.forward_collapsed: the same
         # function, ~16x smaller intermediates); False = the reference's as-written projections
         self.collapsed_training = True
+        # training route: run the pixel decoders (forward AND backward) on the native sm_100a kernels whenever autograd is
+        # recording (dahitra_b200/training.py, csrc/train_decoder.cu); False = stock torch ops as selected above
+        self.native_training = True
         # native engine (lazy: weights are folded / re-laid-out on the first inference call)
         self._engine = NativeEngine()
 
@@ -154,21 +158,35 @@ class BASE_Transformer_UNet(nn.Module):
             a = tk(x).flatten(2).softmax(-1)
             return a @ x.flatten(2).transpose(1, 2)
 
+        native = getattr(self, "native_training", True) and torch.is_grad_enabled()
+        pos = getattr(self, f"pos_embedding_decoder_{k}") if self.with_decoder_pos == 'learned' else None
+
         def decode(x, m):
             b, c, h, w = x.shape
-            if self.with_decoder_pos == 'learned':
-                x = x + getattr(self, f"pos_embedding_decoder_{k}")
+            if pos is not None:
+                x = x + pos
             run = dec.forward_collapsed if getattr(self, "collapsed_training", True) else dec
             return run(x.flatten(2).transpose(1, 2), m).transpose(1, 2).reshape(b, c, h, w)
+
+        def decode_native(x, tab):                           # NCHW is the kernels' channel-planar layout: no transposes
+            if pos is not None:
+                x = x + pos
+            return T.pixel_decoder(x.flatten(2), tab, dec.heads).view(x.shape)
 
         x1, x2 = sq(f1), sq(f2)
         tok = torch.cat([tokens(x1), tokens(x2)], dim=1)
         if self.with_pos:
             tok = tok + getattr(self, f"pos_embedding_{k}")
         t1, t2 = enc(tok).chunk(2, dim=1)
+        conv_decode = getattr(self, f"conv_decode_{k}")
+        if native:
+            # one table build for the level's three decoder calls; both image sets in one launch, the difference call in a second
+            nb = x1.shape[0]
+            tab = dec.train_tables(torch.cat([t1, t2, (t2 - t1).abs()]))
+            x1, x2 = decode_native(torch.cat([x1, x2]), tab[:2 * nb]).chunk(2)
+            return decode_native(conv_decode(torch.cat([x1, x2], dim=1)), tab[2 * nb:])
         x1, x2 = decode(x1, t1), decode(x2, t2)
-        dx = getattr(self, f"conv_decode_{k}")(torch.cat([x1, x2], dim=1))
-        return decode(dx, (t2 - t1).abs())
+        return decode(conv_decode(torch.cat([x1, x2], dim=1)), (t2 - t1).abs())
 
     def _forward_autograd(self, x1, x2):
         a, b = self._trunk_autograd(x1), self._trunk_autograd(x2)   # two passes: BN batch stats per image set

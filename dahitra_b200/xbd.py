@@ -15,6 +15,7 @@ from torch import nn
 import torch.nn.functional as F
 
 from . import modules as M
+from . import training as T
 from .engine import NativeEngine
 from .networks import BASE_Transformer_UNet as _LevirNet
 
@@ -77,6 +78,7 @@ class BASE_Transformer_UNet(_LevirNet):
         self.classifier = nn.Conv2d(32, output_nc, 3, padding=1)
         self.output_nc = output_nc
         self.collapsed_training = True          # training route: pixel decoders in the collapsed algebra (see networks.py)
+        self.native_training = True             # ... on the native kernels whenever autograd is recording (training.py)
         self._engine = NativeEngine()
 
     def pos_shapes(self, H, W):
@@ -108,5 +110,7 @@ class BASE_Transformer_UNet(_LevirNet):
         if self.with_decoder_pos == 'learned' and k == 5:
             dx = dx + self.pos_embedding_decoder_3
         b, c, h, w = dx.shape
+        if getattr(self, "native_training", True) and torch.is_grad_enabled():
+            return T.pixel_decoder(dx.flatten(2), dec.train_tables((t2 - t1).abs()), dec.heads).view(b, c, h, w)
         run = dec.forward_collapsed if getattr(self, "collapsed_training", True) else dec
         return run(dx.flatten(2).transpose(1, 2), (t2 - t1).abs()).transpose(1, 2).reshape(b, c, h, w)

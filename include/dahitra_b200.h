@@ -296,6 +296,24 @@ int dahitra_conv2d_split(const void* in0, const void* in1, int C0, int C1, long 
 int dahitra_classifier(const float* in, int N, int H, int W, int nc, const float* w, const float* bias,
                        float* logits, unsigned char* argmax_u8, void* stream);
 
+/* ---- training step: pixel decoder forward that keeps the layer inputs + its hand-written backward ----------
+ * Replaces, on the training route, the per-pixel arithmetic of reference models/help_funcs.py:66-114,170-186 and the
+ * autograd graph eager PyTorch builds for it (models/trainer.py:247-262).  fp32 FMAs throughout.
+ *   x, out, dout, dx  channel-planar [nimg][32][npix] (the reference's NCHW tensors)
+ *   tables            [nimg][depth][DH_TRAIN_TAB_FLOATS(heads)], per (image, layer), K = 4*heads, k = head*4 + token:
+ *                       A [32][K] | c0 [K] | Bv [K][32] | bo [32] | W1 [32][32] | b1 [32] | W2 [32][32] | b2 [32]
+ *                     (all matrices input-major; built by the host from Wq/Wk/Wv/Wo, the LayerNorm affines, the MLP and the
+ *                     image's 4 memory tokens: dahitra_b200/modules.py PixelDecoder.train_tables)
+ *   xs                [depth][nimg][32][npix]: the input of every layer, written by the forward and read by the backward
+ *   dtables_partial   [nimg][dahitra_pixel_decoder_train_blocks(npix)][depth][DH_TRAIN_TAB_FLOATS]: every CTA WRITES the
+ *                     table gradient of its pixels; the caller sums over the block axis (deterministic) */
+#define DH_TRAIN_TAB_FLOATS(H) (65*4*(H) + 96 + 2048)
+int dahitra_pixel_decoder_train_blocks(int npix);
+int dahitra_pixel_decoder_train_fwd(const float* x, const float* tables, float* xs, float* out, int nimg, int npix,
+                                    int heads, int depth, void* stream);
+int dahitra_pixel_decoder_train_bwd(const float* dout, const float* xs, const float* tables, float* dx,
+                                    float* dtables_partial, int nimg, int npix, int heads, int depth, void* stream);
+
 /* ---- next to the hot path ------------------------------------------------------------ */
 
 /* Device-side confusion matrix: cm[g][p] += #{ i : gt[i] = g < nc, pred[i] = p } — replaces the per-batch

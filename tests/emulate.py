@@ -181,3 +181,28 @@ def forward(P, x1, x2, variant="levir", nc=2):
     C2 = c(O2, "DH_W_CL2", 3, 1, relu=True, up=2)
     wc = P["DH_W_CLS_W"].reshape(3, 3, nc, 32).permute(2, 3, 0, 1)
     return F.conv2d(C2.permute(0, 3, 1, 2), wc, P["DH_W_CLS_B"], 1, 1)
+
+
+def train_decoder_from_tables(x, tables, heads):
+    """The algebra of csrc/train_decoder.cu on its table layout (DH_TRAIN_TAB_FLOATS of include/dahitra_b200.h), with
+    differentiable torch ops: x (B, 32, N) channel-planar, tables (B, depth, T) -> (B, 32, N)."""
+    B, C, N = x.shape
+    K = 4 * heads
+    v = x.transpose(1, 2)                                               # (B, N, 32)
+    for l in range(tables.shape[1]):
+        t = tables[:, l]
+        o = 0
+
+        def take(n, *shape):
+            nonlocal o
+            r = t[:, o:o + n].reshape(B, *shape)
+            o += n
+            return r
+        A, c0, Bv, bo = take(32 * K, 32, K), take(K, 1, K), take(32 * K, K, 32), take(32, 1, 32)
+        W1, b1, W2, b2 = take(1024, 32, 32), take(32, 1, 32), take(1024, 32, 32), take(32, 1, 32)
+        assert o == t.shape[1]
+        d = c0 + ln_hat(v) @ A
+        p = d.view(B, N, heads, 4).softmax(-1).view(B, N, K)
+        v = v + bo + p @ Bv
+        v = v + b2 + gelu(b1 + ln_hat(v) @ W1) @ W2
+    return v.transpose(1, 2)

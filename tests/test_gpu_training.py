@@ -1,0 +1,183 @@
+"""GPU: the native training kernels (csrc/train_decoder.cu behind dahitra_b200/training.py) against fp64 autograd of the same
+function, and the whole training step's gradients against the stock-autograd route (reference
+models/trainer.py:247-262, models/help_funcs.py:66-114,170-186)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import emulate as E
+from dahitra_b200 import modules as M
+from dahitra_b200 import training as T
+from dahitra_b200.networks import define_G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+class Args:
+    net_G = "newUNetTrans"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("heads,depth,B,N", [(4, 4, 3, 256), (4, 1, 2, 1024), (8, 8, 2, 4096), (8, 2, 1, 300), (4, 2, 2, 77)])
+def test_pixel_decoder_train_kernels(heads, depth, B, N):
+    """forward, dL/dx and the gradient of every table entry against fp64 autograd of the same algebra (ragged N included)"""
+    g = torch.Generator().manual_seed(heads * 100 + N)
+    x = torch.randn(B, 32, N, generator=g)
+    tab = torch.randn(B, depth, T.train_tab_floats(heads), generator=g) * 0.15
+    w = torch.randn(B, 32, N, generator=g)
+    xd, td = x.double().requires_grad_(), tab.double().requires_grad_()
+    yd = E.train_decoder_from_tables(xd, td, heads)
+    (yd * w.double()).sum().backward()
+    xg, tg = x.to(DEV).requires_grad_(), tab.to(DEV).requires_grad_()
+    y = T.pixel_decoder(xg, tg, heads)
+    (y * w.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    e = (rel(y, yd), rel(xg.grad, xd.grad), rel(tg.grad, td.grad))
+    print(f"[train decoder] heads {heads} depth {depth} B {B} N {N}: rel err out {e[0]:.2e} dx {e[1]:.2e} dtables {e[2]:.2e}")
+    assert e[0] < 2e-6 and e[1] < 1e-5 and e[2] < 1e-5, e
+    # per-entry check of the table gradient (a wrong row / column order hides in a max-norm)
+    d = (tg.grad.double().cpu() - td.grad).abs()
+    assert bool((d <= 1e-5 * td.grad.abs().max() + 1e-4 * td.grad.abs()).all())
+    # deterministic: a second backward gives the same bits
+    xg2, tg2 = x.to(DEV).requires_grad_(), tab.to(DEV).requires_grad_()
+    (T.pixel_decoder(xg2, tg2, heads) * w.to(DEV)).sum().backward()
+    assert torch.equal(xg2.grad, xg.grad) and torch.equal(tg2.grad, tg.grad)
+
+
+def test_pixel_decoder_module_native_vs_stock():
+    """PixelDecoder parameters + tokens: gradients through train_tables + the native kernels equal the as-written module's"""
+    torch.manual_seed(5)
+    dec = M.PixelDecoder(32, 4, 4, 64, 32).to(DEV)
+    for p in dec.parameters():
+        p.data.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(2, 32, 512, device=DEV)
+    m = torch.randn(2, 4, 32, device=DEV)
+    w = torch.randn(2, 32, 512, device=DEV)
+    res = []
+    for kind in ("fp64", "native", "stock"):
+        d = dec.double() if kind == "fp64" else dec.float()
+        dt = torch.float64 if kind == "fp64" else torch.float32
+        xx, mm = x.to(dt).requires_grad_(), m.to(dt).requires_grad_()
+        for p in d.parameters():
+            p.grad = None
+        if kind == "native":
+            y = T.pixel_decoder(xx, d.train_tables(mm), d.heads)
+        else:
+            y = d(xx.transpose(1, 2), mm).transpose(1, 2)
+        (y * w.to(dt)).sum().backward()
+        res.append([y.detach()] + [t.grad.clone() for t in list(d.parameters()) + [xx, mm]])
+    worst = 0.0
+    for ref, nat, stk in zip(*res):
+        en, es = rel(nat, ref), rel(stk, ref)
+        worst = max(worst, en)
+        assert en <= max(2e-5, 3 * es), (en, es, tuple(ref.shape))
+    print(f"[train decoder] module gradients: worst rel err vs fp64 {worst:.2e}")
+
+
+def _grads(net, x1, x2, y, native):
+    net.native_training = native
+    for p in net.parameters():
+        p.grad = None
+    loss = F.cross_entropy(net(x1, x2), y)
+    loss.backward()
+    return float(loss), {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+
+
+def test_training_step_gradients_native_vs_stock():
+    """One LEVIR training step (train mode: batch-statistics BN): loss and every parameter gradient with the native decoder
+    kernels against the stock-autograd route, both measured against the same network in fp64."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    net = define_G(Args(), gpu_ids=[0]).train()
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    g = torch.Generator(device=DEV).manual_seed(7)
+    x1 = torch.rand(2, 3, 256, 256, device=DEV, generator=g) * 2 - 1
+    x2 = torch.rand(2, 3, 256, 256, device=DEV, generator=g) * 2 - 1
+    y = (torch.rand(2, 256, 256, device=DEV, generator=g) < 0.2).long()
+    ln, gn = _grads(net, x1, x2, y, True)
+    net.load_state_dict(sd0)                                 # BN running stats moved; same starting point for every route
+    ls, gs = _grads(net, x1, x2, y, False)
+    net.load_state_dict(sd0)
+    net.double()
+    l64, g64 = _grads(net, x1.double(), x2.double(), y, False)
+    assert set(gn) == set(gs) == set(g64)
+    assert abs(ln - l64) <= 1e-5 * abs(l64) + 1e-6 and abs(ls - l64) <= 1e-5 * abs(l64) + 1e-6
+    worst_n = worst_s = 0.0
+    errs = sorted(((rel(gn[k], g64[k]), rel(gs[k], g64[k]), k) for k in g64), reverse=True)
+    for en, es, k in errs[:6]:
+        print(f"[train step]   {k}: native {en:.2e} stock {es:.2e}")
+    for en, es, k in errs:
+        worst_n, worst_s = max(worst_n, en), max(worst_s, es)
+        assert en <= max(2e-4, 3 * es), (k, en, es)
+    dec = [(en, es, k) for en, es, k in errs if "transformer_decoder" in k]
+    print(f"[train step] pixel-decoder parameters ({len(dec)}): worst native {dec[0][0]:.2e} ({dec[0][2]}), worst stock {max(e[1] for e in dec):.2e}")
+    print(f"[train step] {len(g64)} gradients: worst rel err vs fp64 native {worst_n:.2e}, stock {worst_s:.2e}; loss {ln:.6f} / {ls:.6f} / {l64:.6f}")
+
+
+def test_training_step_xbd_variant_native_vs_stock():
+    """the xBD variant's training route (one decoder pass per level on conv_decode's output) through the native kernels,
+    anchored on the same network in fp64 like the LEVIR test"""
+    from dahitra_b200 import xbd
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1)
+    net = xbd.BASE_Transformer_UNet(3, 5, with_pos='learned').to(DEV).train()
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    g = torch.Generator(device=DEV).manual_seed(8)
+    x = torch.rand(2, 6, 128, 160, device=DEV, generator=g) * 2 - 1
+    y = torch.randint(0, 5, (2, 128, 160), device=DEV, generator=g)
+    out = {}
+    for kind in ("native", "stock", "fp64"):
+        net.load_state_dict(sd0)
+        net.native_training = kind == "native"
+        if kind == "fp64":
+            net.double()
+        for p in net.parameters():
+            p.grad = None
+        loss = F.cross_entropy(net(x.double() if kind == "fp64" else x), y)
+        loss.backward()
+        out[kind] = (float(loss), {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None})
+    assert abs(out["native"][0] - out["fp64"][0]) <= 1e-5 * abs(out["fp64"][0])
+    assert set(out["native"][1]) == set(out["stock"][1]) == set(out["fp64"][1])
+    errs = sorted(((rel(out["native"][1][k], out["fp64"][1][k]), rel(out["stock"][1][k], out["fp64"][1][k]), k) for k in out["fp64"][1]),
+                  reverse=True)
+    print(f"[train step xBD] {len(errs)} gradients: worst rel err vs fp64 native {errs[0][0]:.2e} ({errs[0][2]}), stock {max(e[1] for e in errs):.2e}")
+    for en, es, k in errs:
+        assert en <= max(2e-4, 3 * es), (k, en, es)
+
+
+def test_training_step_in_cuda_graph_native():
+    """forward + backward with the native kernels is capturable (no allocation-order or synchronisation surprises) and replays
+    to the same gradients"""
+    torch.manual_seed(0)
+    net = define_G(Args(), gpu_ids=[0]).train()
+    g = torch.Generator(device=DEV).manual_seed(9)
+    x1 = torch.rand(2, 3, 256, 256, device=DEV, generator=g) * 2 - 1
+    x2 = torch.rand(2, 3, 256, 256, device=DEV, generator=g) * 2 - 1
+    y = (torch.rand(2, 256, 256, device=DEV, generator=g) < 0.2).long()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            F.cross_entropy(net(x1, x2), y).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    live = [p for p in net.parameters() if p.grad is not None]
+    eager = [p.grad.clone() for p in live]                   # second backward ACCUMULATED: eager = 2 x gradient
+    for p in live:
+        p.grad.zero_()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        F.cross_entropy(net(x1, x2), y).backward()
+    for p in live:
+        p.grad.zero_()
+    gr.replay()
+    gr.replay()
+    torch.cuda.synchronize()
+    for p, e in zip(live, eager):
+        assert rel(p.grad, e) < 1e-3                         # BN running stats do not enter the train-mode forward

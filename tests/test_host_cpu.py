@@ -376,3 +376,36 @@ def test_collapsed_decoder_training_route_equals_as_written():
         assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-11, atol=1e-12)
         for ga, gb in zip(outs[0][1], outs[1][1]):
             assert torch.allclose(ga, gb, rtol=1e-9, atol=1e-11), float((ga - gb).abs().max())
+
+
+def test_train_tables_reproduce_the_decoder():
+    """modules.PixelDecoder.train_tables (host half of the native training decoder) + the kernel's algebra on the table layout
+    (tests/emulate.py) is the same function as the reference's as-written decoder (help_funcs.py:66-114,170-186): outputs and
+    ALL parameter / input gradients agree in fp64."""
+    import torch
+    import emulate as E
+    from dahitra_b200 import modules as M
+    from dahitra_b200.training import train_tab_floats
+    torch.manual_seed(4)
+    for heads, depth in ((4, 2), (8, 3)):
+        dec = M.PixelDecoder(32, depth, heads, 64, 32).double()
+        for p in dec.parameters():
+            p.data.add_(0.1 * torch.randn_like(p))
+        x = torch.randn(2, 50, 32, dtype=torch.float64, requires_grad=True)
+        m = torch.randn(2, 4, 32, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(2, 50, 32, dtype=torch.float64)
+        outs = []
+        for native in (False, True):
+            for t in list(dec.parameters()) + [x, m]:
+                t.grad = None
+            if native:
+                tab = dec.train_tables(m)
+                assert tab.shape == (2, depth, train_tab_floats(heads))
+                y = E.train_decoder_from_tables(x.transpose(1, 2), tab, heads).transpose(1, 2)
+            else:
+                y = dec(x, m)
+            (y * w).sum().backward()
+            outs.append((y.detach().clone(), [t.grad.clone() for t in list(dec.parameters()) + [x, m]]))
+        assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-11, atol=1e-12)
+        for ga, gb in zip(outs[0][1], outs[1][1]):
+            assert torch.allclose(ga, gb, rtol=1e-9, atol=1e-11), float((ga - gb).abs().max())

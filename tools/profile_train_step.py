@@ -1,4 +1,4 @@
-"""Where the stock-autograd training step (config 4, batch 8, one GPU) spends its device time: torch.profiler, top kernels.
+"""Where the training step (native pixel decoders unless --stock) (config 4, batch 8, one GPU) spends its device time: torch.profiler, top kernels.
    python tools/profile_train_step.py > profiles/r02_train_step_profile.txt"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,6 +14,7 @@ class Args:
 
 torch.manual_seed(0)
 net = define_G(Args(), gpu_ids=[0]).train()
+net.native_training = "--stock" not in sys.argv
 opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=0.01)
 g = torch.Generator(device="cuda").manual_seed(100)
 x1 = torch.rand(8, 3, 256, 256, device="cuda", generator=g) * 2 - 1

@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--as-written", action="store_true", help="pixel decoders as the reference writes them (q / k / v / out projections) instead of the collapsed algebra")
+ap.add_argument("--stock", action="store_true", help="pixel decoders on stock torch ops instead of the native training kernels (csrc/train_decoder.cu)")
 ap.add_argument("--graph", action="store_true", help="capture forward + backward + AdamW step in ONE CUDA graph and replay it (1 GPU)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -32,6 +33,7 @@ if world > 1:
 torch.manual_seed(0)
 net = define_G(Args(), gpu_ids=[local]).train()
 net.collapsed_training = not a.as_written
+net.native_training = not (a.stock or a.as_written)
 model = net
 if world > 1 and not a.graph:
     # like the reference, the module owns parameters its forward never uses (scale-2 transformer, conv_pred, layer4)
@@ -73,7 +75,7 @@ def timed(n, sync=True):
     torch.cuda.synchronize()
     e0.record()
     for _ in range(n):
-        losses.append(one_step(sync).detach())
+        losses.append(one_step(sync).detach().clone())
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / n], device="cuda")
@@ -163,7 +165,8 @@ with torch.no_grad():
 y_auto = net._forward_autograd(x1, x2).detach()
 native_vs_autograd = float((y_native - y_auto).abs().max())
 if rank == 0:
-    print(json.dumps(dict(decoder="as written" if a.as_written else "collapsed algebra (modules.PixelDecoder.forward_collapsed)",
+    print(json.dumps(dict(decoder="as written (stock ops)" if a.as_written else "collapsed algebra, stock ops (modules.PixelDecoder.forward_collapsed)" if a.stock
+                          else "native sm_100a forward + backward kernels (csrc/train_decoder.cu)",
                       workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW ({'one CUDA graph per iteration, ' if a.graph else ''}autograd route"
                                    + ((", one flat NCCL all-reduce of the live gradients)" if a.graph else ", DDP/NCCL all-reduce)") if world > 1 else ")"),
                           steps=a.steps, step_ms=step_ms, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
