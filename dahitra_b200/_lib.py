@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdahitra_b200.so")
-SOURCES = ["conv_ffma.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "split.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "classifier.cu", "train_decoder.cu", "prepare.cu", "aux.cu", "forward.cu"]
+SOURCES = ["conv_ffma.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "split.cu", "tokens.cu", "decoder.cu", "decoder_tc.cu", "stem_tc.cu", "classifier.cu", "train_decoder.cu", "train_tokens.cu", "prepare.cu", "aux.cu", "forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -98,8 +98,11 @@ SIGNATURES = {
     "dahitra_split_unpack": (_I, [_P, _LL, _P, _P]),
     "dahitra_maxpool3x3s2_split": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "dahitra_pixel_decoder_train_blocks": (_I, [_I]),
-    "dahitra_pixel_decoder_train_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "dahitra_pixel_decoder_train_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "dahitra_pixel_decoder_train_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "dahitra_pixel_decoder_train_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "dahitra_tokenizer_train_chunks": (_I, [_I]),
+    "dahitra_tokenizer_train_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "dahitra_tokenizer_train_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "dahitra_conv2d_split": (_I, [_P, _P, _I, _I, _LL, _LL, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _P]),
 }
 

@@ -30,7 +30,7 @@ struct Bump {
   }
 };
 
-bool make_plan(Plan& p, int variant, int B, int H, int W, int nc) {
+bool make_plan(Plan& p, int variant, int B, int H, int W, int nc, int flags) {
   if (B < 1 || H < 32 || W < 32 || (H % 32) || (W % 32) || nc < 1 || nc > 8) return false;
   if (variant != DH_VARIANT_LEVIR && variant != DH_VARIANT_XBD) return false;
   p.B = B; p.H = H; p.W = W; p.nc = nc; p.variant = variant;
@@ -59,10 +59,18 @@ bool make_plan(Plan& p, int variant, int B, int H, int W, int nc) {
     L.tab = b.take((size_t)3 * B * L.depth * (DH_TAB_FLOATS(L.heads) > DH_TABTC_FLOATS ? DH_TAB_FLOATS(L.heads) : DH_TABTC_FLOATS));
   }
   p.c4 = b.take((size_t)B * s4 * 32);
-  p.c3 = b.take((size_t)B * s2 * 32);
-  p.y20 = b.take((size_t)B * s2 * 128);
-  p.o2 = b.take((size_t)B * s2 * 32);
-  p.c2 = b.take((size_t)B * H * W * 32);
+  // The head's tensors reuse trunk buffers that are dead by then (every launch that reads them has been joined into the main
+  // stream before the head starts; a programmatic dependent launch only overlaps a kernel with its direct predecessor):
+  //   C3  (conv_layer3 out)      <- T8a | T8b          Y20 (conv_layer2_0.0 out) <- P2 | T4a | T4b | F4
+  //   O2  (conv_layer2_0.3 out)  <- T8c | F8           C2  (conv_layer2 out)     <- F2 (last read by conv_layer2_0.0)
+  // 13 -> 8 units of B * (H/2) * (W/2) * 64 floats: 3.5 -> 2.1 GB at 64 LEVIR pairs.  DH_FLAG_EARLY_HEAD issues conv_layer2_0.0
+  // right after the stem, so Y20 keeps its own buffer under that flag.
+  const size_t n_c3 = (size_t)B * s2 * 32, n_y20 = (size_t)B * s2 * 128, n_c2 = (size_t)B * H * W * 32;
+  const bool early_head = (flags & DH_FLAG_EARLY_HEAD) != 0;
+  p.c3 = (p.t8c - p.t8a >= n_c3) ? p.t8a : b.take(n_c3);
+  p.o2 = (p.p8 - p.t8c >= n_c3) ? p.t8c : b.take(n_c3);
+  p.y20 = (!early_head && p.t8a - p.p2 >= n_y20) ? p.p2 : b.take(n_y20);
+  p.c2 = (p.p2 - p.f2 >= n_c2) ? p.f2 : b.take(n_c2);
   p.total_floats = b.off;
   return true;
 }
@@ -132,9 +140,8 @@ extern "C" const char* dahitra_weight_slot_name(int slot) {
 }
 
 extern "C" size_t dahitra_workspace_bytes(int variant, int B, int H, int W, int output_nc, int flags) {
-  (void)flags;
   Plan p;
-  if (!make_plan(p, variant, B, H, W, output_nc)) return 0;
+  if (!make_plan(p, variant, B, H, W, output_nc, flags)) return 0;
   return p.total_floats * sizeof(float);
 }
 
@@ -502,7 +509,7 @@ extern "C" int dahitra_forward(const void* const* weights, int n_weights, const 
   DH_REQUIRE(n_weights == DH_W_COUNT, DH_E_WEIGHTS);
   Plan p;
   DH_REQUIRE(variant == DH_VARIANT_LEVIR || variant == DH_VARIANT_XBD, DH_E_VARIANT);
-  DH_REQUIRE(make_plan(p, variant, B, H, W, output_nc), DH_E_SHAPE);
+  DH_REQUIRE(make_plan(p, variant, B, H, W, output_nc, flags), DH_E_SHAPE);
   DH_REQUIRE(workspace_bytes >= p.total_floats * sizeof(float), DH_E_WORKSPACE);
   DH_REQUIRE(dh_aligned16(workspace), DH_E_ALIGN);
   for (int i = 0; i < DH_W_COUNT; ++i) {

@@ -59,25 +59,25 @@ __device__ __forceinline__ void matvec(const float* __restrict__ in_col, const f
 }
 
 // out[j][tid] = sum_c W[j][c] * in[c]       (rows of the same input-major matrix dotted with a register vector: the transposed
-// product of the backward pass; four rows at a time for independent FMA chains)
+// product of the backward pass; eight rows at a time for independent FMA chains)
 template <int CIN, int JOUT>
 __device__ __forceinline__ void matvec_t(const float (&in)[CIN], const float* __restrict__ W, float* __restrict__ out_col) {
 #pragma unroll 1
-  for (int j = 0; j < JOUT; j += 4) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const float4* r0 = reinterpret_cast<const float4*>(W + (j + 0) * CIN);
-    const float4* r1 = reinterpret_cast<const float4*>(W + (j + 1) * CIN);
-    const float4* r2 = reinterpret_cast<const float4*>(W + (j + 2) * CIN);
-    const float4* r3 = reinterpret_cast<const float4*>(W + (j + 3) * CIN);
+  for (int j = 0; j < JOUT; j += 8) {
+    float a[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = 0.f;
 #pragma unroll
     for (int q = 0; q < CIN / 4; ++q) {
-      const float4 w0 = r0[q], w1 = r1[q], w2 = r2[q], w3 = r3[q];
-      a0 = fmaf(w0.x, in[4 * q], a0); a0 = fmaf(w0.y, in[4 * q + 1], a0); a0 = fmaf(w0.z, in[4 * q + 2], a0); a0 = fmaf(w0.w, in[4 * q + 3], a0);
-      a1 = fmaf(w1.x, in[4 * q], a1); a1 = fmaf(w1.y, in[4 * q + 1], a1); a1 = fmaf(w1.z, in[4 * q + 2], a1); a1 = fmaf(w1.w, in[4 * q + 3], a1);
-      a2 = fmaf(w2.x, in[4 * q], a2); a2 = fmaf(w2.y, in[4 * q + 1], a2); a2 = fmaf(w2.z, in[4 * q + 2], a2); a2 = fmaf(w2.w, in[4 * q + 3], a2);
-      a3 = fmaf(w3.x, in[4 * q], a3); a3 = fmaf(w3.y, in[4 * q + 1], a3); a3 = fmaf(w3.z, in[4 * q + 2], a3); a3 = fmaf(w3.w, in[4 * q + 3], a3);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float4 w = reinterpret_cast<const float4*>(W + (j + r) * CIN)[q];
+        a[r] = fmaf(w.x, in[4 * q], a[r]); a[r] = fmaf(w.y, in[4 * q + 1], a[r]);
+        a[r] = fmaf(w.z, in[4 * q + 2], a[r]); a[r] = fmaf(w.w, in[4 * q + 3], a[r]);
+      }
     }
-    out_col[(j + 0) * PITCH] = a0; out_col[(j + 1) * PITCH] = a1; out_col[(j + 2) * PITCH] = a2; out_col[(j + 3) * PITCH] = a3;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) out_col[(j + r) * PITCH] = a[r];
   }
 }
 
@@ -127,12 +127,42 @@ __device__ __forceinline__ void softmax4(float (&d)[K]) {
   }
 }
 
+// one pixel's 32 channels from / to a [B][32][N] (planar, PM = false) or [B][N][32] (pixel-major = channels_last, PM = true) tensor
+template <bool PM>
+__device__ __forceinline__ void load_pixel(const float* __restrict__ t, int b, int n, int N, bool live, float (&v)[32]) {
+  if (PM) {
+    const float4* p = reinterpret_cast<const float4*>(t + ((size_t)b * N + n) * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 w = live ? __ldg(p + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+    }
+  } else {
+    const float* p = t + (size_t)b * 32 * N + n;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = live ? p[(size_t)c * N] : 0.f;
+  }
+}
+template <bool PM>
+__device__ __forceinline__ void store_pixel(float* __restrict__ t, int b, int n, int N, bool live, const float (&v)[32]) {
+  if (!live) return;
+  if (PM) {
+    float4* p = reinterpret_cast<float4*>(t + ((size_t)b * N + n) * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) p[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  } else {
+    float* p = t + (size_t)b * 32 * N + n;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) p[(size_t)c * N] = v[c];
+  }
+}
+
 __device__ __forceinline__ void load_table(const float* __restrict__ g, float* __restrict__ s, int T) {
   for (int i = threadIdx.x * 4; i < T; i += PT * 4) *reinterpret_cast<float4*>(s + i) = __ldg(reinterpret_cast<const float4*>(g + i));
 }
 
 // ------------------------------------------------------------------------------------------------ forward (training)
-template <int K>
+template <int K, bool PM>
 __global__ void __launch_bounds__(PT) decoder_train_fwd_kernel(const float* __restrict__ x, const float* __restrict__ table,
                                                                float* __restrict__ xs, float* __restrict__ out, int B, int N, int L) {
   constexpr TabOff O = tab_off(K);
@@ -142,18 +172,12 @@ __global__ void __launch_bounds__(PT) decoder_train_fwd_kernel(const float* __re
   float* bufB = bufA + 32 * PITCH;         // [32][PITCH]
   const int b = blockIdx.y, tid = threadIdx.x, n = blockIdx.x * PT + tid;
   const bool live = n < N;
-  const size_t img = (size_t)b * 32 * N;
   float v[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) v[c] = live ? x[img + (size_t)c * N + n] : 0.f;
+  load_pixel<PM>(x, b, n, N, live, v);
   for (int l = 0; l < L; ++l) {
     __syncthreads();                                                   // the previous layer is done with the table
     load_table(table + ((size_t)b * L + l) * O.T, tab, O.T);
-    if (live) {
-      float* xl = xs + ((size_t)l * B + b) * 32 * N;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) xl[(size_t)c * N + n] = v[c];
-    }
+    store_pixel<false>(xs + (size_t)l * B * 32 * N, b, n, N, live, v);  // layer inputs are kept planar (coalesced both ways)
     {
       float xn[32];
       layer_norm32(v, xn);
@@ -189,10 +213,7 @@ __global__ void __launch_bounds__(PT) decoder_train_fwd_kernel(const float* __re
     for (int c = 0; c < 32; ++c) v[c] += tab[O.b2 + c];
     matvec<32, 32>(bufB + tid, tab + O.W2, v);                         // z = y + b2 + gelu(h) W2
   }
-  if (live) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) out[img + (size_t)c * N + n] = v[c];
-  }
+  store_pixel<PM>(out, b, n, N, live, v);
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -225,47 +246,44 @@ __device__ __forceinline__ void wgrad(const float* __restrict__ a, const float* 
   }
 }
 
-template <int K>
-__global__ void __launch_bounds__(PT) decoder_train_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ xs,
-                                                               const float* __restrict__ table, float* __restrict__ dx,
-                                                               float* __restrict__ dtab, int B, int N, int L) {
+template <int K, bool PM>
+__global__ void __launch_bounds__(PT, 2) decoder_train_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ xs,
+                                                                  const float* __restrict__ table, float* __restrict__ dx,
+                                                                  float* __restrict__ dtab, int B, int N, int L) {
   constexpr TabOff O = tab_off(K);
   extern __shared__ __align__(16) float smem[];
+  // five staged vectors (so that two CTAs fit one SM); xn is recomputed from the layer input where it is needed a second time
   float* tab = smem;
-  float* s_xn = smem + O.T;                // [32][PITCH]
-  float* s_p = s_xn + 32 * PITCH;          // [K][PITCH]
-  float* s_yn = s_p + K * PITCH;           // [32][PITCH]   later: dxn
-  float* s_g = s_yn + 32 * PITCH;          // [32][PITCH]   gelu(h); later dyn, dy
+  float* s_p = smem + O.T;                 // [K][PITCH]    softmax probabilities
+  float* s_yn = s_p + K * PITCH;           // [32][PITCH]   xn (forward), yn, later xn again (for dA)
+  float* s_g = s_yn + 32 * PITCH;          // [32][PITCH]   gelu(h); later dg, dyn, dy, dxn
   float* s_gp = s_g + 32 * PITCH;          // [32][PITCH]   gelu'(h); later dh (in place)
   float* s_dz = s_gp + 32 * PITCH;         // [32][PITCH]   dz; later dp, dd (first K rows)
   const int b = blockIdx.y, tid = threadIdx.x, n = blockIdx.x * PT + tid;
   const bool live = n < N;
-  const size_t img = (size_t)b * 32 * N;
   float dz[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) dz[c] = live ? dout[img + (size_t)c * N + n] : 0.f;
+  load_pixel<PM>(dout, b, n, N, live, dz);
   for (int l = L - 1; l >= 0; --l) {
     __syncthreads();                                                   // the previous layer's last wgrad / table reads are done
     load_table(table + ((size_t)b * L + l) * O.T, tab, O.T);
     float* gt = dtab + (((size_t)b * gridDim.x + blockIdx.x) * L + l) * O.T;     // this CTA's partial of the layer's table gradient
+    const float* xl = xs + (size_t)l * B * 32 * N;
     float rstd1, rstd2;
-    // ---- recompute the layer's forward; keep xn, p, yn, gelu(h), gelu'(h) in shared memory
+    // ---- recompute the layer's forward; keep p, yn, gelu(h), gelu'(h) in shared memory
     {
       float v[32];
-      const float* xl = xs + ((size_t)l * B + b) * 32 * N;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] = live ? xl[(size_t)c * N + n] : 0.f;
+      load_pixel<false>(xl, b, n, N, live, v);
       {
         float xn[32];
         rstd1 = layer_norm32(v, xn);
-        store_col(s_xn + tid, xn);
+        store_col(s_yn + tid, xn);
       }
       __syncthreads();                                                 // table loaded
       {
         float d[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) d[k] = tab[O.c0 + k];
-        matvec<32, K>(s_xn + tid, tab + O.A, d);
+        matvec<32, K>(s_yn + tid, tab + O.A, d);
         softmax4<K>(d);
         store_col(s_p + tid, d);
       }
@@ -291,13 +309,13 @@ __global__ void __launch_bounds__(PT) decoder_train_bwd_kernel(const float* __re
     }
     // ---- z = y + b2 + g W2 :  dW2[j][c] = sum g[j] dz[c], db2 = sum dz, dg = W2 dz
     store_col(s_dz + tid, dz);
-    __syncthreads();
+    __syncthreads();                                                   // (1)
     wgrad<32, 32>(s_g, s_dz, gt + O.W2, gt + O.b2);
-    __syncthreads();                                                   // s_g is overwritten below
+    __syncthreads();                                                   // (2) s_g is overwritten below
     matvec_t<32, 32>(dz, tab + O.W2, s_g + tid);                       // dg -> s_g (own column)
 #pragma unroll
     for (int j = 0; j < 32; ++j) s_gp[j * PITCH + tid] *= s_g[j * PITCH + tid];      // dh = dg * gelu'(h), in place
-    __syncthreads();
+    __syncthreads();                                                   // (3)
     // ---- h = b1 + yn W1 :  dW1[c][j] = sum yn[c] dh[j], db1 = sum dh, dyn = W1 dh
     wgrad<32, 32>(s_yn, s_gp, gt + O.W1, gt + O.b1);
     {
@@ -314,10 +332,16 @@ __global__ void __launch_bounds__(PT) decoder_train_bwd_kernel(const float* __re
       for (int c = 0; c < 32; ++c) dz[c] += t[c];                      // dy = dz (residual) + LayerNorm backward
     }
     store_col(s_g + tid, dz);                                          // dy staged
-    __syncthreads();                                                   // also: the wgrad above has finished reading s_yn / s_gp
+    __syncthreads();                                                   // (4) also: the wgrad above has finished reading s_yn / s_gp
     // ---- y = x + bo + p Bv :  dBv[k][c] = sum p[k] dy[c], dbo = sum dy, dp = Bv dy
     wgrad<K, 32>(s_p, s_g, gt + O.Bv, gt + O.bo);
-    matvec_t<32, K>(dz, tab + O.Bv, s_dz + tid);                       // dp -> s_dz (own column; last read before this layer's 2nd barrier)
+    matvec_t<32, K>(dz, tab + O.Bv, s_dz + tid);                       // dp -> s_dz (own column; last read before barrier (2))
+    {
+      float v[32], xn[32];                                             // xn again (s_yn is free since barrier (4))
+      load_pixel<false>(xl, b, n, N, live, v);
+      layer_norm32(v, xn);
+      store_col(s_yn + tid, xn);
+    }
     {
       float p[K], dp[K];
       load_col(s_p + tid, p);
@@ -329,43 +353,40 @@ __global__ void __launch_bounds__(PT) decoder_train_bwd_kernel(const float* __re
         for (int j = 0; j < 4; ++j) dp[4 * h + j] = p[4 * h + j] * (dp[4 * h + j] - dot);
       }
       store_col(s_dz + tid, dp);                                       // dd staged
-      __syncthreads();
+      __syncthreads();                                                 // (5) also: the Bv wgrad has finished reading s_g
       // ---- d = c0 + xn A :  dA[c][k] = sum xn[c] dd[k], dc0 = sum dd, dxn = A dd
-      wgrad<32, K>(s_xn, s_dz, gt + O.A, gt + O.c0);
-      matvec_t<K, 32>(dp, tab + O.A, s_yn + tid);                      // dxn -> s_yn (own column; not read by this wgrad)
+      wgrad<32, K>(s_yn, s_dz, gt + O.A, gt + O.c0);
+      matvec_t<K, 32>(dp, tab + O.A, s_g + tid);                       // dxn -> s_g (own column; not read by this wgrad)
     }
     {
       float dxn[32], xn[32], t[32];
-      load_col(s_yn + tid, dxn);
-      load_col(s_xn + tid, xn);
+      load_col(s_g + tid, dxn);
+      load_col(s_yn + tid, xn);
       layer_norm32_bwd(dxn, xn, rstd1, t);
 #pragma unroll
       for (int c = 0; c < 32; ++c) dz[c] += t[c];                      // dx = dy (residual) + LayerNorm backward
     }
   }
-  if (live) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) dx[img + (size_t)c * N + n] = dz[c];
-  }
+  store_pixel<PM>(dx, b, n, N, live, dz);
 }
 
-template <int K>
+template <int K, bool PM>
 int launch_fwd(const float* x, const float* table, float* xs, float* out, int B, int N, int L, cudaStream_t s) {
   constexpr TabOff O = tab_off(K);
   const size_t smem = (size_t)(O.T + 2 * 32 * PITCH) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(decoder_train_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(decoder_train_fwd_kernel<K, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  decoder_train_fwd_kernel<K><<<dim3(dh_cdiv(N, PT), B), PT, smem, s>>>(x, table, xs, out, B, N, L);
+  decoder_train_fwd_kernel<K, PM><<<dim3(dh_cdiv(N, PT), B), PT, smem, s>>>(x, table, xs, out, B, N, L);
   DH_CHECK_LAUNCH();
   return 0;
 }
-template <int K>
+template <int K, bool PM>
 int launch_bwd(const float* dout, const float* xs, const float* table, float* dx, float* dtab, int B, int N, int L, cudaStream_t s) {
   constexpr TabOff O = tab_off(K);
-  const size_t smem = (size_t)(O.T + (5 * 32 + K) * PITCH) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(decoder_train_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)(O.T + (4 * 32 + K) * PITCH) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(decoder_train_bwd_kernel<K, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  decoder_train_bwd_kernel<K><<<dim3(dh_cdiv(N, PT), B), PT, smem, s>>>(dout, xs, table, dx, dtab, B, N, L);
+  decoder_train_bwd_kernel<K, PM><<<dim3(dh_cdiv(N, PT), B), PT, smem, s>>>(dout, xs, table, dx, dtab, B, N, L);
   DH_CHECK_LAUNCH();
   return 0;
 }
@@ -375,22 +396,28 @@ int launch_bwd(const float* dout, const float* xs, const float* table, float* dx
 extern "C" int dahitra_pixel_decoder_train_blocks(int npix) { return npix > 0 ? dh_cdiv(npix, PT) : 0; }
 
 extern "C" int dahitra_pixel_decoder_train_fwd(const float* x, const float* tables, float* xs, float* out, int nimg, int npix,
-                                               int heads, int depth, void* stream) {
+                                               int heads, int depth, int pixel_major, void* stream) {
   DH_REQUIRE(x && tables && xs && out, DH_E_NULL);
   DH_REQUIRE(nimg > 0 && npix > 0 && depth > 0 && nimg <= 65535, DH_E_SHAPE);
   DH_REQUIRE(heads == 4 || heads == 8, DH_E_SHAPE);
-  DH_REQUIRE(dh_aligned16(tables), DH_E_ALIGN);
+  DH_REQUIRE(dh_aligned16(tables) && (!pixel_major || (dh_aligned16(x) && dh_aligned16(out))), DH_E_ALIGN);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return heads == 4 ? launch_fwd<16>(x, tables, xs, out, nimg, npix, depth, s) : launch_fwd<32>(x, tables, xs, out, nimg, npix, depth, s);
+  if (pixel_major)
+    return heads == 4 ? launch_fwd<16, true>(x, tables, xs, out, nimg, npix, depth, s) : launch_fwd<32, true>(x, tables, xs, out, nimg, npix, depth, s);
+  return heads == 4 ? launch_fwd<16, false>(x, tables, xs, out, nimg, npix, depth, s) : launch_fwd<32, false>(x, tables, xs, out, nimg, npix, depth, s);
 }
 
 extern "C" int dahitra_pixel_decoder_train_bwd(const float* dout, const float* xs, const float* tables, float* dx,
-                                               float* dtables_partial, int nimg, int npix, int heads, int depth, void* stream) {
+                                               float* dtables_partial, int nimg, int npix, int heads, int depth, int pixel_major,
+                                               void* stream) {
   DH_REQUIRE(dout && xs && tables && dx && dtables_partial, DH_E_NULL);
   DH_REQUIRE(nimg > 0 && npix > 0 && depth > 0 && nimg <= 65535, DH_E_SHAPE);
   DH_REQUIRE(heads == 4 || heads == 8, DH_E_SHAPE);
-  DH_REQUIRE(dh_aligned16(tables), DH_E_ALIGN);
+  DH_REQUIRE(dh_aligned16(tables) && (!pixel_major || (dh_aligned16(dout) && dh_aligned16(dx))), DH_E_ALIGN);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return heads == 4 ? launch_bwd<16>(dout, xs, tables, dx, dtables_partial, nimg, npix, depth, s)
-                    : launch_bwd<32>(dout, xs, tables, dx, dtables_partial, nimg, npix, depth, s);
+  if (pixel_major)
+    return heads == 4 ? launch_bwd<16, true>(dout, xs, tables, dx, dtables_partial, nimg, npix, depth, s)
+                      : launch_bwd<32, true>(dout, xs, tables, dx, dtables_partial, nimg, npix, depth, s);
+  return heads == 4 ? launch_bwd<16, false>(dout, xs, tables, dx, dtables_partial, nimg, npix, depth, s)
+                    : launch_bwd<32, false>(dout, xs, tables, dx, dtables_partial, nimg, npix, depth, s);
 }

@@ -456,12 +456,12 @@ class NativeEngine:
         # one workspace per stream: two forwards issued on different streams must not share scratch memory.  A workspace
         # first needed while a graph is being captured is allocated from that graph's pool and is never handed to eager
         # launches (key "capture"); entries are only freed by release_workspaces().
-        key = (str(device), "capture" if capturing else stream.cuda_stream, variant, B, H, W, nc)
+        nbytes = lib.dahitra_workspace_bytes(variant, B, H, W, nc, self.flags)      # depends on the flags (buffer reuse plan)
+        if nbytes == 0:
+            raise RuntimeError(f"dahitra_b200: unsupported shape B={B} H={H} W={W} (H, W must be multiples of 32)")
+        key = (str(device), "capture" if capturing else stream.cuda_stream, variant, B, H, W, nc, nbytes)
         ws = self._ws.get(key)
         if ws is None:
-            nbytes = lib.dahitra_workspace_bytes(variant, B, H, W, nc, self.flags)
-            if nbytes == 0:
-                raise RuntimeError(f"dahitra_b200: unsupported shape B={B} H={H} W={W} (H, W must be multiples of 32)")
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._ws[key] = ws
         return ws

@@ -96,6 +96,10 @@ class BASE_Transformer_UNet(nn.Module):
         # training route: run the pixel decoders (forward AND backward) on the native sm_100a kernels whenever autograd is
         # recording (dahitra_b200/training.py, csrc/train_decoder.cu); False = stock torch ops as selected above
         self.native_training = True
+        # training route: activations and 4-D parameters in torch.channels_last memory format (cuDNN's native layout on this GPU:
+        # no NCHW <-> NHWC transposes around every convolution; the native decoder kernels read it pixel-major).  Shapes, values
+        # and state_dict keys are unchanged — only strides
+        self.channels_last_training = True
         # native engine (lazy: weights are folded / re-laid-out on the first inference call)
         self._engine = NativeEngine()
 
@@ -168,27 +172,46 @@ class BASE_Transformer_UNet(nn.Module):
             run = dec.forward_collapsed if getattr(self, "collapsed_training", True) else dec
             return run(x.flatten(2).transpose(1, 2), m).transpose(1, 2).reshape(b, c, h, w)
 
-        def decode_native(x, tab):                           # NCHW is the kernels' channel-planar layout: no transposes
+        def decode_native(x, tab):                           # NCHW / channels_last are the kernels' two layouts: no transposes
             if pos is not None:
                 x = x + pos
-            return T.pixel_decoder(x.flatten(2), tab, dec.heads).view(x.shape)
+            return T.pixel_decoder(x, tab, dec.heads)
 
+        conv_decode = getattr(self, f"conv_decode_{k}")
+        if native:
+            # both image sets as one batch (the squeeze has no BatchNorm): tokenizer, ONE table build for the level's three
+            # decoder calls, one decoder launch for x1 | x2 and one for the difference features
+            nb = f1.shape[0]
+            x12 = sq(torch.cat([f1, f2]))
+            t12 = T.semantic_tokens(x12, tk.weight)
+            tok = torch.cat([t12[:nb], t12[nb:]], dim=1)
+            if self.with_pos:
+                tok = tok + getattr(self, f"pos_embedding_{k}")
+            t1, t2 = enc(tok).chunk(2, dim=1)
+            tab = dec.train_tables(torch.cat([t1, t2, (t2 - t1).abs()]))
+            y12 = decode_native(x12, tab[:2 * nb])
+            return decode_native(conv_decode(torch.cat([y12[:nb], y12[nb:]], dim=1)), tab[2 * nb:])
         x1, x2 = sq(f1), sq(f2)
         tok = torch.cat([tokens(x1), tokens(x2)], dim=1)
         if self.with_pos:
             tok = tok + getattr(self, f"pos_embedding_{k}")
         t1, t2 = enc(tok).chunk(2, dim=1)
-        conv_decode = getattr(self, f"conv_decode_{k}")
-        if native:
-            # one table build for the level's three decoder calls; both image sets in one launch, the difference call in a second
-            nb = x1.shape[0]
-            tab = dec.train_tables(torch.cat([t1, t2, (t2 - t1).abs()]))
-            x1, x2 = decode_native(torch.cat([x1, x2]), tab[:2 * nb]).chunk(2)
-            return decode_native(conv_decode(torch.cat([x1, x2], dim=1)), tab[2 * nb:])
         x1, x2 = decode(x1, t1), decode(x2, t2)
         return decode(conv_decode(torch.cat([x1, x2], dim=1)), (t2 - t1).abs())
 
+    def _channels_last(self, *xs):
+        if not getattr(self, "channels_last_training", True):
+            return xs
+        if not self.resnet.conv1.weight.is_contiguous(memory_format=torch.channels_last):
+            for p in self.parameters():
+                if p.dim() == 4:
+                    p.data = p.data.contiguous(memory_format=torch.channels_last)
+                    if p.grad is not None:
+                        p.grad.data = p.grad.data.contiguous(memory_format=torch.channels_last)
+        return tuple(x.contiguous(memory_format=torch.channels_last) for x in xs)
+
     def _forward_autograd(self, x1, x2):
+        x1, x2 = self._channels_last(x1, x2)
         a, b = self._trunk_autograd(x1), self._trunk_autograd(x2)   # two passes: BN batch stats per image set
         up = self.upsamplex2
         o5 = up(self._level_autograd(a[3], b[3], 5))

@@ -79,6 +79,7 @@ class BASE_Transformer_UNet(_LevirNet):
         self.output_nc = output_nc
         self.collapsed_training = True          # training route: pixel decoders in the collapsed algebra (see networks.py)
         self.native_training = True             # ... on the native kernels whenever autograd is recording (training.py)
+        self.channels_last_training = True      # ... with activations / 4-D parameters in torch.channels_last (see networks.py)
         self._engine = NativeEngine()
 
     def pos_shapes(self, H, W):
@@ -101,8 +102,16 @@ class BASE_Transformer_UNet(_LevirNet):
         def tokens(x):
             return tk(x).flatten(2).softmax(-1) @ x.flatten(2).transpose(1, 2)
 
-        x1, x2 = sq(f1), sq(f2)
-        tok = torch.cat([tokens(x1), tokens(x2)], dim=1)
+        native = getattr(self, "native_training", True) and torch.is_grad_enabled()
+        if native:
+            nb = f1.shape[0]
+            x12 = sq(torch.cat([f1, f2]))
+            t12 = T.semantic_tokens(x12, tk.weight)
+            x1, x2 = x12[:nb], x12[nb:]
+            tok = torch.cat([t12[:nb], t12[nb:]], dim=1)
+        else:
+            x1, x2 = sq(f1), sq(f2)
+            tok = torch.cat([tokens(x1), tokens(x2)], dim=1)
         if self.with_pos and k == 5:
             tok = tok + self.pos_embedding_3
         t1, t2 = enc(tok).chunk(2, dim=1)
@@ -110,7 +119,7 @@ class BASE_Transformer_UNet(_LevirNet):
         if self.with_decoder_pos == 'learned' and k == 5:
             dx = dx + self.pos_embedding_decoder_3
         b, c, h, w = dx.shape
-        if getattr(self, "native_training", True) and torch.is_grad_enabled():
-            return T.pixel_decoder(dx.flatten(2), dec.train_tables((t2 - t1).abs()), dec.heads).view(b, c, h, w)
+        if native:
+            return T.pixel_decoder(dx, dec.train_tables((t2 - t1).abs()), dec.heads)
         run = dec.forward_collapsed if getattr(self, "collapsed_training", True) else dec
         return run(dx.flatten(2).transpose(1, 2), (t2 - t1).abs()).transpose(1, 2).reshape(b, c, h, w)

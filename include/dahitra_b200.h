@@ -299,7 +299,8 @@ int dahitra_classifier(const float* in, int N, int H, int W, int nc, const float
 /* ---- training step: pixel decoder forward that keeps the layer inputs + its hand-written backward ----------
  * Replaces, on the training route, the per-pixel arithmetic of reference models/help_funcs.py:66-114,170-186 and the
  * autograd graph eager PyTorch builds for it (models/trainer.py:247-262).  fp32 FMAs throughout.
- *   x, out, dout, dx  channel-planar [nimg][32][npix] (the reference's NCHW tensors)
+ *   x, out, dout, dx  pixel_major = 0: channel-planar [nimg][32][npix] (the reference's NCHW tensors);
+ *                     pixel_major = 1: [nimg][npix][32] (the same tensors in torch.channels_last memory format)
  *   tables            [nimg][depth][DH_TRAIN_TAB_FLOATS(heads)], per (image, layer), K = 4*heads, k = head*4 + token:
  *                       A [32][K] | c0 [K] | Bv [K][32] | bo [32] | W1 [32][32] | b1 [32] | W2 [32][32] | b2 [32]
  *                     (all matrices input-major; built by the host from Wq/Wk/Wv/Wo, the LayerNorm affines, the MLP and the
@@ -310,9 +311,23 @@ int dahitra_classifier(const float* in, int N, int H, int W, int nc, const float
 #define DH_TRAIN_TAB_FLOATS(H) (65*4*(H) + 96 + 2048)
 int dahitra_pixel_decoder_train_blocks(int npix);
 int dahitra_pixel_decoder_train_fwd(const float* x, const float* tables, float* xs, float* out, int nimg, int npix,
-                                    int heads, int depth, void* stream);
+                                    int heads, int depth, int pixel_major, void* stream);
 int dahitra_pixel_decoder_train_bwd(const float* dout, const float* xs, const float* tables, float* dx,
-                                    float* dtables_partial, int nimg, int npix, int heads, int depth, void* stream);
+                                    float* dtables_partial, int nimg, int npix, int heads, int depth, int pixel_major,
+                                    void* stream);
+
+/* Semantic tokenizer of the training step: replaces reference models/networks.py:1273-1280 (_forward_semantic_tokens: 1x1 conv
+ * 32 -> 4, softmax over the N pixels, einsum to 4 tokens) and its autograd graph.
+ *   x, dx        [nimg][32][npix] (pixel_major = 0) or [nimg][npix][32] (pixel_major = 1): the post-ReLU squeeze output
+ *   w_tok        [4][32] (conv_token_k.weight);  tokens / dtokens [nimg][4][32];  stats [nimg][4][2] = softmax max and sum
+ *   partials     scratch [nimg][dahitra_tokenizer_train_chunks(npix)][4][34]
+ *   dw_partial   [nimg][chunks][4][32]: WRITTEN per CTA; the caller sums over the first two axes (deterministic) */
+int dahitra_tokenizer_train_chunks(int npix);
+int dahitra_tokenizer_train_fwd(const float* x, const float* w_tok, float* partials, float* tokens, float* stats,
+                                int nimg, int npix, int pixel_major, void* stream);
+int dahitra_tokenizer_train_bwd(const float* x, const float* w_tok, const float* tokens, const float* stats,
+                                const float* dtokens, float* dx, float* dw_partial, int nimg, int npix, int pixel_major,
+                                void* stream);
 
 /* ---- next to the hot path ------------------------------------------------------------ */
 

@@ -20,8 +20,8 @@ for name, B, N, heads, depth in (("level5 pair", 16, 256, 4, 4), ("level5 diff",
     nblk = lib.dahitra_pixel_decoder_train_blocks(N)
     part = torch.empty(B, nblk, depth, T, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-    fwd = lambda: _lib.check(lib.dahitra_pixel_decoder_train_fwd(x.data_ptr(), tab.data_ptr(), xs.data_ptr(), out.data_ptr(), B, N, heads, depth, st))
-    bwd = lambda: _lib.check(lib.dahitra_pixel_decoder_train_bwd(out.data_ptr(), xs.data_ptr(), tab.data_ptr(), dx.data_ptr(), part.data_ptr(), B, N, heads, depth, st))
+    fwd = lambda: _lib.check(lib.dahitra_pixel_decoder_train_fwd(x.data_ptr(), tab.data_ptr(), xs.data_ptr(), out.data_ptr(), B, N, heads, depth, 0, st))
+    bwd = lambda: _lib.check(lib.dahitra_pixel_decoder_train_bwd(out.data_ptr(), xs.data_ptr(), tab.data_ptr(), dx.data_ptr(), part.data_ptr(), B, N, heads, depth, 0, st))
     ms = []
     for fn in (fwd, bwd):
         for _ in range(3):

@@ -22,6 +22,9 @@ x2 = torch.rand(8, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 y = (torch.rand(8, 256, 256, device="cuda", generator=g) < 0.1).long()
 
 
+net.channels_last_training = "--nchw" not in sys.argv
+
+
 def step():
     opt.zero_grad(set_to_none=True)
     loss = F.cross_entropy(net(x1, x2), y)
@@ -36,4 +39,4 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=150, max_name_column_width=90))

@@ -25,6 +25,7 @@ def measure(patch=None, native=None):
     net = define_G(Args(), gpu_ids=[0]).train()
     if native is not None:
         net.native_training = native
+        net.channels_last_training = native          # stock = round 2's earlier route (NCHW, torch ops)
     undo = patch(net) if patch else None
 
     def fb():

@@ -22,6 +22,7 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--as-written", action="store_true", help="pixel decoders as the reference writes them (q / k / v / out projections) instead of the collapsed algebra")
 ap.add_argument("--stock", action="store_true", help="pixel decoders on stock torch ops instead of the native training kernels (csrc/train_decoder.cu)")
+ap.add_argument("--nchw", action="store_true", help="keep activations / parameters NCHW-contiguous instead of the module's default torch.channels_last training layout")
 ap.add_argument("--graph", action="store_true", help="capture forward + backward + AdamW step in ONE CUDA graph and replay it (1 GPU)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -43,6 +44,7 @@ g = torch.Generator(device="cuda").manual_seed(100 + rank)
 x1 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 x2 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 y = (torch.rand(a.batch, 256, 256, device="cuda", generator=g) < 0.1).long()
+net.channels_last_training = not a.nchw
 losses = []
 w2 = torch.ones(2, device="cuda")
 
@@ -97,8 +99,13 @@ if a.graph:
     live = [p for p in net.parameters() if p.grad is not None]             # the warm-up steps above marked them
     flat_grad = torch.zeros(sum(p.numel() for p in live), device="cuda")
     off = 0
-    for p in live:
-        p.grad = flat_grad[off:off + p.numel()].view_as(p)
+    for p in live:                                                          # views with the parameter's own strides (channels_last
+        g_ = flat_grad[off:off + p.numel()]                                 # for the 4-D ones): the gradient layout contract holds
+        if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+            g_ = g_.view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)
+        else:
+            g_ = g_.view_as(p)
+        p.grad = g_
         off += p.numel()
     for p in net.parameters():
         if p.grad is None:
@@ -169,7 +176,7 @@ if rank == 0:
                           else "native sm_100a forward + backward kernels (csrc/train_decoder.cu)",
                       workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW ({'one CUDA graph per iteration, ' if a.graph else ''}autograd route"
                                    + ((", one flat NCCL all-reduce of the live gradients)" if a.graph else ", DDP/NCCL all-reduce)") if world > 1 else ")"),
-                          steps=a.steps, step_ms=step_ms, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
+                          memory_format="contiguous (NCHW)" if a.nchw else "channels_last (set by the module)", steps=a.steps, step_ms=step_ms, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
                           pairs_per_s_per_gpu=a.steps * a.batch / dt,
                           step_ms_without_allreduce=nosync_ms, exposed_allreduce_share=(None if nosync_ms is None else max(0.0, 1 - nosync_ms / step_ms)),
                           allreduce_alone_ms=ar_ms, gradient_bytes=grad_bytes,
