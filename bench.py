@@ -296,6 +296,18 @@ def run_native(a, wl):
         for i in range(3):
             fwd(*ssets[i % nsets])
         ms_strong = _time_steps(lambda i: fwd(*ssets[i % nsets]), a.steps, barrier)
+        # the same as replayed CUDA graphs (one per input set): at 64/N pairs per rank the step is ~40 dependent launches of
+        # 8-15 us each, and N processes issuing them from Python share the host's cores
+        sgraphs = []
+        for sset in ssets:
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                y_ = fwd(*sset)
+            sgraphs.append((g_, y_))
+        for i in range(3):
+            sgraphs[i % nsets][0].replay()
+        ms_strong_graph = _time_steps(lambda i: sgraphs[i % nsets][0].replay(), a.steps, barrier)
+        del sgraphs
         # ---- e2e through the public pipeline API, host buffers in / class maps out, copies inside the timed region.
         #      Primary: uint8 HWC images as an image reader delivers them (normalised on the device, bit-identical to the
         #      reference loaders); sub-key f32: already-normalised fp32 NCHW host tensors (4x the PCIe bytes).
@@ -412,11 +424,11 @@ def run_native(a, wl):
                                      max_abs_vs_fp32=float(do.max()), outside_tol=int((do > 1e-4 + 1e-3 * y_ref.abs()).sum()),
                                      argmax_agree=float((y_o.argmax(1) == y_ref.argmax(1)).float().mean()))
             net._engine.flags = saved
-    tmax = torch.tensor([ms, e2e_sec * 1e3, e2e_sync_sec * 1e3, ms_strong, f32_sec * 1e3, h2d_u8_ms, h2d_f32_ms],
+    tmax = torch.tensor([ms, e2e_sec * 1e3, e2e_sync_sec * 1e3, ms_strong, f32_sec * 1e3, h2d_u8_ms, h2d_f32_ms, ms_strong_graph],
                         device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, e2e_sync_ms, ms_strong, f32_ms, h2d_u8_ms, h2d_f32_ms = (float(v) for v in tmax)
+    ms, e2e_ms, e2e_sync_ms, ms_strong, f32_ms, h2d_u8_ms, h2d_f32_ms, ms_strong_graph = (float(v) for v in tmax)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -493,6 +505,8 @@ def run_native(a, wl):
                 clocks=clocks,
                 strong_scaling=dict(global_pairs_per_step=sB * world, pairs_per_gpu=sB, value=sB * world / (ms_strong / a.steps / 1e3),
                                     unit="pairs/s", ms_per_step=ms_strong / a.steps,
+                                    cuda_graph=dict(value=sB * world / (ms_strong_graph / a.steps / 1e3), ms_per_step=ms_strong_graph / a.steps,
+                                                    note="the same forward captured once per input set and replayed"),
                                     note="configs[1] as written: one global batch split evenly over the ranks, no collective; "
                                          "efficiency at N = this value / (N=1 value)"),
                 e2e=dict(value=e2e_value, unit="pairs/s", h2d_bytes_per_step=in_u8, d2h_bytes_per_step=Bp * H * W,

@@ -100,6 +100,8 @@ class BASE_Transformer_UNet(nn.Module):
         # no NCHW <-> NHWC transposes around every convolution; the native decoder kernels read it pixel-major).  Shapes, values
         # and state_dict keys are unchanged — only strides
         self.channels_last_training = True
+        # training route: both image sets through each trunk convolution as one batch, BatchNorm per set (_trunk_pair_autograd)
+        self.paired_trunk_training = True
         # native engine (lazy: weights are folded / re-laid-out on the first inference call)
         self._engine = NativeEngine()
 
@@ -154,7 +156,8 @@ class BASE_Transformer_UNet(nn.Module):
         x16 = r.layer3(r.maxpool(x8))
         return x2, x4, x8, x16
 
-    def _level_autograd(self, f1, f2, k):
+    def _level_autograd(self, f1, f2, k, f12=None):
+        """f12: optional batch [f1 | f2] already in one tensor (paired trunk)"""
         sq, tk = getattr(self, f"conv_squeeze_{k}"), getattr(self, f"conv_token_{k}")
         enc, dec = getattr(self, f"transformer_{k}"), getattr(self, f"transformer_decoder_{k}")
 
@@ -182,7 +185,7 @@ class BASE_Transformer_UNet(nn.Module):
             # both image sets as one batch (the squeeze has no BatchNorm): tokenizer, ONE table build for the level's three
             # decoder calls, one decoder launch for x1 | x2 and one for the difference features
             nb = f1.shape[0]
-            x12 = sq(torch.cat([f1, f2]))
+            x12 = sq(torch.cat([f1, f2]) if f12 is None else f12)
             t12 = T.semantic_tokens(x12, tk.weight)
             tok = torch.cat([t12[:nb], t12[nb:]], dim=1)
             if self.with_pos:
@@ -210,13 +213,41 @@ class BASE_Transformer_UNet(nn.Module):
                         p.grad.data = p.grad.data.contiguous(memory_format=torch.channels_last)
         return tuple(x.contiguous(memory_format=torch.channels_last) for x in xs)
 
+    def _trunk_pair_autograd(self, x12, nb):
+        """Both image sets through every convolution as ONE batch (convolutions are per-sample), BatchNorm applied per set:
+        batch statistics and the running-stat updates are exactly the reference's two forward_single passes (set 1, then
+        set 2, per layer), with half the convolution launches and twice the rows per launch."""
+        r = self.resnet
+
+        def bn2(bn, y):
+            return torch.cat([bn(y[:nb]), bn(y[nb:])])
+
+        def stage(blocks, x):
+            for blk in blocks:
+                idt = x if blk.downsample is None else bn2(blk.downsample[1], blk.downsample[0](x))
+                y = F.relu(bn2(blk.bn1, blk.conv1(x)))
+                x = F.relu(bn2(blk.bn2, blk.conv2(y)) + idt)
+            return x
+
+        x2 = F.relu(bn2(r.bn1, r.conv1(x12)))
+        x4 = stage(r.layer1, r.maxpool(x2))
+        x8 = stage(r.layer2, x4)
+        x16 = stage(r.layer3, r.maxpool(x8))
+        return x2, x4, x8, x16
+
     def _forward_autograd(self, x1, x2):
         x1, x2 = self._channels_last(x1, x2)
-        a, b = self._trunk_autograd(x1), self._trunk_autograd(x2)   # two passes: BN batch stats per image set
+        nb = x1.shape[0]
+        if getattr(self, "paired_trunk_training", True) and torch.is_grad_enabled():
+            t = self._trunk_pair_autograd(torch.cat([x1, x2]), nb)
+            a, b = [f[:nb] for f in t], [f[nb:] for f in t]
+        else:
+            a, b = self._trunk_autograd(x1), self._trunk_autograd(x2)   # two passes: BN batch stats per image set
+            t = (None,) * 4
         up = self.upsamplex2
-        o5 = up(self._level_autograd(a[3], b[3], 5))
-        o4 = self.conv_layer4(up(self._level_autograd(a[2], b[2], 4) + o5))
-        o3 = self.conv_layer3(up(self._level_autograd(a[1], b[1], 3) + o4))
+        o5 = up(self._level_autograd(a[3], b[3], 5, f12=t[3]))
+        o4 = self.conv_layer4(up(self._level_autograd(a[2], b[2], 4, f12=t[2]) + o5))
+        o3 = self.conv_layer3(up(self._level_autograd(a[1], b[1], 3, f12=t[1]) + o4))
         o2 = self.conv_layer2(up(self.conv_layer2_0(torch.cat([a[0], b[0]], 1)) + o3))
         return self.classifier(o2)
 

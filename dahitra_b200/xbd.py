@@ -80,6 +80,7 @@ class BASE_Transformer_UNet(_LevirNet):
         self.collapsed_training = True          # training route: pixel decoders in the collapsed algebra (see networks.py)
         self.native_training = True             # ... on the native kernels whenever autograd is recording (training.py)
         self.channels_last_training = True      # ... with activations / 4-D parameters in torch.channels_last (see networks.py)
+        self.paired_trunk_training = True       # ... and both image sets through each trunk convolution as one batch
         self._engine = NativeEngine()
 
     def pos_shapes(self, H, W):
@@ -95,7 +96,7 @@ class BASE_Transformer_UNet(_LevirNet):
         return self._engine.forward_stacked(self, x)
 
     # training route: same chain as the LEVIR class except for the trans-module (one decoder pass)
-    def _level_autograd(self, f1, f2, k):
+    def _level_autograd(self, f1, f2, k, f12=None):
         sq, tk = getattr(self, f"conv_squeeze_{k}"), getattr(self, f"conv_token_{k}")
         enc, dec = getattr(self, f"transformer_{k}"), getattr(self, f"transformer_decoder_{k}")
 
@@ -105,7 +106,7 @@ class BASE_Transformer_UNet(_LevirNet):
         native = getattr(self, "native_training", True) and torch.is_grad_enabled()
         if native:
             nb = f1.shape[0]
-            x12 = sq(torch.cat([f1, f2]))
+            x12 = sq(torch.cat([f1, f2]) if f12 is None else f12)
             t12 = T.semantic_tokens(x12, tk.weight)
             x1, x2 = x12[:nb], x12[nb:]
             tok = torch.cat([t12[:nb], t12[nb:]], dim=1)

@@ -7,11 +7,15 @@ import torch
 from dahitra_b200 import _lib
 from dahitra_b200.training import train_tab_floats
 
+only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None      # e.g. --only "level3 pair" (for ncu captures)
+iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 20
 lib = _lib.load()
 dev = "cuda"
 rows = []
 for name, B, N, heads, depth in (("level5 pair", 16, 256, 4, 4), ("level5 diff", 8, 256, 4, 4), ("level4 pair", 16, 1024, 4, 4),
                                  ("level4 diff", 8, 1024, 4, 4), ("level3 pair", 16, 4096, 8, 8), ("level3 diff", 8, 4096, 8, 8)):
+    if only and name != only:
+        continue
     T = train_tab_floats(heads)
     x = torch.randn(B, 32, N, device=dev)
     tab = torch.randn(B, depth, T, device=dev) * 0.15
@@ -29,11 +33,11 @@ for name, B, N, heads, depth in (("level5 pair", 16, 256, 4, 4), ("level5 diff",
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(20):
+        for _ in range(iters):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms.append(e0.elapsed_time(e1) / 20)
+        ms.append(e0.elapsed_time(e1) / iters)
     K = 4 * heads
     fma_fwd = B * N * depth * (2 * 32 * K + 2 * 1024)
     rows.append(dict(call=name, images=B, pixels=N, heads=heads, depth=depth, ctas=B * nblk, fwd_ms=ms[0], bwd_ms=ms[1],

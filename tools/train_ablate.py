@@ -26,6 +26,7 @@ def measure(patch=None, native=None):
     if native is not None:
         net.native_training = native
         net.channels_last_training = native          # stock = round 2's earlier route (NCHW, torch ops)
+        net.paired_trunk_training = native
     undo = patch(net) if patch else None
 
     def fb():

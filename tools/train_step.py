@@ -23,6 +23,7 @@ ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--as-written", action="store_true", help="pixel decoders as the reference writes them (q / k / v / out projections) instead of the collapsed algebra")
 ap.add_argument("--stock", action="store_true", help="pixel decoders on stock torch ops instead of the native training kernels (csrc/train_decoder.cu)")
 ap.add_argument("--nchw", action="store_true", help="keep activations / parameters NCHW-contiguous instead of the module's default torch.channels_last training layout")
+ap.add_argument("--two-pass-trunk", action="store_true", help="run the trunk once per image set (the reference's two forward_single calls) instead of one batch with per-set BatchNorm")
 ap.add_argument("--graph", action="store_true", help="capture forward + backward + AdamW step in ONE CUDA graph and replay it (1 GPU)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -45,6 +46,7 @@ x1 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 x2 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 y = (torch.rand(a.batch, 256, 256, device="cuda", generator=g) < 0.1).long()
 net.channels_last_training = not a.nchw
+net.paired_trunk_training = not a.two_pass_trunk
 losses = []
 w2 = torch.ones(2, device="cuda")
 
@@ -176,7 +178,7 @@ if rank == 0:
                           else "native sm_100a forward + backward kernels (csrc/train_decoder.cu)",
                       workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW ({'one CUDA graph per iteration, ' if a.graph else ''}autograd route"
                                    + ((", one flat NCCL all-reduce of the live gradients)" if a.graph else ", DDP/NCCL all-reduce)") if world > 1 else ")"),
-                          memory_format="contiguous (NCHW)" if a.nchw else "channels_last (set by the module)", steps=a.steps, step_ms=step_ms, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
+                          trunk="one pass per image set" if a.two_pass_trunk else "both image sets per convolution launch, BatchNorm per set", memory_format="contiguous (NCHW)" if a.nchw else "channels_last (set by the module)", steps=a.steps, step_ms=step_ms, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
                           pairs_per_s_per_gpu=a.steps * a.batch / dt,
                           step_ms_without_allreduce=nosync_ms, exposed_allreduce_share=(None if nosync_ms is None else max(0.0, 1 - nosync_ms / step_ms)),
                           allreduce_alone_ms=ar_ms, gradient_bytes=grad_bytes,
