@@ -139,6 +139,26 @@ class BASE_Transformer_UNet(nn.Module):
             return {}
         return {f"DH_W_LV{k}_POS": (H // d) * (W // d) for k, d in ((5, 16), (4, 8), (3, 4))}
 
+    # ------------------------------------------------------------------ checkpoint ballast
+    _UNUSED_PREFIXES = ("conv_squeeze_2.", "conv_token_2.", "conv_decode_2.", "pos_embedding_2", "pos_embedding_decoder_2",
+                        "transformer_2.", "transformer_decoder_2.", "conv_pred.", "resnet.layer4.", "resnet.fc.")
+
+    def unused_parameter_names(self):
+        """Parameters no forward ever reads — the reference module carries the same ballast (scale-2 tokenizer / transformer
+        that `_forward_trans_module` is never called with, `conv_pred`, `resnet.layer4` / `fc`; models/networks.py:1106,1176-1238,
+        1326-1351).  They never receive a gradient, which is why stock DistributedDataParallel needs
+        `find_unused_parameters=True` on this network."""
+        return [n for n, _ in self.named_parameters() if n.startswith(self._UNUSED_PREFIXES)]
+
+    def freeze_unused_parameters(self):
+        """requires_grad_(False) on `unused_parameter_names()`: DDP then runs without its per-step unused-parameter search.  The
+        optimizer step is unchanged (AdamW skips parameters without a gradient either way).  Returns the names."""
+        names = set(self.unused_parameter_names())
+        for n, p in self.named_parameters():
+            if n in names:
+                p.requires_grad_(False)
+        return sorted(names)
+
     # ------------------------------------------------------------------ forward
     def forward(self, x1, x2):
         if not (x1.is_cuda and x2.is_cuda):

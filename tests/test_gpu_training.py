@@ -238,3 +238,43 @@ def test_training_step_in_cuda_graph_native():
     torch.cuda.synchronize()
     for p, e in zip(live, eager):
         assert rel(p.grad, e) < 1e-3                         # BN running stats do not enter the train-mode forward
+
+
+def test_graphed_train_step_matches_the_eager_loop():
+    """dahitra_b200.train_graph.GraphedTrainStep on the real network: three AdamW steps replayed from the two CUDA graphs leave the
+    same weights and BatchNorm statistics as the plain eager loop of models/trainer.py:247-262 on a copy of the module."""
+    import copy
+    from dahitra_b200.train_graph import GraphedTrainStep
+    torch.manual_seed(0)
+    net = define_G(Args(), gpu_ids=[0]).train()
+    ref = copy.deepcopy(net).train()
+    g = torch.Generator(device=DEV).manual_seed(11)
+    mk = lambda: (torch.rand(2, 3, 256, 256, device=DEV, generator=g) * 2 - 1, torch.rand(2, 3, 256, 256, device=DEV, generator=g) * 2 - 1,   # noqa: E731
+                  (torch.rand(2, 256, 256, device=DEV, generator=g) < 0.2).long())
+    batches = [mk() for _ in range(4)]
+    # SGD with momentum: the weights stay a linear function of the gradients (Adam's first steps are sign-like and would turn
+    # fp32 gradient noise on near-zero entries into +-lr differences); tools/train_step.py runs the same class with AdamW
+    mk_opt = lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=0.01)          # noqa: E731
+    ts = GraphedTrainStep(net, F.cross_entropy, batches[0], mk_opt)
+    assert ts.use_graph and len(ts.frozen) == 48 and ts.flat.numel() == sum(p.numel() for p in ts.live)
+    opt = mk_opt(ref.parameters())
+    for b in batches[1:]:
+        l1 = ts.step(*b).clone()
+        opt.zero_grad(set_to_none=True)
+        l2 = F.cross_entropy(ref(b[0], b[1]), b[2])
+        l2.backward()
+        opt.step()
+        assert abs(float(l1) - float(l2)) <= 1e-5 * abs(float(l2)), (float(l1), float(l2))
+    torch.cuda.synchronize()
+    worst = 0.0
+    for (n, a), b in zip(net.state_dict().items(), ref.state_dict().values()):
+        if a.dtype.is_floating_point:
+            worst = max(worst, rel(a, b))
+            assert rel(a, b) <= 2e-3, (n, rel(a, b))
+        else:
+            assert torch.equal(a, b), n                         # num_batches_tracked: the warm-up left no trace
+    print(f"[graphed step] worst relative weight difference after 3 steps: {worst:.2e}")
+    net.eval()
+    with torch.no_grad():                                       # and the native inference path reads the trained weights
+        y = net(batches[0][0], batches[0][1])
+    assert torch.isfinite(y).all()

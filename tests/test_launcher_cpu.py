@@ -57,3 +57,72 @@ def test_pair_sharding_world_size_2_gloo(tmp_path):
         out, err = p.communicate(timeout=300)
         assert p.returncode == 0, err[-2000:]
         assert "ok" in out
+
+
+TRAIN_WORKER = r"""
+import copy, os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DAHITRA_ROOT"])
+from dahitra_b200.train_graph import GraphedTrainStep
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+r = dist.get_rank()
+torch.manual_seed(0)                                       # same initial weights on both ranks
+
+
+class Net(torch.nn.Module):                                # stand-in with the network's traits: BatchNorm, a conv, dead parameters
+    def __init__(self):
+        super().__init__()
+        self.c1 = torch.nn.Conv2d(3, 8, 3, padding=1)
+        self.bn = torch.nn.BatchNorm2d(8)
+        self.c2 = torch.nn.Conv2d(8, 2, 1)
+        self.dead = torch.nn.Linear(4, 4)
+
+    def forward(self, x):
+        return self.c2(torch.relu(self.bn(self.c1(x))))
+
+
+net = Net().to(memory_format=torch.channels_last)
+ref = copy.deepcopy(net)
+lf = torch.nn.functional.cross_entropy
+g = torch.Generator().manual_seed(10 + r)                  # different data per rank
+x = torch.randn(4, 3, 8, 8, generator=g)
+y = torch.randint(0, 2, (4, 8, 8), generator=g)
+ts = GraphedTrainStep(net, lf, (x, y), lambda ps: torch.optim.AdamW(ps, lr=1e-2, weight_decay=0.01), use_graph=False)
+assert len(ts.frozen) == 2 and ts.world == 2
+opt = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=0.01)
+for i in range(3):
+    xi = torch.randn(4, 3, 8, 8, generator=g)
+    ts.step(xi, y)
+    # reference: plain loop + explicit per-parameter all-reduce (mean) of the gradients
+    opt.zero_grad(set_to_none=True)
+    lf(ref.train()(xi), y).backward()
+    for p in ref.parameters():
+        if p.grad is not None:
+            dist.all_reduce(p.grad)
+            p.grad /= 2
+    opt.step()
+for (n, a), b in zip(net.state_dict().items(), ref.state_dict().values()):
+    if "running" in n or "num_batches" in n:
+        continue                                           # BatchNorm statistics are per rank in both
+    assert torch.allclose(a.double(), b.double(), rtol=1e-6, atol=1e-7), n
+    w = a.clone().contiguous()
+    dist.broadcast(w, 0)
+    assert torch.equal(w, a.contiguous()), "replicas differ: " + n
+dist.destroy_process_group()
+print("rank", r, "ok")
+"""
+
+
+def test_graphed_train_step_flat_allreduce_world_size_2_gloo(tmp_path):
+    """dahitra_b200.train_graph.GraphedTrainStep (eager form): one flat gradient buffer + ONE all-reduce gives exactly the
+    weights of the plain loop with per-parameter gradient averaging; replicas stay identical; dead parameters are frozen."""
+    script = tmp_path / "t.py"
+    script.write_text(TRAIN_WORKER)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), PORT="29643", DAHITRA_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err[-2000:]
+        assert "ok" in out

@@ -24,6 +24,7 @@ ap.add_argument("--as-written", action="store_true", help="pixel decoders as the
 ap.add_argument("--stock", action="store_true", help="pixel decoders on stock torch ops instead of the native training kernels (csrc/train_decoder.cu)")
 ap.add_argument("--nchw", action="store_true", help="keep activations / parameters NCHW-contiguous instead of the module's default torch.channels_last training layout")
 ap.add_argument("--two-pass-trunk", action="store_true", help="run the trunk once per image set (the reference's two forward_single calls) instead of one batch with per-set BatchNorm")
+ap.add_argument("--freeze-unused", action="store_true", help="net.freeze_unused_parameters(): DDP without find_unused_parameters")
 ap.add_argument("--graph", action="store_true", help="capture forward + backward + AdamW step in ONE CUDA graph and replay it (1 GPU)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -37,9 +38,11 @@ net = define_G(Args(), gpu_ids=[local]).train()
 net.collapsed_training = not a.as_written
 net.native_training = not (a.stock or a.as_written)
 model = net
+if a.freeze_unused:
+    net.freeze_unused_parameters()
 if world > 1 and not a.graph:
     # like the reference, the module owns parameters its forward never uses (scale-2 transformer, conv_pred, layer4)
-    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=not a.freeze_unused)
 opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, capturable=a.graph)           # models/trainer.py:39-40
 g = torch.Generator(device="cuda").manual_seed(100 + rank)
 x1 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
@@ -51,18 +54,12 @@ losses = []
 w2 = torch.ones(2, device="cuda")
 
 
-graph, graph_opt, static_loss, flat_grad = None, None, None, None
+ts, flat_grad = None, None
 
 
 def one_step(sync=True):
-    if graph is not None:
-        # graph 1: zero the flat gradient buffer, forward, loss, backward (gradients accumulate in place into views of the flat
-        # buffer); NCCL all-reduce of that ONE buffer; graph 2: the AdamW step
-        graph.replay()
-        if world > 1 and sync:
-            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
-        graph_opt.replay()
-        return static_loss
+    if ts is not None:
+        return ts.step(x1, x2, y, sync_gradients=sync)
     opt.zero_grad(set_to_none=True)
     ctx = model.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
     with ctx:
@@ -89,53 +86,15 @@ def timed(n, sync=True):
 
 
 for _ in range(3):                               # warm-up (cuDNN autotune, allocator, DDP bucket rebuild)
-    if a.graph:                                  # forward + backward only: the replicas must not step before their gradients are shared
-        F.cross_entropy(model(x1, x2), y, weight=w2, ignore_index=255).backward()
-    else:
+    if not a.graph:                              # (GraphedTrainStep does its own warm-up)
         losses.append(one_step().detach())
 if a.graph:
-    # The ~2500 small launches of the stock-autograd step are replayed from CUDA graphs instead of being issued one by one
-    # from Python (the eager step is bound by that issue rate once the decoders run in the collapsed algebra).  Multi-GPU: no
-    # DDP wrapper — every parameter that receives a gradient gets a view into ONE flat buffer as its .grad, the backward
-    # graph accumulates into it in place, and a single NCCL all-reduce (mean) of the buffer runs between the two graphs.
-    live = [p for p in net.parameters() if p.grad is not None]             # the warm-up steps above marked them
-    flat_grad = torch.zeros(sum(p.numel() for p in live), device="cuda")
-    off = 0
-    for p in live:                                                          # views with the parameter's own strides (channels_last
-        g_ = flat_grad[off:off + p.numel()]                                 # for the 4-D ones): the gradient layout contract holds
-        if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
-            g_ = g_.view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)
-        else:
-            g_ = g_.view_as(p)
-        p.grad = g_
-        off += p.numel()
-    for p in net.parameters():
-        if p.grad is None:
-            p.requires_grad_(False)                                         # the 48 tensors the forward never touches
-    opt = torch.optim.AdamW(live, lr=1e-3, weight_decay=0.01, capturable=True)
-
-    def fwd_bwd():
-        flat_grad.zero_()
-        loss = F.cross_entropy(net(x1, x2), y, weight=w2, ignore_index=255)
-        loss.backward()
-        return loss
-
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            fwd_bwd()
-            if world > 1:
-                dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
-            opt.step()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    g_, g2_ = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g_):
-        static_loss = fwd_bwd()
-    with torch.cuda.graph(g2_):
-        opt.step()
-    graph, graph_opt = g_, g2_
+    # forward + backward and the AdamW step replayed from two CUDA graphs around ONE flat NCCL all-reduce (no DDP wrapper):
+    # dahitra_b200/train_graph.py
+    from dahitra_b200.train_graph import GraphedTrainStep
+    ts = GraphedTrainStep(net, lambda out, tgt: F.cross_entropy(out, tgt, weight=w2, ignore_index=255), (x1, x2, y),
+                          lambda ps: torch.optim.AdamW(ps, lr=1e-3, weight_decay=0.01, capturable=True))
+    flat_grad = ts.flat
 step_ms = timed(a.steps)
 dt = step_ms * a.steps / 1e3
 if world > 1:                                   # replicas must hold identical weights after the all-reduced steps
@@ -178,6 +137,7 @@ if rank == 0:
                           else "native sm_100a forward + backward kernels (csrc/train_decoder.cu)",
                       workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW ({'one CUDA graph per iteration, ' if a.graph else ''}autograd route"
                                    + ((", one flat NCCL all-reduce of the live gradients)" if a.graph else ", DDP/NCCL all-reduce)") if world > 1 else ")"),
+                          ddp=(None if (world == 1 or a.graph) else ("unused parameters frozen, find_unused_parameters=False" if a.freeze_unused else "find_unused_parameters=True")),
                           trunk="one pass per image set" if a.two_pass_trunk else "both image sets per convolution launch, BatchNorm per set", memory_format="contiguous (NCHW)" if a.nchw else "channels_last (set by the module)", steps=a.steps, step_ms=step_ms, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
                           pairs_per_s_per_gpu=a.steps * a.batch / dt,
                           step_ms_without_allreduce=nosync_ms, exposed_allreduce_share=(None if nosync_ms is None else max(0.0, 1 - nosync_ms / step_ms)),
