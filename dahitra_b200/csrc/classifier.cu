@@ -76,11 +76,20 @@ classifier_tma_kernel(const __grid_constant__ CUtensorMap tmIn, int H, int W, in
   int q = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int tx = tile % tilesX, ty = (tile / tilesX) % tilesY, n = tile / (tilesX * tilesY);
+    // NC >= 3 is bound by FMA issue (1440 FMAs per pixel at 5 classes against 128 bytes of input): the channel sum is kept as
+    // two partial sums per class (even / odd channel of each pair), so that every pair of products is ONE packed FFMA2 whose
+    // operands are the natural register pairs of the 128-bit halo / filter loads; the halves are added once per pixel.
+    // NC <= 2 (HBM-bound) keeps the scalar chain, bit-identical to classifier_kernel in conv_ffma.cu.
+    constexpr bool PACK = NC >= 3;
     float acc[4][NC];
+    float2 acc2[PACK ? 4 : 1][PACK ? NC : 1];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int k = 0; k < NC; ++k) acc[j][k] = bsv[k];
+      for (int k = 0; k < NC; ++k) {
+        acc[j][k] = bsv[k];
+        if (PACK) acc2[j][k] = make_float2(bsv[k], 0.f);
+      }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass, ++q) {
       const int b = q % CT_NBUF;
@@ -106,10 +115,15 @@ classifier_tma_kernel(const __grid_constant__ CUtensorMap tmIn, int H, int W, in
               if (j < 0 || j > 3) continue;
 #pragma unroll
               for (int k = 0; k < NC; ++k) {
-                acc[j][k] = fmaf(v.x, ww[r][k].x, acc[j][k]);
-                acc[j][k] = fmaf(v.y, ww[r][k].y, acc[j][k]);
-                acc[j][k] = fmaf(v.z, ww[r][k].z, acc[j][k]);
-                acc[j][k] = fmaf(v.w, ww[r][k].w, acc[j][k]);
+                if (PACK) {
+                  acc2[j][k] = ffma2(make_float2(v.x, v.y), make_float2(ww[r][k].x, ww[r][k].y), acc2[j][k]);
+                  acc2[j][k] = ffma2(make_float2(v.z, v.w), make_float2(ww[r][k].z, ww[r][k].w), acc2[j][k]);
+                } else {
+                  acc[j][k] = fmaf(v.x, ww[r][k].x, acc[j][k]);
+                  acc[j][k] = fmaf(v.y, ww[r][k].y, acc[j][k]);
+                  acc[j][k] = fmaf(v.z, ww[r][k].z, acc[j][k]);
+                  acc[j][k] = fmaf(v.w, ww[r][k].w, acc[j][k]);
+                }
               }
             }
           }
@@ -117,6 +131,12 @@ classifier_tma_kernel(const __grid_constant__ CUtensorMap tmIn, int H, int W, in
       }
       __syncwarp();
       if (lx == 0) mbar_arrive_local(smem_u32(&empty[b]));   // this warp has read everything it needs from the buffer
+    }
+    if (PACK) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) acc[j][k] = acc2[j][k].x + acc2[j][k].y;
     }
     const int x = tx * CT_TW + lx;
     if (x < W) {
