@@ -24,10 +24,27 @@
 // memory as [component][pixel] (row pitch 132 floats: conflict-free both for the per-thread column accesses and for the 16-byte
 // row reads of the weight-gradient pass); contractions keep their outputs in registers and read the weights as warp-uniform
 // 16-byte broadcasts.  The weight gradients are the third kind of product: out[i][j] = sum over the CTA's pixels of a[i][p] b[j][p],
-// each thread owning 4-8 entries.
+// each thread owning 4-8 entries.  Products issue as packed FFMA2 on the register pairs of the 128-bit loads.
+// Bound (ncu, profiles/r02_ncu_full_decoder_train_bwd_level3.txt): the shared-memory pipe (74 %; FMA pipe 41 %) — one 16-byte
+// weight read per four FMAs.  Tried and not kept: two pixels per thread (64-thread CTAs; each weight read feeds two pixels,
+// 1.8x fewer shared-memory wavefronts): correct, but 255 registers with spills and four warps per SM made the backward 40 %
+// SLOWER (0.67 -> 0.86 ms at level 3) — the kernel needs its eight warps per SM to cover the shared-memory latency.
 #include "common.cuh"
 
 namespace {
+
+// packed fp32 pairs (sm_100 FFMA2: two IEEE fp32 FMAs per issued instruction, lane-wise identical to scalar FMAs).  Every
+// contraction below keeps its sums as register pairs so that the products of one 128-bit weight / vector load issue as FFMA2.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
 
 constexpr int PT = 128;        // pixels (= threads) per CTA
 constexpr int PITCH = PT + 4;  // floats per row of a staged vector
@@ -43,19 +60,23 @@ __host__ __device__ constexpr TabOff tab_off(int K) {
 // acc[k] += sum_c in[c][tid] * W[c][k]      (W input-major [CIN][KOUT] in shared memory, warp-uniform reads)
 template <int CIN, int KOUT>
 __device__ __forceinline__ void matvec(const float* __restrict__ in_col, const float* __restrict__ W, float (&acc)[KOUT]) {
+  float2 a2[KOUT / 2];
+#pragma unroll
+  for (int k = 0; k < KOUT / 2; ++k) a2[k] = make_float2(acc[2 * k], acc[2 * k + 1]);
 #pragma unroll 4
   for (int c = 0; c < CIN; ++c) {
     const float v = in_col[c * PITCH];
+    const float2 vv = make_float2(v, v);
     const float4* w4 = reinterpret_cast<const float4*>(W + c * KOUT);
 #pragma unroll
     for (int q = 0; q < KOUT / 4; ++q) {
       const float4 w = w4[q];
-      acc[4 * q + 0] = fmaf(v, w.x, acc[4 * q + 0]);
-      acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
-      acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
-      acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+      a2[2 * q] = ffma2(vv, make_float2(w.x, w.y), a2[2 * q]);
+      a2[2 * q + 1] = ffma2(vv, make_float2(w.z, w.w), a2[2 * q + 1]);
     }
   }
+#pragma unroll
+  for (int k = 0; k < KOUT / 2; ++k) { acc[2 * k] = a2[k].x; acc[2 * k + 1] = a2[k].y; }
 }
 
 // out[j][tid] = sum_c W[j][c] * in[c]       (rows of the same input-major matrix dotted with a register vector: the transposed
@@ -64,20 +85,20 @@ template <int CIN, int JOUT>
 __device__ __forceinline__ void matvec_t(const float (&in)[CIN], const float* __restrict__ W, float* __restrict__ out_col) {
 #pragma unroll 1
   for (int j = 0; j < JOUT; j += 8) {
-    float a[8];
+    float2 a[8];                                   // (sum over even, sum over odd input components) of eight rows
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = 0.f;
+    for (int r = 0; r < 8; ++r) a[r] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < CIN / 4; ++q) {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const float4 w = reinterpret_cast<const float4*>(W + (j + r) * CIN)[q];
-        a[r] = fmaf(w.x, in[4 * q], a[r]); a[r] = fmaf(w.y, in[4 * q + 1], a[r]);
-        a[r] = fmaf(w.z, in[4 * q + 2], a[r]); a[r] = fmaf(w.w, in[4 * q + 3], a[r]);
+        a[r] = ffma2(make_float2(w.x, w.y), make_float2(in[4 * q], in[4 * q + 1]), a[r]);
+        a[r] = ffma2(make_float2(w.z, w.w), make_float2(in[4 * q + 2], in[4 * q + 3]), a[r]);
       }
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) out_col[(j + r) * PITCH] = a[r];
+    for (int r = 0; r < 8; ++r) out_col[(j + r) * PITCH] = a[r].x + a[r].y;
   }
 }
 
@@ -224,9 +245,10 @@ __device__ __forceinline__ void wgrad(const float* __restrict__ a, const float* 
   constexpr int TPR = PT / I;            // threads per row of the result
   constexpr int M = J / TPR;             // entries per thread
   const int i = threadIdx.x / TPR, j0 = threadIdx.x % TPR;
-  float acc[M], bsum[M];
+  float2 acc[M];                                   // (sum over even, sum over odd pixels)
+  float bsum[M];
 #pragma unroll
-  for (int m = 0; m < M; ++m) { acc[m] = 0.f; bsum[m] = 0.f; }
+  for (int m = 0; m < M; ++m) { acc[m] = make_float2(0.f, 0.f); bsum[m] = 0.f; }
   const float4* a4 = reinterpret_cast<const float4*>(a + i * PITCH);
 #pragma unroll 2
   for (int p = 0; p < PT / 4; ++p) {
@@ -234,14 +256,14 @@ __device__ __forceinline__ void wgrad(const float* __restrict__ a, const float* 
 #pragma unroll
     for (int m = 0; m < M; ++m) {
       const float4 bv = reinterpret_cast<const float4*>(bm + (j0 + TPR * m) * PITCH)[p];
-      acc[m] = fmaf(av.x, bv.x, acc[m]); acc[m] = fmaf(av.y, bv.y, acc[m]);
-      acc[m] = fmaf(av.z, bv.z, acc[m]); acc[m] = fmaf(av.w, bv.w, acc[m]);
+      acc[m] = ffma2(make_float2(av.x, av.y), make_float2(bv.x, bv.y), acc[m]);
+      acc[m] = ffma2(make_float2(av.z, av.w), make_float2(bv.z, bv.w), acc[m]);
       if (i == 0) bsum[m] += (bv.x + bv.y) + (bv.z + bv.w);
     }
   }
 #pragma unroll
   for (int m = 0; m < M; ++m) {
-    g_w[i * J + j0 + TPR * m] = acc[m];
+    g_w[i * J + j0 + TPR * m] = acc[m].x + acc[m].y;
     if (i == 0) g_bias[j0 + TPR * m] = bsum[m];
   }
 }
