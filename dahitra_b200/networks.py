@@ -15,6 +15,7 @@ autograd over the same parameters ("training step").
 from __future__ import annotations
 
 import functools
+import os
 
 import torch
 from torch import nn
@@ -102,6 +103,9 @@ class BASE_Transformer_UNet(nn.Module):
         self.channels_last_training = True
         # training route: both image sets through each trunk convolution as one batch, BatchNorm per set (_trunk_pair_autograd)
         self.paired_trunk_training = True
+        # training route: replay forward and backward from CUDA graphs inside the caller's eager loop (training.GraphedRoute;
+        # opt-in: the logits then live in a static buffer that the next training forward overwrites)
+        self.graphed_training = False
         # native engine (lazy: weights are folded / re-laid-out on the first inference call)
         self._engine = NativeEngine()
 
@@ -120,7 +124,23 @@ class BASE_Transformer_UNet(nn.Module):
 
     def _apply(self, fn, *a, **kw):
         self.invalidate_native_cache()
+        self.__dict__.pop("_graphed_route", None)            # .to() / .double() replace the tensors the graphs captured
         return super()._apply(fn, *a, **kw)
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.pop("_graphed_route", None)                       # CUDA graphs are neither picklable nor copyable
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k != "_graphed_route":
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
     def load_state_dict(self, *a, **kw):
         self.invalidate_native_cache()
@@ -164,8 +184,19 @@ class BASE_Transformer_UNet(nn.Module):
         if not (x1.is_cuda and x2.is_cuda):
             raise RuntimeError("dahitra_b200: inputs must be CUDA tensors — this framework has no CPU path")
         if self.training or torch.is_grad_enabled():
-            return self._forward_autograd(x1, x2)
+            return self._forward_training(x1, x2)
         return self._engine.forward_pair(self, x1, x2)
+
+    def _forward_training(self, *xs):
+        """the autograd route, replayed from CUDA graphs when `graphed_training` is on (training.GraphedRoute)"""
+        if self.training and torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing() \
+                and (getattr(self, "graphed_training", False) or os.environ.get("DAHITRA_GRAPH_TRAINING") == "1"):
+            route = self.__dict__.get("_graphed_route")
+            if route is None:
+                route = self.__dict__["_graphed_route"] = T.GraphedRoute(self, xs)
+            if route.matches(xs):
+                return route(*xs)
+        return self._forward_autograd(*xs)
 
     # ------------------------------------------------------------------ training route (stock autograd)
     def _trunk_autograd(self, x):

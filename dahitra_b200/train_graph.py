@@ -6,7 +6,8 @@ The eager step of this network is ~1300 small launches, so one GPU spends more t
 the module, like the reference's, owns 48 parameters no forward ever reads — a per-step unused-parameter search on top.
 ``GraphedTrainStep`` removes both without touching the arithmetic:
 
-* graph 1 = zero the gradients, forward, loss, backward;  graph 2 = the optimizer step (a ``capturable`` torch optimizer);
+* graph 1 = forward, loss, backward (gradients written straight into the flat buffer);  graph 2 = the optimizer step (a
+  ``capturable`` torch optimizer);
 * every parameter that receives a gradient gets a view into ONE flat fp32 buffer as its ``.grad`` (with the parameter's own
   strides, channels_last included), so the data-parallel exchange is a single ``all_reduce(mean)`` of that buffer between the
   two graphs (NCCL over NVLink on GPUs; any ``torch.distributed`` backend works) — no DDP wrapper, no buckets, no hooks;
@@ -98,10 +99,14 @@ class GraphedTrainStep:
                 self.opt.step()
 
     def _forward_backward(self, zero):
-        if zero:
-            self.flat.zero_()
         loss = self.loss_fn(self.net(*self.static[:-1]), self.static[-1])
-        loss.backward()
+        if not zero:                                                             # warm-up: marks the live parameters
+            loss.backward()
+            return loss.detach()
+        # the gradients are WRITTEN into the flat buffer (no zeroing pass, no per-parameter accumulation kernels): autograd
+        # returns them, one multi-tensor copy moves them into the views the optimizer reads as .grad
+        grads = torch.autograd.grad(loss, self.live)
+        torch._foreach_copy_([p.grad for p in self.live], list(grads))
         return loss.detach()
 
     def all_reduce(self):

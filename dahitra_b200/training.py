@@ -131,3 +131,45 @@ def semantic_tokens(x: torch.Tensor, w_tok: torch.Tensor) -> torch.Tensor:
     """x: (B, 32, N) or (B, 32, h, w) fp32 CUDA (NCHW-contiguous or channels_last), w_tok: conv_token_k.weight (4, 32, 1, 1)
     -> tokens (B, 4, 32).  Differentiable in both (first order)."""
     return _SemanticTokensTrain.apply(x, w_tok)
+
+
+# ------------------------------------------------------------------------------------------------ graphed autograd route
+class _Route(torch.nn.Module):
+    """the module's training forward as a callable torch.cuda.make_graphed_callables can wrap (it needs an nn.Module to find
+    the parameters)"""
+
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+
+    def forward(self, *xs):
+        return self.net._forward_autograd(*xs)
+
+
+class GraphedRoute:
+    """forward AND backward of the module's training route as two replayed CUDA graphs inside an ordinary eager training loop
+    (torch.cuda.make_graphed_callables): the reference trainer (models/trainer.py:247-262) keeps computing its loss, calling
+    backward() and stepping its optimizer eagerly, but the ~1200 launches of the network itself are issued by two graph
+    replays.  Built on the first training forward of a given input shape when `net.graphed_training` is set (or
+    DAHITRA_GRAPH_TRAINING=1); other shapes (e.g. a last, smaller batch) run the eager route.  The returned logits live in the
+    graph's static output buffer: they are overwritten by the next training forward, like any graphed callable's."""
+
+    def __init__(self, net, xs):
+        self.key = tuple((tuple(x.shape), x.dtype, x.device) for x in xs)
+        if hasattr(net, "_channels_last"):
+            net._channels_last()                                      # parameter layouts settle before anything is captured
+        buffers = [(b, b.clone()) for b in net.buffers()]             # the warm-up / capture passes must leave no trace
+        grads = [(p, p.grad) for p in net.parameters()]
+        sample = tuple(x.detach().clone() for x in xs)
+        self.call = torch.cuda.make_graphed_callables(_Route(net), sample, allow_unused_input=True)
+        with torch.no_grad():
+            for b, s in buffers:
+                b.copy_(s)
+        for p, g in grads:
+            p.grad = g
+
+    def matches(self, xs):
+        return self.key == tuple((tuple(x.shape), x.dtype, x.device) for x in xs) and not any(x.requires_grad for x in xs)
+
+    def __call__(self, *xs):
+        return self.call(*xs)

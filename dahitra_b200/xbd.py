@@ -81,6 +81,7 @@ class BASE_Transformer_UNet(_LevirNet):
         self.native_training = True             # ... on the native kernels whenever autograd is recording (training.py)
         self.channels_last_training = True      # ... with activations / 4-D parameters in torch.channels_last (see networks.py)
         self.paired_trunk_training = True       # ... and both image sets through each trunk convolution as one batch
+        self.graphed_training = False           # opt-in: forward / backward replayed from CUDA graphs (training.GraphedRoute)
         self._engine = NativeEngine()
 
     def pos_shapes(self, H, W):
@@ -92,7 +93,7 @@ class BASE_Transformer_UNet(_LevirNet):
         if not x.is_cuda:
             raise RuntimeError("dahitra_b200: inputs must be CUDA tensors — this framework has no CPU path")
         if self.training or torch.is_grad_enabled():
-            return self._forward_autograd(x[:, :3], x[:, 3:])
+            return self._forward_training(x[:, :3], x[:, 3:])
         return self._engine.forward_stacked(self, x)
 
     # training route: same chain as the LEVIR class except for the trans-module (one decoder pass)

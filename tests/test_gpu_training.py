@@ -278,3 +278,41 @@ def test_graphed_train_step_matches_the_eager_loop():
     with torch.no_grad():                                       # and the native inference path reads the trained weights
         y = net(batches[0][0], batches[0][1])
     assert torch.isfinite(y).all()
+
+
+def test_graphed_route_inside_an_eager_loop():
+    """net.graphed_training: the trainer's own loop (loss, backward(), optimizer.step() issued eagerly, models/trainer.py:247-262)
+    with the network's forward / backward replayed from CUDA graphs gives the same weights and BatchNorm statistics as the
+    plain eager route; another batch size falls back to the eager route; eval() inference is unaffected."""
+    import copy
+    torch.manual_seed(0)
+    net = define_G(Args(), gpu_ids=[0]).train()
+    ref = copy.deepcopy(net).train()
+    net.graphed_training = True
+    g = torch.Generator(device=DEV).manual_seed(12)
+    mk = lambda b: (torch.rand(b, 3, 256, 256, device=DEV, generator=g) * 2 - 1, torch.rand(b, 3, 256, 256, device=DEV, generator=g) * 2 - 1,   # noqa: E731
+                    (torch.rand(b, 256, 256, device=DEV, generator=g) < 0.2).long())
+    opts = [torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9, weight_decay=0.01) for m in (net, ref)]
+    for bsz in (2, 2, 1, 2):                                     # the third batch is smaller: eager fallback
+        b = mk(bsz)
+        losses = []
+        for m, opt in zip((net, ref), opts):
+            opt.zero_grad(set_to_none=True)
+            loss = F.cross_entropy(m(b[0], b[1]), b[2])
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        assert abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[1]), losses
+    assert net.__dict__.get("_graphed_route") is not None and net._graphed_route.key[0][0] == (2, 3, 256, 256)
+    worst = 0.0
+    for (n, a), b_ in zip(net.state_dict().items(), ref.state_dict().values()):
+        if a.dtype.is_floating_point:
+            worst = max(worst, rel(a, b_))
+            assert rel(a, b_) <= 1e-4, (n, rel(a, b_))
+        else:
+            assert torch.equal(a, b_), n
+    print(f"[graphed route] worst relative weight difference after 4 steps: {worst:.2e}")
+    net.eval()
+    with torch.no_grad():
+        y = net(b[0], b[1])
+    assert torch.isfinite(y).all() and copy.deepcopy(net).__dict__.get("_graphed_route") is None

@@ -25,6 +25,8 @@ ap.add_argument("--stock", action="store_true", help="pixel decoders on stock to
 ap.add_argument("--nchw", action="store_true", help="keep activations / parameters NCHW-contiguous instead of the module's default torch.channels_last training layout")
 ap.add_argument("--two-pass-trunk", action="store_true", help="run the trunk once per image set (the reference's two forward_single calls) instead of one batch with per-set BatchNorm")
 ap.add_argument("--freeze-unused", action="store_true", help="net.freeze_unused_parameters(): DDP without find_unused_parameters")
+ap.add_argument("--graphed-route", action="store_true", help="eager loop (loss, backward(), optimizer as written) with the network's forward / backward replayed from CUDA graphs (net.graphed_training, training.GraphedRoute)")
+ap.add_argument("--foreach-adamw", action="store_true", help="with --graph: torch's foreach AdamW inside the optimizer graph instead of the fused one")
 ap.add_argument("--graph", action="store_true", help="capture forward + backward + AdamW step in ONE CUDA graph and replay it (1 GPU)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -49,6 +51,7 @@ x1 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 x2 = torch.rand(a.batch, 3, 256, 256, device="cuda", generator=g) * 2 - 1
 y = (torch.rand(a.batch, 256, 256, device="cuda", generator=g) < 0.1).long()
 net.channels_last_training = not a.nchw
+net.graphed_training = a.graphed_route
 net.paired_trunk_training = not a.two_pass_trunk
 losses = []
 w2 = torch.ones(2, device="cuda")
@@ -93,7 +96,7 @@ if a.graph:
     # dahitra_b200/train_graph.py
     from dahitra_b200.train_graph import GraphedTrainStep
     ts = GraphedTrainStep(net, lambda out, tgt: F.cross_entropy(out, tgt, weight=w2, ignore_index=255), (x1, x2, y),
-                          lambda ps: torch.optim.AdamW(ps, lr=1e-3, weight_decay=0.01, capturable=True))
+                          lambda ps: torch.optim.AdamW(ps, lr=1e-3, weight_decay=0.01, capturable=True, fused=not a.foreach_adamw))
     flat_grad = ts.flat
 step_ms = timed(a.steps)
 dt = step_ms * a.steps / 1e3
@@ -138,12 +141,13 @@ if rank == 0:
                       workload=f"LEVIR-CD training step, batch {a.batch} x {world} GPU(s), CE loss, AdamW ({'one CUDA graph per iteration, ' if a.graph else ''}autograd route"
                                    + ((", one flat NCCL all-reduce of the live gradients)" if a.graph else ", DDP/NCCL all-reduce)") if world > 1 else ")"),
                           ddp=(None if (world == 1 or a.graph) else ("unused parameters frozen, find_unused_parameters=False" if a.freeze_unused else "find_unused_parameters=True")),
+                          loop=("GraphedTrainStep" if a.graph else "eager loop, network forward / backward replayed from CUDA graphs (graphed_training)" if a.graphed_route else "eager"),
                           trunk="one pass per image set" if a.two_pass_trunk else "both image sets per convolution launch, BatchNorm per set", memory_format="contiguous (NCHW)" if a.nchw else "channels_last (set by the module)", steps=a.steps, step_ms=step_ms, steps_per_s=a.steps / dt, pairs_per_s=a.steps * a.batch * world / dt,
                           pairs_per_s_per_gpu=a.steps * a.batch / dt,
                           step_ms_without_allreduce=nosync_ms, exposed_allreduce_share=(None if nosync_ms is None else max(0.0, 1 - nosync_ms / step_ms)),
                           allreduce_alone_ms=ar_ms, gradient_bytes=grad_bytes,
                           allreduce_alone_share_of_step=(None if ar_ms is None else ar_ms / step_ms),
-                          optimizer="AdamW(lr=1e-3, weight_decay=0.01)", timing="CUDA events over the timed steps after 3 warm-up steps, max over ranks",
+                          optimizer="AdamW(lr=1e-3, weight_decay=0.01)" + (", fused, capturable" if (a.graph and not a.foreach_adamw) else ""), timing="CUDA events over the timed steps after 3 warm-up steps, max over ranks",
                           loss_first=losses[0], loss_last=losses[-1], grad_norm_last=gnorm, params_without_grad=len(no_grad),
                           replicas_equal=replicas_equal, native_vs_autograd_after_training_max_abs=native_vs_autograd)))
 if world > 1:
