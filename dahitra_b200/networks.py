@@ -194,7 +194,7 @@ class BASE_Transformer_UNet(nn.Module):
             route = self.__dict__.get("_graphed_route")
             if route is None:
                 route = self.__dict__["_graphed_route"] = T.GraphedRoute(self, xs)
-            if route.matches(xs):
+            if route.matches(self, xs):
                 return route(*xs)
         return self._forward_autograd(*xs)
 

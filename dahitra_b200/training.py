@@ -155,7 +155,7 @@ class GraphedRoute:
     graph's static output buffer: they are overwritten by the next training forward, like any graphed callable's."""
 
     def __init__(self, net, xs):
-        self.key = tuple((tuple(x.shape), x.dtype, x.device) for x in xs)
+        self.key = self._key(net, xs)
         if hasattr(net, "_channels_last"):
             net._channels_last()                                      # parameter layouts settle before anything is captured
         buffers = [(b, b.clone()) for b in net.buffers()]             # the warm-up / capture passes must leave no trace
@@ -168,8 +168,15 @@ class GraphedRoute:
         for p, g in grads:
             p.grad = g
 
-    def matches(self, xs):
-        return self.key == tuple((tuple(x.shape), x.dtype, x.device) for x in xs) and not any(x.requires_grad for x in xs)
+    @staticmethod
+    def _key(net, xs):
+        # input signature + the route switches that were captured (changing one of them afterwards falls back to the eager route)
+        flags = tuple(bool(getattr(net, f, True)) for f in ("native_training", "channels_last_training", "paired_trunk_training",
+                                                            "collapsed_training"))
+        return tuple((tuple(x.shape), x.dtype, x.device) for x in xs) + (flags,)
+
+    def matches(self, net, xs):
+        return self.key == self._key(net, xs) and not any(x.requires_grad for x in xs)
 
     def __call__(self, *xs):
         return self.call(*xs)
