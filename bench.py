@@ -231,6 +231,38 @@ def _time_steps(fn, steps, barrier):
     return e0.elapsed_time(e1)
 
 
+def _training_leg(dev, batch=8, steps=10):
+    import contextlib
+    import torch.nn.functional as F
+    from dahitra_b200.networks import define_G
+    from dahitra_b200.train_graph import GraphedTrainStep
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(sys.stderr):
+        net = define_G(Args(), gpu_ids=[dev.index]).train()
+    g = torch.Generator(device=dev).manual_seed(100)
+    x1 = torch.rand(batch, 3, 256, 256, device=dev, generator=g) * 2 - 1
+    x2 = torch.rand(batch, 3, 256, 256, device=dev, generator=g) * 2 - 1
+    y = (torch.rand(batch, 256, 256, device=dev, generator=g) < 0.1).long()
+    with torch.enable_grad():
+        ts = GraphedTrainStep(net, F.cross_entropy, (x1, x2, y),
+                              lambda ps: torch.optim.AdamW(ps, lr=1e-3, weight_decay=0.01, capturable=True, fused=True), distributed=False)
+        for _ in range(3):
+            ts.step(x1, x2, y)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        first = float(ts.loss)
+        e0.record()
+        for _ in range(steps):
+            ts.step(x1, x2, y)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return dict(workload=f"LEVIR-CD training step, batch {batch}, CE loss, AdamW(1e-3, wd 0.01), one GPU (models/trainer.py:247-262)",
+                route="native pixel-decoder / tokenizer forward + backward kernels, channels_last, GraphedTrainStep (two CUDA graphs, fused AdamW)",
+                ms_per_step=ms, pairs_per_s_per_gpu=batch / (ms / 1e3), steps=steps, loss_before=first, loss_after=float(ts.loss),
+                note="reported next to the headline; multi-GPU form with the NCCL gradient all-reduce: tools/train_step.py --graph")
+
+
 def run_native(a, wl):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -434,6 +466,15 @@ def run_native(a, wl):
             dist.destroy_process_group()
         return 0
 
+    # ---- configs[3] next to the headline (rank 0 only, no collective: the other ranks are gone): the LEVIR training step,
+    #      batch 8, CE loss, AdamW, on the native training kernels as two replayed CUDA graphs (dahitra_b200/train_graph.py).
+    #      Reported, not part of `value`; tools/train_step.py is the multi-GPU form with the gradient all-reduce.
+    training = None
+    if levir and not a.no_train:
+        try:
+            training = _training_leg(dev)
+        except Exception as e:                                  # never lose the headline line to the side measurement
+            training = dict(error=repr(e)[:300])
     peaks, peak_src = load_peaks()
     ms_step = ms / a.steps
     value = world * Bp / (ms_step / 1e3)
@@ -503,6 +544,7 @@ def run_native(a, wl):
                             mode=mode_name, flags=net._engine.flags,
                             l2="3 rotating input sets (3x%.0f MB) + multi-GB per-step intermediates >> 126 MB L2" % (in_f32 / 1e6)),
                 clocks=clocks,
+                training_step=training,
                 strong_scaling=dict(global_pairs_per_step=sB * world, pairs_per_gpu=sB, value=sB * world / (ms_strong / a.steps / 1e3),
                                     unit="pairs/s", ms_per_step=ms_strong / a.steps,
                                     cuda_graph=dict(value=sB * world / (ms_strong_graph / a.steps / 1e3), ms_per_step=ms_strong_graph / a.steps,
@@ -543,6 +585,7 @@ def main():
     ap.add_argument("--mode", default=DEFAULT_MODE, help="precision mode of the native engine: fp32 | tf32 | tf32_fast | tf32x3")
     ap.add_argument("--flags", type=int, default=None, help="raw DH_FLAG_* bitmask (overrides --mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (configs[3], rank 0, ~5 s)")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity block (oracle on CPU + other modes)")
     ap.add_argument("--ref-pairs", type=int, default=None, help="--impl reference: pairs per step (default: the workload batch for LEVIR, 1 for xBD)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-launch table (name, ms, flops, bytes) to this JSON file")

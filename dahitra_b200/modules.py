@@ -11,8 +11,10 @@ registration order and RNG-consumption order of the reference, so that
 
 None of them carries the arithmetic of the inference path: the native forward in
 ``dahitra_b200.networks`` reads the tensors and launches sm_100a kernels.  The
-small ``forward`` methods below exist only for the autograd (training) route,
-which is stock PyTorch by design (see DESIGN.md "training step").
+small ``forward`` methods below exist for the autograd (training) route: its
+convolutions / BatchNorm are stock PyTorch, its pixel decoders and tokenizer run
+on the native training kernels through ``PixelDecoder.train_tables`` and
+``dahitra_b200.training`` (see DESIGN.md "Training step").
 
 Key layout that is mirrored (reference file:line):
   * ResNet-18 trunk           models/resnet.py:125-204 (conv1, bn1, layer1..4, fc)

@@ -9,8 +9,10 @@ arguments, state_dict keys (425) and ``forward(x1, x2) -> logits`` contract:
 Inference (``eval()`` under ``torch.no_grad()``) runs on hand-written sm_100a
 kernels through the C-ABI library (``include/dahitra_b200.h``).  There is no
 CPU path and no PyTorch fallback for inference: a missing library or a CPU
-tensor raises.  The training step (``train()`` / grad enabled) is stock PyTorch
-autograd over the same parameters ("training step").
+tensor raises.  The training step (``train()`` / grad enabled) is autograd over the
+same parameters: pixel decoders and tokenizer on native forward + backward kernels
+(``dahitra_b200.training``), convolutions / BatchNorm on stock PyTorch (DESIGN.md,
+"Training step").
 """
 from __future__ import annotations
 
@@ -198,7 +200,7 @@ class BASE_Transformer_UNet(nn.Module):
                 return route(*xs)
         return self._forward_autograd(*xs)
 
-    # ------------------------------------------------------------------ training route (stock autograd)
+    # ------------------------------------------------------------------ training route (autograd; native decoder / tokenizer kernels)
     def _trunk_autograd(self, x):
         r = self.resnet
         x2 = F.relu(r.bn1(r.conv1(x)))

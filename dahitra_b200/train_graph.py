@@ -43,12 +43,13 @@ class GraphedTrainStep:
     make_optimizer callable(list_of_live_parameters) -> torch optimizer (pass capturable=True for Adam-family optimizers when
                    use_graph); optimizers whose all-zero state equals their fresh state (Adam family, SGD with momentum) are
                    supported — the state is created by one throw-away step before capture and zeroed again
-    group          torch.distributed process group (default: the world group if initialised, else single process)
+    group          torch.distributed process group (default: the world group if initialised, else single process);
+                   distributed=False keeps the step local even inside an initialised process group
     """
 
-    def __init__(self, net, loss_fn, example_batch, make_optimizer, group=None, use_graph=True, warmup=3):
+    def __init__(self, net, loss_fn, example_batch, make_optimizer, group=None, use_graph=True, warmup=3, distributed=True):
         self.net, self.loss_fn, self.group = net.train(), loss_fn, group
-        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = dist.get_world_size(group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
         self.static = [t.clone() for t in example_batch]
         dev = self.static[0].device
         self.use_graph = bool(use_graph) and dev.type == "cuda"
