@@ -69,6 +69,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+EXAMPLE_SRC = os.path.join(_HERE, "..", "examples", "dahitra_infer.c")
+EXAMPLE_BIN = os.path.join(_HERE, "..", "examples", "bin", "dahitra_infer")
+
+
+def build_example(force: bool = False, verbose: bool = False) -> str:
+    """Compile the plain-C host of the C ABI (examples/dahitra_infer.c: C99, gcc, the CUDA runtime linked statically) against the
+    in-tree library.  No Python or PyTorch is involved in what it runs; the binary is git-ignored and travels with the tree."""
+    src, out = os.path.abspath(EXAMPLE_SRC), os.path.abspath(EXAMPLE_BIN)
+    deps = [src, LIB_PATH, os.path.join(_HERE, "..", "include", "dahitra_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [os.environ.get("CC", "gcc"), "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(_HERE, "..", "include"),
+           "-I", os.path.join(cuda, "include"), src, "-L", _HERE, "-ldahitra_b200", "-L", os.path.join(cuda, "lib64"),
+           "-l:libcudart_static.a", "-ldl", "-lpthread", "-lrt", "-Wl,-rpath,$ORIGIN/../../dahitra_b200", "-o", out + ".tmp"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building examples/dahitra_infer.c failed:\n" + r.stdout + r.stderr)
+    os.replace(out + ".tmp", out)
+    return out
+
+
 # (name, restype, argtypes) — must match include/dahitra_b200.h exactly
 _P, _I, _LL, _SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t
 SIGNATURES = {

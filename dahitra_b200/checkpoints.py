@@ -5,7 +5,8 @@ strictly (models/evaluator.py:68-75); the xBD scripts save ``{'state_dict': mode
 ``nn.DataParallel`` wrapper, i.e. with ``module.`` prefixes (xBD_code/train.py:447-457).  These helpers turn either
 into a plain state_dict for the drop-in modules, convert between the LEVIR (425 keys) and xBD (700 keys: the
 ``nn.ModuleList`` containers add ``*_layers.N.*`` aliases of the per-level keys) key layouts, and export the prepared
-(BN-folded, re-laid-out) weight slots for consumers of the C ABI that do not go through PyTorch.
+(BN-folded, re-laid-out) weight slots for consumers of the C ABI that do not go through PyTorch.  The ``*_bin`` functions at
+the end are the file formats of the plain-C host ``examples/dahitra_infer.c``.
 
 Converting the KEY LAYOUT does not make the two variants compute the same function (the xBD forward runs one decoder
 pass per level and applies positional terms on one level only, xBD_code/zoo/model_transformer_encoding.py:358-406).
@@ -73,3 +74,50 @@ def export_prepared(module, path: str) -> dict:
     arrays = {k: v.numpy() for k, v in P.items() if v is not None}
     np.savez(path, **arrays)
     return {k: tuple(a.shape) for k, a in arrays.items()}
+
+
+# ---- flat binary files of the plain-C host (examples/dahitra_infer.c; formats in its header comment) -----------------------
+def export_state_dict_bin(sd: dict, path: str) -> int:
+    """write the floating-point tensors of a state_dict (reference keys, models/trainer.py:150-158) as a DHSD0001 file — the
+    `dh_tensor` list dahitra_prepare_weights takes, for a host without PyTorch; returns the number of tensors written"""
+    import struct
+    keep = [(k, v.detach().cpu().contiguous()) for k, v in extract_state_dict(sd).items()
+            if torch.is_tensor(v) and v.dtype.is_floating_point and v.dim() <= 4]
+    with open(path, "wb") as f:
+        f.write(b"DHSD0001" + struct.pack("<i", len(keep)))
+        for k, v in keep:
+            v = v if v.dtype == torch.float64 else v.float()
+            name = k.encode()
+            shape = list(v.shape) + [1] * (4 - v.dim())
+            data = v.numpy().tobytes()
+            f.write(struct.pack("<i", len(name)) + name + struct.pack("<ii4qq", int(v.dtype == torch.float64), v.dim(), *shape, len(data)))
+            f.write(data)
+    return len(keep)
+
+
+def write_pairs_bin(path: str, x1: torch.Tensor, x2: torch.Tensor | None = None) -> None:
+    """DHIN0001 input file: two (B,3,H,W) tensors (LEVIR: pre, post) or one (B,6,H,W) tensor (xBD: stacked on the channels)"""
+    import struct
+    ts = [x1] if x2 is None else [x1, x2]
+    B, C, H, W = ts[0].shape
+    if C != (6 if x2 is None else 3) or any(t.shape != ts[0].shape for t in ts):
+        raise ValueError("write_pairs_bin: expected two (B,3,H,W) tensors or one (B,6,H,W) tensor")
+    with open(path, "wb") as f:
+        f.write(b"DHIN0001" + struct.pack("<4i", B, C, H, W))
+        for t in ts:
+            f.write(t.detach().cpu().float().contiguous().numpy().tobytes())
+
+
+def read_result_bin(path: str):
+    """DHOUT001 result file -> (logits (B,nc,H,W) fp32, class map (B,H,W) uint8)"""
+    import struct
+    raw = open(path, "rb").read()
+    if raw[:8] != b"DHOUT001":
+        raise ValueError(f"{path} is not a DHOUT001 file")
+    B, nc, H, W = struct.unpack("<4i", raw[8:24])
+    n = B * nc * H * W
+    if len(raw) != 24 + 4 * n + B * H * W:
+        raise ValueError(f"{path}: {len(raw)} bytes for B={B} nc={nc} H={H} W={W}")
+    logits = torch.from_numpy(np.frombuffer(raw, dtype="<f4", count=n, offset=24).reshape(B, nc, H, W).copy())
+    cmap = torch.from_numpy(np.frombuffer(raw, dtype=np.uint8, count=B * H * W, offset=24 + 4 * n).reshape(B, H, W).copy())
+    return logits, cmap
