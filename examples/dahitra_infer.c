@@ -19,7 +19,9 @@
  *   dahitra_infer --weights w.bin --input x.bin --output y.bin [--variant V] [--nc N] [--flags F] [--repeat R]
  *   dahitra_infer --weights w.bin --synthetic BxHxW [--output y.bin] ...      uniform [-1, 1) images made on the host instead of a file
  * --repeat R times R further steps, each = H2D of the step's inputs from pinned memory + forward + D2H of the class map
- * (CUDA events on the launching stream), and prints pairs/s: the end-to-end rate of the C ABI without any Python.
+ * (CUDA events on the launching stream), and prints pairs/s: the end-to-end rate of the C ABI without any Python
+ * (one stream, so the copies do not overlap the forward; dahitra_b200/pipeline.py shows the overlapped form).
+ * --resident leaves the copies out of the timed steps (inputs stay in HBM): the forward alone.
  *
  * Build: __graft_entry__.build() (or:  gcc -std=c99 -O2 -Iinclude -I/usr/local/cuda/include examples/dahitra_infer.c
  *        -Ldahitra_b200 -ldahitra_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/dahitra_b200 -o examples/bin/dahitra_infer)
@@ -89,11 +91,12 @@ static dh_tensor* read_weights(const char* path, int* n_out) {
 
 int main(int argc, char** argv) {
   const char *wpath = NULL, *ipath = NULL, *opath = NULL, *synth = NULL;
-  int variant = DH_VARIANT_LEVIR, nc = 2, flags = DH_FLAGS_TF32X3, repeat = 0, prepare_only = 0;
+  int variant = DH_VARIANT_LEVIR, nc = 2, flags = DH_FLAGS_TF32X3, repeat = 0, prepare_only = 0, resident = 0;
   for (int i = 1; i < argc; ++i) {
     const char* a = argv[i];
     const char* v = i + 1 < argc ? argv[i + 1] : NULL;
     if (!strcmp(a, "--prepare-only")) prepare_only = 1;
+    else if (!strcmp(a, "--resident")) resident = 1;
     else if (!v) DIE("missing value after %s", a);
     else if (!strcmp(a, "--weights")) { wpath = v; ++i; }
     else if (!strcmp(a, "--input")) { ipath = v; ++i; }
@@ -222,17 +225,18 @@ int main(int argc, char** argv) {
     CU(cudaEventCreate(&e1));
     for (int it = -3; it < repeat; ++it) {                     /* 3 untimed steps first */
       if (it == 0) CU(cudaEventRecord(e0, stream));
-      CU(cudaMemcpyAsync(d_in, h_in, in_floats * 4, cudaMemcpyHostToDevice, stream));
+      if (!resident) CU(cudaMemcpyAsync(d_in, h_in, in_floats * 4, cudaMemcpyHostToDevice, stream));
       DH(dahitra_forward(table, DH_W_COUNT, d_in, d_in + x2_off, x_batch_stride, d_logits, d_map, d_ws, ws_bytes,
                          variant, B, H, W, nc, flags, stream));
-      CU(cudaMemcpyAsync(h_map, d_map, map_bytes, cudaMemcpyDeviceToHost, stream));
+      if (!resident) CU(cudaMemcpyAsync(h_map, d_map, map_bytes, cudaMemcpyDeviceToHost, stream));
     }
     CU(cudaEventRecord(e1, stream));
     CU(cudaEventSynchronize(e1));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, e0, e1));
-    printf("repeat=%d ms_per_step=%.4f pairs_per_s=%.1f h2d_bytes_per_step=%zu d2h_bytes_per_step=%zu (copies and forward serialised on one stream)\n",
-           repeat, ms / repeat, 1e3 * B * repeat / ms, in_floats * 4, map_bytes);
+    printf("repeat=%d ms_per_step=%.4f pairs_per_s=%.1f h2d_bytes_per_step=%zu d2h_bytes_per_step=%zu (%s)\n",
+           repeat, ms / repeat, 1e3 * B * repeat / ms, resident ? (size_t)0 : in_floats * 4, resident ? (size_t)0 : map_bytes,
+           resident ? "inputs resident in HBM, forward only" : "copies and forward serialised on one stream");
     CU(cudaEventDestroy(e0));
     CU(cudaEventDestroy(e1));
   }
