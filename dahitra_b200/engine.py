@@ -338,6 +338,26 @@ def prepare_weights_c(sd: dict, variant: int, out_nc: int):
     return flat, list(offs)
 
 
+F16_MAX = 65504.0
+
+
+def _filter_absmax(flat: torch.Tensor, offs: dict):
+    """largest |w| over the folded fp32 filters of a prepared buffer (the `_W` / `_DECODE` / `_SQ` slots: every convolution's
+    BatchNorm-folded weights) and the slot that holds it; NaN if any of them is not finite"""
+    import bisect
+    ends = sorted(offs.values()) + [flat.numel()]
+    worst, where = 0.0, None
+    for name, o in offs.items():
+        if name.endswith(("_W", "_DECODE", "_SQ")):
+            seg = flat[o:ends[bisect.bisect_right(ends, o)]]
+            m = float(seg.abs().max()) if seg.numel() else 0.0
+            if not m <= worst:                  # larger, or NaN
+                worst, where = m, name
+                if m != m:
+                    break
+    return worst, where
+
+
 class PreparedWeights:
     """Device copy of the prepared slots + the C pointer table handed to dahitra_forward.
 
@@ -363,6 +383,12 @@ class PreparedWeights:
         else:
             flat, off_list = prepare_weights_c(sd, variant, out_nc)
             offs = {n: o for n, o in zip(names, off_list) if o >= 0}
+        self.filter_absmax = _filter_absmax(flat, offs)     # (value, slot) over the folded fp32 filters, checked on the host
+        if not (self.filter_absmax[0] <= F16_MAX):            # also true for NaN
+            import warnings
+            warnings.warn(f"dahitra_b200: folded filter {self.filter_absmax[1]} has max |w| = {self.filter_absmax[0]:.4g}, outside the FP16 "
+                          "operand range of the default mode (values saturate at 65504); use net.set_mode('tf32x3_tf32main') or 'fp32' "
+                          "for this checkpoint (DESIGN.md, 'FP16 operand caveat')", RuntimeWarning, stacklevel=3)
         self.flat = flat.to(device)
         base = self.flat.data_ptr()
         self.table = (C.c_void_p * len(names))(*[(base + 4 * offs[n]) if n in offs else None for n in names])

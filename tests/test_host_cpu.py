@@ -435,3 +435,28 @@ def test_unused_parameter_names_are_exactly_the_ones_without_a_path_to_the_outpu
     assert no_grad == sorted(names)
     assert net.freeze_unused_parameters() == sorted(names)
     assert all(p.requires_grad != (n in set(names)) for n, p in net.named_parameters())
+
+
+def test_filters_outside_the_fp16_operand_range_are_reported(levir_template):
+    """the default mode's convolution operands are FP16 pairs (saturating at 65504): a checkpoint whose BatchNorm-folded filters
+    leave that range, or hold a NaN, is reported when its weights are prepared instead of silently losing accuracy"""
+    import warnings
+    from dahitra_b200.engine import PreparedWeights
+    from dahitra_b200 import synth
+    sd = synth.synth_state_dict(levir_template, seed=4, style="default")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        P = PreparedWeights(sd, 0, 2, "cpu")
+    assert not w and 0 < P.filter_absmax[0] < 65504 and P.filter_absmax[1].startswith("DH_W_")
+    big = dict(sd)
+    big["resnet.layer2.0.bn1.running_var"] = torch.full_like(sd["resnet.layer2.0.bn1.running_var"], 1e-30)   # fold scale 1/sqrt(eps) = 316
+    big["resnet.layer2.0.bn1.weight"] = sd["resnet.layer2.0.bn1.weight"] * 1e4
+    with pytest.warns(RuntimeWarning, match="DH_W_L2_0_C1_W.*outside the FP16 operand range"):
+        P = PreparedWeights(big, 0, 2, "cpu")
+    assert P.filter_absmax[0] > 65504
+    bad = dict(sd)
+    bad["classifier.weight"] = sd["classifier.weight"].clone()
+    bad["classifier.weight"][1, 3, 0, 2] = float("nan")
+    with pytest.warns(RuntimeWarning, match="DH_W_CLS_W"):
+        P = PreparedWeights(bad, 0, 2, "cpu")
+    assert P.filter_absmax[0] != P.filter_absmax[0]
