@@ -26,14 +26,49 @@ def _sources():
     return [os.path.join(_CSRC, s) for s in SOURCES if os.path.exists(os.path.join(_CSRC, s))]
 
 
+STAMP_PATH = LIB_PATH + ".stamp"
+
+
+def _deps():
+    deps = _sources() + [os.path.join(_HERE, "..", "include", "dahitra_b200.h")]
+    deps += [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith(".cuh")]
+    return [d for d in deps if os.path.exists(d)]
+
+
+def _source_hash() -> str:
+    """content hash of everything the library is compiled from (sources, headers, flags)"""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + [os.environ.get("DAHITRA_DEBUG_BUILD", "0")]).encode())
+    for d in _deps():
+        h.update(os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
+    """True when the in-tree library is missing or was built from other sources.  The build leaves a content hash of its inputs
+    next to the library (git-ignored like the library, travels with the tree): file times do not survive every copy of a tree.
+    Without a stamp (a library built before stamps existed) the file times decide, and a library they call fresh is stamped."""
     if not os.path.exists(LIB_PATH):
         return True
+    if os.path.exists(STAMP_PATH):
+        with open(STAMP_PATH) as f:
+            return f.read().strip() != _source_hash()
     t = os.path.getmtime(LIB_PATH)
-    deps = _sources() + [os.path.join(_CSRC, "common.cuh"),
-                         os.path.join(_HERE, "..", "include", "dahitra_b200.h")]
-    deps += [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    if any(os.path.getmtime(d) > t for d in _deps()):
+        return True
+    _write_stamp()
+    return False
+
+
+def _write_stamp():
+    try:
+        with open(STAMP_PATH + ".tmp", "w") as f:
+            f.write(_source_hash() + "\n")
+        os.replace(STAMP_PATH + ".tmp", STAMP_PATH)
+    except OSError:
+        pass                                    # read-only tree: the file times keep deciding
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -66,6 +101,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    _write_stamp()
     return LIB_PATH
 
 

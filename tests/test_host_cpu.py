@@ -460,3 +460,22 @@ def test_filters_outside_the_fp16_operand_range_are_reported(levir_template):
     with pytest.warns(RuntimeWarning, match="DH_W_CLS_W"):
         P = PreparedWeights(bad, 0, 2, "cpu")
     assert P.filter_absmax[0] != P.filter_absmax[0]
+
+
+def test_build_staleness_is_decided_by_content_not_file_times(lib, monkeypatch):
+    """the in-tree library travels between machines (file times do not survive every copy): `needs_build` compares a content hash
+    of the sources / headers / flags with the stamp the build left next to the library"""
+    from dahitra_b200 import _lib
+    assert not _lib.needs_build() and os.path.exists(_lib.STAMP_PATH)
+    src = os.path.join(_lib._CSRC, "aux.cu")
+    st = os.stat(src)
+    try:
+        os.utime(src, (st.st_atime, os.path.getmtime(_lib.LIB_PATH) + 1000))      # "newer" than the library, same bytes
+        assert not _lib.needs_build()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+    monkeypatch.setattr(_lib, "_source_hash", lambda: "0" * 64)                      # any edited source
+    assert _lib.needs_build()
+    monkeypatch.undo()
+    monkeypatch.setenv("DAHITRA_DEBUG_BUILD", "1")                                  # other flags = another library
+    assert _lib.needs_build()
