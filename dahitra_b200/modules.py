@@ -78,6 +78,28 @@ class Trunk(nn.Module):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
 
+    IMAGENET_FILE = "resnet18-5c106cde.pth"     # what model_urls['resnet18'] names, reference models/resnet.py:11-12
+
+    def load_imagenet_weights(self, path=None) -> bool:
+        """The reference builds its trunk as ``resnet18(pretrained=True)`` (models/networks.py:1096 -> models/resnet.py:228-233:
+        ``model.load_state_dict(load_state_dict_from_url(...))``).  ``init_weights`` then re-draws every Conv / BatchNorm affine
+        (networks.py:88-105), so what survives ``define_G`` are the ImageNet BatchNorm running statistics (and layer4 / fc, which no
+        forward reads).  This loads the same file, strictly, WITHOUT ever downloading: ``path``, else ``$DAHITRA_RESNET18_CKPT``, else
+        the torch hub cache the reference's own call would have filled.  Returns False (fresh statistics: mean 0, var 1) when no
+        file is there; a path that was asked for explicitly and does not exist is an error."""
+        import os
+        asked = path or os.environ.get("DAHITRA_RESNET18_CKPT")
+        if asked:
+            if not os.path.exists(asked):
+                raise FileNotFoundError(f"dahitra_b200: resnet18 checkpoint {asked} not found")
+            path = asked
+        else:
+            path = os.path.join(torch.hub.get_dir(), "checkpoints", self.IMAGENET_FILE)
+            if not os.path.exists(path):
+                return False
+        self.load_state_dict(torch.load(path, map_location="cpu"), strict=True)
+        return True
+
     @staticmethod
     def _stage(cin: int, cout: int, stride: int) -> nn.Sequential:
         proj = None

@@ -60,6 +60,7 @@ class BASE_Transformer_UNet(nn.Module):
                 "tokenizer/token_trans/with_decoder on, enc_depth=1, dim_head=decoder_dim_head=64, softmax decoder")
         # ---- ResNet_UNet part (reference networks.py:1086-1116) -------------------------------
         self.resnet = M.Trunk()
+        self.resnet.load_imagenet_weights()        # resnet18(pretrained=True) of the reference, from a local file only (no download)
         self.relu = nn.ReLU()
         self.upsamplex2 = nn.Upsample(scale_factor=2)
         self.upsamplex4 = nn.Upsample(scale_factor=4, mode='bilinear')

@@ -35,6 +35,7 @@ class BASE_Transformer_UNet(_LevirNet):
                 or not with_decoder or enc_depth != 1 or dim_head != 64 or decoder_dim_head != 64 or not decoder_softmax:
             raise NotImplementedError("dahitra_b200.xbd implements the configuration of xBD_code/train.py:44-45 only")
         self.resnet = M.Trunk()
+        self.resnet.load_imagenet_weights()        # resnet18(pretrained=True) of the reference, from a local file only (no download)
         self.relu = nn.ReLU()
         self.upsamplex2 = nn.Upsample(scale_factor=2)
         self.upsamplex4 = nn.Upsample(scale_factor=4, mode='bilinear')

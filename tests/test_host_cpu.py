@@ -479,3 +479,50 @@ def test_build_staleness_is_decided_by_content_not_file_times(lib, monkeypatch):
     monkeypatch.undo()
     monkeypatch.setenv("DAHITRA_DEBUG_BUILD", "1")                                  # other flags = another library
     assert _lib.needs_build()
+
+
+def test_imagenet_trunk_file_is_loaded_like_the_reference_does(tmp_path, monkeypatch):
+    """reference models/networks.py:1096: resnet18(pretrained=True), then init_weights re-draws Conv / BatchNorm affines
+    (:88-105) — the ImageNet BatchNorm running statistics survive define_G.  Here the same file is read from a local path only
+    (never downloaded); without it the statistics start at 0 / 1; a path asked for explicitly must exist."""
+    from dahitra_b200 import modules as M
+    from dahitra_b200.networks import define_G
+    from dahitra_b200.xbd import BASE_Transformer_UNet as X
+
+    class Args:
+        net_G = "newUNetTrans"
+    monkeypatch.delenv("DAHITRA_RESNET18_CKPT", raising=False)
+    monkeypatch.setattr(torch.hub, "get_dir", lambda: str(tmp_path / "hub"))          # an empty hub cache
+    torch.manual_seed(0)
+    plain = define_G(Args(), gpu_ids=[])
+    assert float(plain.resnet.bn1.running_mean.abs().sum()) == 0.0
+    # a file in the layout of resnet18-5c106cde.pth: torchvision keys, no num_batches_tracked entries
+    torch.manual_seed(99)
+    donor = M.Trunk()
+    for m in donor.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_()
+            m.running_var.uniform_(0.5, 2.0)
+    ckpt = {k: v for k, v in donor.state_dict().items() if not k.endswith("num_batches_tracked")}
+    path = str(tmp_path / "resnet18-5c106cde.pth")
+    torch.save(ckpt, path)
+    monkeypatch.setenv("DAHITRA_RESNET18_CKPT", path)
+    torch.manual_seed(0)
+    net = define_G(Args(), gpu_ids=[])
+    for k, v in net.resnet.state_dict().items():
+        if "running_" in k:
+            assert torch.equal(v, ckpt[k]), k                                          # survive init_weights
+        elif k.endswith("weight") and v.dim() == 4:
+            assert torch.equal(v, plain.resnet.state_dict()[k]) and not torch.equal(v, ckpt[k]), k   # re-drawn, same RNG stream as without the file
+    assert torch.equal(net.resnet.fc.weight, plain.resnet.fc.weight)                  # init_weights re-draws Linear too
+    # the xBD variant has no init_weights pass: the whole ImageNet trunk stays (xBD_code/zoo/model_transformer_encoding.py:195)
+    xnet = X(3, 5, with_pos="learned")
+    assert torch.equal(xnet.resnet.layer1[0].conv1.weight, ckpt["layer1.0.conv1.weight"])
+    # and the same through the hub cache the reference's own call fills
+    monkeypatch.delenv("DAHITRA_RESNET18_CKPT")
+    os.makedirs(tmp_path / "hub" / "checkpoints")
+    os.replace(path, tmp_path / "hub" / "checkpoints" / "resnet18-5c106cde.pth")
+    assert M.Trunk().load_imagenet_weights() is True
+    monkeypatch.setenv("DAHITRA_RESNET18_CKPT", str(tmp_path / "missing.pth"))
+    with pytest.raises(FileNotFoundError):
+        M.Trunk()  .load_imagenet_weights()

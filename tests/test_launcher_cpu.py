@@ -28,6 +28,45 @@ def test_reference_define_G_builds_the_native_class():
     assert "OK" in r.stdout
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_pretrained_trunk_path_equals_the_reference(tmp_path):
+    """The reference's define_G with its pretrained=True trunk left ON (models/networks.py:1096; load_state_dict_from_url served
+    from a local file instead of the network) against dahitra_b200's define_G reading the same file: all 425 tensors bit-identical
+    under the same seed, ImageNet BatchNorm running statistics included."""
+    code = (
+        "import sys, torch\n"
+        "from dahitra_b200 import modules as M\n"
+        "torch.manual_seed(99)\n"
+        "donor = M.Trunk()\n"
+        "for m in donor.modules():\n"
+        "    if isinstance(m, torch.nn.BatchNorm2d):\n"
+        "        m.running_mean.normal_(); m.running_var.uniform_(0.5, 2.0)\n"
+        "ckpt = {k: v for k, v in donor.state_dict().items() if not k.endswith('num_batches_tracked')}\n"
+        f"path = {str(tmp_path / 'resnet18-5c106cde.pth')!r}\n"
+        "torch.save(ckpt, path)\n"
+        "from dahitra_b200.launch import install\n"
+        f"nets = install({REF!r}, stub_missing=True, rebind=False)\n"      # the reference's own class, trunk NOT patched
+        "import models.resnet as R\n"
+        "R.load_state_dict_from_url = lambda url, progress=True: torch.load(path)\n"
+        "class A: net_G = 'newUNetTrans'\n"
+        "torch.manual_seed(0)\n"
+        "ref = nets.define_G(A(), gpu_ids=[])\n"
+        "assert type(ref).__module__ == 'models.networks', type(ref)\n"
+        "import os; os.environ['DAHITRA_RESNET18_CKPT'] = path\n"
+        "from dahitra_b200.networks import define_G\n"
+        "torch.manual_seed(0)\n"
+        "net = define_G(A(), gpu_ids=[])\n"
+        "a, b = ref.state_dict(), net.state_dict()\n"
+        "assert list(a) == list(b) and len(a) == 425\n"
+        "bad = [k for k in a if not torch.equal(a[k], b[k])]\n"
+        "assert not bad, bad[:5]\n"
+        "assert torch.equal(b['resnet.bn1.running_mean'], ckpt['bn1.running_mean'])\n"
+        "print('OK')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "OK" in r.stdout
+
+
 SHARD_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["DAHITRA_ROOT"])
