@@ -86,9 +86,11 @@ class Trunk(nn.Module):
         (networks.py:88-105), so what survives ``define_G`` are the ImageNet BatchNorm running statistics (and layer4 / fc, which no
         forward reads).  This loads the same file, strictly, WITHOUT ever downloading: ``path``, else ``$DAHITRA_RESNET18_CKPT``, else
         the torch hub cache the reference's own call would have filled.  Returns False (fresh statistics: mean 0, var 1) when no
-        file is there; a path that was asked for explicitly and does not exist is an error."""
+        file is there (or ``DAHITRA_RESNET18_CKPT=none``); a path that was asked for explicitly and does not exist is an error."""
         import os
         asked = path or os.environ.get("DAHITRA_RESNET18_CKPT")
+        if asked is not None and str(asked).lower() in ("", "0", "none", "off"):
+            return False                                     # DAHITRA_RESNET18_CKPT=none: never look (fresh statistics)
         if asked:
             if not os.path.exists(asked):
                 raise FileNotFoundError(f"dahitra_b200: resnet18 checkpoint {asked} not found")

@@ -9,6 +9,11 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# the golden fixtures were generated from the reference with its trunk download patched away (fresh BatchNorm statistics): keep a
+# resnet18 file that happens to sit in this machine's torch hub cache out of the seeded-init comparisons
+os.environ.setdefault("DAHITRA_RESNET18_CKPT", "none")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
