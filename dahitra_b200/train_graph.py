@@ -123,6 +123,9 @@ class GraphedTrainStep:
             raise ValueError(f"GraphedTrainStep.step: expected {len(self.static)} tensors, got {len(batch)}")
         for s, b in zip(self.static, batch):
             if b is not s:
+                if b.shape != s.shape:                                           # copy_ would broadcast (a last, smaller batch x N)
+                    raise ValueError(f"GraphedTrainStep.step: batch tensor of shape {tuple(b.shape)}, the step was built for "
+                                     f"{tuple(s.shape)}; run other shapes through the eager loop")
                 s.copy_(b, non_blocking=True)
         if self.use_graph:
             self.g_fb.replay()

@@ -526,3 +526,45 @@ def test_imagenet_trunk_file_is_loaded_like_the_reference_does(tmp_path, monkeyp
     monkeypatch.setenv("DAHITRA_RESNET18_CKPT", str(tmp_path / "missing.pth"))
     with pytest.raises(FileNotFoundError):
         M.Trunk()  .load_imagenet_weights()
+
+
+def test_graphed_train_step_eager_form_on_cpu_and_shape_guard():
+    """GraphedTrainStep with use_graph=False (what runs without a GPU): the flat-buffer step equals the plain loop bit for bit, unused
+    parameters are frozen, and a batch of another shape is refused instead of being broadcast into the static buffers"""
+    import copy
+    import torch.nn.functional as F
+    from dahitra_b200.train_graph import GraphedTrainStep
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Conv2d(3, 8, 3, padding=1)
+            self.bn = torch.nn.BatchNorm2d(8)
+            self.b = torch.nn.Conv2d(8, 2, 1)
+            self.unused = torch.nn.Linear(4, 4)
+
+        def forward(self, x):
+            return self.b(F.relu(self.bn(self.a(x))))
+
+    torch.manual_seed(3)
+    net = Net()
+    ref = copy.deepcopy(net).train()
+    mk = lambda: (torch.randn(4, 3, 8, 8), torch.randint(0, 2, (4, 8, 8)))          # noqa: E731
+    batches = [mk() for _ in range(4)]
+    mk_opt = lambda ps: torch.optim.AdamW(ps, lr=1e-2, weight_decay=0.01)            # noqa: E731
+    ts = GraphedTrainStep(net, F.cross_entropy, batches[0], mk_opt, use_graph=False)
+    assert not ts.use_graph and len(ts.frozen) == 2 and ts.flat.numel() == sum(p.numel() for p in ts.live)
+    opt = mk_opt([p for n, p in ref.named_parameters() if not n.startswith("unused")])
+    for b in batches[1:]:
+        l1 = float(ts.step(*b))
+        opt.zero_grad(set_to_none=True)
+        l2 = F.cross_entropy(ref(b[0]), b[1])
+        l2.backward()
+        opt.step()
+        assert l1 == float(l2.detach())
+    for (k, v), w in zip(net.state_dict().items(), ref.state_dict().values()):
+        assert torch.equal(v, w), k
+    with pytest.raises(ValueError, match="built for"):
+        ts.step(batches[0][0][:1], batches[0][1][:1])
+    with pytest.raises(ValueError, match="expected 2 tensors"):
+        ts.step(batches[0][0])
